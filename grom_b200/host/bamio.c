@@ -1,0 +1,582 @@
+/* bamio.c -- host read supply: BGZF/BAM/BAI reader -> packed SoA batch, and the
+ * batch -> BAM+BAI serialiser used by the test/bench tooling.
+ *
+ * Replaces the reference's read supply (reference src/GROM.c:82-324, 981-992)
+ * and its per-record field/aux extraction (src/GROM.c:5743-5824): all records of
+ * one contig are inflated block-parallel (OpenMP) and unpacked into the
+ * structure-of-arrays batch of include/grom_reads.h.  Independent of
+ * samtools/htslib; needs only zlib.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <ctype.h>
+#include <zlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "gromhost.h"
+
+static __thread char g_err[512];
+const char *gromhost_last_error(void) { return g_err; }
+static int fail(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return -1;
+}
+
+/* ------------------------------------------------------------------ BAM open */
+
+struct grom_bam {
+    char *path;
+    FILE *f;
+    int n_targets;
+    char **names;
+    int64_t *lens;
+    uint64_t first_voff;      /* virtual offset of the first alignment record */
+    int has_index;
+    uint64_t *tgt_beg;        /* per target: smallest chunk_beg in the .bai, UINT64_MAX if none */
+    uint64_t *tgt_end;        /* per target: largest chunk_end */
+};
+
+static inline uint32_t rd_u32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline int32_t  rd_i32(const uint8_t *p) { return (int32_t)rd_u32(p); }
+
+/* inflate one BGZF block located at file offset `off`; returns isize or -1; *clen = block size */
+static int bgzf_inflate_at(FILE *f, int64_t off, uint8_t *raw, uint8_t *dst, int *bsize_out)
+{
+    uint8_t hdr[18];
+    if (fseeko(f, off, SEEK_SET) != 0) return -1;
+    if (fread(hdr, 1, 18, f) != 18) return -1;
+    if (hdr[0] != 0x1f || hdr[1] != 0x8b || !(hdr[3] & 4)) return -1;
+    int xlen = hdr[10] | (hdr[11] << 8);
+    if (xlen != 6 || hdr[12] != 'B' || hdr[13] != 'C') return -1;
+    int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
+    int clen = bsize - 18;
+    if ((int)fread(raw, 1, clen, f) != clen) return -1;
+    uint32_t isize = rd_u32(raw + clen - 4);
+    z_stream s; memset(&s, 0, sizeof(s));
+    s.next_in = raw; s.avail_in = clen - 8; s.next_out = dst; s.avail_out = 65536;
+    if (inflateInit2(&s, -15) != Z_OK) return -1;
+    int rc = inflate(&s, Z_FINISH);
+    inflateEnd(&s);
+    if (rc != Z_STREAM_END || s.total_out != isize) return -1;
+    *bsize_out = bsize;
+    return (int)isize;
+}
+
+/* sequential reader used only for the header */
+typedef struct { FILE *f; int64_t addr, next; uint8_t raw[65536 + 64], blk[65536]; int len, off; } seqrd;
+static int seq_fill(seqrd *r)
+{
+    int bs;
+    r->addr = r->next;
+    int n = bgzf_inflate_at(r->f, r->addr, r->raw, r->blk, &bs);
+    if (n < 0) return -1;
+    r->next = r->addr + bs; r->len = n; r->off = 0;
+    return 0;
+}
+static int seq_read(seqrd *r, void *dst, int n)
+{
+    uint8_t *d = (uint8_t *)dst; int got = 0;
+    while (got < n) {
+        if (r->off >= r->len) { if (seq_fill(r) < 0) return got; if (r->len == 0) continue; }
+        int k = r->len - r->off; if (k > n - got) k = n - got;
+        memcpy(d + got, r->blk + r->off, k); r->off += k; got += k;
+    }
+    return got;
+}
+
+int gromhost_bam_open(const char *path, grom_bam **out)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail("Could not open %s", path);
+    seqrd *r = (seqrd *)calloc(1, sizeof(seqrd));
+    r->f = f;
+    char magic[4]; int32_t l_text, n_ref;
+    if (seq_read(r, magic, 4) != 4 || memcmp(magic, "BAM\1", 4)) { free(r); fclose(f); return fail("%s: not a BAM file", path); }
+    seq_read(r, &l_text, 4);
+    char *text = (char *)malloc((size_t)l_text + 1);
+    seq_read(r, text, l_text); free(text);
+    seq_read(r, &n_ref, 4);
+    grom_bam *b = (grom_bam *)calloc(1, sizeof(*b));
+    b->path = strdup(path); b->f = f; b->n_targets = n_ref;
+    b->names = (char **)calloc(n_ref > 0 ? n_ref : 1, sizeof(char *));
+    b->lens = (int64_t *)calloc(n_ref > 0 ? n_ref : 1, sizeof(int64_t));
+    for (int i = 0; i < n_ref; i++) {
+        int32_t l_name, l_ref;
+        seq_read(r, &l_name, 4);
+        b->names[i] = (char *)calloc((size_t)l_name + 1, 1);
+        seq_read(r, b->names[i], l_name);
+        seq_read(r, &l_ref, 4);
+        b->lens[i] = l_ref;
+    }
+    if (r->off >= r->len) { b->first_voff = (uint64_t)r->next << 16; }
+    else b->first_voff = ((uint64_t)r->addr << 16) | (uint64_t)r->off;
+    free(r);
+
+    /* optional index: keep only [min chunk_beg, max chunk_end] per target */
+    char iname[4096]; snprintf(iname, sizeof(iname), "%s.bai", path);
+    FILE *fi = fopen(iname, "rb");
+    if (fi) {
+        char m[4]; int32_t nr = 0;
+        if (fread(m, 1, 4, fi) == 4 && !memcmp(m, "BAI\1", 4) && fread(&nr, 4, 1, fi) == 1 && nr == n_ref) {
+            b->tgt_beg = (uint64_t *)malloc(sizeof(uint64_t) * (n_ref > 0 ? n_ref : 1));
+            b->tgt_end = (uint64_t *)malloc(sizeof(uint64_t) * (n_ref > 0 ? n_ref : 1));
+            int ok = 1;
+            for (int i = 0; i < n_ref && ok; i++) {
+                int32_t n_bin, n_intv;
+                b->tgt_beg[i] = UINT64_MAX; b->tgt_end[i] = 0;
+                if (fread(&n_bin, 4, 1, fi) != 1) { ok = 0; break; }
+                for (int j = 0; j < n_bin && ok; j++) {
+                    uint32_t bin; int32_t n_chunk;
+                    if (fread(&bin, 4, 1, fi) != 1 || fread(&n_chunk, 4, 1, fi) != 1) { ok = 0; break; }
+                    for (int k = 0; k < n_chunk; k++) {
+                        uint64_t be[2];
+                        if (fread(be, 8, 2, fi) != 2) { ok = 0; break; }
+                        if (bin == 37450) continue;
+                        if (be[0] < b->tgt_beg[i]) b->tgt_beg[i] = be[0];
+                        if (be[1] > b->tgt_end[i]) b->tgt_end[i] = be[1];
+                    }
+                }
+                if (!ok || fread(&n_intv, 4, 1, fi) != 1) { ok = 0; break; }
+                fseeko(fi, (off_t)n_intv * 8, SEEK_CUR);
+            }
+            b->has_index = ok;
+        }
+        fclose(fi);
+    }
+    *out = b;
+    return 0;
+}
+
+void gromhost_bam_close(grom_bam *b)
+{
+    if (!b) return;
+    for (int i = 0; i < b->n_targets; i++) free(b->names[i]);
+    free(b->names); free(b->lens); free(b->tgt_beg); free(b->tgt_end); free(b->path);
+    if (b->f) fclose(b->f);
+    free(b);
+}
+int gromhost_bam_n_targets(const grom_bam *b) { return b->n_targets; }
+const char *gromhost_bam_target_name(const grom_bam *b, int tid) { return (tid >= 0 && tid < b->n_targets) ? b->names[tid] : NULL; }
+int64_t gromhost_bam_target_len(const grom_bam *b, int tid) { return (tid >= 0 && tid < b->n_targets) ? b->lens[tid] : -1; }
+int gromhost_bam_has_index(const grom_bam *b) { return b->has_index; }
+
+/* ------------------------------------------------------------------ batch */
+
+struct grom_batch {
+    grom_read_batch v;
+    int64_t cap_reads, cap_cigar, cap_slots, cap_names;
+    int32_t *pos, *mpos, *tlen, *mtid, *l_qseq, *sa_pos, *sa_start_adj, *sa_end_adj, *sa_end_adj_indel;
+    uint16_t *flag, *n_cigar; int16_t *sa_mapq;
+    uint8_t *mapq, *qname_len, *sa_strand, *sa_same_chr;
+    uint64_t *qname_hash, *cigar_off, *base_off, *qname_off;
+    uint32_t *cigar; uint8_t *seq4, *qual; char *qname_pool;
+};
+
+void gromhost_batch_view(const grom_batch *bt, grom_read_batch *view) { *view = bt->v; }
+
+void gromhost_batch_free(grom_batch *t)
+{
+    if (!t) return;
+    free(t->pos); free(t->mpos); free(t->tlen); free(t->mtid); free(t->l_qseq); free(t->sa_pos);
+    free(t->sa_start_adj); free(t->sa_end_adj); free(t->sa_end_adj_indel); free(t->flag); free(t->n_cigar);
+    free(t->sa_mapq); free(t->mapq); free(t->qname_len); free(t->sa_strand); free(t->sa_same_chr);
+    free(t->qname_hash); free(t->cigar_off); free(t->base_off); free(t->qname_off); free(t->cigar);
+    free(t->seq4); free(t->qual); free(t->qname_pool); free(t);
+}
+
+static void batch_publish(grom_batch *t)
+{
+    grom_read_batch *v = &t->v;
+    v->pos = t->pos; v->mpos = t->mpos; v->tlen = t->tlen; v->mtid = t->mtid; v->l_qseq = t->l_qseq;
+    v->flag = t->flag; v->n_cigar = t->n_cigar; v->mapq = t->mapq; v->qname_len = t->qname_len;
+    v->qname_hash = t->qname_hash; v->cigar_off = t->cigar_off; v->base_off = t->base_off;
+    v->cigar = t->cigar; v->seq4 = t->seq4; v->qual = t->qual; v->sa_pos = t->sa_pos;
+    v->sa_start_adj = t->sa_start_adj; v->sa_end_adj = t->sa_end_adj; v->sa_end_adj_indel = t->sa_end_adj_indel;
+    v->sa_strand = t->sa_strand; v->sa_mapq = t->sa_mapq; v->sa_same_chr = t->sa_same_chr;
+    v->qname_off = t->qname_off; v->qname_pool = t->qname_pool;
+}
+
+/* ---- aux: first XP else SA entry (reference src/GROM.c:5763-5824, 6686-6733) ---- */
+
+static const uint8_t *aux_find(const uint8_t *s, const uint8_t *e, char a, char b)
+{
+    while (s + 3 <= e) {
+        int hit = (s[0] == (uint8_t)a && s[1] == (uint8_t)b);
+        uint8_t t = s[2];
+        const uint8_t *v = s + 2;
+        s += 3;
+        if (hit) return v;
+        switch (t) {
+        case 'A': case 'c': case 'C': s += 1; break;
+        case 's': case 'S': s += 2; break;
+        case 'i': case 'I': case 'f': s += 4; break;
+        case 'd': s += 8; break;
+        case 'Z': case 'H': while (s < e && *s) s++; s++; break;
+        case 'B': { if (s + 5 > e) return NULL; uint8_t st = s[0]; uint32_t n = rd_u32(s + 1);
+                    int w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                    s += 5 + (size_t)n * w; break; }
+        default: return NULL;
+        }
+    }
+    return NULL;
+}
+
+/* split on ',' like strtok (skips empty fields); returns number of tokens, up to 5 */
+static int split_commas(char *s, char *tok[5])
+{
+    int n = 0;
+    while (n < 5) {
+        while (*s == ',') s++;
+        if (!*s) break;
+        tok[n++] = s;
+        while (*s && *s != ',') s++;
+        if (*s) *s++ = 0;
+    }
+    return n;
+}
+
+static void parse_sa(const uint8_t *aux, int l_aux, const char *target_name,
+                     int32_t *sa_pos, uint8_t *strand, int16_t *mq, uint8_t *same,
+                     int32_t *start_adj, int32_t *end_adj, int32_t *end_adj_indel)
+{
+    *sa_pos = -1; *strand = 0; *mq = -1; *same = 0; *start_adj = *end_adj = *end_adj_indel = 0;
+    if (!(l_aux > 0 && l_aux < 100)) return;
+    const uint8_t *e = aux + l_aux;
+    int is_xp = 1;
+    const uint8_t *v = aux_find(aux, e, 'X', 'P');
+    if (!v) { is_xp = 0; v = aux_find(aux, e, 'S', 'A'); }
+    if (!v) return;
+    char buf[128];
+    const uint8_t *src = (v[0] == 'Z') ? v + 1 : v;
+    int n = 0;
+    while (src + n < e && src[n] && n < 127) { buf[n] = (char)src[n]; n++; }
+    buf[n] = 0;
+    char *tok[5];
+    int nt = split_commas(buf, tok);
+    const char *cig = NULL;
+    if (is_xp) {           /* chr,[+-]pos,cigar,mq */
+        if (nt < 4) return;
+        *strand = (tok[1][0] == '+') ? 0 : 1;
+        *sa_pos = atoi(tok[1] + 1);
+        cig = tok[2]; *mq = (int16_t)atoi(tok[3]);
+    } else {               /* chr,pos,strand,cigar,mq,... */
+        if (nt < 5) return;
+        *sa_pos = atoi(tok[1]);
+        *strand = (tok[2][0] == '+') ? 0 : 1;
+        cig = tok[3]; *mq = (int16_t)atoi(tok[4]);
+    }
+    *same = (strncmp(target_name, tok[0], strlen(target_name)) == 0) ? 1 : 0;
+    /* aux CIGAR: digits accumulate until an alphabetic op letter; non-alnum characters
+     * are skipped without resetting the digit buffer (src/GROM.c:6693-6708) */
+    char digits[32]; int nd = 0; int first = 1; char last_t = 0; long last_l = 0;
+    for (const char *c = cig; *c; c++) {
+        if (isdigit((unsigned char)*c)) { if (nd < 31) digits[nd++] = *c; }
+        else if (isalpha((unsigned char)*c)) {
+            digits[nd] = 0; long len = strtol(digits, NULL, 10); nd = 0;
+            if (first) { if (*c == 'S') *start_adj = (int32_t)len; first = 0; }
+            if (*c == 'I') *end_adj_indel += (int32_t)len;
+            else if (*c == 'D') *end_adj_indel -= (int32_t)len;
+            last_t = *c; last_l = len;
+        }
+    }
+    if (last_t == 'S') *end_adj = (int32_t)last_l;
+}
+
+/* ------------------------------------------------------------------ read one target */
+
+typedef struct { int64_t off; int bsize; int isize; int64_t uoff; } blkinfo;
+
+int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out)
+{
+    if (tid < 0 || tid >= b->n_targets) return fail("target id %d out of range", tid);
+    uint64_t vbeg = b->first_voff, vend = UINT64_MAX;
+    if (b->has_index) {
+        if (b->tgt_beg[tid] == UINT64_MAX) { vbeg = vend = 0; }
+        else { vbeg = b->tgt_beg[tid]; vend = b->tgt_end[tid]; }
+    }
+    grom_batch *t = (grom_batch *)calloc(1, sizeof(*t));
+    t->v.tid = tid;
+    /* 1. enumerate the compressed blocks in [vbeg, vend] */
+    blkinfo *blk = NULL; int64_t nblk = 0, capblk = 0;
+    if (vend != 0) {
+        int64_t off = (int64_t)(vbeg >> 16), endoff = (vend == UINT64_MAX) ? INT64_MAX : (int64_t)(vend >> 16);
+        uint8_t hdr[18];
+        while (off <= endoff) {
+            if (fseeko(b->f, off, SEEK_SET) != 0) break;
+            if (fread(hdr, 1, 18, b->f) != 18) break;
+            if (hdr[0] != 0x1f || hdr[1] != 0x8b) { free(blk); free(t); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
+            int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
+            uint8_t tail[4];
+            if (fseeko(b->f, off + bsize - 4, SEEK_SET) != 0 || fread(tail, 1, 4, b->f) != 4) break;
+            if (nblk == capblk) { capblk = capblk ? capblk * 2 : 1024; blk = (blkinfo *)realloc(blk, capblk * sizeof(blkinfo)); }
+            blk[nblk].off = off; blk[nblk].bsize = bsize; blk[nblk].isize = (int)rd_u32(tail); nblk++;
+            off += bsize;
+        }
+    }
+    int64_t utotal = 0;
+    for (int64_t i = 0; i < nblk; i++) { blk[i].uoff = utotal; utotal += blk[i].isize; }
+    uint8_t *u = (uint8_t *)malloc((size_t)utotal + 64);
+    /* 2. inflate in parallel (each thread its own FILE*) */
+    int bad = 0;
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+    #pragma omp parallel num_threads(n_threads)
+    {
+        FILE *f = fopen(b->path, "rb");
+        uint8_t *raw = (uint8_t *)malloc(65536 + 64), *tmp = (uint8_t *)malloc(65536);
+        #pragma omp for schedule(dynamic, 16)
+        for (int64_t i = 0; i < nblk; i++) {
+            int bs; int n = f ? bgzf_inflate_at(f, blk[i].off, raw, tmp, &bs) : -1;
+            if (n != blk[i].isize) { bad = 1; continue; }
+            memcpy(u + blk[i].uoff, tmp, n);
+        }
+        free(raw); free(tmp); if (f) fclose(f);
+    }
+    if (bad) { free(blk); free(u); free(t); return fail("%s: BGZF inflate failed", b->path); }
+    /* 3. first pass over records: count */
+    int64_t p = (nblk > 0) ? (int64_t)(vbeg & 0xffff) : 0;
+    int64_t n_reads = 0, n_cig = 0, n_slots = 0, n_name = 0, p0 = p;
+    int started = 0;
+    while (p + 36 <= utotal) {
+        int32_t bl = rd_i32(u + p);
+        if (bl < 32 || p + 4 + bl > utotal) break;
+        int32_t rtid = rd_i32(u + p + 4);
+        if (rtid == tid) {
+            if (!started) { started = 1; p0 = p; }
+            uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16); int32_t lq = rd_i32(u + p + 20);
+            n_reads++; n_cig += fnc & 0xffff; n_slots += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN;
+            n_name += bmq & 0xff;
+        } else if (started || rtid > tid || rtid < 0) {
+            break;      /* coordinate-sorted: past the target (or into the unplaced tail) */
+        }
+        p += 4 + bl;
+    }
+    /* 4. allocate */
+    size_t nr = (size_t)(n_reads > 0 ? n_reads : 1);
+#define AL(ptr, type, cnt) t->ptr = (type *)calloc((cnt), sizeof(type))
+    AL(pos, int32_t, nr); AL(mpos, int32_t, nr); AL(tlen, int32_t, nr); AL(mtid, int32_t, nr); AL(l_qseq, int32_t, nr);
+    AL(sa_pos, int32_t, nr); AL(sa_start_adj, int32_t, nr); AL(sa_end_adj, int32_t, nr); AL(sa_end_adj_indel, int32_t, nr);
+    AL(flag, uint16_t, nr); AL(n_cigar, uint16_t, nr); AL(sa_mapq, int16_t, nr);
+    AL(mapq, uint8_t, nr); AL(qname_len, uint8_t, nr); AL(sa_strand, uint8_t, nr); AL(sa_same_chr, uint8_t, nr);
+    AL(qname_hash, uint64_t, nr); AL(cigar_off, uint64_t, nr); AL(base_off, uint64_t, nr);
+    AL(cigar, uint32_t, (size_t)(n_cig > 0 ? n_cig : 1));
+    AL(seq4, uint8_t, (size_t)(n_slots / 2 + 16)); AL(qual, uint8_t, (size_t)(n_slots + 16));
+    if (keep_names) { AL(qname_off, uint64_t, nr + 1); AL(qname_pool, char, (size_t)(n_name + 1)); }
+#undef AL
+    /* 5. offsets (sequential, cheap), then fill (parallel over reads) */
+    int64_t *recoff = (int64_t *)malloc(sizeof(int64_t) * nr);
+    {
+        int64_t q = p0, ci = 0, sl = 0, nm = 0;
+        for (int64_t i = 0; i < n_reads; i++) {
+            int32_t bl = rd_i32(u + q);
+            uint32_t bmq = rd_u32(u + q + 12), fnc = rd_u32(u + q + 16); int32_t lq = rd_i32(u + q + 20);
+            recoff[i] = q; t->cigar_off[i] = (uint64_t)ci; t->base_off[i] = (uint64_t)sl;
+            if (keep_names) t->qname_off[i] = (uint64_t)nm;
+            ci += fnc & 0xffff; sl += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN; nm += bmq & 0xff;
+            q += 4 + bl;
+        }
+        if (keep_names) t->qname_off[n_reads] = (uint64_t)nm;
+    }
+    const char *tname = b->names[tid];
+    #pragma omp parallel for schedule(static) num_threads(n_threads)
+    for (int64_t i = 0; i < n_reads; i++) {
+        const uint8_t *r = u + recoff[i];
+        int32_t bl = rd_i32(r);
+        uint32_t bmq = rd_u32(r + 12), fnc = rd_u32(r + 16);
+        int l_qname = bmq & 0xff, ncig = fnc & 0xffff; int32_t lq = rd_i32(r + 20);
+        t->pos[i] = rd_i32(r + 8); t->mapq[i] = (bmq >> 8) & 0xff; t->flag[i] = (uint16_t)(fnc >> 16); t->n_cigar[i] = (uint16_t)ncig;
+        t->l_qseq[i] = lq; t->mtid[i] = rd_i32(r + 24); t->mpos[i] = rd_i32(r + 28); t->tlen[i] = rd_i32(r + 32);
+        const uint8_t *d = r + 36;
+        int nl = (int)strnlen((const char *)d, l_qname);
+        t->qname_len[i] = (uint8_t)(nl > 255 ? 255 : nl);
+        t->qname_hash[i] = grom_qname_hash((const char *)d, nl);
+        if (keep_names) memcpy(t->qname_pool + t->qname_off[i], d, l_qname);
+        memcpy(t->cigar + t->cigar_off[i], d + l_qname, (size_t)ncig * 4);
+        const uint8_t *sq = d + l_qname + ncig * 4;
+        memcpy(t->seq4 + t->base_off[i] / 2, sq, (size_t)(lq + 1) / 2);
+        memcpy(t->qual + t->base_off[i], sq + (lq + 1) / 2, (size_t)lq);
+        const uint8_t *aux = sq + (lq + 1) / 2 + lq;
+        int l_aux = (int)((r + 4 + bl) - aux);
+        parse_sa(aux, l_aux, tname, &t->sa_pos[i], &t->sa_strand[i], &t->sa_mapq[i], &t->sa_same_chr[i],
+                 &t->sa_start_adj[i], &t->sa_end_adj[i], &t->sa_end_adj_indel[i]);
+    }
+    free(recoff); free(u); free(blk);
+    t->v.n_reads = n_reads; t->v.n_cigar_total = n_cig; t->v.n_base_slots = n_slots;
+    batch_publish(t);
+    *out = t;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ writer (tooling) */
+
+typedef struct {
+    FILE *f; uint8_t buf[0xff00]; int fill; int64_t faddr; int level; uint8_t *cbuf;
+} bgzf_w;
+
+static int bgzf_flush(bgzf_w *w)
+{
+    z_stream s; memset(&s, 0, sizeof(s));
+    if (deflateInit2(&s, w->level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return -1;
+    s.next_in = w->buf; s.avail_in = w->fill; s.next_out = w->cbuf + 18; s.avail_out = 65536 - 18 - 8;
+    int rc = deflate(&s, Z_FINISH);
+    if (rc != Z_STREAM_END) { deflateEnd(&s); return -1; }
+    int clen = (int)s.total_out; deflateEnd(&s);
+    int bsize = clen + 26;
+    static const uint8_t h[12] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0 };
+    memcpy(w->cbuf, h, 12); w->cbuf[12] = 'B'; w->cbuf[13] = 'C'; w->cbuf[14] = 2; w->cbuf[15] = 0;
+    w->cbuf[16] = (uint8_t)((bsize - 1) & 0xff); w->cbuf[17] = (uint8_t)((bsize - 1) >> 8);
+    uint32_t crc = (uint32_t)crc32(crc32(0L, NULL, 0), w->buf, w->fill);
+    uint8_t *t = w->cbuf + 18 + clen;
+    t[0] = crc & 0xff; t[1] = (crc >> 8) & 0xff; t[2] = (crc >> 16) & 0xff; t[3] = (crc >> 24) & 0xff;
+    uint32_t is = (uint32_t)w->fill;
+    t[4] = is & 0xff; t[5] = (is >> 8) & 0xff; t[6] = (is >> 16) & 0xff; t[7] = (is >> 24) & 0xff;
+    if ((int)fwrite(w->cbuf, 1, bsize, w->f) != bsize) return -1;
+    w->faddr += bsize; w->fill = 0;
+    return 0;
+}
+static int bgzf_write(bgzf_w *w, const void *src, int n)
+{
+    const uint8_t *s = (const uint8_t *)src;
+    while (n > 0) {
+        int k = (int)sizeof(w->buf) - w->fill; if (k > n) k = n;
+        memcpy(w->buf + w->fill, s, k); w->fill += k; s += k; n -= k;
+        if (w->fill == (int)sizeof(w->buf) && bgzf_flush(w) < 0) return -1;
+    }
+    return 0;
+}
+static inline uint64_t bgzf_tell(const bgzf_w *w) { return ((uint64_t)w->faddr << 16) | (uint64_t)w->fill; }
+
+static int reg2bin(int64_t beg, int64_t end)
+{
+    --end;
+    if (beg >> 14 == end >> 14) return (int)(((1 << 15) - 1) / 7 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (int)(((1 << 12) - 1) / 7 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (int)(((1 << 9) - 1) / 7 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (int)(((1 << 6) - 1) / 7 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (int)(((1 << 3) - 1) / 7 + (beg >> 26));
+    return 0;
+}
+
+typedef struct { uint64_t *be; int n, cap; } chunklist;
+#define BAI_NBIN 37450
+
+int gromhost_bam_write(const char *path, int n_targets, const char *const *names, const int64_t *lens,
+                       int n_batches, const grom_read_batch *batches,
+                       const uint64_t *const *aux_off, const uint8_t *const *aux_pool, int level)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail("cannot create %s", path);
+    bgzf_w *w = (bgzf_w *)calloc(1, sizeof(*w));
+    w->f = f; w->level = level <= 0 ? 1 : level; w->cbuf = (uint8_t *)malloc(65536 + 64);
+    /* header */
+    char *text = (char *)malloc(64 + (size_t)n_targets * 128); int lt = 0;
+    lt += sprintf(text + lt, "@HD\tVN:1.5\tSO:coordinate\n");
+    for (int i = 0; i < n_targets; i++) lt += sprintf(text + lt, "@SQ\tSN:%s\tLN:%lld\n", names[i], (long long)lens[i]);
+    int32_t v = lt;
+    bgzf_write(w, "BAM\1", 4); bgzf_write(w, &v, 4); bgzf_write(w, text, lt); free(text);
+    v = n_targets; bgzf_write(w, &v, 4);
+    for (int i = 0; i < n_targets; i++) {
+        v = (int32_t)strlen(names[i]) + 1; bgzf_write(w, &v, 4); bgzf_write(w, names[i], v);
+        v = (int32_t)lens[i]; bgzf_write(w, &v, 4);
+    }
+    bgzf_flush(w);
+
+    char iname[4096]; snprintf(iname, sizeof(iname), "%s.bai", path);
+    FILE *fi = fopen(iname, "wb");
+    if (!fi) { fclose(f); return fail("cannot create %s", iname); }
+    int32_t nt = n_targets; fwrite("BAI\1", 1, 4, fi); fwrite(&nt, 4, 1, fi);
+
+    int bi = 0; int rc = 0;
+    uint8_t *rec = (uint8_t *)malloc(1 << 20);
+    for (int tid = 0; tid < n_targets && rc == 0; tid++) {
+        const grom_read_batch *bt = NULL;
+        if (bi < n_batches && batches[bi].tid == tid) bt = &batches[bi];
+        if (!bt || bt->n_reads == 0) {
+            int32_t z = 0; fwrite(&z, 4, 1, fi); fwrite(&z, 4, 1, fi);
+            if (bt) bi++;
+            continue;
+        }
+        if (!bt->qname_off || !bt->qname_pool) { rc = fail("batch for target %d carries no read names", tid); break; }
+        chunklist *bins = (chunklist *)calloc(BAI_NBIN + 1, sizeof(chunklist));
+        int64_t nlin = (lens[tid] >> 14) + 2;
+        uint64_t *lin = (uint64_t *)calloc((size_t)nlin, 8);
+        int cur_bin = -1; uint64_t chunk_beg = 0;
+        uint64_t ref_beg = bgzf_tell(w), n_mapped = 0, n_unmapped = 0;
+        for (int64_t i = 0; i < bt->n_reads && rc == 0; i++) {
+            int nc = bt->n_cigar[i]; int32_t lq = bt->l_qseq[i];
+            int64_t qo = (int64_t)bt->qname_off[i]; int l_qname = (int)(bt->qname_off[i + 1] - bt->qname_off[i]);
+            const uint32_t *cg = bt->cigar + bt->cigar_off[i];
+            int64_t end = bt->pos[i];
+            if (!(bt->flag[i] & 4)) for (int k = 0; k < nc; k++) { int op = cg[k] & 15; if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += cg[k] >> 4; }
+            if (end <= bt->pos[i]) end = (int64_t)bt->pos[i] + 1;
+            int bin = reg2bin(bt->pos[i], end);
+            int l_aux = (aux_off && aux_off[bi]) ? (int)(aux_off[bi][i + 1] - aux_off[bi][i]) : 0;
+            int32_t bl = 32 + l_qname + nc * 4 + (lq + 1) / 2 + lq + l_aux;
+            if (bl + 4 > (1 << 20)) { rc = fail("record too large"); break; }
+            uint8_t *q = rec;
+            int32_t x[9];
+            x[0] = bl; x[1] = tid; x[2] = bt->pos[i];
+            x[3] = (int32_t)(((uint32_t)bin << 16) | ((uint32_t)bt->mapq[i] << 8) | (uint32_t)l_qname);
+            x[4] = (int32_t)(((uint32_t)bt->flag[i] << 16) | (uint32_t)nc);
+            x[5] = lq; x[6] = bt->mtid[i]; x[7] = bt->mpos[i]; x[8] = bt->tlen[i];
+            memcpy(q, x, 36); q += 36;
+            memcpy(q, bt->qname_pool + qo, l_qname); q += l_qname;
+            memcpy(q, cg, (size_t)nc * 4); q += nc * 4;
+            memcpy(q, bt->seq4 + bt->base_off[i] / 2, (size_t)(lq + 1) / 2);
+            if (lq & 1) q[(lq + 1) / 2 - 1] &= 0xf0;
+            q += (lq + 1) / 2;
+            memcpy(q, bt->qual + bt->base_off[i], (size_t)lq); q += lq;
+            if (l_aux) { memcpy(q, aux_pool[bi] + aux_off[bi][i], l_aux); q += l_aux; }
+            uint64_t vo = bgzf_tell(w);
+            if (w->fill == (int)sizeof(w->buf)) vo = ((uint64_t)w->faddr << 16);
+            if (bin != cur_bin) {
+                if (cur_bin >= 0) {
+                    chunklist *c = &bins[cur_bin];
+                    if (c->n == c->cap) { c->cap = c->cap ? c->cap * 2 : 4; c->be = (uint64_t *)realloc(c->be, (size_t)c->cap * 16); }
+                    c->be[2 * c->n] = chunk_beg; c->be[2 * c->n + 1] = vo; c->n++;
+                }
+                cur_bin = bin; chunk_beg = vo;
+            }
+            for (int64_t wdw = bt->pos[i] >> 14; wdw <= (end - 1) >> 14 && wdw < nlin; wdw++)
+                if (lin[wdw] == 0 || vo < lin[wdw]) lin[wdw] = vo;
+            if (bt->flag[i] & 4) n_unmapped++; else n_mapped++;
+            if (bgzf_write(w, rec, 4 + bl) < 0) rc = fail("write failed");
+        }
+        uint64_t ref_end = bgzf_tell(w);
+        if (cur_bin >= 0) {
+            chunklist *c = &bins[cur_bin];
+            if (c->n == c->cap) { c->cap = c->cap ? c->cap * 2 : 4; c->be = (uint64_t *)realloc(c->be, (size_t)c->cap * 16); }
+            c->be[2 * c->n] = chunk_beg; c->be[2 * c->n + 1] = ref_end; c->n++;
+        }
+        int32_t n_bin = 1;
+        for (int k = 0; k < BAI_NBIN; k++) if (bins[k].n) n_bin++;
+        fwrite(&n_bin, 4, 1, fi);
+        for (int k = 0; k < BAI_NBIN; k++) if (bins[k].n) {
+            uint32_t bk = (uint32_t)k; int32_t ncnk = bins[k].n;
+            fwrite(&bk, 4, 1, fi); fwrite(&ncnk, 4, 1, fi); fwrite(bins[k].be, 16, (size_t)ncnk, fi);
+            free(bins[k].be);
+        }
+        { uint32_t bk = BAI_NBIN; int32_t two = 2; uint64_t m[4] = { ref_beg, ref_end, n_mapped, n_unmapped };
+          fwrite(&bk, 4, 1, fi); fwrite(&two, 4, 1, fi); fwrite(m, 8, 4, fi); }
+        int64_t last = 0;
+        for (int64_t k = 0; k < nlin; k++) if (lin[k]) last = k + 1;
+        for (int64_t k = 1; k < last; k++) if (lin[k] == 0) lin[k] = lin[k - 1];
+        int32_t n_intv = (int32_t)last;
+        fwrite(&n_intv, 4, 1, fi); fwrite(lin, 8, (size_t)last, fi);
+        free(lin); free(bins);
+        bi++;
+    }
+    free(rec);
+    if (w->fill) bgzf_flush(w);
+    static const uint8_t eof[28] = { 0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 0x42, 0x43, 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    fwrite(eof, 1, 28, f);
+    fclose(f); fclose(fi); free(w->cbuf); free(w);
+    return rc;
+}

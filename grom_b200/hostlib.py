@@ -1,0 +1,99 @@
+"""ctypes binding of libgromhost.so (include/gromhost.h): BAM -> packed batch, batch -> BAM+BAI."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Sequence
+
+import numpy as np
+
+from .reads import CReadBatch, ReadBatch, batch_from_c
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libgromhost.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(path)
+        L.gromhost_last_error.restype = C.c_char_p
+        L.gromhost_bam_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.gromhost_bam_close.argtypes = [C.c_void_p]
+        L.gromhost_bam_n_targets.argtypes = [C.c_void_p]
+        L.gromhost_bam_target_name.argtypes = [C.c_void_p, C.c_int]
+        L.gromhost_bam_target_name.restype = C.c_char_p
+        L.gromhost_bam_target_len.argtypes = [C.c_void_p, C.c_int]
+        L.gromhost_bam_target_len.restype = C.c_int64
+        L.gromhost_bam_has_index.argtypes = [C.c_void_p]
+        L.gromhost_bam_read_target.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.gromhost_batch_view.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
+        L.gromhost_batch_free.argtypes = [C.c_void_p]
+        L.gromhost_bam_write.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int,
+                                         C.POINTER(CReadBatch), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RuntimeError(lib().gromhost_last_error().decode())
+
+
+class Bam:
+    """An open BAM; `read_target(tid)` returns the contig's reads as a ReadBatch."""
+
+    def __init__(self, path: str):
+        self._h = C.c_void_p()
+        _check(lib().gromhost_bam_open(path.encode(), C.byref(self._h)))
+        n = lib().gromhost_bam_n_targets(self._h)
+        self.names = [lib().gromhost_bam_target_name(self._h, i).decode() for i in range(n)]
+        self.lens = [int(lib().gromhost_bam_target_len(self._h, i)) for i in range(n)]
+        self.has_index = bool(lib().gromhost_bam_has_index(self._h))
+
+    def read_target(self, tid: int, keep_names: bool = False, threads: int = 0) -> ReadBatch:
+        bt = C.c_void_p()
+        _check(lib().gromhost_bam_read_target(self._h, tid, int(keep_names), threads, C.byref(bt)))
+        try:
+            v = CReadBatch()
+            lib().gromhost_batch_view(bt, C.byref(v))
+            return batch_from_c(v, keep_names)
+        finally:
+            lib().gromhost_batch_free(bt)
+
+    def close(self):
+        if self._h:
+            lib().gromhost_bam_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def write_bam(path: str, names: Sequence[str], lens: Sequence[int], batches: List[ReadBatch], level: int = 1):
+    """Serialise batches (sorted by tid, each with qname_off/qname_pool) as BAM + .bai."""
+    batches = sorted(batches, key=lambda b: b.tid)
+    n = len(names)
+    c_names = (C.c_char_p * n)(*[s.encode() for s in names])
+    c_lens = (C.c_int64 * n)(*[int(x) for x in lens])
+    cb = (CReadBatch * max(1, len(batches)))()
+    aux_off = (C.c_void_p * max(1, len(batches)))()
+    aux_pool = (C.c_void_p * max(1, len(batches)))()
+    any_aux = False
+    for i, b in enumerate(batches):
+        cb[i] = b.as_c()
+        if b.aux_off is not None:
+            any_aux = True
+            aux_off[i] = b.aux_off.ctypes.data
+            aux_pool[i] = b.aux_pool.ctypes.data if b.aux_pool.size else None
+        else:
+            aux_off[i] = None
+            aux_pool[i] = None
+    _check(lib().gromhost_bam_write(path.encode(), n, c_names, c_lens, len(batches), cb,
+                                    aux_off if any_aux else None, aux_pool if any_aux else None, level))

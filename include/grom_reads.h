@@ -1,0 +1,85 @@
+/* grom_reads.h -- the packed read-record batch that crosses the host/GPU seam.
+ *
+ * The reference consumes one `bam1_t` at a time through `my_samread`
+ * (reference src/GROM.c:981-992) and copies 8 core fields plus the first
+ * SA/XP aux entry out of it (src/GROM.c:5743-5824, 10971-11068, 14864-14955).
+ * This header is the structure-of-arrays form of exactly those fields for all
+ * reads of ONE contig, in BAM order.  It is what the host batcher
+ * (include/gromhost.h) produces and what the CUDA library (include/gromgpu.h)
+ * consumes; plain pointers and sizes only.
+ *
+ * Layout rules
+ *  - every per-read array has n_reads entries, index = BAM order on the contig;
+ *  - cigar[] holds BAM-encoded ops (len<<4|op); read i owns
+ *    cigar[cigar_off[i] .. cigar_off[i]+n_cigar[i]);
+ *  - bases: read i owns base slots base_off[i] .. base_off[i]+l_qseq[i);
+ *    base_off[i] is a multiple of 16 (so a read's quals start 16-byte aligned
+ *    and its nibbles 8-byte aligned); qual[slot] is the phred byte, and the
+ *    4-bit BAM base code ("=ACMGRSVTWYHKDBN") of a slot is
+ *    (seq4[slot>>1] >> ((~slot&1)<<2)) & 15, i.e. the BAM nibble order.
+ *    4-bit codes rather than 2-bit are kept on purpose: the reference compares
+ *    the decoded character (including IUPAC codes and 'N') with toupper(ref)
+ *    (src/GROM.c:6806) and a 2-bit+mask form could not reproduce that bit-exactly;
+ *  - qname_hash is a 64-bit FNV-1a hash of the read name, qname_len its strlen
+ *    (capped at 255).  The reference stores/compares names only as strings of
+ *    length < 50 (src/GROM.c:6810-6821);
+ *  - sa_*: first entry of the XP tag, else of the SA tag, parsed only when
+ *    0 < l_aux < 100 (src/GROM.c:5763); sa_pos = -1 when absent.  sa_same_chr is
+ *    the reference's prefix test strncmp(target_name, sa_chr, strlen(target_name))==0
+ *    (src/GROM.c:7431).  sa_start_adj/sa_end_adj/sa_end_adj_indel follow
+ *    src/GROM.c:6686-6733 (leading/trailing 'S' length, sum(I)-sum(D)).
+ */
+#ifndef GROM_READS_H
+#define GROM_READS_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GROM_BASE_ALIGN 16
+
+typedef struct grom_read_batch {
+    int64_t n_reads;
+    int64_t n_cigar_total;      /* entries in cigar[] */
+    int64_t n_base_slots;       /* entries in qual[]; seq4 has (n_base_slots+1)/2 bytes */
+    int32_t tid;                /* BAM target id shared by every read of the batch */
+    int32_t reserved;
+    const int32_t  *pos;        /* 0-based leftmost position (core.pos) */
+    const int32_t  *mpos;       /* core.mpos */
+    const int32_t  *tlen;       /* core.isize */
+    const int32_t  *mtid;       /* core.mtid */
+    const int32_t  *l_qseq;     /* core.l_qseq */
+    const uint16_t *flag;       /* core.flag */
+    const uint16_t *n_cigar;    /* core.n_cigar */
+    const uint8_t  *mapq;       /* core.qual */
+    const uint8_t  *qname_len;
+    const uint64_t *qname_hash;
+    const uint64_t *cigar_off;
+    const uint64_t *base_off;
+    const uint32_t *cigar;
+    const uint8_t  *seq4;
+    const uint8_t  *qual;
+    const int32_t  *sa_pos;     /* as written in the tag (1-based), -1 = none (src/GROM.c:5808) */
+    const int32_t  *sa_start_adj;
+    const int32_t  *sa_end_adj;
+    const int32_t  *sa_end_adj_indel;
+    const uint8_t  *sa_strand;  /* 0 '+', 1 otherwise */
+    const int16_t  *sa_mapq;
+    const uint8_t  *sa_same_chr;
+    /* host-only, optional (NULL allowed): read names for BAM serialisation */
+    const uint64_t *qname_off;  /* [n_reads+1] */
+    const char     *qname_pool;
+} grom_read_batch;
+
+static inline uint64_t grom_qname_hash(const char *s, int len)
+{
+    uint64_t h = 1469598103934665603ULL;
+    for (int i = 0; i < len; i++) { h ^= (uint8_t)s[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,58 @@
+/* gromhost.h -- host-side read supply for the GROM hot path (C, zlib + OpenMP only).
+ *
+ * Replaces, for the new host, the reference's read supply layer
+ * (reference src/GROM.c:82-324 ring buffer + bam_fetch producer, 981-992
+ * my_samread, 5743-5824 per-record field/aux extraction): instead of one
+ * bam1_t at a time it returns all records of one contig as a packed
+ * structure-of-arrays batch (include/grom_reads.h) ready to be handed to
+ * gromgpu_push_reads().  BGZF blocks of the contig are inflated in parallel.
+ *
+ * Also exports the serialiser used by the test/bench tooling to write a batch
+ * back out as BAM + BAI, so that the reference binary can be run on exactly
+ * the same reads.
+ *
+ * All functions return 0 on success, non-zero on error with a message in
+ * gromhost_last_error().
+ */
+#ifndef GROMHOST_H
+#define GROMHOST_H
+#include <stdint.h>
+#include "grom_reads.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct grom_bam grom_bam;       /* an open BAM (+ optional BAI) */
+typedef struct grom_batch grom_batch;   /* owns the arrays a grom_read_batch points to */
+
+const char *gromhost_last_error(void);
+
+/* open / header access (reference: samopen src/GROM.c:20474, bam_index_load 22129) */
+int  gromhost_bam_open(const char *path, grom_bam **out);
+void gromhost_bam_close(grom_bam *b);
+int  gromhost_bam_n_targets(const grom_bam *b);
+const char *gromhost_bam_target_name(const grom_bam *b, int tid);
+int64_t gromhost_bam_target_len(const grom_bam *b, int tid);
+int  gromhost_bam_has_index(const grom_bam *b);
+
+/* decode every record of target `tid` (BAM order) into a new batch.
+ * keep_names != 0 also fills qname_off/qname_pool.  n_threads <= 0: OpenMP default. */
+int  gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out);
+
+/* view of an owned batch; pointers stay valid until gromhost_batch_free() */
+void gromhost_batch_view(const grom_batch *bt, grom_read_batch *view);
+void gromhost_batch_free(grom_batch *bt);
+
+/* Serialise batches (one per target that has reads; sorted by tid) as a
+ * coordinate-sorted BAM plus its .bai.  Every batch must carry qname_off/qname_pool.
+ * aux, if not NULL, is per batch: aux_off[b][i]..aux_off[b][i+1] bytes of raw BAM
+ * aux data for read i (so SA tags can be planted). */
+int  gromhost_bam_write(const char *path, int n_targets, const char *const *names, const int64_t *lens,
+                        int n_batches, const grom_read_batch *batches,
+                        const uint64_t *const *aux_off, const uint8_t *const *aux_pool, int level);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
