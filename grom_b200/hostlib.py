@@ -97,3 +97,29 @@ def write_bam(path: str, names: Sequence[str], lens: Sequence[int], batches: Lis
             aux_pool[i] = None
     _check(lib().gromhost_bam_write(path.encode(), n, c_names, c_lens, len(batches), cb,
                                     aux_off if any_aux else None, aux_pool if any_aux else None, level))
+
+
+def _table_protos():
+    L = lib()
+    L.gromhost_tables_get.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.gromhost_tables_compute.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    L.gromhost_pval2sd.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    return L
+
+
+def tables(table_dir=None, min_mapq: int = 20, write_missing: bool = False):
+    """(hez, mq) binomial tables, float64 [1001, 1001]; loaded from `table_dir` when the reference's
+    text files are there, else computed (reference src/GROM.c:21134-21586)."""
+    L = _table_protos()
+    hez = np.zeros((1001, 1001)); mq = np.zeros((1001, 1001))
+    L.gromhost_tables_get(table_dir.encode() if table_dir else None, min_mapq, int(write_missing),
+                          hez.ctypes.data, mq.ctypes.data)
+    return hez, mq
+
+
+def pval2sd():
+    L = _table_protos()
+    pv = np.zeros(1001); sd = np.zeros(1001)
+    n = L.gromhost_pval2sd(pv.ctypes.data, sd.ctypes.data, 1001)
+    assert n == 1001
+    return pv, sd

@@ -52,6 +52,18 @@ int  gromhost_bam_write(const char *path, int n_targets, const char *const *name
                         int n_batches, const grom_read_batch *batches,
                         const uint64_t *const *aux_off, const uint8_t *const *aux_pool, int level);
 
+
+/* ---- statistics tables (reference src/GROM.c:21134-21626, 20705-20748) ----
+ * hez / mq: row-major double[1001*1001].  _get() mirrors the reference: load
+ * "<dir>/GROM_hez_binom_table_1000.txt" / "<dir>/GROM_mq_binom_table_<max(q,10)>_1000.txt"
+ * when present, else compute (and write the file when write_missing != 0).  dir == NULL: compute. */
+#define GROM_TABLE_DIM 1001
+void   gromhost_tables_compute(int min_mapq, double *hez, double *mq);
+int    gromhost_tables_get(const char *dir, int min_mapq, int write_missing, double *hez, double *mq);
+void   gromhost_table_paths(const char *dir, int min_mapq, char *hez_path, char *mq_path, int cap);
+double gromhost_mq_prob(int min_mapq);
+int    gromhost_pval2sd(double *pval, double *sd, int cap);   /* returns the length (1001) */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,51 @@
+/* oracle/grom_oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement of the reference's per-chromosome hot path
+ * (reference src/GROM.c:1432-18228 count_discordant_pairs) over chromosome-length
+ * arrays instead of the reference's sliding window.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this; the
+ * product (grom_b200/csrc) never does.
+ *
+ * Parity pinning: every function here is checked in tests/test_oracle_vs_reference.py
+ * against array dumps of the reference itself (oracle/_ref/GROM_ref, the reference's own
+ * translation unit built with dump hooks) and its VCF output; the binomial tables are
+ * additionally pinned against the reference's golden tilapia VCF (tests/test_tables.py).
+ */
+#ifndef GROM_ORACLE_H
+#define GROM_ORACLE_H
+#include <stdint.h>
+#include "grom_reads.h"
+#include "grom_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* read_state[i]: 0 = never reaches the evidence code (before W/4+1, UNMAP or DUP flag),
+ *                1 = applied, 2 = dropped by the -M duplicate filter */
+typedef struct oracle_chr_out {
+    int64_t  chr_len;
+    int32_t *arrays;            /* [GA_COUNT][chr_len], caller-allocated, zeroed by oracle */
+    uint8_t *read_state;        /* [n_reads] */
+    int32_t  scan_first;        /* first scanned position (W/4+1), -1 if nothing is scanned */
+    int32_t  scan_last;         /* last scanned position (inclusive) */
+    int32_t *lookahead_lseq;    /* [chr_len] cdp_lseq seen by the scan at each scanned position (0 elsewhere) */
+    grom_snv_cand *snv;         /* caller-allocated [snv_cap] */
+    int64_t  snv_cap, n_snv;
+    double   snv_ave_rd;        /* mean depth used by the SNV emission filter (src/GROM.c:15035-15043) */
+} oracle_chr_out;
+
+int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *fasta, int64_t chr_len,
+                   const double *hez_tbl, const double *mq_tbl, oracle_chr_out *out);
+
+/* GC / ACGT percentages of the triangular window (src/GROM.c:1766-1859) into arrays[GA_GC], arrays[GA_ACGT] */
+void oracle_gc_prepass(const grom_params *p, const char *fasta, int64_t chr_len, int32_t *gc, int32_t *acgt);
+
+/* format the SNV VCF lines the reference prints at src/GROM.c:15082-15095 into buf; returns bytes written */
+int64_t oracle_format_snv_vcf(const grom_params *p, const char *chr_name, const char *fasta,
+                              const grom_snv_cand *snv, int64_t n_snv, double ave_rd, char *buf, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
