@@ -1,0 +1,783 @@
+// gromgpu.cu -- B200 (sm_100a) implementation of GROM's per-chromosome evidence accumulation and SNV scan
+// behind the C ABI of include/gromgpu.h.
+//
+// Design: the reference walks reads one at a time and scatters into a sliding window
+// (reference src/GROM.c:5842-14980).  Here every reference position is owned by exactly one thread
+// ("pull" formulation): a CTA owns a tile of consecutive positions, stages the records of the reads that
+// overlap the tile in shared memory (BAM order) and every position-thread folds the reads that cover it
+// into registers, then stores its counts once, coalesced.  No atomics on the hot arrays, every count array
+// is written exactly once, and order-dependent per-position rules (the mate-overlap read-name slots of
+// src/GROM.c:6805-6824) are evaluated in BAM order for free.  Sparse point/range updates (soft-clip
+// classes, physical depth ranges) are scattered by the per-read prep kernel and finished by a single-pass
+// decoupled-look-back prefix scan.
+//
+// All work is HBM-bound integer/byte work; there is deliberately no tensor-core path.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <algorithm>
+#include <vector>
+#include "gromgpu.h"
+
+#define F_PAIRED 1
+#define F_UNMAP 4
+#define F_MUNMAP 8
+#define F_REVERSE 16
+#define F_MREVERSE 32
+#define F_DUP 1024
+
+enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X };
+
+static thread_local char g_err[1024];
+static int fail(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return -1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// ------------------------------------------------------------------------------------------------ globals
+static bool g_inited = false;
+static int g_device = -1;
+static grom_params g_params;
+static double *d_hez = nullptr, *d_mq = nullptr;
+static cudaStream_t g_own_stream = nullptr, g_stream = nullptr;
+__constant__ grom_params c_prm;
+
+// ------------------------------------------------------------------------------------------------ device data
+// per-read record produced by the prep kernel and consumed by the pileup kernel (32 bytes, 2 x 16-byte loads)
+struct __align__(16) PrepRec {
+    int32_t  pos;
+    int32_t  ext_end;     // one past the last reference position any M/=/X base of the read can touch
+    uint32_t base16;      // base_off / 16
+    uint32_t misc;        // [7:0] mapq  [8] applied  [9] reverse  [10] simple (one M op == whole read)  [11] name storable  [31:16] l_qseq
+    uint64_t hash;
+    uint32_t cig_off;
+    uint32_t n_cigar;
+};
+#define PR_APPLIED 0x100u
+#define PR_REV     0x200u
+#define PR_SIMPLE  0x400u
+#define PR_NAMEOK  0x800u
+
+struct DevReads {
+    int64_t n;
+    const int32_t *pos, *mpos, *tlen, *mtid, *l_qseq;
+    const uint16_t *flag, *n_cigar;
+    const uint8_t *mapq, *qname_len;
+    const uint64_t *qname_hash, *cigar_off, *base_off;
+    const uint32_t *cigar;
+    const uint8_t *seq4, *qual;
+};
+
+#define TILE 256           // positions per CTA in the pileup kernel (one per thread)
+#define CHUNK 128          // read records staged per shared-memory refill
+
+// reference character -> BAM 4-bit code of toupper(char), 16 if the character is not a code letter
+__device__ __forceinline__ int ref_code(unsigned char c)
+{
+    if (c >= 'a' && c <= 'z') c -= 32;
+    switch (c) {
+    case '=': return 0; case 'A': return 1; case 'C': return 2; case 'M': return 3; case 'G': return 4; case 'R': return 5;
+    case 'S': return 6; case 'V': return 7; case 'T': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11;
+    case 'K': return 12; case 'D': return 13; case 'B': return 14; case 'N': return 15; default: return 16;
+    }
+}
+
+// -M svtype (src/GROM.c:6435-6542); -1 = no class
+__device__ __forceinline__ int dup_svtype(int tid, int mtid, int pos, int mpos, int flag)
+{
+    const bool rev = flag & F_REVERSE, mrev = flag & F_MREVERSE;
+    if (tid == mtid) {
+        if (mpos > pos) { if (!rev && mrev) return 0; if (!rev && !mrev) return 8; return mrev ? 9 : 1; }
+        if (rev && !mrev) return 0;
+        if (!rev && !mrev) return 8;
+        if (mrev) return rev ? 9 : 1;
+        return -1;
+    }
+    if (!rev) return mrev ? 12 : 11;
+    return mrev ? 14 : 13;
+}
+
+// ---- K3: -M duplicate flags.  A read is a duplicate iff mapq >= q and an earlier read of the same start
+// position carries the same (mpos, mtid, l_qseq, tlen, svtype) (src/GROM.c:6548-6588; the first read of a
+// key run is always kept, so "an earlier kept read with this key exists" == "an earlier read with this key
+// exists").  Reads of one position are adjacent in BAM order, so each thread scans its own short run
+// backwards.  state: 0 not applied, 1 applied, 2 duplicate.
+__global__ void __launch_bounds__(256) k_read_state(DevReads R, int tid, int first_pos, uint8_t *state)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R.n) return;
+    const int pos = R.pos[i], flag = R.flag[i];
+    uint8_t st = 1;
+    if (pos < first_pos || (flag & (F_UNMAP | F_DUP))) st = 0;
+    else if (c_prm.rmdup > 0 && (flag & F_PAIRED) && !(flag & F_MUNMAP) && R.mapq[i] >= c_prm.min_mapq) {
+        const int mtid = R.mtid[i], mpos = R.mpos[i], tlen = R.tlen[i], lq = R.l_qseq[i];
+        const int sv = dup_svtype(tid, mtid, pos, mpos, flag);
+        if (sv >= 0) {
+            for (int64_t j = i - 1; j >= 0 && R.pos[j] == pos; j--) {
+                const int fj = R.flag[j];
+                if ((fj & (F_UNMAP | F_DUP)) || !(fj & F_PAIRED) || (fj & F_MUNMAP)) continue;
+                if (R.mpos[j] == mpos && R.mtid[j] == mtid && R.l_qseq[j] == lq && R.tlen[j] == tlen &&
+                    dup_svtype(tid, mtid, pos, mpos, fj) == sv) { st = 2; break; }
+            }
+        }
+    }
+    state[i] = st;
+}
+
+// ---- K0: per-read CIGAR summary (src/GROM.c:6740-6750, 7067-7099), soft-clip class point updates
+// (src/GROM.c:7103-7170) and the read-span range add for physical depth as a +1/-1 difference pair
+// (src/GROM.c:7176-7181; finished by k_scan_inplace).
+__global__ void __launch_bounds__(256) k_read_prep(DevReads R, int tid, int64_t P, int64_t Ppad, const uint8_t *state,
+                                                    PrepRec *prep, int32_t *arrays, int *max_span,
+                                                    unsigned long long *counters /* [0] applied [1] dups [2] aligned bases [3] rec bytes */)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int span = 0;
+    unsigned long long n_app = 0, n_dup = 0, n_al = 0, n_bytes = 0;
+    if (i < R.n) {
+        const int pos = R.pos[i], flag = R.flag[i], mq = R.mapq[i], lq = R.l_qseq[i];
+        const int ncig_all = R.n_cigar[i];
+        const uint64_t coff = R.cigar_off[i];
+        const uint8_t st = state[i];
+        PrepRec pr;
+        pr.pos = pos; pr.base16 = (uint32_t)(R.base_off[i] >> 4); pr.hash = R.qname_hash[i];
+        pr.cig_off = (uint32_t)coff; pr.n_cigar = (uint32_t)ncig_all;
+        uint32_t misc = (uint32_t)mq | ((uint32_t)(lq & 0xffff) << 16);
+        if (flag & F_REVERSE) misc |= PR_REV;
+        if (R.qname_len[i] < c_prm.read_name_len) misc |= PR_NAMEOK;
+        int ext_end = pos;
+        if (st == 1) {
+            misc |= PR_APPLIED;
+            const int ncig = min(ncig_all, c_prm.max_cigar_ops);
+            int rp = 0, rd_ = 0;            // reference offsets of the pileup walk and of the CNV-depth walk
+            int start_adj = 0, end_adj = 0, indel = 0, lseq = lq, al = 0;
+            int ext_p = 0, ext_d = 0;
+            for (int k = 0; k < ncig_all; k++) {
+                const uint32_t c = R.cigar[coff + k];
+                const int op = c & 15, len = (int)(c >> 4);
+                const bool in_pile = k < ncig;
+                if (op == OP_M || op == OP_EQ || op == OP_X) {
+                    if (in_pile) { rp += len; ext_p = rp; }
+                    rd_ += len; ext_d = rd_; al += len;
+                } else if (op == OP_D) { if (in_pile) { rp += len; indel -= len; } rd_ += len; }
+                else if (op == OP_N) { if (in_pile) rp += len; }
+                else if (op == OP_I) { if (in_pile) indel += len; }
+                else if (op == OP_H) { if (in_pile) lseq += len; }
+                if (in_pile && (op == OP_S || op == OP_H)) { if (k == 0) start_adj = len; if (k == ncig - 1) end_adj = len; }
+            }
+            if (ncig_all == 1 && (R.cigar[coff] & 15) == OP_M && (int)(R.cigar[coff] >> 4) == lq) misc |= PR_SIMPLE;
+            ext_end = pos + max(ext_p, ext_d);
+            span = ext_end - pos;
+            n_app = 1; n_al = (unsigned long long)al;
+            n_bytes = 40ull + 4ull * ncig_all + (unsigned long long)((lq + 3) / 4) + (unsigned long long)lq;
+            // soft-clip classes
+            const int add = (mq >= c_prm.min_mapq) ? c_prm.add_factor : 0;
+            const int mtid = R.mtid[i], mpos = R.mpos[i], tlen = R.tlen[i];
+            const bool paired = flag & F_PAIRED, munmap = flag & F_MUNMAP, rev = flag & F_REVERSE, same = (tid == mtid);
+            const int64_t rend = (int64_t)pos - start_adj + lseq - end_adj - indel;
+#define BUMP(ARR, RD, CRD, X) do { const int64_t x_ = (X); if (x_ >= 0 && x_ < P) { \
+                if (add) atomicAdd(arrays + (int64_t)(ARR) * Ppad + x_, add); \
+                atomicAdd(arrays + (int64_t)(RD) * Ppad + x_, 1); atomicAdd(arrays + (int64_t)(CRD) * Ppad + x_, 1); } } while (0)
+            if (start_adj >= c_prm.sc_min) {
+                const int64_t x = (int64_t)pos - 1;
+                if (!paired || (!rev && (munmap || (same && mpos > pos)))) BUMP(GA_SC_LEFT, GA_SC_LEFT_RD, GA_SC_RD, x);
+                if (paired && !munmap && !same && rev) BUMP(GA_CTX_SC_LEFT, GA_CTX_SC_LEFT_RD, GA_CTX_SC_RD, x);
+                if (paired && !munmap && same && rev && abs(tlen) <= c_prm.insert_max && mpos < pos)
+                    BUMP(GA_INDEL_SC_LEFT, GA_INDEL_SC_LEFT_RD, GA_INDEL_SC_RD, x);
+            }
+            if (end_adj >= c_prm.sc_min) {
+                if (!paired || (rev && (munmap || (same && mpos < pos)))) BUMP(GA_SC_RIGHT, GA_SC_RIGHT_RD, GA_SC_RD, rend);
+                if (paired && !munmap && !same && !rev) BUMP(GA_CTX_SC_RIGHT, GA_CTX_SC_RIGHT_RD, GA_CTX_SC_RD, rend);
+                if (paired && !munmap && same && !rev && abs(tlen) <= c_prm.insert_max && mpos > pos)
+                    BUMP(GA_INDEL_SC_RIGHT, GA_INDEL_SC_RIGHT_RD, GA_INDEL_SC_RD, rend);
+            }
+#undef BUMP
+            // physical depth over [pos, rend): difference pair
+            if (rend > pos) {
+                const int64_t a = max((int64_t)pos, (int64_t)0), e = min(rend, P);
+                if (a < e) {
+                    atomicAdd(arrays + (int64_t)GA_RD * Ppad + a, 1);
+                    if (e < P) atomicAdd(arrays + (int64_t)GA_RD * Ppad + e, -1);
+                }
+            }
+        } else if (st == 2) n_dup = 1;
+        pr.ext_end = ext_end; pr.misc = misc;
+        prep[i] = pr;
+    }
+    // block-level reductions of the small statistics
+    span = __reduce_max_sync(0xffffffffu, span);
+    n_app = __reduce_add_sync(0xffffffffu, (unsigned)n_app);
+    n_dup = __reduce_add_sync(0xffffffffu, (unsigned)n_dup);
+    unsigned al32 = __reduce_add_sync(0xffffffffu, (unsigned)n_al);
+    unsigned by32 = __reduce_add_sync(0xffffffffu, (unsigned)n_bytes);
+    if ((threadIdx.x & 31) == 0) {
+        if (span) atomicMax(max_span, span);
+        if (n_app) atomicAdd(counters + 0, n_app);
+        if (n_dup) atomicAdd(counters + 1, n_dup);
+        if (al32) atomicAdd(counters + 2, (unsigned long long)al32);
+        if (by32) atomicAdd(counters + 3, (unsigned long long)by32);
+    }
+}
+
+// ---- tile -> index of the first read that can overlap it: lower_bound(pos, tile_start - max_span)
+__global__ void __launch_bounds__(256) k_tile_index(const int32_t *pos, int64_t n, const int *max_span, int64_t n_tiles, int64_t *tile_first)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int64_t key = t * TILE - (int64_t)(*max_span);
+    int64_t lo = 0, hi = n;
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)pos[mid] < key) lo = mid + 1; else hi = mid; }
+    tile_first[t] = lo;
+}
+
+// ---- K1: pileup + CNV depth, one thread per reference position (src/GROM.c:6605-6671, 6740-7059)
+struct PileAcc {
+    int snv[4], low[4], pir[4], fs[4];
+    int bq, bq_all, mq, mq_all;
+    int rd_mq, rd_rd, rd_low;
+    uint64_t nm0, nm1, nm2; int nm_cnt;
+};
+
+__device__ __forceinline__ void pile_base(PileAcc &a, const DevReads &R, const PrepRec &r, int qi, int lseq, int rc4,
+                                          int q, int bqmin, int min_snv)
+{
+    const uint64_t slot = ((uint64_t)r.base16 << 4) + (uint64_t)qi;
+    const int qv = __ldg(R.qual + slot);
+    const int byte = __ldg(R.seq4 + (slot >> 1));
+    const int code = (byte >> ((~(int)slot & 1) << 2)) & 15;
+    const int mq = r.misc & 0xff;
+    const int bi = (code == 1) ? 0 : (code == 2) ? 1 : (code == 4) ? 2 : (code == 8) ? 3 : -1;
+    if (mq >= q && qv >= bqmin) {
+        bool skip = false;
+        const bool mism = (code != rc4);
+        if (mism) {
+            // first min_snv (<= 3) distinct names seen on mismatching high-quality bases (src/GROM.c:6805-6824)
+            const uint64_t h = r.hash;
+            if (a.nm_cnt > 0 && a.nm0 == h) skip = true;
+            else if (a.nm_cnt > 1 && a.nm1 == h) skip = true;
+            else if (a.nm_cnt > 2 && a.nm2 == h) skip = true;
+            else if (a.nm_cnt < min_snv && (r.misc & PR_NAMEOK)) {
+                if (a.nm_cnt == 0) a.nm0 = h; else if (a.nm_cnt == 1) a.nm1 = h; else a.nm2 = h;
+                a.nm_cnt++;
+            }
+        }
+        if (!skip && bi >= 0) {
+            const bool fwd = !(r.misc & PR_REV);
+            const int pir = (mism || fwd) ? qi : lseq - qi;
+            a.bq += qv; a.bq_all += qv; a.mq += mq; a.mq_all += mq;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int m = (bi == k); a.snv[k] += m; a.pir[k] += m ? pir : 0; a.fs[k] += (m && fwd); }
+        }
+    } else if (bi >= 0) {
+        a.bq_all += qv; a.mq_all += mq;
+#pragma unroll
+        for (int k = 0; k < 4; k++) a.low[k] += (bi == k);
+    }
+}
+
+__global__ void __launch_bounds__(TILE) k_pileup(DevReads R, const PrepRec *__restrict__ prep, const int64_t *__restrict__ tile_first,
+                                                  const char *__restrict__ fasta, int64_t P, int64_t Ppad, int32_t *__restrict__ arrays)
+{
+    __shared__ PrepRec s_rec[CHUNK];
+    __shared__ int s_cnt;
+    __shared__ int s_done;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_lo = tile * TILE, tile_hi = min(tile_lo + TILE, P);
+    const int64_t p = tile_lo + threadIdx.x;
+    const bool live = p < P;
+    const int rc4 = live ? ref_code((unsigned char)fasta[p]) : 16;
+    const int wlo = (int)(tile_lo + (threadIdx.x & ~31)), whi = wlo + 31;   // this warp's position window
+    const int q = c_prm.min_mapq, bqmin = c_prm.min_base_qual, rdq = c_prm.rd_min_mapq, min_snv = min(c_prm.min_snv, 3);
+    PileAcc a;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { a.snv[k] = a.low[k] = a.pir[k] = a.fs[k] = 0; }
+    a.bq = a.bq_all = a.mq = a.mq_all = a.rd_mq = a.rd_rd = a.rd_low = 0; a.nm0 = a.nm1 = a.nm2 = 0; a.nm_cnt = 0;
+
+    int64_t next = tile_first[tile];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { s_done = 0; }
+        __syncthreads();
+        if (threadIdx.x < CHUNK) {
+            const int64_t i = next + threadIdx.x;
+            if (i < R.n) {
+                const PrepRec r = prep[i];
+                s_rec[threadIdx.x] = r;
+                if ((int64_t)r.pos >= tile_hi) s_done = 1;      // benign race: every writer stores 1
+            }
+        }
+        if (threadIdx.x == 0) s_cnt = (int)min((int64_t)CHUNK, R.n - next);
+        __syncthreads();
+        const int cnt = s_cnt;
+        for (int t = 0; t < cnt; t++) {
+            const PrepRec r = s_rec[t];
+            if (!(r.misc & PR_APPLIED)) continue;
+            if (r.ext_end <= wlo || r.pos > whi) continue;               // warp-uniform
+            if (!live) continue;
+            const int mq = r.misc & 0xff;
+            if (r.misc & PR_SIMPLE) {
+                const int lq = (int)(r.misc >> 16);
+                const int off = (int)(p - r.pos);
+                if ((unsigned)off < (unsigned)lq) {
+                    if ((int64_t)r.pos + lq < P) { a.rd_mq += mq; if (mq >= rdq) a.rd_rd++; else a.rd_low++; }
+                    pile_base(a, R, r, off, lq, rc4, q, bqmin, min_snv);
+                }
+            } else {
+                // general CIGAR: every lane walks the same op list; pileup offsets advance on M/=/X/D/N,
+                // CNV-depth offsets on M/=/X/D only (src/GROM.c:6621-6663), H extends lseq (6997-7000)
+                const int ncig_all = (int)r.n_cigar, ncig = min(ncig_all, c_prm.max_cigar_ops);
+                int qi = 0, rp = r.pos, rdp = r.pos, lseq = (int)(r.misc >> 16);
+                for (int k = 0; k < ncig_all; k++) {
+                    const uint32_t c = __ldg(R.cigar + r.cig_off + k);
+                    const int op = c & 15, len = (int)(c >> 4);
+                    const bool in_pile = k < ncig;
+                    if (op == OP_M || op == OP_EQ || op == OP_X) {
+                        const int od = (int)(p - rdp);
+                        if ((unsigned)od < (unsigned)len && rdp >= 0 && (int64_t)rdp + len < P) { a.rd_mq += mq; if (mq >= rdq) a.rd_rd++; else a.rd_low++; }
+                        rdp += len;
+                        if (in_pile) {
+                            const int o = (int)(p - rp);
+                            if ((unsigned)o < (unsigned)len && qi + o < (int)(r.misc >> 16)) pile_base(a, R, r, qi + o, lseq, rc4, q, bqmin, min_snv);
+                            qi += len; rp += len;
+                        }
+                    } else if (op == OP_D) { rdp += len; if (in_pile) rp += len; }
+                    else if (op == OP_N) { if (in_pile) rp += len; }
+                    else if (op == OP_I || op == OP_S) { if (in_pile) qi += len; }
+                    else if (op == OP_H) { if (in_pile) lseq += len; }
+                }
+            }
+        }
+        next += cnt;
+        if (s_done || next >= R.n) break;
+    }
+    if (live) {
+        int32_t *o = arrays + p;
+        const int tot = a.snv[0] + a.snv[1] + a.snv[2] + a.snv[3];
+        const int lowt = a.low[0] + a.low[1] + a.low[2] + a.low[3];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            o[(int64_t)(GA_SNV_A + k) * Ppad] = a.snv[k]; o[(int64_t)(GA_SNVLOW_A + k) * Ppad] = a.low[k];
+            o[(int64_t)(GA_PIR_A + k) * Ppad] = a.pir[k]; o[(int64_t)(GA_FS_A + k) * Ppad] = a.fs[k];
+        }
+        o[(int64_t)GA_BQ * Ppad] = a.bq; o[(int64_t)GA_BQ_ALL * Ppad] = a.bq_all;
+        o[(int64_t)GA_MQ * Ppad] = a.mq; o[(int64_t)GA_MQ_ALL * Ppad] = a.mq_all;
+        o[(int64_t)GA_BQ_RC * Ppad] = tot; o[(int64_t)GA_MQ_RC * Ppad] = tot; o[(int64_t)GA_RC_ALL * Ppad] = tot + lowt;
+        o[(int64_t)GA_RD_MQ * Ppad] = a.rd_mq; o[(int64_t)GA_RD_RD * Ppad] = a.rd_rd; o[(int64_t)GA_RD_LOW * Ppad] = a.rd_low;
+    }
+}
+
+// ---- single-pass inclusive prefix sum, in place (decoupled look-back).  4096 elements per CTA.
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 16
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_inplace(int32_t *data, int64_t n, unsigned long long *status, unsigned int *ticket)
+{
+    __shared__ int s_tile, s_warp[SCAN_THREADS / 32], s_excl;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    const int64_t base = (int64_t)tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k += 4) {
+        if (base + k + 3 < n) { const int4 x = *reinterpret_cast<const int4 *>(data + base + k); v[k] = x.x; v[k + 1] = x.y; v[k + 2] = x.z; v[k + 3] = x.w; }
+        else { for (int j = 0; j < 4; j++) v[k + j] = (base + k + j < n) ? data[base + k + j] : 0; }
+    }
+#pragma unroll
+    for (int k = 1; k < SCAN_ITEMS; k++) v[k] += v[k - 1];
+    const int mine = v[SCAN_ITEMS - 1];
+    int incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < SCAN_THREADS / 32) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = w;       // inclusive warp totals
+    }
+    __syncthreads();
+    const int warp_excl = wid ? s_warp[wid - 1] : 0;
+    const int tile_sum = s_warp[SCAN_THREADS / 32 - 1];
+    if (threadIdx.x == 0) {
+        int excl = 0;
+        if (tile == 0) {
+            atomicExch(status + tile, (2ull << 32) | (unsigned int)tile_sum);
+        } else {
+            atomicExch(status + tile, (1ull << 32) | (unsigned int)tile_sum);
+            for (int j = tile - 1; j >= 0; j--) {
+                unsigned long long s;
+                do { s = *((volatile unsigned long long *)(status + j)); } while ((s >> 32) == 0);
+                excl += (int)(unsigned int)s;
+                if ((s >> 32) == 2) break;
+            }
+            __threadfence();
+            atomicExch(status + tile, (2ull << 32) | (unsigned int)(excl + tile_sum));
+        }
+        s_excl = excl;
+    }
+    __syncthreads();
+    const int off = s_excl + warp_excl + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k += 4) {
+        if (base + k + 3 < n) *reinterpret_cast<int4 *>(data + base + k) = make_int4(v[k] + off, v[k + 1] + off, v[k + 2] + off, v[k + 3] + off);
+        else { for (int j = 0; j < 4; j++) if (base + k + j < n) data[base + k + j] = v[k + j] + off; }
+    }
+}
+
+// ---- K2: per-position SNV gate with warp-ballot compaction (src/GROM.c:11096-11199) and the depth
+// reduction for the emission filter (src/GROM.c:15035-15043).
+__global__ void __launch_bounds__(256) k_snv_scan(const int32_t *__restrict__ arrays, const char *__restrict__ fasta, int64_t P, int64_t Ppad,
+                                                   int scan_first, int scan_last, int64_t depth_bound,
+                                                   const double *__restrict__ hez, const double *__restrict__ mqt,
+                                                   grom_snv_cand *cand, unsigned int cand_cap, unsigned int *n_cand,
+                                                   unsigned long long *depth_sum /* [0] sum [1] count */)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool is_cand = false;
+    grom_snv_cand c;
+    unsigned long long dsum = 0; unsigned dcnt = 0;
+    if (p < P) {
+        const char fc = fasta[p];
+        const bool is_n = (fc == 'N' || fc == 'n');
+        const int32_t *a = arrays + p;
+        if (p < depth_bound && !is_n) { dsum = (unsigned long long)((long long)a[(int64_t)GA_RD_RD * Ppad] + (long long)a[(int64_t)GA_RD_LOW * Ppad]); dcnt = 1; }
+        if (p >= scan_first && p <= scan_last && !is_n && a[(int64_t)GA_RD * Ppad] + a[(int64_t)GA_INDEL_SC_RD * Ppad] > 0) {
+            int cnt[4], total = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) { cnt[k] = a[(int64_t)(GA_SNV_A + k) * Ppad]; total += cnt[k]; }
+            const int rc4 = ref_code((unsigned char)fc);
+            const int bq_all = a[(int64_t)GA_BQ_ALL * Ppad], rc_all = a[(int64_t)GA_RC_ALL * Ppad];
+            const bool bq_ok = (double)bq_all / (double)rc_all >= c_prm.min_ave_bq;
+            const int T = c_prm.max_trials, TD = T + 1;
+            double best = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double ratio = (double)((float)cnt[k] / (float)total);
+                if (rc4 != (1 << k) && ratio >= c_prm.min_snv_ratio && cnt[k] >= c_prm.min_snv && bq_ok) {
+                    if (!is_cand || ratio > best) {
+                        const size_t idx = (total > T) ? (size_t)T * TD + (size_t)(cnt[k] * T / total) : (size_t)total * TD + (size_t)cnt[k];
+                        c.base = k; c.ratio = ratio; c.pr = mqt[idx]; c.hez = hez[idx];
+                        best = ratio; is_cand = true;
+                    }
+                }
+            }
+            if (is_cand) {
+                c.pos = (int32_t)p; c.reserved = 0;
+#pragma unroll
+                for (int t = 0; t < GA_PILEUP_COUNT; t++) c.v[t] = a[(int64_t)t * Ppad];
+            }
+        }
+    }
+    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
+    if (ball) {
+        unsigned basei = 0;
+        if (lane == 0) basei = atomicAdd(n_cand, (unsigned)__popc(ball));
+        basei = __shfl_sync(0xffffffffu, basei, 0);
+        if (is_cand) {
+            const unsigned slot = basei + (unsigned)__popc(ball & ((1u << lane) - 1u));
+            if (slot < cand_cap) cand[slot] = c;
+        }
+    }
+    // depth reduction: warp shuffle, one atomic per warp
+    for (int d = 16; d; d >>= 1) { dsum += __shfl_xor_sync(0xffffffffu, dsum, d); dcnt += __shfl_xor_sync(0xffffffffu, dcnt, d); }
+    if (lane == 0 && dcnt) { atomicAdd(depth_sum, dsum); atomicAdd(depth_sum + 1, (unsigned long long)dcnt); }
+}
+
+__global__ void k_fix_offsets(uint64_t *cigar_off, uint64_t *base_off, int64_t n, uint64_t cig_base, uint64_t slot_base)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { cigar_off[i] += cig_base; base_off[i] += slot_base; }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0, size = 0;
+    int ensure(size_t need, cudaStream_t s)
+    {
+        if (need <= cap) return 0;
+        size_t ncap = std::max(need, cap + cap / 2);
+        ncap = (ncap + 255) & ~(size_t)255;
+        void *np = nullptr;
+        CK(cudaMalloc(&np, ncap));
+        if (p && size) CK(cudaMemcpyAsync(np, p, size, cudaMemcpyDeviceToDevice, s));
+        if (p) { CK(cudaStreamSynchronize(s)); CK(cudaFree(p)); }
+        p = np; cap = ncap;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = size = 0; }
+};
+
+enum { B_POS, B_MPOS, B_TLEN, B_MTID, B_LQSEQ, B_FLAG, B_NCIGAR, B_MAPQ, B_QLEN, B_HASH, B_CIGOFF, B_BASEOFF, B_CIGAR, B_SEQ4, B_QUAL, B_COUNT };
+
+struct gromgpu_chr {
+    int tid = 0;
+    int64_t P = 0, Ppad = 0;
+    cudaStream_t stream = nullptr;
+    char *d_fasta = nullptr;
+    int32_t *d_arrays = nullptr;
+    DevBuf rb[B_COUNT];
+    int64_t n_reads = 0, n_cigar = 0, n_slots = 0;
+    int32_t last_pos = -1, last_lseq = 0;
+    int64_t n_leading = 0;             // reads before W/4+1 (they advance the reference's window index, src/GROM.c:5845)
+    uint8_t *d_state = nullptr; PrepRec *d_prep = nullptr; int64_t *d_tile_first = nullptr; size_t cap_state = 0, cap_tiles = 0;
+    int *d_max_span = nullptr; unsigned long long *d_counters = nullptr;   // 4 counters + 2 depth sums
+    unsigned long long *d_scan_status = nullptr; unsigned int *d_ticket = nullptr; size_t cap_scan = 0;
+    grom_snv_cand *d_cand = nullptr; unsigned int cand_cap = 0; unsigned int *d_ncand = nullptr;
+    std::vector<grom_snv_cand> h_cand;
+    cudaEvent_t ev[9];
+    bool ran = false;
+    gromgpu_stats stats;
+    gromgpu_result res;
+};
+
+extern "C" const char *gromgpu_last_error(void) { return g_err; }
+
+extern "C" int gromgpu_init(int device, const double *hez_tbl, const double *mq_tbl, const grom_params *p)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail("gromgpu_init: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail("gromgpu_init: device %d out of range (%d devices)", device, ndev);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail("gromgpu_init: device %d is sm_%d%d; this build targets sm_100a only", device, prop.major, prop.minor);
+    if (!g_own_stream) CK(cudaStreamCreateWithFlags(&g_own_stream, cudaStreamNonBlocking));
+    if (!g_stream) g_stream = g_own_stream;
+    const size_t tb = sizeof(double) * 1001 * 1001;
+    if (!d_hez) CK(cudaMalloc(&d_hez, tb));
+    if (!d_mq) CK(cudaMalloc(&d_mq, tb));
+    CK(cudaMemcpy(d_hez, hez_tbl, tb, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_mq, mq_tbl, tb, cudaMemcpyHostToDevice));
+    g_params = *p;
+    CK(cudaMemcpyToSymbol(c_prm, p, sizeof(grom_params)));
+    g_device = device; g_inited = true;
+    return 0;
+}
+
+extern "C" void gromgpu_shutdown(void)
+{
+    if (d_hez) cudaFree(d_hez); if (d_mq) cudaFree(d_mq);
+    d_hez = d_mq = nullptr;
+    if (g_own_stream) cudaStreamDestroy(g_own_stream);
+    g_own_stream = g_stream = nullptr; g_inited = false;
+}
+
+extern "C" int gromgpu_set_stream(void *s)
+{
+    if (!g_inited) return fail("gromgpu_set_stream: call gromgpu_init first");
+    g_stream = s ? (cudaStream_t)s : g_own_stream;
+    return 0;
+}
+
+extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, int64_t len)
+{
+    if (!g_inited) return fail("gromgpu_chr_begin: call gromgpu_init first");
+    if (len <= 0 || len > 0x7fffffff) return fail("gromgpu_chr_begin: chromosome length %lld unsupported", (long long)len);
+    gromgpu_chr *h = new gromgpu_chr();
+    h->tid = tid; h->P = len; h->Ppad = (len + 1023) & ~(int64_t)1023; h->stream = g_stream;
+    memset(&h->stats, 0, sizeof(h->stats)); memset(&h->res, 0, sizeof(h->res));
+    for (int i = 0; i < 9; i++) h->ev[i] = nullptr;
+    *out = h;
+    CK(cudaMalloc(&h->d_fasta, (size_t)h->Ppad));
+    CK(cudaMemcpyAsync(h->d_fasta, fasta, (size_t)len, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMalloc(&h->d_arrays, sizeof(int32_t) * (size_t)GA_COUNT * (size_t)h->Ppad));
+    CK(cudaMalloc(&h->d_max_span, sizeof(int)));
+    CK(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 8));
+    CK(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+    CK(cudaMalloc(&h->d_ncand, sizeof(unsigned int)));
+    for (int i = 0; i < 9; i++) CK(cudaEventCreate(&h->ev[i]));
+    return 0;
+}
+
+extern "C" void gromgpu_chr_free(gromgpu_chr *h)
+{
+    if (!h) return;
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < B_COUNT; i++) h->rb[i].release();
+    cudaFree(h->d_fasta); cudaFree(h->d_arrays); cudaFree(h->d_state); cudaFree(h->d_prep); cudaFree(h->d_tile_first);
+    cudaFree(h->d_max_span); cudaFree(h->d_counters); cudaFree(h->d_scan_status); cudaFree(h->d_ticket);
+    cudaFree(h->d_cand); cudaFree(h->d_ncand);
+    for (int i = 0; i < 9; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+}
+
+extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
+{
+    if (!h || !b) return fail("gromgpu_push_reads: null argument");
+    const int64_t n = b->n_reads;
+    if (n == 0) return 0;
+    if (b->pos[0] < h->last_pos) return fail("gromgpu_push_reads: reads are not in coordinate order");
+    if ((h->n_cigar + b->n_cigar_total) > 0xffffffffLL) return fail("gromgpu_push_reads: more than 2^32 CIGAR operations on one chromosome");
+    struct { int id; const void *src; size_t elt; int64_t cnt, have; } f[B_COUNT] = {
+        { B_POS, b->pos, 4, n, h->n_reads }, { B_MPOS, b->mpos, 4, n, h->n_reads }, { B_TLEN, b->tlen, 4, n, h->n_reads },
+        { B_MTID, b->mtid, 4, n, h->n_reads }, { B_LQSEQ, b->l_qseq, 4, n, h->n_reads }, { B_FLAG, b->flag, 2, n, h->n_reads },
+        { B_NCIGAR, b->n_cigar, 2, n, h->n_reads }, { B_MAPQ, b->mapq, 1, n, h->n_reads }, { B_QLEN, b->qname_len, 1, n, h->n_reads },
+        { B_HASH, b->qname_hash, 8, n, h->n_reads }, { B_CIGOFF, b->cigar_off, 8, n, h->n_reads }, { B_BASEOFF, b->base_off, 8, n, h->n_reads },
+        { B_CIGAR, b->cigar, 4, b->n_cigar_total, h->n_cigar }, { B_SEQ4, b->seq4, 1, (b->n_base_slots + 1) / 2, h->n_slots / 2 },
+        { B_QUAL, b->qual, 1, b->n_base_slots, h->n_slots } };
+    for (int k = 0; k < B_COUNT; k++) {
+        DevBuf &d = h->rb[f[k].id];
+        const size_t need = (size_t)(f[k].have + f[k].cnt) * f[k].elt + 64;
+        if (d.ensure(need, h->stream)) return -1;
+        if (f[k].cnt) CK(cudaMemcpyAsync((char *)d.p + (size_t)f[k].have * f[k].elt, f[k].src, (size_t)f[k].cnt * f[k].elt, cudaMemcpyHostToDevice, h->stream));
+        d.size = (size_t)(f[k].have + f[k].cnt) * f[k].elt;
+    }
+    if (h->n_cigar || h->n_slots) {
+        k_fix_offsets<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((uint64_t *)h->rb[B_CIGOFF].p + h->n_reads, (uint64_t *)h->rb[B_BASEOFF].p + h->n_reads,
+                                                                           n, (uint64_t)h->n_cigar, (uint64_t)h->n_slots);
+        CK(cudaGetLastError());
+    }
+    // host-side bookkeeping the scan range needs (src/GROM.c:6406, 11075-11083)
+    const int first_pos = grom_first_pos(&g_params);
+    for (int64_t i = 0; i < n && b->pos[i] < first_pos; i++) h->n_leading++;
+    h->last_pos = b->pos[n - 1]; h->last_lseq = b->l_qseq[n - 1];
+    h->n_reads += n; h->n_cigar += b->n_cigar_total;
+    h->n_slots += (b->n_base_slots + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN;
+    h->ran = false;
+    return 0;
+}
+
+static DevReads dev_reads(const gromgpu_chr *h)
+{
+    DevReads R;
+    R.n = h->n_reads;
+    R.pos = (const int32_t *)h->rb[B_POS].p; R.mpos = (const int32_t *)h->rb[B_MPOS].p; R.tlen = (const int32_t *)h->rb[B_TLEN].p;
+    R.mtid = (const int32_t *)h->rb[B_MTID].p; R.l_qseq = (const int32_t *)h->rb[B_LQSEQ].p; R.flag = (const uint16_t *)h->rb[B_FLAG].p;
+    R.n_cigar = (const uint16_t *)h->rb[B_NCIGAR].p; R.mapq = (const uint8_t *)h->rb[B_MAPQ].p; R.qname_len = (const uint8_t *)h->rb[B_QLEN].p;
+    R.qname_hash = (const uint64_t *)h->rb[B_HASH].p; R.cigar_off = (const uint64_t *)h->rb[B_CIGOFF].p; R.base_off = (const uint64_t *)h->rb[B_BASEOFF].p;
+    R.cigar = (const uint32_t *)h->rb[B_CIGAR].p; R.seq4 = (const uint8_t *)h->rb[B_SEQ4].p; R.qual = (const uint8_t *)h->rb[B_QUAL].p;
+    return R;
+}
+
+extern "C" int gromgpu_chr_run(gromgpu_chr *h)
+{
+    if (!h) return fail("gromgpu_chr_run: null handle");
+    cudaStream_t s = h->stream;
+    const int64_t n = h->n_reads, P = h->P, Ppad = h->Ppad;
+    const int64_t n_tiles = (P + TILE - 1) / TILE;
+    const int64_t n_scan_tiles = (Ppad + SCAN_TILE - 1) / SCAN_TILE;
+    // scratch sized to the current input
+    if ((size_t)n > h->cap_state) {
+        cudaFree(h->d_state); cudaFree(h->d_prep);
+        h->cap_state = (size_t)n + (size_t)n / 8 + 1024;
+        CK(cudaMalloc(&h->d_state, h->cap_state));
+        CK(cudaMalloc(&h->d_prep, h->cap_state * sizeof(PrepRec)));
+    }
+    if ((size_t)n_tiles > h->cap_tiles) { cudaFree(h->d_tile_first); h->cap_tiles = (size_t)n_tiles; CK(cudaMalloc(&h->d_tile_first, sizeof(int64_t) * h->cap_tiles)); }
+    if ((size_t)n_scan_tiles > h->cap_scan) { cudaFree(h->d_scan_status); h->cap_scan = (size_t)n_scan_tiles; CK(cudaMalloc(&h->d_scan_status, sizeof(unsigned long long) * h->cap_scan)); }
+    if (!h->d_cand) { h->cand_cap = 1u << 20; CK(cudaMalloc(&h->d_cand, sizeof(grom_snv_cand) * (size_t)h->cand_cap)); }
+
+    const int first_pos = grom_first_pos(&g_params);
+    int scan_first = -1, scan_last = -1;
+    if (h->n_leading < n) {
+        scan_first = first_pos;
+        int64_t sl = (int64_t)h->last_pos - (int64_t)g_params.overlap_mult * g_params.insert_max;
+        if (sl < scan_first) sl = scan_first;
+        if (sl >= P) sl = P - 1;
+        scan_last = (int)sl;
+    }
+    int64_t depth_bound = 0;
+    if (scan_first >= 0) {
+        const int W = grom_window_len(&g_params);
+        const int64_t idx = W / 4 + ((h->n_leading + 2 + ((int64_t)scan_last - first_pos)) % (W / 2));
+        depth_bound = (int64_t)scan_last + 1 - idx;
+    }
+    int launches = 0;
+    DevReads R = dev_reads(h);
+    CK(cudaEventRecord(h->ev[0], s));
+    // zero only the arrays that are scatter targets (rd .. indel_d_r_rd); the pileup and depth arrays are fully overwritten
+    CK(cudaMemsetAsync(h->d_arrays + (int64_t)GA_RD * Ppad, 0, sizeof(int32_t) * (size_t)(GA_RD_MQ - GA_RD) * (size_t)Ppad, s));
+    CK(cudaMemsetAsync(h->d_arrays + (int64_t)GA_GC * Ppad, 0, sizeof(int32_t) * (size_t)2 * (size_t)Ppad, s));
+    CK(cudaMemsetAsync(h->d_max_span, 0, sizeof(int), s));
+    CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, s));
+    CK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(h->d_ncand, 0, sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(h->d_scan_status, 0, sizeof(unsigned long long) * (size_t)n_scan_tiles, s));
+    CK(cudaEventRecord(h->ev[1], s));
+    const unsigned rb = (unsigned)((n + 255) / 256);
+    if (n) { k_read_state<<<rb, 256, 0, s>>>(R, h->tid, first_pos, h->d_state); launches++; }
+    CK(cudaEventRecord(h->ev[2], s));
+    if (n) { k_read_prep<<<rb, 256, 0, s>>>(R, h->tid, P, Ppad, h->d_state, h->d_prep, h->d_arrays, h->d_max_span, h->d_counters); launches++; }
+    CK(cudaEventRecord(h->ev[3], s));
+    k_tile_index<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(R.pos, n, h->d_max_span, n_tiles, h->d_tile_first); launches++;
+    CK(cudaEventRecord(h->ev[4], s));
+    k_pileup<<<(unsigned)n_tiles, TILE, 0, s>>>(R, h->d_prep, h->d_tile_first, h->d_fasta, P, Ppad, h->d_arrays); launches++;
+    CK(cudaEventRecord(h->ev[5], s));
+    k_scan_inplace<<<(unsigned)n_scan_tiles, SCAN_THREADS, 0, s>>>(h->d_arrays + (int64_t)GA_RD * Ppad, Ppad, h->d_scan_status, h->d_ticket); launches++;
+    CK(cudaEventRecord(h->ev[6], s));
+    k_snv_scan<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(h->d_arrays, h->d_fasta, P, Ppad, scan_first, scan_last, depth_bound, d_hez, d_mq,
+                                                         h->d_cand, h->cand_cap, h->d_ncand, h->d_counters + 4); launches++;
+    CK(cudaEventRecord(h->ev[7], s));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(s));
+    float ms;
+    gromgpu_stats &st = h->stats;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[7]); st.ms_total = ms;
+    cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); st.ms_clear = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); st.ms_dup = ms;
+    cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); st.ms_prep = ms;
+    cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); st.ms_index = ms;
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); st.ms_pileup = ms;
+    cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); st.ms_rdscan = ms;
+    cudaEventElapsedTime(&ms, h->ev[6], h->ev[7]); st.ms_snvscan = ms;
+    st.launches = launches;
+    unsigned long long cnt[8];
+    CK(cudaMemcpy(cnt, h->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    st.n_reads = n; st.n_applied = (int64_t)cnt[0]; st.n_dups = (int64_t)cnt[1]; st.aligned_bases = (int64_t)cnt[2]; st.bytes_reads = (int64_t)cnt[3];
+    h->res.scan_first = scan_first; h->res.scan_last = scan_last;
+    h->res.snv_ave_rd = (double)(long)cnt[4] / (double)(long)cnt[5];
+    h->ran = true;
+    return 0;
+}
+
+extern "C" int gromgpu_chr_result(gromgpu_chr *h, gromgpu_result *out)
+{
+    if (!h || !h->ran) return fail("gromgpu_chr_result: call gromgpu_chr_run first");
+    unsigned int nc = 0;
+    CK(cudaMemcpy(&nc, h->d_ncand, sizeof(nc), cudaMemcpyDeviceToHost));
+    if (nc > h->cand_cap) return fail("gromgpu_chr_result: %u SNV candidates exceed the buffer of %u", nc, h->cand_cap);
+    h->h_cand.resize(nc);
+    if (nc) CK(cudaMemcpy(h->h_cand.data(), h->d_cand, sizeof(grom_snv_cand) * (size_t)nc, cudaMemcpyDeviceToHost));
+    std::sort(h->h_cand.begin(), h->h_cand.end(), [](const grom_snv_cand &a, const grom_snv_cand &b) { return a.pos < b.pos; });
+    h->res.n_snv = nc; h->res.snv = h->h_cand.data();
+    *out = h->res;
+    return 0;
+}
+
+extern "C" int gromgpu_chr_finish(gromgpu_chr *h, gromgpu_result *out)
+{
+    if (gromgpu_chr_run(h)) return -1;
+    return gromgpu_chr_result(h, out);
+}
+
+extern "C" int gromgpu_chr_stats(const gromgpu_chr *h, gromgpu_stats *out)
+{
+    if (!h || !h->ran) return fail("gromgpu_chr_stats: call gromgpu_chr_run first");
+    *out = h->stats;
+    return 0;
+}
+
+extern "C" int gromgpu_debug_fetch(gromgpu_chr *h, int ga, int32_t *dst, int64_t p0, int64_t p1)
+{
+    if (!h || !h->ran) return fail("gromgpu_debug_fetch: call gromgpu_chr_run first");
+    if (ga < 0 || ga >= GA_COUNT || p0 < 0 || p1 > h->P || p0 > p1) return fail("gromgpu_debug_fetch: bad array %d or range [%lld,%lld)", ga, (long long)p0, (long long)p1);
+    CK(cudaMemcpy(dst, h->d_arrays + (int64_t)ga * h->Ppad + p0, sizeof(int32_t) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0, int64_t i1)
+{
+    if (!h || !h->ran) return fail("gromgpu_fetch_read_state: call gromgpu_chr_run first");
+    if (i0 < 0 || i1 > h->n_reads || i0 > i1) return fail("gromgpu_fetch_read_state: bad range");
+    CK(cudaMemcpy(dst, h->d_state + i0, (size_t)(i1 - i0), cudaMemcpyDeviceToHost));
+    return 0;
+}

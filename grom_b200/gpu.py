@@ -1,0 +1,158 @@
+"""Host-side mirror of the C ABI in include/gromgpu.h (ctypes over grom_b200/libgromgpu.so).
+
+`Chromosome` plays the role the body of `count_discordant_pairs` plays in the reference
+(reference src/GROM.c:1432, call site 21057): one object per chromosome, reads pushed in BAM
+order, `finish()` returns what the host needs for candidate post-processing and VCF text.
+There is no CPU fallback: a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .params import GA, GA_COUNT, Params, SNV_CAND_DTYPE
+from .reads import CReadBatch, ReadBatch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgromgpu.so")
+_LIB = None
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_total", C.c_float), ("ms_clear", C.c_float), ("ms_dup", C.c_float), ("ms_prep", C.c_float),
+                ("ms_index", C.c_float), ("ms_pileup", C.c_float), ("ms_rdscan", C.c_float), ("ms_snvscan", C.c_float),
+                ("launches", C.c_int32), ("reserved", C.c_int32), ("n_reads", C.c_int64), ("n_applied", C.c_int64),
+                ("n_dups", C.c_int64), ("aligned_bases", C.c_int64), ("bytes_reads", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class CResult(C.Structure):
+    _fields_ = [("scan_first", C.c_int32), ("scan_last", C.c_int32), ("n_snv", C.c_int64), ("snv", C.c_void_p),
+                ("snv_ave_rd", C.c_double)]
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.gromgpu_last_error.restype = C.c_char_p
+        L.gromgpu_init.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Params)]
+        L.gromgpu_set_stream.argtypes = [C.c_void_p]
+        L.gromgpu_chr_begin.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64]
+        L.gromgpu_push_reads.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
+        L.gromgpu_chr_run.argtypes = [C.c_void_p]
+        L.gromgpu_chr_result.argtypes = [C.c_void_p, C.POINTER(CResult)]
+        L.gromgpu_chr_finish.argtypes = [C.c_void_p, C.POINTER(CResult)]
+        L.gromgpu_chr_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.gromgpu_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64]
+        L.gromgpu_fetch_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        L.gromgpu_chr_free.argtypes = [C.c_void_p]
+        L.gromgpu_chr_free.restype = None
+        L.gromgpu_shutdown.restype = None
+        _LIB = L
+    return _LIB
+
+
+class GromGpuError(RuntimeError):
+    pass
+
+
+def _ck(rc: int):
+    if rc != 0:
+        raise GromGpuError(lib().gromgpu_last_error().decode())
+
+
+def init(device: int, hez: np.ndarray, mq: np.ndarray, params: Params):
+    hez = np.ascontiguousarray(hez, dtype=np.float64); mq = np.ascontiguousarray(mq, dtype=np.float64)
+    assert hez.shape == (1001, 1001) and mq.shape == (1001, 1001)
+    _ck(lib().gromgpu_init(device, hez.ctypes.data, mq.ctypes.data, C.byref(params)))
+
+
+def set_stream(cuda_stream_ptr: Optional[int]):
+    _ck(lib().gromgpu_set_stream(C.c_void_p(cuda_stream_ptr) if cuda_stream_ptr else None))
+
+
+def shutdown():
+    lib().gromgpu_shutdown()
+
+
+@dataclass
+class ChrResult:
+    scan_first: int
+    scan_last: int
+    snv: np.ndarray           # SNV_CAND_DTYPE, ascending position
+    snv_ave_rd: float
+
+
+class Chromosome:
+    def __init__(self, tid: int, fasta: np.ndarray):
+        fa = np.ascontiguousarray(fasta, dtype=np.uint8)
+        self.length = int(fa.shape[0])
+        self._h = C.c_void_p()
+        _ck(lib().gromgpu_chr_begin(C.byref(self._h), tid, fa.ctypes.data, self.length))
+
+    def push_reads(self, batch: ReadBatch):
+        cb = batch.as_c()
+        _ck(lib().gromgpu_push_reads(self._h, C.byref(cb)))
+
+    def push_reads_c(self, cb: CReadBatch):
+        _ck(lib().gromgpu_push_reads(self._h, C.byref(cb)))
+
+    def run(self):
+        _ck(lib().gromgpu_chr_run(self._h))
+
+    def result(self) -> ChrResult:
+        r = CResult()
+        _ck(lib().gromgpu_chr_result(self._h, C.byref(r)))
+        if r.n_snv:
+            buf = (C.c_char * (r.n_snv * SNV_CAND_DTYPE.itemsize)).from_address(r.snv)
+            snv = np.frombuffer(buf, dtype=SNV_CAND_DTYPE, count=r.n_snv).copy()
+        else:
+            snv = np.zeros(0, dtype=SNV_CAND_DTYPE)
+        return ChrResult(r.scan_first, r.scan_last, snv, r.snv_ave_rd)
+
+    def finish(self) -> ChrResult:
+        self.run()
+        return self.result()
+
+    def stats(self) -> Stats:
+        s = Stats()
+        _ck(lib().gromgpu_chr_stats(self._h, C.byref(s)))
+        return s
+
+    def fetch(self, name: str, p0: int = 0, p1: Optional[int] = None) -> np.ndarray:
+        p1 = self.length if p1 is None else p1
+        out = np.empty(p1 - p0, dtype=np.int32)
+        _ck(lib().gromgpu_debug_fetch(self._h, GA[name], out.ctypes.data, p0, p1))
+        return out
+
+    def fetch_all(self) -> np.ndarray:
+        out = np.empty((GA_COUNT, self.length), dtype=np.int32)
+        for k in range(GA_COUNT):
+            _ck(lib().gromgpu_debug_fetch(self._h, k, out[k].ctypes.data, 0, self.length))
+        return out
+
+    def read_state(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.uint8)
+        _ck(lib().gromgpu_fetch_read_state(self._h, out.ctypes.data, 0, n))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().gromgpu_chr_free(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -1,0 +1,101 @@
+/* gromgpu.h -- C ABI of the B200 (sm_100a) implementation of GROM's per-chromosome hot path.
+ *
+ * The reference has no plugin/FFI seam: the whole path is the body of
+ *
+ *     void count_discordant_pairs(samfile_t *bam, char *bam_name, char *chr_fasta, long chr_fasta_len,
+ *             char *chr_name, int chr_name_len, FILE *results, ..., char *results_file_name);
+ *
+ * (reference src/GROM.c:1432, single call site src/GROM.c:21057, one call per
+ * chromosome, reads pulled one at a time through my_samread src/GROM.c:981-992,
+ * configuration in ~90 globals src/GROM.c:710-974).  This header is the seam a
+ * maintainer would cut there: the host keeps BAM decode, FASTA load, candidate
+ * post-processing and VCF text; everything between "reads of one chromosome" and
+ * "compacted candidate records + count arrays" runs on the GPU behind these
+ * entry points.  Plain pointers and sizes only.  INTEGRATION.md shows the call
+ * sequence that replaces the body of count_discordant_pairs.
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on
+ * failure, with text in gromgpu_last_error() (the reference's convention is
+ * printf + exit, src/GROM.c:1611-1615; the host keeps that policy).  No CPU
+ * fallback exists: without a CUDA device gromgpu_init fails.
+ * One handle = one chromosome on one device; handles are independent, so one
+ * host thread per GPU can run different chromosomes concurrently (the -P
+ * process fan-out of src/GROM.c:549-599 becomes chromosome -> GPU assignment).
+ */
+#ifndef GROMGPU_H
+#define GROMGPU_H
+#include <stdint.h>
+#include "grom_reads.h"
+#include "grom_params.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gromgpu_chr gromgpu_chr;
+
+/* device-side time of each stage of the last gromgpu_chr_run(), from CUDA events on the handle's stream */
+typedef struct gromgpu_stats {
+    float ms_total;             /* first kernel start -> last kernel end */
+    float ms_clear;             /* zero-fill of the scatter-target arrays */
+    float ms_dup;               /* -M duplicate flags            (replaces src/GROM.c:6432-6588) */
+    float ms_prep;              /* per-read CIGAR summary + clip / depth-range scatter (7067-7181) */
+    float ms_index;             /* tile -> first-read index */
+    float ms_pileup;            /* pileup + CNV depth            (6605-6671, 6740-7059) */
+    float ms_rdscan;            /* range-add prefix scan -> rd   (7176-7181) */
+    float ms_snvscan;           /* per-position SNV gate + compaction (11096-11199) */
+    int32_t launches;           /* kernels launched by the run */
+    int32_t reserved;
+    int64_t n_reads, n_applied, n_dups, aligned_bases;
+    int64_t bytes_reads;        /* read-record bytes the pileup consumed (sum rec(r)) */
+} gromgpu_stats;
+
+typedef struct gromgpu_result {
+    int32_t scan_first, scan_last;      /* positions the reference would scan, inclusive; -1/-1 if none */
+    int64_t n_snv;                      /* SNV candidates, ascending position */
+    const grom_snv_cand *snv;           /* host memory owned by the handle, valid until chr_free / next run */
+    double  snv_ave_rd;                 /* mean depth for the SNV emission filter (src/GROM.c:15035-15043) */
+} gromgpu_result;
+
+/* Select the device, upload both 1001x1001 tables (row-major double) and the parameters.
+ * Replaces: read_binom_tables consumers src/GROM.c:796-799 and the g_* thresholds. */
+int gromgpu_init(int device, const double *hez_tbl, const double *mq_tbl, const grom_params *p);
+void gromgpu_shutdown(void);
+const char *gromgpu_last_error(void);
+
+/* Optional: run every later handle on a caller-owned CUDA stream (cudaStream_t passed as void*);
+ * NULL restores the library's own stream. */
+int gromgpu_set_stream(void *cuda_stream);
+
+/* Start a chromosome: uploads the FASTA characters (case preserved; the reference compares through
+ * toupper, src/GROM.c:6806, and tests 'N'/'n' literally, src/GROM.c:11113).
+ * Replaces the per-call allocation + zeroing of src/GROM.c:1884-1908, 2931-5719. */
+int gromgpu_chr_begin(gromgpu_chr **h, int tid, const char *fasta, int64_t len);
+
+/* Append reads of this chromosome in BAM order (host pointers; may be called repeatedly with
+ * consecutive slices).  Replaces the my_samread pulls at src/GROM.c:5740, 10968, 14861. */
+int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b);
+
+/* Run the kernels over everything pushed so far (inputs already resident in HBM). */
+int gromgpu_chr_run(gromgpu_chr *h);
+
+/* Copy the compacted results to the host (position-sorted). */
+int gromgpu_chr_result(gromgpu_chr *h, gromgpu_result *out);
+
+/* Convenience = run + result. */
+int gromgpu_chr_finish(gromgpu_chr *h, gromgpu_result *out);
+
+int gromgpu_chr_stats(const gromgpu_chr *h, gromgpu_stats *out);
+
+/* Parity access to the raw per-position arrays: copies array `ga` (GA_* of grom_params.h),
+ * positions [p0, p1), to dst (int32, host). */
+int gromgpu_debug_fetch(gromgpu_chr *h, int ga, int32_t *dst, int64_t p0, int64_t p1);
+/* read_state per read [i0, i1): 0 = not applied (before W/4+1, UNMAP/DUP flag), 1 = applied, 2 = -M duplicate */
+int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0, int64_t i1);
+
+void gromgpu_chr_free(gromgpu_chr *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -152,3 +152,18 @@ def reference_tables(min_mapq: int = 20):
     """The two tables as the reference binary in oracle/_ref loads them (text files next to it)."""
     from grom_b200 import hostlib
     return hostlib.tables(REF_DIR, min_mapq, write_missing=True)
+
+
+def normalise_records(lines):
+    """VCF record lines with the fields the reference leaves uninitialised masked out: small-insertion
+    records print ECO and EOT from candidate-list slots that are never written for that class (reference
+    src/GROM.c:16335), so their values are whatever malloc returned."""
+    out = []
+    for l in lines:
+        f = l.rstrip("\n").split("\t")
+        if len(f) >= 10 and f[8] == "SPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP":
+            v = f[9].split(":")
+            v[4] = "*"; v[6] = "*"
+            f[9] = ":".join(v)
+        out.append("\t".join(f) + "\n")
+    return out

@@ -1,0 +1,66 @@
+"""Regenerates the committed golden fixtures by running the REFERENCE ITSELF (oracle/_ref/GROM_ref, the
+reference's own translation unit built with dump hooks, and oracle/_ref/GROM_dist, its prebuilt binary)
+on a small synthetic data set.  Run in the build container (needs /root/reference for `make -C oracle ref`):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed):
+    tests/golden/g1.fa.gz, g1.bam, g1.bam.bai      the input (so nothing depends on numpy's RNG stream)
+    tests/golden/g1_default.npz, g1_rmdup.npz      reference arrays at every scanned position, per-read keep
+                                                   flags, CNV depth arrays, VCF records, library statistics
+"""
+import gzip
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+from tools import synth  # noqa: E402
+
+CONTIGS = [("chrG", 40_000), ("chrH", 25_000), ("chrZ", 8_000)]
+
+
+def main():
+    spec = synth.SynthSpec(contigs=CONTIGS, depth=30, seed=2024, dup_frac=0.06, clip_frac=0.04, disc_frac=0.02,
+                           snv_every=400, indel_every=3000, hardclip_frac=0.005, refskip_frac=0.002, long_name_frac=0.01)
+    cs = synth.simulate(spec)
+    tmp = tempfile.mkdtemp()
+    fa, bam = synth.write_dataset(os.path.join(tmp, "g1"), cs)
+    shutil.copy(bam, os.path.join(HERE, "g1.bam"))
+    shutil.copy(bam + ".bai", os.path.join(HERE, "g1.bam.bai"))
+    with open(fa, "rb") as f, gzip.open(os.path.join(HERE, "g1.fa.gz"), "wb", 9) as g:
+        g.write(f.read())
+    for tag, args in (("default", []), ("rmdup", ["-M"])):
+        dump = os.path.join(tmp, "dump_" + tag)
+        vcf = os.path.join(tmp, tag + ".vcf")
+        po.run_reference(bam, fa, vcf, args=args, dump_dir=dump, kind="ref")
+        vcf_dist = os.path.join(tmp, tag + ".dist.vcf")
+        po.run_reference(bam, fa, vcf_dist, args=args, kind="dist")
+        rec = [l for l in open(vcf) if not l.startswith("##")]
+        rec_dist = [l for l in open(vcf_dist) if not l.startswith("##")]
+        assert po.normalise_records(rec) == po.normalise_records(rec_dist), "white-box build and prebuilt reference binary disagree"
+        rec = rec_dist      # keep the prebuilt binary's text (identical up to the uninitialised ECO/EOT fields)
+        out = dict(vcf=np.array("".join(rec)), mean=np.array([po.read_mean_file(bam)[k] for k in
+                                                              ("insert_mean", "lseq", "insert_min", "insert_max", "mapped_reads")]))
+        for name, _ in CONTIGS:
+            n = name.lower()
+            sd = po.load_scan_dump(dump, n)
+            out[f"{n}_scan_pos"] = sd["pos"]
+            out[f"{n}_scan_v"] = sd["v"]
+            out[f"{n}_scan_d"] = sd["d"]
+            out[f"{n}_reads"] = po.load_reads_dump(dump, n)
+            out[f"{n}_depth"] = po.load_depth_dump(dump, n)
+            out[f"{n}_gc"] = po.load_gc_dump(dump, n)
+        np.savez_compressed(os.path.join(HERE, f"g1_{tag}.npz"), **out)
+        print(tag, "records", len(rec))
+    shutil.rmtree(tmp)
+
+
+if __name__ == "__main__":
+    main()

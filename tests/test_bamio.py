@@ -1,0 +1,60 @@
+"""Host batcher: BAM/BAI writer -> reader round trip, SA parsing rules, C-ABI surface of libgromhost."""
+import os
+
+import numpy as np
+
+from util import GOLDEN, golden_batches
+from grom_b200 import hostlib
+from grom_b200.reads import fnv1a64
+from tools import synth
+
+
+def test_roundtrip_all_fields(tmp_path):
+    spec = synth.SynthSpec(contigs=[("c1", 60_000), ("c2", 30_000)], depth=12, seed=5, dup_frac=0.05, clip_frac=0.05)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "rt"), cs)
+    with hostlib.Bam(bam) as b:
+        assert b.names == ["c1", "c2"] and b.lens == [60_000, 30_000] and b.has_index
+        for tid, c in enumerate(cs):
+            r = b.read_target(tid, keep_names=True)
+            o = c.batch
+            assert r.n_reads == o.n_reads
+            for k in ["pos", "mpos", "tlen", "mtid", "l_qseq", "flag", "n_cigar", "mapq", "qname_len", "qname_hash", "cigar",
+                      "sa_pos", "sa_strand", "sa_mapq", "sa_same_chr", "sa_start_adj", "sa_end_adj", "sa_end_adj_indel"]:
+                assert np.array_equal(getattr(r, k), getattr(o, k)), k
+            for i in range(0, r.n_reads, 211):
+                assert np.array_equal(r.bases(i), o.bases(i)) and np.array_equal(r.quals(i), o.quals(i))
+                assert r.qname(i) == o.qname(i)
+            assert np.all(r.base_off % 16 == 0)
+            assert (r.sa_pos >= 0).sum() > 0
+
+
+def test_reader_without_index(tmp_path):
+    spec = synth.SynthSpec(contigs=[("c1", 30_000), ("c2", 20_000)], depth=8, seed=6)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "ni"), cs)
+    os.remove(bam + ".bai")
+    with hostlib.Bam(bam) as b:
+        assert not b.has_index
+        for tid, c in enumerate(cs):
+            r = b.read_target(tid)
+            assert np.array_equal(r.pos, c.batch.pos) and np.array_equal(r.cigar, c.batch.cigar)
+
+
+def test_golden_bam_decodes_and_hashes():
+    names, batches = golden_batches()
+    assert names == ["chrG", "chrH", "chrZ"]
+    for b in batches:
+        assert b.n_reads > 0 and np.all(np.diff(b.pos) >= 0)
+        assert np.array_equal(b.qname_hash, fnv1a64(b.qname_pool, b.qname_off))
+
+
+def test_empty_target(tmp_path):
+    spec = synth.SynthSpec(contigs=[("c1", 20_000), ("c2", 20_000)], depth=5, seed=9)
+    cs = synth.simulate(spec)
+    cs[1].batch = None
+    synth.write_fasta(str(tmp_path / "e.fa"), [(c.name, c.chars) for c in cs])
+    hostlib.write_bam(str(tmp_path / "e.bam"), ["c1", "c2"], [20_000, 20_000], [cs[0].batch])
+    with hostlib.Bam(str(tmp_path / "e.bam")) as b:
+        assert b.read_target(1).n_reads == 0
+        assert b.read_target(0).n_reads == cs[0].batch.n_reads

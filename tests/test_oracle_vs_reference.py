@@ -1,0 +1,51 @@
+"""Live cross-check (build container only): run the white-box reference (oracle/_ref/GROM_ref) on freshly
+generated data and compare the oracle with its dumps.  Skipped where the binary is absent."""
+import os
+
+import numpy as np
+import pytest
+
+from util import CLIPS, PILEUP
+from grom_b200 import hostlib
+from grom_b200.params import GA_NAMES, Params
+from oracle import pyoracle as po
+from tools import synth
+
+pytestmark = pytest.mark.skipif(not po.have_reference("ref"), reason="oracle/_ref/GROM_ref not built")
+
+
+@pytest.mark.parametrize("seed,rmdup,read_len", [(31, 0, 150), (32, 1, 100)])
+def test_live_reference_dump_parity(tmp_path, seed, rmdup, read_len):
+    spec = synth.SynthSpec(contigs=[("chrQ", 120_000), ("chrR", 50_000), ("chrZ", 10_000)], depth=25, seed=seed,
+                           read_len=read_len, ins_mean=3.0 * read_len, ins_sd=30, ins_floor=read_len + 20,
+                           dup_frac=0.05, clip_frac=0.04)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "d"), cs)
+    dump = str(tmp_path / "dump")
+    po.run_reference(bam, fa, str(tmp_path / "o.vcf"), args=(["-M"] if rmdup else []), dump_dir=dump)
+    m = po.read_mean_file(bam)
+    prm = Params.default(insert_mean=max(m["insert_mean"], m["lseq"]), insert_min=m["insert_min"], insert_max=m["insert_max"],
+                         lseq=m["lseq"], rmdup=rmdup)
+    hez, mq = po.reference_tables(20)
+    vcf = [l for l in open(str(tmp_path / "o.vcf")) if not l.startswith("#")]
+    with hostlib.Bam(bam) as b:
+        for tid, c in enumerate(cs):
+            n = c.name.lower()
+            batch = b.read_target(tid)
+            r = po.run_chr(prm, batch, c.chars, hez, mq)
+            sd = po.load_scan_dump(dump, n)
+            pos = sd["pos"]
+            assert (r.scan_first, r.scan_last) == (int(pos[0]), int(pos[-1]))
+            for k in PILEUP + CLIPS:
+                assert np.array_equal(r.arrays[k][pos], sd["v"][:, k]), (n, GA_NAMES[k])
+            assert np.array_equal(r.lookahead_lseq[pos], sd["v"][:, 84])
+            dd = po.load_depth_dump(dump, n)
+            for j, k in enumerate(("rd_mq", "rd_rd", "rd_low")):
+                assert np.array_equal(r[k], dd[j])
+            rd = po.load_reads_dump(dump, n)
+            proc = np.nonzero(r.read_state > 0)[0]
+            assert np.array_equal(batch.pos[proc], rd["pos"])
+            assert np.array_equal((r.read_state[proc] == 1).astype(np.int32), rd["keep"])
+            mine = po.format_snv_vcf(prm, n, c.chars, r.snv, r.snv_ave_rd).splitlines(keepends=True)
+            ref = [l for l in vcf if l.startswith(n + "\t") and l.split("\t")[2] == ""]
+            assert mine == ref

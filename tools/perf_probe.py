@@ -1,0 +1,33 @@
+"""Quick device-side timing of one synthetic contig (development aid, not the bench)."""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from grom_b200 import gpu, hostlib
+from grom_b200.params import Params
+from tools import synth
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--mb", type=float, default=8.0)
+ap.add_argument("--depth", type=float, default=30.0)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--simple", type=int, default=1)
+ap.add_argument("--rmdup", type=int, default=1)
+a = ap.parse_args()
+t = time.time()
+spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05)
+c = synth.simulate(spec)[0]
+print("generated", c.batch.n_reads, "reads in", round(time.time() - t, 1), "s", flush=True)
+prm = Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=a.rmdup)
+hez, mq = hostlib.tables(None, prm.min_mapq)
+gpu.init(0, hez, mq, prm)
+with gpu.Chromosome(0, c.chars) as ch:
+    t = time.time(); ch.push_reads(c.batch); ch.run(); print("first run incl H2D", round(time.time() - t, 3), "s")
+    for r in range(a.reps):
+        ch.run()
+        s = ch.stats().as_dict()
+        print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.items()}))
+    P = len(c.chars)
+    s = ch.stats()
+    alg = s.bytes_reads + 104 * P   # 26 arrays written by the pileup kernel
+    print(f"pileup: {alg/1e9:.3f} GB algorithmic / {s.ms_pileup:.3f} ms = {alg/s.ms_pileup/1e6:.1f} GB/s; "
+          f"aligned bases/s (device total) = {s.aligned_bases/s.ms_total/1e-3/1e9:.2f} G")

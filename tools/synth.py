@@ -438,3 +438,61 @@ def write_dataset(prefix: str, contigs: List[SynthContig], level: int = 1) -> Tu
             if os.path.exists(p):
                 os.remove(p)
     return fa, bam
+
+
+def batch_from_records(tid: int, recs: List[dict]) -> ReadBatch:
+    """Hand-made reads for edge-case tests.  Each record: pos, cigar [(op,len)...], seq (str over ACGTN=...),
+    qual (int or list), and optional flag, mapq, mpos, mtid, tlen, name, sa=(pos,strand,mapq,same,start_adj,end_adj,indel)."""
+    n = len(recs)
+    recs = sorted(recs, key=lambda r: r["pos"])
+    from grom_b200.reads import NT16
+    lq = np.array([len(r["seq"]) for r in recs], dtype=np.int64)
+    slots = (lq + BASE_ALIGN - 1) // BASE_ALIGN * BASE_ALIGN
+    base_off = np.concatenate([[0], np.cumsum(slots)])[:-1] if n else np.zeros(0, dtype=np.int64)
+    total = int(slots.sum())
+    codes = np.zeros(total + (total & 1), dtype=np.uint8)
+    qual = np.zeros(total + (total & 1), dtype=np.uint8)
+    ncig = np.array([len(r["cigar"]) for r in recs], dtype=np.int64)
+    cig_off = np.concatenate([[0], np.cumsum(ncig)])[:-1] if n else np.zeros(0, dtype=np.int64)
+    cigar = np.zeros(int(ncig.sum()), dtype=np.uint32)
+    names = []
+    sa = dict(sa_pos=np.full(n, -1, dtype=np.int32), sa_start_adj=np.zeros(n, np.int32), sa_end_adj=np.zeros(n, np.int32),
+              sa_end_adj_indel=np.zeros(n, np.int32), sa_strand=np.zeros(n, np.uint8), sa_mapq=np.full(n, -1, np.int16),
+              sa_same_chr=np.zeros(n, np.uint8))
+    for i, r in enumerate(recs):
+        o = int(base_off[i])
+        codes[o:o + lq[i]] = [NT16.index(ch) for ch in r["seq"]]
+        q = r.get("qual", 30)
+        qual[o:o + lq[i]] = q if not np.isscalar(q) else np.full(lq[i], q)
+        for k, (op, ln) in enumerate(r["cigar"]):
+            cigar[int(cig_off[i]) + k] = (ln << 4) | op
+        names.append(r.get("name", f"r{i}"))
+        if "sa" in r:
+            s = r["sa"]
+            sa["sa_pos"][i], sa["sa_strand"][i], sa["sa_mapq"][i], sa["sa_same_chr"][i] = s[0], s[1], s[2], s[3]
+            sa["sa_start_adj"][i], sa["sa_end_adj"][i], sa["sa_end_adj_indel"][i] = s[4], s[5], s[6]
+    enc = [s.encode() for s in names]
+    lens = np.array([len(e) + 1 for e in enc], dtype=np.int64)
+    qname_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    pool = np.frombuffer(b"\0".join(enc) + b"\0", dtype=np.uint8).copy() if n else np.zeros(0, dtype=np.uint8)
+    g = lambda k, d: np.array([r.get(k, d) for r in recs], dtype=np.int64)  # noqa: E731
+    return ReadBatch(
+        tid=tid, pos=g("pos", 0), mpos=g("mpos", 0), tlen=g("tlen", 0), mtid=g("mtid", tid), l_qseq=lq, flag=g("flag", 0),
+        n_cigar=ncig, mapq=g("mapq", 60), qname_len=np.minimum(lens - 1, 255), qname_hash=fnv1a64(pool, qname_off) if n else np.zeros(0, np.uint64),
+        cigar_off=cig_off.astype(np.uint64), base_off=base_off.astype(np.uint64), cigar=cigar,
+        seq4=((codes[0::2] << 4) | codes[1::2]).astype(np.uint8), qual=qual, qname_off=qname_off, qname_pool=pool,
+        aux_off=np.zeros(n + 1, dtype=np.uint64), aux_pool=np.zeros(0, dtype=np.uint8), **sa).normalise()
+
+
+def slice_batch(b: ReadBatch, i0: int, i1: int) -> ReadBatch:
+    """Reads [i0, i1) of a batch as a self-contained batch (offsets rebased) -- for multi-push tests."""
+    if i1 <= i0:
+        raise ValueError("empty slice")
+    c0 = int(b.cigar_off[i0]); c1 = int(b.cigar_off[i1 - 1]) + int(b.n_cigar[i1 - 1])
+    s0 = int(b.base_off[i0])
+    s1 = int(b.base_off[i1 - 1]) + (int(b.l_qseq[i1 - 1]) + BASE_ALIGN - 1) // BASE_ALIGN * BASE_ALIGN
+    kw = {k: getattr(b, k)[i0:i1].copy() for k in ["pos", "mpos", "tlen", "mtid", "l_qseq", "flag", "n_cigar", "mapq", "qname_len",
+                                                   "qname_hash", "sa_pos", "sa_start_adj", "sa_end_adj", "sa_end_adj_indel",
+                                                   "sa_strand", "sa_mapq", "sa_same_chr"]}
+    return ReadBatch(tid=b.tid, cigar_off=b.cigar_off[i0:i1] - np.uint64(c0), base_off=b.base_off[i0:i1] - np.uint64(s0),
+                     cigar=b.cigar[c0:c1].copy(), seq4=b.seq4[s0 // 2:s1 // 2].copy(), qual=b.qual[s0:s1].copy(), **kw).normalise()
