@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- aligned bases/sec through the GROM hot path on B200 (BASELINE.json metric).
+
+One "step" = one pass of the whole hot path (duplicate flags, read prep + clip scatter, pileup + CNV depth,
+range-add scan, SNV gate + compaction) over one chr20-sized synthetic contig (64 Mb, 30x, 2x150 bp,
+BASELINE.json configs[2]) per GPU.  Ranks are independent (chromosomes partition across GPUs exactly like the
+reference's -P processes, no data-path collective): weak scaling, value = bases of all ranks / max-over-ranks time.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mb 64] [--depth 30]
+  python bench.py --impl reference ...      times the reference's own CPU implementation (oracle/_ref/GROM_ref,
+                                            built from the reference's translation unit) with -P on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aligned_bases_per_sec_hot_path"
+UNIT = "bases/s"
+N_ARRAYS_PILEUP = 26          # int32 arrays the pileup kernel writes per position (23 pileup + 3 CNV depth)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mb", type=float, default=64.0, help="contig length per GPU in Mb (default: chr20-sized)")
+    ap.add_argument("--depth", type=float, default=30.0)
+    ap.add_argument("--cpu-sample-mb", type=float, default=1.5, help="contig length of each CPU-baseline sample contig")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"synthetic {a.depth:g}x paired-end 2x150 contig of {a.mb:g} Mb per GPU (chr20-sized), -M, SNV scan"
+
+
+def params_for_bench():
+    from grom_b200.params import Params
+    return Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=1)
+
+
+# ---------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4) if r[3 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU baseline
+def cpu_reference_run(a, steps: int, warmup: int):
+    """Time the reference's own implementation (oracle/_ref/GROM_ref = reference src/GROM.c built with a zlib-only
+    samtools shim) on a bounded sample: P = cores/2 contigs (+ a dummy last contig, which -P >= 2 silently skips,
+    reference src/GROM.c:20999) processed by `-P P -M`, 2 threads per process (src/GROM.c:575)."""
+    from oracle import pyoracle as po
+    from tools import synth
+    if not po.have_reference("ref"):
+        return None
+    cores = os.cpu_count() or 2
+    nproc = max(1, min(cores // 2, 32))
+    L = int(a.cpu_sample_mb * 1e6)
+    contigs = [(f"chr{i + 1}", L) for i in range(nproc)] + [("chrzz", 60_000)]
+    spec = synth.SynthSpec(contigs=contigs, depth=a.depth, seed=4242, simple=True, dup_frac=0.05)
+    cs = synth.simulate(spec)
+    tmp = tempfile.mkdtemp(prefix="grom_cpu_")
+    try:
+        fa, bam = synth.write_dataset(os.path.join(tmp, "sample"), cs)
+        bases = sum(c.batch.aligned_bases() for c in cs[:-1]) if nproc >= 2 else sum(c.batch.aligned_bases() for c in cs)
+        po.reference_tables(20)                         # tables pre-generated next to the binary
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            po.run_reference(bam, fa, os.path.join(tmp, "out.vcf"), args=["-M", "-P", str(nproc)], kind="ref")
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        sec = float(np.mean(times))
+        return {"value": bases / sec, "unit": UNIT, "cores": 2 * nproc if nproc >= 1 else 1, "kind": "reference",
+                "sample": f"GROM_ref -M -P {nproc} on {nproc} synthetic contigs x {a.cpu_sample_mb:g} Mb at {a.depth:g}x "
+                          f"({bases / 1e6:.0f} M aligned bases, whole program incl. BAM decode), {sec:.2f} s wall, host has {cores} cores",
+                "seconds": sec, "aligned_bases": bases}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(a, max(1, a.steps), min(a.warmup, 1))
+    if r is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/GROM_ref was not built (needs /root/reference at build time)"}))
+        return 0
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": {"workload": workload_name(a), "sample": r["sample"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+def pin_batch(batch):
+    """Copy every array of the batch into pinned host memory; returns (batch view over pinned memory, keepalive, bytes)."""
+    import torch
+    from grom_b200.reads import _DTYPES, ReadBatch
+    keep, kw, nbytes = [], {}, 0
+    for k in _DTYPES:
+        src = getattr(batch, k)
+        t = torch.from_numpy(src).pin_memory() if src.size else torch.from_numpy(src)
+        keep.append(t)
+        kw[k] = t.numpy()
+        nbytes += src.nbytes
+    return ReadBatch(tid=batch.tid, **kw), keep, nbytes
+
+
+def main_b200(a):
+    import torch
+    import torch.distributed as dist
+    from grom_b200 import gpu, hostlib
+    from tools import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    prm = params_for_bench()
+    hez, mq = hostlib.tables(None, prm.min_mapq)
+    # synthetic chr20-sized contig of this rank (rank-specific seed); inputs (>3 GB) far exceed the 126 MB L2
+    P = int(a.mb * 1e6)
+    spec = synth.SynthSpec(contigs=[(f"chr{20 + rank}", P)], depth=a.depth, seed=20 + rank, simple=True, dup_frac=0.05, names=False)
+    t0 = time.time()
+    c = synth.simulate(spec)[0]
+    gen_s = time.time() - t0
+    pinned, keep, read_bytes = pin_batch(c.batch)
+    fasta_pinned = torch.from_numpy(c.chars).pin_memory()
+    fasta_np = fasta_pinned.numpy()
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        gpu.init(local, hez, mq, prm)
+        gpu.set_stream(stream.cuda_stream)
+        ch = gpu.Chromosome(c.batch.tid, fasta_np)
+        ch.push_reads(pinned)
+        # ---- resident-input timing (value): W warm-up + K timed steps
+        for _ in range(max(3, a.warmup)):
+            ch.run()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per = {k: 0.0 for k in ("ms_total", "ms_clear", "ms_dup", "ms_prep", "ms_index", "ms_pileup", "ms_rdscan", "ms_snvscan")}
+        launches = 0
+        ev0.record(stream)
+        for _ in range(a.steps):
+            ch.run()
+            s = ch.stats()
+            for k in per:
+                per[k] += getattr(s, k)
+            launches += s.launches
+        ev1.record(stream)
+        barrier()
+        ms_steps = ev0.elapsed_time(ev1)
+        st = ch.stats()
+        res = ch.result()
+        # ---- end-to-end timing through the C ABI with host (pinned) buffers: reset + FASTA H2D + reads H2D + kernels + result D2H
+        d2h_bytes = len(res.snv) * 128 + 64
+        for _ in range(2):
+            ch.reset(fasta_np); ch.push_reads(pinned); ch.finish()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            ch.reset(fasta_np)
+            ch.push_reads(pinned)
+            r2 = ch.finish()
+        e1.record(stream)
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        assert len(r2.snv) == len(res.snv)
+        ch.close()
+
+    bases = int(st.aligned_bases)
+    tmax = torch.tensor([ms_steps, ms_e2e], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([bases], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_steps_max, ms_e2e_max = float(tmax[0]), float(tmax[1])
+    total_bases = float(tot[0])
+
+    if rank == 0:
+        peaks = {}
+        pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk_path):
+            peaks = json.load(open(pk_path))
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        # dominant kernel = pileup: algorithmic bytes = read records consumed + the 26 int32 arrays it writes + FASTA char
+        alg_bytes = st.bytes_reads + (4 * N_ARRAYS_PILEUP + 1) * P
+        ms_pile = per["ms_pileup"] / a.steps
+        achieved = alg_bytes / (ms_pile * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "pileup_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                traffic = tj.get("dram_bytes_per_launch_scaled_to_mb", {}).get(f"{a.mb:g}") or tj.get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            r = cpu_reference_run(a, 1, 0)
+            if r:
+                cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line = {
+            "metric": METRIC, "value": total_bases * a.steps / (ms_steps_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": max(3, a.warmup), "ms_per_step": ms_steps_max / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "contig_len": P, "reads_per_gpu": int(st.n_reads), "aligned_bases_per_gpu": bases,
+                       "flags": "-M (duplicate filter on), defaults otherwise", "l2": "inputs (>3 GB reads + 6.7 GB arrays per step) exceed the 126 MB L2; no flush needed",
+                       "partition": "one contig per GPU, no data-path collective", "host_gen_s": round(gen_s, 1)},
+            "e2e": {"value": total_bases * a.steps / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(read_bytes + P),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_pileup", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": ms_pile},
+            "kernels_ms_per_step": {k: v / a.steps for k, v in per.items()},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "results": {"snv_candidates": int(len(res.snv)), "dups": int(st.n_dups), "applied_reads": int(st.n_applied)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(main_reference(args) if args.impl == "reference" else main_b200(args))

@@ -50,6 +50,7 @@ def lib() -> C.CDLL:
         L.gromgpu_chr_begin.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64]
         L.gromgpu_push_reads.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
         L.gromgpu_chr_run.argtypes = [C.c_void_p]
+        L.gromgpu_chr_reset.argtypes = [C.c_void_p, C.c_void_p]
         L.gromgpu_chr_result.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.gromgpu_chr_finish.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.gromgpu_chr_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -106,6 +107,14 @@ class Chromosome:
 
     def push_reads_c(self, cb: CReadBatch):
         _ck(lib().gromgpu_push_reads(self._h, C.byref(cb)))
+
+    def reset(self, fasta: Optional[np.ndarray] = None):
+        """Drop the pushed reads, keep the device buffers; optionally upload new FASTA characters (same length)."""
+        ptr = None
+        if fasta is not None:
+            assert fasta.dtype == np.uint8 and fasta.shape[0] == self.length and fasta.flags.c_contiguous
+            ptr = fasta.ctypes.data
+        _ck(lib().gromgpu_chr_reset(self._h, ptr))
 
     def run(self):
         _ck(lib().gromgpu_chr_run(self._h))

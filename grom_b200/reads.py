@@ -13,7 +13,7 @@ from typing import Optional
 
 import numpy as np
 
-BASE_ALIGN = 16
+BASE_ALIGN = 32
 
 # BAM CIGAR op codes
 CMATCH, CINS, CDEL, CREF_SKIP, CSOFT_CLIP, CHARD_CLIP, CPAD, CEQUAL, CDIFF = range(9)

@@ -13,8 +13,9 @@
  *  - cigar[] holds BAM-encoded ops (len<<4|op); read i owns
  *    cigar[cigar_off[i] .. cigar_off[i]+n_cigar[i]);
  *  - bases: read i owns base slots base_off[i] .. base_off[i]+l_qseq[i);
- *    base_off[i] is a multiple of 16 (so a read's quals start 16-byte aligned
- *    and its nibbles 8-byte aligned); qual[slot] is the phred byte, and the
+ *    base_off[i] is a multiple of GROM_BASE_ALIGN = 32 (a read's quals start 32-byte
+ *    aligned and its nibbles 16-byte aligned, which is what the bulk-copy (TMA)
+ *    staging of the pileup kernel requires); qual[slot] is the phred byte, and the
  *    4-bit BAM base code ("=ACMGRSVTWYHKDBN") of a slot is
  *    (seq4[slot>>1] >> ((~slot&1)<<2)) & 15, i.e. the BAM nibble order.
  *    4-bit codes rather than 2-bit are kept on purpose: the reference compares
@@ -37,7 +38,7 @@
 extern "C" {
 #endif
 
-#define GROM_BASE_ALIGN 16
+#define GROM_BASE_ALIGN 32
 
 typedef struct grom_read_batch {
     int64_t n_reads;

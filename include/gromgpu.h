@@ -72,6 +72,10 @@ int gromgpu_set_stream(void *cuda_stream);
  * Replaces the per-call allocation + zeroing of src/GROM.c:1884-1908, 2931-5719. */
 int gromgpu_chr_begin(gromgpu_chr **h, int tid, const char *fasta, int64_t len);
 
+/* Forget the pushed reads (device buffers are kept) and, if fasta != NULL, upload new characters of the
+ * same length: lets one handle be reused for the next chromosome-sized unit without reallocating. */
+int gromgpu_chr_reset(gromgpu_chr *h, const char *fasta);
+
 /* Append reads of this chromosome in BAM order (host pointers; may be called repeatedly with
  * consecutive slices).  Replaces the my_samread pulls at src/GROM.c:5740, 10968, 14861. */
 int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b);

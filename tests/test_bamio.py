@@ -25,7 +25,7 @@ def test_roundtrip_all_fields(tmp_path):
             for i in range(0, r.n_reads, 211):
                 assert np.array_equal(r.bases(i), o.bases(i)) and np.array_equal(r.quals(i), o.quals(i))
                 assert r.qname(i) == o.qname(i)
-            assert np.all(r.base_off % 16 == 0)
+            assert np.all(r.base_off % 32 == 0)
             assert (r.sa_pos >= 0).sum() > 0
 
 

@@ -57,6 +57,7 @@ class SynthSpec:
     lower_frac: float = 0.1
     long_name_frac: float = 0.0005
     simple: bool = False            # bench mode: only the vectorised read classes
+    names: bool = True              # False: no read-name strings (hash only; such a batch cannot be written as BAM)
 
 
 def make_reference(length: int, rng: np.random.Generator, n_frac=0.01, lower_frac=0.1) -> np.ndarray:
@@ -380,6 +381,21 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
         for k, (op, ln) in enumerate(c):
             cigar[o + k] = (ln << 4) | op
     # read names "<contig>.<pair>" (+ a few >= 50 chars long)
+    if not spec.names:
+        # bench mode: no name strings, only a 64-bit per-pair id hash (both mates share it, like a shared read name)
+        with np.errstate(over="ignore"):
+            z = (pair_id.astype(np.uint64) + np.uint64(tid + 1) * np.uint64(0x9E3779B97F4A7C15))
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            z = z ^ (z >> np.uint64(31))
+        batch = ReadBatch(
+            tid=tid, pos=pos, mpos=mpos, tlen=tlen, mtid=mtid, l_qseq=l_qseq, flag=flag, n_cigar=n_cigar, mapq=mapq,
+            qname_len=np.full(n, 12, dtype=np.uint8), qname_hash=z, cigar_off=cigar_off.astype(np.uint64),
+            base_off=(np.arange(n, dtype=np.uint64) * np.uint64(S)), cigar=cigar, seq4=_pack_nibbles(codes).reshape(-1),
+            qual=qual.reshape(-1), sa_pos=np.full(n, -1, dtype=np.int32), sa_start_adj=np.zeros(n, np.int32),
+            sa_end_adj=np.zeros(n, np.int32), sa_end_adj_indel=np.zeros(n, np.int32), sa_strand=np.zeros(n, np.uint8),
+            sa_mapq=np.full(n, -1, np.int16), sa_same_chr=np.zeros(n, np.uint8)).normalise()
+        return SynthContig(name=name, chars=chars, batch=batch, truth=truth)
     base = np.char.add(f"{name}.", pair_id.astype(str))
     if not spec.simple and spec.long_name_frac > 0:
         lp = rng.choice(n_pairs, max(1, int(n_pairs * spec.long_name_frac)), replace=False)
