@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(256) k_tile_index(const int32_t *pos, int64_t 
 //  * generic path (mismatches, non-ACGT codes, N/IUPAC reference letters): the reference's full rule including
 //    the read-name slots, evaluated in BAM order because the staged read list is in BAM order.
 struct PileAcc {
-    int m_hi, m_low, m_fs, m_pir;                       // reference-matching bases
+    int m_hi, m_low, m_fs, m_pir, m_all;                // reference-matching bases (m_low is derived: m_all - m_hi)
     int snv[4], low[4], pir[4], fs[4];                  // everything else
     int bq, bq_all, mq, mq_all;
     int rd_mq, rd_rd, rd_low;
@@ -292,9 +292,8 @@ __device__ __forceinline__ void pile_apply(PileAcc &a, int code, int qv, uint64_
     if (ref_acgt && code == rc4) {
         const int mq = misc & 0xff;
         const bool fwd = !(misc & PR_REV);
-        a.bq_all += qv; a.mq_all += mq;
+        a.bq_all += qv; a.mq_all += mq; a.m_all += 1;
         if (hi) { a.bq += qv; a.mq += mq; a.m_hi += 1; a.m_pir += fwd ? qi : lseq - qi; a.m_fs += fwd ? 1 : 0; }
-        else a.m_low += 1;
     } else {
         pile_generic(a, hash, misc, code, qv, qi, lseq, rc4, hi, min_snv);
     }
@@ -321,251 +320,254 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { while
 __device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 #define QCAP (CHUNK * 160)        // quality bytes per stage (64 reads of 2x150 data); the 4-bit area is half of it
-#define NSTAGE 3
-#define PILE_THREADS (TILE + 32)  // 8 consumer warps (one position per thread) + 1 producer warp
+#define NSTAGE 4
+#define NWARP (TILE / 32)         // consumer warps, one reference position per thread
+#define PILE_THREADS (TILE + 32)  // + 1 producer warp
+#define SUBTILES 8                // consecutive tiles handled by one CTA (keeps the producer pipeline full across tiles)
 
-// per-read record the producer warp leaves in shared memory for the position threads (2 x 16 bytes)
-#define SM_REV     0x100u         // read is on the reverse strand
-#define SM_MQOK    0x200u         // mapq >= -q
-#define SM_RDHI    0x400u         // mapq >= g_rd_min_mapq
-#define SM_INSIDE  0x800u         // single-M read whose op satisfies the CNV-depth bound pos + len < P (src/GROM.c:6625)
-#define SM_COMPLEX 0x1000u        // applied read with a general CIGAR
-#define SM_NAMEOK  0x2000u        // read name short enough to be stored (src/GROM.c:6810)
-#define SM_GLOBAL  0x4000u        // bases not staged (longer than a stage): read them from global memory
-struct __align__(16) StageA { int pos; uint32_t lq_fast; uint32_t qa; uint32_t sa; };       // lq_fast = 0 unless simple applied read
-struct __align__(16) StageB { uint32_t misc; int lq; uint64_t hash; };                      // misc = mapq | SM_*
-struct __align__(16) StageC { uint32_t cig_off, n_cigar, base16; int ext_end; };
+// Per staged read the producer warp leaves three 16-byte records of plain ints in shared memory so that the
+// position threads need no bit unpacking (all values are warp-uniform broadcasts):
+struct __align__(16) StageA { int pos; uint32_t lq_fast; uint32_t qa; uint32_t sa; };   // lq_fast = 0 unless single-M read fully inside the contig
+struct __align__(16) StageB { int mq; int bq_eff; int fwd01; int rdhi01; };             // bq_eff = -b if mapq >= -q else 256 (never reached)
+struct __align__(16) StageD { int pir_c; int pir_s; int lq; uint32_t flags; };          // position-in-read = off * pir_s + pir_c (src/GROM.c:6853-6864)
+struct __align__(16) StageC { uint64_t hash; uint32_t cig_off, n_cigar; };
+struct __align__(8)  StageE { uint32_t base16; int ext_end; };
+#define SF_COMPLEX 1u             // needs the general CIGAR walk (or CNV-depth bound fails, or bases are not staged)
+#define SF_GLOBAL  2u             // bases longer than a stage: read them from global memory
+#define SF_REV     4u
+#define SF_NAMEOK  8u
+#define SF_MQOK    16u
 
 struct __align__(128) PileSmem {
     uint8_t qual[NSTAGE][QCAP];
     uint8_t seq[NSTAGE][QCAP / 2];
     StageA a[NSTAGE][CHUNK];
     StageB b[NSTAGE][CHUNK];
+    StageD d[NSTAGE][CHUNK];
     StageC c[NSTAGE][CHUNK];
+    StageE e[NSTAGE][CHUNK];
+    int2 rng[NSTAGE][NWARP];      // per consumer warp: slice [t0, t1) of the staged reads that can reach its 32 positions
     uint64_t full[NSTAGE], empty[NSTAGE];
-    int cnt[NSTAGE], last[NSTAGE];
+    int last[NSTAGE];
 };
 
 __global__ void __launch_bounds__(PILE_THREADS) k_pileup(DevReads R, const PrepRec *__restrict__ prep, const int64_t *__restrict__ tile_first,
-                                                          const int *__restrict__ max_span_p,
+                                                          const int *__restrict__ max_span_p, int64_t n_tiles,
                                                           const char *__restrict__ fasta, int64_t P, int64_t Ppad, int32_t *__restrict__ arrays)
 {
     extern __shared__ __align__(128) uint8_t pile_smem_raw[];
     PileSmem &S = *reinterpret_cast<PileSmem *>(pile_smem_raw);
-    uint8_t (*s_qual)[QCAP] = S.qual;
-    uint8_t (*s_seq)[QCAP / 2] = S.seq;
-    StageA (*s_a)[CHUNK] = S.a;
-    StageB (*s_b)[CHUNK] = S.b;
-    StageC (*s_c)[CHUNK] = S.c;
-    int *s_cnt = S.cnt, *s_last = S.last;
-    uint64_t *s_full = S.full, *s_empty = S.empty;
-
-    const int64_t tile = blockIdx.x;
-    const int64_t tile_lo = tile * TILE, tile_hi = min(tile_lo + TILE, P);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int q = c_prm.min_mapq, bqmin = c_prm.min_base_qual, rdq = c_prm.rd_min_mapq, min_snv = min(c_prm.min_snv, 3);
+    const int64_t tile_begin = (int64_t)blockIdx.x * SUBTILES, tile_end = min(tile_begin + SUBTILES, n_tiles);
 
     if (threadIdx.x == 0) {
-        for (int k = 0; k < NSTAGE; k++) { mbar_init(smem_u32(&s_full[k]), 32); mbar_init(smem_u32(&s_empty[k]), TILE / 32); }
+        for (int k = 0; k < NSTAGE; k++) { mbar_init(smem_u32(&S.full[k]), 32); mbar_init(smem_u32(&S.empty[k]), NWARP); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int64_t first_read = tile_first[tile];
-    if (first_read >= R.n) {
-        // no read can reach this tile: the position threads still have to write their zeros
-        if (wid < TILE / 32) {
-            const int64_t p = tile_lo + threadIdx.x;
-            if (p < P) {
-                int32_t *o = arrays + p;
-                for (int k = 0; k < GA_PILEUP_COUNT; k++) o[(int64_t)k * Ppad] = 0;
-                o[(int64_t)GA_RD_MQ * Ppad] = 0; o[(int64_t)GA_RD_RD * Ppad] = 0; o[(int64_t)GA_RD_LOW * Ppad] = 0;
-            }
-        }
-        return;
-    }
 
-    if (wid == TILE / 32) {
-        // ================= producer warp: metadata + bulk copies (TMA) of the bases of up to CHUNK reads per stage
-        int64_t next = first_read;
-        for (int c = 0;; c++) {
-            const int buf = c % NSTAGE;
-            if (c >= NSTAGE) mbar_wait(smem_u32(&s_empty[buf]), (uint32_t)((c / NSTAGE - 1) & 1));
-            const int64_t i0 = next + 2 * lane, i1 = i0 + 1;
-            const bool v0 = i0 < R.n, v1 = i1 < R.n;
-            PrepRec r0, r1;
-            r0.pos = r1.pos = INT32_MAX; r0.misc = r1.misc = 0; r0.ext_end = r1.ext_end = INT32_MIN; r0.base16 = r1.base16 = 0;
-            r0.hash = r1.hash = 0; r0.cig_off = r1.cig_off = r0.n_cigar = r1.n_cigar = 0;
-            if (v0) r0 = prep[i0];
-            if (v1) r1 = prep[i1];
-            const bool use0 = v0 && (r0.misc & PR_APPLIED) && (int64_t)r0.ext_end > tile_lo && (int64_t)r0.pos < tile_hi;
-            const bool use1 = v1 && (r1.misc & PR_APPLIED) && (int64_t)r1.ext_end > tile_lo && (int64_t)r1.pos < tile_hi;
-            uint32_t sz0 = use0 ? (((r0.misc >> 16) + 31u) & ~31u) : 0u, sz1 = use1 ? (((r1.misc >> 16) + 31u) & ~31u) : 0u;
-            const bool big0 = sz0 > QCAP, big1 = sz1 > QCAP;        // longer than a whole stage: consumers read global memory
-            if (big0) sz0 = 0;
-            if (big1) sz1 = 0;
-            uint32_t incl = sz0 + sz1;
+    if (wid == NWARP) {
+        // ================= producer warp: for every tile, stream the reads that can reach it through the stage ring:
+        // per chunk up to CHUNK reads (two per lane), compacted to the applied reads that overlap the tile, metadata as
+        // plain ints + bulk copies (TMA) of their bases
+        const int max_span = *max_span_p;
+        int c = 0;
+        for (int64_t tile = tile_begin; tile < tile_end; tile++) {
+            const int64_t tile_lo = tile * TILE, tile_hi = min(tile_lo + TILE, P);
+            int64_t next = tile_first[tile];
+            for (;; c++) {
+                const int buf = c % NSTAGE;
+                if (c >= NSTAGE) mbar_wait(smem_u32(&S.empty[buf]), (uint32_t)((c / NSTAGE - 1) & 1));
+                const int64_t i0 = next + 2 * lane, i1 = i0 + 1;
+                const bool v0 = i0 < R.n, v1 = i1 < R.n;
+                PrepRec r0, r1;
+                r0.pos = r1.pos = INT32_MAX; r0.misc = r1.misc = 0; r0.ext_end = r1.ext_end = INT32_MIN; r0.base16 = r1.base16 = 0;
+                r0.hash = r1.hash = 0; r0.cig_off = r1.cig_off = r0.n_cigar = r1.n_cigar = 0;
+                if (v0) r0 = prep[i0];
+                if (v1) r1 = prep[i1];
+                const bool use0 = v0 && (r0.misc & PR_APPLIED) && (int64_t)r0.ext_end > tile_lo && (int64_t)r0.pos < tile_hi;
+                const bool use1 = v1 && (r1.misc & PR_APPLIED) && (int64_t)r1.ext_end > tile_lo && (int64_t)r1.pos < tile_hi;
+                uint32_t sz0 = use0 ? (((r0.misc >> 16) + 31u) & ~31u) : 0u, sz1 = use1 ? (((r1.misc >> 16) + 31u) & ~31u) : 0u;
+                const bool big0 = sz0 > QCAP, big1 = sz1 > QCAP;
+                if (big0) sz0 = 0;
+                if (big1) sz1 = 0;
+                uint32_t incl = sz0 + sz1;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-            const uint32_t off0 = incl - sz0 - sz1, off1 = off0 + sz0;
-            const bool fit0 = v0 && off0 + sz0 <= QCAP, fit1 = v1 && off1 + sz1 <= QCAP;
-            const unsigned b0 = __ballot_sync(0xffffffffu, fit0), b1 = __ballot_sync(0xffffffffu, fit1);
-            const int count = __popc(b0) + __popc(b1);
-            const unsigned anypast = __ballot_sync(0xffffffffu, (fit0 && (int64_t)r0.pos >= tile_hi) || (fit1 && (int64_t)r1.pos >= tile_hi));
-            uint32_t bytes = (fit0 ? sz0 + (sz0 >> 1) : 0u) + (fit1 ? sz1 + (sz1 >> 1) : 0u);
-            bytes = __reduce_add_sync(0xffffffffu, bytes);
-            const bool last = (anypast != 0u) || (next + count >= R.n);
-            const uint32_t bar = smem_u32(&s_full[buf]);
-            const uint32_t qbase = smem_u32(&s_qual[buf][0]), sbase = smem_u32(&s_seq[buf][0]);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const PrepRec &r = h ? r1 : r0;
-                const bool fit = h ? fit1 : fit0, use = h ? use1 : use0, big = h ? big1 : big0;
-                const uint32_t sz = h ? sz1 : sz0, off = h ? off1 : off0;
-                if (fit) {
-                    const int t = 2 * lane + h;
-                    const int mq = r.misc & 0xff, lq = (int)(r.misc >> 16);
-                    const bool simple = use && (r.misc & PR_SIMPLE);
-                    uint32_t misc = (uint32_t)mq;
-                    if (r.misc & PR_REV) misc |= SM_REV;
-                    if (mq >= q) misc |= SM_MQOK;
-                    if (mq >= rdq) misc |= SM_RDHI;
-                    if (simple && (int64_t)r.pos + lq < P) misc |= SM_INSIDE;
-                    if (use && !simple) misc |= SM_COMPLEX;
-                    if (r.misc & PR_NAMEOK) misc |= SM_NAMEOK;
-                    if (big) misc |= SM_GLOBAL;
-                    StageA A; A.pos = r.pos; A.lq_fast = (simple && !big) ? (uint32_t)lq : 0u; A.qa = qbase + off; A.sa = sbase + (off >> 1);
-                    StageB B; B.misc = misc; B.lq = lq; B.hash = r.hash;
-                    StageC C; C.cig_off = r.cig_off; C.n_cigar = r.n_cigar; C.base16 = r.base16; C.ext_end = use ? r.ext_end : INT32_MIN;
-                    s_a[buf][t] = A; s_b[buf][t] = B; s_c[buf][t] = C;
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                const uint32_t off0 = incl - sz0 - sz1, off1 = off0 + sz0;
+                const bool fit0 = v0 && off0 + sz0 <= QCAP, fit1 = v1 && off1 + sz1 <= QCAP;
+                const unsigned bf0 = __ballot_sync(0xffffffffu, fit0), bf1 = __ballot_sync(0xffffffffu, fit1);
+                const int count = __popc(bf0) + __popc(bf1);              // reads consumed from the stream
+                const unsigned anypast = __ballot_sync(0xffffffffu, (fit0 && (int64_t)r0.pos >= tile_hi) || (fit1 && (int64_t)r1.pos >= tile_hi));
+                const bool last = (anypast != 0u) || (next + count >= R.n);
+                const bool st0 = fit0 && use0, st1 = fit1 && use1;         // staged (compacted) reads
+                const unsigned bs0 = __ballot_sync(0xffffffffu, st0), bs1 = __ballot_sync(0xffffffffu, st1);
+                const unsigned lt = (1u << lane) - 1u;
+                const int idx0 = __popc(bs0 & lt) + __popc(bs1 & lt), idx1 = idx0 + (st0 ? 1 : 0);
+                uint32_t bytes = (st0 ? sz0 + (sz0 >> 1) : 0u) + (st1 ? sz1 + (sz1 >> 1) : 0u);
+                bytes = __reduce_add_sync(0xffffffffu, bytes);
+                const uint32_t bar = smem_u32(&S.full[buf]);
+                const uint32_t qbase = smem_u32(&S.qual[buf][0]), sbase = smem_u32(&S.seq[buf][0]);
+                // per consumer warp: staged reads with pos in (wlo - max_span, whi]
+                if (lane < NWARP) {
+                    // filled below by every lane cooperatively through ballots; placeholder to keep lanes converged
                 }
+#pragma unroll
+                for (int w = 0; w < NWARP; w++) {
+                    const int wlo = (int)tile_lo + 32 * w, key = wlo - max_span, whi = wlo + 31;
+                    const int t0 = __popc(__ballot_sync(0xffffffffu, st0 && r0.pos <= key)) + __popc(__ballot_sync(0xffffffffu, st1 && r1.pos <= key));
+                    const int t1 = __popc(__ballot_sync(0xffffffffu, st0 && r0.pos <= whi)) + __popc(__ballot_sync(0xffffffffu, st1 && r1.pos <= whi));
+                    if (lane == w) S.rng[buf][w] = make_int2(t0, t1);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const PrepRec &r = h ? r1 : r0;
+                    const bool st = h ? st1 : st0, big = h ? big1 : big0;
+                    const uint32_t off = h ? off1 : off0;
+                    const int t = h ? idx1 : idx0;
+                    if (st) {
+                        const int mq = r.misc & 0xff, lq = (int)(r.misc >> 16);
+                        const bool rev = r.misc & PR_REV;
+                        const bool fast = (r.misc & PR_SIMPLE) && !big && (int64_t)r.pos + lq < P;
+                        StageA A; A.pos = r.pos; A.lq_fast = fast ? (uint32_t)lq : 0u; A.qa = qbase + off; A.sa = sbase + (off >> 1);
+                        StageB B; B.mq = mq; B.bq_eff = (mq >= q) ? bqmin : 256; B.fwd01 = rev ? 0 : 1; B.rdhi01 = (mq >= rdq) ? 1 : 0;
+                        StageD D; D.pir_c = rev ? lq : 0; D.pir_s = rev ? -1 : 1; D.lq = lq;
+                        D.flags = (fast ? 0u : SF_COMPLEX) | (big ? SF_GLOBAL : 0u) | (rev ? SF_REV : 0u) | ((r.misc & PR_NAMEOK) ? SF_NAMEOK : 0u) | ((mq >= q) ? SF_MQOK : 0u);
+                        StageC C; C.hash = r.hash; C.cig_off = r.cig_off; C.n_cigar = r.n_cigar;
+                        StageE E; E.base16 = r.base16; E.ext_end = r.ext_end;
+                        S.a[buf][t] = A; S.b[buf][t] = B; S.d[buf][t] = D; S.c[buf][t] = C; S.e[buf][t] = E;
+                    }
+                }
+                if (lane == 0) { S.last[buf] = last ? 1 : 0; mbar_expect_tx(bar, bytes); }
+                else mbar_arrive(bar);
+                __syncwarp();
+                if (st0 && sz0) {
+                    bulk_g2s(qbase + off0, R.qual + ((uint64_t)r0.base16 << 4), sz0, bar);
+                    bulk_g2s(sbase + (off0 >> 1), R.seq4 + ((uint64_t)r0.base16 << 3), sz0 >> 1, bar);
+                }
+                if (st1 && sz1) {
+                    bulk_g2s(qbase + off1, R.qual + ((uint64_t)r1.base16 << 4), sz1, bar);
+                    bulk_g2s(sbase + (off1 >> 1), R.seq4 + ((uint64_t)r1.base16 << 3), sz1 >> 1, bar);
+                }
+                next += count;
+                if (last) { c++; break; }
             }
-            if (lane == 0) { s_cnt[buf] = count; s_last[buf] = last ? 1 : 0; mbar_expect_tx(bar, bytes); }
-            else mbar_arrive(bar);
-            __syncwarp();
-            if (fit0 && sz0) {
-                bulk_g2s(qbase + off0, R.qual + ((uint64_t)r0.base16 << 4), sz0, bar);
-                bulk_g2s(sbase + (off0 >> 1), R.seq4 + ((uint64_t)r0.base16 << 3), sz0 >> 1, bar);
-            }
-            if (fit1 && sz1) {
-                bulk_g2s(qbase + off1, R.qual + ((uint64_t)r1.base16 << 4), sz1, bar);
-                bulk_g2s(sbase + (off1 >> 1), R.seq4 + ((uint64_t)r1.base16 << 3), sz1 >> 1, bar);
-            }
-            if (last) break;
-            next += count;
         }
         return;
     }
 
     // ================= position threads
-    const int64_t p = tile_lo + threadIdx.x;
-    const bool live = p < P;
-    const int rc4 = live ? ref_code((unsigned char)fasta[p]) : 16;
-    const bool ref_acgt = (rc4 == 1 || rc4 == 2 || rc4 == 4 || rc4 == 8);
-    const int rc4m = ref_acgt ? rc4 : 99;                                  // never equals a 4-bit code
-    const int wlo = (int)(tile_lo + (threadIdx.x & ~31)), whi = wlo + 31;   // this warp's position window
     const int max_cig = c_prm.max_cigar_ops;
-    const int warp_key = wlo - *max_span_p;        // reads with pos <= warp_key cannot reach this warp
-    const int ip = (int)p;
-    PileAcc a;
-    a.m_hi = a.m_low = a.m_fs = a.m_pir = 0;
+    int c = 0;
+    for (int64_t tile = tile_begin; tile < tile_end; tile++) {
+        const int64_t tile_lo = tile * TILE;
+        const int64_t p = tile_lo + threadIdx.x;
+        const bool live = p < P;
+        const int rc4 = live ? ref_code((unsigned char)fasta[p]) : 16;
+        const bool ref_acgt = (rc4 == 1 || rc4 == 2 || rc4 == 4 || rc4 == 8);
+        const int rc4m = ref_acgt ? rc4 : 0x10;                                // 0x10: never equals a nibble
+        const int wlo = (int)(tile_lo + (threadIdx.x & ~31));
+        const int ip = (int)p;
+        PileAcc a;
+        a.m_hi = a.m_low = a.m_fs = a.m_pir = a.m_all = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) { a.snv[k] = a.low[k] = a.pir[k] = a.fs[k] = 0; }
-    a.bq = a.bq_all = a.mq = a.mq_all = a.rd_mq = a.rd_rd = a.rd_low = 0; a.nm0 = a.nm1 = a.nm2 = 0; a.nm_cnt = 0;
+        for (int k = 0; k < 4; k++) { a.snv[k] = a.low[k] = a.pir[k] = a.fs[k] = 0; }
+        a.bq = a.bq_all = a.mq = a.mq_all = a.rd_mq = a.rd_rd = a.rd_low = 0; a.nm0 = a.nm1 = a.nm2 = 0; a.nm_cnt = 0;
+        int rd_cnt = 0;
 
-    for (int c = 0;; c++) {
-        const int buf = c % NSTAGE;
-        mbar_wait(smem_u32(&s_full[buf]), (uint32_t)((c / NSTAGE) & 1));
-        const int cnt = s_cnt[buf];
-        const bool last = s_last[buf] != 0;
-        // this warp's slice [t0, t1) of the staged reads: pos in (warp_key, whi]  (positions are sorted)
-        int t0 = 0, t1 = 0;
-        { int hi_ = cnt; while (t0 < hi_) { const int mid = (t0 + hi_) >> 1; if (s_a[buf][mid].pos <= warp_key) t0 = mid + 1; else hi_ = mid; } }
-        { int lo_ = t0, hi_ = cnt; while (lo_ < hi_) { const int mid = (lo_ + hi_) >> 1; if (s_a[buf][mid].pos <= whi) lo_ = mid + 1; else hi_ = mid; } t1 = lo_; }
+        for (;; c++) {
+            const int buf = c % NSTAGE;
+            mbar_wait(smem_u32(&S.full[buf]), (uint32_t)((c / NSTAGE) & 1));
+            const bool last = S.last[buf] != 0;
+            const int2 rng = S.rng[buf][wid];
 #pragma unroll 2
-        for (int t = t0; t < t1; t++) {
-            const StageA A = s_a[buf][t];
-            const StageB B = s_b[buf][t];
-            const int mq = B.misc & 0xff;
-            const int off = ip - A.pos;
-            const bool hit = (unsigned)off < A.lq_fast;
-            const int offc = hit ? off : 0;
-            const int qv = lds_u8(A.qa + offc);
-            const int byte = lds_u8(A.sa + (offc >> 1));
-            const int code = (byte >> ((~offc & 1) << 2)) & 15;
-            const bool match = hit && code == rc4m;
-            const bool mh = match && (qv >= bqmin) && (B.misc & SM_MQOK);
-            const bool rev = B.misc & SM_REV;
-            a.bq_all += match ? qv : 0; a.mq_all += match ? mq : 0;
-            a.bq += mh ? qv : 0; a.mq += mh ? mq : 0;
-            a.m_hi += mh ? 1 : 0; a.m_low += (match && !mh) ? 1 : 0;
-            a.m_pir += mh ? (rev ? B.lq - offc : offc) : 0;
-            a.m_fs += (mh && !rev) ? 1 : 0;
-            const bool dep = hit && (B.misc & SM_INSIDE);
-            a.rd_mq += dep ? mq : 0;
-            a.rd_rd += (dep && (B.misc & SM_RDHI)) ? 1 : 0;
-            a.rd_low += (dep && !(B.misc & SM_RDHI)) ? 1 : 0;
-            if (hit && !match)
-                pile_generic(a, B.hash, (B.misc & 0xff) | (rev ? PR_REV : 0u) | ((B.misc & SM_NAMEOK) ? PR_NAMEOK : 0u), code, qv, off, B.lq, rc4,
-                             (qv >= bqmin) && (B.misc & SM_MQOK), min_snv);
-            if (B.misc & (SM_COMPLEX | SM_GLOBAL)) {
-                // general CIGAR (or unstaged bases): every lane walks the same op list; pileup offsets advance on
-                // M/=/X/D/N, CNV-depth offsets on M/=/X/D only (src/GROM.c:6621-6663), H extends lseq (6997-7000)
-                const StageC C = s_c[buf][t];
-                if (C.ext_end > wlo && live) {
-                    const bool glob = B.misc & SM_GLOBAL;
-                    const bool mq_ok = B.misc & SM_MQOK;
-                    const uint32_t gmisc = (B.misc & 0xff) | (rev ? PR_REV : 0u) | ((B.misc & SM_NAMEOK) ? PR_NAMEOK : 0u);
-                    const int ncig_all = (int)C.n_cigar, ncig = min(ncig_all, max_cig);
-                    int qi = 0, rp = A.pos, rdp = A.pos, lseq = B.lq;
-                    for (int k = 0; k < ncig_all; k++) {
-                        const uint32_t cg = __ldg(R.cigar + C.cig_off + k);
-                        const int op = cg & 15, len = (int)(cg >> 4);
-                        const bool in_pile = k < ncig;
-                        if (op == OP_M || op == OP_EQ || op == OP_X) {
-                            const int od = ip - rdp;
-                            if ((unsigned)od < (unsigned)len && rdp >= 0 && (int64_t)rdp + len < P) { a.rd_mq += mq; if (B.misc & SM_RDHI) a.rd_rd++; else a.rd_low++; }
-                            rdp += len;
-                            if (in_pile) {
-                                const int o = ip - rp;
-                                if ((unsigned)o < (unsigned)len && qi + o < B.lq) {
-                                    const int x = qi + o;
-                                    int qv2, byte2;
-                                    if (!glob) { qv2 = lds_u8(A.qa + x); byte2 = lds_u8(A.sa + (x >> 1)); }
-                                    else { const uint64_t slot = ((uint64_t)C.base16 << 4) + (uint64_t)x; qv2 = __ldg(R.qual + slot); byte2 = __ldg(R.seq4 + (slot >> 1)); }
-                                    const int code2 = (byte2 >> ((~x & 1) << 2)) & 15;
-                                    pile_apply(a, code2, qv2, B.hash, gmisc, x, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv);
+            for (int t = rng.x; t < rng.y; t++) {
+                const StageA A = S.a[buf][t];
+                const StageB B = S.b[buf][t];
+                const StageD D = S.d[buf][t];
+                const int off = ip - A.pos;
+                const bool hit = (unsigned)off < A.lq_fast;
+                const int offc = hit ? off : 0;
+                const int qv = lds_u8(A.qa + offc);
+                const int byte = lds_u8(A.sa + (offc >> 1));
+                const int x = ((byte >> ((~offc << 2) & 4)) & 15) ^ rc4m;
+                const bool match = hit && x == 0;
+                const bool mh = match && qv >= B.bq_eff;
+                const int hit01 = hit ? 1 : 0, m01 = match ? 1 : 0, mh01 = mh ? 1 : 0;
+                const int pv = off * D.pir_s + D.pir_c;
+                a.bq_all += m01 * qv; a.mq_all += m01 * B.mq; a.m_all += m01;
+                a.bq += mh01 * qv; a.mq += mh01 * B.mq; a.m_hi += mh01; a.m_pir += mh01 * pv; a.m_fs += mh01 * B.fwd01;
+                rd_cnt += hit01; a.rd_mq += hit01 * B.mq; a.rd_rd += hit01 * B.rdhi01;
+                if (hit && !match) {
+                    const StageC C = S.c[buf][t];
+                    const int code = (byte >> ((~offc << 2) & 4)) & 15;
+                    pile_generic(a, C.hash, (uint32_t)B.mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u), code, qv, off, D.lq, rc4,
+                                 qv >= B.bq_eff, min_snv);
+                }
+                if (D.flags & SF_COMPLEX) {
+                    // general CIGAR (or unstaged bases / depth bound not met): every lane walks the same op list; pileup offsets
+                    // advance on M/=/X/D/N, CNV-depth offsets on M/=/X/D only (src/GROM.c:6621-6663), H extends lseq (6997-7000)
+                    const StageC C = S.c[buf][t];
+                    const StageE E = S.e[buf][t];
+                    if (E.ext_end > wlo && live) {
+                        const bool glob = D.flags & SF_GLOBAL;
+                        const bool mq_ok = D.flags & SF_MQOK;
+                        const uint32_t gmisc = (uint32_t)B.mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u);
+                        const int ncig_all = (int)C.n_cigar, ncig = min(ncig_all, max_cig);
+                        int qi = 0, rp = A.pos, rdp = A.pos, lseq = D.lq;
+                        for (int k = 0; k < ncig_all; k++) {
+                            const uint32_t cg = __ldg(R.cigar + C.cig_off + k);
+                            const int op = cg & 15, len = (int)(cg >> 4);
+                            const bool in_pile = k < ncig;
+                            if (op == OP_M || op == OP_EQ || op == OP_X) {
+                                const int od = ip - rdp;
+                                if ((unsigned)od < (unsigned)len && rdp >= 0 && (int64_t)rdp + len < P) { a.rd_mq += B.mq; rd_cnt++; a.rd_rd += B.rdhi01; }
+                                rdp += len;
+                                if (in_pile) {
+                                    const int o = ip - rp;
+                                    if ((unsigned)o < (unsigned)len && qi + o < D.lq) {
+                                        const int xq = qi + o;
+                                        int qv2, byte2;
+                                        if (!glob) { qv2 = lds_u8(A.qa + xq); byte2 = lds_u8(A.sa + (xq >> 1)); }
+                                        else { const uint64_t slot = ((uint64_t)E.base16 << 4) + (uint64_t)xq; qv2 = __ldg(R.qual + slot); byte2 = __ldg(R.seq4 + (slot >> 1)); }
+                                        const int code2 = (byte2 >> ((~xq & 1) << 2)) & 15;
+                                        pile_apply(a, code2, qv2, C.hash, gmisc, xq, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv);
+                                    }
+                                    qi += len; rp += len;
                                 }
-                                qi += len; rp += len;
-                            }
-                        } else if (op == OP_D) { rdp += len; if (in_pile) rp += len; }
-                        else if (op == OP_N) { if (in_pile) rp += len; }
-                        else if (op == OP_I || op == OP_S) { if (in_pile) qi += len; }
-                        else if (op == OP_H) { if (in_pile) lseq += len; }
+                            } else if (op == OP_D) { rdp += len; if (in_pile) rp += len; }
+                            else if (op == OP_N) { if (in_pile) rp += len; }
+                            else if (op == OP_I || op == OP_S) { if (in_pile) qi += len; }
+                            else if (op == OP_H) { if (in_pile) lseq += len; }
+                        }
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.empty[buf]));
+            if (last) { c++; break; }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[buf]));
-        if (last) break;
-    }
-    if (live) {
-        // fold the matching-base registers into the per-base counters
-        const int rb = (rc4 == 1) ? 0 : (rc4 == 2) ? 1 : (rc4 == 4) ? 2 : 3;
+        if (live) {
+            // fold the matching-base registers into the per-base counters
+            a.m_low = a.m_all - a.m_hi;
+            a.rd_low += rd_cnt - a.rd_rd;
+            const int rb = (rc4 == 1) ? 0 : (rc4 == 2) ? 1 : (rc4 == 4) ? 2 : 3;
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (ref_acgt && rb == k) { a.snv[k] += a.m_hi; a.low[k] += a.m_low; a.pir[k] += a.m_pir; a.fs[k] += a.m_fs; }
-        int32_t *o = arrays + p;
-        const int tot = a.snv[0] + a.snv[1] + a.snv[2] + a.snv[3];
-        const int lowt = a.low[0] + a.low[1] + a.low[2] + a.low[3];
+            for (int k = 0; k < 4; k++) if (ref_acgt && rb == k) { a.snv[k] += a.m_hi; a.low[k] += a.m_low; a.pir[k] += a.m_pir; a.fs[k] += a.m_fs; }
+            int32_t *o = arrays + p;
+            const int tot = a.snv[0] + a.snv[1] + a.snv[2] + a.snv[3];
+            const int lowt = a.low[0] + a.low[1] + a.low[2] + a.low[3];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            o[(int64_t)(GA_SNV_A + k) * Ppad] = a.snv[k]; o[(int64_t)(GA_SNVLOW_A + k) * Ppad] = a.low[k];
-            o[(int64_t)(GA_PIR_A + k) * Ppad] = a.pir[k]; o[(int64_t)(GA_FS_A + k) * Ppad] = a.fs[k];
+            for (int k = 0; k < 4; k++) {
+                o[(int64_t)(GA_SNV_A + k) * Ppad] = a.snv[k]; o[(int64_t)(GA_SNVLOW_A + k) * Ppad] = a.low[k];
+                o[(int64_t)(GA_PIR_A + k) * Ppad] = a.pir[k]; o[(int64_t)(GA_FS_A + k) * Ppad] = a.fs[k];
+            }
+            o[(int64_t)GA_BQ * Ppad] = a.bq; o[(int64_t)GA_BQ_ALL * Ppad] = a.bq_all;
+            o[(int64_t)GA_MQ * Ppad] = a.mq; o[(int64_t)GA_MQ_ALL * Ppad] = a.mq_all;
+            o[(int64_t)GA_BQ_RC * Ppad] = tot; o[(int64_t)GA_MQ_RC * Ppad] = tot; o[(int64_t)GA_RC_ALL * Ppad] = tot + lowt;
+            o[(int64_t)GA_RD_MQ * Ppad] = a.rd_mq; o[(int64_t)GA_RD_RD * Ppad] = a.rd_rd; o[(int64_t)GA_RD_LOW * Ppad] = a.rd_low;
         }
-        o[(int64_t)GA_BQ * Ppad] = a.bq; o[(int64_t)GA_BQ_ALL * Ppad] = a.bq_all;
-        o[(int64_t)GA_MQ * Ppad] = a.mq; o[(int64_t)GA_MQ_ALL * Ppad] = a.mq_all;
-        o[(int64_t)GA_BQ_RC * Ppad] = tot; o[(int64_t)GA_MQ_RC * Ppad] = tot; o[(int64_t)GA_RC_ALL * Ppad] = tot + lowt;
-        o[(int64_t)GA_RD_MQ * Ppad] = a.rd_mq; o[(int64_t)GA_RD_RD * Ppad] = a.rd_rd; o[(int64_t)GA_RD_LOW * Ppad] = a.rd_low;
     }
 }
 
@@ -918,7 +920,7 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     CK(cudaEventRecord(h->ev[3], s));
     k_tile_index<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(R.pos, n, h->d_max_span, n_tiles, h->d_tile_first); launches++;
     CK(cudaEventRecord(h->ev[4], s));
-    k_pileup<<<(unsigned)n_tiles, PILE_THREADS, sizeof(PileSmem), s>>>(R, h->d_prep, h->d_tile_first, h->d_max_span, h->d_fasta, P, Ppad, h->d_arrays); launches++;
+    k_pileup<<<(unsigned)((n_tiles + SUBTILES - 1) / SUBTILES), PILE_THREADS, sizeof(PileSmem), s>>>(R, h->d_prep, h->d_tile_first, h->d_max_span, n_tiles, h->d_fasta, P, Ppad, h->d_arrays); launches++;
     CK(cudaEventRecord(h->ev[5], s));
     k_scan_inplace<<<(unsigned)n_scan_tiles, SCAN_THREADS, 0, s>>>(h->d_arrays + (int64_t)GA_RD * Ppad, Ppad, h->d_scan_status, h->d_ticket); launches++;
     CK(cudaEventRecord(h->ev[6], s));
