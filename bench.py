@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 METRIC = "aligned_bases_per_sec_hot_path"
 UNIT = "bases/s"
 N_ARRAYS_PILEUP = 26          # int32 arrays the pileup kernel writes per position (23 pileup + 3 CNV depth)
+N_ARRAYS_PILEUP_READ = 2      # rd and indel_sc_rd, read by the SNV gate fused into the pileup epilogue
 
 
 def parse():
@@ -208,7 +209,7 @@ def main_b200(a):
         if rank == 0:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        per = {k: 0.0 for k in ("ms_total", "ms_clear", "ms_dup", "ms_prep", "ms_index", "ms_pileup", "ms_rdscan", "ms_snvscan")}
+        per = {k: 0.0 for k in ("ms_total", "ms_clear", "ms_gc", "ms_dup", "ms_prep", "ms_index", "ms_rdscan", "ms_pileup")}
         launches = 0
         ev0.record(stream)
         for _ in range(a.steps):
@@ -256,8 +257,9 @@ def main_b200(a):
             peaks = json.load(open(pk_path))
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        # dominant kernel = pileup: algorithmic bytes = read records consumed + the 26 int32 arrays it writes + FASTA char
-        alg_bytes = st.bytes_reads + (4 * N_ARRAYS_PILEUP + 1) * P
+        # dominant kernel = pileup (+ fused SNV gate): algorithmic bytes = read records consumed + the 26 int32 arrays it writes
+        # + the 2 it reads for the gate + the FASTA char
+        alg_bytes = st.bytes_reads + (4 * (N_ARRAYS_PILEUP + N_ARRAYS_PILEUP_READ) + 1) * P
         ms_pile = per["ms_pileup"] / a.steps
         achieved = alg_bytes / (ms_pile * 1e-3) / 1e9
         traffic = None

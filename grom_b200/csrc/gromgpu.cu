@@ -786,6 +786,68 @@ __global__ void __launch_bounds__(256) k_snv_scan(const int32_t *__restrict__ ar
     if (lane == 0 && dcnt) { atomicAdd(depth_sum, dsum); atomicAdd(depth_sum + 1, (unsigned long long)dcnt); }
 }
 
+// ---- K5a: GC / ACGT percentage of the triangular window (src/GROM.c:1766-1859).  count(r) = sum_{|d|<M} (M-|d|) is(r+d)
+// is a second difference of the double prefix sum of the indicator, so each CTA scans a tile + halo of the FASTA in
+// shared memory twice (S1, then S2; tile-local constants cancel in the symmetric second difference).
+#define GC_TILE 2048
+#define GC_THREADS 256
+__device__ __forceinline__ int block_excl_scan_256(int v, int *s_w)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+    __syncthreads();
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < w; k++) base += s_w[k];
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(GC_THREADS) k_gc_prepass(const char *__restrict__ fasta, int64_t P, int M, int32_t *__restrict__ gc_out, int32_t *__restrict__ acgt_out)
+{
+    extern __shared__ int gc_smem[];
+    __shared__ int s_w[GC_THREADS / 32];
+    const int L = GC_TILE + 2 * M;                 // local index i <-> position tile_lo - M + i
+    int *sg = gc_smem, *sa = gc_smem + (L + 1);    // inclusive prefix arrays shifted by one (element 0 = 0)
+    const int64_t tile_lo = (int64_t)blockIdx.x * GC_TILE;
+    int seg = (L + GC_THREADS - 1) / GC_THREADS; seg |= 1;          // odd segment length: conflict-free strided access
+    const int i0 = threadIdx.x * seg, i1 = min(i0 + seg, L);
+    // pass 0: indicators -> S1
+    int tg = 0, ta = 0;
+    for (int i = i0; i < i1; i++) {
+        const int64_t x = tile_lo - M + i;
+        int g = 0, a = 0;
+        if (x >= 0 && x < P) { const char c = fasta[x]; g = (c == 'C' || c == 'G' || c == 'c' || c == 'g'); a = g || (c == 'A' || c == 'T' || c == 'a' || c == 't'); }
+        tg += g; ta += a; sg[i + 1] = tg; sa[i + 1] = ta;
+    }
+    int og = block_excl_scan_256(tg, s_w);
+    int oa = block_excl_scan_256(ta, s_w);
+    // pass 1: S1 -> S2 (in place)
+    tg = 0; ta = 0;
+    for (int i = i0; i < i1; i++) { tg += sg[i + 1] + og; ta += sa[i + 1] + oa; sg[i + 1] = tg; sa[i + 1] = ta; }
+    og = block_excl_scan_256(tg, s_w);
+    oa = block_excl_scan_256(ta, s_w);
+    for (int i = i0; i < i1; i++) { sg[i + 1] += og; sa[i + 1] += oa; }
+    if (threadIdx.x == 0) { sg[0] = 0; sa[0] = 0; }
+    __syncthreads();
+    const long long total = (long long)M * M;
+    const int64_t valid_lo = M - 1, valid_hi = P - (2 * (int64_t)M - 1);
+    for (int k = threadIdx.x; k < GC_TILE; k += GC_THREADS) {
+        const int64_t r = tile_lo + k;
+        if (r >= P) break;
+        int vg = 0, va = 0;
+        if (r >= valid_lo && r < valid_hi) {
+            const int ir = k + M;                   // local index of r; S2 inclusive at local j is s[j + 1]
+            const long long cg = (long long)(sg[ir + M] - sg[ir]) - (long long)(sg[ir] - sg[ir - M]);
+            const long long ca = (long long)(sa[ir + M] - sa[ir]) - (long long)(sa[ir] - sa[ir - M]);
+            vg = (int)(100 * cg / total); va = (int)(100 * ca / total);
+        }
+        gc_out[r] = vg; acgt_out[r] = va;
+    }
+}
+
 __global__ void k_fix_offsets(uint64_t *cigar_off, uint64_t *base_off, int64_t n, uint64_t cig_base, uint64_t slot_base)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1006,6 +1068,15 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     CK(cudaMemsetAsync(h->d_ncand, 0, sizeof(unsigned int), s));
     CK(cudaMemsetAsync(h->d_scan_status, 0, sizeof(unsigned long long) * (size_t)n_scan_tiles, s));
     CK(cudaEventRecord(h->ev[1], s));
+    {
+        const int M = g_params.insert_mean;
+        const size_t smem = sizeof(int) * 2 * (size_t)(GC_TILE + 2 * M + 1);
+        if (smem > 200 * 1024) return fail("gromgpu_chr_run: insert_mean %d too large for the GC pre-pass tile", M);
+        CK(cudaFuncSetAttribute(k_gc_prepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gc_prepass<<<(unsigned)((P + GC_TILE - 1) / GC_TILE), GC_THREADS, smem, s>>>(h->d_fasta, P, M, h->d_arrays + (int64_t)GA_GC * Ppad,
+                                                                                       h->d_arrays + (int64_t)GA_ACGT * Ppad); launches++;
+    }
+    CK(cudaEventRecord(h->ev[8], s));
     const unsigned rb = (unsigned)((n + 255) / 256);
     if (n) { k_read_state<<<rb, 256, 0, s>>>(R, h->tid, first_pos, h->d_state); launches++; }
     CK(cudaEventRecord(h->ev[2], s));
@@ -1028,7 +1099,8 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     gromgpu_stats &st = h->stats;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[7]); st.ms_total = ms;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); st.ms_clear = ms;
-    cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); st.ms_dup = ms;
+    cudaEventElapsedTime(&ms, h->ev[1], h->ev[8]); st.ms_gc = ms;
+    cudaEventElapsedTime(&ms, h->ev[8], h->ev[2]); st.ms_dup = ms;
     cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); st.ms_prep = ms;
     cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); st.ms_index = ms;
     cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); st.ms_rdscan = ms;

@@ -25,11 +25,12 @@ _LIB = None
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_clear", C.c_float), ("ms_dup", C.c_float), ("ms_prep", C.c_float),
                 ("ms_index", C.c_float), ("ms_pileup", C.c_float), ("ms_rdscan", C.c_float), ("ms_snvscan", C.c_float),
+                ("ms_gc", C.c_float), ("reserved_f", C.c_float),
                 ("launches", C.c_int32), ("reserved", C.c_int32), ("n_reads", C.c_int64), ("n_applied", C.c_int64),
                 ("n_dups", C.c_int64), ("aligned_bases", C.c_int64), ("bytes_reads", C.c_int64)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
 
 
 class CResult(C.Structure):

@@ -43,7 +43,9 @@ typedef struct gromgpu_stats {
     float ms_index;             /* tile -> first-read index */
     float ms_pileup;            /* pileup + CNV depth            (6605-6671, 6740-7059) */
     float ms_rdscan;            /* range-add prefix scan -> rd   (7176-7181) */
-    float ms_snvscan;           /* per-position SNV gate + compaction (11096-11199) */
+    float ms_snvscan;           /* per-position SNV gate + compaction (11096-11199); 0 when fused into the pileup epilogue */
+    float ms_gc;                /* GC / ACGT triangular-window percentages (1766-1859) */
+    float reserved_f;
     int32_t launches;           /* kernels launched by the run */
     int32_t reserved;
     int64_t n_reads, n_applied, n_dups, aligned_bases;

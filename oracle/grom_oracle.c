@@ -270,6 +270,7 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
             out->snv_ave_rd = (double)tot / (double)cntb;
         }
     }
+    oracle_gc_prepass(p, fasta, P, A.a[GA_GC], A.a[GA_ACGT]);
     free(nm_hash); free(nm_cnt); free(dl); free(c_type); free(c_len);
     return 0;
 }
@@ -302,9 +303,30 @@ int64_t oracle_format_snv_vcf(const grom_params *p, const char *chr_name, const 
     return w;
 }
 
+/* GC / ACGT percentage of the triangular window of half-width insert_mean centred on each position
+ * (src/GROM.c:1766-1859).  The reference updates the weighted counts incrementally; the closed form is
+ * count(r) = sum_{|d| < M} (M - |d|) * is(r + d), M = insert_mean, defined for r in [M-1, P-(2M-1));
+ * value = 100 * count / M^2 (integer division).  Positions outside that range are never written by the
+ * reference (malloc'ed memory); they are reported as 0 here. */
 void oracle_gc_prepass(const grom_params *p, const char *fasta, int64_t chr_len, int32_t *gc, int32_t *acgt)
 {
-    (void)p; (void)fasta;
+    const int64_t M = p->insert_mean, W1 = 2 * M - 1, total = M * M;
     memset(gc, 0, sizeof(int32_t) * (size_t)chr_len);
     memset(acgt, 0, sizeof(int32_t) * (size_t)chr_len);
+    if (chr_len < W1 + M) return;
+    /* S1g[i] = number of G/C in fasta[0..i), likewise for A/C/G/T */
+    int64_t *s1g = (int64_t *)calloc((size_t)chr_len + 1, sizeof(int64_t)), *s1a = (int64_t *)calloc((size_t)chr_len + 1, sizeof(int64_t));
+    for (int64_t i = 0; i < chr_len; i++) {
+        char c = fasta[i];
+        int g = (c == 'C' || c == 'G' || c == 'c' || c == 'g');
+        int a = g || (c == 'A' || c == 'T' || c == 'a' || c == 't');
+        s1g[i + 1] = s1g[i] + g; s1a[i + 1] = s1a[i] + a;
+    }
+    for (int64_t r = M - 1; r < chr_len - W1; r++) {
+        /* sum_{j=0}^{M-1} (S1[r+j+1] - S1[r+j+1-M]) */
+        int64_t cg = 0, ca = 0;
+        for (int64_t j = 0; j < M; j++) { cg += s1g[r + j + 1] - s1g[r + j + 1 - M]; ca += s1a[r + j + 1] - s1a[r + j + 1 - M]; }
+        gc[r] = (int32_t)(100 * cg / total); acgt[r] = (int32_t)(100 * ca / total);
+    }
+    free(s1g); free(s1a);
 }

@@ -45,6 +45,8 @@ def lib() -> C.CDLL:
         L.oracle_format_snv_vcf.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64,
                                             C.c_double, C.c_char_p, C.c_int64]
         L.oracle_format_snv_vcf.restype = C.c_int64
+        L.oracle_gc_prepass.argtypes = [C.POINTER(Params), C.c_char_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.oracle_gc_prepass.restype = None
         _LIB = L
     return _LIB
 
@@ -92,6 +94,15 @@ def format_snv_vcf(params: Params, chr_name: str, fasta: np.ndarray, snv: np.nda
                                     len(s), ave_rd, buf, cap)
     assert n >= 0
     return buf.raw[:n].decode()
+
+
+def gc_prepass(params: Params, fasta: np.ndarray):
+    """(gc_weighted, acgt_weighted) int32 arrays (reference src/GROM.c:1766-1859)."""
+    fa = np.ascontiguousarray(fasta, dtype=np.uint8)
+    P = int(fa.shape[0])
+    gc = np.zeros(P, dtype=np.int32); acgt = np.zeros(P, dtype=np.int32)
+    lib().oracle_gc_prepass(C.byref(params), fa.ctypes.data_as(C.c_char_p), P, gc.ctypes.data, acgt.ctypes.data)
+    return gc, acgt
 
 
 # ---------------------------------------------------------------- reference runners

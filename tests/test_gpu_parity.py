@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from util import CHECKED, CLIPS, DEPTH, GOLDEN, PILEUP, assert_arrays_equal, golden_batches, golden_params, load_golden_fasta, tables, tables_7digit
+from util import CHECKED, CLIPS, DEPTH, GCS, GOLDEN, PILEUP, assert_arrays_equal, golden_batches, golden_params, load_golden_fasta, tables, tables_7digit
 from grom_b200 import gpu
 from grom_b200.params import GA, GA_NAMES, Params
 from grom_b200.reads import CDEL, CHARD_CLIP, CINS, CMATCH, CREF_SKIP, CSOFT_CLIP, FPAIRED, FREVERSE, FMREVERSE
@@ -58,6 +58,10 @@ def test_gpu_reproduces_reference_golden(tag, rmdup):
         depth = g[f"{n}_depth"]
         for j, k in enumerate(DEPTH):
             assert np.array_equal(got[k], depth[j]), (n, GA_NAMES[k])
+        gcd = g[f"{n}_gc"]
+        M = prm.insert_mean
+        lo, hi = M - 1, len(fasta[name]) - (2 * M - 1)
+        assert np.array_equal(got[GA["gc"]][lo:hi], gcd[0][lo:hi]) and np.array_equal(got[GA["acgt"]][lo:hi], gcd[1][lo:hi])
         reads = g[f"{n}_reads"]
         proc = np.nonzero(state > 0)[0]
         assert np.array_equal(batches[tid].pos[proc], reads["pos"])
@@ -106,12 +110,12 @@ def test_empty_and_all_skipped_inputs():
     with gpu.Chromosome(0, fa) as ch:          # no reads at all
         res = ch.finish()
         assert (res.scan_first, res.scan_last, len(res.snv)) == (-1, -1, 0)
-        assert not ch.fetch_all()[CHECKED].any()
+        assert not ch.fetch_all()[PILEUP + CLIPS + DEPTH].any()
     # every read before W/4+1: nothing is applied, nothing is scanned (reference src/GROM.c:6406)
     recs = [dict(pos=p, cigar=[(CMATCH, 50)], seq="ACGTA" * 10) for p in (10, 500, 3000)]
     b = synth.batch_from_records(0, recs)
     res, got, state, st, ref = check_against_oracle(prm, b, fa, hez, mq)
-    assert res.scan_first == -1 and not state.any() and not got[CHECKED].any()
+    assert res.scan_first == -1 and not state.any() and not got[PILEUP + CLIPS + DEPTH].any()
 
 
 def test_edge_cigars_and_ragged_reads():

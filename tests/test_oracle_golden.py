@@ -37,6 +37,10 @@ def test_oracle_reproduces_reference_dumps(data, tag, rmdup):
         depth = g[f"{n}_depth"]
         for j, k in enumerate(("rd_mq", "rd_rd", "rd_low")):
             assert np.array_equal(r[k], depth[j]), (n, k)
+        gcd = g[f"{n}_gc"]
+        M = prm.insert_mean
+        lo, hi = M - 1, len(fasta[name]) - (2 * M - 1)      # the reference writes only this range (src/GROM.c:1684)
+        assert np.array_equal(r["gc"][lo:hi], gcd[0][lo:hi]) and np.array_equal(r["acgt"][lo:hi], gcd[1][lo:hi])
         reads = g[f"{n}_reads"]
         proc = np.nonzero(r.read_state > 0)[0]
         assert len(proc) == len(reads)

@@ -16,7 +16,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 PILEUP = list(range(0, 23))
 CLIPS = list(range(24, 39))
 DEPTH = [GA["rd_mq"], GA["rd_rd"], GA["rd_low"]]
-CHECKED = PILEUP + CLIPS + DEPTH
+GCS = [GA["gc"], GA["acgt"]]
+CHECKED = PILEUP + CLIPS + DEPTH + GCS
 
 
 def load_golden_fasta():
