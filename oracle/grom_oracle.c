@@ -13,7 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include "grom_oracle.h"
+#include "grom_oracle_int.h"
 
 #define F_PAIRED 1
 #define F_UNMAP 4
@@ -27,7 +27,6 @@ enum { SV_DEL = 0, SV_DUP = 1, SV_INV_F = 8, SV_INV_R = 9, SV_CTX_FF = 11, SV_CT
 
 static const char NT16[] = "=ACMGRSVTWYHKDBN";
 
-typedef struct { int64_t len; int32_t *a[GA_COUNT]; } arrs;
 
 static inline int base_code(const grom_read_batch *b, int64_t i, int k)
 {
@@ -75,6 +74,15 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
     const int NS = p->min_snv;
     uint64_t *nm_hash = (uint64_t *)calloc((size_t)P * NS, sizeof(uint64_t));
     uint8_t *nm_cnt = (uint8_t *)calloc((size_t)P, 1);
+
+    svctx S; memset(&S, 0, sizeof(S));
+    S.p = p; S.P = P; S.A = &A; S.W = W;
+    for (int k = 0; k < CL_COUNT; k++) {
+        S.cw[k] = (int32_t *)calloc((size_t)P, 4); S.crs[k] = (int32_t *)calloc((size_t)P, 4); S.cre[k] = (int32_t *)calloc((size_t)P, 4);
+        S.cdist[k] = (double *)calloc((size_t)P, 8);
+    }
+    S.cmchr[0] = (int32_t *)calloc((size_t)P, 4); S.cmchr[1] = (int32_t *)calloc((size_t)P, 4);
+    S.oth = (oslot **)calloc((size_t)P, sizeof(oslot *));
 
     dupkey *dl = (dupkey *)malloc(sizeof(dupkey) * (size_t)p->rmdup_list_len);
     int dl_n = 0, old_pos = -1;
@@ -214,6 +222,22 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
         }
 #undef BUMP
         for (int64_t x = pos; x < rend; x++) if (x >= 0 && x < P) A.a[GA_RD][x] += 1;
+        /* ---- small indels, split reads, pair ranges (grom_oracle_sv.c) */
+        {
+            svread r;
+            r.tid = b->tid; r.pos = pos; r.mpos = mpos; r.mtid = mtid; r.tlen = tlen; r.flag = flag; r.mapq = mq; r.add = add;
+            r.lseq = lseq; r.start_adj = start_adj; r.end_adj = end_adj; r.end_adj_indel = end_adj_indel;
+            r.cigar = cg; r.n_cigar = ncig;
+            r.sa_pos = b->sa_pos[i]; r.sa_strand = b->sa_strand[i]; r.sa_mapq = b->sa_mapq[i]; r.sa_same = b->sa_same_chr[i];
+            r.sa_start_adj = b->sa_start_adj[i]; r.sa_end_adj = b->sa_end_adj[i]; r.sa_end_adj_indel = b->sa_end_adj_indel[i];
+            if (!p->splitread) r.sa_pos = -1;
+            /* window geometry when this read is applied: scan position = max(pos - ins_max, W/4+1), window index advances once
+             * per loop iteration incl. the skipped leading reads and wraps 3W/4 -> W/4 (src/GROM.c:5845-5847, 6317, 6408-6411) */
+            int64_t pproc = (int64_t)pos - (int64_t)p->overlap_mult * p->insert_max; if (pproc < first_pos) pproc = first_pos;
+            int64_t idx = W / 4 + ((i0 + 2 + (pproc - first_pos)) % (W / 2));
+            r.win_lo = pproc - idx;
+            sv_evidence_read(&S, &r);
+        }
     }
 
     /* ---- scanned range and look-ahead read length (src/GROM.c:6406-6411, 11075-11086) */
@@ -271,6 +295,20 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
         }
     }
     oracle_gc_prepass(p, fasta, P, A.a[GA_GC], A.a[GA_ACGT]);
+    for (int k = 0; k < CL_COUNT; k++) {
+        if (out->cl_w) memcpy(out->cl_w + (size_t)k * P, S.cw[k], (size_t)P * 4);
+        if (out->cl_rs) memcpy(out->cl_rs + (size_t)k * P, S.crs[k], (size_t)P * 4);
+        if (out->cl_re) memcpy(out->cl_re + (size_t)k * P, S.cre[k], (size_t)P * 4);
+        if (out->cl_dist) memcpy(out->cl_dist + (size_t)k * P, S.cdist[k], (size_t)P * 8);
+        free(S.cw[k]); free(S.crs[k]); free(S.cre[k]); free(S.cdist[k]);
+    }
+    for (int k = 0; k < 2; k++) { if (out->cl_mchr) memcpy(out->cl_mchr + (size_t)k * P, S.cmchr[k], (size_t)P * 4); free(S.cmchr[k]); }
+    for (int64_t x = 0; x < P; x++) {
+        int ol = 0;
+        if (S.oth[x]) { while (ol < p->other_len && S.oth[x][ol].type != OTHER_EMPTY) ol++; free(S.oth[x]); }
+        if (out->other_len) out->other_len[x] = ol;
+    }
+    free(S.oth);
     free(nm_hash); free(nm_cnt); free(dl); free(c_type); free(c_len);
     return 0;
 }

@@ -33,6 +33,13 @@ typedef struct oracle_chr_out {
     grom_snv_cand *snv;         /* caller-allocated [snv_cap] */
     int64_t  snv_cap, n_snv;
     double   snv_ave_rd;        /* mean depth used by the SNV emission filter (src/GROM.c:15035-15043) */
+    /* breakpoint clusters, 10 classes in the order del_f del_r dup_f dup_r inv_f1 inv_r1 inv_f2 inv_r2 ctx_f ctx_r
+     * (src/GROM.c:7955-10953); all caller-allocated, NULL = not wanted */
+    int32_t *cl_w;              /* [10][chr_len] weight */
+    int32_t *cl_rs, *cl_re;     /* [10][chr_len] first / last read position */
+    double  *cl_dist;           /* [10][chr_len] running-mean distance (ctx: signed mate position) */
+    int32_t *cl_mchr;           /* [2][chr_len]  mate contig of ctx_f / ctx_r */
+    int32_t *other_len;         /* [chr_len] index of the first empty `other` slot */
 } oracle_chr_out;
 
 int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *fasta, int64_t chr_len,

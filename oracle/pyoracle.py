@@ -27,7 +27,9 @@ READS_DTYPE = np.dtype([("pos", np.int32), ("mpos", np.int32), ("tlen", np.int32
 class COut(C.Structure):
     _fields_ = [("chr_len", C.c_int64), ("arrays", C.c_void_p), ("read_state", C.c_void_p),
                 ("scan_first", C.c_int32), ("scan_last", C.c_int32), ("lookahead_lseq", C.c_void_p),
-                ("snv", C.c_void_p), ("snv_cap", C.c_int64), ("n_snv", C.c_int64), ("snv_ave_rd", C.c_double)]
+                ("snv", C.c_void_p), ("snv_cap", C.c_int64), ("n_snv", C.c_int64), ("snv_ave_rd", C.c_double),
+                ("cl_w", C.c_void_p), ("cl_rs", C.c_void_p), ("cl_re", C.c_void_p), ("cl_dist", C.c_void_p),
+                ("cl_mchr", C.c_void_p), ("other_len", C.c_void_p)]
 
 
 _LIB = None
@@ -60,6 +62,12 @@ class OracleResult:
     lookahead_lseq: np.ndarray
     snv: np.ndarray             # SNV_CAND_DTYPE
     snv_ave_rd: float
+    cl_w: np.ndarray = None     # [10, P] cluster weights (del_f del_r dup_f dup_r inv_f1 inv_r1 inv_f2 inv_r2 ctx_f ctx_r)
+    cl_rs: np.ndarray = None
+    cl_re: np.ndarray = None
+    cl_dist: np.ndarray = None  # [10, P] float64
+    cl_mchr: np.ndarray = None  # [2, P]
+    other_len: np.ndarray = None
 
     def __getitem__(self, name: str) -> np.ndarray:
         return self.arrays[GA[name]]
@@ -72,8 +80,11 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
     state = np.zeros(max(1, batch.n_reads), dtype=np.uint8)
     look = np.zeros(P, dtype=np.int32)
     snv = np.zeros(snv_cap, dtype=SNV_CAND_DTYPE)
+    cl_w = np.zeros((10, P), dtype=np.int32); cl_rs = np.zeros((10, P), dtype=np.int32); cl_re = np.zeros((10, P), dtype=np.int32)
+    cl_dist = np.zeros((10, P), dtype=np.float64); cl_mchr = np.zeros((2, P), dtype=np.int32); other_len = np.zeros(P, dtype=np.int32)
     out = COut(chr_len=P, arrays=arrays.ctypes.data, read_state=state.ctypes.data, lookahead_lseq=look.ctypes.data,
-               snv=snv.ctypes.data, snv_cap=snv_cap)
+               snv=snv.ctypes.data, snv_cap=snv_cap, cl_w=cl_w.ctypes.data, cl_rs=cl_rs.ctypes.data, cl_re=cl_re.ctypes.data,
+               cl_dist=cl_dist.ctypes.data, cl_mchr=cl_mchr.ctypes.data, other_len=other_len.ctypes.data)
     cb = batch.as_c()
     fa = np.ascontiguousarray(fasta, dtype=np.uint8)
     rc = lib().oracle_run_chr(C.byref(params), C.byref(cb), fa.ctypes.data_as(C.c_char_p), P,
@@ -82,7 +93,7 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
         raise RuntimeError(f"oracle_run_chr failed: {rc}")
     assert out.n_snv <= snv_cap
     return OracleResult(arrays, state[:batch.n_reads], out.scan_first, out.scan_last, look, snv[:out.n_snv].copy(),
-                        out.snv_ave_rd)
+                        out.snv_ave_rd, cl_w, cl_rs, cl_re, cl_dist, cl_mchr, other_len)
 
 
 def format_snv_vcf(params: Params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, ave_rd: float) -> str:

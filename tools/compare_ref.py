@@ -1,0 +1,65 @@
+"""Development aid: run the white-box reference with dump hooks on a synthetic data set and compare every dumped
+per-position value with the oracle (needs oracle/_ref/GROM_ref; build container only)."""
+import argparse, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from grom_b200 import hostlib
+from grom_b200.params import GA_NAMES, Params
+from oracle import pyoracle as po
+from tools import synth
+
+CL = ["del_f", "del_r", "dup_f", "dup_r", "inv_f1", "inv_r1", "inv_f2", "inv_r2", "ctx_f", "ctx_r"]
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--seed", type=int, default=7)
+ap.add_argument("--rmdup", type=int, default=0)
+ap.add_argument("--sa", type=float, default=0.5)
+ap.add_argument("--disc", type=float, default=0.03)
+ap.add_argument("--len", type=int, default=300000)
+ap.add_argument("--sv", type=float, default=10.0)
+a = ap.parse_args()
+spec = synth.SynthSpec(contigs=[("chrA", a.len), ("chrB", a.len // 2), ("chrZ", 50000)], depth=30, seed=a.seed, dup_frac=0.05,
+                       sa_frac=a.sa, disc_frac=a.disc, sv_sites_per_mb=a.sv, munmap_frac=0.01)
+cs = synth.simulate(spec)
+fa, bam = synth.write_dataset("/tmp/cmpref", cs)
+dump = "/tmp/cmpref_dump"
+os.system(f"rm -rf {dump}")
+po.run_reference(bam, fa, "/tmp/cmpref.vcf", args=(["-M"] if a.rmdup else []), dump_dir=dump)
+m = po.read_mean_file(bam)
+print(m)
+prm = Params.default(insert_mean=max(m["insert_mean"], m["lseq"]), insert_min=m["insert_min"], insert_max=m["insert_max"], lseq=m["lseq"], rmdup=a.rmdup)
+hez, mq = po.reference_tables(20)
+bad_total = 0
+with hostlib.Bam(bam) as b:
+    for tid, c in enumerate(cs):
+        batch = b.read_target(tid)
+        name = c.name.lower()
+        r = po.run_chr(prm, batch, c.chars, hez, mq)
+        sd = po.load_scan_dump(dump, name)
+        pos = sd["pos"]
+        print(name, "scan", r.scan_first, r.scan_last, "dump", pos[0], pos[-1])
+        for k in range(51):
+            mine, ref = r.arrays[k][pos], sd["v"][:, k]
+            nb = int((mine != ref).sum())
+            if nb:
+                j = np.nonzero(mine != ref)[0][:3]; bad_total += nb
+                print(f"  {GA_NAMES[k]:16s} mismatches {nb:7d}  pos {pos[j]} mine {mine[j]} ref {ref[j]}")
+        for k, cn in enumerate(CL):
+            for nm, mine, ref in (("w", r.cl_w[k][pos], sd["v"][:, 51 + 3 * k]), ("rs", r.cl_rs[k][pos], sd["v"][:, 52 + 3 * k]),
+                                  ("re", r.cl_re[k][pos], sd["v"][:, 53 + 3 * k]), ("dist", r.cl_dist[k][pos], sd["d"][:, k])):
+                # read_start/end/dist are only meaningful where the cluster exists
+                live = (r.cl_w[k][pos] != 0) | (sd["v"][:, 51 + 3 * k] != 0) if nm != "w" else np.ones(len(pos), bool)
+                bad = np.nonzero((mine != ref) & live)[0]
+                if bad.size:
+                    bad_total += bad.size
+                    print(f"  {cn}.{nm:5s} mismatches {bad.size:7d}  pos {pos[bad[:3]]} mine {mine[bad[:3]]} ref {ref[bad[:3]]}   (nonzero ref {int((sd['v'][:, 51 + 3 * k] != 0).sum())})")
+        for k, cn in enumerate(("ctx_f", "ctx_r")):
+            live = r.cl_w[8 + k][pos] != 0
+            bad = np.nonzero((r.cl_mchr[k][pos] != sd["v"][:, 81 + k]) & live)[0]
+            if bad.size:
+                print(f"  {cn}.mchr mismatches {bad.size}"); bad_total += bad.size
+        bad = np.nonzero(r.other_len[pos] != sd["v"][:, 83])[0]
+        if bad.size:
+            bad_total += bad.size
+            print(f"  other_len mismatches {bad.size} pos {pos[bad[:3]]} mine {r.other_len[pos][bad[:3]]} ref {sd['v'][:, 83][bad[:3]]}  (max ref {sd['v'][:, 83].max()})")
+print("TOTAL MISMATCHES", bad_total)

@@ -56,6 +56,7 @@ class SynthSpec:
     n_frac: float = 0.01
     lower_frac: float = 0.1
     long_name_frac: float = 0.0005
+    sa_frac: float = 0.5            # fraction of (>= 20 bp) soft-clipped reads that carry an SA tag
     simple: bool = False            # bench mode: only the vectorised read classes
     names: bool = True              # False: no read-name strings (hash only; such a batch cannot be written as BAM)
 
@@ -298,7 +299,7 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
                 pos[i] += k; mpos[mate(i)] = pos[i] if not (flag[mate(i)] & FUNMAP) and mtid[mate(i)] == tid and not (flag[mate(i)] & FMUNMAP) else mpos[mate(i)]
             else:
                 codes[i, rl - k:rl] = junk; cig[i] = [(CMATCH, rl - k), (CSOFT_CLIP, k)]
-            if rng.random() < 0.5 and k >= 20:
+            if rng.random() < spec.sa_frac and k >= 20:
                 sa_pos = int(pos[i] + rng.integers(-3000, 3000)); sa_pos = max(1, sa_pos)
                 strand = "+" if ((flag[i] & FREVERSE) == 0) == (rng.random() < 0.8) else "-"
                 sa_cig = f"{rl - k}S{k}M" if not leftside else f"{k}M{rl - k}S"
