@@ -199,6 +199,9 @@ void sv_evidence_read(svctx *c, const svread *r)
         }
     }
 
+    /* ---- split-read deletions, src/GROM.c:7425-7950 */
+    sv_split_del(c, r);
+
     /* ---- pairs, src/GROM.c:7963-10953 */
     clu u; memset(&u, 0, sizeof(u)); u.v = pos; u.mode = RS_SET_RE; u.tol = tol;
     if (paired && !munmap) {
@@ -300,6 +303,123 @@ void sv_evidence_read(svctx *c, const svread *r)
 #undef MIN2
 }
 
-/* split-read tandem-duplication evidence: filled in with the split-read restatement (returns 0 = not a split dup) */
-int sv_split_dup_fwd(svctx *c, const svread *r) { (void)c; (void)r; return 0; }
-void sv_split_dup_rev(svctx *c, const svread *r) { (void)c; (void)r; }
+/* ---- split reads (first SA/XP entry on this contig), src/GROM.c:7425-7950, 7978-8340, 9361-9722 ---- */
+
+static int sa_usable(const svctx *c, const svread *r)
+{
+    return r->sa_pos >= 0 && r->sa_same && r->sa_mapq >= c->p->min_mapq && r->mapq >= c->p->min_mapq;
+}
+
+/* split-read deletion: small gaps also feed the small-indel slots, every gap feeds del_f / del_r with
+ * x = gap + insert_mean (src/GROM.c:7425-7950) */
+void sv_split_del(svctx *c, const svread *r)
+{
+    const grom_params *p = c->p;
+    if (!(r->sa_pos >= 0 && r->sa_same)) return;
+    if (!(r->sa_mapq >= p->min_mapq && r->mapq >= p->min_mapq)) return;
+    const int flag = r->flag, rev = (flag & 16) != 0;
+    const int paired_same = (flag & 1) && !(flag & 8) && r->tid == r->mtid;
+    const int pos = r->pos, apos = r->sa_pos, lseq = r->lseq;
+    const int64_t E = (int64_t)pos - r->start_adj + lseq - r->end_adj - r->end_adj_indel;
+    const int64_t AE = (int64_t)apos - r->sa_start_adj + lseq - r->sa_end_adj - r->sa_end_adj_indel;
+    int sr_del = 0; int64_t S = 0, Eo = 0;
+    if (!((!rev && r->sa_strand == 0) || (rev && r->sa_strand == 1))) return;
+    if (paired_same) {
+        if (!rev && r->sa_strand == 0) {
+            if (pos < apos && r->tlen <= p->insert_max && apos < r->mpos) {
+                if (apos - E < p->insert_max && apos - E > 0) {
+                    if (abs(lseq - r->end_adj - r->sa_start_adj) <= p->max_split_loss && lseq - r->start_adj - r->end_adj - r->end_adj_indel >= p->min_sr_len &&
+                        lseq - r->sa_start_adj - r->sa_end_adj - r->sa_end_adj_indel >= p->min_sr_len) { sr_del = 1; S = E; Eo = apos; }
+                }
+            }
+        } else if (rev && r->sa_strand == 1) {
+            if (apos < pos && abs(r->tlen) < p->insert_max && r->mpos < apos) {
+                if (abs(lseq - r->start_adj - r->sa_end_adj) <= p->max_split_loss && lseq - r->start_adj - r->end_adj - r->end_adj_indel >= p->min_sr_len &&
+                    lseq - r->sa_start_adj - r->sa_end_adj - r->sa_end_adj_indel >= p->min_sr_len) { S = AE; Eo = pos; if (S < Eo) sr_del = 1; }
+            }
+        }
+    } else {
+        if (!rev && r->sa_strand == 0) {
+            if (pos < apos && apos - E < p->insert_max && apos - E > 0) { sr_del = 1; S = E; Eo = apos; }
+        } else if (rev && r->sa_strand == 1) {
+            if (apos < pos && pos - AE < p->insert_max) { S = AE; Eo = pos; if (S < Eo) sr_del = 1; }
+        }
+    }
+    if (!sr_del) return;
+    const int64_t gap = Eo - S;
+    if (gap < p->lseq && gap < p->insert_max - p->insert_mean) {
+        if (S >= 0 && S < c->P) c->A->a[GA_INDEL_D_F_RD][S] += 1;
+        indel_update(c, S, GA_INDEL_D_F, GA_INDEL_D_FDIST, OTHER_INDEL_D_F, (int)gap, r->add);
+        if (Eo - 1 >= 0 && Eo - 1 < c->P) c->A->a[GA_INDEL_D_R_RD][Eo - 1] += 1;
+        indel_update(c, Eo - 1, GA_INDEL_D_R, GA_INDEL_D_RDIST, OTHER_INDEL_D_R, (int)gap, r->add);
+    }
+    clu u; memset(&u, 0, sizeof(u));
+    u.x = (double)(gap + p->insert_mean); u.w = r->add; u.wd = (double)r->add; u.w_repl = r->add; u.tol = (double)(p->insert_max - p->insert_min);
+    rd_inc(c, S);
+    u.cls = CL_DEL_F; u.v = pos < apos ? pos : apos; u.mode = RS_MAX_ONLY;
+    cl_update(c, S, &u);
+    rd_inc(c, Eo - 1);
+    u.cls = CL_DEL_R; u.v = pos < apos ? apos : pos; u.mode = RS_MINMAX;
+    cl_update(c, Eo - 1, &u);
+}
+
+/* tandem-duplication breakpoints from a split read: dup_f at the downstream junction, dup_r at the upstream one,
+ * x = span - insert_mean (src/GROM.c:8016-8340, 9402-9722).  Bug-compatible: when the dup_f primary is created its
+ * read_end is not written; del_f's read_end at that position is written instead (src/GROM.c:8037-8045, 9423-9429). */
+static void split_dup_evidence(svctx *c, const svread *r, int64_t lp_start, int64_t lp_end)
+{
+    const grom_params *p = c->p;
+    const int pos = r->pos, apos = r->sa_pos;
+    clu u; memset(&u, 0, sizeof(u));
+    u.x = (double)(lp_end - lp_start - p->insert_mean); u.w = r->add; u.wd = (double)r->add; u.w_repl = r->add;
+    u.tol = (double)(p->insert_max - p->insert_min); u.mode = RS_MINMAX;
+    rd_inc(c, lp_end);
+    if (lp_end >= 0 && lp_end < c->P) {
+        u.cls = CL_DUP_F; u.v = pos < apos ? apos : pos;
+        const int was_empty = c->cw[CL_DUP_F][lp_end] == 0;
+        const int32_t old_re = c->cre[CL_DUP_F][lp_end];
+        cl_update(c, lp_end, &u);
+        if (was_empty) { c->cre[CL_DUP_F][lp_end] = old_re; c->cre[CL_DEL_F][lp_end] = u.v; }
+    }
+    rd_inc(c, lp_start - 1);
+    u.cls = CL_DUP_R; u.v = pos < apos ? pos : apos;
+    cl_update(c, lp_start - 1, &u);
+}
+
+/* forward read of a concordant-looking pair whose SA lies between read and mate (src/GROM.c:7978-8011) */
+int sv_split_dup_fwd(svctx *c, const svread *r)
+{
+    const grom_params *p = c->p;
+    if (!sa_usable(c, r)) return 0;
+    const int rev = (r->flag & 16) != 0;
+    if (!(!rev && r->sa_strand == 0)) return 0;
+    if (!((r->flag & 1) && !(r->flag & 8) && r->tid == r->mtid)) return 0;
+    if (!(r->pos < r->sa_pos && r->sa_pos < r->mpos)) return 0;
+    const int it = r->end_adj_indel > 0 ? r->end_adj_indel : 0;
+    const int ait = r->sa_end_adj_indel > 0 ? r->end_adj_indel : 0;        /* sic: the read's own value, src/GROM.c:7998 */
+    if (!(abs(r->lseq - r->start_adj - r->sa_end_adj) <= p->max_split_loss && r->lseq - r->start_adj - r->end_adj - it >= p->min_sr_len &&
+          r->lseq - r->sa_start_adj - r->sa_end_adj - ait >= p->min_sr_len)) return 0;
+    const int64_t lp_start = r->pos;
+    const int64_t lp_end = (int64_t)r->sa_pos - r->sa_start_adj + r->lseq - r->sa_end_adj - r->sa_end_adj_indel;
+    split_dup_evidence(c, r, lp_start, lp_end);
+    return 1;
+}
+
+/* reverse read, mate upstream, SA between mate and read (src/GROM.c:9361-9400) */
+void sv_split_dup_rev(svctx *c, const svread *r)
+{
+    const grom_params *p = c->p;
+    if (!sa_usable(c, r)) return;
+    const int rev = (r->flag & 16) != 0;
+    if (!(rev && r->sa_strand == 1)) return;
+    if (!((r->flag & 1) && !(r->flag & 8) && r->tid == r->mtid)) return;
+    if (!(r->sa_pos < r->pos && r->mpos < r->sa_pos)) return;
+    const int it = r->end_adj_indel > 0 ? r->end_adj_indel : 0;
+    const int ait = r->sa_end_adj_indel > 0 ? r->end_adj_indel : 0;
+    if (!(abs(r->lseq - r->sa_start_adj - r->end_adj) <= p->max_split_loss && r->lseq - r->start_adj - r->end_adj - it >= p->min_sr_len &&
+          r->lseq - r->sa_start_adj - r->sa_end_adj - ait >= p->min_sr_len)) return;
+    const int64_t lp_start = r->sa_pos;
+    const int64_t lp_end = (int64_t)r->pos - r->start_adj + r->lseq - r->end_adj - r->end_adj_indel;
+    if (!(lp_start < lp_end)) return;
+    split_dup_evidence(c, r, lp_start, lp_end);
+}

@@ -30,9 +30,21 @@ def test_oracle_reproduces_reference_dumps(data, tag, rmdup):
         v = g[f"{n}_scan_v"]
         assert (r.scan_first, r.scan_last) == (int(pos[0]), int(pos[-1]))
         assert np.array_equal(pos, np.arange(pos[0], pos[-1] + 1))
-        for k in PILEUP + CLIPS:
+        for k in range(51):                                   # every per-position int the reference keeps (oracle/hooks.h)
             bad = np.nonzero(r.arrays[k][pos] != v[:, k])[0]
             assert bad.size == 0, (n, GA_NAMES[k], pos[bad[:5]])
+        d = g[f"{n}_scan_d"]
+        for k in range(10):                                   # the ten breakpoint clusters: weight, first/last read, running mean
+            w_ref = v[:, 51 + 3 * k]
+            assert np.array_equal(r.cl_w[k][pos], w_ref), (n, "cluster weight", k)
+            live = w_ref != 0
+            assert np.array_equal(r.cl_rs[k][pos][live], v[:, 52 + 3 * k][live]), (n, "read_start", k)
+            assert np.array_equal(r.cl_re[k][pos][live], v[:, 53 + 3 * k][live]), (n, "read_end", k)
+            assert np.array_equal(r.cl_dist[k][pos][live], d[:, k][live]), (n, "dist", k)      # doubles, bit-exact
+        for k in range(2):
+            live = v[:, 51 + 3 * (8 + k)] != 0
+            assert np.array_equal(r.cl_mchr[k][pos][live], v[:, 81 + k][live])
+        assert np.array_equal(r.other_len[pos], v[:, 83])
         assert np.array_equal(r.lookahead_lseq[pos], v[:, 84])
         depth = g[f"{n}_depth"]
         for j, k in enumerate(("rd_mq", "rd_rd", "rd_low")):

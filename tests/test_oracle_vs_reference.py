@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(not po.have_reference("ref"), reason="oracle/_re
 def test_live_reference_dump_parity(tmp_path, seed, rmdup, read_len):
     spec = synth.SynthSpec(contigs=[("chrQ", 120_000), ("chrR", 50_000), ("chrZ", 10_000)], depth=25, seed=seed,
                            read_len=read_len, ins_mean=3.0 * read_len, ins_sd=30, ins_floor=read_len + 20,
-                           dup_frac=0.05, clip_frac=0.04)
+                           dup_frac=0.05, clip_frac=0.04, disc_frac=0.03, sa_frac=0.8, munmap_frac=0.01)
     cs = synth.simulate(spec)
     fa, bam = synth.write_dataset(str(tmp_path / "d"), cs)
     dump = str(tmp_path / "dump")
@@ -36,8 +36,16 @@ def test_live_reference_dump_parity(tmp_path, seed, rmdup, read_len):
             sd = po.load_scan_dump(dump, n)
             pos = sd["pos"]
             assert (r.scan_first, r.scan_last) == (int(pos[0]), int(pos[-1]))
-            for k in PILEUP + CLIPS:
+            for k in range(51):
                 assert np.array_equal(r.arrays[k][pos], sd["v"][:, k]), (n, GA_NAMES[k])
+            for k in range(10):
+                w_ref = sd["v"][:, 51 + 3 * k]
+                live = w_ref != 0
+                assert np.array_equal(r.cl_w[k][pos], w_ref)
+                assert np.array_equal(r.cl_rs[k][pos][live], sd["v"][:, 52 + 3 * k][live])
+                assert np.array_equal(r.cl_re[k][pos][live], sd["v"][:, 53 + 3 * k][live])
+                assert np.array_equal(r.cl_dist[k][pos][live], sd["d"][:, k][live])
+            assert np.array_equal(r.other_len[pos], sd["v"][:, 83])
             assert np.array_equal(r.lookahead_lseq[pos], sd["v"][:, 84])
             dd = po.load_depth_dump(dump, n)
             for j, k in enumerate(("rd_mq", "rd_rd", "rd_low")):
