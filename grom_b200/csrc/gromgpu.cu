@@ -669,9 +669,13 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 16
 #define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_inplace(int32_t *data, int64_t n, unsigned long long *status, unsigned int *ticket)
+struct ScanList { int64_t off[8]; };     // element offsets of up to 8 arrays scanned by one launch (blockIdx.y selects the array)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_inplace(int32_t *data_base, ScanList list, int64_t n, unsigned long long *status_base, unsigned int *ticket_base)
 {
     __shared__ int s_tile, s_warp[SCAN_THREADS / 32], s_excl;
+    int32_t *data = data_base + list.off[blockIdx.y];
+    unsigned long long *status = status_base + (size_t)blockIdx.y * gridDim.x;
+    unsigned int *ticket = ticket_base + blockIdx.y;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
     __syncthreads();
     const int tile = s_tile;
@@ -848,6 +852,8 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc_prepass(const char *__restric
     }
 }
 
+#include "sv_evidence.cuh"
+
 __global__ void k_fix_offsets(uint64_t *cigar_off, uint64_t *base_off, int64_t n, uint64_t cig_base, uint64_t slot_base)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -872,7 +878,8 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = size = 0; }
 };
 
-enum { B_POS, B_MPOS, B_TLEN, B_MTID, B_LQSEQ, B_FLAG, B_NCIGAR, B_MAPQ, B_QLEN, B_HASH, B_CIGOFF, B_BASEOFF, B_CIGAR, B_SEQ4, B_QUAL, B_COUNT };
+enum { B_POS, B_MPOS, B_TLEN, B_MTID, B_LQSEQ, B_FLAG, B_NCIGAR, B_MAPQ, B_QLEN, B_HASH, B_CIGOFF, B_BASEOFF, B_CIGAR, B_SEQ4, B_QUAL,
+       B_SAPOS, B_SASADJ, B_SAEADJ, B_SAINDEL, B_SASTRAND, B_SAMAPQ, B_SASAME, B_COUNT };
 
 struct gromgpu_chr {
     int tid = 0;
@@ -888,8 +895,17 @@ struct gromgpu_chr {
     int *d_max_span = nullptr; unsigned long long *d_counters = nullptr;   // 4 counters + 2 depth sums
     unsigned long long *d_scan_status = nullptr; unsigned int *d_ticket = nullptr; size_t cap_scan = 0;
     grom_snv_cand *d_cand = nullptr; unsigned int cand_cap = 0; unsigned int *d_ncand = nullptr;
+    // SV / indel evidence (sv_evidence.cuh)
+    int32_t *d_item_cnt = nullptr; size_t cap_item_cnt = 0;
+    SvItem *d_items = nullptr; size_t cap_items = 0;
+    int2 *d_sv_tiles = nullptr; uint8_t *d_sv_dirty = nullptr; size_t cap_sv_tiles = 0;
+    int *d_sv_small = nullptr;                       // [0] reach fwd [1] reach bwd [2] pool used [3] error flag
+    SvOther *d_pool = nullptr; int pool_cap = 0;
+    int32_t *d_cl_int = nullptr;                     // cl_w[10] cl_rs[10] cl_re[10] cl_mchr[2] other_len[1]  (33 x Ppad int32)
+    double *d_cl_dist = nullptr;                     // [10][Ppad]
+    int64_t n_items = 0;
     std::vector<grom_snv_cand> h_cand;
-    cudaEvent_t ev[9];
+    cudaEvent_t ev[12];
     bool ran = false;
     gromgpu_stats stats;
     gromgpu_result res;
@@ -942,16 +958,33 @@ extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, 
     gromgpu_chr *h = new gromgpu_chr();
     h->tid = tid; h->P = len; h->Ppad = (len + 1023) & ~(int64_t)1023; h->stream = g_stream;
     memset(&h->stats, 0, sizeof(h->stats)); memset(&h->res, 0, sizeof(h->res));
-    for (int i = 0; i < 9; i++) h->ev[i] = nullptr;
+    for (int i = 0; i < 12; i++) h->ev[i] = nullptr;
     *out = h;
     CK(cudaMalloc(&h->d_fasta, (size_t)h->Ppad));
     CK(cudaMemcpyAsync(h->d_fasta, fasta, (size_t)len, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMalloc(&h->d_arrays, sizeof(int32_t) * (size_t)GA_COUNT * (size_t)h->Ppad));
     CK(cudaMalloc(&h->d_max_span, sizeof(int)));
     CK(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 8));
-    CK(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+    CK(cudaMalloc(&h->d_ticket, sizeof(unsigned int) * 8));
     CK(cudaMalloc(&h->d_ncand, sizeof(unsigned int)));
-    for (int i = 0; i < 9; i++) CK(cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 12; i++) CK(cudaEventCreate(&h->ev[i]));
+    CK(cudaMalloc(&h->d_cl_int, sizeof(int32_t) * 33 * (size_t)h->Ppad));
+    CK(cudaMalloc(&h->d_cl_dist, sizeof(double) * 10 * (size_t)h->Ppad));
+    CK(cudaMemsetAsync(h->d_cl_int, 0, sizeof(int32_t) * 33 * (size_t)h->Ppad, h->stream));
+    CK(cudaMemsetAsync(h->d_cl_dist, 0, sizeof(double) * 10 * (size_t)h->Ppad, h->stream));
+    CK(cudaMemsetAsync(h->d_arrays, 0, sizeof(int32_t) * (size_t)GA_COUNT * (size_t)h->Ppad, h->stream));
+    CK(cudaMalloc(&h->d_sv_small, sizeof(int) * 4));
+    // one slab of 50 side slots per position that ever holds a second cluster of some class: every position for small
+    // contigs, at most 2 M slabs (3.2 GB) for chromosome-sized ones; exhaustion is reported as an error, never ignored
+    h->pool_cap = (int)std::min<int64_t>(h->Ppad, std::max<int64_t>(h->Ppad / 32, 2 << 20));
+    CK(cudaMalloc(&h->d_pool, sizeof(SvOther) * SV_OTHER * (size_t)h->pool_cap));
+    {
+        const int64_t nt = (h->P + SV_T - 1) / SV_T;
+        h->cap_sv_tiles = (size_t)nt;
+        CK(cudaMalloc(&h->d_sv_tiles, sizeof(int2) * (size_t)nt));
+        CK(cudaMalloc(&h->d_sv_dirty, (size_t)nt));
+        CK(cudaMemsetAsync(h->d_sv_dirty, 0, (size_t)nt, h->stream));
+    }
     return 0;
 }
 
@@ -972,7 +1005,9 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
     cudaFree(h->d_fasta); cudaFree(h->d_arrays); cudaFree(h->d_state); cudaFree(h->d_prep); cudaFree(h->d_tile_first);
     cudaFree(h->d_max_span); cudaFree(h->d_counters); cudaFree(h->d_scan_status); cudaFree(h->d_ticket);
     cudaFree(h->d_cand); cudaFree(h->d_ncand);
-    for (int i = 0; i < 9; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 12; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    cudaFree(h->d_item_cnt); cudaFree(h->d_items); cudaFree(h->d_sv_tiles); cudaFree(h->d_sv_dirty); cudaFree(h->d_sv_small); cudaFree(h->d_pool);
+    cudaFree(h->d_cl_int); cudaFree(h->d_cl_dist);
     delete h;
 }
 
@@ -989,7 +1024,10 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
         { B_NCIGAR, b->n_cigar, 2, n, h->n_reads }, { B_MAPQ, b->mapq, 1, n, h->n_reads }, { B_QLEN, b->qname_len, 1, n, h->n_reads },
         { B_HASH, b->qname_hash, 8, n, h->n_reads }, { B_CIGOFF, b->cigar_off, 8, n, h->n_reads }, { B_BASEOFF, b->base_off, 8, n, h->n_reads },
         { B_CIGAR, b->cigar, 4, b->n_cigar_total, h->n_cigar }, { B_SEQ4, b->seq4, 1, (b->n_base_slots + 1) / 2, h->n_slots / 2 },
-        { B_QUAL, b->qual, 1, b->n_base_slots, h->n_slots } };
+        { B_QUAL, b->qual, 1, b->n_base_slots, h->n_slots },
+        { B_SAPOS, b->sa_pos, 4, n, h->n_reads }, { B_SASADJ, b->sa_start_adj, 4, n, h->n_reads }, { B_SAEADJ, b->sa_end_adj, 4, n, h->n_reads },
+        { B_SAINDEL, b->sa_end_adj_indel, 4, n, h->n_reads }, { B_SASTRAND, b->sa_strand, 1, n, h->n_reads }, { B_SAMAPQ, b->sa_mapq, 2, n, h->n_reads },
+        { B_SASAME, b->sa_same_chr, 1, n, h->n_reads } };
     for (int k = 0; k < B_COUNT; k++) {
         DevBuf &d = h->rb[f[k].id];
         const size_t need = (size_t)(f[k].have + f[k].cnt) * f[k].elt + 64;
@@ -1039,8 +1077,15 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
         CK(cudaMalloc(&h->d_prep, h->cap_state * sizeof(PrepRec)));
     }
     if ((size_t)n_tiles > h->cap_tiles) { cudaFree(h->d_tile_first); h->cap_tiles = (size_t)n_tiles; CK(cudaMalloc(&h->d_tile_first, sizeof(int64_t) * h->cap_tiles)); }
-    if ((size_t)n_scan_tiles > h->cap_scan) { cudaFree(h->d_scan_status); h->cap_scan = (size_t)n_scan_tiles; CK(cudaMalloc(&h->d_scan_status, sizeof(unsigned long long) * h->cap_scan)); }
     if (!h->d_cand) { h->cand_cap = 1u << 20; CK(cudaMalloc(&h->d_cand, sizeof(grom_snv_cand) * (size_t)h->cand_cap)); }
+    const int64_t n_cnt_pad = (n + 1023) & ~(int64_t)1023;
+    const int64_t n_cnt_tiles = (n_cnt_pad + SCAN_TILE - 1) / SCAN_TILE;
+    if ((size_t)n_cnt_pad > h->cap_item_cnt) { cudaFree(h->d_item_cnt); h->cap_item_cnt = (size_t)n_cnt_pad + (size_t)n_cnt_pad / 8; CK(cudaMalloc(&h->d_item_cnt, sizeof(int32_t) * h->cap_item_cnt)); }
+    const int64_t n_sv_tiles = (P + SV_T - 1) / SV_T;
+    {   // scan status: 5 position arrays + 1 item-count array
+        const size_t need = (size_t)n_scan_tiles * 5 + (size_t)n_cnt_tiles + 8;
+        if (need > h->cap_scan) { cudaFree(h->d_scan_status); h->cap_scan = need; CK(cudaMalloc(&h->d_scan_status, sizeof(unsigned long long) * h->cap_scan)); }
+    }
 
     const int first_pos = grom_first_pos(&g_params);
     int scan_first = -1, scan_last = -1;
@@ -1061,12 +1106,16 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     DevReads R = dev_reads(h);
     CK(cudaEventRecord(h->ev[0], s));
     // zero only the arrays that are scatter targets (rd .. indel_d_r_rd); the pileup and depth arrays are fully overwritten
-    CK(cudaMemsetAsync(h->d_arrays + (int64_t)GA_RD * Ppad, 0, sizeof(int32_t) * (size_t)(GA_CONC - GA_RD) * (size_t)Ppad, s));
+    CK(cudaMemsetAsync(h->d_arrays + (int64_t)GA_RD * Ppad, 0, sizeof(int32_t) * (size_t)(GA_INDEL_I - GA_RD) * (size_t)Ppad, s));   // rd, clips, conc, ins, munmapped
+    CK(cudaMemsetAsync(h->d_arrays + (int64_t)GA_INDEL_D_F_RD * Ppad, 0, sizeof(int32_t) * (size_t)Ppad, s));
+    CK(cudaMemsetAsync(h->d_arrays + (int64_t)GA_INDEL_D_R_RD * Ppad, 0, sizeof(int32_t) * (size_t)Ppad, s));
+    CK(cudaMemsetAsync(h->d_sv_small, 0, sizeof(int) * 4, s));
+    CK(cudaMemsetAsync(h->d_item_cnt, 0, sizeof(int32_t) * (size_t)n_cnt_pad, s));
     CK(cudaMemsetAsync(h->d_max_span, 0, sizeof(int), s));
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, s));
-    CK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int) * 8, s));
     CK(cudaMemsetAsync(h->d_ncand, 0, sizeof(unsigned int), s));
-    CK(cudaMemsetAsync(h->d_scan_status, 0, sizeof(unsigned long long) * (size_t)n_scan_tiles, s));
+    CK(cudaMemsetAsync(h->d_scan_status, 0, sizeof(unsigned long long) * ((size_t)n_scan_tiles * 5 + (size_t)n_cnt_tiles), s));
     CK(cudaEventRecord(h->ev[1], s));
     {
         const int M = g_params.insert_mean;
@@ -1084,7 +1133,39 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     CK(cudaEventRecord(h->ev[3], s));
     k_tile_index<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(R.pos, n, h->d_max_span, n_tiles, h->d_tile_first); launches++;
     CK(cudaEventRecord(h->ev[4], s));
-    k_scan_inplace<<<(unsigned)n_scan_tiles, SCAN_THREADS, 0, s>>>(h->d_arrays + (int64_t)GA_RD * Ppad, Ppad, h->d_scan_status, h->d_ticket); launches++;
+    // ---- SV / indel evidence: items in BAM order, per-tile fold, then the five range-add prefix scans
+    SvDev SD;
+    SD.cl_w = h->d_cl_int; SD.cl_rs = h->d_cl_int + 10 * Ppad; SD.cl_re = h->d_cl_int + 20 * Ppad; SD.cl_mchr = h->d_cl_int + 30 * Ppad;
+    SD.other_len = h->d_cl_int + 32 * Ppad; SD.cl_dist = h->d_cl_dist; SD.pool = h->d_pool; SD.pool_cap = h->pool_cap;
+    SD.pool_used = h->d_sv_small + 2; SD.err = h->d_sv_small + 3;
+    h->n_items = 0;
+    k_sv_clear<<<(unsigned)n_sv_tiles, SV_T, 0, s>>>(h->d_sv_dirty, P, Ppad, h->d_arrays, SD); launches++;
+    if (n) {
+        SvReadArrays SA;
+        SA.sa_pos = (const int32_t *)h->rb[B_SAPOS].p; SA.sa_start_adj = (const int32_t *)h->rb[B_SASADJ].p; SA.sa_end_adj = (const int32_t *)h->rb[B_SAEADJ].p;
+        SA.sa_end_adj_indel = (const int32_t *)h->rb[B_SAINDEL].p; SA.sa_strand = (const uint8_t *)h->rb[B_SASTRAND].p;
+        SA.sa_mapq = (const int16_t *)h->rb[B_SAMAPQ].p; SA.sa_same = (const uint8_t *)h->rb[B_SASAME].p;
+        k_sv_count<<<rb, 256, 0, s>>>(R, SA, h->tid, h->n_leading, h->d_state, P, h->d_item_cnt); launches++;
+        ScanList sl0; memset(&sl0, 0, sizeof(sl0));
+        k_scan_inplace<<<dim3((unsigned)n_cnt_tiles, 1), SCAN_THREADS, 0, s>>>(h->d_item_cnt, sl0, n_cnt_pad, h->d_scan_status + (size_t)n_scan_tiles * 5, h->d_ticket + 5); launches++;
+        int32_t total_items = 0;
+        CK(cudaMemcpyAsync(&total_items, h->d_item_cnt + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        h->n_items = total_items;
+        if ((size_t)total_items > h->cap_items) { cudaFree(h->d_items); h->cap_items = (size_t)total_items + (size_t)total_items / 4 + 1024; CK(cudaMalloc(&h->d_items, sizeof(SvItem) * h->cap_items)); }
+        k_sv_emit<<<rb, 256, 0, s>>>(R, SA, h->tid, h->n_leading, h->d_state, h->d_item_cnt, h->d_items, h->d_arrays, P, Ppad, h->d_sv_small); launches++;
+        if (total_items > 0) {
+            k_sv_tiles<<<(unsigned)((n_sv_tiles + 255) / 256), 256, 0, s>>>(R.pos, n, h->d_item_cnt, h->d_sv_small, n_sv_tiles, h->d_sv_tiles); launches++;
+            k_sv_apply<<<(unsigned)n_sv_tiles, SV_T, sizeof(SvTileState), s>>>(h->d_items, h->d_sv_tiles, P, Ppad, h->d_arrays, SD, h->d_sv_dirty); launches++;
+        }
+    }
+    CK(cudaEventRecord(h->ev[9], s));
+    {
+        ScanList sl; memset(&sl, 0, sizeof(sl));
+        sl.off[0] = (int64_t)GA_RD * Ppad; sl.off[1] = (int64_t)GA_CONC * Ppad; sl.off[2] = (int64_t)GA_INS * Ppad;
+        sl.off[3] = (int64_t)GA_MUNMAPPED_F * Ppad; sl.off[4] = (int64_t)GA_MUNMAPPED_R * Ppad;
+        k_scan_inplace<<<dim3((unsigned)n_scan_tiles, 5), SCAN_THREADS, 0, s>>>(h->d_arrays, sl, Ppad, h->d_scan_status, h->d_ticket); launches++;
+    }
     CK(cudaEventRecord(h->ev[5], s));
     SnvScanArgs sca;
     sca.scan_first = scan_first; sca.scan_last = scan_last; sca.depth_bound = depth_bound; sca.hez = d_hez; sca.mqt = d_mq;
@@ -1103,12 +1184,19 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     cudaEventElapsedTime(&ms, h->ev[8], h->ev[2]); st.ms_dup = ms;
     cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); st.ms_prep = ms;
     cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); st.ms_index = ms;
-    cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); st.ms_rdscan = ms;
+    cudaEventElapsedTime(&ms, h->ev[4], h->ev[9]); st.ms_sv = ms;
+    cudaEventElapsedTime(&ms, h->ev[9], h->ev[5]); st.ms_rdscan = ms;
     cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); st.ms_pileup = ms;
     st.ms_snvscan = 0.f;      // the SNV gate runs in the pileup kernel's epilogue
     st.launches = launches;
     unsigned long long cnt[8];
     CK(cudaMemcpy(cnt, h->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
+    {
+        int small[4];
+        CK(cudaMemcpy(small, h->d_sv_small, sizeof(small), cudaMemcpyDeviceToHost));
+        if (small[3]) return fail("gromgpu_chr_run: other-slot pool of %d position slabs exhausted", h->pool_cap);
+        st.n_sv_items = h->n_items; st.n_other_slabs = small[2];
+    }
     st.n_reads = n; st.n_applied = (int64_t)cnt[0]; st.n_dups = (int64_t)cnt[1]; st.aligned_bases = (int64_t)cnt[2]; st.bytes_reads = (int64_t)cnt[3];
     h->res.scan_first = scan_first; h->res.scan_last = scan_last;
     h->res.snv_ave_rd = (double)(long)cnt[4] / (double)(long)cnt[5];
@@ -1148,6 +1236,18 @@ extern "C" int gromgpu_debug_fetch(gromgpu_chr *h, int ga, int32_t *dst, int64_t
     if (!h || !h->ran) return fail("gromgpu_debug_fetch: call gromgpu_chr_run first");
     if (ga < 0 || ga >= GA_COUNT || p0 < 0 || p1 > h->P || p0 > p1) return fail("gromgpu_debug_fetch: bad array %d or range [%lld,%lld)", ga, (long long)p0, (long long)p1);
     CK(cudaMemcpy(dst, h->d_arrays + (int64_t)ga * h->Ppad + p0, sizeof(int32_t) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int gromgpu_debug_fetch_cluster(gromgpu_chr *h, int what, int cls, void *dst, int64_t p0, int64_t p1)
+{
+    if (!h || !h->ran) return fail("gromgpu_debug_fetch_cluster: call gromgpu_chr_run first");
+    if (p0 < 0 || p1 > h->P || p0 > p1 || what < 0 || what > 5 || cls < 0 || cls >= 10) return fail("gromgpu_debug_fetch_cluster: bad arguments");
+    const int64_t Ppad = h->Ppad; const size_t cntp = (size_t)(p1 - p0);
+    if (what == 3) { CK(cudaMemcpy(dst, h->d_cl_dist + (int64_t)cls * Ppad + p0, sizeof(double) * cntp, cudaMemcpyDeviceToHost)); return 0; }
+    int64_t row;
+    if (what <= 2) row = what * 10 + cls; else if (what == 4) { if (cls > 1) return fail("gromgpu_debug_fetch_cluster: ctx class index must be 0 or 1"); row = 30 + cls; } else row = 32;
+    CK(cudaMemcpy(dst, h->d_cl_int + row * Ppad + p0, sizeof(int32_t) * cntp, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -25,9 +25,10 @@ _LIB = None
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_float), ("ms_clear", C.c_float), ("ms_dup", C.c_float), ("ms_prep", C.c_float),
                 ("ms_index", C.c_float), ("ms_pileup", C.c_float), ("ms_rdscan", C.c_float), ("ms_snvscan", C.c_float),
-                ("ms_gc", C.c_float), ("reserved_f", C.c_float),
+                ("ms_gc", C.c_float), ("ms_sv", C.c_float),
                 ("launches", C.c_int32), ("reserved", C.c_int32), ("n_reads", C.c_int64), ("n_applied", C.c_int64),
-                ("n_dups", C.c_int64), ("aligned_bases", C.c_int64), ("bytes_reads", C.c_int64)]
+                ("n_dups", C.c_int64), ("aligned_bases", C.c_int64), ("bytes_reads", C.c_int64), ("n_sv_items", C.c_int64),
+                ("n_other_slabs", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if not k.startswith("reserved")}
@@ -56,6 +57,7 @@ def lib() -> C.CDLL:
         L.gromgpu_chr_finish.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.gromgpu_chr_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.gromgpu_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64]
+        L.gromgpu_debug_fetch_cluster.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64]
         L.gromgpu_fetch_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
         L.gromgpu_chr_free.argtypes = [C.c_void_p]
         L.gromgpu_chr_free.restype = None
@@ -150,6 +152,19 @@ class Chromosome:
         for k in range(GA_COUNT):
             _ck(lib().gromgpu_debug_fetch(self._h, k, out[k].ctypes.data, 0, self.length))
         return out
+
+    def fetch_clusters(self):
+        """(w, rs, re, dist, mchr, other_len): [10,P] int32 x3, [10,P] float64, [2,P] int32, [P] int32."""
+        P = self.length
+        w = np.empty((10, P), np.int32); rs = np.empty((10, P), np.int32); re = np.empty((10, P), np.int32)
+        dist = np.empty((10, P), np.float64); mchr = np.empty((2, P), np.int32); ol = np.empty(P, np.int32)
+        for k in range(10):
+            for what, arr in ((0, w), (1, rs), (2, re), (3, dist)):
+                _ck(lib().gromgpu_debug_fetch_cluster(self._h, what, k, arr[k].ctypes.data, 0, P))
+        for k in range(2):
+            _ck(lib().gromgpu_debug_fetch_cluster(self._h, 4, k, mchr[k].ctypes.data, 0, P))
+        _ck(lib().gromgpu_debug_fetch_cluster(self._h, 5, 0, ol.ctypes.data, 0, P))
+        return w, rs, re, dist, mchr, ol
 
     def read_state(self, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.uint8)

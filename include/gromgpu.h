@@ -45,11 +45,13 @@ typedef struct gromgpu_stats {
     float ms_rdscan;            /* range-add prefix scan -> rd   (7176-7181) */
     float ms_snvscan;           /* per-position SNV gate + compaction (11096-11199); 0 when fused into the pileup epilogue */
     float ms_gc;                /* GC / ACGT triangular-window percentages (1766-1859) */
-    float reserved_f;
+    float ms_sv;                /* CIGAR indel slots, split reads, pair ranges and breakpoint clusters (7187-10953) */
     int32_t launches;           /* kernels launched by the run */
     int32_t reserved;
     int64_t n_reads, n_applied, n_dups, aligned_bases;
     int64_t bytes_reads;        /* read-record bytes the pileup consumed (sum rec(r)) */
+    int64_t n_sv_items;         /* order-dependent evidence items emitted (indel slots, split reads, discordant ranges) */
+    int64_t n_other_slabs;      /* positions that needed the 50 side slots */
 } gromgpu_stats;
 
 typedef struct gromgpu_result {
@@ -96,6 +98,10 @@ int gromgpu_chr_stats(const gromgpu_chr *h, gromgpu_stats *out);
 /* Parity access to the raw per-position arrays: copies array `ga` (GA_* of grom_params.h),
  * positions [p0, p1), to dst (int32, host). */
 int gromgpu_debug_fetch(gromgpu_chr *h, int ga, int32_t *dst, int64_t p0, int64_t p1);
+/* Parity access to the breakpoint clusters (class order: del_f del_r dup_f dup_r inv_f1 inv_r1 inv_f2 inv_r2 ctx_f ctx_r):
+ * what = 0 weight, 1 read_start, 2 read_end (int32), 3 running-mean distance (double), 4 ctx mate contig (cls 0/1 = ctx_f/ctx_r),
+ * 5 other_len (cls ignored).  dst receives positions [p0, p1). */
+int gromgpu_debug_fetch_cluster(gromgpu_chr *h, int what, int cls, void *dst, int64_t p0, int64_t p1);
 /* read_state per read [i0, i1): 0 = not applied (before W/4+1, UNMAP/DUP flag), 1 = applied, 2 = -M duplicate */
 int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0, int64_t i1);
 

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from util import CHECKED, CLIPS, DEPTH, GCS, GOLDEN, PILEUP, assert_arrays_equal, golden_batches, golden_params, load_golden_fasta, tables, tables_7digit
+from util import CHECKED, CLIPS, DEPTH, EVIDENCE, GCS, GOLDEN, PILEUP, assert_arrays_equal, assert_clusters_equal, golden_batches, golden_params, load_golden_fasta, tables, tables_7digit
 from grom_b200 import gpu
 from grom_b200.params import GA, GA_NAMES, Params
 from grom_b200.reads import CDEL, CHARD_CLIP, CINS, CMATCH, CREF_SKIP, CSOFT_CLIP, FPAIRED, FREVERSE, FMREVERSE
@@ -22,6 +22,7 @@ def run_gpu(prm, batch_or_slices, fasta, hez, mq, tid=0):
         for b in (batch_or_slices if isinstance(batch_or_slices, list) else [batch_or_slices]):
             ch.push_reads(b); n += b.n_reads
         res = ch.finish()
+        run_gpu.clusters = ch.fetch_clusters()
         return res, ch.fetch_all(), ch.read_state(n), ch.stats()
 
 
@@ -30,6 +31,7 @@ def check_against_oracle(prm, batch, fasta, hez, mq, slices=None):
     ref = po.run_chr(prm, batch, fasta, hez, mq)
     assert np.array_equal(state, ref.read_state)
     assert_arrays_equal(got, ref.arrays)
+    assert_clusters_equal(run_gpu.clusters, ref)
     assert (res.scan_first, res.scan_last) == (ref.scan_first, ref.scan_last)
     assert np.array_equal(res.snv["pos"], ref.snv["pos"])
     for f in ("base", "ratio", "pr", "hez", "v"):
@@ -53,8 +55,16 @@ def test_gpu_reproduces_reference_golden(tag, rmdup):
         res, got, state, st = run_gpu(prm, batches[tid], fasta[name], hez, mq, tid=tid)
         pos, v = g[f"{n}_scan_pos"], g[f"{n}_scan_v"]
         assert (res.scan_first, res.scan_last) == (int(pos[0]), int(pos[-1]))
-        for k in PILEUP + CLIPS:
+        for k in EVIDENCE:
             assert np.array_equal(got[k][pos], v[:, k]), (n, GA_NAMES[k])
+        cw, crs, cre, cdist, cmchr, col = run_gpu.clusters
+        d = g[f"{n}_scan_d"]
+        for k in range(10):
+            w_ref = v[:, 51 + 3 * k]; live = w_ref != 0
+            assert np.array_equal(cw[k][pos], w_ref), (n, "cluster", k)
+            assert np.array_equal(crs[k][pos][live], v[:, 52 + 3 * k][live]) and np.array_equal(cre[k][pos][live], v[:, 53 + 3 * k][live])
+            assert np.array_equal(cdist[k][pos][live], d[:, k][live])
+        assert np.array_equal(col[pos], v[:, 83])
         depth = g[f"{n}_depth"]
         for j, k in enumerate(DEPTH):
             assert np.array_equal(got[k], depth[j]), (n, GA_NAMES[k])
@@ -75,7 +85,8 @@ def test_gpu_reproduces_reference_golden(tag, rmdup):
 def test_gpu_matches_oracle_synthetic(seed, rmdup, read_len, depth):
     spec = synth.SynthSpec(contigs=[("chrA", 300_000), ("chrB", 100_000)], depth=depth, seed=seed, read_len=read_len,
                            ins_mean=2.8 * read_len, ins_sd=35, ins_floor=read_len + 15, dup_frac=0.06, clip_frac=0.04,
-                           hardclip_frac=0.01, refskip_frac=0.003, long_name_frac=0.01)
+                           hardclip_frac=0.01, refskip_frac=0.003, long_name_frac=0.01, disc_frac=0.03, sa_frac=0.8, munmap_frac=0.01,
+                           sv_sites_per_mb=10)
     hez, mq = tables()
     prm = Params.default(insert_mean=int(2.8 * read_len), insert_min=read_len + 15, insert_max=int(2.8 * read_len) + 120,
                          lseq=read_len, rmdup=rmdup)
@@ -110,12 +121,12 @@ def test_empty_and_all_skipped_inputs():
     with gpu.Chromosome(0, fa) as ch:          # no reads at all
         res = ch.finish()
         assert (res.scan_first, res.scan_last, len(res.snv)) == (-1, -1, 0)
-        assert not ch.fetch_all()[PILEUP + CLIPS + DEPTH].any()
+        assert not ch.fetch_all()[EVIDENCE + DEPTH].any()
     # every read before W/4+1: nothing is applied, nothing is scanned (reference src/GROM.c:6406)
     recs = [dict(pos=p, cigar=[(CMATCH, 50)], seq="ACGTA" * 10) for p in (10, 500, 3000)]
     b = synth.batch_from_records(0, recs)
     res, got, state, st, ref = check_against_oracle(prm, b, fa, hez, mq)
-    assert res.scan_first == -1 and not state.any() and not got[PILEUP + CLIPS + DEPTH].any()
+    assert res.scan_first == -1 and not state.any() and not got[EVIDENCE + DEPTH].any()
 
 
 def test_edge_cigars_and_ragged_reads():
@@ -203,8 +214,9 @@ def test_size_independent_properties_large():
     assert int(a1[GA["rc_all"]].sum(dtype=np.int64)) == tot
     assert np.array_equal(a1[GA["bq_rc"]], a1[0] + a1[1] + a1[2] + a1[3])
     assert st.aligned_bases == int(applied.sum()) * 150
-    # physical depth: sum of rd == sum of read spans
-    assert int(a1[GA["rd"]].sum(dtype=np.int64)) == int(np.minimum(c.batch.pos[applied] + 150, len(c.chars)).sum() - c.batch.pos[applied].sum())
+    # physical depth: sum of rd == read spans + insert gaps of concordant forward reads (src/GROM.c:7176-7181, 8345-8365)
+    assert int(a1[GA["rd"]].sum(dtype=np.int64)) >= int(np.minimum(c.batch.pos[applied] + 150, len(c.chars)).sum() - c.batch.pos[applied].sum())
+    assert int(a1[GA["conc"]].sum(dtype=np.int64)) > 0 and np.all(a1[GA["conc"]] <= a1[GA["rd"]])
     # planted homozygous SNVs far from the ends are all called
     hom = c.truth["snv_pos"][~c.truth["snv_het"]]
     hom = hom[(hom > prm.first_pos + 200) & (hom < r1.scan_last - 200)]

@@ -17,7 +17,8 @@ PILEUP = list(range(0, 23))
 CLIPS = list(range(24, 39))
 DEPTH = [GA["rd_mq"], GA["rd_rd"], GA["rd_low"]]
 GCS = [GA["gc"], GA["acgt"]]
-CHECKED = PILEUP + CLIPS + DEPTH + GCS
+EVIDENCE = list(range(0, 51))          # every per-position int of the evidence accumulation (oracle/hooks.h order)
+CHECKED = EVIDENCE + DEPTH + GCS
 
 
 def load_golden_fasta():
@@ -65,3 +66,17 @@ def assert_arrays_equal(got, want, names=None, where=None):
             a, b = a[where], b[where]
         bad = np.nonzero(a != b)[0]
         assert bad.size == 0, f"array {GA_NAMES[k]}: {bad.size} mismatches, first at {bad[:5]}: got {a[bad[:5]]} want {b[bad[:5]]}"
+
+
+def assert_clusters_equal(got, ref):
+    """got = (w, rs, re, dist, mchr, other_len) from the GPU; ref = OracleResult.  read_start/read_end/dist only where a cluster exists."""
+    w, rs, re, dist, mchr, ol = got
+    assert np.array_equal(w, ref.cl_w), "cluster weights differ"
+    live = ref.cl_w != 0
+    assert np.array_equal(rs[live], ref.cl_rs[live]), "cluster read_start differs"
+    assert np.array_equal(re[live], ref.cl_re[live]), "cluster read_end differs"
+    assert np.array_equal(dist[live], ref.cl_dist[live]), "cluster running-mean distance differs (double, bit-exact)"
+    for k in range(2):
+        lv = ref.cl_w[8 + k] != 0
+        assert np.array_equal(mchr[k][lv], ref.cl_mchr[k][lv]), "ctx mate contig differs"
+    assert np.array_equal(ol, ref.other_len), "other_len differs"
