@@ -898,7 +898,7 @@ struct gromgpu_chr {
     // SV / indel evidence (sv_evidence.cuh)
     int32_t *d_item_cnt = nullptr; size_t cap_item_cnt = 0;
     SvItem *d_items = nullptr; size_t cap_items = 0;
-    int2 *d_sv_tiles = nullptr; uint8_t *d_sv_dirty = nullptr; size_t cap_sv_tiles = 0;
+    int2 *d_sv_tiles = nullptr; uint16_t *d_sv_dirty = nullptr; size_t cap_sv_tiles = 0;
     int *d_sv_small = nullptr;                       // [0] reach fwd [1] reach bwd [2] pool used [3] error flag
     SvOther *d_pool = nullptr; int pool_cap = 0;
     int32_t *d_cl_int = nullptr;                     // cl_w[10] cl_rs[10] cl_re[10] cl_mchr[2] other_len[1]  (33 x Ppad int32)
@@ -982,8 +982,8 @@ extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, 
         const int64_t nt = (h->P + SV_T - 1) / SV_T;
         h->cap_sv_tiles = (size_t)nt;
         CK(cudaMalloc(&h->d_sv_tiles, sizeof(int2) * (size_t)nt));
-        CK(cudaMalloc(&h->d_sv_dirty, (size_t)nt));
-        CK(cudaMemsetAsync(h->d_sv_dirty, 0, (size_t)nt, h->stream));
+        CK(cudaMalloc(&h->d_sv_dirty, sizeof(uint16_t) * (size_t)nt));
+        CK(cudaMemsetAsync(h->d_sv_dirty, 0, sizeof(uint16_t) * (size_t)nt, h->stream));
     }
     return 0;
 }

@@ -326,6 +326,7 @@ struct SvTileState {
     int rs[SV_NCL][SV_T], re[SV_NCL][SV_T];
     int mchr[2][SV_T];
     int oth[SV_T];                     // index into the other-slot pool, -1 = none
+    int oth_n[SV_T];                   // side slots in use (slots are handed out in order and never freed, so slot oth_n is the first empty one)
     double dist[SV_NCL][SV_T];
 };
 
@@ -355,10 +356,7 @@ __device__ SvOther *sv_others(SvTileState &S, int t, const SvDev &D)
     if (S.oth[t] < 0) {
         const int k = atomicAdd(D.pool_used, 1);
         if (k >= D.pool_cap) { atomicExch(D.err, 1); return nullptr; }
-        S.oth[t] = k;
-        SvOther *o = D.pool + (size_t)k * SV_OTHER;
-        for (int s = 0; s < SV_OTHER; s++) { o[s].w = 0; o[s].type = 0; o[s].mchr = 0; o[s].rs = 0; o[s].re = 0; o[s].dist = 0; }
-        return o;
+        S.oth[t] = k; S.oth_n[t] = 0;          // no zero fill: only slots below oth_n are ever read
     }
     return D.pool + (size_t)S.oth[t] * SV_OTHER;
 }
@@ -389,26 +387,26 @@ __device__ void sv_apply_cluster(SvTileState &S, int t, const SvItem &it, int p,
     SvOther *o = sv_others(S, t, D);
     if (!o) return;
     const int otype = k + 1;
-    for (int s = 0; s < SV_OTHER; s++) {
-        if (o[s].type == otype) {
-            if (sv_join(it, x, o[s].dist, o[s].w, o[s].mchr)) {
-                o[s].w += w; o[s].dist += wd * (x - o[s].dist) / (double)o[s].w;
-                sv_track(mode, it.v, o[s].rs, o[s].re);
-                if (o[s].w > W) {
-                    const int tw = o[s].w, trs = o[s].rs, tre = o[s].re, tm = o[s].mchr; const double td = o[s].dist;
-                    o[s].w = W; o[s].dist = DI; o[s].rs = RS; o[s].re = RE;
-                    W = tw; DI = td; RS = trs; RE = tre;
-                    if (ctx) { o[s].mchr = S.mchr[k - CL_CTX_F][t]; S.mchr[k - CL_CTX_F][t] = tm; }
-                }
-                return;
+    const int nu = S.oth_n[t];
+    for (int s = 0; s < nu; s++) {
+        if (o[s].type == otype && sv_join(it, x, o[s].dist, o[s].w, o[s].mchr)) {
+            o[s].w += w; o[s].dist += wd * (x - o[s].dist) / (double)o[s].w;
+            sv_track(mode, it.v, o[s].rs, o[s].re);
+            if (o[s].w > W) {
+                const int tw = o[s].w, trs = o[s].rs, tre = o[s].re, tm = o[s].mchr; const double td = o[s].dist;
+                o[s].w = W; o[s].dist = DI; o[s].rs = RS; o[s].re = RE;
+                W = tw; DI = td; RS = trs; RE = tre;
+                if (ctx) { o[s].mchr = S.mchr[k - CL_CTX_F][t]; S.mchr[k - CL_CTX_F][t] = tm; }
             }
-        } else if (o[s].type == 0) {
-            o[s].w = w; o[s].type = otype; o[s].dist = x; o[s].rs = it.v; o[s].re = it.v;
-            if (ctx) o[s].mchr = it.mchr;
             return;
         }
     }
-    for (int s = 0; s < SV_OTHER; s++) {
+    if (nu < SV_OTHER) {                       // first empty slot
+        SvOther n_; n_.w = w; n_.type = otype; n_.mchr = ctx ? it.mchr : 0; n_.rs = it.v; n_.re = it.v; n_.pad = 0; n_.dist = x;
+        o[nu] = n_; S.oth_n[t] = nu + 1;
+        return;
+    }
+    for (int s = 0; s < SV_OTHER; s++) {       // all 50 in use: overwrite the first whose weight is <= cdp_add (src/GROM.c:8506-8523)
         if (o[s].w <= it.add) {
             o[s].w = w; o[s].type = otype; o[s].dist = x; o[s].rs = it.v; o[s].re = it.v;
             if (ctx) o[s].mchr = it.mchr;
@@ -427,21 +425,25 @@ __device__ void sv_apply_indel(SvTileState &S, int t, const SvItem &it, const Sv
     SvOther *o = sv_others(S, t, D);
     if (!o) return;
     const int otype = 11 + j;
-    for (int s = 0; s < SV_OTHER; s++) {
-        if (o[s].type == otype) {
-            if ((uint32_t)len == (uint32_t)(o[s].dist + 0.5)) {
-                o[s].w += add;
-                if (o[s].w > W) { const int tw = o[s].w; const double td = o[s].dist; o[s].w = W; o[s].dist = (double)DI; W = tw; DI = (int)(uint32_t)(td + 0.5); }
-                return;
-            }
-        } else if (o[s].type == 0) { o[s].w = add; o[s].type = otype; o[s].dist = (double)len; return; }
+    const int nu = S.oth_n[t];
+    for (int s = 0; s < nu; s++) {
+        if (o[s].type == otype && (uint32_t)len == (uint32_t)(o[s].dist + 0.5)) {
+            o[s].w += add;
+            if (o[s].w > W) { const int tw = o[s].w; const double td = o[s].dist; o[s].w = W; o[s].dist = (double)DI; W = tw; DI = (int)(uint32_t)(td + 0.5); }
+            return;
+        }
+    }
+    if (nu < SV_OTHER) {
+        SvOther n_; n_.w = add; n_.type = otype; n_.mchr = 0; n_.rs = 0; n_.re = 0; n_.pad = 0; n_.dist = (double)len;
+        o[nu] = n_; S.oth_n[t] = nu + 1;
+        return;
     }
     for (int s = 0; s < SV_OTHER; s++)
         if (o[s].w <= add) { o[s].w = add; o[s].type = otype; o[s].dist = (double)len; o[s].rs = 0; o[s].re = 0; return; }
 }
 
 __global__ void __launch_bounds__(SV_T) k_sv_apply(const SvItem *__restrict__ items, const int2 *__restrict__ tile_rng, int64_t P, int64_t Ppad,
-                                                    int32_t *__restrict__ arrays, SvDev D, uint8_t *tile_dirty)
+                                                    int32_t *__restrict__ arrays, SvDev D, uint16_t *tile_dirty)
 {
     extern __shared__ __align__(16) uint8_t sv_smem_raw[];
     SvTileState &S = *reinterpret_cast<SvTileState *>(sv_smem_raw);
@@ -454,11 +456,10 @@ __global__ void __launch_bounds__(SV_T) k_sv_apply(const SvItem *__restrict__ it
     int any = 0;
     for (int k = rng.x + t; k < rng.y; k += SV_T) { const int lo = items[k].lo, hi = items[k].hi; if (hi > tile_lo && lo < tile_lo + SV_T) any = 1; }
     if (!__syncthreads_or(any)) return;
-    if (t == 0) tile_dirty[blockIdx.x] = 1;
     for (int k = 0; k < SV_NCLS; k++) S.w[k][t] = 0;
     for (int k = 0; k < 3; k++) S.idist[k][t] = 0;
     for (int k = 0; k < SV_NCL; k++) { S.rs[k][t] = 0; S.re[k][t] = 0; S.dist[k][t] = 0; }
-    S.mchr[0][t] = S.mchr[1][t] = 0; S.oth[t] = -1;
+    S.mchr[0][t] = S.mchr[1][t] = 0; S.oth[t] = -1; S.oth_n[t] = 0;
     for (int base = rng.x; base < rng.y; base += SV_T) {
         __syncthreads();
         const int cnt = min(SV_T, rng.y - base);
@@ -471,34 +472,48 @@ __global__ void __launch_bounds__(SV_T) k_sv_apply(const SvItem *__restrict__ it
             }
         }
     }
+    // write only the classes that occur in this tile (bit k of the tile mask; bit 13 = side slots); k_sv_clear undoes exactly these
+    unsigned mask = 0;
+    for (int k = 0; k < SV_NCLS; k++) if (S.w[k][t] != 0 || (k < SV_NCL && (S.dist[k][t] != 0 || S.rs[k][t] != 0 || S.re[k][t] != 0)) || (k >= SV_NCL && S.idist[k - SV_NCL][t] != 0)) mask |= 1u << k;
+    if (S.oth_n[t]) mask |= 1u << 13;
+    __shared__ unsigned s_mask;
+    if (t == 0) s_mask = 0;
+    __syncthreads();
+    mask = __reduce_or_sync(0xffffffffu, mask);
+    if ((t & 31) == 0 && mask) atomicOr(&s_mask, mask);
+    __syncthreads();
+    mask = s_mask;
+    if (t == 0) tile_dirty[blockIdx.x] = (uint16_t)mask;
     if (p < P) {
-        for (int k = 0; k < SV_NCL; k++) {
+        for (int k = 0; k < SV_NCL; k++) if (mask & (1u << k)) {
             D.cl_w[(int64_t)k * Ppad + p] = S.w[k][t]; D.cl_rs[(int64_t)k * Ppad + p] = S.rs[k][t]; D.cl_re[(int64_t)k * Ppad + p] = S.re[k][t];
             D.cl_dist[(int64_t)k * Ppad + p] = S.dist[k][t];
         }
-        D.cl_mchr[p] = S.mchr[0][t]; D.cl_mchr[Ppad + p] = S.mchr[1][t];
-        arrays[(int64_t)GA_INDEL_I * Ppad + p] = S.w[CL_INDEL_I][t]; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = S.idist[0][t];
-        arrays[(int64_t)GA_INDEL_D_F * Ppad + p] = S.w[CL_INDEL_D_F][t]; arrays[(int64_t)GA_INDEL_D_FDIST * Ppad + p] = S.idist[1][t];
-        arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = S.w[CL_INDEL_D_R][t]; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = S.idist[2][t];
-        int ol = 0;
-        if (S.oth[t] >= 0) { const SvOther *o = D.pool + (size_t)S.oth[t] * SV_OTHER; while (ol < SV_OTHER && o[ol].type != 0) ol++; }
-        D.other_len[p] = ol;
+        if (mask & (1u << CL_CTX_F)) D.cl_mchr[p] = S.mchr[0][t];
+        if (mask & (1u << CL_CTX_R)) D.cl_mchr[Ppad + p] = S.mchr[1][t];
+        if (mask & (1u << CL_INDEL_I)) { arrays[(int64_t)GA_INDEL_I * Ppad + p] = S.w[CL_INDEL_I][t]; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = S.idist[0][t]; }
+        if (mask & (1u << CL_INDEL_D_F)) { arrays[(int64_t)GA_INDEL_D_F * Ppad + p] = S.w[CL_INDEL_D_F][t]; arrays[(int64_t)GA_INDEL_D_FDIST * Ppad + p] = S.idist[1][t]; }
+        if (mask & (1u << CL_INDEL_D_R)) { arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = S.w[CL_INDEL_D_R][t]; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = S.idist[2][t]; }
+        if (mask & (1u << 13)) D.other_len[p] = S.oth_n[t];
     }
 }
 
 // zero the outputs of the tiles the previous run touched (everything else is still zero from allocation time)
-__global__ void __launch_bounds__(SV_T) k_sv_clear(uint8_t *tile_dirty, int64_t P, int64_t Ppad, int32_t *__restrict__ arrays, SvDev D)
+__global__ void __launch_bounds__(SV_T) k_sv_clear(uint16_t *tile_dirty, int64_t P, int64_t Ppad, int32_t *__restrict__ arrays, SvDev D)
 {
-    if (!tile_dirty[blockIdx.x]) return;
+    const unsigned mask = tile_dirty[blockIdx.x];
+    if (!mask) return;
     const int64_t p = (int64_t)blockIdx.x * SV_T + threadIdx.x;
     if (p < P) {
-        for (int k = 0; k < SV_NCL; k++) {
+        for (int k = 0; k < SV_NCL; k++) if (mask & (1u << k)) {
             D.cl_w[(int64_t)k * Ppad + p] = 0; D.cl_rs[(int64_t)k * Ppad + p] = 0; D.cl_re[(int64_t)k * Ppad + p] = 0; D.cl_dist[(int64_t)k * Ppad + p] = 0;
         }
-        D.cl_mchr[p] = 0; D.cl_mchr[Ppad + p] = 0; D.other_len[p] = 0;
-        arrays[(int64_t)GA_INDEL_I * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = 0;
-        arrays[(int64_t)GA_INDEL_D_F * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_D_FDIST * Ppad + p] = 0;
-        arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = 0;
+        if (mask & (1u << CL_CTX_F)) D.cl_mchr[p] = 0;
+        if (mask & (1u << CL_CTX_R)) D.cl_mchr[Ppad + p] = 0;
+        if (mask & (1u << 13)) D.other_len[p] = 0;
+        if (mask & (1u << CL_INDEL_I)) { arrays[(int64_t)GA_INDEL_I * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = 0; }
+        if (mask & (1u << CL_INDEL_D_F)) { arrays[(int64_t)GA_INDEL_D_F * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_D_FDIST * Ppad + p] = 0; }
+        if (mask & (1u << CL_INDEL_D_R)) { arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = 0; }
     }
     __syncthreads();
     if (threadIdx.x == 0) tile_dirty[blockIdx.x] = 0;

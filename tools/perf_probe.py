@@ -14,7 +14,7 @@ ap.add_argument("--simple", type=int, default=1)
 ap.add_argument("--rmdup", type=int, default=1)
 a = ap.parse_args()
 t = time.time()
-spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05)
+spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05, simple_disc_frac=0.01, names=False)
 c = synth.simulate(spec)[0]
 print("generated", c.batch.n_reads, "reads in", round(time.time() - t, 1), "s", flush=True)
 prm = Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=a.rmdup)

@@ -58,6 +58,7 @@ class SynthSpec:
     long_name_frac: float = 0.0005
     sa_frac: float = 0.5            # fraction of (>= 20 bp) soft-clipped reads that carry an SA tag
     simple: bool = False            # bench mode: only the vectorised read classes
+    simple_disc_frac: float = 0.0   # simple mode: vectorised deletion-like / inverted / mate-unmapped pairs (bench realism)
     names: bool = True              # False: no read-name strings (hash only; such a batch cannot be written as BAM)
 
 
@@ -364,6 +365,24 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
         truth = {"snv_pos": snv_pos, "snv_het": het, "sv": np.array(truth_sv, dtype=np.int64).reshape(-1, 2)}
     else:
         truth = {"snv_pos": snv_pos, "snv_het": het}
+        if spec.simple_disc_frac > 0:
+            # vectorised discordant classes: 60 % deletion-like (mate 2-20 kb downstream), 20 % same-strand (FF), 20 % mate unmapped
+            nd = int(n_pairs * spec.simple_disc_frac)
+            dp = rng.choice(n_pairs, nd, replace=False)
+            kind = rng.random(nd)
+            a_i, b_i = 2 * dp, 2 * dp + 1
+            far = kind < 0.8
+            d = rng.integers(2000, 20000, nd)
+            ok = far & (pos[b_i] + d + rl < length)
+            pos[b_i[ok]] += d[ok]; mpos[a_i[ok]] = pos[b_i[ok]]; tlen[a_i[ok]] += d[ok]; tlen[b_i[ok]] -= d[ok]
+            flag[a_i[ok]] &= ~FPROPER; flag[b_i[ok]] &= ~FPROPER
+            ff = ok & (kind >= 0.6)
+            flag[b_i[ff]] &= ~FREVERSE; flag[a_i[ff]] &= ~FMREVERSE
+            mb = b_i[ok]
+            codes[mb, :rl] = np.where((hpr[mb] == 0)[:, None], win0[pos[mb]], win1[pos[mb]])
+            mu = ~far
+            flag[a_i[mu]] |= FMUNMAP; flag[a_i[mu]] &= ~FPROPER; tlen[a_i[mu]] = 0; mpos[a_i[mu]] = pos[a_i[mu]]
+            flag[b_i[mu]] |= FUNMAP; flag[b_i[mu]] &= ~FPROPER; pos[b_i[mu]] = pos[a_i[mu]]; mpos[b_i[mu]] = pos[a_i[mu]]; tlen[b_i[mu]] = 0
 
     # names
     order = np.argsort(pos, kind="stable")
