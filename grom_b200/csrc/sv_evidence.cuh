@@ -40,10 +40,11 @@ struct __align__(8) SvOther { int w, type, mchr, rs, re, pad; double dist; };   
 
 struct SvDev {
     // outputs (dense, [class][Ppad]); zero-filled before the run, written only for touched tiles
-    int32_t *cl_w, *cl_rs, *cl_re, *cl_mchr, *other_len;
+    int32_t *cl_w, *cl_rs, *cl_re, *cl_mchr, *other_len, *ins_src;    // ins_src: [3][Ppad] read index, query offset, length of the stored inserted bases
     double *cl_dist;
     // other-slot pool
     SvOther *pool; int pool_cap; int *pool_used; int *err;
+    int32_t *ins_pos; int ins_pos_cap; int *n_ins_pos;     // compacted positions whose insertion slot weight reaches min_disc
 };
 
 struct SvReadArrays {                 // per-read SA fields (include/grom_reads.h)
@@ -94,12 +95,13 @@ __device__ void sv_read_items(const DevReads &R, const SvReadArrays &SA, int64_t
     const uint64_t coff = R.cigar_off[i];
     int start_adj = 0, end_adj = 0, indel = 0, lseq = lq;
     {
-        int64_t tp = pos;
+        int64_t tp = pos; int qoff = 0;
         for (int k = 0; k < ncig; k++) {
             const uint32_t c = R.cigar[coff + k];
             const int op = c & 15, len = (int)(c >> 4);
-            if (op == OP_M || op == OP_N || op == OP_EQ || op == OP_X) tp += len;
-            else if (op == OP_I) { indel += len; em.item(tp, tp + 1, CL_INDEL_I, len, 0, 0, AN_FULL, false, 0, add); }
+            if (op == OP_M || op == OP_N || op == OP_EQ || op == OP_X) { tp += len; if (op != OP_N) qoff += len; }
+            else if (op == OP_S) qoff += len;
+            else if (op == OP_I) { indel += len; em.item(tp, tp + 1, CL_INDEL_I, len, (int)i, 0, AN_FULL, false, 0, add, 0, qoff); qoff += len; }   // v = read index, mchr = query offset of the inserted bases
             else if (op == OP_D) {
                 indel -= len;
                 em.point(GA_INDEL_D_F_RD, tp, 1);
@@ -326,6 +328,7 @@ struct SvTileState {
     int rs[SV_NCL][SV_T], re[SV_NCL][SV_T];
     int mchr[2][SV_T];
     int oth[SV_T];                     // index into the other-slot pool, -1 = none
+    int ins_src[3][SV_T];              // read index / query offset / length of the inserted sequence last stored (src/GROM.c:7219-7228)
     int oth_n[SV_T];                   // side slots in use (slots are handed out in order and never freed, so slot oth_n is the first empty one)
     double dist[SV_NCL][SV_T];
 };
@@ -420,7 +423,10 @@ __device__ void sv_apply_indel(SvTileState &S, int t, const SvItem &it, const Sv
 {
     const int k = it.meta & 15, j = k - CL_INDEL_I, len = it.x, add = it.add;
     int &W = S.w[k][t]; int &DI = S.idist[j][t];
-    if (W == 0) { W = add; DI = len; return; }
+    if (W == 0) {
+        if (k == CL_INDEL_I && len <= c_prm.indel_i_seq_len) { S.ins_src[0][t] = it.v; S.ins_src[1][t] = it.mchr; S.ins_src[2][t] = len; }
+        W = add; DI = len; return;
+    }
     if (len == DI) { W += add; return; }
     SvOther *o = sv_others(S, t, D);
     if (!o) return;
@@ -459,7 +465,7 @@ __global__ void __launch_bounds__(SV_T) k_sv_apply(const SvItem *__restrict__ it
     for (int k = 0; k < SV_NCLS; k++) S.w[k][t] = 0;
     for (int k = 0; k < 3; k++) S.idist[k][t] = 0;
     for (int k = 0; k < SV_NCL; k++) { S.rs[k][t] = 0; S.re[k][t] = 0; S.dist[k][t] = 0; }
-    S.mchr[0][t] = S.mchr[1][t] = 0; S.oth[t] = -1; S.oth_n[t] = 0;
+    S.mchr[0][t] = S.mchr[1][t] = 0; S.oth[t] = -1; S.oth_n[t] = 0; S.ins_src[0][t] = S.ins_src[1][t] = S.ins_src[2][t] = 0;
     for (int base = rng.x; base < rng.y; base += SV_T) {
         __syncthreads();
         const int cnt = min(SV_T, rng.y - base);
@@ -491,10 +497,17 @@ __global__ void __launch_bounds__(SV_T) k_sv_apply(const SvItem *__restrict__ it
         }
         if (mask & (1u << CL_CTX_F)) D.cl_mchr[p] = S.mchr[0][t];
         if (mask & (1u << CL_CTX_R)) D.cl_mchr[Ppad + p] = S.mchr[1][t];
-        if (mask & (1u << CL_INDEL_I)) { arrays[(int64_t)GA_INDEL_I * Ppad + p] = S.w[CL_INDEL_I][t]; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = S.idist[0][t]; }
+        if (mask & (1u << CL_INDEL_I)) {
+            arrays[(int64_t)GA_INDEL_I * Ppad + p] = S.w[CL_INDEL_I][t]; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = S.idist[0][t];
+            D.ins_src[p] = S.ins_src[0][t]; D.ins_src[Ppad + p] = S.ins_src[1][t]; D.ins_src[2 * Ppad + p] = S.ins_src[2][t];
+        }
         if (mask & (1u << CL_INDEL_D_F)) { arrays[(int64_t)GA_INDEL_D_F * Ppad + p] = S.w[CL_INDEL_D_F][t]; arrays[(int64_t)GA_INDEL_D_FDIST * Ppad + p] = S.idist[1][t]; }
         if (mask & (1u << CL_INDEL_D_R)) { arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = S.w[CL_INDEL_D_R][t]; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = S.idist[2][t]; }
         if (mask & (1u << 13)) D.other_len[p] = S.oth_n[t];
+        if (S.w[CL_INDEL_I][t] / c_prm.add_factor >= c_prm.min_disc) {
+            const int k = atomicAdd(D.n_ins_pos, 1);
+            if (k < D.ins_pos_cap) D.ins_pos[k] = p; else atomicExch(D.err, 2);
+        }
     }
 }
 
@@ -511,7 +524,7 @@ __global__ void __launch_bounds__(SV_T) k_sv_clear(uint16_t *tile_dirty, int64_t
         if (mask & (1u << CL_CTX_F)) D.cl_mchr[p] = 0;
         if (mask & (1u << CL_CTX_R)) D.cl_mchr[Ppad + p] = 0;
         if (mask & (1u << 13)) D.other_len[p] = 0;
-        if (mask & (1u << CL_INDEL_I)) { arrays[(int64_t)GA_INDEL_I * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = 0; }
+        if (mask & (1u << CL_INDEL_I)) { arrays[(int64_t)GA_INDEL_I * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_IDIST * Ppad + p] = 0; D.ins_src[2 * Ppad + p] = 0; }
         if (mask & (1u << CL_INDEL_D_F)) { arrays[(int64_t)GA_INDEL_D_F * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_D_FDIST * Ppad + p] = 0; }
         if (mask & (1u << CL_INDEL_D_R)) { arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = 0; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = 0; }
     }

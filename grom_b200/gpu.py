@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-from .params import GA, GA_COUNT, Params, SNV_CAND_DTYPE
+from .params import GA, GA_COUNT, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE
 from .reads import CReadBatch, ReadBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -36,7 +36,7 @@ class Stats(C.Structure):
 
 class CResult(C.Structure):
     _fields_ = [("scan_first", C.c_int32), ("scan_last", C.c_int32), ("n_snv", C.c_int64), ("snv", C.c_void_p),
-                ("snv_ave_rd", C.c_double)]
+                ("snv_ave_rd", C.c_double), ("n_ins", C.c_int64), ("ins", C.c_void_p)]
 
 
 def lib() -> C.CDLL:
@@ -95,6 +95,7 @@ class ChrResult:
     scan_last: int
     snv: np.ndarray           # SNV_CAND_DTYPE, ascending position
     snv_ave_rd: float
+    ins: np.ndarray = None    # INS_CAND_DTYPE small-insertion candidates, ascending position
 
 
 class Chromosome:
@@ -130,7 +131,12 @@ class Chromosome:
             snv = np.frombuffer(buf, dtype=SNV_CAND_DTYPE, count=r.n_snv).copy()
         else:
             snv = np.zeros(0, dtype=SNV_CAND_DTYPE)
-        return ChrResult(r.scan_first, r.scan_last, snv, r.snv_ave_rd)
+        if r.n_ins:
+            buf = (C.c_char * (r.n_ins * INS_CAND_DTYPE.itemsize)).from_address(r.ins)
+            ins = np.frombuffer(buf, dtype=INS_CAND_DTYPE, count=r.n_ins).copy()
+        else:
+            ins = np.zeros(0, dtype=INS_CAND_DTYPE)
+        return ChrResult(r.scan_first, r.scan_last, snv, r.snv_ave_rd, ins)
 
     def finish(self) -> ChrResult:
         self.run()

@@ -65,3 +65,8 @@ GA_PILEUP_COUNT = 23
 SNV_CAND_DTYPE = np.dtype([("pos", np.int32), ("base", np.int32), ("ratio", np.float64), ("pr", np.float64),
                            ("hez", np.float64), ("v", np.int32, (GA_PILEUP_COUNT,)), ("reserved", np.int32)], align=True)
 assert SNV_CAND_DTYPE.itemsize == 128, SNV_CAND_DTYPE.itemsize
+
+INS_CAND_DTYPE = np.dtype([("pos", np.int32), ("dist", np.int32), ("pr", np.float64), ("hez", np.float64), ("conc", np.int32),
+                           ("weight", np.int32), ("rd", np.int32), ("sc", np.int32), ("other_len", np.int32), ("reserved", np.int32),
+                           ("seq", "S56")], align=True)
+assert INS_CAND_DTYPE.itemsize == 104, INS_CAND_DTYPE.itemsize

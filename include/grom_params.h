@@ -121,6 +121,21 @@ typedef struct grom_snv_cand {
     int32_t reserved;
 } grom_snv_cand;
 
+/* one small-insertion candidate = the record the reference appends at src/GROM.c:11400-11443 */
+typedef struct grom_ins_cand {
+    int32_t pos;                /* 0-based */
+    int32_t dist;               /* inserted length of the primary slot (indel_idist) */
+    double  pr;                 /* mq table value */
+    double  hez;                /* hez table value */
+    int32_t conc;               /* concordant-pair count at the position */
+    int32_t weight;             /* indel_i clamped to depth * 6 (cdp_indel_i_temp) */
+    int32_t rd;                 /* sum of snv + snv_lowmq */
+    int32_t sc;                 /* sc_left[pos+1] + sc_right[pos] */
+    int32_t other_len;
+    int32_t reserved;
+    char    seq[56];            /* first-seen inserted bases when dist <= 50 (src/GROM.c:7219-7228), NUL padded */
+} grom_ins_cand;
+
 #ifdef __cplusplus
 }
 #endif

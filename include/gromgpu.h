@@ -59,6 +59,8 @@ typedef struct gromgpu_result {
     int64_t n_snv;                      /* SNV candidates, ascending position */
     const grom_snv_cand *snv;           /* host memory owned by the handle, valid until chr_free / next run */
     double  snv_ave_rd;                 /* mean depth for the SNV emission filter (src/GROM.c:15035-15043) */
+    int64_t n_ins;                      /* small-insertion candidates (src/GROM.c:11400-11443), ascending position */
+    const grom_ins_cand *ins;           /* host memory owned by the handle */
 } gromgpu_result;
 
 /* Select the device, upload both 1001x1001 tables (row-major double) and the parameters.

@@ -83,6 +83,7 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
     }
     S.cmchr[0] = (int32_t *)calloc((size_t)P, 4); S.cmchr[1] = (int32_t *)calloc((size_t)P, 4);
     S.oth = (oslot **)calloc((size_t)P, sizeof(oslot *));
+    S.ins_seq = (char **)calloc((size_t)P, sizeof(char *));
 
     dupkey *dl = (dupkey *)malloc(sizeof(dupkey) * (size_t)p->rmdup_list_len);
     int dl_n = 0, old_pos = -1;
@@ -235,7 +236,7 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
              * per loop iteration incl. the skipped leading reads and wraps 3W/4 -> W/4 (src/GROM.c:5845-5847, 6317, 6408-6411) */
             int64_t pproc = (int64_t)pos - (int64_t)p->overlap_mult * p->insert_max; if (pproc < first_pos) pproc = first_pos;
             int64_t idx = W / 4 + ((i0 + 2 + (pproc - first_pos)) % (W / 2));
-            r.win_lo = pproc - idx;
+            r.win_lo = pproc - idx; r.read_index = i; r.batch = b;
             sv_evidence_read(&S, &r);
         }
     }
@@ -280,6 +281,37 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
             }
             if (have) { if (out->n_snv < out->snv_cap) out->snv[out->n_snv] = c; out->n_snv++; }
         }
+        /* ---- small-insertion gate per scanned position, src/GROM.c:11329-11453 */
+        out->n_ins = 0;
+        for (int64_t x = scan_first; x <= scan_last; x++) {
+            if (A.a[GA_RD][x] + A.a[GA_INDEL_SC_RD][x] <= 0) continue;
+            int rdt = 0;
+            for (int k = 0; k < 8; k++) rdt += A.a[GA_SNV_A + k][x];
+            int it = A.a[GA_INDEL_I][x];
+            const int af = p->add_factor;
+            if (it / af > rdt) it = rdt * af;
+            if (!(it / af >= p->min_disc) || rdt > p->max_trials) continue;
+            double pr = mq_tbl[(size_t)rdt * TD + it / af], hz;
+            if ((it + A.a[GA_INDEL_SC_LEFT][x]) / af < rdt) {
+                hz = hez_tbl[(size_t)rdt * TD + (it + A.a[GA_INDEL_SC_LEFT][x]) / af];
+                if ((it + A.a[GA_INDEL_SC_RIGHT][x]) / af < rdt) {
+                    double h2 = hez_tbl[(size_t)rdt * TD + (it + A.a[GA_INDEL_SC_RIGHT][x]) / af];
+                    if (h2 > hz) hz = h2;
+                } else hz = hez_tbl[(size_t)rdt * TD + rdt];
+            } else hz = hez_tbl[(size_t)rdt * TD + rdt];
+            if (!(pr <= p->pval_threshold1)) continue;
+            if (out->ins && out->n_ins < out->ins_cap) {
+                grom_ins_cand *c = &out->ins[out->n_ins];
+                memset(c, 0, sizeof(*c));
+                c->pos = (int32_t)x; c->dist = A.a[GA_INDEL_IDIST][x]; c->pr = pr; c->hez = hz; c->conc = A.a[GA_CONC][x]; c->weight = it; c->rd = rdt;
+                c->sc = (x + 1 < P ? A.a[GA_SC_LEFT][x + 1] : 0) + A.a[GA_SC_RIGHT][x];
+                int ol = 0; if (S.oth[x]) while (ol < p->other_len && S.oth[x][ol].type != OTHER_EMPTY) ol++;
+                c->other_len = ol;
+                if (c->dist <= p->indel_i_seq_len && S.ins_seq[x])
+                    for (int k = 0; k < c->dist && k < 50; k++) c->seq[k] = S.ins_seq[x][k];
+            }
+            out->n_ins++;
+        }
         /* ---- mean depth for the emission filter, src/GROM.c:15035-15043.  Upper bound = position of
          * window index 0 when the loop ends: (scan_last+1) - index(scan_last), where the window index
          * advances once per loop iteration (including one per skipped leading read) and wraps from
@@ -309,6 +341,8 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
         if (out->other_len) out->other_len[x] = ol;
     }
     free(S.oth);
+    for (int64_t x = 0; x < P; x++) free(S.ins_seq[x]);
+    free(S.ins_seq);
     free(nm_hash); free(nm_cnt); free(dl); free(c_type); free(c_len);
     return 0;
 }
@@ -337,6 +371,35 @@ int64_t oracle_format_snv_vcf(const grom_params *p, const char *chr_name, const 
                       c->v[GA_SNVLOW_A], c->v[GA_SNVLOW_C], c->v[GA_SNVLOW_G], c->v[GA_SNVLOW_T],
                       (double)c->v[GA_BQ_ALL] / (double)c->v[GA_RC_ALL], (double)c->v[GA_MQ_ALL] / (double)c->v[GA_RC_ALL],
                       (double)c->v[GA_PIR_A + c->base] / (double)nb, (double)c->v[GA_FS_A + c->base] / (double)nb);
+    }
+    return w;
+}
+
+/* src/GROM.c:16253-16340.  Bug-compatible homopolymer rule: the second run is counted against the character
+ * code fasta[pos] + 1 (src/GROM.c:16284), not against the next base.  END prints list_end + 1 = 0 (the field is
+ * initialised to -1 and never set, src/GROM.c:5545); ECO / EOT are uninitialised in the reference and printed as 0 here. */
+int64_t oracle_format_ins_vcf(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                              const grom_ins_cand *ins, int64_t n_ins, char *buf, int64_t cap)
+{
+    int64_t w = 0;
+    for (int64_t i = 0; i < n_ins; i++) {
+        const grom_ins_cand *c = &ins[i];
+        if (!(c->pr <= p->pval_threshold && (double)c->weight / (double)c->rd > p->min_indel_ratio * (double)p->add_factor)) continue;
+        int hp = 1;
+        char hc = fasta[c->pos];
+        for (int k = 1; k < 20; k++) { if (c->pos - k >= 0 && hc == fasta[c->pos - k]) hp++; else break; }
+        int hp2 = 1;
+        if (fasta[c->pos] + 1 < chr_len) {
+            hc = (char)(fasta[c->pos] + 1);
+            for (int k = 1; k < 20; k++) { if (c->pos + k + 1 < chr_len && hc == fasta[c->pos + k + 1]) hp2++; else break; }
+        }
+        if (hp2 > hp) hp = hp2;
+        if (hp > 10) continue;                                   /* g_max_homopolymer */
+        char alt[64];
+        if (c->dist <= p->indel_i_seq_len) { memcpy(alt, c->seq, (size_t)c->dist); alt[c->dist] = 0; } else strcpy(alt, "<INS>");
+        if (cap - w < 512) return -1;
+        w += snprintf(buf + w, (size_t)(cap - w), "%s\t%d\t.\t.\t%s\t.\t.\tEND=%d\tSPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP\t%e:%.1f:%d:%d:%d:%d:%d:%d:%d\n",
+                      chr_name, c->pos + 1, alt, 0, c->pr, (double)c->weight / (double)p->add_factor, c->rd, c->conc, 0, c->other_len, 0, c->sc, hp);
     }
     return w;
 }

@@ -40,6 +40,8 @@ typedef struct oracle_chr_out {
     double  *cl_dist;           /* [10][chr_len] running-mean distance (ctx: signed mate position) */
     int32_t *cl_mchr;           /* [2][chr_len]  mate contig of ctx_f / ctx_r */
     int32_t *other_len;         /* [chr_len] index of the first empty `other` slot */
+    grom_ins_cand *ins;         /* small-insertion candidates (src/GROM.c:11340-11453), caller-allocated [ins_cap] or NULL */
+    int64_t  ins_cap, n_ins;
 } oracle_chr_out;
 
 int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *fasta, int64_t chr_len,
@@ -51,6 +53,10 @@ void oracle_gc_prepass(const grom_params *p, const char *fasta, int64_t chr_len,
 /* format the SNV VCF lines the reference prints at src/GROM.c:15082-15095 into buf; returns bytes written */
 int64_t oracle_format_snv_vcf(const grom_params *p, const char *chr_name, const char *fasta,
                               const grom_snv_cand *snv, int64_t n_snv, double ave_rd, char *buf, int64_t cap);
+
+/* small-insertion VCF records as printed at src/GROM.c:16253-16340 (emission filter, homopolymer rule, text) */
+int64_t oracle_format_ins_vcf(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                              const grom_ins_cand *ins, int64_t n_ins, char *buf, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,7 @@ typedef struct {
     double *cdist[CL_COUNT];
     int32_t *cmchr[2];
     oslot **oth;                 /* per position, allocated on first use: other_len slots */
+    char **ins_seq;              /* per position, allocated on first use: the 50-char inserted-sequence row set (src/GROM.c:7219-7228) */
     int W;
 } svctx;
 
@@ -30,6 +31,8 @@ typedef struct {
     const uint32_t *cigar; int n_cigar;       /* capped at max_cigar_ops */
     int sa_pos, sa_strand, sa_mapq, sa_same, sa_start_adj, sa_end_adj, sa_end_adj_indel;
     int64_t win_lo;              /* reference position of window index 0 when this read is applied */
+    int64_t read_index;
+    const grom_read_batch *batch;
 } svread;
 
 

@@ -183,11 +183,25 @@ void sv_evidence_read(svctx *c, const svread *r)
 
     /* ---- CIGAR indels, src/GROM.c:7187-7423 */
     {
-        int64_t tp = pos;
+        int64_t tp = pos; int qoff = 0;
         for (int k = 0; k < r->n_cigar; k++) {
             int op = r->cigar[k] & 15, len = (int)(r->cigar[k] >> 4);
-            if (op == 0 || op == 3 || op == 7 || op == 8) tp += len;
-            else if (op == 1) indel_update(c, tp, GA_INDEL_I, GA_INDEL_IDIST, OTHER_INDEL_I, len, add);
+            if (op == 0 || op == 3 || op == 7 || op == 8) { tp += len; if (op != 3) qoff += len; }
+            else if (op == 4) qoff += len;
+            else if (op == 1) {
+                if (tp >= 0 && tp < c->P && c->A->a[GA_INDEL_I][tp] == 0 && len <= c->p->indel_i_seq_len) {
+                    /* the primary slot is (re)created: its first `len` sequence characters are overwritten, longer
+                     * leftovers of an earlier zero-weight creation stay (src/GROM.c:7219-7228) */
+                    if (!c->ins_seq[tp]) c->ins_seq[tp] = (char *)calloc(64, 1);
+                    const grom_read_batch *b = r->batch;
+                    for (int j = 0; j < len; j++) {
+                        uint64_t slot = b->base_off[r->read_index] + (uint64_t)(qoff + j);
+                        c->ins_seq[tp][j] = "=ACMGRSVTWYHKDBN"[(b->seq4[slot >> 1] >> ((~slot & 1) << 2)) & 15];
+                    }
+                }
+                indel_update(c, tp, GA_INDEL_I, GA_INDEL_IDIST, OTHER_INDEL_I, len, add);
+                qoff += len;
+            }
             else if (op == 2) {
                 if (tp >= 0 && tp < c->P) c->A->a[GA_INDEL_D_F_RD][tp] += 1;
                 indel_update(c, tp, GA_INDEL_D_F, GA_INDEL_D_FDIST, OTHER_INDEL_D_F, len, add);

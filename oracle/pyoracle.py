@@ -14,7 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
-from grom_b200.params import GA, GA_COUNT, GA_NAMES, Params, SNV_CAND_DTYPE  # noqa: E402
+from grom_b200.params import GA, GA_COUNT, GA_NAMES, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE  # noqa: E402
 from grom_b200.reads import CReadBatch, ReadBatch  # noqa: E402
 
 REF_DIR = os.path.join(_HERE, "_ref")
@@ -29,7 +29,7 @@ class COut(C.Structure):
                 ("scan_first", C.c_int32), ("scan_last", C.c_int32), ("lookahead_lseq", C.c_void_p),
                 ("snv", C.c_void_p), ("snv_cap", C.c_int64), ("n_snv", C.c_int64), ("snv_ave_rd", C.c_double),
                 ("cl_w", C.c_void_p), ("cl_rs", C.c_void_p), ("cl_re", C.c_void_p), ("cl_dist", C.c_void_p),
-                ("cl_mchr", C.c_void_p), ("other_len", C.c_void_p)]
+                ("cl_mchr", C.c_void_p), ("other_len", C.c_void_p), ("ins", C.c_void_p), ("ins_cap", C.c_int64), ("n_ins", C.c_int64)]
 
 
 _LIB = None
@@ -68,6 +68,7 @@ class OracleResult:
     cl_dist: np.ndarray = None  # [10, P] float64
     cl_mchr: np.ndarray = None  # [2, P]
     other_len: np.ndarray = None
+    ins: np.ndarray = None      # INS_CAND_DTYPE small-insertion candidates
 
     def __getitem__(self, name: str) -> np.ndarray:
         return self.arrays[GA[name]]
@@ -85,6 +86,8 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
     out = COut(chr_len=P, arrays=arrays.ctypes.data, read_state=state.ctypes.data, lookahead_lseq=look.ctypes.data,
                snv=snv.ctypes.data, snv_cap=snv_cap, cl_w=cl_w.ctypes.data, cl_rs=cl_rs.ctypes.data, cl_re=cl_re.ctypes.data,
                cl_dist=cl_dist.ctypes.data, cl_mchr=cl_mchr.ctypes.data, other_len=other_len.ctypes.data)
+    ins = np.zeros(1 << 16, dtype=INS_CAND_DTYPE)
+    out.ins = ins.ctypes.data; out.ins_cap = len(ins)
     cb = batch.as_c()
     fa = np.ascontiguousarray(fasta, dtype=np.uint8)
     rc = lib().oracle_run_chr(C.byref(params), C.byref(cb), fa.ctypes.data_as(C.c_char_p), P,
@@ -93,7 +96,7 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
         raise RuntimeError(f"oracle_run_chr failed: {rc}")
     assert out.n_snv <= snv_cap
     return OracleResult(arrays, state[:batch.n_reads], out.scan_first, out.scan_last, look, snv[:out.n_snv].copy(),
-                        out.snv_ave_rd, cl_w, cl_rs, cl_re, cl_dist, cl_mchr, other_len)
+                        out.snv_ave_rd, cl_w, cl_rs, cl_re, cl_dist, cl_mchr, other_len, ins[:min(out.n_ins, len(ins))].copy())
 
 
 def format_snv_vcf(params: Params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, ave_rd: float) -> str:
@@ -114,6 +117,19 @@ def gc_prepass(params: Params, fasta: np.ndarray):
     gc = np.zeros(P, dtype=np.int32); acgt = np.zeros(P, dtype=np.int32)
     lib().oracle_gc_prepass(C.byref(params), fa.ctypes.data_as(C.c_char_p), P, gc.ctypes.data, acgt.ctypes.data)
     return gc, acgt
+
+
+def format_ins_vcf(params: Params, chr_name: str, fasta: np.ndarray, ins: np.ndarray) -> str:
+    cap = 512 * (len(ins) + 1)
+    buf = C.create_string_buffer(cap)
+    fa = np.ascontiguousarray(fasta, dtype=np.uint8)
+    a = np.ascontiguousarray(ins)
+    L = lib()
+    L.oracle_format_ins_vcf.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64, C.c_char_p, C.c_int64]
+    L.oracle_format_ins_vcf.restype = C.c_int64
+    n = L.oracle_format_ins_vcf(C.byref(params), chr_name.encode(), fa.ctypes.data_as(C.c_char_p), len(fa), a.ctypes.data, len(a), buf, cap)
+    assert n >= 0
+    return buf.raw[:n].decode()
 
 
 # ---------------------------------------------------------------- reference runners
@@ -185,7 +201,7 @@ def normalise_records(lines):
         f = l.rstrip("\n").split("\t")
         if len(f) >= 10 and f[8] == "SPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP":
             v = f[9].split(":")
-            v[4] = "*"; v[6] = "*"
+            v[4] = "*"; v[6] = "*"          # ECO, EOT: never written for this record class
             f[9] = ":".join(v)
         out.append("\t".join(f) + "\n")
     return out

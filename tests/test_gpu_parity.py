@@ -36,6 +36,9 @@ def check_against_oracle(prm, batch, fasta, hez, mq, slices=None):
     assert np.array_equal(res.snv["pos"], ref.snv["pos"])
     for f in ("base", "ratio", "pr", "hez", "v"):
         assert np.array_equal(res.snv[f], ref.snv[f]), f
+    assert len(res.ins) == len(ref.ins)
+    for f in ("pos", "dist", "pr", "hez", "conc", "weight", "rd", "sc", "other_len", "seq"):
+        assert np.array_equal(res.ins[f], ref.ins[f]), ("insertion candidate", f)
     if len(ref.snv) or ref.scan_first >= 0:
         assert res.snv_ave_rd == ref.snv_ave_rd or (np.isnan(res.snv_ave_rd) and np.isnan(ref.snv_ave_rd))
     return res, got, state, st, ref
@@ -79,6 +82,9 @@ def test_gpu_reproduces_reference_golden(tag, rmdup):
         mine = po.format_snv_vcf(prm, n, fasta[name], res.snv, res.snv_ave_rd).splitlines(keepends=True)
         ref = [l for l in vcf if l.startswith(n + "\t") and l.split("\t")[2] == ""]
         assert mine == ref
+        mine = po.normalise_records(po.format_ins_vcf(prm, n, fasta[name], res.ins).splitlines(keepends=True))
+        ref = po.normalise_records([l for l in vcf if l.startswith(n + "\t") and "\tSPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP\t" in l])
+        assert len(ref) > 0 and mine == ref
 
 
 @pytest.mark.parametrize("seed,rmdup,read_len,depth", [(1, 0, 150, 30), (2, 1, 150, 30), (3, 1, 100, 60), (4, 0, 250, 10)])

@@ -58,6 +58,16 @@ with hostlib.Bam(bam) as b:
             bad = np.nonzero((r.cl_mchr[k][pos] != sd["v"][:, 81 + k]) & live)[0]
             if bad.size:
                 print(f"  {cn}.mchr mismatches {bad.size}"); bad_total += bad.size
+        vcf = [l for l in open("/tmp/cmpref.vcf") if not l.startswith("#")]
+        for kind, mine in (("SNV", po.format_snv_vcf(prm, name, c.chars, r.snv, r.snv_ave_rd)), ("INS", po.format_ins_vcf(prm, name, c.chars, r.ins))):
+            mine = po.normalise_records(mine.splitlines(keepends=True))
+            if kind == "SNV":
+                ref = [l for l in vcf if l.startswith(name + "\t") and l.split("\t")[2] == ""]
+            else:
+                ref = po.normalise_records([l for l in vcf if l.startswith(name + "\t") and "\tSPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP\t" in l])
+            print(f"  {kind} vcf lines mine/ref {len(mine)}/{len(ref)} identical {mine == ref}")
+            if mine != ref:
+                bad_total += 1
         bad = np.nonzero(r.other_len[pos] != sd["v"][:, 83])[0]
         if bad.size:
             bad_total += bad.size
