@@ -355,6 +355,7 @@ struct SnvScanArgs {
     unsigned long long *depth_sum;      // [0] sum of rd_rd + rd_low over non-N positions below depth_bound, [1] their count
     // small-insertion gate (src/GROM.c:11329-11453)
     grom_ins_cand *ins; unsigned int ins_cap; unsigned int *n_ins;
+    grom_del_event *del_ev; unsigned int del_cap; unsigned int *n_del;
     const int32_t *other_len, *ins_src;
 };
 
@@ -668,48 +669,73 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
     if (lane == 0 && dcnt) { atomicAdd(sc.depth_sum, dsum); atomicAdd(sc.depth_sum + 1, (unsigned long long)dcnt); }
 }
 
-// ---- small-insertion gate (src/GROM.c:11329-11453) over the (few) positions whose insertion slot carries enough weight;
-// the position list is compacted by k_sv_apply, the depth comes from the pileup arrays
-__global__ void __launch_bounds__(128) k_ins_gate(const int32_t *__restrict__ pos_list, const unsigned int *__restrict__ n_list, unsigned int list_cap,
-                                                   DevReads R, int64_t P, int64_t Ppad, const int32_t *__restrict__ arrays, SnvScanArgs sc)
+// ---- small-indel gates (src/GROM.c:11329-11745) over the (few) positions whose insertion / deletion-start / deletion-end
+// slot carries enough weight; the position list is compacted by k_sv_apply, the depth comes from the pileup arrays
+__global__ void __launch_bounds__(128) k_indel_gate(const int2 *__restrict__ pos_list, const unsigned int *__restrict__ n_list, unsigned int list_cap,
+                                                     DevReads R, int64_t P, int64_t Ppad, const int32_t *__restrict__ arrays, SnvScanArgs sc)
 {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= min(*n_list, list_cap)) return;
-    const int ip = pos_list[i];
+    const int2 pk = pos_list[i];
+    const int ip = pk.x;
     const int64_t p = ip;
     if (ip < sc.scan_first || ip > sc.scan_last) return;
-    int it = arrays[(int64_t)GA_INDEL_I * Ppad + p];
-    const int af = c_prm.add_factor;
     if (!(arrays[(int64_t)GA_RD * Ppad + p] + arrays[(int64_t)GA_INDEL_SC_RD * Ppad + p] > 0)) return;
-    const int rdt = arrays[(int64_t)GA_RC_ALL * Ppad + p];
-    if (it / af > rdt) it = rdt * af;
-    if (!(it / af >= c_prm.min_disc && rdt <= c_prm.max_trials)) return;
+    const int af = c_prm.add_factor;
+    const int base = arrays[(int64_t)GA_RC_ALL * Ppad + p];             // sum of snv + snv_lowmq
     const int TD = c_prm.max_trials + 1;
     const int scl = arrays[(int64_t)GA_INDEL_SC_LEFT * Ppad + p], scr = arrays[(int64_t)GA_INDEL_SC_RIGHT * Ppad + p];
-    const double pr = sc.mqt[(size_t)rdt * TD + it / af];
-    double hz;
-    if ((it + scl) / af < rdt) {
-        hz = sc.hez[(size_t)rdt * TD + (it + scl) / af];
-        if ((it + scr) / af < rdt) { const double h2 = sc.hez[(size_t)rdt * TD + (it + scr) / af]; if (h2 > hz) hz = h2; }
-        else hz = sc.hez[(size_t)rdt * TD + rdt];
-    } else hz = sc.hez[(size_t)rdt * TD + rdt];
-    if (!(pr <= c_prm.pval_threshold1)) return;
-    const unsigned slot = atomicAdd(sc.n_ins, 1u);
-    if (slot >= sc.ins_cap) return;
-    grom_ins_cand *c = sc.ins + slot;
-    c->pos = ip; c->dist = arrays[(int64_t)GA_INDEL_IDIST * Ppad + p]; c->pr = pr; c->hez = hz;
-    c->conc = arrays[(int64_t)GA_CONC * Ppad + p]; c->weight = it; c->rd = rdt;
-    c->sc = (p + 1 < P ? arrays[(int64_t)GA_SC_LEFT * Ppad + p + 1] : 0) + arrays[(int64_t)GA_SC_RIGHT * Ppad + p];
-    c->other_len = sc.other_len[p]; c->reserved = 0;
-    for (int k = 0; k < 56; k++) c->seq[k] = 0;
-    if (c->dist <= c_prm.indel_i_seq_len) {
-        // characters of the creation that is still visible; longer leftovers of an earlier zero-weight creation
-        // (the reference keeps them, src/GROM.c:7219-7228) are not tracked on the device
-        const int64_t ri = sc.ins_src[p]; const int qo = sc.ins_src[Ppad + p], sl = min(sc.ins_src[2 * Ppad + p], c->dist);
-        const uint64_t bo = R.base_off[ri];
-        for (int k = 0; k < sl; k++) {
-            const uint64_t slot2 = bo + (uint64_t)(qo + k);
-            c->seq[k] = "=ACMGRSVTWYHKDBN"[(R.seq4[slot2 >> 1] >> ((~(int)slot2 & 1) << 2)) & 15];
+    if (pk.y & 1) {                                                     // insertion, src/GROM.c:11329-11453
+        int it = arrays[(int64_t)GA_INDEL_I * Ppad + p];
+        const int rdt = base;
+        if (it / af > rdt) it = rdt * af;
+        if (it / af >= c_prm.min_disc && rdt <= c_prm.max_trials) {
+            const double pr = sc.mqt[(size_t)rdt * TD + it / af];
+            double hz;
+            if ((it + scl) / af < rdt) {
+                hz = sc.hez[(size_t)rdt * TD + (it + scl) / af];
+                if ((it + scr) / af < rdt) { const double h2 = sc.hez[(size_t)rdt * TD + (it + scr) / af]; if (h2 > hz) hz = h2; }
+                else hz = sc.hez[(size_t)rdt * TD + rdt];
+            } else hz = sc.hez[(size_t)rdt * TD + rdt];
+            if (pr <= c_prm.pval_threshold1) {
+                const unsigned slot = atomicAdd(sc.n_ins, 1u);
+                if (slot < sc.ins_cap) {
+                    grom_ins_cand *c = sc.ins + slot;
+                    c->pos = ip; c->dist = arrays[(int64_t)GA_INDEL_IDIST * Ppad + p]; c->pr = pr; c->hez = hz;
+                    c->conc = arrays[(int64_t)GA_CONC * Ppad + p]; c->weight = it; c->rd = rdt;
+                    c->sc = (p + 1 < P ? arrays[(int64_t)GA_SC_LEFT * Ppad + p + 1] : 0) + arrays[(int64_t)GA_SC_RIGHT * Ppad + p];
+                    c->other_len = sc.other_len[p]; c->reserved = 0;
+                    for (int k = 0; k < 56; k++) c->seq[k] = 0;
+                    if (c->dist <= c_prm.indel_i_seq_len) {
+                        // characters of the creation that is still visible; longer leftovers of an earlier zero-weight creation
+                        // (the reference keeps them, src/GROM.c:7219-7228) are not tracked on the device
+                        const int64_t ri = sc.ins_src[p]; const int qo = sc.ins_src[Ppad + p], sl = min(sc.ins_src[2 * Ppad + p], c->dist);
+                        const uint64_t bo = R.base_off[ri];
+                        for (int k = 0; k < sl; k++) {
+                            const uint64_t slot2 = bo + (uint64_t)(qo + k);
+                            c->seq[k] = "=ACMGRSVTWYHKDBN"[(R.seq4[slot2 >> 1] >> ((~(int)slot2 & 1) << 2)) & 15];
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int kind = 0; kind < 2; kind++) {                             // deletion start / end, src/GROM.c:11454-11745
+        if (!(pk.y & (2 << kind))) continue;
+        const int wt = arrays[(int64_t)(kind ? GA_INDEL_D_R : GA_INDEL_D_F) * Ppad + p];
+        const int rdt = wt / af + base;
+        if (!(wt / af >= c_prm.min_disc) || rdt > c_prm.max_trials) continue;
+        const int scv = kind ? scl : scr;
+        const double pr = sc.mqt[(size_t)rdt * TD + wt / af];
+        const double hz = ((wt + scv) / af < rdt) ? sc.hez[(size_t)rdt * TD + (wt + scv) / af] : sc.hez[(size_t)rdt * TD + rdt];
+        if (!(pr <= c_prm.pval_threshold1)) continue;
+        const unsigned slot = atomicAdd(sc.n_del, 1u);
+        if (slot < sc.del_cap) {
+            grom_del_event *e = sc.del_ev + slot;
+            e->pos = ip; e->kind = kind; e->pr = pr; e->hez = hz; e->conc = arrays[(int64_t)GA_CONC * Ppad + p]; e->weight = wt; e->rd = rdt;
+            e->sc = arrays[(int64_t)(kind ? GA_SC_LEFT : GA_SC_RIGHT) * Ppad + p]; e->other_len = sc.other_len[p];
+            e->rdist = arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p];
         }
     }
 }
@@ -945,7 +971,8 @@ struct gromgpu_chr {
     unsigned long long *d_scan_status = nullptr; unsigned int *d_ticket = nullptr; size_t cap_scan = 0;
     grom_snv_cand *d_cand = nullptr; unsigned int cand_cap = 0; unsigned int *d_ncand = nullptr;
     grom_ins_cand *d_ins = nullptr; unsigned int ins_cap = 0; std::vector<grom_ins_cand> h_ins;
-    int32_t *d_ins_pos = nullptr; unsigned int ins_pos_cap = 0;     // positions whose insertion slot reaches min_disc (compacted by k_sv_apply)
+    int2 *d_ins_pos = nullptr; unsigned int ins_pos_cap = 0;        // (position, slot mask) whose indel slots reach min_disc (compacted by k_sv_apply)
+    grom_del_event *d_del = nullptr; unsigned int del_cap = 0; std::vector<grom_del_event> h_del;
     // SV / indel evidence (sv_evidence.cuh)
     int32_t *d_item_cnt = nullptr; size_t cap_item_cnt = 0;
     SvItem *d_items = nullptr; size_t cap_items = 0;
@@ -1017,7 +1044,7 @@ extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, 
     CK(cudaMalloc(&h->d_max_span, sizeof(int)));
     CK(cudaMalloc(&h->d_counters, sizeof(unsigned long long) * 8));
     CK(cudaMalloc(&h->d_ticket, sizeof(unsigned int) * 8));
-    CK(cudaMalloc(&h->d_ncand, sizeof(unsigned int) * 2));
+    CK(cudaMalloc(&h->d_ncand, sizeof(unsigned int) * 4));
     for (int i = 0; i < 12; i++) CK(cudaEventCreate(&h->ev[i]));
     CK(cudaMalloc(&h->d_cl_int, sizeof(int32_t) * 36 * (size_t)h->Ppad));
     CK(cudaMalloc(&h->d_cl_dist, sizeof(double) * 10 * (size_t)h->Ppad));
@@ -1055,7 +1082,7 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
     for (int i = 0; i < B_COUNT; i++) h->rb[i].release();
     cudaFree(h->d_fasta); cudaFree(h->d_arrays); cudaFree(h->d_state); cudaFree(h->d_prep); cudaFree(h->d_tile_first);
     cudaFree(h->d_max_span); cudaFree(h->d_counters); cudaFree(h->d_scan_status); cudaFree(h->d_ticket);
-    cudaFree(h->d_cand); cudaFree(h->d_ncand); cudaFree(h->d_ins); cudaFree(h->d_ins_pos);
+    cudaFree(h->d_cand); cudaFree(h->d_ncand); cudaFree(h->d_ins); cudaFree(h->d_ins_pos); cudaFree(h->d_del);
     for (int i = 0; i < 12; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_item_cnt); cudaFree(h->d_items); cudaFree(h->d_sv_tiles); cudaFree(h->d_sv_dirty); cudaFree(h->d_sv_small); cudaFree(h->d_pool);
     cudaFree(h->d_cl_int); cudaFree(h->d_cl_dist);
@@ -1130,7 +1157,8 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     if ((size_t)n_tiles > h->cap_tiles) { cudaFree(h->d_tile_first); h->cap_tiles = (size_t)n_tiles; CK(cudaMalloc(&h->d_tile_first, sizeof(int64_t) * h->cap_tiles)); }
     if (!h->d_cand) { h->cand_cap = 1u << 20; CK(cudaMalloc(&h->d_cand, sizeof(grom_snv_cand) * (size_t)h->cand_cap)); }
     if (!h->d_ins) { h->ins_cap = 1u << 18; CK(cudaMalloc(&h->d_ins, sizeof(grom_ins_cand) * (size_t)h->ins_cap)); }
-    if (!h->d_ins_pos) { h->ins_pos_cap = 1u << 20; CK(cudaMalloc(&h->d_ins_pos, sizeof(int32_t) * (size_t)h->ins_pos_cap)); }
+    if (!h->d_ins_pos) { h->ins_pos_cap = 1u << 20; CK(cudaMalloc(&h->d_ins_pos, sizeof(int2) * (size_t)h->ins_pos_cap)); }
+    if (!h->d_del) { h->del_cap = 1u << 19; CK(cudaMalloc(&h->d_del, sizeof(grom_del_event) * (size_t)h->del_cap)); }
     const int64_t n_cnt_pad = (n + 1023) & ~(int64_t)1023;
     const int64_t n_cnt_tiles = (n_cnt_pad + SCAN_TILE - 1) / SCAN_TILE;
     if ((size_t)n_cnt_pad > h->cap_item_cnt) { cudaFree(h->d_item_cnt); h->cap_item_cnt = (size_t)n_cnt_pad + (size_t)n_cnt_pad / 8; CK(cudaMalloc(&h->d_item_cnt, sizeof(int32_t) * h->cap_item_cnt)); }
@@ -1167,7 +1195,7 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     CK(cudaMemsetAsync(h->d_max_span, 0, sizeof(int), s));
     CK(cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long) * 8, s));
     CK(cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int) * 8, s));
-    CK(cudaMemsetAsync(h->d_ncand, 0, sizeof(unsigned int) * 2, s));
+    CK(cudaMemsetAsync(h->d_ncand, 0, sizeof(unsigned int) * 4, s));
     CK(cudaMemsetAsync(h->d_scan_status, 0, sizeof(unsigned long long) * ((size_t)n_scan_tiles * 5 + (size_t)n_cnt_tiles), s));
     CK(cudaEventRecord(h->ev[1], s));
     {
@@ -1224,11 +1252,11 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     SnvScanArgs sca;
     sca.scan_first = scan_first; sca.scan_last = scan_last; sca.depth_bound = depth_bound; sca.hez = d_hez; sca.mqt = d_mq;
     sca.cand = h->d_cand; sca.cand_cap = h->cand_cap; sca.n_cand = h->d_ncand; sca.depth_sum = h->d_counters + 4;
-    sca.ins = h->d_ins; sca.ins_cap = h->ins_cap; sca.n_ins = h->d_ncand + 1; sca.other_len = SD.other_len; sca.ins_src = SD.ins_src;
+    sca.ins = h->d_ins; sca.ins_cap = h->ins_cap; sca.n_ins = h->d_ncand + 1; sca.del_ev = h->d_del; sca.del_cap = h->del_cap; sca.n_del = h->d_ncand + 2; sca.other_len = SD.other_len; sca.ins_src = SD.ins_src;
     k_pileup<<<(unsigned)((n_tiles + SUBTILES - 1) / SUBTILES), PILE_THREADS, sizeof(PileSmem), s>>>(R, h->d_prep, h->d_tile_first, h->d_max_span, n_tiles,
                                                                                                    h->d_fasta, P, Ppad, h->d_arrays, sca); launches++;
     CK(cudaEventRecord(h->ev[6], s));
-    k_ins_gate<<<(h->ins_pos_cap + 127) / 128, 128, 0, s>>>(h->d_ins_pos, (const unsigned int *)(h->d_sv_small + 4), h->ins_pos_cap, R, P, Ppad, h->d_arrays, sca); launches++;
+    k_indel_gate<<<(h->ins_pos_cap + 127) / 128, 128, 0, s>>>(h->d_ins_pos, (const unsigned int *)(h->d_sv_small + 4), h->ins_pos_cap, R, P, Ppad, h->d_arrays, sca); launches++;
     CK(cudaEventRecord(h->ev[7], s));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
@@ -1278,6 +1306,13 @@ extern "C" int gromgpu_chr_result(gromgpu_chr *h, gromgpu_result *out)
     if (ni) CK(cudaMemcpy(h->h_ins.data(), h->d_ins, sizeof(grom_ins_cand) * (size_t)ni, cudaMemcpyDeviceToHost));
     std::sort(h->h_ins.begin(), h->h_ins.end(), [](const grom_ins_cand &a, const grom_ins_cand &b) { return a.pos < b.pos; });
     h->res.n_ins = ni; h->res.ins = h->h_ins.data();
+    unsigned int nd = 0;
+    CK(cudaMemcpy(&nd, h->d_ncand + 2, sizeof(nd), cudaMemcpyDeviceToHost));
+    if (nd > h->del_cap) return fail("gromgpu_chr_result: %u deletion events exceed the buffer of %u", nd, h->del_cap);
+    h->h_del.resize(nd);
+    if (nd) CK(cudaMemcpy(h->h_del.data(), h->d_del, sizeof(grom_del_event) * (size_t)nd, cudaMemcpyDeviceToHost));
+    std::sort(h->h_del.begin(), h->h_del.end(), [](const grom_del_event &a, const grom_del_event &b) { return a.pos != b.pos ? a.pos < b.pos : a.kind < b.kind; });
+    h->res.n_del = nd; h->res.del_ev = h->h_del.data();
     *out = h->res;
     return 0;
 }

@@ -44,7 +44,7 @@ struct SvDev {
     double *cl_dist;
     // other-slot pool
     SvOther *pool; int pool_cap; int *pool_used; int *err;
-    int32_t *ins_pos; int ins_pos_cap; int *n_ins_pos;     // compacted positions whose insertion slot weight reaches min_disc
+    int2 *ins_pos; int ins_pos_cap; int *n_ins_pos;        // compacted (position, slot mask) whose insertion / deletion-start / deletion-end slot weight reaches min_disc
 };
 
 struct SvReadArrays {                 // per-read SA fields (include/grom_reads.h)
@@ -504,9 +504,11 @@ __global__ void __launch_bounds__(SV_T) k_sv_apply(const SvItem *__restrict__ it
         if (mask & (1u << CL_INDEL_D_F)) { arrays[(int64_t)GA_INDEL_D_F * Ppad + p] = S.w[CL_INDEL_D_F][t]; arrays[(int64_t)GA_INDEL_D_FDIST * Ppad + p] = S.idist[1][t]; }
         if (mask & (1u << CL_INDEL_D_R)) { arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = S.w[CL_INDEL_D_R][t]; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = S.idist[2][t]; }
         if (mask & (1u << 13)) D.other_len[p] = S.oth_n[t];
-        if (S.w[CL_INDEL_I][t] / c_prm.add_factor >= c_prm.min_disc) {
+        const int af = c_prm.add_factor, md = c_prm.min_disc;
+        const int km = (S.w[CL_INDEL_I][t] / af >= md ? 1 : 0) | (S.w[CL_INDEL_D_F][t] / af >= md ? 2 : 0) | (S.w[CL_INDEL_D_R][t] / af >= md ? 4 : 0);
+        if (km) {
             const int k = atomicAdd(D.n_ins_pos, 1);
-            if (k < D.ins_pos_cap) D.ins_pos[k] = p; else atomicExch(D.err, 2);
+            if (k < D.ins_pos_cap) D.ins_pos[k] = make_int2(p, km); else atomicExch(D.err, 2);
         }
     }
 }

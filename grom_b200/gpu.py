@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-from .params import GA, GA_COUNT, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE
+from .params import DEL_EVENT_DTYPE, GA, GA_COUNT, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE
 from .reads import CReadBatch, ReadBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -36,7 +36,7 @@ class Stats(C.Structure):
 
 class CResult(C.Structure):
     _fields_ = [("scan_first", C.c_int32), ("scan_last", C.c_int32), ("n_snv", C.c_int64), ("snv", C.c_void_p),
-                ("snv_ave_rd", C.c_double), ("n_ins", C.c_int64), ("ins", C.c_void_p)]
+                ("snv_ave_rd", C.c_double), ("n_ins", C.c_int64), ("ins", C.c_void_p), ("n_del", C.c_int64), ("del_ev", C.c_void_p)]
 
 
 def lib() -> C.CDLL:
@@ -96,6 +96,7 @@ class ChrResult:
     snv: np.ndarray           # SNV_CAND_DTYPE, ascending position
     snv_ave_rd: float
     ins: np.ndarray = None    # INS_CAND_DTYPE small-insertion candidates, ascending position
+    del_ev: np.ndarray = None  # DEL_EVENT_DTYPE small-deletion scan events (position, start before end)
 
 
 class Chromosome:
@@ -136,7 +137,12 @@ class Chromosome:
             ins = np.frombuffer(buf, dtype=INS_CAND_DTYPE, count=r.n_ins).copy()
         else:
             ins = np.zeros(0, dtype=INS_CAND_DTYPE)
-        return ChrResult(r.scan_first, r.scan_last, snv, r.snv_ave_rd, ins)
+        if r.n_del:
+            buf = (C.c_char * (r.n_del * DEL_EVENT_DTYPE.itemsize)).from_address(r.del_ev)
+            dev = np.frombuffer(buf, dtype=DEL_EVENT_DTYPE, count=r.n_del).copy()
+        else:
+            dev = np.zeros(0, dtype=DEL_EVENT_DTYPE)
+        return ChrResult(r.scan_first, r.scan_last, snv, r.snv_ave_rd, ins, dev)
 
     def finish(self) -> ChrResult:
         self.run()

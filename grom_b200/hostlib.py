@@ -123,3 +123,36 @@ def pval2sd():
     n = L.gromhost_pval2sd(pv.ctypes.data, sd.ctypes.data, 1001)
     assert n == 1001
     return pv, sd
+
+
+def _vcf(fn_name, params, chr_name, fasta, *args):
+    from .params import Params
+    L = lib()
+    fn = getattr(L, fn_name)
+    fn.restype = C.c_int64
+    fa = np.ascontiguousarray(fasta, dtype=np.uint8)
+    cap = 1 << 16
+    while True:
+        buf = C.create_string_buffer(cap)
+        n = fn(C.byref(params), chr_name.encode(), fa.ctypes.data_as(C.c_char_p), *args, buf, C.c_int64(cap))
+        if n >= 0:
+            return buf.raw[:n].decode()
+        cap *= 4
+
+
+def vcf_snv(params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, ave_rd: float) -> str:
+    """SNV records (reference src/GROM.c:15046-15095) from the candidates gromgpu_chr_result returns."""
+    a = np.ascontiguousarray(snv)
+    return _vcf("gromhost_vcf_snv", params, chr_name, fasta, C.c_void_p(a.ctypes.data), C.c_int64(len(a)), C.c_double(ave_rd))
+
+
+def vcf_ins(params, chr_name: str, fasta: np.ndarray, ins: np.ndarray) -> str:
+    """Small-insertion records (reference src/GROM.c:16253-16340)."""
+    a = np.ascontiguousarray(ins)
+    return _vcf("gromhost_vcf_ins", params, chr_name, fasta, C.c_int64(len(fasta)), C.c_void_p(a.ctypes.data), C.c_int64(len(a)))
+
+
+def vcf_smalldel(params, chr_name: str, fasta: np.ndarray, events: np.ndarray) -> str:
+    """Small-deletion records: pairing state machine + filter + text (reference src/GROM.c:11475-11745, 16351-16490)."""
+    a = np.ascontiguousarray(events)
+    return _vcf("gromhost_vcf_smalldel", params, chr_name, fasta, C.c_int64(len(fasta)), C.c_void_p(a.ctypes.data), C.c_int64(len(a)))

@@ -70,3 +70,7 @@ INS_CAND_DTYPE = np.dtype([("pos", np.int32), ("dist", np.int32), ("pr", np.floa
                            ("weight", np.int32), ("rd", np.int32), ("sc", np.int32), ("other_len", np.int32), ("reserved", np.int32),
                            ("seq", "S56")], align=True)
 assert INS_CAND_DTYPE.itemsize == 104, INS_CAND_DTYPE.itemsize
+
+DEL_EVENT_DTYPE = np.dtype([("pos", np.int32), ("kind", np.int32), ("pr", np.float64), ("hez", np.float64), ("conc", np.int32),
+                            ("weight", np.int32), ("rd", np.int32), ("sc", np.int32), ("other_len", np.int32), ("rdist", np.int32)], align=True)
+assert DEL_EVENT_DTYPE.itemsize == 48, DEL_EVENT_DTYPE.itemsize

@@ -136,6 +136,22 @@ typedef struct grom_ins_cand {
     char    seq[56];            /* first-seen inserted bases when dist <= 50 (src/GROM.c:7219-7228), NUL padded */
 } grom_ins_cand;
 
+/* one small-deletion scan event: position whose deletion-start slot (kind 0, indel_d_f, src/GROM.c:11454-11563) or
+ * deletion-end slot (kind 1, indel_d_r, src/GROM.c:11630-11745) passes the binomial gate.  The host pairs them with the
+ * reference's sequential state machine. */
+typedef struct grom_del_event {
+    int32_t pos;                /* 0-based */
+    int32_t kind;               /* 0 = start (indel_d_f), 1 = end (indel_d_r) */
+    double  pr;                 /* mq table value */
+    double  hez;                /* hez table value */
+    int32_t conc;
+    int32_t weight;             /* indel_d_f / indel_d_r */
+    int32_t rd;                 /* weight/6 + sum of snv + snv_lowmq */
+    int32_t sc;                 /* sc_right (start) / sc_left (end) */
+    int32_t other_len;
+    int32_t rdist;              /* indel_d_rdist (end events) */
+} grom_del_event;
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,8 @@ typedef struct gromgpu_result {
     double  snv_ave_rd;                 /* mean depth for the SNV emission filter (src/GROM.c:15035-15043) */
     int64_t n_ins;                      /* small-insertion candidates (src/GROM.c:11400-11443), ascending position */
     const grom_ins_cand *ins;           /* host memory owned by the handle */
+    int64_t n_del;                      /* small-deletion scan events (src/GROM.c:11454-11745), by position, start before end */
+    const grom_del_event *del_ev;       /* feed to gromhost_vcf_smalldel() */
 } gromgpu_result;
 
 /* Select the device, upload both 1001x1001 tables (row-major double) and the parameters.

@@ -18,6 +18,7 @@
 #define GROMHOST_H
 #include <stdint.h>
 #include "grom_reads.h"
+#include "grom_params.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -63,6 +64,16 @@ int    gromhost_tables_get(const char *dir, int min_mapq, int write_missing, dou
 void   gromhost_table_paths(const char *dir, int min_mapq, char *hez_path, char *mq_path, int cap);
 double gromhost_mq_prob(int min_mapq);
 int    gromhost_pval2sd(double *pval, double *sd, int cap);   /* returns the length (1001) */
+
+/* ---- host stages of the scan: emission filters + VCF record text (reference src/GROM.c:15046-15095, 16253-16340,
+ * 11475-11745 + 16351-16490).  Each returns the number of bytes written to buf, or -1 if cap is too small.
+ * Candidates / events must be in ascending position (events: start before end at equal position). */
+int64_t gromhost_vcf_snv(const grom_params *p, const char *chr_name, const char *fasta,
+                         const grom_snv_cand *snv, int64_t n, double ave_rd, char *buf, int64_t cap);
+int64_t gromhost_vcf_ins(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                         const grom_ins_cand *ins, int64_t n, char *buf, int64_t cap);
+int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                              const grom_del_event *ev, int64_t n, char *buf, int64_t cap);
 
 #ifdef __cplusplus
 }

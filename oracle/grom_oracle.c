@@ -312,6 +312,31 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
             }
             out->n_ins++;
         }
+        /* ---- small-deletion start / end gates per scanned position, src/GROM.c:11454-11745 (events; the pairing state
+         * machine runs on the host over this compact stream) */
+        out->n_del = 0;
+        for (int64_t x = scan_first; x <= scan_last; x++) {
+            if (A.a[GA_RD][x] + A.a[GA_INDEL_SC_RD][x] <= 0) continue;
+            int base = 0;
+            for (int k = 0; k < 8; k++) base += A.a[GA_SNV_A + k][x];
+            const int af = p->add_factor;
+            int ol = 0; if (S.oth[x]) while (ol < p->other_len && S.oth[x][ol].type != OTHER_EMPTY) ol++;
+            for (int kind = 0; kind < 2; kind++) {
+                const int wt = A.a[kind ? GA_INDEL_D_R : GA_INDEL_D_F][x];
+                const int rdt = wt / af + base;
+                if (!(wt / af >= p->min_disc) || rdt > p->max_trials) continue;
+                const int scv = A.a[kind ? GA_INDEL_SC_LEFT : GA_INDEL_SC_RIGHT][x];
+                const double pr = mq_tbl[(size_t)rdt * TD + wt / af];
+                const double hz = ((wt + scv) / af < rdt) ? hez_tbl[(size_t)rdt * TD + (wt + scv) / af] : hez_tbl[(size_t)rdt * TD + rdt];
+                if (!(pr <= p->pval_threshold1)) continue;
+                if (out->del_ev && out->n_del < out->del_cap) {
+                    grom_del_event *e = &out->del_ev[out->n_del];
+                    e->pos = (int32_t)x; e->kind = kind; e->pr = pr; e->hez = hz; e->conc = A.a[GA_CONC][x]; e->weight = wt; e->rd = rdt;
+                    e->sc = A.a[kind ? GA_SC_LEFT : GA_SC_RIGHT][x]; e->other_len = ol; e->rdist = A.a[GA_INDEL_D_RDIST][x];
+                }
+                out->n_del++;
+            }
+        }
         /* ---- mean depth for the emission filter, src/GROM.c:15035-15043.  Upper bound = position of
          * window index 0 when the loop ends: (scan_last+1) - index(scan_last), where the window index
          * advances once per loop iteration (including one per skipped leading read) and wraps from

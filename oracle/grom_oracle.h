@@ -42,6 +42,8 @@ typedef struct oracle_chr_out {
     int32_t *other_len;         /* [chr_len] index of the first empty `other` slot */
     grom_ins_cand *ins;         /* small-insertion candidates (src/GROM.c:11340-11453), caller-allocated [ins_cap] or NULL */
     int64_t  ins_cap, n_ins;
+    grom_del_event *del_ev;     /* small-deletion scan events in scan order (src/GROM.c:11454-11745), caller-allocated or NULL */
+    int64_t  del_cap, n_del;
 } oracle_chr_out;
 
 int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *fasta, int64_t chr_len,

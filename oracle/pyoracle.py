@@ -14,7 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
-from grom_b200.params import GA, GA_COUNT, GA_NAMES, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE  # noqa: E402
+from grom_b200.params import DEL_EVENT_DTYPE, GA, GA_COUNT, GA_NAMES, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE  # noqa: E402
 from grom_b200.reads import CReadBatch, ReadBatch  # noqa: E402
 
 REF_DIR = os.path.join(_HERE, "_ref")
@@ -29,7 +29,8 @@ class COut(C.Structure):
                 ("scan_first", C.c_int32), ("scan_last", C.c_int32), ("lookahead_lseq", C.c_void_p),
                 ("snv", C.c_void_p), ("snv_cap", C.c_int64), ("n_snv", C.c_int64), ("snv_ave_rd", C.c_double),
                 ("cl_w", C.c_void_p), ("cl_rs", C.c_void_p), ("cl_re", C.c_void_p), ("cl_dist", C.c_void_p),
-                ("cl_mchr", C.c_void_p), ("other_len", C.c_void_p), ("ins", C.c_void_p), ("ins_cap", C.c_int64), ("n_ins", C.c_int64)]
+                ("cl_mchr", C.c_void_p), ("other_len", C.c_void_p), ("ins", C.c_void_p), ("ins_cap", C.c_int64), ("n_ins", C.c_int64),
+                ("del_ev", C.c_void_p), ("del_cap", C.c_int64), ("n_del", C.c_int64)]
 
 
 _LIB = None
@@ -69,6 +70,7 @@ class OracleResult:
     cl_mchr: np.ndarray = None  # [2, P]
     other_len: np.ndarray = None
     ins: np.ndarray = None      # INS_CAND_DTYPE small-insertion candidates
+    del_ev: np.ndarray = None   # DEL_EVENT_DTYPE small-deletion scan events
 
     def __getitem__(self, name: str) -> np.ndarray:
         return self.arrays[GA[name]]
@@ -88,6 +90,8 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
                cl_dist=cl_dist.ctypes.data, cl_mchr=cl_mchr.ctypes.data, other_len=other_len.ctypes.data)
     ins = np.zeros(1 << 16, dtype=INS_CAND_DTYPE)
     out.ins = ins.ctypes.data; out.ins_cap = len(ins)
+    dev = np.zeros(1 << 17, dtype=DEL_EVENT_DTYPE)
+    out.del_ev = dev.ctypes.data; out.del_cap = len(dev)
     cb = batch.as_c()
     fa = np.ascontiguousarray(fasta, dtype=np.uint8)
     rc = lib().oracle_run_chr(C.byref(params), C.byref(cb), fa.ctypes.data_as(C.c_char_p), P,
@@ -96,7 +100,8 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
         raise RuntimeError(f"oracle_run_chr failed: {rc}")
     assert out.n_snv <= snv_cap
     return OracleResult(arrays, state[:batch.n_reads], out.scan_first, out.scan_last, look, snv[:out.n_snv].copy(),
-                        out.snv_ave_rd, cl_w, cl_rs, cl_re, cl_dist, cl_mchr, other_len, ins[:min(out.n_ins, len(ins))].copy())
+                        out.snv_ave_rd, cl_w, cl_rs, cl_re, cl_dist, cl_mchr, other_len, ins[:min(out.n_ins, len(ins))].copy(),
+                        dev[:min(out.n_del, len(dev))].copy())
 
 
 def format_snv_vcf(params: Params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, ave_rd: float) -> str:

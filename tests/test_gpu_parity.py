@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from util import CHECKED, CLIPS, DEPTH, EVIDENCE, GCS, GOLDEN, PILEUP, assert_arrays_equal, assert_clusters_equal, golden_batches, golden_params, load_golden_fasta, tables, tables_7digit
-from grom_b200 import gpu
+from grom_b200 import gpu, hostlib
 from grom_b200.params import GA, GA_NAMES, Params
 from grom_b200.reads import CDEL, CHARD_CLIP, CINS, CMATCH, CREF_SKIP, CSOFT_CLIP, FPAIRED, FREVERSE, FMREVERSE
 from oracle import pyoracle as po
@@ -39,6 +39,7 @@ def check_against_oracle(prm, batch, fasta, hez, mq, slices=None):
     assert len(res.ins) == len(ref.ins)
     for f in ("pos", "dist", "pr", "hez", "conc", "weight", "rd", "sc", "other_len", "seq"):
         assert np.array_equal(res.ins[f], ref.ins[f]), ("insertion candidate", f)
+    assert np.array_equal(res.del_ev, ref.del_ev), "small-deletion scan events differ"
     if len(ref.snv) or ref.scan_first >= 0:
         assert res.snv_ave_rd == ref.snv_ave_rd or (np.isnan(res.snv_ave_rd) and np.isnan(ref.snv_ave_rd))
     return res, got, state, st, ref
@@ -82,9 +83,13 @@ def test_gpu_reproduces_reference_golden(tag, rmdup):
         mine = po.format_snv_vcf(prm, n, fasta[name], res.snv, res.snv_ave_rd).splitlines(keepends=True)
         ref = [l for l in vcf if l.startswith(n + "\t") and l.split("\t")[2] == ""]
         assert mine == ref
-        mine = po.normalise_records(po.format_ins_vcf(prm, n, fasta[name], res.ins).splitlines(keepends=True))
+        mine = po.normalise_records(hostlib.vcf_ins(prm, n, fasta[name], res.ins).splitlines(keepends=True))
         ref = po.normalise_records([l for l in vcf if l.startswith(n + "\t") and "\tSPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP\t" in l])
         assert len(ref) > 0 and mine == ref
+        # product host writer on the GPU results == the reference's records, all three classes
+        assert hostlib.vcf_snv(prm, n, fasta[name], res.snv, res.snv_ave_rd).splitlines(keepends=True) == [l for l in vcf if l.startswith(n + "\t") and l.split("\t")[2] == ""]
+        mine = hostlib.vcf_smalldel(prm, n, fasta[name], res.del_ev).splitlines(keepends=True)
+        assert mine == [l for l in vcf if l.startswith(n + "\t") and "\tSPR:EPR:SEV:EEV:SRD:ERD:SCO:ECO:SOT:EOT:SSC:ESC:HP\t" in l]
 
 
 @pytest.mark.parametrize("seed,rmdup,read_len,depth", [(1, 0, 150, 30), (2, 1, 150, 30), (3, 1, 100, 60), (4, 0, 250, 10)])

@@ -1,0 +1,47 @@
+"""Host stage of the scan (grom_b200/host/vcf.c): emission filters, small-deletion pairing state machine and VCF text,
+checked against the reference's own records (golden fixture) using the oracle's candidates as input."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, golden_batches, golden_params, load_golden_fasta, tables_7digit
+from grom_b200 import hostlib
+from oracle import pyoracle as po
+
+
+@pytest.mark.parametrize("tag,rmdup", [("default", 0), ("rmdup", 1)])
+def test_host_writer_reproduces_reference_records(tag, rmdup):
+    names, batches = golden_batches()
+    fasta = load_golden_fasta()
+    hez, mq = tables_7digit()
+    g = np.load(os.path.join(GOLDEN, f"g1_{tag}.npz"))
+    prm = golden_params(g, rmdup)
+    vcf = [l for l in str(g["vcf"]).splitlines(keepends=True) if not l.startswith("#")]
+    n_ref = n_mine = 0
+    for tid, name in enumerate(names):
+        n = name.lower()
+        r = po.run_chr(prm, batches[tid], fasta[name], hez, mq)
+        snv = hostlib.vcf_snv(prm, n, fasta[name], r.snv, r.snv_ave_rd).splitlines(keepends=True)
+        ins = hostlib.vcf_ins(prm, n, fasta[name], r.ins).splitlines(keepends=True)
+        dele = hostlib.vcf_smalldel(prm, n, fasta[name], r.del_ev).splitlines(keepends=True)
+        mine = [l for l in vcf if l.startswith(n + "\t")]
+        assert snv == [l for l in mine if l.split("\t")[2] == ""]
+        assert po.normalise_records(ins) == po.normalise_records([l for l in mine if "\tSPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP\t" in l])
+        assert dele == [l for l in mine if "\tSPR:EPR:SEV:EEV:SRD:ERD:SCO:ECO:SOT:EOT:SSC:ESC:HP\t" in l]
+        # the reference prints the classes in this order per contig: SNV ... small INS, small DEL ...
+        n_ref += len(mine); n_mine += len(snv) + len(ins) + len(dele)
+    assert n_mine >= 0.95 * n_ref          # what is still missing are the <DEL>/<INS>/<INV>/<DUP> structural classes
+
+
+def test_smalldel_state_machine_edge_cases():
+    from grom_b200.params import DEL_EVENT_DTYPE, Params
+    prm = Params.default()
+    fa = np.frombuffer(b"ACGT" * 2000, dtype=np.uint8).copy()
+    ev = np.zeros(0, dtype=DEL_EVENT_DTYPE)
+    assert hostlib.vcf_smalldel(prm, "c", fa, ev) == ""
+    # one complete pair followed by a second start: only the first is emitted (the loop stops before the last entry)
+    ev = np.zeros(3, dtype=DEL_EVENT_DTYPE)
+    ev["pos"] = [1000, 1004, 3000]; ev["kind"] = [0, 1, 0]; ev["pr"] = 1e-9; ev["weight"] = 60; ev["rd"] = 20; ev["rdist"] = 5
+    out = hostlib.vcf_smalldel(prm, "c", fa, ev).splitlines()
+    assert len(out) == 1 and out[0].startswith("c\t1001\t.\t" + bytes(fa[1000:1005]).decode() + "\t.\t.\t.\tEND=1005\t")

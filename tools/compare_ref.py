@@ -59,12 +59,15 @@ with hostlib.Bam(bam) as b:
             if bad.size:
                 print(f"  {cn}.mchr mismatches {bad.size}"); bad_total += bad.size
         vcf = [l for l in open("/tmp/cmpref.vcf") if not l.startswith("#")]
-        for kind, mine in (("SNV", po.format_snv_vcf(prm, name, c.chars, r.snv, r.snv_ave_rd)), ("INS", po.format_ins_vcf(prm, name, c.chars, r.ins))):
+        for kind, mine in (("SNV", hostlib.vcf_snv(prm, name, c.chars, r.snv, r.snv_ave_rd)), ("INS", hostlib.vcf_ins(prm, name, c.chars, r.ins)),
+                           ("DEL", hostlib.vcf_smalldel(prm, name, c.chars, r.del_ev))):
             mine = po.normalise_records(mine.splitlines(keepends=True))
             if kind == "SNV":
                 ref = [l for l in vcf if l.startswith(name + "\t") and l.split("\t")[2] == ""]
-            else:
+            elif kind == "INS":
                 ref = po.normalise_records([l for l in vcf if l.startswith(name + "\t") and "\tSPR:SEV:SRD:SCO:ECO:SOT:EOT:SSC:HP\t" in l])
+            else:
+                ref = [l for l in vcf if l.startswith(name + "\t") and "\tSPR:EPR:SEV:EEV:SRD:ERD:SCO:ECO:SOT:EOT:SSC:ESC:HP\t" in l]
             print(f"  {kind} vcf lines mine/ref {len(mine)}/{len(ref)} identical {mine == ref}")
             if mine != ref:
                 bad_total += 1
@@ -73,3 +76,5 @@ with hostlib.Bam(bam) as b:
             bad_total += bad.size
             print(f"  other_len mismatches {bad.size} pos {pos[bad[:3]]} mine {r.other_len[pos][bad[:3]]} ref {sd['v'][:, 83][bad[:3]]}  (max ref {sd['v'][:, 83].max()})")
 print("TOTAL MISMATCHES", bad_total)
+allrec = [l for l in open("/tmp/cmpref.vcf") if not l.startswith("#")]
+print("reference records:", len(allrec), "of which SV/CNV classes not yet produced:", sum(1 for l in allrec if l.split("\t")[4].startswith("<") and "SSC:ESC" not in l and "SSC:HP" not in l))
