@@ -60,6 +60,41 @@ int64_t oracle_format_snv_vcf(const grom_params *p, const char *chr_name, const 
 int64_t oracle_format_ins_vcf(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
                               const grom_ins_cand *ins, int64_t n_ins, char *buf, int64_t cap);
 
+/* ---- read-depth CNV path (grom_oracle_cnv.c; src/GROM.c:1684-1764, 16633-17500, 18228-20355) ---- */
+#define ORACLE_CNV_BINS 101
+typedef struct oracle_cnv_cfg {
+    int32_t insert_mean, rd_min_mapq;
+    int32_t ploidy;                     /* effective: halved on chrx / x when -g 1 (src/GROM.c:17024-17035) */
+    int32_t windows_sampling_factor;    /* -A */
+    int64_t min_win, max_win;           /* g_min_rd_window_len 100, g_max_rd_window_len 10000 */
+    int64_t sample_cap;                 /* g_sample_lists_len 100000 */
+    uint32_t seed; uint32_t reserved;   /* srand() seed (the white-box build takes it from GROM_SEED) */
+    double  rd_pval_threshold;          /* -V */
+} oracle_cnv_cfg;
+
+typedef struct oracle_cnv_out {
+    long n_nblk, *nb_s, *nb_e;                          /* N-run blocks */
+    long n_rep, *rep_t, *rep_s, *rep_e;                 /* dinucleotide-repeat runs */
+    double chr_ave, chr_sd, rep_ave[10], rep_sd[10]; long rep_cnt[10], biased; double blk_ave;
+    long n_sblk, *sb_s, *sb_e;                          /* sample blocks */
+    int *mq_mean;                                       /* [len] rd_mq after the in-place mean */
+    double *z; unsigned char *mask;                     /* [len] stdev_list, rd_low_acgt_or_windows_list */
+    double *win_sd; long *win_cnt;                      /* [max_win+1] */
+    double ave[2][ORACLE_CNV_BINS], sd[2][ORACLE_CNV_BINS], del_thr[2][ORACLE_CNV_BINS], dup_thr[2][ORACLE_CNV_BINS];
+    long windows[2][ORACLE_CNV_BINS], n_high[ORACLE_CNV_BINS], n_low[ORACLE_CNV_BINS];
+    long n_call[2], *call_s[2], *call_e[2];             /* [0] deletions, [1] duplications */
+    double *call_z[2], *call_cn[2], *call_cs[2], *call_p[2];
+} oracle_cnv_out;
+
+int oracle_cnv_run(const oracle_cnv_cfg *c, const char *fasta, long len, const int *gc, const int *acgt, const int *rd_mq_sum,
+                   const int *rd_rd, const int *rd_low, const double *p2s_p, const double *p2s_sd, int n_p2s, oracle_cnv_out *o);
+void oracle_cnv_free(oracle_cnv_out *o);
+char *oracle_format_cnv_vcf(const oracle_cnv_cfg *c, const char *chr, const oracle_cnv_out *o);
+long oracle_bisect_left(const int *a, int v, long s, long e);
+long oracle_bisect_right(const int *a, int v, long s, long e);
+long oracle_bisect_left_double(const double *a, double v, long s, long e);
+long oracle_bisect_right_double(const double *a, double v, long s, long e);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,3 +72,45 @@ void grom_hook_srand(unsigned seed)
     const char *s = getenv("GROM_SEED");
     srand(s ? (unsigned)strtoul(s, NULL, 10) : seed);
 }
+
+/* cnvpre_<chr>.bin: int64 n_nblk, (int64 start, end)[n_nblk], int64 n_rep, (int64 type, start, end)[n_rep], double chr_ave, chr_sd,
+ * double rep_ave[10], rep_sd[10], int64 rep_cnt[10], int64 biased, double blk_ave, int64 n_sblk, (int64 start, end)[n_sblk] */
+void grom_hook_cnvpre(const char *chr, long n_nblk, const long *nb_s, const long *nb_e, long n_rep, const int *rep_t, const long *rep_s,
+                      const long *rep_e, double chr_ave, double chr_sd, const double *rep_ave, const double *rep_sd, const long *rep_cnt,
+                      int biased, double blk_ave, long n_sblk, const long *sb_s, const long *sb_e)
+{
+    FILE *f = open_for("cnvpre", chr);
+    long i, t;
+    fwrite(&n_nblk, 8, 1, f);
+    for (i = 0; i < n_nblk; i++) { fwrite(&nb_s[i], 8, 1, f); fwrite(&nb_e[i], 8, 1, f); }
+    fwrite(&n_rep, 8, 1, f);
+    for (i = 0; i < n_rep; i++) { t = rep_t[i]; fwrite(&t, 8, 1, f); fwrite(&rep_s[i], 8, 1, f); fwrite(&rep_e[i], 8, 1, f); }
+    fwrite(&chr_ave, 8, 1, f); fwrite(&chr_sd, 8, 1, f);
+    fwrite(rep_ave, 8, 10, f); fwrite(rep_sd, 8, 10, f); fwrite(rep_cnt, 8, 10, f);
+    t = biased; fwrite(&t, 8, 1, f); fwrite(&blk_ave, 8, 1, f);
+    fwrite(&n_sblk, 8, 1, f);
+    for (i = 0; i < n_sblk; i++) { fwrite(&sb_s[i], 8, 1, f); fwrite(&sb_e[i], 8, 1, f); }
+    fclose(f);
+}
+
+/* cnv_<chr>.bin: int64 len, nwin, nbins, n_del, n_dup; double z[len]; uint8 mask[len]; double win_sd[nwin]; int64 win_cnt[nwin];
+ * double ave[2][nbins], sd[2][nbins], del_thr[2][nbins], dup_thr[2][nbins]; int64 windows[2][nbins], n_high[nbins], n_low[nbins];
+ * per call (del then dup): int64 start, end; double z, cn, cs */
+void grom_hook_cnv(const char *chr, long len, const double *z, const int *mask, long nwin, const double *win_sd, const long *win_cnt,
+                   long nbins, const double *ave, const double *sd, const double *del_thr, const double *dup_thr, const long *windows,
+                   const long *n_high, const long *n_low, long n_del, const long *del_s, const long *del_e, const double *del_z,
+                   const double *del_cn, const double *del_cs, long n_dup, const long *dup_s, const long *dup_e, const double *dup_z,
+                   const double *dup_cn, const double *dup_cs)
+{
+    FILE *f = open_for("cnv", chr);
+    long i;
+    fwrite(&len, 8, 1, f); fwrite(&nwin, 8, 1, f); fwrite(&nbins, 8, 1, f); fwrite(&n_del, 8, 1, f); fwrite(&n_dup, 8, 1, f);
+    fwrite(z, 8, len, f);
+    for (i = 0; i < len; i++) fputc(mask[i], f);
+    fwrite(win_sd, 8, nwin, f); fwrite(win_cnt, 8, nwin, f);
+    fwrite(ave, 8, 2 * nbins, f); fwrite(sd, 8, 2 * nbins, f); fwrite(del_thr, 8, 2 * nbins, f); fwrite(dup_thr, 8, 2 * nbins, f);
+    fwrite(windows, 8, 2 * nbins, f); fwrite(n_high, 8, nbins, f); fwrite(n_low, 8, nbins, f);
+    for (i = 0; i < n_del; i++) { fwrite(&del_s[i], 8, 1, f); fwrite(&del_e[i], 8, 1, f); fwrite(&del_z[i], 8, 1, f); fwrite(&del_cn[i], 8, 1, f); fwrite(&del_cs[i], 8, 1, f); }
+    for (i = 0; i < n_dup; i++) { fwrite(&dup_s[i], 8, 1, f); fwrite(&dup_e[i], 8, 1, f); fwrite(&dup_z[i], 8, 1, f); fwrite(&dup_cn[i], 8, 1, f); fwrite(&dup_cs[i], 8, 1, f); }
+    fclose(f);
+}

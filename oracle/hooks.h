@@ -14,6 +14,8 @@
  *   reads_<chr>.bin : per read that reaches the -M test   int32 pos, mpos, tlen, flag, mapq, keep
  *   depth_<chr>.bin : int32 rd_mq[P], rd_rd[P], rd_low_mq_rd[P]   (before the in-place mean, src/GROM.c:16637)
  *   gc_<chr>.bin    : int32 gc_weighted[P], acgt_weighted[P]
+ *   cnvpre_<chr>.bin: state after the CNV pre-statistics (src/GROM.c:16633-16990), see grom_hook_cnvpre
+ *   cnv_<chr>.bin   : state at the end of detect_del_dup (src/GROM.c:20348), see grom_hook_cnv
  */
 #ifndef GROM_ORACLE_HOOKS_H
 #define GROM_ORACLE_HOOKS_H
@@ -27,6 +29,14 @@ void grom_hook_read(const char *chr, int pos, int mpos, int tlen, int flag, int 
 void grom_hook_depth(const char *chr, long len, const int *mq, const int *rd, const int *low);
 void grom_hook_gc(const char *chr, long len, const int *gc, const int *acgt);
 void grom_hook_srand(unsigned seed);
+void grom_hook_cnvpre(const char *chr, long n_nblk, const long *nb_s, const long *nb_e, long n_rep, const int *rep_t, const long *rep_s,
+                      const long *rep_e, double chr_ave, double chr_sd, const double *rep_ave, const double *rep_sd, const long *rep_cnt,
+                      int biased, double blk_ave, long n_sblk, const long *sb_s, const long *sb_e);
+void grom_hook_cnv(const char *chr, long len, const double *z, const int *mask, long nwin, const double *win_sd, const long *win_cnt,
+                   long nbins, const double *ave, const double *sd, const double *del_thr, const double *dup_thr, const long *windows,
+                   const long *n_high, const long *n_low, long n_del, const long *del_s, const long *del_e, const double *del_z,
+                   const double *del_cn, const double *del_cs, long n_dup, const long *dup_s, const long *dup_e, const double *dup_z,
+                   const double *dup_cn, const double *dup_cs);
 
 #define GH_CL(k, w, rs, re) v[51 + 3 * (k)] = (w)[ix]; v[52 + 3 * (k)] = (rs)[ix]; v[53 + 3 * (k)] = (re)[ix];
 
@@ -74,5 +84,19 @@ void grom_hook_srand(unsigned seed);
 
 /* inserted immediately before reference src/GROM.c:1883 (end of the FASTA pre-pass) */
 #define GROM_HOOK_GC() do { if (g_hook_on) grom_hook_gc(cdp_chr_name, caf_chr_fasta_len, caf_one_base_rd_gc_weighted, caf_one_base_rd_acgt_weighted); } while (0)
+
+
+/* inserted immediately before reference src/GROM.c:17016 (after the CNV pre-statistics, same block scope) */
+#define GROM_HOOK_CNVPRE() do { if (g_hook_on) grom_hook_cnvpre(cdp_chr_name, caf_n_index, caf_n_blocks_start, caf_n_blocks_end, caf_repeat_index, \
+    caf_repeat_type_list, caf_repeat_start_list, caf_repeat_end_list, caf_repeat_chr_rd_ave, caf_repeat_chr_rd_stdev, caf_repeat_rd_average, \
+    caf_repeat_rd_stdev, caf_repeat_rd_type_count, g_most_biased_repeat, caf_chr_rd_ave, g_lowvar_block_sample_index, \
+    g_lowvar_block_sample_start_list, g_lowvar_block_sample_end_list); } while (0)
+
+/* inserted immediately before reference src/GROM.c:20348 (end of detect_del_dup, all locals alive) */
+#define GROM_HOOK_CNV() do { if (g_hook_on) grom_hook_cnv(ddd_chr_name, ddd_chr_fasta_len, ddd_stdev_list, ddd_rd_low_acgt_or_windows_list, \
+    g_max_rd_window_len + 1, ddd_rd_windows_low_stdev, ddd_rd_windows_count, g_num_gc_bins, &ddd_rd_ave_by_gc[0][0], &ddd_rd_stdev_by_gc[0][0], \
+    &ddd_rd_ave_by_gc_del_threshold[0][0], &ddd_rd_ave_by_gc_dup_threshold[0][0], &ddd_rd_windows_by_gc[0][0], ddd_high_mq_index, ddd_low_mq_index, \
+    *ddd_del_list_index, ddd_del_list_start, ddd_del_list_end, ddd_del_list_stdev, ddd_del_list_cn, ddd_del_list_cn_stdev, \
+    *ddd_dup_list_index, ddd_dup_list_start, ddd_dup_list_end, ddd_dup_list_stdev, ddd_dup_list_cn, ddd_dup_list_cn_stdev); } while (0)
 
 #endif

@@ -210,3 +210,153 @@ def normalise_records(lines):
             f[9] = ":".join(v)
         out.append("\t".join(f) + "\n")
     return out
+
+
+# ---- read-depth CNV path ------------------------------------------------------------------------------------------------
+NB = 101
+
+
+class CCnvCfg(C.Structure):
+    _fields_ = [("insert_mean", C.c_int32), ("rd_min_mapq", C.c_int32), ("ploidy", C.c_int32), ("windows_sampling_factor", C.c_int32),
+                ("min_win", C.c_int64), ("max_win", C.c_int64), ("sample_cap", C.c_int64), ("seed", C.c_uint32), ("reserved", C.c_uint32),
+                ("rd_pval_threshold", C.c_double)]
+
+
+class CCnvOut(C.Structure):
+    _fields_ = [("n_nblk", C.c_long), ("nb_s", C.POINTER(C.c_long)), ("nb_e", C.POINTER(C.c_long)),
+                ("n_rep", C.c_long), ("rep_t", C.POINTER(C.c_long)), ("rep_s", C.POINTER(C.c_long)), ("rep_e", C.POINTER(C.c_long)),
+                ("chr_ave", C.c_double), ("chr_sd", C.c_double), ("rep_ave", C.c_double * 10), ("rep_sd", C.c_double * 10),
+                ("rep_cnt", C.c_long * 10), ("biased", C.c_long), ("blk_ave", C.c_double),
+                ("n_sblk", C.c_long), ("sb_s", C.POINTER(C.c_long)), ("sb_e", C.POINTER(C.c_long)),
+                ("mq_mean", C.POINTER(C.c_int)), ("z", C.POINTER(C.c_double)), ("mask", C.POINTER(C.c_ubyte)),
+                ("win_sd", C.POINTER(C.c_double)), ("win_cnt", C.POINTER(C.c_long)),
+                ("ave", C.c_double * (2 * NB)), ("sd", C.c_double * (2 * NB)), ("del_thr", C.c_double * (2 * NB)), ("dup_thr", C.c_double * (2 * NB)),
+                ("windows", C.c_long * (2 * NB)), ("n_high", C.c_long * NB), ("n_low", C.c_long * NB),
+                ("n_call", C.c_long * 2), ("call_s", C.POINTER(C.c_long) * 2), ("call_e", C.POINTER(C.c_long) * 2),
+                ("call_z", C.POINTER(C.c_double) * 2), ("call_cn", C.POINTER(C.c_double) * 2), ("call_cs", C.POINTER(C.c_double) * 2),
+                ("call_p", C.POINTER(C.c_double) * 2)]
+
+
+CALL_DTYPE = np.dtype([("start", np.int64), ("end", np.int64), ("z", np.float64), ("cn", np.float64), ("cs", np.float64), ("p", np.float64)])
+
+
+@dataclass
+class CnvResult:
+    nblocks: np.ndarray         # [n, 2] N-run blocks
+    repeats: np.ndarray         # [n, 3] type, start, end
+    chr_ave: float
+    chr_sd: float
+    rep_ave: np.ndarray
+    rep_sd: np.ndarray
+    rep_cnt: np.ndarray
+    biased: int
+    blk_ave: float
+    sample_blocks: np.ndarray   # [n, 2]
+    mq_mean: np.ndarray
+    z: np.ndarray
+    mask: np.ndarray
+    win_sd: np.ndarray
+    win_cnt: np.ndarray
+    ave: np.ndarray             # [2, 101]
+    sd: np.ndarray
+    del_thr: np.ndarray
+    dup_thr: np.ndarray
+    windows: np.ndarray
+    n_high: np.ndarray
+    n_low: np.ndarray
+    dels: np.ndarray            # CALL_DTYPE
+    dups: np.ndarray
+    vcf: str
+
+
+def _np(ptr, n, dtype):
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype).copy() if n else np.zeros(0, dtype=dtype)
+
+
+def cnv_cfg(params: Params, ploidy: Optional[int] = None, seed: int = 1, sample_cap: int = 100000, min_win: int = 100, max_win: int = 10000) -> CCnvCfg:
+    return CCnvCfg(params.insert_mean, params.rd_min_mapq, params.ploidy if ploidy is None else ploidy, params.windows_sampling_factor,
+                   min_win, max_win, sample_cap, seed, 0, params.rd_pval_threshold)
+
+
+def cnv_run(params: Params, chr_name: str, fasta: np.ndarray, gc: np.ndarray, acgt: np.ndarray, rd_mq: np.ndarray, rd_rd: np.ndarray,
+            rd_low: np.ndarray, ploidy: Optional[int] = None, seed: int = 1, sample_cap: int = 100000, min_win: int = 100,
+            max_win: int = 10000) -> CnvResult:
+    """CNV oracle on the raw CNV depth arrays (rd_mq = MAPQ sums, before the in-place mean)."""
+    from grom_b200 import hostlib
+    L = lib()
+    L.oracle_cnv_run.argtypes = [C.POINTER(CCnvCfg), C.c_char_p, C.c_long] + [C.c_void_p] * 7 + [C.c_int, C.POINTER(CCnvOut)]
+    L.oracle_format_cnv_vcf.argtypes = [C.POINTER(CCnvCfg), C.c_char_p, C.POINTER(CCnvOut)]
+    L.oracle_format_cnv_vcf.restype = C.c_void_p
+    L.oracle_cnv_free.argtypes = [C.POINTER(CCnvOut)]
+    cfg = cnv_cfg(params, ploidy, seed, sample_cap, min_win, max_win)
+    pv, sdv = hostlib.pval2sd()
+    arrs = [np.ascontiguousarray(a, dtype=np.int32) for a in (gc, acgt, rd_mq, rd_rd, rd_low)]
+    fa = np.ascontiguousarray(fasta, dtype=np.uint8)
+    fa0 = np.concatenate([fa, np.zeros(2, dtype=np.uint8)])
+    out = CCnvOut()
+    rc = L.oracle_cnv_run(C.byref(cfg), fa0.ctypes.data_as(C.c_char_p), len(fa), *[a.ctypes.data for a in arrs],
+                          pv.ctypes.data, sdv.ctypes.data, len(pv), C.byref(out))
+    if rc != 0:
+        raise RuntimeError("oracle_cnv_run failed (contig too short)")
+    P, nw = len(fa), max_win + 1
+
+    def calls(k):
+        n = out.n_call[k]
+        r = np.zeros(n, dtype=CALL_DTYPE)
+        for f, src in (("start", out.call_s), ("end", out.call_e), ("z", out.call_z), ("cn", out.call_cn), ("cs", out.call_cs), ("p", out.call_p)):
+            r[f] = _np(src[k], n, r.dtype[f])
+        return r
+    txt = L.oracle_format_cnv_vcf(C.byref(cfg), chr_name.encode(), C.byref(out))
+    vcf = C.string_at(txt).decode()
+    res = CnvResult(
+        nblocks=np.stack([_np(out.nb_s, out.n_nblk, np.int64), _np(out.nb_e, out.n_nblk, np.int64)], 1),
+        repeats=np.stack([_np(out.rep_t, out.n_rep, np.int64), _np(out.rep_s, out.n_rep, np.int64), _np(out.rep_e, out.n_rep, np.int64)], 1),
+        chr_ave=out.chr_ave, chr_sd=out.chr_sd, rep_ave=np.array(out.rep_ave), rep_sd=np.array(out.rep_sd), rep_cnt=np.array(out.rep_cnt),
+        biased=out.biased, blk_ave=out.blk_ave,
+        sample_blocks=np.stack([_np(out.sb_s, out.n_sblk, np.int64), _np(out.sb_e, out.n_sblk, np.int64)], 1),
+        mq_mean=_np(out.mq_mean, P, np.int32), z=_np(out.z, P, np.float64), mask=_np(out.mask, P, np.uint8),
+        win_sd=_np(out.win_sd, nw, np.float64), win_cnt=_np(out.win_cnt, nw, np.int64),
+        ave=np.array(out.ave).reshape(2, NB), sd=np.array(out.sd).reshape(2, NB), del_thr=np.array(out.del_thr).reshape(2, NB),
+        dup_thr=np.array(out.dup_thr).reshape(2, NB), windows=np.array(out.windows).reshape(2, NB), n_high=np.array(out.n_high),
+        n_low=np.array(out.n_low), dels=calls(0), dups=calls(1), vcf=vcf)
+    L.oracle_cnv_free(C.byref(out))
+    return res
+
+
+def load_cnvpre_dump(dump_dir: str, chr_name: str) -> dict:
+    a = np.fromfile(os.path.join(dump_dir, f"cnvpre_{chr_name}.bin"), dtype=np.int64)
+    f = a.view(np.float64)
+    i = 0
+    n = int(a[i]); i += 1
+    nblocks = a[i:i + 2 * n].reshape(n, 2).copy(); i += 2 * n
+    n = int(a[i]); i += 1
+    repeats = a[i:i + 3 * n].reshape(n, 3).copy(); i += 3 * n
+    d = dict(nblocks=nblocks, repeats=repeats, chr_ave=f[i], chr_sd=f[i + 1]); i += 2
+    d["rep_ave"] = f[i:i + 10].copy(); d["rep_sd"] = f[i + 10:i + 20].copy(); d["rep_cnt"] = a[i + 20:i + 30].copy(); i += 30
+    d["biased"] = int(a[i]); d["blk_ave"] = f[i + 1]; i += 2
+    n = int(a[i]); i += 1
+    d["sample_blocks"] = a[i:i + 2 * n].reshape(n, 2).copy()
+    return d
+
+
+def load_cnv_dump(dump_dir: str, chr_name: str) -> dict:
+    raw = np.fromfile(os.path.join(dump_dir, f"cnv_{chr_name}.bin"), dtype=np.uint8)
+    P, nwin, nb, nd, nu = (int(x) for x in raw[:40].view(np.int64))
+    o = 40
+    d = {}
+
+    def take(n, dt):
+        nonlocal o
+        sz = n * np.dtype(dt).itemsize
+        v = raw[o:o + sz].view(dt).copy()
+        o += sz
+        return v
+    d["z"] = take(P, np.float64); d["mask"] = take(P, np.uint8)
+    d["win_sd"] = take(nwin, np.float64); d["win_cnt"] = take(nwin, np.int64)
+    for k in ("ave", "sd", "del_thr", "dup_thr"):
+        d[k] = take(2 * nb, np.float64).reshape(2, nb)
+    d["windows"] = take(2 * nb, np.int64).reshape(2, nb)
+    d["n_high"] = take(nb, np.int64); d["n_low"] = take(nb, np.int64)
+    rec = np.dtype([("start", np.int64), ("end", np.int64), ("z", np.float64), ("cn", np.float64), ("cs", np.float64)])
+    d["dels"] = take(nd, rec); d["dups"] = take(nu, rec)
+    return d

@@ -60,6 +60,9 @@ class SynthSpec:
     simple: bool = False            # bench mode: only the vectorised read classes
     simple_disc_frac: float = 0.0   # simple mode: vectorised deletion-like / inverted / mate-unmapped pairs (bench realism)
     names: bool = True              # False: no read-name strings (hash only; such a batch cannot be written as BAM)
+    cnv_per_mb: float = 0.0         # planted copy-number segments (alternating loss / gain of one copy, every 4th a full loss)
+    cnv_min: int = 20_000
+    cnv_max: int = 120_000
 
 
 def make_reference(length: int, rng: np.random.Generator, n_frac=0.01, lower_frac=0.1) -> np.ndarray:
@@ -148,6 +151,28 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
     ins = np.clip(np.rint(rng.normal(spec.ins_mean, spec.ins_sd, n_pairs)), spec.ins_floor, None).astype(np.int64)
     fs = np.sort(rng.integers(0, max(1, length - int(ins.max()) - 1), n_pairs)).astype(np.int64)
     hp = rng.integers(0, 2, n_pairs)
+    cnv_truth = []
+    if spec.cnv_per_mb > 0:
+        # copy-number segments: thin (loss) or thicken (gain) the pairs that start inside the segment
+        keep = np.ones(n_pairs, dtype=bool)
+        extra = []
+        for k in range(max(1, int(length / 1e6 * spec.cnv_per_mb))):
+            L = int(rng.integers(spec.cnv_min, spec.cnv_max))
+            a = int(rng.integers(15_000, max(15_001, length - L - 15_000)))
+            i0, i1 = np.searchsorted(fs, [a, a + L])
+            if k % 2 == 0:
+                keep[i0:i1] &= rng.random(i1 - i0) < (0.0 if k % 4 == 2 else 0.5)
+                cnv_truth.append((a, a + L, 0 if k % 4 == 2 else 1))
+            else:
+                extra.append(rng.integers(a, a + L, (i1 - i0) // 2))
+                cnv_truth.append((a, a + L, 3))
+        fs = np.sort(np.concatenate([fs[keep]] + extra)).astype(np.int64)
+        fs = np.minimum(fs, max(1, length - int(ins.max()) - 2))
+        n_pairs = len(fs)
+        ins = np.clip(np.rint(rng.normal(spec.ins_mean, spec.ins_sd, n_pairs)), spec.ins_floor, None).astype(np.int64)
+        fs = np.minimum(fs, length - ins - 1)
+        fs.sort()
+        hp = rng.integers(0, 2, n_pairs)
     # PCR duplicates: copy (fs, ins, hap) of a random earlier pair
     if spec.dup_frac > 0:
         nd = int(n_pairs * spec.dup_frac)
@@ -362,9 +387,9 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
                     pos[ib] = npos; mpos[ia] = npos; tlen[ia] = npos + rl - pos[ia]; tlen[ib] = -tlen[ia]
                     flag[ia] = FPAIRED | FMREVERSE | FREAD1; flag[ib] = FPAIRED | FREVERSE | FREAD2
                     codes[ib, :rl] = hap[0][npos:npos + rl]
-        truth = {"snv_pos": snv_pos, "snv_het": het, "sv": np.array(truth_sv, dtype=np.int64).reshape(-1, 2)}
+        truth = {"snv_pos": snv_pos, "snv_het": het, "sv": np.array(truth_sv, dtype=np.int64).reshape(-1, 2), "cnv": cnv_truth}
     else:
-        truth = {"snv_pos": snv_pos, "snv_het": het}
+        truth = {"snv_pos": snv_pos, "snv_het": het, "cnv": cnv_truth}
         if spec.simple_disc_frac > 0:
             # vectorised discordant classes: 60 % deletion-like (mate 2-20 kb downstream), 20 % same-strand (FF), 20 % mate unmapped
             nd = int(n_pairs * spec.simple_disc_frac)
