@@ -1,0 +1,554 @@
+// cnv.cuh -- read-depth CNV path of the reference (SURVEY.md §8 rows a13 side lists, a14, a15, a17) on the device.
+//
+// Reference: src/GROM.c:1684-1764 (dinucleotide-repeat runs), 16633-16990 (pre-statistics), 18228-20355 (detect_del_dup),
+// 17146-17240 (p-value + -V filter), 21630-21860 (bisections).
+//
+// Split of the work (DESIGN.md "CNV path"):
+//   device, one thread per reference position or better: mean MAPQ, depth, 10 kb block sums, depth histogram, repeat runs,
+//           depth samples, mask, rank -> sd transform (cumulative-count tables instead of per-base binary searches),
+//           per-frame window sweep for every window length (sequential inside a frame = the reference's summation order),
+//           ordered reduction over frames, seed bitmaps for the segmentation
+//   host,   O(samples) / O(calls) sequential logic with libc-rand / qsort semantics: reservoir lists, block clustering,
+//           greedy DEL / DUP segmentation over the packed per-position records, copy number
+//
+// Every double that reaches the output is produced by the same operation sequence as the reference (no FMA contraction:
+// __dmul_rn / __dadd_rn where a product feeds a sum).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace cnv {
+
+constexpr int NB = 101;                 // g_num_gc_bins
+constexpr int NLIST = 2 * NB;           // [mq class][gc bin]
+constexpr int BLK_UNIT = 10000;         // g_block_unit_size
+constexpr int CTILE = 2048;              // positions per carry tile
+constexpr int HIST = 4096;              // depth histogram bins kept on chip
+constexpr int HIST_ALL = 65536;         // bins of the global histogram (last bin collects everything deeper)
+constexpr int MIN_ACGT = 99;            // g_insert_min_acgt
+constexpr int NO_COMBINE = 100;         // g_rd_no_combine_min_windows
+constexpr int MIN_WINDOWS = 20;         // g_rd_min_windows
+constexpr int RD_MAX_MAPQ = 60;         // g_rd_max_mapq
+constexpr int P2S = 1001;               // p-value -> sd table length
+
+// packed per-position record (uint32)
+constexpr uint32_t R_MASK = 1u;                          // rd_low_acgt_or_windows_list
+constexpr int      R_CLASS = 1;                          // 2 bits: 0 mean MAPQ >= q, 1 covered with low MAPQ, 2 uncovered
+constexpr uint32_t R_DEL0 = 1u << 3, R_DEL1 = 1u << 4;   // depth <= deletion threshold of the high / low list of the bin
+constexpr uint32_t R_DUP0 = 1u << 5, R_DUP1 = 1u << 6;   // depth >= duplication threshold
+constexpr uint32_t R_WIN0 = 1u << 7, R_WIN1 = 1u << 8;   // list has more than one sample
+constexpr uint32_t R_NEG = 1u << 9, R_NZ = 1u << 10, R_OVR = 1u << 11;
+constexpr int      R_K = 12, R_MQ = 22;                  // 10 bits table index, 8 bits mean MAPQ
+constexpr uint32_t R_USABLE = 1u << 30;                  // mask == 0 and the list of the position's own MAPQ class has > 1 sample (the z kernel's carry walk reads it)
+
+struct Tables {                 // device pointers
+    const int32_t *cum;         // [NLIST][D+1]  number of samples <= d
+    int32_t D;
+    const int32_t *n;           // [NLIST]
+    const int32_t *small;       // [NLIST][2]    the samples themselves when n < 3 (the reference's bisection is not a true bisection there)
+    const double *ave, *del_thr, *dup_thr;   // [NLIST]
+    const double *p2s_p, *p2s_sd;            // [P2S]
+};
+
+__host__ __device__ inline double rec_z(uint32_t r, int q, const double *sd)
+{
+    if (!(r & R_NZ)) return 0.0;
+    const int mq = (r >> R_MQ) & 255, k = (r >> R_K) & 1023;
+    double w;
+    if (r & R_OVR) w = 1.0;
+    else if (((r >> R_CLASS) & 3) == 0) w = 0.5 + (1.0 - 0.5) * (mq - q) / (double)(RD_MAX_MAPQ - q);
+    else w = 0.5;
+    const double z = w * sd[k];
+    return (r & R_NEG) ? -z : z;
+}
+__host__ __device__ inline bool rec_usable(uint32_t r)
+{
+    return !(r & R_MASK) && ((((r >> R_CLASS) & 3) == 0) ? (r & R_WIN0) != 0 : (r & R_WIN1) != 0);
+}
+
+// ---- K1: mean MAPQ, depth, per-10kb block sums, contig sums, depth histogram (src/GROM.c:16637-16686, 16812-16831)
+struct PreOut { unsigned long long blk_sum, acgt_sum, acgt_cnt, ave_sum, ave_cnt; };
+__global__ void __launch_bounds__(256) k_pre(const int32_t *__restrict__ mqsum, const int32_t *__restrict__ rd, const int32_t *__restrict__ low,
+                                             const int32_t *__restrict__ acgt, const char *__restrict__ fasta, int64_t P, int64_t lo, int64_t hi,
+                                             int32_t *__restrict__ depth, uint8_t *__restrict__ mq8, PreOut *__restrict__ out,
+                                             unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[HIST];
+    __shared__ unsigned long long red[5];
+    for (int i = threadIdx.x; i < HIST; i += blockDim.x) sh[i] = 0;
+    if (threadIdx.x < 5) red[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t p0 = (int64_t)blockIdx.x * BLK_UNIT, p1 = min(p0 + BLK_UNIT, P);
+    unsigned long long s_blk = 0, s_acgt = 0, n_acgt = 0, s_ave = 0, n_ave = 0;
+    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+        const int d = rd[p] + low[p];
+        const int m = d > 0 ? mqsum[p] / d : mqsum[p];
+        depth[p] = d; mq8[p] = (uint8_t)min(max(m, 0), 255);
+        s_blk += (unsigned)d;
+        const char c = fasta[p] & 0xDF;
+        if (c == 'A' || c == 'C' || c == 'G' || c == 'T') { s_acgt += (unsigned)d; n_acgt++; }
+        if (p >= lo && p < hi && acgt[p] >= MIN_ACGT) {
+            s_ave += (unsigned)d; n_ave++;
+            if (d < HIST) atomicAdd(&sh[d], 1u);
+            else atomicAdd(&hist[min(d, HIST_ALL - 1)], 1ull);
+        }
+    }
+    atomicAdd(&red[0], s_blk); atomicAdd(&red[1], s_acgt); atomicAdd(&red[2], n_acgt); atomicAdd(&red[3], s_ave); atomicAdd(&red[4], n_ave);
+    __syncthreads();
+    if (threadIdx.x == 0) { PreOut o; o.blk_sum = red[0]; o.acgt_sum = red[1]; o.acgt_cnt = red[2]; o.ave_sum = red[3]; o.ave_cnt = red[4]; out[blockIdx.x] = o; }
+    for (int i = threadIdx.x; i < HIST; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+// ---- K2: dinucleotide-repeat runs >= 20 (src/GROM.c:1727-1764): the thread at a run start walks the run
+struct RepRec { int32_t s, e, type, pad; long long depth_sum; };
+__device__ __forceinline__ int dinuc_type(char c0, char c1)
+{
+    if (((c0 ^ c1) & 0x20) != 0) return 10;                 // mixed case never matches
+    auto code = [](char c) { c &= 0xDF; return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1; };
+    int a = code(c0), b = code(c1);
+    if (a < 0 || b < 0) return 10;
+    if (a > b) { const int t = a; a = b; b = t; }
+    return a * 4 - a * (a - 1) / 2 + (b - a);               // 0..9 over the unordered pairs AA AC AG AT CC CG CT GG GT TT
+}
+__global__ void __launch_bounds__(256) k_repeats(const char *__restrict__ fasta, const int32_t *__restrict__ depth, int64_t lo, int64_t hi,
+                                                 RepRec *__restrict__ out, unsigned int cap, unsigned int *__restrict__ n_out)
+{
+    const int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= hi) return;
+    const int t = dinuc_type(fasta[p], fasta[p + 1]);
+    if (t == 10) return;
+    if (p > lo && dinuc_type(fasta[p - 1], fasta[p]) == t) return;          // not the first pair of its run
+    int64_t e = p;
+    long long sum = depth[p];
+    while (e + 1 < hi && dinuc_type(fasta[e + 1], fasta[e + 2]) == t) { e++; sum += depth[e]; }
+    if (e + 1 >= hi) return;                                                 // a run still open at the end of the span is never flushed
+    if (e - p < 19) return;
+    const unsigned int k = atomicAdd(n_out, 1u);             // [s, e + 1) is the reference's half-open run
+    if (k < cap) { RepRec r; r.s = (int32_t)p; r.e = (int32_t)(e + 1); r.type = t; r.pad = 0; r.depth_sum = sum; out[k] = r; }
+}
+
+// ---- K3: depth samples every insert_mean/2 bases of the sample blocks (src/GROM.c:18373-18456)
+struct Sample { int32_t depth; int32_t code; };     // code: bit0 valid, bits1-2 class (0 high, 1 low, 2 uncovered), bits 8.. gc bin
+__global__ void __launch_bounds__(256) k_samples(const int32_t *__restrict__ depth, const int32_t *__restrict__ rd, const int32_t *__restrict__ low,
+                                                 const uint8_t *__restrict__ mq8, const int32_t *__restrict__ gc, const int32_t *__restrict__ acgt,
+                                                 const int64_t *__restrict__ blk_start, const int64_t *__restrict__ blk_first, int n_blk,
+                                                 int64_t n_samples, int64_t step, int q, Sample *__restrict__ out)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_samples) return;
+    int b = 0;
+    while (b + 1 < n_blk && blk_first[b + 1] <= j) b++;
+    const int64_t p = blk_start[b] + (j - blk_first[b]) * step;
+    Sample s; s.depth = depth[p]; s.code = 0;
+    if (acgt[p] >= MIN_ACGT) {
+        const int cls = (rd[p] == 0 && low[p] == 0) ? 2 : (mq8[p] >= q ? 0 : 1);
+        s.code = 1 | (cls << 1) | (gc[p] << 8);
+    }
+    out[j] = s;
+}
+
+// ---- carry tiles: "class of the last setter position before p" (the reference's ddd_last_low_mq) ------------------------
+// summary: class (0/1) of the last setter in the tile, 2 if none
+__global__ void __launch_bounds__(256) k_tile_last_mask(const int32_t *__restrict__ depth, const uint8_t *__restrict__ mq8, const int32_t *__restrict__ acgt,
+                                                        int64_t lo, int64_t hi, int q, uint8_t *__restrict__ tile_last)
+{
+    __shared__ int best;
+    if (threadIdx.x == 0) best = -1;
+    __syncthreads();
+    const int64_t t0 = (int64_t)blockIdx.x * CTILE;
+    int mine = -1;
+    for (int i = threadIdx.x; i < CTILE; i += blockDim.x) {
+        const int64_t p = t0 + i;
+        if (p >= lo && p < hi && acgt[p] >= MIN_ACGT && depth[p] > 0) mine = max(mine, i);
+    }
+    if (mine >= 0) atomicMax(&best, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_last[blockIdx.x] = best < 0 ? 2 : (mq8[t0 + best] >= q ? 0 : 1);
+}
+// exclusive "last non-2" scan over the tile summaries, one block
+__global__ void __launch_bounds__(1024) k_carry_scan(const uint8_t *__restrict__ tile_last, uint8_t *__restrict__ tile_in, int n_tiles)
+{
+    __shared__ uint8_t chunk_last[1024], chunk_in[1024];
+    const int per = (n_tiles + 1023) / 1024, a = threadIdx.x * per, b = min(a + per, n_tiles);
+    uint8_t last = 2;
+    for (int t = a; t < b; t++) if (tile_last[t] != 2) last = tile_last[t];
+    chunk_last[threadIdx.x] = last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint8_t c = 0;                                   // ddd_last_low_mq starts at 0
+        for (int i = 0; i < 1024; i++) { chunk_in[i] = c; if (chunk_last[i] != 2) c = chunk_last[i]; }
+    }
+    __syncthreads();
+    uint8_t c = chunk_in[threadIdx.x];
+    for (int t = a; t < b; t++) { tile_in[t] = c; if (tile_last[t] != 2) c = tile_last[t]; }
+}
+
+// ---- K5: mask (src/GROM.c:18681-18720), class, list-size bits; summary of the z-stage setters per tile
+__global__ void __launch_bounds__(256) k_mask(const int32_t *__restrict__ depth, const uint8_t *__restrict__ mq8, const int32_t *__restrict__ gc,
+                                              const int32_t *__restrict__ acgt, int64_t P, int64_t lo, int64_t hi, int q, const int32_t *__restrict__ nlist,
+                                              const uint8_t *__restrict__ tile_in, uint32_t *__restrict__ rec, uint8_t *__restrict__ tile_last_z)
+{
+    __shared__ int best;
+    if (threadIdx.x == 0) best = -1;
+    __syncthreads();
+    const int64_t t0 = (int64_t)blockIdx.x * CTILE;
+    int mine = -1;
+    for (int i = threadIdx.x; i < CTILE; i += blockDim.x) {
+        const int64_t p = t0 + i;
+        if (p >= P) break;
+        const int d = depth[p], m = mq8[p];
+        const int cls = m >= q ? 0 : (d > 0 ? 1 : 2);
+        uint32_t r = (uint32_t)cls << R_CLASS | (uint32_t)m << R_MQ | R_MASK;
+        if (p >= lo) {
+            const int g = gc[p];
+            if (nlist[g] > 1) r |= R_WIN0;
+            if (nlist[NB + g] > 1) r |= R_WIN1;
+        }
+        if (p >= lo && p < hi) {
+            const int g = gc[p];
+            if (acgt[p] >= MIN_ACGT) {
+                int mi;
+                if (d > 0) mi = m >= q ? 0 : 1;
+                else {
+                    // uncovered: the list of the last covered position with enough ACGT context (walk back inside the tile, else the tile's carry-in)
+                    mi = -1;
+                    for (int64_t b = p - 1; b >= t0 && b >= lo; b--) if (acgt[b] >= MIN_ACGT && depth[b] > 0) { mi = mq8[b] >= q ? 0 : 1; break; }
+                    if (mi < 0) mi = tile_in[blockIdx.x];
+                }
+                if (nlist[mi * NB + g] >= NO_COMBINE) r &= ~R_MASK;
+            }
+            if (rec_usable(r)) { r |= R_USABLE; if (cls != 2) mine = max(mine, i); }
+        }
+        rec[p] = r;
+    }
+    if (mine >= 0) atomicMax(&best, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint8_t v = 2;
+        if (best >= 0) v = mq8[t0 + best] >= q ? 0 : 1;
+        tile_last_z[blockIdx.x] = v;
+    }
+}
+
+// the reference's bisections on a sorted sample list, answered from the cumulative counts (exact for n >= 3; n < 3 spelled out)
+__device__ __forceinline__ int rank_le(const Tables &T, int list, int v)   // bisect_right
+{
+    const int n = T.n[list];
+    if (n >= 3) return v < 0 ? 0 : T.cum[(int64_t)list * (T.D + 1) + min(v, T.D)];
+    if (n == 2) return v < T.small[list * 2 + 1] ? 1 : 2;
+    return v < T.small[list * 2] ? 0 : 1;
+}
+__device__ __forceinline__ int rank_lt(const Tables &T, int list, int v)   // bisect_left
+{
+    const int n = T.n[list];
+    if (n >= 3) return v <= 0 ? 0 : T.cum[(int64_t)list * (T.D + 1) + min(v - 1, T.D)];
+    if (n == 2) return v <= T.small[list * 2 + 1] ? 1 : 2;
+    return v <= T.small[list * 2] ? 0 : 1;
+}
+
+// ---- K6: rank -> probability -> sd units (src/GROM.c:18754-18963), threshold bits, seed bitmaps
+__global__ void __launch_bounds__(256) k_z(const int32_t *__restrict__ depth, const int32_t *__restrict__ gc, int64_t P, int64_t lo, int64_t hi, int q,
+                                           Tables T, const uint8_t *__restrict__ tile_in, uint32_t *__restrict__ rec,
+                                           uint32_t *__restrict__ seed_del, uint32_t *__restrict__ seed_dup)
+{
+    __shared__ double sp[P2S];
+    for (int i = threadIdx.x; i < P2S; i += blockDim.x) sp[i] = T.p2s_p[i];
+    __syncthreads();
+    const int64_t t0 = (int64_t)blockIdx.x * CTILE;
+    for (int i = threadIdx.x; i < CTILE; i += blockDim.x) {
+        const int64_t p = t0 + i;
+        uint32_t r = 0;
+        bool s_del = false, s_dup = false;
+        if (p < P) {
+            r = rec[p];
+            const int d = depth[p];
+            if (p >= lo) {
+                // thresholds of the position's GC bin; past the analysed span the reference reads bin 0 of a zero-filled array
+                const int g = gc[p];
+                if ((double)d <= T.del_thr[g]) r |= R_DEL0;
+                if ((double)d <= T.del_thr[NB + g]) r |= R_DEL1;
+                if ((double)d >= T.dup_thr[g]) r |= R_DUP0;
+                if ((double)d >= T.dup_thr[NB + g]) r |= R_DUP1;
+            }
+            if (p >= lo && p < hi) {
+                const int g = gc[p];
+                const int cls = (r >> R_CLASS) & 3;
+                s_del = cls == 0 ? (r & R_DEL0) : cls == 1 ? (r & R_DEL1) : (r & (R_DEL0 | R_DEL1));
+                s_dup = cls == 0 ? (r & R_DUP0) : cls == 1 ? (r & R_DUP1) : (r & (R_DUP0 | R_DUP1));
+                if (r & R_USABLE) {
+                    int mi;
+                    if (cls == 0) mi = 0;
+                    else if (cls == 1) mi = 1;
+                    else {
+                        mi = -1;
+                        for (int64_t b = p - 1; b >= t0 && b >= lo; b--) { const uint32_t rb = rec[b]; if ((rb & R_USABLE) && ((rb >> R_CLASS) & 3) != 2) { mi = (rb >> R_CLASS) & 3; break; } }
+                        if (mi < 0) mi = tile_in[blockIdx.x];
+                    }
+                    const int list = mi * NB + g, n = T.n[list];
+                    if (n > 0) {
+                        const double ave = T.ave[list];
+                        int i1, i2;
+                        bool neg;
+                        if ((double)d < ave) { i1 = rank_le(T, list, d); i2 = rank_lt(T, list, d); neg = false; }
+                        else {
+                            if ((double)d > 2 * ave) i1 = rank_lt(T, list, (int)(2 * ave)); else i1 = rank_lt(T, list, d);
+                            i2 = rank_le(T, list, d);
+                            i1 = n - i1; i2 = n - i2; neg = true;
+                        }
+                        const double prob = ((i1 <= 0 ? 0.5 : (double)i1) + (i2 <= 0 ? 0.5 : (double)i2)) / (double)(2 * (long long)n);
+                        int a = 0, b = P2S;                       // first table entry > prob (bisect_right over the ascending p-value table)
+                        while (a < b) { const int m = (a + b) >> 1; if (prob < sp[m]) b = m; else a = m + 1; }
+                        if (a >= P2S) a = P2S - 1;
+                        r |= R_NZ | (neg ? R_NEG : 0u) | ((uint32_t)a << R_K);
+                    }
+                }
+            }
+            rec[p] = r;
+        }
+        const unsigned bd = __ballot_sync(0xffffffffu, s_del), bu = __ballot_sync(0xffffffffu, s_dup);
+        if ((threadIdx.x & 31) == 0 && p < ((P + 31) / 32) * 32) { seed_del[p >> 5] = bd; seed_dup[p >> 5] = bu; }
+    }
+}
+
+// ---- K7: window-length sweep (src/GROM.c:18967-19018).  The walk over a sample block, repeated at each -A offset without resetting
+// the running frame, is cut into frames of Lmax elements; one thread owns one frame and accumulates in the reference's order.
+struct SweepBlock { int64_t start, end; int64_t first_frame, n_frames; };
+__global__ void __launch_bounds__(64) k_sweep(const uint32_t *__restrict__ rec, const SweepBlock *__restrict__ blocks, int n_blocks, int64_t n_frames,
+                                              int A, int Lmin, int Lmax, int q, const double *__restrict__ p2s_sd, double *__restrict__ X)
+{
+    __shared__ double sd[P2S];
+    for (int i = threadIdx.x; i < P2S; i += blockDim.x) sd[i] = p2s_sd[i];
+    __syncthreads();
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_frames) return;
+    int b = 0;
+    while (b + 1 < n_blocks && blocks[b + 1].first_frame <= f) b++;
+    const int64_t s = blocks[b].start, e = blocks[b].end;
+    int64_t c = (f - blocks[b].first_frame) * (int64_t)Lmax;      // index of the frame's first element in the concatenated walk
+    int a = 0;
+    int64_t p = s;
+    for (; a < A; a++) {                                          // locate (offset pass, position) of element c
+        const int64_t adj = (int64_t)a * Lmax / A, len = max((int64_t)0, e - (s + adj));
+        if (c < len) { p = s + adj + c; break; }
+        c -= len;
+    }
+    double tot = 0.0;
+    long long n_us = 0;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int w = 1; w <= Lmax; w++) {
+        while (a < A && p >= e) { a++; p = s + (int64_t)a * Lmax / A; }
+        if (a >= A) {                                             // the walk ended inside this frame: no more observations
+            for (int ww = max(w, Lmin); ww <= Lmax; ww++) X[(int64_t)(ww - Lmin) * n_frames + f] = nan;
+            return;
+        }
+        const uint32_t r = rec[p];
+        if (rec_usable(r)) { tot = __dadd_rn(tot, rec_z(r, q, sd)); n_us++; }
+        p++;
+        if (w >= Lmin) {
+            double x2 = nan;
+            if (n_us > 0) { const double x = tot / (double)n_us; x2 = __dmul_rn(x, x); }
+            X[(int64_t)(w - Lmin) * n_frames + f] = x2;
+        }
+    }
+}
+// ordered sum over the frames: one warp per window length, lanes fetch 32 frames at a time, every lane adds them in frame order
+__global__ void __launch_bounds__(128) k_sweep_sum(const double *__restrict__ X, int64_t n_frames, int n_len, double *__restrict__ wsq, long long *__restrict__ wcnt)
+{
+    const int L = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (L >= n_len) return;
+    const double *row = X + (int64_t)L * n_frames;
+    double sum = 0.0;
+    long long cnt = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += 32) {
+        const double v = f0 + lane < n_frames ? row[f0 + lane] : __longlong_as_double(0x7ff8000000000000LL);
+        for (int i = 0; i < 32; i++) {
+            const double x = __shfl_sync(0xffffffffu, v, i);
+            if (x == x) { sum = __dadd_rn(sum, x); cnt++; }
+        }
+    }
+    if (lane == 0) { wsq[L] = sum; wcnt[L] = cnt; }
+}
+
+// ---- K8: depth and GC bin of the called segments, packed back to back (copy-number step, src/GROM.c:20071-20224)
+// out_gc: bits 0-6 GC bin, bit 7 = ACGT context >= 99 %
+__global__ void __launch_bounds__(256) k_gather(const int32_t *__restrict__ depth, const int32_t *__restrict__ gc, const int32_t *__restrict__ acgt, const int64_t *__restrict__ seg_start,
+                                                const int64_t *__restrict__ seg_first, int n_seg, int64_t total, int32_t *__restrict__ out_depth, uint8_t *__restrict__ out_gc)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= total) return;
+    int a = 0, b = n_seg - 1;
+    while (a < b) { const int m = (a + b + 1) >> 1; if (seg_first[m] <= j) a = m; else b = m - 1; }
+    const int64_t p = seg_start[a] + (j - seg_first[a]);
+    out_depth[j] = depth[p]; out_gc[j] = (uint8_t)((gc[p] & 0x7f) | (acgt[p] >= MIN_ACGT ? 0x80 : 0));
+}
+
+// =====================================================================================================================
+// host side: sequential logic with the reference's libc semantics
+// =====================================================================================================================
+
+// glibc rand(): TYPE_3 additive feedback generator, seeded as srandom_r does
+struct GlibcRand {
+    int32_t r[34]; int f = 3, b = 0;
+    explicit GlibcRand(unsigned seed)
+    {
+        int32_t w = (int32_t)seed; if (w == 0) w = 1;
+        r[0] = w;
+        for (int i = 1; i < 31; i++) { long h = w / 127773, l = w % 127773, t = 16807 * l - 2836 * h; if (t < 0) t += 2147483647; w = (int32_t)t; r[i] = w; }
+        for (int i = 0; i < 310; i++) next();
+    }
+    int next() { const uint32_t v = (uint32_t)r[f] + (uint32_t)r[b]; r[f] = (int32_t)v; f = (f + 1) % 31; b = (b + 1) % 31; return (int)(v >> 1); }
+    long below(long max)            // grom_rand, src/GROM.c:1185-1203
+    {
+        long val = 0, scale = 1;
+        while (scale < max) { long t = (next() % 10) * scale; while (t + val >= max) t = (next() % 10) * scale; val += t; scale *= 10; }
+        return val;
+    }
+};
+
+struct SampleList {
+    std::vector<int> v; long n_all = 0;
+    void add(int x, long cap, GlibcRand &g)
+    {
+        if ((long)v.size() < cap) { v.push_back(x); n_all++; }
+        else { if (g.below(n_all) == 0) v[g.below((long)v.size())] = x; n_all++; }
+    }
+};
+
+struct Call { int64_t start, end; double z; };
+struct DevTmpRaw { void *p = nullptr; ~DevTmpRaw() { if (p) cudaFree(p); } };
+
+// the reference's qsort on the copy-number ratios: glibc merge sort with the comparator `*(int*)a - *(int*)b`, i.e. ordered by the
+// low word of each double with wrapping subtraction (src/GROM.c:1105, 20113)
+inline void lowword_msort(double *b, size_t n, double *tmp)
+{
+    if (n <= 1) return;
+    const size_t n1 = n / 2, n2 = n - n1;
+    lowword_msort(b, n1, tmp); lowword_msort(b + n1, n2, tmp);
+    size_t i = 0, j = n1, k = 0;
+    auto key = [](const double &d) { uint64_t u; memcpy(&u, &d, 8); return (uint32_t)u; };
+    while (i < n1 && j < n) {
+        if ((int32_t)(key(b[i]) - key(b[j])) <= 0) tmp[k++] = b[i++]; else tmp[k++] = b[j++];
+    }
+    while (i < n1) tmp[k++] = b[i++];
+    memcpy(b, tmp, k * sizeof(double));
+}
+
+// greedy segmentation over the packed records (src/GROM.c:19361-19678 deletions, 19702-20010 duplications)
+struct Segmenter {
+    const uint32_t *rec; const uint32_t *seeds; int64_t len, lo, hi; int q; long Lmin, Lmax; const double *sd; const double *win_sd; bool dup;
+    inline int cls(int64_t p) const { return (rec[p] >> R_CLASS) & 3; }
+    inline bool beyond(int64_t p, int mi) const { return rec[p] & (dup ? (mi ? R_DUP1 : R_DUP0) : (mi ? R_DEL1 : R_DEL0)); }
+    inline bool win_gt1(int64_t p, int mi) const { return rec[p] & (mi ? R_WIN1 : R_WIN0); }
+    inline double z(int64_t p) const { const double v = rec_z(rec[p], q, sd); return dup ? -v : v; }
+    inline int64_t next_seed(int64_t p, int64_t end) const
+    {
+        if (p >= end) return end;
+        int64_t w = p >> 5;
+        uint32_t bits = seeds[w] & (0xffffffffu << (p & 31));
+        const int64_t wend = (end + 31) >> 5;
+        while (!bits) { if (++w >= wend) return end; bits = seeds[w]; }
+        const int64_t r = (w << 5) + __builtin_ctz(bits);
+        return r < end ? r : end;
+    }
+    void run(std::vector<Call> &out) const
+    {
+        const int64_t end = hi - Lmin, max_gap = Lmax + 500;
+        int mi = 0, last_low = 0, mi_a = 0, mi_b = 0;
+        int64_t pos = lo;
+#define CNV_STEP(var, p) do { const int c_ = cls(p); if (c_ != 2) var = c_; } while (0)
+        while (pos < end) {
+            // positions between seeds only move last_low: it is the class of the last covered position passed by the outer loop
+            const int64_t nx = next_seed(pos, end);
+            for (int64_t b = nx - 1; b >= pos; b--) { const int c = cls(b); if (c != 2) { last_low = c; break; } }
+            pos = nx;
+            if (pos >= end) break;
+            const int c0 = cls(pos);
+            if (c0 != 2) { mi = c0; last_low = c0; } else mi = last_low;
+            if (!beyond(pos, mi)) { pos++; continue; }
+            bool stop = false, begun = false;
+            int64_t tpos = pos, wlen = 0, cnt = 0, cnt2 = 0, pa, c_start = 0, c_end = 0, last_good = 0;
+            double tot = 0, c_z = 0, tz;
+            for (pa = pos; pa < pos + Lmin; pa++) {
+                wlen++;
+                if (!(rec[pa] & R_MASK)) {
+                    CNV_STEP(mi, pa);
+                    if (beyond(pa, mi)) cnt2++;
+                    else if (2 * cnt2 < wlen) { stop = true; tpos = pa; break; }
+                } else if (2 * cnt2 < wlen) { stop = true; tpos = pa; break; }
+            }
+            if (!stop) {
+                cnt = Lmin;
+                for (int64_t a = pos; a < pos + Lmin; a++) { cnt -= rec[a] & R_MASK; tot += z(a); }
+                if (cnt > 0 && win_sd[Lmin] > 0 && tot / (cnt * win_sd[Lmin]) >= 3) {
+                    begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tot / (cnt * win_sd[Lmin]);
+                }
+                for (pa = pos + Lmin; pa < pos + Lmax; pa++) {
+                    wlen++;
+                    if (pa >= end) { stop = true; break; }
+                    if (!(rec[pa] & R_MASK)) {
+                        CNV_STEP(mi, pa);
+                        tot += z(pa); cnt++;
+                        if (beyond(pa, mi)) {
+                            cnt2++;
+                            if (win_sd[wlen] > 0 && tot / (cnt * win_sd[wlen]) >= 3) {
+                                last_good = pa; tz = tot / (cnt * win_sd[wlen]);
+                                if (!begun) { begun = true; c_start = pos; c_end = pa; c_z = tz; }
+                                else { c_end = pa; if (tz > c_z) c_z = tz; }
+                            }
+                        } else if (2 * cnt2 < wlen) { stop = true; break; }
+                    } else if (2 * cnt2 < wlen) { stop = true; break; }
+                }
+            }
+            if (!stop && begun) {
+                pa = pos + Lmax; tot = 0; cnt = 0; mi_b = mi;
+                while (pa < len && pa - last_good <= max_gap) {
+                    if (pa == pos + Lmax) {
+                        for (int64_t pb = pa - Lmax + 1; pb < pa + 1; pb++) {
+                            CNV_STEP(mi_b, pb);
+                            if (!(rec[pb] & R_MASK) && win_gt1(pb, mi_b)) { tot += z(pb); cnt++; }
+                        }
+                    } else {
+                        const int64_t pb = pa - Lmax;
+                        CNV_STEP(mi_b, pb);
+                        if (!(rec[pb] & R_MASK) && win_gt1(pb, mi_b)) { tot -= z(pb); cnt--; }
+                        CNV_STEP(mi, pa);
+                        if (!(rec[pa] & R_MASK) && win_gt1(pa, mi)) { tot += z(pa); cnt++; }
+                    }
+                    if (cnt > 0 && win_sd[Lmax] > 0 && tot / (cnt * win_sd[Lmax]) >= 3) {
+                        last_good = pa; c_end = pa; tz = tot / (cnt * win_sd[Lmax]);
+                        if (tz > c_z) c_z = tz;
+                    }
+                    pa++;
+                }
+            }
+            if (begun) {
+                int64_t t = c_end;
+                while (t > c_start + Lmin) {
+                    CNV_STEP(mi, t);
+                    if (!beyond(t, mi)) { t--; c_end = t; }
+                    else {
+                        int64_t c2 = 0, c3 = 0;
+                        bool halt = false;
+                        pa = c_end; mi_a = mi;
+                        while (pa > c_start + Lmin && !halt) {
+                            if (!(rec[pa] & R_MASK)) { CNV_STEP(mi_a, pa); c3++; if (beyond(pa, mi_a)) c2++; }
+                            if (c3 == 0 || c2 / (double)c3 < 0.5) { c_end = pa - 1; halt = true; }
+                            pa--;
+                        }
+                        t = pa;
+                    }
+                }
+                out.push_back({c_start, c_end, c_z});
+                pos = c_end + 1;
+            } else if (stop) pos = tpos;
+            pos++;
+        }
+#undef CNV_STEP
+    }
+};
+
+}  // namespace cnv

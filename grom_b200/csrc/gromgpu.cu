@@ -20,6 +20,8 @@
 #include <stdarg.h>
 #include <algorithm>
 #include <vector>
+#include <chrono>
+#include <thread>
 #include "gromgpu.h"
 
 #define F_PAIRED 1
@@ -928,6 +930,7 @@ __global__ void __launch_bounds__(GC_THREADS) k_gc_prepass(const char *__restric
 }
 
 #include "sv_evidence.cuh"
+#include "cnv.cuh"
 
 __global__ void k_fix_offsets(uint64_t *cigar_off, uint64_t *base_off, int64_t n, uint64_t cig_base, uint64_t slot_base)
 {
@@ -956,6 +959,8 @@ struct DevBuf {
 enum { B_POS, B_MPOS, B_TLEN, B_MTID, B_LQSEQ, B_FLAG, B_NCIGAR, B_MAPQ, B_QLEN, B_HASH, B_CIGOFF, B_BASEOFF, B_CIGAR, B_SEQ4, B_QUAL,
        B_SAPOS, B_SASADJ, B_SAEADJ, B_SAINDEL, B_SASTRAND, B_SAMAPQ, B_SASAME, B_COUNT };
 
+struct CnvState;
+static void cnv_state_free(CnvState *c);
 struct gromgpu_chr {
     int tid = 0;
     int64_t P = 0, Ppad = 0;
@@ -983,6 +988,7 @@ struct gromgpu_chr {
     double *d_cl_dist = nullptr;                     // [10][Ppad]
     int64_t n_items = 0;
     std::vector<grom_snv_cand> h_cand;
+    struct CnvState *cnv = nullptr;
     cudaEvent_t ev[12];
     bool ran = false;
     gromgpu_stats stats;
@@ -1086,6 +1092,7 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
     for (int i = 0; i < 12; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_item_cnt); cudaFree(h->d_items); cudaFree(h->d_sv_tiles); cudaFree(h->d_sv_dirty); cudaFree(h->d_sv_small); cudaFree(h->d_pool);
     cudaFree(h->d_cl_int); cudaFree(h->d_cl_dist);
+    cnv_state_free(h->cnv);
     delete h;
 }
 
@@ -1355,5 +1362,483 @@ extern "C" int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0
     if (!h || !h->ran) return fail("gromgpu_fetch_read_state: call gromgpu_chr_run first");
     if (i0 < 0 || i1 > h->n_reads || i0 > i1) return fail("gromgpu_fetch_read_state: bad range");
     CK(cudaMemcpy(dst, h->d_state + i0, (size_t)(i1 - i0), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+
+// ================================================================================================ read-depth CNV path (cnv.cuh)
+struct CnvState {
+    int32_t *d_depth = nullptr; uint8_t *d_mq8 = nullptr; uint32_t *d_rec = nullptr, *d_seed = nullptr;   // d_seed: [2][words]
+    cnv::PreOut *d_pre = nullptr; unsigned long long *d_hist = nullptr;
+    cnv::RepRec *d_rep = nullptr; unsigned int *d_nrep = nullptr; unsigned int rep_cap = 0;
+    uint8_t *d_tile = nullptr;                                         // [4][n_tiles]: last/in of the mask stage, last/in of the z stage
+    uint32_t *h_rec = nullptr, *h_seed = nullptr;                      // pinned
+    std::vector<grom_cnv_call> calls;
+    std::vector<double> win_sd, bin_d; std::vector<int64_t> win_cnt, bin_n;
+    int64_t P = 0, words = 0;
+    int q = 0;
+    std::vector<double> sd_tbl;
+};
+static void cnv_state_free(CnvState *c)
+{
+    if (!c) return;
+    cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
+    cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
+    if (c->h_rec) cudaFreeHost(c->h_rec);
+    if (c->h_seed) cudaFreeHost(c->h_seed);
+    delete c;
+}
+
+// the reference's bisections run literally (src/GROM.c:21630-21744); STRICT = bisect_right
+template <bool STRICT> static long ref_bisect(const int *a, int v, long s, long e)
+{
+    auto less = [](int x, int y) { return STRICT ? x < y : x <= y; };
+    long lo = s, hi = e, i = s + (e - s) / 2;
+    for (;;) {
+        if (i <= s) return less(v, a[s]) ? s : s + 1;
+        if (i >= e - 1) return less(v, a[e - 1]) ? e - 1 : e;
+        if (less(v, a[i])) { hi = i; i = lo + (i - lo) / 2; if (hi == i) return i + 1; }
+        else { lo = i; i = i + (hi - i) / 2; if (lo == i) return i + 1; }
+    }
+}
+
+namespace {
+struct DevTmp {             // scoped device allocation
+    void *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+    template <class T> T *as() { return (T *)p; }
+};
+}
+
+extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double *p2s_sd, int n_p2s, int ploidy, gromgpu_cnv_result *out)
+{
+    using namespace cnv;
+    if (!h || !h->ran) return fail("gromgpu_chr_cnv: call gromgpu_chr_run first");
+    if (!out || !p2s_p || !p2s_sd) return fail("gromgpu_chr_cnv: null argument");
+    if (n_p2s != P2S) return fail("gromgpu_chr_cnv: the p-value table must have %d entries (got %d)", P2S, n_p2s);
+    if (ploidy <= 0) return fail("gromgpu_chr_cnv: ploidy must be positive");
+    const grom_params &prm = g_params;
+    const int64_t P = h->P, Ppad = h->Ppad, M = prm.insert_mean, W1 = 2 * M - 1, lo = M - 1, hi = P - W1, half = M / 2;
+    const int q = prm.rd_min_mapq, A = prm.windows_sampling_factor, Lmin = prm.min_rd_window_len, Lmax = prm.max_rd_window_len;
+    const long cap = prm.sample_lists_len;
+    if (Lmin < 1 || Lmax < Lmin || A < 1 || half < 1) return fail("gromgpu_chr_cnv: bad window parameters");
+    memset(out, 0, sizeof(*out));
+    out->biased_repeat = -1;
+    cudaStream_t s = h->stream;
+    if (!h->cnv) h->cnv = new CnvState();
+    CnvState &c = *h->cnv;
+    c.calls.clear(); c.q = q; c.P = P;
+    c.sd_tbl.assign(p2s_sd, p2s_sd + P2S);
+    c.win_sd.assign(Lmax + 1, 0.0); c.win_cnt.assign(Lmax + 1, 0); c.bin_d.assign(4 * NLIST, 0.0); c.bin_n.assign(NLIST, 0);
+    out->win_sd = c.win_sd.data(); out->win_cnt = c.win_cnt.data();
+    out->bin_ave = c.bin_d.data(); out->bin_sd = c.bin_d.data() + NLIST; out->bin_del_thr = c.bin_d.data() + 2 * NLIST; out->bin_dup_thr = c.bin_d.data() + 3 * NLIST;
+    out->bin_n = c.bin_n.data();
+    if (hi <= lo) return 0;                                            // contig shorter than the GC window: nothing is analysed
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const auto t_begin = std::chrono::steady_clock::now();
+    double ms_dev = 0;
+    auto dev_begin = [&]() { cudaEventRecord(e0, s); };
+    auto dev_end = [&]() { cudaEventRecord(e1, s); cudaEventSynchronize(e1); float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms_dev += ms; };
+
+    const int32_t *A_mq = h->d_arrays + (int64_t)GA_RD_MQ * Ppad, *A_rd = h->d_arrays + (int64_t)GA_RD_RD * Ppad, *A_low = h->d_arrays + (int64_t)GA_RD_LOW * Ppad;
+    const int32_t *A_gc = h->d_arrays + (int64_t)GA_GC * Ppad, *A_acgt = h->d_arrays + (int64_t)GA_ACGT * Ppad;
+    const int64_t n_blk = (P + BLK_UNIT - 1) / BLK_UNIT, n_tiles = (P + CTILE - 1) / CTILE, words = (P + 31) / 32;
+    c.words = words;
+    if (!c.d_depth) {
+        CK(cudaMalloc(&c.d_depth, sizeof(int32_t) * P)); CK(cudaMalloc(&c.d_mq8, P)); CK(cudaMalloc(&c.d_rec, sizeof(uint32_t) * P));
+        CK(cudaMalloc(&c.d_seed, sizeof(uint32_t) * 2 * words)); CK(cudaMalloc(&c.d_pre, sizeof(PreOut) * n_blk));
+        CK(cudaMalloc(&c.d_hist, sizeof(unsigned long long) * HIST_ALL));
+        c.rep_cap = (unsigned int)(P / 20 + 2);
+        CK(cudaMalloc(&c.d_rep, sizeof(RepRec) * c.rep_cap)); CK(cudaMalloc(&c.d_nrep, sizeof(unsigned int)));
+        CK(cudaMalloc(&c.d_tile, 4 * n_tiles));
+        CK(cudaMallocHost(&c.h_rec, sizeof(uint32_t) * P)); CK(cudaMallocHost(&c.h_seed, sizeof(uint32_t) * 2 * words));
+    }
+
+    // ---- stage 1: pre-statistics + repeat runs
+    dev_begin();
+    CK(cudaMemsetAsync(c.d_hist, 0, sizeof(unsigned long long) * HIST_ALL, s));
+    CK(cudaMemsetAsync(c.d_nrep, 0, sizeof(unsigned int), s));
+    k_pre<<<(unsigned)n_blk, 256, 0, s>>>(A_mq, A_rd, A_low, A_acgt, h->d_fasta, P, lo, hi, c.d_depth, c.d_mq8, c.d_pre, c.d_hist);
+    k_repeats<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(h->d_fasta, c.d_depth, lo, hi, c.d_rep, c.rep_cap, c.d_nrep);
+    std::vector<PreOut> pre(n_blk);
+    std::vector<unsigned long long> hist(HIST_ALL);
+    unsigned int n_rep = 0;
+    CK(cudaMemcpyAsync(pre.data(), c.d_pre, sizeof(PreOut) * n_blk, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hist.data(), c.d_hist, sizeof(unsigned long long) * HIST_ALL, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&n_rep, c.d_nrep, sizeof(n_rep), cudaMemcpyDeviceToHost, s));
+    dev_end();
+    CK(cudaGetLastError());
+    if (n_rep > c.rep_cap) return fail("gromgpu_chr_cnv: %u repeat runs exceed the buffer of %u", n_rep, c.rep_cap);
+    std::vector<RepRec> reps(n_rep);
+    if (n_rep) CK(cudaMemcpy(reps.data(), c.d_rep, sizeof(RepRec) * n_rep, cudaMemcpyDeviceToHost));
+    std::sort(reps.begin(), reps.end(), [](const RepRec &a, const RepRec &b) { return a.s < b.s; });
+    out->n_repeats = n_rep;
+
+    // contig mean / sd (src/GROM.c:16648-16686); the sd sums squares per depth value instead of per position
+    unsigned long long ave_sum = 0, ave_cnt = 0, acgt_sum = 0, acgt_cnt = 0;
+    for (const PreOut &b : pre) { ave_sum += b.ave_sum; ave_cnt += b.ave_cnt; acgt_sum += b.acgt_sum; acgt_cnt += b.acgt_cnt; }
+    double chr_ave = (double)ave_sum, chr_sd = 0;
+    if (ave_cnt > 0) chr_ave = chr_ave / (double)(long)ave_cnt;
+    for (int d = 0; d < HIST_ALL; d++) if (hist[d]) {
+        const double term = (double)d < 2 * chr_ave ? ((double)d - chr_ave) * ((double)d - chr_ave) : chr_ave * chr_ave;
+        chr_sd += term * (double)hist[d];
+    }
+    chr_sd = ave_cnt > 1 ? sqrt(chr_sd / ((double)ave_cnt - 1.0)) : 0.0;
+    out->chr_ave = chr_ave; out->chr_sd = chr_sd;
+    // per-type repeat depth and the most biased type (src/GROM.c:16693-16774)
+    int biased = -1;
+    {
+        double r_ave[10] = {0}, r_sd[10] = {0}; long r_cnt[10] = {0};
+        std::vector<double> rl(n_rep);
+        for (unsigned i = 0; i < n_rep; i++) {
+            rl[i] = (double)reps[i].depth_sum / (double)(reps[i].e - reps[i].s);
+            r_ave[reps[i].type] += rl[i] < 2 * chr_ave ? rl[i] : 2 * chr_ave;
+            r_cnt[reps[i].type]++;
+        }
+        for (int k = 0; k < 10; k++) r_ave[k] = r_ave[k] / (double)r_cnt[k];
+        for (unsigned i = 0; i < n_rep; i++) {
+            const int t = reps[i].type;
+            const double x = rl[i] < 2 * chr_ave ? rl[i] : 2 * chr_ave;
+            r_sd[t] += (x - r_ave[t]) * (x - r_ave[t]);
+        }
+        long best = 0;
+        for (int k = 0; k < 10; k++) {
+            r_sd[k] = r_cnt[k] > 1 ? sqrt(r_sd[k] / ((double)r_cnt[k] - 1.0)) : 0.0;
+            if (r_cnt[k] > NO_COMBINE && r_ave[k] + 1.5 * r_sd[k] < chr_ave && chr_ave - 1.5 * chr_sd > r_ave[k] && r_cnt[k] > best) { biased = k; best = r_cnt[k]; }
+        }
+    }
+    out->biased_repeat = biased;
+    // 10 kb blocks above twice the contig mean -> runs -> their complement is what gets sampled (src/GROM.c:16784-16990)
+    std::vector<int64_t> sb_s, sb_e;
+    {
+        const int64_t nfull = P / BLK_UNIT;
+        const double blk_ave = (double)(long)acgt_sum / (double)(long)acgt_cnt, thr = 2 * blk_ave;
+        out->blk_ave = blk_ave;
+        std::vector<long> over;
+        for (int64_t k = 0; k < nfull; k++) if ((double)(long)pre[k].blk_sum / (double)BLK_UNIT > thr) over.push_back((long)k);
+        std::vector<long> bs(10001, 0), be(10001, 0);
+        long run = 0, r_s = 0, r_e = 0, bi = 0;
+        for (size_t a = 1; a < over.size(); a++) {
+            if (run == 0) {
+                if (run + 1 > (over[a] - over[a - 1]) / 4) { r_e = over[a] + 1; run++; } else r_e = over[a - 1] + 1;
+                r_s = over[a - 1]; run++;
+            } else {
+                if (run + 1 > (over[a - 1] - r_s) / 4) { r_e = over[a - 1] + 1; run++; }
+                else { if (run >= 4) bi++; r_s = over[a - 1]; r_e = over[a - 1] + 1; run = 1; }
+                if (run >= 4 && bi < 10000) { bs[bi] = r_s * BLK_UNIT; be[bi] = r_e * BLK_UNIT; }
+            }
+        }
+        if (run >= 4) bi++;
+        std::vector<long> ls(bi + 3, 0), le(bi + 3, 0);
+        long li = 0;
+        for (long a = 0; a < bi && a < 10000; a++) if (be[a] - bs[a] >= 10000) { le[li] = bs[a]; ls[li + 1] = be[a]; li++; }
+        li++;
+        le[li - 1] = P;
+        for (long k = 0; k < li; k++) {
+            if (ls[k] < lo) ls[k] = lo; else if (ls[k] >= hi) ls[k] = hi;
+            if (le[k] < lo) le[k] = lo; else if (le[k] >= hi) le[k] = hi;
+            if (le[k] - ls[k] >= Lmin) { sb_s.push_back(ls[k]); sb_e.push_back(le[k]); }
+        }
+    }
+    const int n_sb = (int)sb_s.size();
+    out->n_sample_blocks = n_sb;
+
+    // ---- stage 2: depth samples -> per-bin sorted lists (host: reservoir with libc-rand semantics), statistics, rank tables
+    std::vector<int64_t> sb_first(n_sb + 1, 0);
+    for (int k = 0; k < n_sb; k++) sb_first[k + 1] = sb_first[k] + (sb_e[k] - sb_s[k] + half - 1) / half;
+    const int64_t n_samples = sb_first[n_sb];
+    out->n_samples = n_samples;
+    std::vector<Sample> samples(n_samples);
+    DevTmp t_sb, t_first, t_samples;
+    if (n_samples) {
+        CK(cudaMalloc(&t_sb.p, sizeof(int64_t) * n_sb)); CK(cudaMalloc(&t_first.p, sizeof(int64_t) * (n_sb + 1))); CK(cudaMalloc(&t_samples.p, sizeof(Sample) * n_samples));
+        dev_begin();
+        CK(cudaMemcpyAsync(t_sb.p, sb_s.data(), sizeof(int64_t) * n_sb, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(t_first.p, sb_first.data(), sizeof(int64_t) * (n_sb + 1), cudaMemcpyHostToDevice, s));
+        k_samples<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(c.d_depth, A_rd, A_low, c.d_mq8, A_gc, A_acgt, t_sb.as<int64_t>(), t_first.as<int64_t>(), n_sb,
+                                                                     n_samples, half, q, t_samples.as<Sample>());
+        CK(cudaMemcpyAsync(samples.data(), t_samples.p, sizeof(Sample) * n_samples, cudaMemcpyDeviceToHost, s));
+        dev_end();
+        CK(cudaGetLastError());
+    }
+    GlibcRand rng((unsigned)prm.rand_seed);
+    // most-biased repeat: depth samples by distance segment around every run of that type (src/GROM.c:18262-18367)
+    constexpr int SEG = 10;
+    std::vector<int64_t> rp_start, rp_first;      // gathered ranges around the biased repeats
+    std::vector<int32_t> rp_depth; std::vector<uint8_t> rp_gc;
+    SampleList rsl[SEG];
+    double rs_ave[SEG] = {0}, rs_sd[SEG] = {0};
+    std::vector<unsigned> biased_idx;
+    auto gather = [&](const std::vector<int64_t> &starts, const std::vector<int64_t> &firsts, std::vector<int32_t> &o_depth, std::vector<uint8_t> &o_gc) -> int {
+        const int n_seg = (int)starts.size();
+        const int64_t total = firsts.back();
+        o_depth.resize(total); o_gc.resize(total);
+        if (!total) return 0;
+        DevTmp a, b, od, og;
+        CK(cudaMalloc(&a.p, sizeof(int64_t) * n_seg)); CK(cudaMalloc(&b.p, sizeof(int64_t) * (n_seg + 1)));
+        CK(cudaMalloc(&od.p, sizeof(int32_t) * total)); CK(cudaMalloc(&og.p, total));
+        dev_begin();
+        CK(cudaMemcpyAsync(a.p, starts.data(), sizeof(int64_t) * n_seg, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b.p, firsts.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, s));
+        k_gather<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c.d_depth, A_gc, A_acgt, a.as<int64_t>(), b.as<int64_t>(), n_seg, total, od.as<int32_t>(), og.as<uint8_t>());
+        CK(cudaMemcpyAsync(o_depth.data(), od.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(o_gc.data(), og.p, total, cudaMemcpyDeviceToHost, s));
+        dev_end();
+        CK(cudaGetLastError());
+        return 0;
+    };
+    auto rep_segment = [&](int64_t p, const RepRec &r) -> int {
+        if (p < r.s) return (int)((SEG - 1) * (p - (r.s - half)) / half);
+        if (p >= r.e) return (int)((SEG - 1) * ((r.e + half) - p) / half);
+        return SEG - 1;
+    };
+    if (biased != -1) {
+        rp_first.push_back(0);
+        for (unsigned i = 0; i < n_rep; i++) if (reps[i].type == biased) {
+            const int64_t a = std::max<int64_t>(0, reps[i].s - half), b = std::min<int64_t>(P, reps[i].e + half);
+            biased_idx.push_back(i); rp_start.push_back(a); rp_first.push_back(rp_first.back() + (b - a));
+        }
+        if (gather(rp_start, rp_first, rp_depth, rp_gc)) return -1;
+        for (size_t k = 0; k < biased_idx.size(); k++) {
+            const RepRec &r = reps[biased_idx[k]];
+            for (int64_t j = rp_first[k]; j < rp_first[k + 1]; j++) {
+                const int64_t p = rp_start[k] + (j - rp_first[k]);
+                if (rp_gc[j] & 0x80) rsl[rep_segment(p, r)].add(rp_depth[j], cap, rng);
+            }
+        }
+        for (int k = 0; k < SEG; k++) {
+            std::sort(rsl[k].v.begin(), rsl[k].v.end());
+            const long n = (long)rsl[k].v.size();
+            if (n > 0) {
+                const long a = n / 20, b = n - a, m = b - a;
+                double sm = 0, v = 0;
+                for (long j = a; j < b; j++) sm += rsl[k].v[j];
+                rs_ave[k] = sm / m;
+                for (long j = a; j < b; j++) v += (rsl[k].v[j] - rs_ave[k]) * (rsl[k].v[j] - rs_ave[k]);
+                rs_sd[k] = m > 1 ? sqrt(v / (m - 1)) : v;
+            }
+        }
+    }
+    // GC-stratified lists: an uncovered sample joins the list of the last covered one (src/GROM.c:18373-18456)
+    std::vector<SampleList> lists(NLIST);
+    {
+        int last_low = 0;
+        for (int64_t j = 0; j < n_samples; j++) {
+            const int code = samples[j].code;
+            if (!(code & 1)) continue;
+            const int cls = (code >> 1) & 3, g = code >> 8;
+            int to_low;
+            if (cls == 2) to_low = last_low; else to_low = last_low = cls;
+            lists[to_low * NB + g].add(samples[j].depth, cap, rng);
+        }
+    }
+    for (auto &l : lists) std::sort(l.v.begin(), l.v.end());
+    {
+        // thin bins (20 <= n < 100) borrow the original samples of the two bins on either side (src/GROM.c:18481-18548)
+        std::vector<std::vector<int>> grown(NLIST);
+        for (int m = 0; m < 2; m++)
+            for (int b = 2; b < NB - 2; b++) {
+                const auto &me = lists[m * NB + b].v;
+                if ((long)me.size() < MIN_WINDOWS || (long)me.size() >= NO_COMBINE) continue;
+                std::vector<int> g(me);
+                for (int a = b - 2; a <= b + 2; a++) if (a != b) for (int x : lists[m * NB + a].v) if ((long)g.size() < cap) g.push_back(x);
+                std::sort(g.begin(), g.end());
+                grown[m * NB + b] = std::move(g);
+            }
+        for (int l = 0; l < NLIST; l++) if (!grown[l].empty()) lists[l].v = std::move(grown[l]);
+    }
+    const double del_f = 1.0 - 0.6 / ploidy, dup_f = 1.0 + 0.6 / ploidy;
+    std::vector<double> ave(NLIST, 0.0), sdv(NLIST, 0.0), del_thr(NLIST, 0.0), dup_thr(NLIST, 0.0);
+    std::vector<int32_t> nlist(NLIST, 0), small(2 * NLIST, 0);
+    int D = 0;
+    for (int l = 0; l < NLIST; l++) {
+        const auto &v = lists[l].v;
+        const long n = (long)v.size();
+        nlist[l] = (int32_t)n;
+        if (n > 0) {
+            double sm = 0, var = 0;
+            for (long j = 0; j < n; j++) sm += v[j];
+            ave[l] = sm / n; del_thr[l] = del_f * ave[l]; dup_thr[l] = dup_f * ave[l];
+            for (long j = 0; j < n; j++) var += (v[j] - ave[l]) * (v[j] - ave[l]);
+            sdv[l] = n > 1 ? sqrt(var / (n - 1)) : var;
+            D = std::max(D, v.back());
+            small[2 * l] = v[0]; small[2 * l + 1] = n > 1 ? v[1] : v[0];
+        }
+        c.bin_d[l] = ave[l]; c.bin_d[NLIST + l] = sdv[l]; c.bin_d[2 * NLIST + l] = del_thr[l]; c.bin_d[3 * NLIST + l] = dup_thr[l]; c.bin_n[l] = n;
+    }
+    if (D < 0) D = 0;
+    if ((int64_t)NLIST * (D + 1) > (int64_t)1 << 30) return fail("gromgpu_chr_cnv: sampled depth %d is too large for the rank tables", D);
+    std::vector<int32_t> cum((size_t)NLIST * (D + 1), 0);
+    for (int l = 0; l < NLIST; l++) {
+        int32_t *row = cum.data() + (size_t)l * (D + 1);
+        for (int x : lists[l].v) row[x]++;
+        for (int d = 1; d <= D; d++) row[d] += row[d - 1];
+    }
+    DevTmp t_cum, t_n, t_small, t_dbl;
+    CK(cudaMalloc(&t_cum.p, sizeof(int32_t) * cum.size())); CK(cudaMalloc(&t_n.p, sizeof(int32_t) * NLIST)); CK(cudaMalloc(&t_small.p, sizeof(int32_t) * 2 * NLIST));
+    CK(cudaMalloc(&t_dbl.p, sizeof(double) * (3 * NLIST + 2 * P2S)));
+    std::vector<double> dbl(3 * NLIST + 2 * P2S);
+    std::copy(ave.begin(), ave.end(), dbl.begin()); std::copy(del_thr.begin(), del_thr.end(), dbl.begin() + NLIST); std::copy(dup_thr.begin(), dup_thr.end(), dbl.begin() + 2 * NLIST);
+    std::copy(p2s_p, p2s_p + P2S, dbl.begin() + 3 * NLIST); std::copy(p2s_sd, p2s_sd + P2S, dbl.begin() + 3 * NLIST + P2S);
+    Tables T;
+    T.cum = t_cum.as<int32_t>(); T.D = D; T.n = t_n.as<int32_t>(); T.small = t_small.as<int32_t>();
+    T.ave = t_dbl.as<double>(); T.del_thr = T.ave + NLIST; T.dup_thr = T.ave + 2 * NLIST; T.p2s_p = T.ave + 3 * NLIST; T.p2s_sd = T.p2s_p + P2S;
+
+    // ---- stage 3: mask, z, seeds, window sweep
+    // walk of every sample block at each -A offset, cut into frames of Lmax elements
+    std::vector<SweepBlock> sw(n_sb);
+    int64_t n_frames = 0;
+    for (int k = 0; k < n_sb; k++) {
+        int64_t total = 0;
+        for (int a = 0; a < A; a++) total += std::max<int64_t>(0, sb_e[k] - (sb_s[k] + (int64_t)a * Lmax / A));
+        sw[k].start = sb_s[k]; sw[k].end = sb_e[k]; sw[k].first_frame = n_frames; sw[k].n_frames = (total + Lmax - 1) / Lmax;
+        n_frames += sw[k].n_frames;
+    }
+    out->n_frames = n_frames;
+    const int n_len = Lmax - Lmin + 1;
+    DevTmp t_sw, t_X, t_wsq, t_wcnt;
+    if (n_frames) {
+        CK(cudaMalloc(&t_sw.p, sizeof(SweepBlock) * n_sb)); CK(cudaMalloc(&t_X.p, sizeof(double) * (size_t)n_len * n_frames));
+        CK(cudaMalloc(&t_wsq.p, sizeof(double) * n_len)); CK(cudaMalloc(&t_wcnt.p, sizeof(long long) * n_len));
+    }
+    uint8_t *tl_mask = c.d_tile, *ti_mask = c.d_tile + n_tiles, *tl_z = c.d_tile + 2 * n_tiles, *ti_z = c.d_tile + 3 * n_tiles;
+    std::vector<double> wsq(n_len, 0.0); std::vector<long long> wcnt(n_len, 0);
+    dev_begin();
+    CK(cudaMemcpyAsync(t_cum.p, cum.data(), sizeof(int32_t) * cum.size(), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t_n.p, nlist.data(), sizeof(int32_t) * NLIST, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t_small.p, small.data(), sizeof(int32_t) * 2 * NLIST, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(t_dbl.p, dbl.data(), sizeof(double) * dbl.size(), cudaMemcpyHostToDevice, s));
+    k_tile_last_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_acgt, lo, hi, q, tl_mask);
+    k_carry_scan<<<1, 1024, 0, s>>>(tl_mask, ti_mask, (int)n_tiles);
+    k_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_gc, A_acgt, P, lo, hi, q, T.n, ti_mask, c.d_rec, tl_z);
+    k_carry_scan<<<1, 1024, 0, s>>>(tl_z, ti_z, (int)n_tiles);
+    k_z<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, A_gc, P, lo, hi, q, T, ti_z, c.d_rec, c.d_seed, c.d_seed + words);
+    CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
+    if (n_frames) {
+        CK(cudaMemcpyAsync(t_sw.p, sw.data(), sizeof(SweepBlock) * n_sb, cudaMemcpyHostToDevice, s));
+        k_sweep<<<(unsigned)((n_frames + 63) / 64), 64, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>());
+        k_sweep_sum<<<(unsigned)((n_len * 32 + 127) / 128), 128, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>());
+        CK(cudaMemcpyAsync(wsq.data(), t_wsq.p, sizeof(double) * n_len, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(wcnt.data(), t_wcnt.p, sizeof(long long) * n_len, cudaMemcpyDeviceToHost, s));
+    }
+    dev_end();
+    CK(cudaGetLastError());
+    for (int L = Lmin; L <= Lmax; L++) {
+        c.win_cnt[L] = wcnt[L - Lmin];
+        c.win_sd[L] = wcnt[L - Lmin] > 1 ? sqrt(wsq[L - Lmin] / (double)(wcnt[L - Lmin] - 1)) : 0.0;
+    }
+
+    // most-biased repeat override of the z list, after the sweep like the reference (src/GROM.c:19023-19150)
+    if (biased != -1) {
+        for (size_t k = 0; k < biased_idx.size(); k++) {
+            const RepRec &r = reps[biased_idx[k]];
+            for (int64_t j = rp_first[k]; j < rp_first[k + 1]; j++) {
+                const int64_t p = rp_start[k] + (j - rp_first[k]);
+                uint32_t &rec = c.h_rec[p];
+                if (rec & R_MASK) continue;
+                const int sg = rep_segment(p, r), d = rp_depth[j];
+                const std::vector<int> &v = rsl[sg].v;
+                const long n = (long)v.size();
+                long i1, i2; bool neg;
+                if ((double)d < rs_ave[sg]) { i1 = ref_bisect<true>(v.data(), d, 0, n); i2 = ref_bisect<false>(v.data(), d, 0, n); neg = false; }
+                else {
+                    if ((double)d > 2 * rs_ave[sg]) i1 = ref_bisect<false>(v.data(), (int)(2 * rs_ave[sg]), 0, n); else i1 = ref_bisect<false>(v.data(), d, 0, n);
+                    i2 = ref_bisect<true>(v.data(), d, 0, n);
+                    i1 = n - i1; i2 = n - i2; neg = true;
+                }
+                const double prob = ((i1 <= 0 ? 0.5 : (double)i1) + (i2 <= 0 ? 0.5 : (double)i2)) / (double)(2 * n);
+                long kk = std::upper_bound(p2s_p, p2s_p + P2S, prob) - p2s_p;
+                if (kk >= P2S) kk = P2S - 1;
+                rec = (rec & ~(R_NEG | (1023u << R_K))) | R_NZ | R_OVR | (neg ? R_NEG : 0u) | ((uint32_t)kk << R_K);
+            }
+        }
+        CK(cudaMemcpyAsync(c.d_rec, c.h_rec, sizeof(uint32_t) * P, cudaMemcpyHostToDevice, s));      // keeps gromgpu_cnv_fetch consistent
+        CK(cudaStreamSynchronize(s));
+    }
+
+    // ---- stage 4: greedy segmentation (two host threads: deletions, duplications) and copy number
+    std::vector<Call> found[2];
+    {
+        Segmenter sg[2];
+        for (int k = 0; k < 2; k++) {
+            sg[k].rec = c.h_rec; sg[k].seeds = c.h_seed + k * words; sg[k].len = P; sg[k].lo = lo; sg[k].hi = hi; sg[k].q = q; sg[k].Lmin = Lmin; sg[k].Lmax = Lmax;
+            sg[k].sd = c.sd_tbl.data(); sg[k].win_sd = c.win_sd.data(); sg[k].dup = k == 1;
+        }
+        std::thread th([&]() { sg[1].run(found[1]); });
+        sg[0].run(found[0]);
+        th.join();
+    }
+    std::vector<int64_t> seg_start, seg_first(1, 0);
+    for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) { seg_start.push_back(cl.start); seg_first.push_back(seg_first.back() + std::max<int64_t>(0, cl.end - cl.start)); }
+    std::vector<int32_t> g_depth; std::vector<uint8_t> g_gc;
+    if (!seg_start.empty() && gather(seg_start, seg_first, g_depth, g_gc)) return -1;
+    {
+        std::vector<double> buf, tmp;
+        size_t si = 0;
+        for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) {
+            grom_cnv_call o; o.start = cl.start; o.end = cl.end; o.kind = k; o.reserved = 0; o.z = cl.z; o.cn = -1; o.cn_sd = 0;
+            buf.clear();
+            for (int64_t j = seg_first[si]; j < seg_first[si + 1]; j++) {
+                const int64_t p = cl.start + (j - seg_first[si]);
+                const uint32_t r = c.h_rec[p];
+                if (r & R_MASK) continue;
+                const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (g_gc[j] & 0x7f);
+                if (ave[l] > 0) buf.push_back((double)g_depth[j] / ave[l]);
+            }
+            si++;
+            const long n = (long)buf.size();
+            if (n > 0) {
+                tmp.resize(n);
+                lowword_msort(buf.data(), n, tmp.data());
+                const long a = (long)(0.1 * n), b = n - a;
+                double tot = 0;
+                for (long j = a; j < b; j++) tot += buf[j];
+                if (b - a > 0) {
+                    o.cn = (tot / (b - a)) * ploidy;
+                    double v = 0;
+                    for (long j = 0; j < n; j++) { const double dd = ploidy * buf[j] - o.cn; v += dd * dd; }
+                    o.cn_sd = sqrt(v / n);
+                }
+            }
+            // one-sided normal tail through the reference's own erf variant, t = 1 / (1 + p + x) (src/GROM.c:17163-17172)
+            const double x = fabs(o.z) / sqrt(2.0), t = 1.0 / (1.0 + 0.3275911 + x);
+            const double erf_ = 1.0 - ((0.254829592 * t + -0.284496736 * (t * t) + 1.421413741 * pow(t, 3) + -1.453152027 * pow(t, 4) + 1.061405429 * pow(t, 5)) * exp(-(x * x)));
+            o.pvalue = (1.0 - erf_) / 2.0;
+            c.calls.push_back(o);
+        }
+    }
+    out->n_calls = (int64_t)c.calls.size(); out->calls = c.calls.data();
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const double ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    out->ms_device = (float)ms_dev; out->ms_total = (float)ms_total; out->ms_host = (float)(ms_total - ms_dev);
+    return 0;
+}
+
+__global__ void k_cnv_decode(const uint32_t *__restrict__ rec, const double *__restrict__ sd, int q, int what, int64_t p0, int64_t n, double *__restrict__ oz, uint8_t *__restrict__ ob)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t r = rec[p0 + i];
+    if (what == 0) oz[i] = cnv::rec_z(r, q, sd); else ob[i] = (uint8_t)(r & cnv::R_MASK);
+}
+
+extern "C" int gromgpu_cnv_fetch(gromgpu_chr *h, int what, void *dst, int64_t p0, int64_t p1)
+{
+    if (!h || !h->cnv || !h->cnv->d_rec) return fail("gromgpu_cnv_fetch: call gromgpu_chr_cnv first");
+    if (p0 < 0 || p1 > h->P || p0 > p1) return fail("gromgpu_cnv_fetch: bad range");
+    CnvState &c = *h->cnv;
+    const int64_t n = p1 - p0;
+    if (!n) return 0;
+    if (what == 2) { CK(cudaMemcpy(dst, c.d_mq8 + p0, n, cudaMemcpyDeviceToHost)); return 0; }
+    if (what == 3) { CK(cudaMemcpy(dst, c.d_depth + p0, sizeof(int32_t) * n, cudaMemcpyDeviceToHost)); return 0; }
+    if (what != 0 && what != 1) return fail("gromgpu_cnv_fetch: unknown selector %d", what);
+    cnv::DevTmpRaw o, sd;
+    CK(cudaMalloc(&o.p, what == 0 ? sizeof(double) * n : (size_t)n)); CK(cudaMalloc(&sd.p, sizeof(double) * cnv::P2S));
+    CK(cudaMemcpy(sd.p, c.sd_tbl.data(), sizeof(double) * cnv::P2S, cudaMemcpyHostToDevice));
+    k_cnv_decode<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(c.d_rec, (const double *)sd.p, c.q, what, p0, n, (double *)o.p, (uint8_t *)o.p);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, o.p, what == 0 ? sizeof(double) * n : (size_t)n, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-from .params import DEL_EVENT_DTYPE, GA, GA_COUNT, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE
+from .params import CNV_CALL_DTYPE, DEL_EVENT_DTYPE, GA, GA_COUNT, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE
 from .reads import CReadBatch, ReadBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -59,11 +59,16 @@ def lib() -> C.CDLL:
         L.gromgpu_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64]
         L.gromgpu_debug_fetch_cluster.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int64]
         L.gromgpu_fetch_read_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        L.gromgpu_chr_cnv.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.gromgpu_cnv_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64]
         L.gromgpu_chr_free.argtypes = [C.c_void_p]
         L.gromgpu_chr_free.restype = None
         L.gromgpu_shutdown.restype = None
         _LIB = L
     return _LIB
+
+
+_PARAMS: Optional[Params] = None
 
 
 class GromGpuError(RuntimeError):
@@ -79,6 +84,8 @@ def init(device: int, hez: np.ndarray, mq: np.ndarray, params: Params):
     hez = np.ascontiguousarray(hez, dtype=np.float64); mq = np.ascontiguousarray(mq, dtype=np.float64)
     assert hez.shape == (1001, 1001) and mq.shape == (1001, 1001)
     _ck(lib().gromgpu_init(device, hez.ctypes.data, mq.ctypes.data, C.byref(params)))
+    global _PARAMS
+    _PARAMS = params
 
 
 def set_stream(cuda_stream_ptr: Optional[int]):
@@ -87,6 +94,37 @@ def set_stream(cuda_stream_ptr: Optional[int]):
 
 def shutdown():
     lib().gromgpu_shutdown()
+
+
+class CCnvResult(C.Structure):
+    _fields_ = [("n_calls", C.c_int64), ("calls", C.c_void_p), ("chr_ave", C.c_double), ("chr_sd", C.c_double), ("blk_ave", C.c_double),
+                ("biased_repeat", C.c_int32), ("n_sample_blocks", C.c_int32), ("n_repeats", C.c_int64), ("n_samples", C.c_int64),
+                ("n_frames", C.c_int64), ("win_sd", C.c_void_p), ("win_cnt", C.c_void_p), ("bin_ave", C.c_void_p), ("bin_sd", C.c_void_p),
+                ("bin_del_thr", C.c_void_p), ("bin_dup_thr", C.c_void_p), ("bin_n", C.c_void_p),
+                ("ms_device", C.c_float), ("ms_host", C.c_float), ("ms_total", C.c_float)]
+
+
+@dataclass
+class CnvResult:
+    calls: np.ndarray           # CNV_CALL_DTYPE, deletions then duplications
+    chr_ave: float
+    chr_sd: float
+    blk_ave: float
+    biased_repeat: int
+    n_sample_blocks: int
+    n_repeats: int
+    n_samples: int
+    n_frames: int
+    win_sd: np.ndarray
+    win_cnt: np.ndarray
+    ave: np.ndarray
+    sd: np.ndarray
+    del_thr: np.ndarray
+    dup_thr: np.ndarray
+    n: np.ndarray
+    ms_device: float
+    ms_host: float
+    ms_total: float
 
 
 @dataclass
@@ -177,6 +215,37 @@ class Chromosome:
             _ck(lib().gromgpu_debug_fetch_cluster(self._h, 4, k, mchr[k].ctypes.data, 0, P))
         _ck(lib().gromgpu_debug_fetch_cluster(self._h, 5, 0, ol.ctypes.data, 0, P))
         return w, rs, re, dist, mchr, ol
+
+    def cnv(self, ploidy: Optional[int] = None, params=None) -> "CnvResult":
+        """Read-depth CNV path (gromgpu_chr_cnv) on the depth arrays of the last run()."""
+        from . import hostlib
+        pv, sd = hostlib.pval2sd()
+        r = CCnvResult()
+        params = params if params is not None else _PARAMS
+        pl = ploidy if ploidy is not None else params.ploidy
+        _ck(lib().gromgpu_chr_cnv(self._h, pv.ctypes.data, sd.ctypes.data, len(pv), pl, C.byref(r)))
+        if r.n_calls:
+            buf = (C.c_char * (r.n_calls * CNV_CALL_DTYPE.itemsize)).from_address(r.calls)
+            calls = np.frombuffer(buf, dtype=CNV_CALL_DTYPE, count=r.n_calls).copy()
+        else:
+            calls = np.zeros(0, dtype=CNV_CALL_DTYPE)
+        nw = int(params.max_rd_window_len) + 1
+
+        def arr(ptr, n, dt):
+            return np.frombuffer((C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr), dtype=dt, count=n).copy()
+        return CnvResult(calls=calls, chr_ave=r.chr_ave, chr_sd=r.chr_sd, blk_ave=r.blk_ave, biased_repeat=r.biased_repeat,
+                         n_sample_blocks=r.n_sample_blocks, n_repeats=r.n_repeats, n_samples=r.n_samples, n_frames=r.n_frames,
+                         win_sd=arr(r.win_sd, nw, np.float64), win_cnt=arr(r.win_cnt, nw, np.int64),
+                         ave=arr(r.bin_ave, 202, np.float64).reshape(2, 101), sd=arr(r.bin_sd, 202, np.float64).reshape(2, 101),
+                         del_thr=arr(r.bin_del_thr, 202, np.float64).reshape(2, 101), dup_thr=arr(r.bin_dup_thr, 202, np.float64).reshape(2, 101),
+                         n=arr(r.bin_n, 202, np.int64).reshape(2, 101), ms_device=r.ms_device, ms_host=r.ms_host, ms_total=r.ms_total)
+
+    def cnv_fetch(self, what: str, p0: int = 0, p1: Optional[int] = None) -> np.ndarray:
+        sel, dt = {"z": (0, np.float64), "mask": (1, np.uint8), "mq_mean": (2, np.uint8), "depth": (3, np.int32)}[what]
+        p1 = self.length if p1 is None else p1
+        out = np.empty(p1 - p0, dtype=dt)
+        _ck(lib().gromgpu_cnv_fetch(self._h, sel, out.ctypes.data, p0, p1))
+        return out
 
     def read_state(self, n: int) -> np.ndarray:
         out = np.empty(n, dtype=np.uint8)

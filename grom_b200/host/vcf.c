@@ -142,3 +142,22 @@ int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const 
     free(L);
     return w;
 }
+
+/* read-depth CNV calls: emission filter and text of src/GROM.c:17197-17240, 17280, 17414 */
+int64_t gromhost_vcf_cnv(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                         const grom_cnv_call *calls, int64_t n, char *buf, int64_t cap)
+{
+    int64_t w = 0;
+    (void)fasta; (void)chr_len;
+    for (int kind = 0; kind < 2; kind++)
+        for (int64_t i = 0; i < n; i++) {
+            const grom_cnv_call *c = &calls[i];
+            if (c->kind != kind || !(c->pvalue < p->rd_pval_threshold)) continue;
+            char line[512];
+            int m = snprintf(line, sizeof(line), "%s\t%ld\t.\t.\t<%s>\t.\t.\tEND=%ld\tSD:Z:CN:CS\t%e:%e:%.2f:%e\n", chr_name, (long)c->start + 1,
+                             kind ? "DUP" : "DEL", (long)c->end + 1, c->z, c->pvalue, c->cn, c->cn_sd);
+            if (w + m > cap) return -1;
+            memcpy(buf + w, line, m); w += m;
+        }
+    return w;
+}

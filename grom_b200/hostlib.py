@@ -156,3 +156,9 @@ def vcf_smalldel(params, chr_name: str, fasta: np.ndarray, events: np.ndarray) -
     """Small-deletion records: pairing state machine + filter + text (reference src/GROM.c:11475-11745, 16351-16490)."""
     a = np.ascontiguousarray(events)
     return _vcf("gromhost_vcf_smalldel", params, chr_name, fasta, C.c_int64(len(fasta)), C.c_void_p(a.ctypes.data), C.c_int64(len(a)))
+
+
+def vcf_cnv(params, chr_name: str, calls: np.ndarray) -> str:
+    """Read-depth CNV records (-V filter + text, reference src/GROM.c:17197-17500) from gromgpu_chr_cnv's calls."""
+    a = np.ascontiguousarray(calls)
+    return _vcf("gromhost_vcf_cnv", params, chr_name, np.zeros(1, dtype=np.uint8), C.c_int64(0), C.c_void_p(a.ctypes.data), C.c_int64(len(a)))

@@ -18,7 +18,8 @@ class Params(C.Structure):
         ("high_cov_min_snv_ratio", C.c_double), ("pval_threshold1", C.c_double), ("pval_threshold", C.c_double),
         ("pval_insertion1", C.c_double), ("pval_insertion", C.c_double), ("rd_pval_threshold", C.c_double),
         ("max_evidence_ratio", C.c_double), ("min_sv_ratio", C.c_double), ("min_indel_ratio", C.c_double),
-        ("windows_sampling_factor", C.c_int32), ("reserved0", C.c_int32),
+        ("windows_sampling_factor", C.c_int32), ("rand_seed", C.c_int32), ("min_rd_window_len", C.c_int32),
+        ("max_rd_window_len", C.c_int32), ("sample_lists_len", C.c_int32), ("reserved0", C.c_int32),
     ]
 
     @classmethod
@@ -29,7 +30,8 @@ class Params(C.Structure):
                 max_trials=1000, add_factor=6, min_snv_ratio=0.2, min_ave_bq=15, snv_rd_min_factor=1.75,
                 high_cov_min_snv_ratio=0.4, pval_threshold1=0.01, pval_threshold=0.001, pval_insertion1=0.01,
                 pval_insertion=1e-10, rd_pval_threshold=1e-9, max_evidence_ratio=0.25, min_sv_ratio=0.05,
-                min_indel_ratio=0.125, windows_sampling_factor=2, reserved0=0)
+                min_indel_ratio=0.125, windows_sampling_factor=2, rand_seed=1, min_rd_window_len=100,
+                max_rd_window_len=10000, sample_lists_len=100000, reserved0=0)
         for k, v in kw.items():
             if not hasattr(p, k):
                 raise AttributeError(k)
@@ -74,3 +76,7 @@ assert INS_CAND_DTYPE.itemsize == 104, INS_CAND_DTYPE.itemsize
 DEL_EVENT_DTYPE = np.dtype([("pos", np.int32), ("kind", np.int32), ("pr", np.float64), ("hez", np.float64), ("conc", np.int32),
                             ("weight", np.int32), ("rd", np.int32), ("sc", np.int32), ("other_len", np.int32), ("rdist", np.int32)], align=True)
 assert DEL_EVENT_DTYPE.itemsize == 48, DEL_EVENT_DTYPE.itemsize
+
+CNV_CALL_DTYPE = np.dtype([("start", np.int64), ("end", np.int64), ("kind", np.int32), ("reserved", np.int32), ("z", np.float64),
+                           ("pvalue", np.float64), ("cn", np.float64), ("cn_sd", np.float64)], align=True)
+assert CNV_CALL_DTYPE.itemsize == 56, CNV_CALL_DTYPE.itemsize

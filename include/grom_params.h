@@ -58,6 +58,11 @@ typedef struct grom_params {
     double  min_sv_ratio;       /*     g_min_sv_ratio      0.05 */
     double  min_indel_ratio;    /*     g_min_indel_ratio  0.125 */
     int32_t windows_sampling_factor; /* -A g_windows_sampling_factor 2 */
+    int32_t rand_seed;          /*     srand() argument; the reference uses time() (src/GROM.c:1584), which only matters once a depth
+                                       sample list overflows sample_lists_len */
+    int32_t min_rd_window_len;  /*     g_min_rd_window_len  100 */
+    int32_t max_rd_window_len;  /*     g_max_rd_window_len  10000 */
+    int32_t sample_lists_len;   /*     g_sample_lists_len   100000 */
     int32_t reserved0;
 } grom_params;
 
@@ -81,7 +86,8 @@ static inline void grom_params_default(grom_params *p)
     p->min_snv_ratio = 0.2; p->min_ave_bq = 15; p->snv_rd_min_factor = 1.75; p->high_cov_min_snv_ratio = 0.4;
     p->pval_threshold1 = 0.01; p->pval_threshold = 0.001; p->pval_insertion1 = 0.01; p->pval_insertion = 1e-10;
     p->rd_pval_threshold = 1e-9; p->max_evidence_ratio = 0.25; p->min_sv_ratio = 0.05; p->min_indel_ratio = 0.125;
-    p->windows_sampling_factor = 2; p->reserved0 = 0;
+    p->windows_sampling_factor = 2; p->rand_seed = 1; p->min_rd_window_len = 100; p->max_rd_window_len = 10000;
+    p->sample_lists_len = 100000; p->reserved0 = 0;
 }
 
 /* ---- canonical per-position int32 arrays (one value per reference position) ----
@@ -151,6 +157,17 @@ typedef struct grom_del_event {
     int32_t other_len;
     int32_t rdist;              /* indel_d_rdist (end events) */
 } grom_del_event;
+
+/* one read-depth CNV call of detect_del_dup (src/GROM.c:19654-19658 / 19988-19992) with its copy number (20071-20224) and the
+ * reference's p-value (17163-17190) */
+typedef struct grom_cnv_call {
+    int64_t start, end;         /* 0-based, as stored by the reference (printed +1) */
+    int32_t kind;               /* 0 = deletion, 1 = duplication */
+    int32_t reserved;
+    double  z;                  /* largest window score in units of the window-length-specific sd */
+    double  pvalue;
+    double  cn, cn_sd;          /* trimmed-mean copy number and its spread; -1 / 0 when no usable base */
+} grom_cnv_call;
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,30 @@ int gromgpu_debug_fetch_cluster(gromgpu_chr *h, int what, int cls, void *dst, in
 /* read_state per read [i0, i1): 0 = not applied (before W/4+1, UNMAP/DUP flag), 1 = applied, 2 = -M duplicate */
 int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0, int64_t i1);
 
+/* ---- read-depth CNV path: replaces the pre-statistics at src/GROM.c:16633-16990 and the call
+ *   detect_del_dup(chr, begin, len, gc_weighted, acgt_weighted, rd_mq, rd_rd, rd_low_mq_rd, sample lists ..., pval2sd_pval, pval2sd_sd,
+ *                  pval2sd_len, &del_index, del lists ..., &dup_index, dup lists ..., ploidy, repeat lists ..., file, chr_name)
+ * at src/GROM.c:17133 plus the p-values of 17163-17190.  Call after gromgpu_chr_run (it consumes the CNV depth arrays of that
+ * run, which stay untouched).  pval2sd_* are the caller's tables exactly as the reference passes them (gromhost_pval2sd()).
+ * ploidy is the reference's caf_ploidy. */
+typedef struct gromgpu_cnv_result {
+    int64_t n_calls;                    /* deletions in position order, then duplications */
+    const grom_cnv_call *calls;         /* host memory owned by the handle; filter with -V and print via gromhost_vcf_cnv() */
+    double  chr_ave, chr_sd;            /* contig depth mean / clamped sd over positions with >= 99 % ACGT context */
+    double  blk_ave;                    /* mean depth over A/C/G/T reference bases (10 kb block threshold = 2 x) */
+    int32_t biased_repeat;              /* g_most_biased_repeat, -1 = none */
+    int32_t n_sample_blocks;
+    int64_t n_repeats, n_samples, n_frames;
+    const double  *win_sd;              /* [max_rd_window_len + 1] null-distribution sd per window length */
+    const int64_t *win_cnt;             /* [max_rd_window_len + 1] observations per window length */
+    const double  *bin_ave, *bin_sd, *bin_del_thr, *bin_dup_thr;   /* [2][101]: high-MAPQ list, low-MAPQ list per GC bin */
+    const int64_t *bin_n;               /* [2][101] */
+    float   ms_device, ms_host, ms_total;
+} gromgpu_cnv_result;
+int gromgpu_chr_cnv(gromgpu_chr *h, const double *pval2sd_pval, const double *pval2sd_sd, int pval2sd_len, int ploidy, gromgpu_cnv_result *out);
+/* Parity access after gromgpu_chr_cnv: what = 0 z list (double), 1 mask (uint8), 2 mean MAPQ (uint8), 3 depth (int32); positions [p0, p1) */
+int gromgpu_cnv_fetch(gromgpu_chr *h, int what, void *dst, int64_t p0, int64_t p1);
+
 void gromgpu_chr_free(gromgpu_chr *h);
 
 #ifdef __cplusplus

@@ -74,6 +74,10 @@ int64_t gromhost_vcf_ins(const grom_params *p, const char *chr_name, const char 
                          const grom_ins_cand *ins, int64_t n, char *buf, int64_t cap);
 int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
                               const grom_del_event *ev, int64_t n, char *buf, int64_t cap);
+/* read-depth CNV records: -V filter (p-value < rd_pval_threshold) and text, deletions then duplications (src/GROM.c:17197-17500).
+ * fasta / chr_len are unused (kept for a uniform signature). */
+int64_t gromhost_vcf_cnv(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                         const grom_cnv_call *calls, int64_t n, char *buf, int64_t cap);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,96 @@
+"""Read-depth CNV path on the GPU (gromgpu_chr_cnv) against the CPU oracle (oracle/grom_oracle_cnv.c, pinned against the
+reference's own dumps): pre-statistics, per-bin distributions, mask and z list, window-length sd table, calls, copy number,
+p-values and the VCF text of the host writer.  Doubles are compared bit for bit unless noted."""
+import numpy as np
+import pytest
+
+from util import tables_7digit
+from grom_b200 import gpu, hostlib
+from grom_b200.params import Params
+from oracle import pyoracle as po
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dataset(seed, length, depth, cnv_per_mb, **kw):
+    spec = synth.SynthSpec(contigs=[("chrA", length)], depth=depth, seed=seed, cnv_per_mb=cnv_per_mb, disc_frac=0.005, sv_sites_per_mb=1.0,
+                           low_mapq_frac=0.05, **kw)
+    return synth.simulate(spec)[0]
+
+
+def _run_both(prm, c, ploidy=None):
+    hez, mq = tables_7digit()
+    gpu.init(0, hez, mq, prm)
+    ref = po.run_chr(prm, c.batch, c.chars, hez, mq)
+    gc, acgt = ref["gc"], ref["acgt"]
+    o = po.cnv_run(prm, "chra", c.chars, gc, acgt, ref["rd_mq"], ref["rd_rd"], ref["rd_low"], ploidy=ploidy, seed=prm.rand_seed,
+                   sample_cap=prm.sample_lists_len, min_win=prm.min_rd_window_len, max_win=prm.max_rd_window_len)
+    with gpu.Chromosome(0, c.chars) as ch:
+        ch.push_reads(c.batch)
+        ch.run()
+        g = ch.cnv(ploidy=ploidy)
+        z, mask, mqm = ch.cnv_fetch("z"), ch.cnv_fetch("mask"), ch.cnv_fetch("mq_mean")
+        # the CNV stage must leave the depth arrays of the run untouched
+        assert np.array_equal(ch.fetch("rd_mq"), ref["rd_mq"])
+    return o, g, z, mask, mqm
+
+
+def _check(o, g, z, mask, mqm, prm):
+    assert g.chr_ave == o.chr_ave and g.blk_ave == o.blk_ave and g.biased_repeat == o.biased
+    assert abs(g.chr_sd - o.chr_sd) <= 1e-9 * max(1.0, abs(o.chr_sd))       # summed per depth value, not per position
+    assert g.n_repeats == len(o.repeats) and g.n_sample_blocks == len(o.sample_blocks)
+    assert np.array_equal(g.n, o.windows)
+    for a, b, nm in ((g.ave, o.ave, "ave"), (g.sd, o.sd, "sd"), (g.del_thr, o.del_thr, "del_thr"), (g.dup_thr, o.dup_thr, "dup_thr")):
+        assert np.array_equal(a, b), nm
+    assert np.array_equal(mqm, np.minimum(o.mq_mean, 255).astype(np.uint8))
+    assert np.array_equal(mask, o.mask), f"mask differs at {np.nonzero(mask != o.mask)[0][:5]}"
+    assert np.array_equal(z, o.z), f"z differs at {np.nonzero(z != o.z)[0][:5]}"
+    assert np.array_equal(g.win_cnt, o.win_cnt)
+    assert np.array_equal(g.win_sd, o.win_sd)
+    dels, dups = g.calls[g.calls["kind"] == 0], g.calls[g.calls["kind"] == 1]
+    for mine, ref in ((dels, o.dels), (dups, o.dups)):
+        assert np.array_equal(mine["start"], ref["start"]) and np.array_equal(mine["end"], ref["end"])
+        for f, rf in (("z", "z"), ("cn", "cn"), ("cn_sd", "cs"), ("pvalue", "p")):
+            assert np.array_equal(mine[f], ref[rf]), f
+    assert hostlib.vcf_cnv(prm, "chra", g.calls) == o.vcf
+
+
+def test_cnv_matches_oracle_default():
+    c = _dataset(seed=5, length=3_000_000, depth=30, cnv_per_mb=0.7)
+    prm = Params.default()
+    o, g, z, mask, mqm = _run_both(prm, c)
+    assert len(o.dels) > 0 and len(o.dups) > 0 and (mask == 0).sum() > 1_000_000
+    assert "<DEL>" in o.vcf                     # at least one planted loss survives the -V filter
+    _check(o, g, z, mask, mqm, prm)
+
+
+def test_cnv_matches_oracle_tetraploid_A4():
+    c = _dataset(seed=8, length=900_000, depth=40, cnv_per_mb=2.3)
+    prm = Params.default(ploidy=4, windows_sampling_factor=4)
+    o, g, z, mask, mqm = _run_both(prm, c)
+    _check(o, g, z, mask, mqm, prm)
+
+
+def test_cnv_reservoir_and_small_windows():
+    """A small list capacity forces the libc-rand reservoir path (src/GROM.c:18391-18398); short windows exercise the frame logic."""
+    c = _dataset(seed=9, length=700_000, depth=15, cnv_per_mb=3.0)
+    prm = Params.default(sample_lists_len=150, rand_seed=7, min_rd_window_len=50, max_rd_window_len=3000, windows_sampling_factor=3)
+    o, g, z, mask, mqm = _run_both(prm, c)
+    assert int(o.windows.max()) == 150
+    _check(o, g, z, mask, mqm, prm)
+
+
+def test_cnv_short_contig_is_empty():
+    """A contig shorter than the GC window has no analysed span (lo >= hi): no calls, no error."""
+    rng = np.random.default_rng(3)
+    chars = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, 1000)].copy()
+    batch = synth.batch_from_records(0, [dict(pos=100 + 50 * i, cigar=[(0, 100)], seq="A" * 100, qual=30, flag=0, mapq=60) for i in range(5)])
+    prm = Params.default()
+    hez, mq = tables_7digit()
+    gpu.init(0, hez, mq, prm)
+    with gpu.Chromosome(0, chars) as ch:
+        ch.push_reads(batch)
+        ch.run()
+        g = ch.cnv()
+    assert len(g.calls) == 0 and g.n_samples == 0
