@@ -315,62 +315,271 @@ __global__ void __launch_bounds__(256) k_z(const int32_t *__restrict__ depth, co
 }
 
 // ---- K7: window-length sweep (src/GROM.c:18967-19018).  The walk over a sample block, repeated at each -A offset without resetting
-// the running frame, is cut into frames of Lmax elements; one thread owns one frame and accumulates in the reference's order.
+// the running frame, is cut into frames of Lmax elements.  One warp owns one frame: 32 elements are fetched and decoded in parallel,
+// then folded into the running sum one by one in element order (the reference's summation order), so every prefix mean is bit-exact.
 struct SweepBlock { int64_t start, end; int64_t first_frame, n_frames; };
-__global__ void __launch_bounds__(64) k_sweep(const uint32_t *__restrict__ rec, const SweepBlock *__restrict__ blocks, int n_blocks, int64_t n_frames,
-                                              int A, int Lmin, int Lmax, int q, const double *__restrict__ p2s_sd, double *__restrict__ X)
+__device__ __forceinline__ void sweep_advance(int &a, int64_t &p, int64_t n, int64_t s, int64_t e, int A, int Lmax)
+{
+    // move n elements along the concatenated walk; a == A means the walk is over
+    while (a < A) {
+        const int64_t rem = max((int64_t)0, e - p);
+        if (n < rem) { p += n; return; }
+        n -= rem; a++; p = s + (int64_t)a * Lmax / A;
+    }
+}
+__global__ void __launch_bounds__(256) k_sweep(const uint32_t *__restrict__ rec, const SweepBlock *__restrict__ blocks, int n_blocks, int64_t n_frames,
+                                               int A, int Lmin, int Lmax, int q, const double *__restrict__ p2s_sd, double *__restrict__ X)
 {
     __shared__ double sd[P2S];
     for (int i = threadIdx.x; i < P2S; i += blockDim.x) sd[i] = p2s_sd[i];
     __syncthreads();
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (f >= n_frames) return;
     int b = 0;
     while (b + 1 < n_blocks && blocks[b + 1].first_frame <= f) b++;
     const int64_t s = blocks[b].start, e = blocks[b].end;
-    int64_t c = (f - blocks[b].first_frame) * (int64_t)Lmax;      // index of the frame's first element in the concatenated walk
+    const int n_len = Lmax - Lmin + 1;
     int a = 0;
     int64_t p = s;
-    for (; a < A; a++) {                                          // locate (offset pass, position) of element c
-        const int64_t adj = (int64_t)a * Lmax / A, len = max((int64_t)0, e - (s + adj));
-        if (c < len) { p = s + adj + c; break; }
-        c -= len;
-    }
+    sweep_advance(a, p, (f - blocks[b].first_frame) * (int64_t)Lmax, s, e, A, Lmax);
     double tot = 0.0;
     long long n_us = 0;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int w = 1; w <= Lmax; w++) {
-        while (a < A && p >= e) { a++; p = s + (int64_t)a * Lmax / A; }
-        if (a >= A) {                                             // the walk ended inside this frame: no more observations
-            for (int ww = max(w, Lmin); ww <= Lmax; ww++) X[(int64_t)(ww - Lmin) * n_frames + f] = nan;
-            return;
+    double *row = X + f * (int64_t)n_len;
+    for (int w0 = 0; w0 < Lmax; w0 += 32) {
+        int la = a; int64_t lp = p;
+        sweep_advance(la, lp, lane, s, e, A, Lmax);
+        const bool valid = la < A && w0 + lane < Lmax;
+        const uint32_t r = valid ? rec[lp] : R_MASK;
+        const bool us = valid && rec_usable(r);
+        const double z = us ? rec_z(r, q, sd) : 0.0;
+        const unsigned um = __ballot_sync(0xffffffffu, us);
+        double mine = tot;
+        if (um) {
+            for (int i = 0; i < 32; i++) {
+                const double zi = __shfl_sync(0xffffffffu, z, i);
+                if ((um >> i) & 1) tot = __dadd_rn(tot, zi);
+                if (lane == i) mine = tot;
+            }
         }
-        const uint32_t r = rec[p];
-        if (rec_usable(r)) { tot = __dadd_rn(tot, rec_z(r, q, sd)); n_us++; }
-        p++;
-        if (w >= Lmin) {
+        const long long n_mine = n_us + __popc(um & (0xffffffffu >> (31 - lane)));
+        n_us += __popc(um);
+        const int w = w0 + lane + 1;
+        if (w >= Lmin && w <= Lmax) {
             double x2 = nan;
-            if (n_us > 0) { const double x = tot / (double)n_us; x2 = __dmul_rn(x, x); }
-            X[(int64_t)(w - Lmin) * n_frames + f] = x2;
+            if (valid && n_mine > 0) { const double x = mine / (double)n_mine; x2 = __dmul_rn(x, x); }
+            row[w - Lmin] = x2;
         }
+        sweep_advance(a, p, 32, s, e, A, Lmax);
     }
 }
-// ordered sum over the frames: one warp per window length, lanes fetch 32 frames at a time, every lane adds them in frame order
+// ordered sum over the frames: one thread per window length walks the frames in order (loads batched ahead of the dependent adds)
 __global__ void __launch_bounds__(128) k_sweep_sum(const double *__restrict__ X, int64_t n_frames, int n_len, double *__restrict__ wsq, long long *__restrict__ wcnt)
 {
-    const int L = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int L = blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= n_len) return;
-    const double *row = X + (int64_t)L * n_frames;
     double sum = 0.0;
     long long cnt = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += 32) {
-        const double v = f0 + lane < n_frames ? row[f0 + lane] : __longlong_as_double(0x7ff8000000000000LL);
-        for (int i = 0; i < 32; i++) {
-            const double x = __shfl_sync(0xffffffffu, v, i);
-            if (x == x) { sum = __dadd_rn(sum, x); cnt++; }
+    for (int64_t f0 = 0; f0 < n_frames; f0 += 8) {
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = f0 + i < n_frames ? X[(f0 + i) * (int64_t)n_len + L] : __longlong_as_double(0x7ff8000000000000LL);
+#pragma unroll
+        for (int i = 0; i < 8; i++) if (v[i] == v[i]) { sum = __dadd_rn(sum, v[i]); cnt++; }
+    }
+    wsq[L] = sum; wcnt[L] = cnt;
+}
+
+// ---- greedy segmentation (src/GROM.c:19361-19678 deletions, 19702-20010 duplications) --------------------------------------------
+// What happens at one seed -- a position whose depth is beyond the threshold -- depends only on the seed and, for an uncovered
+// seed, on the carried MAPQ class: walk Lmin positions and give up as soon as fewer than half are beyond the threshold; otherwise
+// grow the window to Lmax scoring every length, slide it, trim the end.  eval_seed() is that function, shared by the device (every
+// seed evaluated speculatively in parallel, bounded to SEED_BOUND positions) and the host (the sequential hop from seed to seed,
+// plus the few evaluations the device left unresolved).
+struct SegCtx {
+    const uint32_t *rec; int64_t len, end; int q, Lmin, Lmax, bound; const double *sd, *win_sd; bool dup;
+    __host__ __device__ inline int cls(int64_t p) const { return (rec[p] >> R_CLASS) & 3; }
+    __host__ __device__ inline bool beyond(int64_t p, int mi) const { return (rec[p] & (dup ? (mi ? R_DUP1 : R_DUP0) : (mi ? R_DEL1 : R_DEL0))) != 0; }
+    __host__ __device__ inline bool win_gt1(int64_t p, int mi) const { return (rec[p] & (mi ? R_WIN1 : R_WIN0)) != 0; }
+    __host__ __device__ inline double z(int64_t p) const { const double v = rec_z(rec[p], q, sd); return dup ? -v : v; }
+};
+enum { SEG_RESUME = 0, SEG_CALL = 1, SEG_UNRESOLVED = 2 };
+struct Outcome { int kind; int64_t next, c_end; double c_z; };
+constexpr int SEED_BOUND = 1024, SEED_BOUND2 = 8192;   // first round for every seed; second round for the unresolved ones when they are few
+
+template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCtx &C, const int64_t pos, int mi)
+{
+#define CNV_STEP(var, p) do { const int c_ = C.cls(p); if (c_ != 2) var = c_; } while (0)
+    const int64_t Lmin = C.Lmin, Lmax = C.Lmax, end = C.end, max_gap = Lmax + 500;
+    Outcome o; o.kind = SEG_RESUME; o.next = pos + 1; o.c_end = 0; o.c_z = 0;
+    bool stop = false, begun = false;
+    int64_t wlen = 0, cnt = 0, cnt2 = 0, pa, c_start = 0, c_end = 0, last_good = 0;
+    double tot = 0, c_z = 0, tz;
+    for (pa = pos; pa < pos + Lmin; pa++) {
+        wlen++;
+        bool ok = false;
+        if (!(C.rec[pa] & R_MASK)) { CNV_STEP(mi, pa); ok = C.beyond(pa, mi); }
+        if (ok) cnt2++;
+        else if (2 * cnt2 < wlen) { o.next = pa + 1; return o; }            // give up inside the first window: resume after the offender
+    }
+    cnt = Lmin;
+    for (int64_t a = pos; a < pos + Lmin; a++) { cnt -= C.rec[a] & R_MASK; tot += C.z(a); }
+    if (cnt > 0 && tot > 0 && C.win_sd[Lmin] > 0 && tot / (cnt * C.win_sd[Lmin]) >= 3) {   // tot <= 0 cannot score (exact)
+        begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tot / (cnt * C.win_sd[Lmin]);
+    }
+    for (pa = pos + Lmin; pa < pos + Lmax; pa++) {
+        wlen++;
+        if (BOUNDED && wlen > C.bound) { o.kind = SEG_UNRESOLVED; return o; }
+        if (pa >= end) { stop = true; break; }
+        bool ok = false;
+        if (!(C.rec[pa] & R_MASK)) {
+            CNV_STEP(mi, pa);
+            tot += C.z(pa); cnt++;
+            ok = C.beyond(pa, mi);
+            if (ok) {
+                cnt2++;
+                if (tot > 0 && C.win_sd[wlen] > 0 && tot / (cnt * C.win_sd[wlen]) >= 3) {
+                    last_good = pa; tz = tot / (cnt * C.win_sd[wlen]);
+                    if (!begun) { begun = true; c_start = pos; c_end = pa; c_z = tz; }
+                    else { c_end = pa; if (tz > c_z) c_z = tz; }
+                }
+            }
+        }
+        if (!ok && 2 * cnt2 < wlen) { stop = true; break; }
+    }
+    if (!stop && begun) {
+        if (BOUNDED) { o.kind = SEG_UNRESOLVED; return o; }
+        int mi_b = mi;
+        pa = pos + Lmax; tot = 0; cnt = 0;
+        while (pa < C.len && pa - last_good <= max_gap) {
+            if (pa == pos + Lmax) {
+                for (int64_t pb = pa - Lmax + 1; pb < pa + 1; pb++) {
+                    CNV_STEP(mi_b, pb);
+                    if (!(C.rec[pb] & R_MASK) && C.win_gt1(pb, mi_b)) { tot += C.z(pb); cnt++; }
+                }
+            } else {
+                const int64_t pb = pa - Lmax;
+                CNV_STEP(mi_b, pb);
+                if (!(C.rec[pb] & R_MASK) && C.win_gt1(pb, mi_b)) { tot -= C.z(pb); cnt--; }
+                CNV_STEP(mi, pa);
+                if (!(C.rec[pa] & R_MASK) && C.win_gt1(pa, mi)) { tot += C.z(pa); cnt++; }
+            }
+            if (cnt > 0 && tot > 0 && C.win_sd[Lmax] > 0 && tot / (cnt * C.win_sd[Lmax]) >= 3) {
+                last_good = pa; c_end = pa; tz = tot / (cnt * C.win_sd[Lmax]);
+                if (tz > c_z) c_z = tz;
+            }
+            pa++;
         }
     }
-    if (lane == 0) { wsq[L] = sum; wcnt[L] = cnt; }
+    if (!begun) return o;                                                  // gave up while growing (or never scored): resume at seed + 1
+    int64_t t = c_end;                                                     // trim the end back to a stretch that is still mostly beyond
+    while (t > c_start + Lmin) {
+        CNV_STEP(mi, t);
+        if (!C.beyond(t, mi)) { t--; c_end = t; }
+        else {
+            int64_t c2 = 0, c3 = 0;
+            bool halt = false;
+            int mi_a = mi;
+            pa = c_end;
+            while (pa > c_start + Lmin && !halt) {
+                if (!(C.rec[pa] & R_MASK)) { CNV_STEP(mi_a, pa); c3++; if (C.beyond(pa, mi_a)) c2++; }
+                if (c3 == 0 || c2 / (double)c3 < 0.5) { c_end = pa - 1; halt = true; }
+                pa--;
+            }
+            t = pa;
+        }
+    }
+    o.kind = SEG_CALL; o.c_end = c_end; o.c_z = c_z; o.next = c_end + 2;
+    return o;
+#undef CNV_STEP
+}
+
+// land[2*rank + class] (uint32): 0xFFFFFFFF not a seed under that class; top bits SEG_*; RESUME: low bits = distance to the next
+// position; CALL: low bits = index into the speculative call list
+constexpr uint32_t LAND_NOT = 0xFFFFFFFFu;
+constexpr int LAND_SHIFT = 29;
+struct SeedCall { int64_t c_end; double c_z; };
+constexpr int SEED_WORDS = 1024;            // seed-bitmap words per CTA
+__global__ void __launch_bounds__(256) k_seed_blocksum(const uint32_t *__restrict__ seeds, int64_t words, uint32_t *__restrict__ blk, int nb)
+{
+    __shared__ uint32_t red[8];
+    const uint32_t *sd = seeds + (int64_t)blockIdx.y * words;
+    uint32_t n = 0;
+    for (int j = 0; j < 4; j++) { const int64_t w = (int64_t)blockIdx.x * SEED_WORDS + threadIdx.x * 4 + j; if (w < words) n += __popc(sd[w]); }
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int i = 0; i < 8; i++) t += red[i]; blk[blockIdx.y * nb + blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_seed_blockscan(uint32_t *__restrict__ blk, int nb, uint32_t *__restrict__ totals)
+{
+    __shared__ uint32_t part[1024];
+    uint32_t *b = blk + blockIdx.x * nb;
+    const int per = (nb + 1023) / 1024, i0 = threadIdx.x * per, i1 = min(i0 + per, nb);
+    uint32_t t = 0;
+    for (int i = i0; i < i1; i++) t += b[i];
+    part[threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 1024; i++) { const uint32_t v = part[i]; part[i] = run; run += v; } totals[blockIdx.x] = run; }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (int i = i0; i < i1; i++) { const uint32_t v = b[i]; b[i] = run; run += v; }
+}
+// per-word seed ranks (exclusive prefix of the bitmap popcounts), one CTA per SEED_WORDS words
+__global__ void __launch_bounds__(256) k_seed_rank(const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ blk, int nb, uint32_t *__restrict__ wp)
+{
+    __shared__ uint32_t part[256];
+    const int kind = blockIdx.y;
+    const uint32_t *sd = seeds + (int64_t)kind * words;
+    uint32_t bits[4], n = 0;
+    const int64_t w0 = (int64_t)blockIdx.x * SEED_WORDS + threadIdx.x * 4;
+    for (int j = 0; j < 4; j++) { bits[j] = w0 + j < words ? sd[w0 + j] : 0u; n += __popc(bits[j]); }
+    part[threadIdx.x] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t run = blk[kind * nb + blockIdx.x]; for (int i = 0; i < 256; i++) { const uint32_t v = part[i]; part[i] = run; run += v; } }
+    __syncthreads();
+    uint32_t rank = part[threadIdx.x];
+    for (int j = 0; j < 4; j++) { if (w0 + j < words) wp[(int64_t)kind * words + w0 + j] = rank; rank += __popc(bits[j]); }
+}
+// one thread per reference position: evaluate the seed (both carried classes when it is uncovered)
+__global__ void __launch_bounds__(128) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+                                                   uint32_t *__restrict__ land, uint32_t cap, int64_t lo, SeedCall *__restrict__ calls, uint32_t call_cap,
+                                                   unsigned int *__restrict__ n_calls, int second_round)
+{
+    const int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= Cdel.end) return;
+    for (int kind = 0; kind < 2; kind++) {
+        const uint32_t word = seeds[(int64_t)kind * words + (p >> 5)];
+        if (!((word >> (p & 31)) & 1)) continue;
+        const uint32_t rank = wp[(int64_t)kind * words + (p >> 5)] + __popc(word & ((1u << (p & 31)) - 1u));
+        if (rank >= cap) continue;
+        const SegCtx &C = kind ? Cdup : Cdel;
+        const int c0 = C.cls(p);
+        uint32_t res[2] = {LAND_NOT, LAND_NOT};
+        const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
+        if (second_round) {
+            res[0] = land[((int64_t)kind * cap + rank) * 2]; res[1] = land[((int64_t)kind * cap + rank) * 2 + 1];
+            if (res[0] != unres && res[1] != unres) continue;
+        }
+        for (int v = 0; v < 2; v++) {
+            if (c0 != 2 && v == 1) { res[1] = res[0]; break; }
+            const int mi = c0 == 2 ? v : c0;
+            if (second_round && res[v] != unres) continue;
+            if (!C.beyond(p, mi)) continue;
+            const Outcome o = eval_seed<true>(C, p, mi);
+            uint32_t e;
+            if (o.kind == SEG_RESUME) e = (uint32_t)(o.next - p);
+            else if (o.kind == SEG_CALL) {
+                const unsigned int k = atomicAdd(n_calls, 1u);
+                if (k < call_cap) { calls[k].c_end = o.c_end; calls[k].c_z = o.c_z; e = ((uint32_t)SEG_CALL << LAND_SHIFT) | k; }
+                else e = unres;
+            } else e = unres;
+            if (e == unres) atomicAdd(n_calls + 1, 1u);
+            res[v] = e;
+        }
+        land[((int64_t)kind * cap + rank) * 2] = res[0]; land[((int64_t)kind * cap + rank) * 2 + 1] = res[1];
+    }
 }
 
 // ---- K8: depth and GC bin of the called segments, packed back to back (copy-number step, src/GROM.c:20071-20224)
@@ -420,6 +629,11 @@ struct SampleList {
 
 struct Call { int64_t start, end; double z; };
 struct DevTmpRaw { void *p = nullptr; ~DevTmpRaw() { if (p) cudaFree(p); } };
+struct Grow {                  // grow-only device buffer kept across calls
+    void *p = nullptr; size_t cap = 0;
+    bool ensure(size_t n) { if (n <= cap) return true; if (p) cudaFree(p); p = nullptr; cap = n + n / 4 + 256; return cudaMalloc(&p, cap) == cudaSuccess; }
+    template <class T> T *as() { return (T *)p; }
+};
 
 // the reference's qsort on the copy-number ratios: glibc merge sort with the comparator `*(int*)a - *(int*)b`, i.e. ordered by the
 // low word of each double with wrapping subtraction (src/GROM.c:1105, 20113)
@@ -437,13 +651,11 @@ inline void lowword_msort(double *b, size_t n, double *tmp)
     memcpy(b, tmp, k * sizeof(double));
 }
 
-// greedy segmentation over the packed records (src/GROM.c:19361-19678 deletions, 19702-20010 duplications)
+// the sequential part that is left: hop from seed to seed (src/GROM.c:19370-19389, 19670-19676)
 struct Segmenter {
-    const uint32_t *rec; const uint32_t *seeds; int64_t len, lo, hi; int q; long Lmin, Lmax; const double *sd; const double *win_sd; bool dup;
-    inline int cls(int64_t p) const { return (rec[p] >> R_CLASS) & 3; }
-    inline bool beyond(int64_t p, int mi) const { return rec[p] & (dup ? (mi ? R_DUP1 : R_DUP0) : (mi ? R_DEL1 : R_DEL0)); }
-    inline bool win_gt1(int64_t p, int mi) const { return rec[p] & (mi ? R_WIN1 : R_WIN0); }
-    inline double z(int64_t p) const { const double v = rec_z(rec[p], q, sd); return dup ? -v : v; }
+    SegCtx C; const uint32_t *seeds; int64_t lo;
+    const uint32_t *wp = nullptr, *land = nullptr; const SeedCall *spec = nullptr;     // optional device-evaluated seeds (k_seed_eval)
+    long n_table = 0, n_host = 0, host_span = 0;
     inline int64_t next_seed(int64_t p, int64_t end) const
     {
         if (p >= end) return end;
@@ -454,100 +666,32 @@ struct Segmenter {
         const int64_t r = (w << 5) + __builtin_ctz(bits);
         return r < end ? r : end;
     }
-    void run(std::vector<Call> &out) const
+    void run(std::vector<Call> &out)
     {
-        const int64_t end = hi - Lmin, max_gap = Lmax + 500;
-        int mi = 0, last_low = 0, mi_a = 0, mi_b = 0;
+        const int64_t end = C.end;
+        int mi = 0, last_low = 0;
         int64_t pos = lo;
-#define CNV_STEP(var, p) do { const int c_ = cls(p); if (c_ != 2) var = c_; } while (0)
         while (pos < end) {
-            // positions between seeds only move last_low: it is the class of the last covered position passed by the outer loop
+            // positions between seeds only move last_low: it is the class of the last covered position the outer loop passed
             const int64_t nx = next_seed(pos, end);
-            for (int64_t b = nx - 1; b >= pos; b--) { const int c = cls(b); if (c != 2) { last_low = c; break; } }
+            for (int64_t b = nx - 1; b >= pos; b--) { const int c = C.cls(b); if (c != 2) { last_low = c; break; } }
             pos = nx;
             if (pos >= end) break;
-            const int c0 = cls(pos);
+            const int c0 = C.cls(pos);
             if (c0 != 2) { mi = c0; last_low = c0; } else mi = last_low;
-            if (!beyond(pos, mi)) { pos++; continue; }
-            bool stop = false, begun = false;
-            int64_t tpos = pos, wlen = 0, cnt = 0, cnt2 = 0, pa, c_start = 0, c_end = 0, last_good = 0;
-            double tot = 0, c_z = 0, tz;
-            for (pa = pos; pa < pos + Lmin; pa++) {
-                wlen++;
-                if (!(rec[pa] & R_MASK)) {
-                    CNV_STEP(mi, pa);
-                    if (beyond(pa, mi)) cnt2++;
-                    else if (2 * cnt2 < wlen) { stop = true; tpos = pa; break; }
-                } else if (2 * cnt2 < wlen) { stop = true; tpos = pa; break; }
+            if (land) {
+                const uint32_t v = land[2 * ((int64_t)wp[pos >> 5] + __builtin_popcount(seeds[pos >> 5] & ((1u << (pos & 31)) - 1u))) + mi];
+                const uint32_t kind = v >> LAND_SHIFT, low = v & ((1u << LAND_SHIFT) - 1u);
+                if (v == LAND_NOT) { pos++; continue; }
+                if (kind == SEG_RESUME) { pos += low; n_table++; continue; }
+                if (kind == SEG_CALL) { out.push_back({pos, spec[low].c_end, spec[low].c_z}); pos = spec[low].c_end + 2; n_table++; continue; }
             }
-            if (!stop) {
-                cnt = Lmin;
-                for (int64_t a = pos; a < pos + Lmin; a++) { cnt -= rec[a] & R_MASK; tot += z(a); }
-                if (cnt > 0 && win_sd[Lmin] > 0 && tot / (cnt * win_sd[Lmin]) >= 3) {
-                    begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tot / (cnt * win_sd[Lmin]);
-                }
-                for (pa = pos + Lmin; pa < pos + Lmax; pa++) {
-                    wlen++;
-                    if (pa >= end) { stop = true; break; }
-                    if (!(rec[pa] & R_MASK)) {
-                        CNV_STEP(mi, pa);
-                        tot += z(pa); cnt++;
-                        if (beyond(pa, mi)) {
-                            cnt2++;
-                            if (win_sd[wlen] > 0 && tot / (cnt * win_sd[wlen]) >= 3) {
-                                last_good = pa; tz = tot / (cnt * win_sd[wlen]);
-                                if (!begun) { begun = true; c_start = pos; c_end = pa; c_z = tz; }
-                                else { c_end = pa; if (tz > c_z) c_z = tz; }
-                            }
-                        } else if (2 * cnt2 < wlen) { stop = true; break; }
-                    } else if (2 * cnt2 < wlen) { stop = true; break; }
-                }
-            }
-            if (!stop && begun) {
-                pa = pos + Lmax; tot = 0; cnt = 0; mi_b = mi;
-                while (pa < len && pa - last_good <= max_gap) {
-                    if (pa == pos + Lmax) {
-                        for (int64_t pb = pa - Lmax + 1; pb < pa + 1; pb++) {
-                            CNV_STEP(mi_b, pb);
-                            if (!(rec[pb] & R_MASK) && win_gt1(pb, mi_b)) { tot += z(pb); cnt++; }
-                        }
-                    } else {
-                        const int64_t pb = pa - Lmax;
-                        CNV_STEP(mi_b, pb);
-                        if (!(rec[pb] & R_MASK) && win_gt1(pb, mi_b)) { tot -= z(pb); cnt--; }
-                        CNV_STEP(mi, pa);
-                        if (!(rec[pa] & R_MASK) && win_gt1(pa, mi)) { tot += z(pa); cnt++; }
-                    }
-                    if (cnt > 0 && win_sd[Lmax] > 0 && tot / (cnt * win_sd[Lmax]) >= 3) {
-                        last_good = pa; c_end = pa; tz = tot / (cnt * win_sd[Lmax]);
-                        if (tz > c_z) c_z = tz;
-                    }
-                    pa++;
-                }
-            }
-            if (begun) {
-                int64_t t = c_end;
-                while (t > c_start + Lmin) {
-                    CNV_STEP(mi, t);
-                    if (!beyond(t, mi)) { t--; c_end = t; }
-                    else {
-                        int64_t c2 = 0, c3 = 0;
-                        bool halt = false;
-                        pa = c_end; mi_a = mi;
-                        while (pa > c_start + Lmin && !halt) {
-                            if (!(rec[pa] & R_MASK)) { CNV_STEP(mi_a, pa); c3++; if (beyond(pa, mi_a)) c2++; }
-                            if (c3 == 0 || c2 / (double)c3 < 0.5) { c_end = pa - 1; halt = true; }
-                            pa--;
-                        }
-                        t = pa;
-                    }
-                }
-                out.push_back({c_start, c_end, c_z});
-                pos = c_end + 1;
-            } else if (stop) pos = tpos;
-            pos++;
+            if (!C.beyond(pos, mi)) { pos++; continue; }
+            const Outcome o = eval_seed<false>(C, pos, mi);
+            n_host++; host_span += o.next - pos;
+            if (o.kind == SEG_CALL) out.push_back({pos, o.c_end, o.c_z});
+            pos = o.next;
         }
-#undef CNV_STEP
     }
 };
 

@@ -1372,20 +1372,28 @@ struct CnvState {
     cnv::PreOut *d_pre = nullptr; unsigned long long *d_hist = nullptr;
     cnv::RepRec *d_rep = nullptr; unsigned int *d_nrep = nullptr; unsigned int rep_cap = 0;
     uint8_t *d_tile = nullptr;                                         // [4][n_tiles]: last/in of the mask stage, last/in of the z stage
-    uint32_t *h_rec = nullptr, *h_seed = nullptr;                      // pinned
+    uint32_t *h_rec = nullptr, *h_seed = nullptr, *h_wp = nullptr, *h_land = nullptr; cnv::SeedCall *h_spec = nullptr;   // pinned
+    uint32_t *d_blk = nullptr, *d_wp = nullptr, *d_land = nullptr; uint32_t land_cap = 0, spec_cap = 0; int nb = 0;
+    cnv::SeedCall *d_spec = nullptr; unsigned int *d_nspec = nullptr; double *d_winsd = nullptr;
     std::vector<grom_cnv_call> calls;
     std::vector<double> win_sd, bin_d; std::vector<int64_t> win_cnt, bin_n;
     int64_t P = 0, words = 0;
     int q = 0;
     std::vector<double> sd_tbl;
+    cnv::Grow tmp[16];
 };
 static void cnv_state_free(CnvState *c)
 {
     if (!c) return;
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
+    for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     if (c->h_seed) cudaFreeHost(c->h_seed);
+    if (c->h_wp) cudaFreeHost(c->h_wp);
+    if (c->h_land) cudaFreeHost(c->h_land);
+    if (c->h_spec) cudaFreeHost(c->h_spec);
+    cudaFree(c->d_blk); cudaFree(c->d_wp); cudaFree(c->d_land); cudaFree(c->d_spec); cudaFree(c->d_nspec); cudaFree(c->d_winsd);
     delete c;
 }
 
@@ -1438,6 +1446,14 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const auto t_begin = std::chrono::steady_clock::now();
     double ms_dev = 0;
+    const bool trace = getenv("GROMGPU_CNV_TRACE") != nullptr;
+    auto t_last = t_begin;
+    auto mark = [&](const char *what) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cnv] %-28s %8.3f ms (device so far %.3f)\n", what, std::chrono::duration<double, std::milli>(now - t_last).count(), ms_dev);
+        t_last = now;
+    };
     auto dev_begin = [&]() { cudaEventRecord(e0, s); };
     auto dev_end = [&]() { cudaEventRecord(e1, s); cudaEventSynchronize(e1); float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ms_dev += ms; };
 
@@ -1453,6 +1469,13 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMalloc(&c.d_rep, sizeof(RepRec) * c.rep_cap)); CK(cudaMalloc(&c.d_nrep, sizeof(unsigned int)));
         CK(cudaMalloc(&c.d_tile, 4 * n_tiles));
         CK(cudaMallocHost(&c.h_rec, sizeof(uint32_t) * P)); CK(cudaMallocHost(&c.h_seed, sizeof(uint32_t) * 2 * words));
+        c.nb = (int)((words + SEED_WORDS - 1) / SEED_WORDS); c.land_cap = (uint32_t)(P / 4 + 1024);
+        CK(cudaMalloc(&c.d_blk, sizeof(uint32_t) * (2 * c.nb + 2))); CK(cudaMalloc(&c.d_wp, sizeof(uint32_t) * 2 * words));
+        CK(cudaMalloc(&c.d_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
+        CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * words)); CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
+        c.spec_cap = (uint32_t)std::min<int64_t>(P / 8 + 1024, (int64_t)1 << 28);
+        CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
+        CK(cudaMalloc(&c.d_nspec, 2 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (Lmax + 1)));
     }
 
     // ---- stage 1: pre-statistics + repeat runs
@@ -1469,6 +1492,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     CK(cudaMemcpyAsync(&n_rep, c.d_nrep, sizeof(n_rep), cudaMemcpyDeviceToHost, s));
     dev_end();
     CK(cudaGetLastError());
+    mark("stage1 kernels+D2H");
     if (n_rep > c.rep_cap) return fail("gromgpu_chr_cnv: %u repeat runs exceed the buffer of %u", n_rep, c.rep_cap);
     std::vector<RepRec> reps(n_rep);
     if (n_rep) CK(cudaMemcpy(reps.data(), c.d_rep, sizeof(RepRec) * n_rep, cudaMemcpyDeviceToHost));
@@ -1541,6 +1565,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             if (le[k] - ls[k] >= Lmin) { sb_s.push_back(ls[k]); sb_e.push_back(le[k]); }
         }
     }
+    mark("pre-statistics host");
     const int n_sb = (int)sb_s.size();
     out->n_sample_blocks = n_sb;
 
@@ -1550,9 +1575,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     const int64_t n_samples = sb_first[n_sb];
     out->n_samples = n_samples;
     std::vector<Sample> samples(n_samples);
-    DevTmp t_sb, t_first, t_samples;
+    Grow &t_sb = c.tmp[0], &t_first = c.tmp[1], &t_samples = c.tmp[2];
     if (n_samples) {
-        CK(cudaMalloc(&t_sb.p, sizeof(int64_t) * n_sb)); CK(cudaMalloc(&t_first.p, sizeof(int64_t) * (n_sb + 1))); CK(cudaMalloc(&t_samples.p, sizeof(Sample) * n_samples));
+        if (!t_sb.ensure(sizeof(int64_t) * n_sb) || !t_first.ensure(sizeof(int64_t) * (n_sb + 1)) || !t_samples.ensure(sizeof(Sample) * n_samples)) return fail("gromgpu_chr_cnv: out of device memory");
         dev_begin();
         CK(cudaMemcpyAsync(t_sb.p, sb_s.data(), sizeof(int64_t) * n_sb, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(t_first.p, sb_first.data(), sizeof(int64_t) * (n_sb + 1), cudaMemcpyHostToDevice, s));
@@ -1562,6 +1587,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         dev_end();
         CK(cudaGetLastError());
     }
+    mark("samples kernel+D2H");
     GlibcRand rng((unsigned)prm.rand_seed);
     // most-biased repeat: depth samples by distance segment around every run of that type (src/GROM.c:18262-18367)
     constexpr int SEG = 10;
@@ -1575,9 +1601,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         const int64_t total = firsts.back();
         o_depth.resize(total); o_gc.resize(total);
         if (!total) return 0;
-        DevTmp a, b, od, og;
-        CK(cudaMalloc(&a.p, sizeof(int64_t) * n_seg)); CK(cudaMalloc(&b.p, sizeof(int64_t) * (n_seg + 1)));
-        CK(cudaMalloc(&od.p, sizeof(int32_t) * total)); CK(cudaMalloc(&og.p, total));
+        Grow &a = c.tmp[3], &b = c.tmp[4], &od = c.tmp[5], &og = c.tmp[6];
+        if (!a.ensure(sizeof(int64_t) * n_seg) || !b.ensure(sizeof(int64_t) * (n_seg + 1)) || !od.ensure(sizeof(int32_t) * total) || !og.ensure(total)) return fail("gromgpu_chr_cnv: out of device memory");
         dev_begin();
         CK(cudaMemcpyAsync(a.p, starts.data(), sizeof(int64_t) * n_seg, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.p, firsts.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, s));
@@ -1675,9 +1700,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         for (int x : lists[l].v) row[x]++;
         for (int d = 1; d <= D; d++) row[d] += row[d - 1];
     }
-    DevTmp t_cum, t_n, t_small, t_dbl;
-    CK(cudaMalloc(&t_cum.p, sizeof(int32_t) * cum.size())); CK(cudaMalloc(&t_n.p, sizeof(int32_t) * NLIST)); CK(cudaMalloc(&t_small.p, sizeof(int32_t) * 2 * NLIST));
-    CK(cudaMalloc(&t_dbl.p, sizeof(double) * (3 * NLIST + 2 * P2S)));
+    Grow &t_cum = c.tmp[7], &t_n = c.tmp[8], &t_small = c.tmp[9], &t_dbl = c.tmp[10];
+    if (!t_cum.ensure(sizeof(int32_t) * cum.size()) || !t_n.ensure(sizeof(int32_t) * NLIST) || !t_small.ensure(sizeof(int32_t) * 2 * NLIST) ||
+        !t_dbl.ensure(sizeof(double) * (3 * NLIST + 2 * P2S))) return fail("gromgpu_chr_cnv: out of device memory");
     std::vector<double> dbl(3 * NLIST + 2 * P2S);
     std::copy(ave.begin(), ave.end(), dbl.begin()); std::copy(del_thr.begin(), del_thr.end(), dbl.begin() + NLIST); std::copy(dup_thr.begin(), dup_thr.end(), dbl.begin() + 2 * NLIST);
     std::copy(p2s_p, p2s_p + P2S, dbl.begin() + 3 * NLIST); std::copy(p2s_sd, p2s_sd + P2S, dbl.begin() + 3 * NLIST + P2S);
@@ -1685,6 +1710,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     T.cum = t_cum.as<int32_t>(); T.D = D; T.n = t_n.as<int32_t>(); T.small = t_small.as<int32_t>();
     T.ave = t_dbl.as<double>(); T.del_thr = T.ave + NLIST; T.dup_thr = T.ave + 2 * NLIST; T.p2s_p = T.ave + 3 * NLIST; T.p2s_sd = T.p2s_p + P2S;
 
+    mark("lists+tables host");
     // ---- stage 3: mask, z, seeds, window sweep
     // walk of every sample block at each -A offset, cut into frames of Lmax elements
     std::vector<SweepBlock> sw(n_sb);
@@ -1697,10 +1723,10 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     }
     out->n_frames = n_frames;
     const int n_len = Lmax - Lmin + 1;
-    DevTmp t_sw, t_X, t_wsq, t_wcnt;
+    Grow &t_sw = c.tmp[11], &t_X = c.tmp[12], &t_wsq = c.tmp[13], &t_wcnt = c.tmp[14];
     if (n_frames) {
-        CK(cudaMalloc(&t_sw.p, sizeof(SweepBlock) * n_sb)); CK(cudaMalloc(&t_X.p, sizeof(double) * (size_t)n_len * n_frames));
-        CK(cudaMalloc(&t_wsq.p, sizeof(double) * n_len)); CK(cudaMalloc(&t_wcnt.p, sizeof(long long) * n_len));
+        if (!t_sw.ensure(sizeof(SweepBlock) * n_sb) || !t_X.ensure(sizeof(double) * (size_t)n_len * n_frames) || !t_wsq.ensure(sizeof(double) * n_len) ||
+            !t_wcnt.ensure(sizeof(long long) * n_len)) return fail("gromgpu_chr_cnv: out of device memory for the window sweep (%lld frames)", (long long)n_frames);
     }
     uint8_t *tl_mask = c.d_tile, *ti_mask = c.d_tile + n_tiles, *tl_z = c.d_tile + 2 * n_tiles, *ti_z = c.d_tile + 3 * n_tiles;
     std::vector<double> wsq(n_len, 0.0); std::vector<long long> wcnt(n_len, 0);
@@ -1716,15 +1742,22 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     k_z<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, A_gc, P, lo, hi, q, T, ti_z, c.d_rec, c.d_seed, c.d_seed + words);
     CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
+    uint32_t seed_tot[2] = {0, 0};
+    k_seed_blocksum<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb);
+    k_seed_blockscan<<<2, 1024, 0, s>>>(c.d_blk, c.nb, c.d_blk + 2 * c.nb);
+    k_seed_rank<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb, c.d_wp);
+    CK(cudaMemcpyAsync(seed_tot, c.d_blk + 2 * c.nb, sizeof(seed_tot), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(c.h_wp, c.d_wp, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
     if (n_frames) {
         CK(cudaMemcpyAsync(t_sw.p, sw.data(), sizeof(SweepBlock) * n_sb, cudaMemcpyHostToDevice, s));
-        k_sweep<<<(unsigned)((n_frames + 63) / 64), 64, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>());
-        k_sweep_sum<<<(unsigned)((n_len * 32 + 127) / 128), 128, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>());
+        k_sweep<<<(unsigned)((n_frames * 32 + 255) / 256), 256, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>());
+        k_sweep_sum<<<(unsigned)((n_len + 127) / 128), 128, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>());
         CK(cudaMemcpyAsync(wsq.data(), t_wsq.p, sizeof(double) * n_len, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(wcnt.data(), t_wcnt.p, sizeof(long long) * n_len, cudaMemcpyDeviceToHost, s));
     }
     dev_end();
     CK(cudaGetLastError());
+    mark("stage3 kernels+D2H");
     for (int L = Lmin; L <= Lmax; L++) {
         c.win_cnt[L] = wcnt[L - Lmin];
         c.win_sd[L] = wcnt[L - Lmin] > 1 ? sqrt(wsq[L - Lmin] / (double)(wcnt[L - Lmin] - 1)) : 0.0;
@@ -1761,19 +1794,50 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     // ---- stage 4: greedy segmentation (two host threads: deletions, duplications) and copy number
     std::vector<Call> found[2];
     {
+        SegCtx ctx[2];
+        for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].dup = k == 1; }
+        // every seed evaluated on the device (bounded); a seed list that outgrew its buffer, or the biased-repeat override (it rewrites
+        // z on the host copy after the sweep), leaves the evaluation to the host
+        unsigned int n_spec = 0;
+        const bool have_land = seed_tot[0] <= c.land_cap && seed_tot[1] <= c.land_cap && (int64_t)Lmax + SEED_BOUND < ((int64_t)1 << LAND_SHIFT) && hi - Lmin > lo;
+        if (have_land) {
+            dev_begin();
+            CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
+            CK(cudaMemsetAsync(c.d_nspec, 0, 2 * sizeof(unsigned int), s));
+            k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 0);
+            unsigned int cnt2[2] = {0, 0};
+            CK(cudaMemcpyAsync(cnt2, c.d_nspec, sizeof(cnt2), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            if (cnt2[1] > 0 && cnt2[1] <= 32768 && SEED_BOUND2 < Lmax) {
+                // few seeds ran past the first bound (typically the uncovered stretch before the first applied read): give them a longer leash
+                ctx[0].bound = ctx[1].bound = SEED_BOUND2;
+                k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 1);
+            }
+            for (int k = 0; k < 2; k++) if (seed_tot[k]) CK(cudaMemcpyAsync(c.h_land + (size_t)k * 2 * c.land_cap, c.d_land + (size_t)k * 2 * c.land_cap, sizeof(uint32_t) * 2 * seed_tot[k], cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(&n_spec, c.d_nspec, sizeof(n_spec), cudaMemcpyDeviceToHost, s));
+            dev_end();
+            CK(cudaGetLastError());
+            n_spec = std::min(n_spec, c.spec_cap);
+            if (n_spec) CK(cudaMemcpy(c.h_spec, c.d_spec, sizeof(SeedCall) * n_spec, cudaMemcpyDeviceToHost));
+        }
+        mark("seed evaluation device");
         Segmenter sg[2];
         for (int k = 0; k < 2; k++) {
-            sg[k].rec = c.h_rec; sg[k].seeds = c.h_seed + k * words; sg[k].len = P; sg[k].lo = lo; sg[k].hi = hi; sg[k].q = q; sg[k].Lmin = Lmin; sg[k].Lmax = Lmax;
-            sg[k].sd = c.sd_tbl.data(); sg[k].win_sd = c.win_sd.data(); sg[k].dup = k == 1;
+            sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
+            if (have_land) { sg[k].wp = c.h_wp + k * words; sg[k].land = c.h_land + (size_t)k * 2 * c.land_cap; sg[k].spec = c.h_spec; }
         }
         std::thread th([&]() { sg[1].run(found[1]); });
         sg[0].run(found[0]);
         th.join();
+        if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u, speculative calls %u; table/host evaluations del %ld/%ld dup %ld/%ld host span %ld %ld\n", seed_tot[0], seed_tot[1], n_spec,
+                           sg[0].n_table, sg[0].n_host, sg[1].n_table, sg[1].n_host, sg[0].host_span, sg[1].host_span);
     }
+    mark("segmentation host");
     std::vector<int64_t> seg_start, seg_first(1, 0);
     for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) { seg_start.push_back(cl.start); seg_first.push_back(seg_first.back() + std::max<int64_t>(0, cl.end - cl.start)); }
     std::vector<int32_t> g_depth; std::vector<uint8_t> g_gc;
     if (!seg_start.empty() && gather(seg_start, seg_first, g_depth, g_gc)) return -1;
+    mark("gather");
     {
         std::vector<double> buf, tmp;
         size_t si = 0;
@@ -1809,6 +1873,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             c.calls.push_back(o);
         }
     }
+    mark("gather+copy number");
     out->n_calls = (int64_t)c.calls.size(); out->calls = c.calls.data();
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();

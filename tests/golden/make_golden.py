@@ -8,6 +8,10 @@ Outputs (committed):
     tests/golden/g1.fa.gz, g1.bam, g1.bam.bai      the input (so nothing depends on numpy's RNG stream)
     tests/golden/g1_default.npz, g1_rmdup.npz      reference arrays at every scanned position, per-read keep
                                                    flags, CNV depth arrays, VCF records, library statistics
+    tests/golden/g2_cnv.npz                        read-depth CNV path of a 1.2 Mb contig with a planted one-copy loss and thinned
+                                                   (AT)n runs: the reference's own CNV depth / GC arrays as compact input, and its
+                                                   pre-statistics, per-bin distributions, mask, z list (sampled + checksums), window
+                                                   sd table, calls with copy number, and VCF records as expected output
 """
 import gzip
 import os
@@ -62,5 +66,44 @@ def main():
     shutil.rmtree(tmp)
 
 
+def main_cnv():
+    spec = synth.SynthSpec(contigs=[("chrA", 1_200_000), ("chrZ", 50_000)], depth=30, seed=21, cnv_per_mb=0.9, disc_frac=0.005,
+                           sv_sites_per_mb=1.0, low_mapq_frac=0.05, at_repeats=260, cnv_min=15000, cnv_max=30000)
+    cs = synth.simulate(spec)
+    tmp = tempfile.mkdtemp()
+    fa, bam = synth.write_dataset(os.path.join(tmp, "g2"), cs)
+    dump = os.path.join(tmp, "dump")
+    vcf = os.path.join(tmp, "g2.vcf")
+    po.run_reference(bam, fa, vcf, dump_dir=dump, kind="ref", seed=5)
+    vcf_dist = os.path.join(tmp, "g2.dist.vcf")
+    po.run_reference(bam, fa, vcf_dist, kind="dist")
+    cnv_lines = [l for l in open(vcf) if l.startswith("chra\t") and "\tSD:Z:CN:CS\t" in l]
+    assert cnv_lines == [l for l in open(vcf_dist) if l.startswith("chra\t") and "\tSD:Z:CN:CS\t" in l], "white-box and prebuilt binary disagree"
+    assert len(cnv_lines) >= 1
+    m = po.read_mean_file(bam)
+    dep = po.load_depth_dump(dump, "chra")
+    gcd = po.load_gc_dump(dump, "chra")
+    pre = po.load_cnvpre_dump(dump, "chra")
+    d = po.load_cnv_dump(dump, "chra")
+    assert dep[1].max() < 256 and dep[2].max() < 256 and dep[0].max() < 65536 and pre["biased"] != -1
+    out = dict(fasta=cs[0].chars, rd_mq=dep[0].astype(np.uint16), rd_rd=dep[1].astype(np.uint8), rd_low=dep[2].astype(np.uint8),
+               gc=gcd[0].astype(np.uint8), acgt=gcd[1].astype(np.uint8),
+               mean=np.array([m[k] for k in ("insert_mean", "lseq", "insert_min", "insert_max", "mapped_reads")]), seed=np.array(5),
+               vcf=np.array("".join(cnv_lines)), z_stride=d["z"][::53].copy(), z_sum=np.array(float(d["z"].sum())),
+               z_abs_sum=np.array(float(np.abs(d["z"]).sum())), z_nonzero=np.array(int((d["z"] != 0).sum())), mask_bits=np.packbits(d["mask"]))
+    for k in ("nblocks", "repeats", "chr_ave", "chr_sd", "rep_ave", "rep_sd", "rep_cnt", "biased", "blk_ave", "sample_blocks"):
+        out["pre_" + k] = np.asarray(pre[k])
+    for k in ("win_sd", "win_cnt", "ave", "sd", "del_thr", "dup_thr", "windows", "n_high", "n_low", "dels", "dups"):
+        out[k] = d[k]
+    np.savez_compressed(os.path.join(HERE, "g2_cnv.npz"), **out)
+    print("g2_cnv: records", len(cnv_lines), "dels", len(d["dels"]), "dups", len(d["dups"]), "biased", pre["biased"],
+          "size %.2f MB" % (os.path.getsize(os.path.join(HERE, "g2_cnv.npz")) / 1e6))
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cnv":
+        main_cnv()
+    else:
+        main()
+        main_cnv()

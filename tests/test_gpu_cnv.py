@@ -81,6 +81,15 @@ def test_cnv_reservoir_and_small_windows():
     _check(o, g, z, mask, mqm, prm)
 
 
+def test_cnv_biased_repeat_override():
+    """> 100 thinned (AT)n runs make AT the most biased repeat type: sampled repeat lists and the z override around every run."""
+    c = _dataset(seed=21, length=1_200_000, depth=30, cnv_per_mb=0.9, at_repeats=260, cnv_min=15000, cnv_max=30000)
+    prm = Params.default()
+    o, g, z, mask, mqm = _run_both(prm, c)
+    assert o.biased == 3 and "<DEL>" in o.vcf
+    _check(o, g, z, mask, mqm, prm)
+
+
 def test_cnv_short_contig_is_empty():
     """A contig shorter than the GC window has no analysed span (lo >= hi): no calls, no error."""
     rng = np.random.default_rng(3)

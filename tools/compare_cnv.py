@@ -15,10 +15,11 @@ ap.add_argument("--depth", type=float, default=20)
 ap.add_argument("--cnv", type=float, default=4.0)
 ap.add_argument("--A", type=int, default=2)
 ap.add_argument("--ploidy", type=int, default=2)
-ap.add_argument("--flat", type=int, default=0, help="constant-GC reference (all samples in one bin)")
+ap.add_argument("--at", type=int, default=0, help="planted thinned (AT)n runs")
+ap.add_argument("--cnvmax", type=int, default=120000)
 a = ap.parse_args()
 spec = synth.SynthSpec(contigs=[("chrA", a.len), ("chrx", a.len // 2), ("chrZ", 50000)], depth=a.depth, seed=a.seed, cnv_per_mb=a.cnv,
-                       disc_frac=0.005, sv_sites_per_mb=1.0, low_mapq_frac=0.05)
+                       disc_frac=0.005, sv_sites_per_mb=1.0, low_mapq_frac=0.05, at_repeats=a.at, cnv_min=min(20000, a.cnvmax // 2), cnv_max=a.cnvmax)
 cs = synth.simulate(spec)
 fa, bam = synth.write_dataset("/tmp/cmpcnv", cs)
 dump = "/tmp/cmpcnv_dump"

@@ -31,3 +31,7 @@ with gpu.Chromosome(0, c.chars) as ch:
     alg = s.bytes_reads + 104 * P   # 26 arrays written by the pileup kernel
     print(f"pileup: {alg/1e9:.3f} GB algorithmic / {s.ms_pileup:.3f} ms = {alg/s.ms_pileup/1e6:.1f} GB/s; "
           f"aligned bases/s (device total) = {s.aligned_bases/s.ms_total/1e-3/1e9:.2f} G")
+    for r in range(2):
+        t = time.time(); g = ch.cnv(); dt = time.time() - t
+        print(json.dumps(dict(cnv_ms_total=round(g.ms_total, 2), cnv_ms_device=round(g.ms_device, 2), cnv_ms_host=round(g.ms_host, 2), wall_ms=round(dt * 1e3, 2),
+                              calls=len(g.calls), samples=g.n_samples, frames=g.n_frames, repeats=g.n_repeats, biased=g.biased_repeat)))

@@ -63,6 +63,8 @@ class SynthSpec:
     cnv_per_mb: float = 0.0         # planted copy-number segments (alternating loss / gain of one copy, every 4th a full loss)
     cnv_min: int = 20_000
     cnv_max: int = 120_000
+    at_repeats: int = 0             # planted (AT)n runs of 24-60 bp whose coverage is thinned (exercises the biased-repeat path)
+    at_repeat_keep: float = 0.3
 
 
 def make_reference(length: int, rng: np.random.Generator, n_frac=0.01, lower_frac=0.1) -> np.ndarray:
@@ -152,6 +154,14 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
     fs = np.sort(rng.integers(0, max(1, length - int(ins.max()) - 1), n_pairs)).astype(np.int64)
     hp = rng.integers(0, 2, n_pairs)
     cnv_truth = []
+    if spec.at_repeats and name in _AT_RUNS:
+        # pairs whose first read overlaps a planted (AT)n run are mostly lost
+        ra, rn = _AT_RUNS.pop(name)
+        j = np.searchsorted(ra, fs + rl, side="left") - 1
+        hit = (j >= 0) & (ra[np.maximum(j, 0)] + rn[np.maximum(j, 0)] > fs)
+        keep = ~hit | (rng.random(n_pairs) < spec.at_repeat_keep)
+        fs, ins, hp = fs[keep], ins[keep], hp[keep]
+        n_pairs = len(fs)
     if spec.cnv_per_mb > 0:
         # copy-number segments: thin (loss) or thicken (gain) the pairs that start inside the segment
         keep = np.ones(n_pairs, dtype=bool)
@@ -478,12 +488,22 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
     return SynthContig(name=name, chars=chars, batch=batch, truth=truth)
 
 
+_AT_RUNS: Dict[str, Tuple[np.ndarray, np.ndarray]] = {}
+
+
 def simulate(spec: SynthSpec) -> List[SynthContig]:
     rng = np.random.default_rng(spec.seed)
     lens = [l for _, l in spec.contigs]
     out = []
     for tid, (name, length) in enumerate(spec.contigs):
         chars = make_reference(length, rng, spec.n_frac, spec.lower_frac)
+        if spec.at_repeats and length > 20_000:
+            a = np.sort(rng.integers(5_000, length - 5_000, spec.at_repeats))
+            a = a[np.concatenate([[True], np.diff(a) > 700])]
+            n = rng.integers(24, 60, len(a))
+            for x, k in zip(a, n):
+                chars[x:x + k] = np.tile(np.frombuffer(b"AT", dtype=np.uint8), k // 2 + 1)[:k]
+            _AT_RUNS[name] = (a, n)
         out.append(_simulate_contig(tid, name, length, spec, len(spec.contigs), lens, rng, chars))
     return out
 
