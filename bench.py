@@ -212,28 +212,31 @@ def main_b200(a):
         if rank == 0:
             sampler.start()
         for _ in range(max(3, a.warmup)):
-            ch.run()
+            ch.run(); ch.cnv()
         barrier()
         t_region0 = time.time()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         per = {k: 0.0 for k in ("ms_total", "ms_clear", "ms_gc", "ms_dup", "ms_prep", "ms_index", "ms_sv", "ms_rdscan", "ms_pileup")}
         launches = 0
+        cnv_ms = {"ms_cnv_device": 0.0, "ms_cnv_host": 0.0}
         ev0.record(stream)
         for _ in range(a.steps):
             ch.run()
+            cn = ch.cnv()
             s = ch.stats()
             for k in per:
                 per[k] += getattr(s, k)
-            launches += s.launches
+            launches += s.launches + cn.launches
+            cnv_ms["ms_cnv_device"] += cn.ms_device; cnv_ms["ms_cnv_host"] += cn.ms_host
         ev1.record(stream)
         barrier()
         ms_steps = ev0.elapsed_time(ev1)
         st = ch.stats()
         res = ch.result()
         # ---- end-to-end timing through the C ABI with host (pinned) buffers: reset + FASTA H2D + reads H2D + kernels + result D2H
-        d2h_bytes = len(res.snv) * 128 + 64
+        d2h_bytes = len(res.snv) * 128 + len(res.ins) * 104 + len(res.del_ev) * 48 + 64 + cn.d2h_bytes + len(cn.calls) * 56
         for _ in range(2):
-            ch.reset(fasta_np); ch.push_reads(pinned); ch.finish()
+            ch.reset(fasta_np); ch.push_reads(pinned); ch.finish(); ch.cnv()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -241,13 +244,14 @@ def main_b200(a):
             ch.reset(fasta_np)
             ch.push_reads(pinned)
             r2 = ch.finish()
+            cn2 = ch.cnv()
         e1.record(stream)
         barrier()
         ms_e2e = e0.elapsed_time(e1)
         if rank == 0:
             sampler.window(t_region0, time.time())
         clocks = sampler.stop() if rank == 0 else None
-        assert len(r2.snv) == len(res.snv)
+        assert len(r2.snv) == len(res.snv) and len(cn2.calls) == len(cn.calls)
         ch.close()
 
     bases = int(st.aligned_bases)
@@ -289,18 +293,19 @@ def main_b200(a):
             "warmup": max(3, a.warmup), "ms_per_step": ms_steps_max / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(a), "contig_len": P, "reads_per_gpu": int(st.n_reads), "aligned_bases_per_gpu": bases,
-                       "flags": "-M (duplicate filter on), defaults otherwise", "discordant_pairs": "1 % (deletion-like / same-strand / mate-unmapped)", "l2": "inputs (>3 GB reads + 6.7 GB arrays per step) exceed the 126 MB L2; no flush needed",
+                       "flags": "-M (duplicate filter on), defaults otherwise", "step": "evidence + SNV/indel scan (gromgpu_chr_run) + read-depth CNV path (gromgpu_chr_cnv, incl. its host segmentation)", "discordant_pairs": "1 % (deletion-like / same-strand / mate-unmapped)", "l2": "inputs (>3 GB reads + 6.7 GB arrays per step) exceed the 126 MB L2; no flush needed",
                        "partition": "one contig per GPU, no data-path collective", "host_gen_s": round(gen_s, 1)},
             "e2e": {"value": total_bases * a.steps / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(read_bytes + P),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_pileup", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": ms_pile},
-            "kernels_ms_per_step": {k: v / a.steps for k, v in per.items()},
+            "kernels_ms_per_step": {**{k: v / a.steps for k, v in per.items()}, **{k: v / a.steps for k, v in cnv_ms.items()}},
             "cpu_baseline": cpu,
             "clocks": clocks,
             "results": {"snv_candidates": int(len(res.snv)), "dups": int(st.n_dups), "applied_reads": int(st.n_applied),
-                        "sv_items": int(st.n_sv_items)},
+                        "sv_items": int(st.n_sv_items), "small_ins": int(len(res.ins)),
+                        "small_del_events": int(len(res.del_ev)), "cnv_calls": int(len(cn.calls))},
         }
         print(json.dumps(line))
     if world > 1:

@@ -666,12 +666,17 @@ struct Segmenter {
         const int64_t r = (w << 5) + __builtin_ctz(bits);
         return r < end ? r : end;
     }
-    void run(std::vector<Call> &out)
+    struct Seen { int64_t pos; int mi; };
+    struct Piece { std::vector<Seen> seen; std::vector<std::pair<size_t, Call>> calls; int64_t exit_pos = 0; int exit_low = 0; };
+    // Hop from (pos, last_low) until pos >= limit.  Every evaluated seed is appended to piece.seen, every call to piece.calls (with the
+    // index of its seed).  If `probe` is given, stop as soon as the next seed to evaluate is one the probe path evaluated with the same
+    // class: from there on both paths are identical; returns that index, else -1.
+    long hop(int64_t pos, int last_low, int64_t limit, Piece &piece, const Piece *probe)
     {
         const int64_t end = C.end;
-        int mi = 0, last_low = 0;
-        int64_t pos = lo;
-        while (pos < end) {
+        if (limit > end) limit = end;
+        int mi = 0;
+        while (pos < limit) {
             // positions between seeds only move last_low: it is the class of the last covered position the outer loop passed
             const int64_t nx = next_seed(pos, end);
             for (int64_t b = nx - 1; b >= pos; b--) { const int c = C.cls(b); if (c != 2) { last_low = c; break; } }
@@ -679,18 +684,61 @@ struct Segmenter {
             if (pos >= end) break;
             const int c0 = C.cls(pos);
             if (c0 != 2) { mi = c0; last_low = c0; } else mi = last_low;
+            uint32_t v = LAND_NOT - 1;                     // "no table"
             if (land) {
-                const uint32_t v = land[2 * ((int64_t)wp[pos >> 5] + __builtin_popcount(seeds[pos >> 5] & ((1u << (pos & 31)) - 1u))) + mi];
-                const uint32_t kind = v >> LAND_SHIFT, low = v & ((1u << LAND_SHIFT) - 1u);
+                v = land[2 * ((int64_t)wp[pos >> 5] + __builtin_popcount(seeds[pos >> 5] & ((1u << (pos & 31)) - 1u))) + mi];
                 if (v == LAND_NOT) { pos++; continue; }
-                if (kind == SEG_RESUME) { pos += low; n_table++; continue; }
-                if (kind == SEG_CALL) { out.push_back({pos, spec[low].c_end, spec[low].c_z}); pos = spec[low].c_end + 2; n_table++; continue; }
+            } else if (!C.beyond(pos, mi)) { pos++; continue; }
+            if (pos >= limit) break;                       // the seed belongs to the next piece
+            if (probe) {
+                auto it = std::lower_bound(probe->seen.begin(), probe->seen.end(), pos, [](const Seen &s, int64_t x) { return s.pos < x; });
+                if (it != probe->seen.end() && it->pos == pos && it->mi == mi) { piece.exit_pos = pos; piece.exit_low = last_low; return (long)(it - probe->seen.begin()); }
             }
-            if (!C.beyond(pos, mi)) { pos++; continue; }
+            piece.seen.push_back({pos, mi});
+            const uint32_t kind = v >> LAND_SHIFT, low = v & ((1u << LAND_SHIFT) - 1u);
+            if (land && kind == SEG_RESUME) { pos += low; n_table++; continue; }
+            if (land && kind == SEG_CALL) { piece.calls.push_back({piece.seen.size() - 1, Call{pos, spec[low].c_end, spec[low].c_z}}); pos = spec[low].c_end + 2; n_table++; continue; }
             const Outcome o = eval_seed<false>(C, pos, mi);
             n_host++; host_span += o.next - pos;
-            if (o.kind == SEG_CALL) out.push_back({pos, o.c_end, o.c_z});
+            if (o.kind == SEG_CALL) piece.calls.push_back({piece.seen.size() - 1, Call{pos, o.c_end, o.c_z}});
             pos = o.next;
+        }
+        piece.exit_pos = pos; piece.exit_low = last_low;
+        return -1;
+    }
+    // The scan is a chain (each seed decides where the next one is), so pieces of the contig are hopped speculatively in parallel from
+    // their own start, then stitched in order: the true path entering a piece is followed until it meets the speculative one.
+    void run(std::vector<Call> &out, int n_threads)
+    {
+        const int64_t end = C.end;
+        int K = std::max(1, n_threads);
+        if (end - lo < (int64_t)K * 200000) K = (int)std::max<int64_t>(1, (end - lo) / 200000);
+        std::vector<Piece> pieces(K);
+        std::vector<int64_t> bound(K + 1);
+        for (int t = 0; t <= K; t++) bound[t] = lo + (end - lo) * t / K;
+        std::vector<Segmenter> workers(K, *this);
+        std::vector<std::thread> th;
+        for (int t = 0; t < K; t++) {
+            auto job = [&, t]() {
+                int guess = 0;
+                for (int64_t b = bound[t] - 1; b >= lo && b >= bound[t] - 100000; b--) { const int c = C.cls(b); if (c != 2) { guess = c; break; } }
+                workers[t].hop(bound[t], t == 0 ? 0 : guess, bound[t + 1], pieces[t], nullptr);
+            };
+            if (t + 1 < K) th.emplace_back(job); else job();
+        }
+        for (auto &x : th) x.join();
+        for (auto &w : workers) { n_table += w.n_table; n_host += w.n_host; host_span += w.host_span; }
+        for (auto &c : pieces[0].calls) out.push_back(c.second);
+        int64_t pos = pieces[0].exit_pos; int last_low = pieces[0].exit_low;
+        for (int t = 1; t < K; t++) {
+            if (pos >= bound[t + 1]) continue;                                   // a call reached past this whole piece
+            Piece link;
+            const long j = hop(pos, last_low, bound[t + 1], link, &pieces[t]);
+            for (auto &c : link.calls) out.push_back(c.second);
+            if (j >= 0) {
+                for (auto &c : pieces[t].calls) if ((long)c.first >= j) out.push_back(c.second);
+                pos = pieces[t].exit_pos; last_low = pieces[t].exit_low;
+            } else { pos = link.exit_pos; last_low = link.exit_low; }
         }
     }
 };

@@ -1446,6 +1446,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     const auto t_begin = std::chrono::steady_clock::now();
     double ms_dev = 0;
+    int n_launch = 0;
+    int64_t d2h = 0;
     const bool trace = getenv("GROMGPU_CNV_TRACE") != nullptr;
     auto t_last = t_begin;
     auto mark = [&](const char *what) {
@@ -1482,8 +1484,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     dev_begin();
     CK(cudaMemsetAsync(c.d_hist, 0, sizeof(unsigned long long) * HIST_ALL, s));
     CK(cudaMemsetAsync(c.d_nrep, 0, sizeof(unsigned int), s));
-    k_pre<<<(unsigned)n_blk, 256, 0, s>>>(A_mq, A_rd, A_low, A_acgt, h->d_fasta, P, lo, hi, c.d_depth, c.d_mq8, c.d_pre, c.d_hist);
-    k_repeats<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(h->d_fasta, c.d_depth, lo, hi, c.d_rep, c.rep_cap, c.d_nrep);
+    k_pre<<<(unsigned)n_blk, 256, 0, s>>>(A_mq, A_rd, A_low, A_acgt, h->d_fasta, P, lo, hi, c.d_depth, c.d_mq8, c.d_pre, c.d_hist); n_launch++;
+    k_repeats<<<(unsigned)((hi - lo + 255) / 256), 256, 0, s>>>(h->d_fasta, c.d_depth, lo, hi, c.d_rep, c.rep_cap, c.d_nrep); n_launch++;
     std::vector<PreOut> pre(n_blk);
     std::vector<unsigned long long> hist(HIST_ALL);
     unsigned int n_rep = 0;
@@ -1582,7 +1584,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMemcpyAsync(t_sb.p, sb_s.data(), sizeof(int64_t) * n_sb, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(t_first.p, sb_first.data(), sizeof(int64_t) * (n_sb + 1), cudaMemcpyHostToDevice, s));
         k_samples<<<(unsigned)((n_samples + 255) / 256), 256, 0, s>>>(c.d_depth, A_rd, A_low, c.d_mq8, A_gc, A_acgt, t_sb.as<int64_t>(), t_first.as<int64_t>(), n_sb,
-                                                                     n_samples, half, q, t_samples.as<Sample>());
+                                                                     n_samples, half, q, t_samples.as<Sample>()); n_launch++;
         CK(cudaMemcpyAsync(samples.data(), t_samples.p, sizeof(Sample) * n_samples, cudaMemcpyDeviceToHost, s));
         dev_end();
         CK(cudaGetLastError());
@@ -1606,7 +1608,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         dev_begin();
         CK(cudaMemcpyAsync(a.p, starts.data(), sizeof(int64_t) * n_seg, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.p, firsts.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, s));
-        k_gather<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c.d_depth, A_gc, A_acgt, a.as<int64_t>(), b.as<int64_t>(), n_seg, total, od.as<int32_t>(), og.as<uint8_t>());
+        k_gather<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c.d_depth, A_gc, A_acgt, a.as<int64_t>(), b.as<int64_t>(), n_seg, total, od.as<int32_t>(), og.as<uint8_t>()); n_launch++;
         CK(cudaMemcpyAsync(o_depth.data(), od.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(o_gc.data(), og.p, total, cudaMemcpyDeviceToHost, s));
         dev_end();
@@ -1658,7 +1660,18 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             lists[to_low * NB + g].add(samples[j].depth, cap, rng);
         }
     }
-    for (auto &l : lists) std::sort(l.v.begin(), l.v.end());
+    // depths are small non-negative integers: counting sort
+    auto sort_depths = [](std::vector<int> &v) {
+        if (v.size() < 64) { std::sort(v.begin(), v.end()); return; }
+        int mx = 0, mn = 0;
+        for (int x : v) { mx = std::max(mx, x); mn = std::min(mn, x); }
+        if (mn < 0 || mx > (1 << 20)) { std::sort(v.begin(), v.end()); return; }
+        std::vector<int> h(mx + 1, 0);
+        for (int x : v) h[x]++;
+        size_t k = 0;
+        for (int d = 0; d <= mx; d++) for (int j = 0; j < h[d]; j++) v[k++] = d;
+    };
+    for (auto &l : lists) sort_depths(l.v);
     {
         // thin bins (20 <= n < 100) borrow the original samples of the two bins on either side (src/GROM.c:18481-18548)
         std::vector<std::vector<int>> grown(NLIST);
@@ -1668,7 +1681,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 if ((long)me.size() < MIN_WINDOWS || (long)me.size() >= NO_COMBINE) continue;
                 std::vector<int> g(me);
                 for (int a = b - 2; a <= b + 2; a++) if (a != b) for (int x : lists[m * NB + a].v) if ((long)g.size() < cap) g.push_back(x);
-                std::sort(g.begin(), g.end());
+                sort_depths(g);
                 grown[m * NB + b] = std::move(g);
             }
         for (int l = 0; l < NLIST; l++) if (!grown[l].empty()) lists[l].v = std::move(grown[l]);
@@ -1735,23 +1748,23 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     CK(cudaMemcpyAsync(t_n.p, nlist.data(), sizeof(int32_t) * NLIST, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(t_small.p, small.data(), sizeof(int32_t) * 2 * NLIST, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(t_dbl.p, dbl.data(), sizeof(double) * dbl.size(), cudaMemcpyHostToDevice, s));
-    k_tile_last_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_acgt, lo, hi, q, tl_mask);
-    k_carry_scan<<<1, 1024, 0, s>>>(tl_mask, ti_mask, (int)n_tiles);
-    k_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_gc, A_acgt, P, lo, hi, q, T.n, ti_mask, c.d_rec, tl_z);
-    k_carry_scan<<<1, 1024, 0, s>>>(tl_z, ti_z, (int)n_tiles);
-    k_z<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, A_gc, P, lo, hi, q, T, ti_z, c.d_rec, c.d_seed, c.d_seed + words);
+    k_tile_last_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_acgt, lo, hi, q, tl_mask); n_launch++;
+    k_carry_scan<<<1, 1024, 0, s>>>(tl_mask, ti_mask, (int)n_tiles); n_launch++;
+    k_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_gc, A_acgt, P, lo, hi, q, T.n, ti_mask, c.d_rec, tl_z); n_launch++;
+    k_carry_scan<<<1, 1024, 0, s>>>(tl_z, ti_z, (int)n_tiles); n_launch++;
+    k_z<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, A_gc, P, lo, hi, q, T, ti_z, c.d_rec, c.d_seed, c.d_seed + words); n_launch++;
     CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
     uint32_t seed_tot[2] = {0, 0};
-    k_seed_blocksum<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb);
-    k_seed_blockscan<<<2, 1024, 0, s>>>(c.d_blk, c.nb, c.d_blk + 2 * c.nb);
-    k_seed_rank<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb, c.d_wp);
+    k_seed_blocksum<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb); n_launch++;
+    k_seed_blockscan<<<2, 1024, 0, s>>>(c.d_blk, c.nb, c.d_blk + 2 * c.nb); n_launch++;
+    k_seed_rank<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb, c.d_wp); n_launch++;
     CK(cudaMemcpyAsync(seed_tot, c.d_blk + 2 * c.nb, sizeof(seed_tot), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(c.h_wp, c.d_wp, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
     if (n_frames) {
         CK(cudaMemcpyAsync(t_sw.p, sw.data(), sizeof(SweepBlock) * n_sb, cudaMemcpyHostToDevice, s));
-        k_sweep<<<(unsigned)((n_frames * 32 + 255) / 256), 256, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>());
-        k_sweep_sum<<<(unsigned)((n_len + 127) / 128), 128, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>());
+        k_sweep<<<(unsigned)((n_frames * 32 + 255) / 256), 256, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>()); n_launch++;
+        k_sweep_sum<<<(unsigned)((n_len + 127) / 128), 128, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>()); n_launch++;
         CK(cudaMemcpyAsync(wsq.data(), t_wsq.p, sizeof(double) * n_len, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(wcnt.data(), t_wcnt.p, sizeof(long long) * n_len, cudaMemcpyDeviceToHost, s));
     }
@@ -1793,6 +1806,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
 
     // ---- stage 4: greedy segmentation (two host threads: deletions, duplications) and copy number
     std::vector<Call> found[2];
+    int64_t seed_tot_all = 0, n_spec_all = 0;
     {
         SegCtx ctx[2];
         for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].dup = k == 1; }
@@ -1804,20 +1818,21 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
             CK(cudaMemsetAsync(c.d_nspec, 0, 2 * sizeof(unsigned int), s));
-            k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 0);
+            k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 0); n_launch++;
             unsigned int cnt2[2] = {0, 0};
             CK(cudaMemcpyAsync(cnt2, c.d_nspec, sizeof(cnt2), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             if (cnt2[1] > 0 && cnt2[1] <= 32768 && SEED_BOUND2 < Lmax) {
                 // few seeds ran past the first bound (typically the uncovered stretch before the first applied read): give them a longer leash
                 ctx[0].bound = ctx[1].bound = SEED_BOUND2;
-                k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 1);
+                k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 1); n_launch++;
             }
             for (int k = 0; k < 2; k++) if (seed_tot[k]) CK(cudaMemcpyAsync(c.h_land + (size_t)k * 2 * c.land_cap, c.d_land + (size_t)k * 2 * c.land_cap, sizeof(uint32_t) * 2 * seed_tot[k], cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(&n_spec, c.d_nspec, sizeof(n_spec), cudaMemcpyDeviceToHost, s));
             dev_end();
             CK(cudaGetLastError());
             n_spec = std::min(n_spec, c.spec_cap);
+            seed_tot_all = (int64_t)seed_tot[0] + seed_tot[1]; n_spec_all = n_spec;
             if (n_spec) CK(cudaMemcpy(c.h_spec, c.d_spec, sizeof(SeedCall) * n_spec, cudaMemcpyDeviceToHost));
         }
         mark("seed evaluation device");
@@ -1826,8 +1841,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
             if (have_land) { sg[k].wp = c.h_wp + k * words; sg[k].land = c.h_land + (size_t)k * 2 * c.land_cap; sg[k].spec = c.h_spec; }
         }
-        std::thread th([&]() { sg[1].run(found[1]); });
-        sg[0].run(found[0]);
+        const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));
+        std::thread th([&]() { sg[1].run(found[1], per_scan); });
+        sg[0].run(found[0], per_scan);
         th.join();
         if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u, speculative calls %u; table/host evaluations del %ld/%ld dup %ld/%ld host span %ld %ld\n", seed_tot[0], seed_tot[1], n_spec,
                            sg[0].n_table, sg[0].n_host, sg[1].n_table, sg[1].n_host, sg[0].host_span, sg[1].host_span);
@@ -1839,44 +1855,56 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     if (!seg_start.empty() && gather(seg_start, seg_first, g_depth, g_gc)) return -1;
     mark("gather");
     {
-        std::vector<double> buf, tmp;
-        size_t si = 0;
-        for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) {
-            grom_cnv_call o; o.start = cl.start; o.end = cl.end; o.kind = k; o.reserved = 0; o.z = cl.z; o.cn = -1; o.cn_sd = 0;
-            buf.clear();
-            for (int64_t j = seg_first[si]; j < seg_first[si + 1]; j++) {
-                const int64_t p = cl.start + (j - seg_first[si]);
-                const uint32_t r = c.h_rec[p];
-                if (r & R_MASK) continue;
-                const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (g_gc[j] & 0x7f);
-                if (ave[l] > 0) buf.push_back((double)g_depth[j] / ave[l]);
-            }
-            si++;
-            const long n = (long)buf.size();
-            if (n > 0) {
-                tmp.resize(n);
-                lowword_msort(buf.data(), n, tmp.data());
-                const long a = (long)(0.1 * n), b = n - a;
-                double tot = 0;
-                for (long j = a; j < b; j++) tot += buf[j];
-                if (b - a > 0) {
-                    o.cn = (tot / (b - a)) * ploidy;
-                    double v = 0;
-                    for (long j = 0; j < n; j++) { const double dd = ploidy * buf[j] - o.cn; v += dd * dd; }
-                    o.cn_sd = sqrt(v / n);
+        // copy number per call (src/GROM.c:20071-20224): independent per call, spread over a few host threads
+        std::vector<const Call *> flat; std::vector<int> flat_kind;
+        for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) { flat.push_back(&cl); flat_kind.push_back(k); }
+        c.calls.assign(flat.size(), grom_cnv_call());
+        auto work = [&](size_t i0, size_t i1) {
+            std::vector<double> buf, tmp;
+            for (size_t si = i0; si < i1; si++) {
+                const Call &cl = *flat[si];
+                grom_cnv_call o; o.start = cl.start; o.end = cl.end; o.kind = flat_kind[si]; o.reserved = 0; o.z = cl.z; o.cn = -1; o.cn_sd = 0;
+                buf.clear();
+                for (int64_t j = seg_first[si]; j < seg_first[si + 1]; j++) {
+                    const int64_t p = cl.start + (j - seg_first[si]);
+                    const uint32_t r = c.h_rec[p];
+                    if (r & R_MASK) continue;
+                    const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (g_gc[j] & 0x7f);
+                    if (ave[l] > 0) buf.push_back((double)g_depth[j] / ave[l]);
                 }
+                const long n = (long)buf.size();
+                if (n > 0) {
+                    tmp.resize(n);
+                    lowword_msort(buf.data(), n, tmp.data());
+                    const long a = (long)(0.1 * n), b = n - a;
+                    double tot = 0;
+                    for (long j = a; j < b; j++) tot += buf[j];
+                    if (b - a > 0) {
+                        o.cn = (tot / (b - a)) * ploidy;
+                        double v = 0;
+                        for (long j = 0; j < n; j++) { const double dd = ploidy * buf[j] - o.cn; v += dd * dd; }
+                        o.cn_sd = sqrt(v / n);
+                    }
+                }
+                // one-sided normal tail through the reference's own erf variant, t = 1 / (1 + p + x) (src/GROM.c:17163-17172)
+                const double x = fabs(o.z) / sqrt(2.0), t = 1.0 / (1.0 + 0.3275911 + x);
+                const double erf_ = 1.0 - ((0.254829592 * t + -0.284496736 * (t * t) + 1.421413741 * pow(t, 3) + -1.453152027 * pow(t, 4) + 1.061405429 * pow(t, 5)) * exp(-(x * x)));
+                o.pvalue = (1.0 - erf_) / 2.0;
+                c.calls[si] = o;
             }
-            // one-sided normal tail through the reference's own erf variant, t = 1 / (1 + p + x) (src/GROM.c:17163-17172)
-            const double x = fabs(o.z) / sqrt(2.0), t = 1.0 / (1.0 + 0.3275911 + x);
-            const double erf_ = 1.0 - ((0.254829592 * t + -0.284496736 * (t * t) + 1.421413741 * pow(t, 3) + -1.453152027 * pow(t, 4) + 1.061405429 * pow(t, 5)) * exp(-(x * x)));
-            o.pvalue = (1.0 - erf_) / 2.0;
-            c.calls.push_back(o);
-        }
+        };
+        const size_t nc = flat.size(), T = std::max<size_t>(1, std::min<size_t>(8, std::min<size_t>(std::thread::hardware_concurrency(), nc / 64 + 1)));
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < T; t++) pool.emplace_back(work, nc * t / T, nc * (t + 1) / T);
+        work(0, nc / T);
+        for (auto &x : pool) x.join();
     }
-    mark("gather+copy number");
     out->n_calls = (int64_t)c.calls.size(); out->calls = c.calls.data();
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    d2h += (int64_t)sizeof(cnv::PreOut) * n_blk + 8 * HIST_ALL + (int64_t)sizeof(RepRec) * n_rep + (int64_t)sizeof(Sample) * n_samples + 4 * P + 16 * words +
+           8 * ((int64_t)seed_tot_all) + 16 * (int64_t)n_spec_all + 5 * (int64_t)(g_depth.size() + rp_depth.size()) + 16 * (int64_t)n_len;
+    out->launches = n_launch; out->d2h_bytes = d2h;
     out->ms_device = (float)ms_dev; out->ms_total = (float)ms_total; out->ms_host = (float)(ms_total - ms_dev);
     return 0;
 }

@@ -101,7 +101,8 @@ class CCnvResult(C.Structure):
                 ("biased_repeat", C.c_int32), ("n_sample_blocks", C.c_int32), ("n_repeats", C.c_int64), ("n_samples", C.c_int64),
                 ("n_frames", C.c_int64), ("win_sd", C.c_void_p), ("win_cnt", C.c_void_p), ("bin_ave", C.c_void_p), ("bin_sd", C.c_void_p),
                 ("bin_del_thr", C.c_void_p), ("bin_dup_thr", C.c_void_p), ("bin_n", C.c_void_p),
-                ("ms_device", C.c_float), ("ms_host", C.c_float), ("ms_total", C.c_float)]
+                ("ms_device", C.c_float), ("ms_host", C.c_float), ("ms_total", C.c_float), ("launches", C.c_int32), ("reserved", C.c_int32),
+                ("d2h_bytes", C.c_int64)]
 
 
 @dataclass
@@ -125,6 +126,8 @@ class CnvResult:
     ms_device: float
     ms_host: float
     ms_total: float
+    launches: int = 0
+    d2h_bytes: int = 0
 
 
 @dataclass
@@ -238,7 +241,7 @@ class Chromosome:
                          win_sd=arr(r.win_sd, nw, np.float64), win_cnt=arr(r.win_cnt, nw, np.int64),
                          ave=arr(r.bin_ave, 202, np.float64).reshape(2, 101), sd=arr(r.bin_sd, 202, np.float64).reshape(2, 101),
                          del_thr=arr(r.bin_del_thr, 202, np.float64).reshape(2, 101), dup_thr=arr(r.bin_dup_thr, 202, np.float64).reshape(2, 101),
-                         n=arr(r.bin_n, 202, np.int64).reshape(2, 101), ms_device=r.ms_device, ms_host=r.ms_host, ms_total=r.ms_total)
+                         n=arr(r.bin_n, 202, np.int64).reshape(2, 101), ms_device=r.ms_device, ms_host=r.ms_host, ms_total=r.ms_total, launches=r.launches, d2h_bytes=r.d2h_bytes)
 
     def cnv_fetch(self, what: str, p0: int = 0, p1: Optional[int] = None) -> np.ndarray:
         sel, dt = {"z": (0, np.float64), "mask": (1, np.uint8), "mq_mean": (2, np.uint8), "depth": (3, np.int32)}[what]

@@ -128,6 +128,9 @@ typedef struct gromgpu_cnv_result {
     const double  *bin_ave, *bin_sd, *bin_del_thr, *bin_dup_thr;   /* [2][101]: high-MAPQ list, low-MAPQ list per GC bin */
     const int64_t *bin_n;               /* [2][101] */
     float   ms_device, ms_host, ms_total;
+    int32_t launches;                   /* kernels launched by this call */
+    int32_t reserved;
+    int64_t d2h_bytes;                  /* bytes copied device -> host by this call (packed records, seed tables, samples ...) */
 } gromgpu_cnv_result;
 int gromgpu_chr_cnv(gromgpu_chr *h, const double *pval2sd_pval, const double *pval2sd_sd, int pval2sd_len, int ploidy, gromgpu_cnv_result *out);
 /* Parity access after gromgpu_chr_cnv: what = 0 z list (double), 1 mask (uint8), 2 mean MAPQ (uint8), 3 depth (int32); positions [p0, p1) */
