@@ -162,3 +162,33 @@ def vcf_cnv(params, chr_name: str, calls: np.ndarray) -> str:
     """Read-depth CNV records (-V filter + text, reference src/GROM.c:17197-17500) from gromgpu_chr_cnv's calls."""
     a = np.ascontiguousarray(calls)
     return _vcf("gromhost_vcf_cnv", params, chr_name, np.zeros(1, dtype=np.uint8), C.c_int64(0), C.c_void_p(a.ctypes.data), C.c_int64(len(a)))
+
+
+class CSvLists(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_dup", "n_del", "n_inv_f", "n_inv_r", "n_ins", "n_ctx_f", "n_ctx_r")] + \
+               [(n, C.c_void_p) for n in ("dup", "del_", "inv_f", "inv_r", "ins", "ctx_f", "ctx_r")]
+
+
+def sv_lists(params, events: np.ndarray) -> dict:
+    """Candidate lists of the structural-variant scan (reference state at src/GROM.c:15164) from the gate events:
+    {"dup","del","inv_f","inv_r","ins": SV_PAIR_DTYPE arrays, "ctx_f","ctx_r": SV_EVENT_DTYPE arrays}."""
+    from .params import SV_EVENT_DTYPE, SV_PAIR_DTYPE
+    L = lib()
+    L.gromhost_sv_lists.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(CSvLists)]
+    L.gromhost_sv_lists_free.argtypes = [C.POINTER(CSvLists)]
+    L.gromhost_sv_lists_free.restype = None
+    ev = np.ascontiguousarray(events, dtype=SV_EVENT_DTYPE)
+    out = CSvLists()
+    if L.gromhost_sv_lists(C.byref(params), ev.ctypes.data, len(ev), C.byref(out)) != 0:
+        raise RuntimeError("gromhost_sv_lists failed")
+
+    def take(ptr, n, dt):
+        if not n:
+            return np.zeros(0, dtype=dt)
+        return np.frombuffer((C.c_char * (n * dt.itemsize)).from_address(ptr), dtype=dt, count=n).copy()
+    res = {"dup": take(out.dup, out.n_dup, SV_PAIR_DTYPE), "del": take(out.del_, out.n_del, SV_PAIR_DTYPE),
+           "inv_f": take(out.inv_f, out.n_inv_f, SV_PAIR_DTYPE), "inv_r": take(out.inv_r, out.n_inv_r, SV_PAIR_DTYPE),
+           "ins": take(out.ins, out.n_ins, SV_PAIR_DTYPE), "ctx_f": take(out.ctx_f, out.n_ctx_f, SV_EVENT_DTYPE),
+           "ctx_r": take(out.ctx_r, out.n_ctx_r, SV_EVENT_DTYPE)}
+    L.gromhost_sv_lists_free(C.byref(out))
+    return res

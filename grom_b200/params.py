@@ -28,7 +28,7 @@ class Params(C.Structure):
                 min_snv=3, min_disc=3, sc_min=1, rmdup=0, rmdup_list_len=10000, splitread=1, max_split_loss=20, min_sr_len=30,
                 overlap_mult=1, other_len=50, read_name_len=50, indel_i_seq_len=50, max_cigar_ops=1000, ploidy=2, gender=0,
                 max_trials=1000, add_factor=6, min_snv_ratio=0.2, min_ave_bq=15, snv_rd_min_factor=1.75,
-                high_cov_min_snv_ratio=0.4, pval_threshold1=0.01, pval_threshold=0.001, pval_insertion1=0.01,
+                high_cov_min_snv_ratio=0.4, pval_threshold1=0.001, pval_threshold=0.001, pval_insertion1=0.01,
                 pval_insertion=1e-10, rd_pval_threshold=1e-9, max_evidence_ratio=0.25, min_sv_ratio=0.05,
                 min_indel_ratio=0.125, windows_sampling_factor=2, rand_seed=1, min_rd_window_len=100,
                 max_rd_window_len=10000, sample_lists_len=100000, reserved0=0)
@@ -76,6 +76,16 @@ assert INS_CAND_DTYPE.itemsize == 104, INS_CAND_DTYPE.itemsize
 DEL_EVENT_DTYPE = np.dtype([("pos", np.int32), ("kind", np.int32), ("pr", np.float64), ("hez", np.float64), ("conc", np.int32),
                             ("weight", np.int32), ("rd", np.int32), ("sc", np.int32), ("other_len", np.int32), ("rdist", np.int32)], align=True)
 assert DEL_EVENT_DTYPE.itemsize == 48, DEL_EVENT_DTYPE.itemsize
+
+SV_EVENT_DTYPE = np.dtype([("pos", np.int32), ("cls", np.int32), ("binom", np.float64), ("hez", np.float64), ("dist", np.float64),
+                           ("weight", np.int32), ("rd", np.int32), ("conc", np.int32), ("read_start", np.int32), ("read_end", np.int32),
+                           ("other_len", np.int32), ("mchr", np.int32), ("reserved", np.int32)], align=True)
+assert SV_EVENT_DTYPE.itemsize == 64, SV_EVENT_DTYPE.itemsize
+SV_CLASSES = ["del_f", "del_r", "dup_f", "dup_r", "inv_f1", "inv_r1", "inv_f2", "inv_r2", "ctx_f", "ctx_r", "ins_l", "ins_r"]
+SV_SIDE_DTYPE = np.dtype([("pos", np.int32), ("weight", np.int32), ("rd", np.int32), ("conc", np.int32), ("read_start", np.int32),
+                          ("read_end", np.int32), ("other_len", np.int32), ("reserved", np.int32), ("binom", np.float64), ("hez", np.float64)], align=True)
+SV_PAIR_DTYPE = np.dtype([("start", SV_SIDE_DTYPE), ("end", SV_SIDE_DTYPE), ("dist", np.float64)], align=True)
+assert SV_SIDE_DTYPE.itemsize == 48 and SV_PAIR_DTYPE.itemsize == 104, (SV_SIDE_DTYPE.itemsize, SV_PAIR_DTYPE.itemsize)
 
 CNV_CALL_DTYPE = np.dtype([("start", np.int64), ("end", np.int64), ("kind", np.int32), ("reserved", np.int32), ("z", np.float64),
                            ("pvalue", np.float64), ("cn", np.float64), ("cn_sd", np.float64)], align=True)

@@ -49,7 +49,7 @@ typedef struct grom_params {
     double  min_ave_bq;         /* -x  g_min_ave_bq          15 */
     double  snv_rd_min_factor;  /*     g_snv_rd_min_factor 1.75 */
     double  high_cov_min_snv_ratio; /* g_high_cov_min_snv_ratio 0.4 */
-    double  pval_threshold1;    /*     g_pval_threshold1   0.01 (= -v copy, src/GROM.c:22101) */
+    double  pval_threshold1;    /*     g_pval_threshold1   declared 0.01 but overwritten with the -v value at start-up (src/GROM.c:22101): 0.001 */
     double  pval_threshold;     /* -v  g_pval_threshold   0.001 */
     double  pval_insertion1;    /*     g_pval_insertion1   0.01 */
     double  pval_insertion;     /* -e  g_pval_insertion   1e-10 */
@@ -84,7 +84,7 @@ static inline void grom_params_default(grom_params *p)
     p->overlap_mult = 1; p->other_len = 50; p->read_name_len = 50; p->indel_i_seq_len = 50; p->max_cigar_ops = 1000;
     p->ploidy = 2; p->gender = 0; p->max_trials = 1000; p->add_factor = 6;
     p->min_snv_ratio = 0.2; p->min_ave_bq = 15; p->snv_rd_min_factor = 1.75; p->high_cov_min_snv_ratio = 0.4;
-    p->pval_threshold1 = 0.01; p->pval_threshold = 0.001; p->pval_insertion1 = 0.01; p->pval_insertion = 1e-10;
+    p->pval_threshold1 = 0.001; p->pval_threshold = 0.001; p->pval_insertion1 = 0.01; p->pval_insertion = 1e-10;
     p->rd_pval_threshold = 1e-9; p->max_evidence_ratio = 0.25; p->min_sv_ratio = 0.05; p->min_indel_ratio = 0.125;
     p->windows_sampling_factor = 2; p->rand_seed = 1; p->min_rd_window_len = 100; p->max_rd_window_len = 10000;
     p->sample_lists_len = 100000; p->reserved0 = 0;
@@ -157,6 +157,37 @@ typedef struct grom_del_event {
     int32_t other_len;
     int32_t rdist;              /* indel_d_rdist (end events) */
 } grom_del_event;
+
+/* ---- structural-variant scan (src/GROM.c:11750-13541) ----
+ * One gate event = one (position, class) whose cluster passes the binomial gate; classes 0-9 are the breakpoint clusters in the order
+ * del_f del_r dup_f dup_r inv_f1 inv_r1 inv_f2 inv_r2 ctx_f ctx_r, 10 / 11 the insertion gates (soft clips + short pairs, left / right). */
+enum { GROM_SV_DEL_F = 0, GROM_SV_DEL_R, GROM_SV_DUP_F, GROM_SV_DUP_R, GROM_SV_INV_F1, GROM_SV_INV_R1, GROM_SV_INV_F2, GROM_SV_INV_R2,
+       GROM_SV_CTX_F, GROM_SV_CTX_R, GROM_SV_INS_L, GROM_SV_INS_R, GROM_SV_CLASSES };
+typedef struct grom_sv_event {
+    int32_t pos;                /* 0-based */
+    int32_t cls;                /* GROM_SV_* */
+    double  binom;              /* mq table value */
+    double  hez;                /* hez table value; 2.0 = side evidence ratio above g_max_evidence_ratio (not computed) */
+    double  dist;               /* cluster running-mean distance; ctx: signed mate position */
+    int32_t weight;             /* cluster weight (ins gates: the `ins` range-add value) */
+    int32_t rd, conc;
+    int32_t read_start, read_end;
+    int32_t other_len;
+    int32_t mchr;               /* ctx: mate contig */
+    int32_t reserved;
+} grom_sv_event;
+
+/* one side of a breakpoint pair as the reference's *_list_start_* / *_list_end_* arrays hold it */
+typedef struct grom_sv_side {
+    int32_t pos;                /* -1 = side not found */
+    int32_t weight, rd, conc, read_start, read_end, other_len, reserved;
+    double  binom, hez;
+} grom_sv_side;
+/* entry of cdp_dup_list / cdp_del_list / cdp_inv_f_list / cdp_inv_r_list / cdp_ins_list before the list -> list2 merge */
+typedef struct grom_sv_pair {
+    grom_sv_side start, end;
+    double dist;
+} grom_sv_pair;
 
 /* one read-depth CNV call of detect_del_dup (src/GROM.c:19654-19658 / 19988-19992) with its copy number (20071-20224) and the
  * reference's p-value (17163-17190) */

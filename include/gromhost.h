@@ -79,6 +79,17 @@ int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const 
 int64_t gromhost_vcf_cnv(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
                          const grom_cnv_call *calls, int64_t n, char *buf, int64_t cap);
 
+/* ---- structural-variant candidate lists (grom_b200/host/svlists.c): the state of cdp_dup_list / cdp_del_list / cdp_inv_f_list /
+ * cdp_inv_r_list / cdp_ins_list / cdp_ctx_f_list / cdp_ctx_r_list at src/GROM.c:15164, rebuilt from the gate events of
+ * gromgpu_chr_result (any order; sorted into scan order here).  Arrays are malloc'ed, release with gromhost_sv_lists_free. */
+typedef struct gromhost_sv_lists_t {
+    int64_t n_dup, n_del, n_inv_f, n_inv_r, n_ins, n_ctx_f, n_ctx_r;
+    grom_sv_pair *dup, *del, *inv_f, *inv_r, *ins;
+    grom_sv_event *ctx_f, *ctx_r;
+} gromhost_sv_lists_t;
+int  gromhost_sv_lists(const grom_params *p, const grom_sv_event *events, int64_t n_events, gromhost_sv_lists_t *out);
+void gromhost_sv_lists_free(gromhost_sv_lists_t *l);
+
 #ifdef __cplusplus
 }
 #endif

@@ -248,11 +248,12 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
         if (scan_last < scan_first) scan_last = scan_first;
         if (scan_last >= P) scan_last = P - 1;
         out->scan_first = scan_first; out->scan_last = (int32_t)scan_last;
-        if (out->lookahead_lseq) {
+        int32_t *la = out->lookahead_lseq ? out->lookahead_lseq : (int32_t *)calloc((size_t)P, sizeof(int32_t));
+        {
             int64_t j = i0;
             for (int64_t x = scan_first; x <= scan_last; x++) {
                 while (j < n && (int64_t)b->pos[j] - (int64_t)p->overlap_mult * p->insert_max <= x) j++;
-                out->lookahead_lseq[x] = (j < n) ? b->l_qseq[j] : last_lseq_after_clip;
+                la[x] = (j < n) ? b->l_qseq[j] : last_lseq_after_clip;
             }
         }
         /* ---- SNV gate per scanned position, src/GROM.c:11096-11199 */
@@ -337,6 +338,57 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
                 out->n_del++;
             }
         }
+        /* ---- structural-variant gates per scanned position, src/GROM.c:11750-13541 (events in the reference's evaluation order:
+         * insertion left / right, ctx_f, ctx_r, dup_r, dup_f, del_f, del_r, inv_f1, inv_f2, inv_r1, inv_r2) */
+        out->n_sv = 0;
+        for (int64_t x = scan_first; x <= scan_last; x++) {
+            const int af = p->add_factor, rd = A.a[GA_RD][x], mt = p->max_trials;
+            int ol = -1;
+#define SV_EMIT(CLS, BIN, HEZ, DIST, WGT, RS, RE, MCHR) do {                                                                      \
+                if (ol < 0) { ol = 0; if (S.oth[x]) while (ol < p->other_len && S.oth[x][ol].type != OTHER_EMPTY) ol++; }            \
+                if (out->sv_ev && out->n_sv < out->sv_cap) {                                                                        \
+                    grom_sv_event *e = &out->sv_ev[out->n_sv]; memset(e, 0, sizeof(*e));                                            \
+                    e->pos = (int32_t)x; e->cls = (CLS); e->binom = (BIN); e->hez = (HEZ); e->dist = (DIST); e->weight = (WGT);     \
+                    e->rd = rd; e->conc = A.a[GA_CONC][x]; e->read_start = (RS); e->read_end = (RE); e->other_len = ol; e->mchr = (MCHR); \
+                }                                                                                                                   \
+                out->n_sv++; } while (0)
+            if (rd + A.a[GA_SC_RD][x] > 0) {
+                /* insertions: soft clips + short-insert pairs (+ mate-unmapped reads in the table column), src/GROM.c:11750-11961 */
+                for (int side = 0; side < 2; side++) {
+                    const int sc = A.a[side ? GA_SC_RIGHT : GA_SC_LEFT][x], scrd = rd + A.a[side ? GA_SC_RIGHT_RD : GA_SC_LEFT_RD][x];
+                    const int mu = A.a[side ? GA_MUNMAPPED_F : GA_MUNMAPPED_R][x], ins = A.a[GA_INS][x];
+                    if (!((sc + ins) / af >= p->min_disc) || scrd > mt) continue;
+                    const double bin = ((mu + sc + ins) / af < scrd) ? mq_tbl[(size_t)scrd * TD + (mu + sc + ins) / af] : mq_tbl[(size_t)scrd * TD + scrd];
+                    if (bin <= p->pval_insertion1) SV_EMIT(GROM_SV_INS_L + side, bin, 2.0, 0.0, ins, 0, 0, 0);
+                }
+            }
+            if (rd > 0) {
+                static const int order[10] = { CL_CTX_F, CL_CTX_R, CL_DUP_R, CL_DUP_F, CL_DEL_F, CL_DEL_R, CL_INV_F1, CL_INV_F2, CL_INV_R1, CL_INV_R2 };
+                for (int oi = 0; oi < 10; oi++) {
+                    const int c = order[oi], fwd = (c == CL_CTX_F || c == CL_DUP_F || c == CL_DEL_F || c == CL_INV_F1 || c == CL_INV_F2);
+                    const int w = S.cw[c][x];
+                    if (!(w / af >= p->min_disc)) continue;
+                    if (fwd ? !((int)x - S.cre[c][x] < p->insert_mean) : !(S.crs[c][x] + la[x] - (int)x < p->insert_mean)) continue;
+                    const int side = fwd ? A.a[GA_SC_RIGHT][x] + A.a[GA_MUNMAPPED_F][x] : A.a[GA_SC_LEFT][x] + A.a[GA_MUNMAPPED_R][x];
+                    double bin, hz = 2.0;
+                    if (rd > mt) {
+                        bin = mq_tbl[(size_t)mt * TD + w * mt / (af * rd)];
+                        if ((float)side / (float)w <= p->max_evidence_ratio)
+                            hz = ((w + side) / af < rd) ? hez_tbl[(size_t)mt * TD + (w + side) * mt / (af * rd)] : hez_tbl[(size_t)mt * TD + mt];
+                    } else {
+                        bin = mq_tbl[(size_t)rd * TD + w / af];
+                        /* ctx_r tests the ctx_f ratio here (src/GROM.c:12074) */
+                        const float ratio = c == CL_CTX_R ? (float)(A.a[GA_SC_RIGHT][x] + A.a[GA_MUNMAPPED_F][x]) / (float)S.cw[CL_CTX_F][x] : (float)side / (float)w;
+                        if (ratio <= p->max_evidence_ratio)
+                            hz = ((w + side) / af < rd) ? hez_tbl[(size_t)rd * TD + (w + side) / af] : hez_tbl[(size_t)rd * TD + rd];
+                    }
+                    if (bin <= p->pval_threshold1)
+                        SV_EMIT(c, bin, hz, S.cdist[c][x], w, S.crs[c][x], S.cre[c][x], c >= CL_CTX_F ? S.cmchr[c - CL_CTX_F][x] : 0);
+                }
+            }
+#undef SV_EMIT
+        }
+        if (!out->lookahead_lseq) free(la);
         /* ---- mean depth for the emission filter, src/GROM.c:15035-15043.  Upper bound = position of
          * window index 0 when the loop ends: (scan_last+1) - index(scan_last), where the window index
          * advances once per loop iteration (including one per skipped leading read) and wraps from

@@ -44,6 +44,8 @@ typedef struct oracle_chr_out {
     int64_t  ins_cap, n_ins;
     grom_del_event *del_ev;     /* small-deletion scan events in scan order (src/GROM.c:11454-11745), caller-allocated or NULL */
     int64_t  del_cap, n_del;
+    grom_sv_event *sv_ev;       /* structural-variant gate events in scan order (src/GROM.c:11750-13541), caller-allocated or NULL */
+    int64_t  sv_cap, n_sv;
 } oracle_chr_out;
 
 int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *fasta, int64_t chr_len,

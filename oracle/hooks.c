@@ -114,3 +114,46 @@ void grom_hook_cnv(const char *chr, long len, const double *z, const int *mask, 
     for (i = 0; i < n_dup; i++) { fwrite(&dup_s[i], 8, 1, f); fwrite(&dup_e[i], 8, 1, f); fwrite(&dup_z[i], 8, 1, f); fwrite(&dup_cn[i], 8, 1, f); fwrite(&dup_cs[i], 8, 1, f); }
     fclose(f);
 }
+
+/* svl_<name>_<chr>.bin: int64 n, then column by column (n values each): int32 start, end; double dist, start_binom, start_hez; int32
+ * start_conc, start_rd, start_weight, start_read_start, start_read_end, start_other_len; double end_binom, end_hez; int32 end_conc,
+ * end_rd, end_weight, end_read_start, end_read_end, end_other_len */
+static FILE *open_list(const char *name, const char *chr)
+{
+    char tag[64];
+    snprintf(tag, sizeof(tag), "svl_%s", name);
+    return open_for(tag, chr);
+}
+void grom_hook_svpairs(const char *chr, const char *name, long n, const int *start, const int *end, const double *dist,
+                       const double *sb, const double *sh, const int *sc, const int *srd, const int *sw, const int *srs, const int *sre, const int *sol,
+                       const double *eb, const double *eh, const int *ec, const int *erd, const int *ew, const int *ers, const int *ere, const int *eol)
+{
+    FILE *f = open_list(name, chr);
+    fwrite(&n, 8, 1, f);
+    fwrite(start, 4, n, f); fwrite(end, 4, n, f); fwrite(dist, 8, n, f); fwrite(sb, 8, n, f); fwrite(sh, 8, n, f);
+    fwrite(sc, 4, n, f); fwrite(srd, 4, n, f); fwrite(sw, 4, n, f); fwrite(srs, 4, n, f); fwrite(sre, 4, n, f); fwrite(sol, 4, n, f);
+    fwrite(eb, 8, n, f); fwrite(eh, 8, n, f);
+    fwrite(ec, 4, n, f); fwrite(erd, 4, n, f); fwrite(ew, 4, n, f); fwrite(ers, 4, n, f); fwrite(ere, 4, n, f); fwrite(eol, 4, n, f);
+    fclose(f);
+}
+/* svl_ctx_?_<chr>.bin: int64 n; int32 pos; double binom, hez; int32 mchr, mpos, conc, rd, weight, read_start, read_end, other_len */
+void grom_hook_svctx(const char *chr, const char *name, long n, const int *pos, const double *b, const double *h, const int *mchr, const int *mpos,
+                     const int *conc, const int *rd, const int *w, const int *rs, const int *re, const int *ol)
+{
+    FILE *f = open_list(name, chr);
+    fwrite(&n, 8, 1, f);
+    fwrite(pos, 4, n, f); fwrite(b, 8, n, f); fwrite(h, 8, n, f); fwrite(mchr, 4, n, f); fwrite(mpos, 4, n, f); fwrite(conc, 4, n, f);
+    fwrite(rd, 4, n, f); fwrite(w, 4, n, f); fwrite(rs, 4, n, f); fwrite(re, 4, n, f); fwrite(ol, 4, n, f);
+    fclose(f);
+}
+/* svl_ins_<chr>.bin: int64 n; int32 start, end; double start_binom, end_binom; int32 start_ins, end_ins, start_rd, end_rd, start_conc,
+ * end_conc, start_other_len, end_other_len */
+void grom_hook_svins(const char *chr, long n, const int *start, const int *end, const double *sb, const double *eb, const int *si, const int *ei,
+                     const int *srd, const int *erd, const int *sc, const int *ec, const int *sol, const int *eol)
+{
+    FILE *f = open_list("ins", chr);
+    fwrite(&n, 8, 1, f);
+    fwrite(start, 4, n, f); fwrite(end, 4, n, f); fwrite(sb, 8, n, f); fwrite(eb, 8, n, f); fwrite(si, 4, n, f); fwrite(ei, 4, n, f);
+    fwrite(srd, 4, n, f); fwrite(erd, 4, n, f); fwrite(sc, 4, n, f); fwrite(ec, 4, n, f); fwrite(sol, 4, n, f); fwrite(eol, 4, n, f);
+    fclose(f);
+}

@@ -14,6 +14,7 @@
  *   reads_<chr>.bin : per read that reaches the -M test   int32 pos, mpos, tlen, flag, mapq, keep
  *   depth_<chr>.bin : int32 rd_mq[P], rd_rd[P], rd_low_mq_rd[P]   (before the in-place mean, src/GROM.c:16637)
  *   gc_<chr>.bin    : int32 gc_weighted[P], acgt_weighted[P]
+ *   svl_<list>_<chr>.bin: candidate lists at the end of the per-position scan (src/GROM.c:15164), see grom_hook_svpairs / _svctx / _svins
  *   cnvpre_<chr>.bin: state after the CNV pre-statistics (src/GROM.c:16633-16990), see grom_hook_cnvpre
  *   cnv_<chr>.bin   : state at the end of detect_del_dup (src/GROM.c:20348), see grom_hook_cnv
  */
@@ -29,6 +30,13 @@ void grom_hook_read(const char *chr, int pos, int mpos, int tlen, int flag, int 
 void grom_hook_depth(const char *chr, long len, const int *mq, const int *rd, const int *low);
 void grom_hook_gc(const char *chr, long len, const int *gc, const int *acgt);
 void grom_hook_srand(unsigned seed);
+void grom_hook_svpairs(const char *chr, const char *name, long n, const int *start, const int *end, const double *dist,
+                       const double *sb, const double *sh, const int *sc, const int *srd, const int *sw, const int *srs, const int *sre, const int *sol,
+                       const double *eb, const double *eh, const int *ec, const int *erd, const int *ew, const int *ers, const int *ere, const int *eol);
+void grom_hook_svctx(const char *chr, const char *name, long n, const int *pos, const double *b, const double *h, const int *mchr, const int *mpos,
+                     const int *conc, const int *rd, const int *w, const int *rs, const int *re, const int *ol);
+void grom_hook_svins(const char *chr, long n, const int *start, const int *end, const double *sb, const double *eb, const int *si, const int *ei,
+                     const int *srd, const int *erd, const int *sc, const int *ec, const int *sol, const int *eol);
 void grom_hook_cnvpre(const char *chr, long n_nblk, const long *nb_s, const long *nb_e, long n_rep, const int *rep_t, const long *rep_s,
                       const long *rep_e, double chr_ave, double chr_sd, const double *rep_ave, const double *rep_sd, const long *rep_cnt,
                       int biased, double blk_ave, long n_sblk, const long *sb_s, const long *sb_e);
@@ -85,6 +93,20 @@ void grom_hook_cnv(const char *chr, long len, const double *z, const int *mask, 
 /* inserted immediately before reference src/GROM.c:1883 (end of the FASTA pre-pass) */
 #define GROM_HOOK_GC() do { if (g_hook_on) grom_hook_gc(cdp_chr_name, caf_chr_fasta_len, caf_one_base_rd_gc_weighted, caf_one_base_rd_acgt_weighted); } while (0)
 
+
+/* inserted immediately before reference src/GROM.c:15164 (per-position scan finished, candidate lists complete, before list -> list2) */
+#define GH_PAIRS(NAME, L, SW, EW) grom_hook_svpairs(cdp_chr_name, NAME, L##_index, L##_start, L##_end, L##_dist, L##_start_binom_cdf, \
+    L##_start_hez_binom_cdf, L##_start_conc, L##_start_rd, L##_start_##SW, L##_start_read_start, L##_start_read_end, L##_start_other_len, \
+    L##_end_binom_cdf, L##_end_hez_binom_cdf, L##_end_conc, L##_end_rd, L##_end_##EW, L##_end_read_start, L##_end_read_end, L##_end_other_len)
+#define GH_CTX(NAME, L, W) grom_hook_svctx(cdp_chr_name, NAME, L##_index, L, L##_binom_cdf, L##_hez_binom_cdf, L##_mchr, L##_mpos, L##_conc, \
+    L##_rd, L##_##W, L##_read_start, L##_read_end, L##_other_len)
+#define GROM_HOOK_SVLISTS() do { if (g_hook_on) { \
+    GH_PAIRS("dup", cdp_dup_list, dup_r, dup_f); GH_PAIRS("del", cdp_del_list, del_f, del_r); \
+    GH_PAIRS("inv_f", cdp_inv_f_list, inv, inv); GH_PAIRS("inv_r", cdp_inv_r_list, inv, inv); \
+    GH_CTX("ctx_f", cdp_ctx_f_list, ctx_f); GH_CTX("ctx_r", cdp_ctx_r_list, ctx_r); \
+    grom_hook_svins(cdp_chr_name, cdp_ins_list_index + 1, cdp_ins_list_start, cdp_ins_list_end, cdp_ins_list_start_binom_cdf, cdp_ins_list_end_binom_cdf, \
+        cdp_ins_list_start_ins, cdp_ins_list_end_ins, cdp_ins_list_start_rd, cdp_ins_list_end_rd, cdp_ins_list_start_conc, cdp_ins_list_end_conc, \
+        cdp_ins_list_start_other_len, cdp_ins_list_end_other_len); } } while (0)
 
 /* inserted immediately before reference src/GROM.c:17016 (after the CNV pre-statistics, same block scope) */
 #define GROM_HOOK_CNVPRE() do { if (g_hook_on) grom_hook_cnvpre(cdp_chr_name, caf_n_index, caf_n_blocks_start, caf_n_blocks_end, caf_repeat_index, \

@@ -14,7 +14,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
-from grom_b200.params import DEL_EVENT_DTYPE, GA, GA_COUNT, GA_NAMES, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE  # noqa: E402
+from grom_b200.params import SV_EVENT_DTYPE, DEL_EVENT_DTYPE, GA, GA_COUNT, GA_NAMES, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE  # noqa: E402
 from grom_b200.reads import CReadBatch, ReadBatch  # noqa: E402
 
 REF_DIR = os.path.join(_HERE, "_ref")
@@ -30,7 +30,8 @@ class COut(C.Structure):
                 ("snv", C.c_void_p), ("snv_cap", C.c_int64), ("n_snv", C.c_int64), ("snv_ave_rd", C.c_double),
                 ("cl_w", C.c_void_p), ("cl_rs", C.c_void_p), ("cl_re", C.c_void_p), ("cl_dist", C.c_void_p),
                 ("cl_mchr", C.c_void_p), ("other_len", C.c_void_p), ("ins", C.c_void_p), ("ins_cap", C.c_int64), ("n_ins", C.c_int64),
-                ("del_ev", C.c_void_p), ("del_cap", C.c_int64), ("n_del", C.c_int64)]
+                ("del_ev", C.c_void_p), ("del_cap", C.c_int64), ("n_del", C.c_int64),
+                ("sv_ev", C.c_void_p), ("sv_cap", C.c_int64), ("n_sv", C.c_int64)]
 
 
 _LIB = None
@@ -71,6 +72,7 @@ class OracleResult:
     other_len: np.ndarray = None
     ins: np.ndarray = None      # INS_CAND_DTYPE small-insertion candidates
     del_ev: np.ndarray = None   # DEL_EVENT_DTYPE small-deletion scan events
+    sv_ev: np.ndarray = None    # SV_EVENT_DTYPE structural-variant gate events, scan order
 
     def __getitem__(self, name: str) -> np.ndarray:
         return self.arrays[GA[name]]
@@ -92,6 +94,8 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
     out.ins = ins.ctypes.data; out.ins_cap = len(ins)
     dev = np.zeros(1 << 17, dtype=DEL_EVENT_DTYPE)
     out.del_ev = dev.ctypes.data; out.del_cap = len(dev)
+    sve = np.zeros(1 << 18, dtype=SV_EVENT_DTYPE)
+    out.sv_ev = sve.ctypes.data; out.sv_cap = len(sve)
     cb = batch.as_c()
     fa = np.ascontiguousarray(fasta, dtype=np.uint8)
     rc = lib().oracle_run_chr(C.byref(params), C.byref(cb), fa.ctypes.data_as(C.c_char_p), P,
@@ -101,7 +105,7 @@ def run_chr(params: Params, batch: ReadBatch, fasta: np.ndarray, hez: np.ndarray
     assert out.n_snv <= snv_cap
     return OracleResult(arrays, state[:batch.n_reads], out.scan_first, out.scan_last, look, snv[:out.n_snv].copy(),
                         out.snv_ave_rd, cl_w, cl_rs, cl_re, cl_dist, cl_mchr, other_len, ins[:min(out.n_ins, len(ins))].copy(),
-                        dev[:min(out.n_del, len(dev))].copy())
+                        dev[:min(out.n_del, len(dev))].copy(), sve[:min(out.n_sv, len(sve))].copy())
 
 
 def format_snv_vcf(params: Params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, ave_rd: float) -> str:
@@ -360,3 +364,79 @@ def load_cnv_dump(dump_dir: str, chr_name: str) -> dict:
     rec = np.dtype([("start", np.int64), ("end", np.int64), ("z", np.float64), ("cn", np.float64), ("cs", np.float64)])
     d["dels"] = take(nd, rec); d["dups"] = take(nu, rec)
     return d
+
+
+def load_svlist_dump(dump_dir: str, chr_name: str) -> dict:
+    """The reference's candidate lists at the end of the per-position scan (hook at src/GROM.c:15164), in the product's record layouts
+    (grom_b200.params.SV_PAIR_DTYPE / SV_EVENT_DTYPE).  End sides that were never filled carry uninitialised memory in the reference;
+    they are zeroed here (pos == -1 marks them)."""
+    from grom_b200.params import SV_PAIR_DTYPE
+    out = {}
+
+    def cols(path, spec):
+        raw = np.fromfile(path, dtype=np.uint8)
+        n = int(raw[:8].view(np.int64)[0]); o = 8; r = {}
+        for name, dt in spec:
+            sz = n * np.dtype(dt).itemsize
+            r[name] = raw[o:o + sz].view(dt).copy(); o += sz
+        return n, r
+    i4, f8 = np.int32, np.float64
+    for name in ("dup", "del", "inv_f", "inv_r"):
+        n, c = cols(os.path.join(dump_dir, f"svl_{name}_{chr_name}.bin"),
+                    [("start", i4), ("end", i4), ("dist", f8), ("sb", f8), ("sh", f8), ("sc", i4), ("srd", i4), ("sw", i4), ("srs", i4), ("sre", i4),
+                     ("sol", i4), ("eb", f8), ("eh", f8), ("ec", i4), ("erd", i4), ("ew", i4), ("ers", i4), ("ere", i4), ("eol", i4)])
+        a = np.zeros(n, dtype=SV_PAIR_DTYPE)
+        a["dist"] = c["dist"]
+        for side, pos, pre in (("start", "start", "s"), ("end", "end", "e")):
+            a[side]["pos"] = c[pos]
+            for f, k in (("binom", "b"), ("hez", "h"), ("conc", "c"), ("rd", "rd"), ("weight", "w"), ("read_start", "rs"), ("read_end", "re"), ("other_len", "ol")):
+                a[side][f] = c[pre + k]
+        dead = a["end"]["pos"] == -1
+        for f in ("binom", "hez", "conc", "rd", "weight", "read_start", "read_end", "other_len"):
+            a["end"][f][dead] = 0
+        out[name] = a
+    for name in ("ctx_f", "ctx_r"):
+        n, c = cols(os.path.join(dump_dir, f"svl_{name}_{chr_name}.bin"),
+                    [("pos", i4), ("binom", f8), ("hez", f8), ("mchr", i4), ("mpos", i4), ("conc", i4), ("rd", i4), ("weight", i4), ("read_start", i4),
+                     ("read_end", i4), ("other_len", i4)])
+        a = np.zeros(n, dtype=SV_EVENT_DTYPE)
+        for f in ("pos", "binom", "hez", "mchr", "conc", "rd", "weight", "read_start", "read_end", "other_len"):
+            a[f] = c[f]
+        a["dist"] = c["mpos"]                       # the reference's list keeps (int) of the running mate position
+        a["cls"] = 8 if name == "ctx_f" else 9
+        out[name] = a
+    n, c = cols(os.path.join(dump_dir, f"svl_ins_{chr_name}.bin"),
+                [("start", i4), ("end", i4), ("sb", f8), ("eb", f8), ("si", i4), ("ei", i4), ("srd", i4), ("erd", i4), ("sc", i4), ("ec", i4), ("sol", i4), ("eol", i4)])
+    a = np.zeros(n, dtype=SV_PAIR_DTYPE)
+    for side, pos, pre in (("start", "start", "s"), ("end", "end", "e")):
+        a[side]["pos"] = c[pos]
+        for f, k in (("binom", "b"), ("weight", "i"), ("rd", "rd"), ("conc", "c"), ("other_len", "ol")):
+            a[side][f] = c[pre + k]
+        dead = a[side]["pos"] == -1
+        for f in ("binom", "weight", "rd", "conc", "other_len"):
+            a[side][f][dead] = 0
+    out["ins"] = a
+    return out
+
+
+def normalise_sv_lists(lists: dict) -> dict:
+    """Product lists in the comparable form of load_svlist_dump: unfilled sides zeroed, insertion sides carry no hez / read range,
+    ctx distance truncated like the reference's int list."""
+    out = {}
+    for k, a in lists.items():
+        a = a.copy()
+        if k in ("ctx_f", "ctx_r"):
+            a["dist"] = a["dist"].astype(np.int32)
+            a["reserved"] = 0
+        else:
+            for side in ("start", "end"):
+                dead = a[side]["pos"] == -1
+                for f in ("binom", "hez", "conc", "rd", "weight", "read_start", "read_end", "other_len"):
+                    a[side][f][dead] = 0
+                if k == "ins":
+                    for f in ("hez", "read_start", "read_end"):
+                        a[side][f] = 0
+            if k == "ins":
+                a["dist"] = 0
+        out[k] = a
+    return out

@@ -17,9 +17,10 @@ ap.add_argument("--sa", type=float, default=0.5)
 ap.add_argument("--disc", type=float, default=0.03)
 ap.add_argument("--len", type=int, default=300000)
 ap.add_argument("--sv", type=float, default=10.0)
+ap.add_argument("--svc", type=float, default=0.0, help="planted clusters per Mb of each further SV class")
 a = ap.parse_args()
 spec = synth.SynthSpec(contigs=[("chrA", a.len), ("chrB", a.len // 2), ("chrZ", 50000)], depth=30, seed=a.seed, dup_frac=0.05,
-                       sa_frac=a.sa, disc_frac=a.disc, sv_sites_per_mb=a.sv, munmap_frac=0.01)
+                       sa_frac=a.sa, disc_frac=a.disc, sv_sites_per_mb=a.sv, munmap_frac=0.01, sv_classes=a.svc)
 cs = synth.simulate(spec)
 fa, bam = synth.write_dataset("/tmp/cmpref", cs)
 dump = "/tmp/cmpref_dump"
@@ -75,6 +76,18 @@ with hostlib.Bam(bam) as b:
         if bad.size:
             bad_total += bad.size
             print(f"  other_len mismatches {bad.size} pos {pos[bad[:3]]} mine {r.other_len[pos][bad[:3]]} ref {sd['v'][:, 83][bad[:3]]}  (max ref {sd['v'][:, 83].max()})")
+        # structural-variant candidate lists at the end of the scan: product host stage on the oracle's gate events vs the reference's lists
+        ref_l = po.load_svlist_dump(dump, name)
+        mine_l = po.normalise_sv_lists(hostlib.sv_lists(prm, r.sv_ev))
+        for k in ("dup", "del", "inv_f", "inv_r", "ins", "ctx_f", "ctx_r"):
+            same = len(ref_l[k]) == len(mine_l[k]) and ref_l[k].tobytes() == mine_l[k].tobytes()
+            print(f"  sv list {k:6s} ref {len(ref_l[k]):5d} mine {len(mine_l[k]):5d} identical {same}")
+            if not same:
+                bad_total += 1
+                n = min(len(ref_l[k]), len(mine_l[k]))
+                for i in range(n):
+                    if ref_l[k][i].tobytes() != mine_l[k][i].tobytes():
+                        print("    first difference at", i, "\n     ref ", ref_l[k][i], "\n     mine", mine_l[k][i]); break
 print("TOTAL MISMATCHES", bad_total)
 allrec = [l for l in open("/tmp/cmpref.vcf") if not l.startswith("#")]
 print("reference records:", len(allrec), "of which SV/CNV classes not yet produced:", sum(1 for l in allrec if l.split("\t")[4].startswith("<") and "SSC:ESC" not in l and "SSC:HP" not in l))

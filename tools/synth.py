@@ -63,6 +63,8 @@ class SynthSpec:
     cnv_per_mb: float = 0.0         # planted copy-number segments (alternating loss / gain of one copy, every 4th a full loss)
     cnv_min: int = 20_000
     cnv_max: int = 120_000
+    sv_classes: float = 0.0         # planted clusters per Mb of EACH further class: tandem duplication (RF pairs), inversion (FF and RR pairs),
+                                    # translocation (mates on another contig), insertion (soft clips + unmapped mates + short pairs)
     at_repeats: int = 0             # planted (AT)n runs of 24-60 bp whose coverage is thinned (exercises the biased-repeat path)
     at_repeat_keep: float = 0.3
 
@@ -397,6 +399,60 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
                     pos[ib] = npos; mpos[ia] = npos; tlen[ia] = npos + rl - pos[ia]; tlen[ib] = -tlen[ia]
                     flag[ia] = FPAIRED | FMREVERSE | FREAD1; flag[ib] = FPAIRED | FREVERSE | FREAD2
                     codes[ib, :rl] = hap[0][npos:npos + rl]
+        if spec.sv_classes > 0:
+            other = (tid + 1) % n_contigs
+            n_each = max(1, int(length / 1e6 * spec.sv_classes))
+            for k in range(n_each * 5):
+                kind = k % 5
+                a = int(rng.integers(20000, max(20001, length - 60000))); dl = int(rng.integers(1500, 20000))
+                tgt = int(rng.integers(5000, max(5001, contig_lens[other] - 5000)))
+                lo = np.searchsorted(fs, a - 380); hi2 = np.searchsorted(fs, a - 100)
+                for p in range(lo, hi2):
+                    ia, ib = 2 * p, 2 * p + 1
+                    if ia in cig or ib in cig or (flag[ia] | flag[ib]) & (FUNMAP | FMUNMAP) or mtid[ia] != tid or not (flag[ia] & FPROPER):
+                        continue
+                    if kind == 4:
+                        # insertion breakpoint at a: forward reads start there behind a clipped head, reverse reads end there before a
+                        # clipped tail, both without a mapped mate (the mate sits in the inserted sequence)
+                        if pos[ia] < a < pos[ia] + rl - 20 and a - pos[ia] >= 20:
+                            k0 = a - pos[ia]
+                            cig[ia] = [(CSOFT_CLIP, k0), (CMATCH, rl - k0)]
+                            codes[ia, k0:rl] = hap[0][a:a + rl - k0]
+                            pos[ia] = a
+                            flag[ia] = FPAIRED | FMUNMAP | FREAD1; tlen[ia] = 0; mpos[ia] = a
+                            flag[ib] = FPAIRED | FUNMAP | FREAD2; pos[ib] = a; mpos[ib] = a; tlen[ib] = 0
+                        elif pos[ib] < a < pos[ib] + rl - 20 and a - pos[ib] >= 20:
+                            cig[ib] = [(CMATCH, a - pos[ib]), (CSOFT_CLIP, rl - (a - pos[ib]))]
+                            flag[ib] = FPAIRED | FREVERSE | FMUNMAP | FREAD2; tlen[ib] = 0; mpos[ib] = pos[ib]
+                            flag[ia] = FPAIRED | FUNMAP | FREAD1; pos[ia] = pos[ib]; mpos[ia] = pos[ib]; tlen[ia] = 0
+                        continue
+                    if not (pos[ia] + rl <= a and pos[ib] >= a - 60):
+                        continue
+                    if kind == 0:        # tandem duplication of [a - dl, a): the reverse mate lands near the start of the copy (RF)
+                        npos = a - dl + int(pos[ib] - (a - 60))
+                        if npos < 1000:
+                            continue
+                        pos[ib] = npos; mpos[ia] = npos; tlen[ib] = pos[ia] + rl - npos; tlen[ia] = -tlen[ib]
+                        flag[ia] = FPAIRED | FMREVERSE | FREAD1; flag[ib] = FPAIRED | FREVERSE | FREAD2
+                    elif kind == 1:      # inversion, left breakpoint: both reads forward
+                        npos = a + dl - int(pos[ib] - (a - 60)) - rl
+                        if npos + rl >= length:
+                            continue
+                        pos[ib] = npos; mpos[ia] = npos; tlen[ia] = npos + rl - pos[ia]; tlen[ib] = -tlen[ia]
+                        flag[ia] = FPAIRED | FREAD1; flag[ib] = FPAIRED | FREAD2
+                    elif kind == 2:      # inversion, right breakpoint: both reads reverse
+                        npos = a + dl + int(pos[ib] - (a - 60))
+                        if npos + rl >= length:
+                            continue
+                        pos[ia], pos[ib] = pos[ib], npos
+                        mpos[ia] = pos[ib]; mpos[ib] = pos[ia]; tlen[ia] = pos[ib] + rl - pos[ia]; tlen[ib] = -tlen[ia]
+                        flag[ia] = FPAIRED | FREVERSE | FMREVERSE | FREAD1; flag[ib] = FPAIRED | FREVERSE | FMREVERSE | FREAD2
+                        codes[ia, :rl] = hap[0][pos[ia]:pos[ia] + rl]
+                    else:                # translocation: both mates are reported on the other contig
+                        j = int(rng.integers(0, 120))
+                        mtid[ia] = other; mpos[ia] = tgt + j; tlen[ia] = 0; flag[ia] = FPAIRED | FMREVERSE | FREAD1
+                        mtid[ib] = other; mpos[ib] = tgt + 5000 + j; tlen[ib] = 0; flag[ib] = FPAIRED | FREVERSE | FREAD2
+                    codes[ib, :rl] = hap[0][pos[ib]:pos[ib] + rl]
         truth = {"snv_pos": snv_pos, "snv_het": het, "sv": np.array(truth_sv, dtype=np.int64).reshape(-1, 2), "cnv": cnv_truth}
     else:
         truth = {"snv_pos": snv_pos, "snv_het": het, "cnv": cnv_truth}
