@@ -742,6 +742,96 @@ __global__ void __launch_bounds__(128) k_indel_gate(const int2 *__restrict__ pos
     }
 }
 
+// ---- structural-variant gates (src/GROM.c:11963-13541): the ten breakpoint classes at the positions k_sv_apply listed.  One gate per
+// (position, class): weight, freshness of the supporting reads relative to the scanned position (reverse classes measure it with the
+// length of the look-ahead read, i.e. the first read that starts more than ins_max beyond the position), binomial tail from the mq
+// table, side-evidence-corrected tail from the hez table.  Events are compacted with an atomic counter and sorted on the host.
+struct SvGateArgs {
+    const int32_t *cl_w, *cl_rs, *cl_re, *cl_mchr, *other_len; const double *cl_dist;
+    grom_sv_event *ev; unsigned int cap; unsigned int *n_ev;
+    int64_t i0, n_reads; int last_lseq, last_lseq_applied; const uint8_t *state;
+};
+__device__ __forceinline__ void sv_emit(const SvGateArgs &G, int pos, int cls, double bin, double hez, double dist, int w, int rd, int conc, int rs, int re, int ol, int mchr)
+{
+    const unsigned int k = atomicAdd(G.n_ev, 1u);
+    if (k >= G.cap) return;
+    grom_sv_event e;
+    e.pos = pos; e.cls = cls; e.binom = bin; e.hez = hez; e.dist = dist; e.weight = w; e.rd = rd; e.conc = conc; e.read_start = rs; e.read_end = re;
+    e.other_len = ol; e.mchr = mchr; e.reserved = 0;
+    G.ev[k] = e;
+}
+__global__ void __launch_bounds__(128) k_sv_gate(const int2 *__restrict__ pos_list, const unsigned int *__restrict__ n_list, unsigned int list_cap,
+                                                  DevReads R, int64_t Ppad, const int32_t *__restrict__ arrays, SnvScanArgs sc, SvGateArgs G)
+{
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(*n_list, list_cap)) return;
+    const int2 pk = pos_list[i];
+    const int ip = pk.x, cm = pk.y >> 3;
+    const int64_t p = ip;
+    if (!cm || ip < sc.scan_first || ip > sc.scan_last) return;
+    const int rd = arrays[(int64_t)GA_RD * Ppad + p];
+    if (rd <= 0) return;
+    const int af = c_prm.add_factor, mt = c_prm.max_trials, TD = mt + 1;
+    const int side_f = arrays[(int64_t)GA_SC_RIGHT * Ppad + p] + arrays[(int64_t)GA_MUNMAPPED_F * Ppad + p];
+    const int side_r = arrays[(int64_t)GA_SC_LEFT * Ppad + p] + arrays[(int64_t)GA_MUNMAPPED_R * Ppad + p];
+    int la = -1;                                                      // look-ahead read length, found on first use
+#pragma unroll 1
+    for (int c = 0; c < 10; c++) {
+        if (!((cm >> c) & 1)) continue;
+        const bool fwd = !(c & 1);                                    // del_f dup_f inv_f1 inv_f2 ctx_f sit on even class numbers
+        const int w = G.cl_w[(int64_t)c * Ppad + p], rs = G.cl_rs[(int64_t)c * Ppad + p], re = G.cl_re[(int64_t)c * Ppad + p];
+        if (fwd) { if (!(ip - re < c_prm.insert_mean)) continue; }
+        else {
+            if (la < 0) {
+                // first read index >= i0 whose start exceeds position + ins_max
+                int64_t lo = G.i0, hi = G.n_reads;
+                const int key = ip + c_prm.overlap_mult * c_prm.insert_max;
+                while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (R.pos[m] <= key) lo = m + 1; else hi = m; }
+                la = lo < G.n_reads ? R.l_qseq[lo] : (G.n_reads > 0 && G.state[G.n_reads - 1] == 1 ? G.last_lseq_applied : G.last_lseq);
+            }
+            if (!(rs + la - ip < c_prm.insert_mean)) continue;
+        }
+        const int side = fwd ? side_f : side_r;
+        double bin, hz = 2.0;
+        if (rd > mt) {
+            bin = sc.mqt[(size_t)mt * TD + w * mt / (af * rd)];
+            if ((double)((float)side / (float)w) <= c_prm.max_evidence_ratio)
+                hz = ((w + side) / af < rd) ? sc.hez[(size_t)mt * TD + (w + side) * mt / (af * rd)] : sc.hez[(size_t)mt * TD + mt];
+        } else {
+            bin = sc.mqt[(size_t)rd * TD + w / af];
+            // ctx_r tests the ctx_f ratio in this branch (src/GROM.c:12074)
+            const float ratio = c == GROM_SV_CTX_R ? (float)side_f / (float)G.cl_w[(int64_t)GROM_SV_CTX_F * Ppad + p] : (float)side / (float)w;
+            if ((double)ratio <= c_prm.max_evidence_ratio)
+                hz = ((w + side) / af < rd) ? sc.hez[(size_t)rd * TD + (w + side) / af] : sc.hez[(size_t)rd * TD + rd];
+        }
+        if (bin <= c_prm.pval_threshold1)
+            sv_emit(G, ip, c, bin, hz, G.cl_dist[(int64_t)c * Ppad + p], w, rd, arrays[(int64_t)GA_CONC * Ppad + p], rs, re, G.other_len[p],
+                    c >= GROM_SV_CTX_F ? G.cl_mchr[(int64_t)(c - GROM_SV_CTX_F) * Ppad + p] : 0);
+    }
+}
+// insertion gates (src/GROM.c:11750-11961): soft-clip weight + short-pair range adds on either side, dense over the scanned range
+__global__ void __launch_bounds__(256) k_ins_sv_gate(int64_t Ppad, const int32_t *__restrict__ arrays, SnvScanArgs sc, SvGateArgs G)
+{
+    const int64_t p = sc.scan_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > sc.scan_last) return;
+    const int af = c_prm.add_factor, md = c_prm.min_disc;
+    const int ins = arrays[(int64_t)GA_INS * Ppad + p], scl = arrays[(int64_t)GA_SC_LEFT * Ppad + p], scr = arrays[(int64_t)GA_SC_RIGHT * Ppad + p];
+    const bool l_ok = (scl + ins) / af >= md, r_ok = (scr + ins) / af >= md;
+    if (!l_ok && !r_ok) return;
+    const int rd = arrays[(int64_t)GA_RD * Ppad + p];
+    if (!(rd + arrays[(int64_t)GA_SC_RD * Ppad + p] > 0)) return;
+    const int mt = c_prm.max_trials, TD = mt + 1;
+    for (int side = 0; side < 2; side++) {
+        if (!(side ? r_ok : l_ok)) continue;
+        const int sv = side ? scr : scl, scrd = rd + arrays[(int64_t)(side ? GA_SC_RIGHT_RD : GA_SC_LEFT_RD) * Ppad + p];
+        if (scrd > mt) continue;
+        const int mu = arrays[(int64_t)(side ? GA_MUNMAPPED_F : GA_MUNMAPPED_R) * Ppad + p];
+        const double bin = ((mu + sv + ins) / af < scrd) ? sc.mqt[(size_t)scrd * TD + (mu + sv + ins) / af] : sc.mqt[(size_t)scrd * TD + scrd];
+        if (bin <= c_prm.pval_insertion1)
+            sv_emit(G, (int)p, GROM_SV_INS_L + side, bin, 2.0, 0.0, ins, rd, arrays[(int64_t)GA_CONC * Ppad + p], 0, 0, G.other_len[p], 0);
+    }
+}
+
 // ---- single-pass inclusive prefix sum, in place (decoupled look-back).  4096 elements per CTA.
 #define SCAN_THREADS 256
 #define SCAN_ITEMS 16
@@ -978,6 +1068,8 @@ struct gromgpu_chr {
     grom_ins_cand *d_ins = nullptr; unsigned int ins_cap = 0; std::vector<grom_ins_cand> h_ins;
     int2 *d_ins_pos = nullptr; unsigned int ins_pos_cap = 0;        // (position, slot mask) whose indel slots reach min_disc (compacted by k_sv_apply)
     grom_del_event *d_del = nullptr; unsigned int del_cap = 0; std::vector<grom_del_event> h_del;
+    grom_sv_event *d_svev = nullptr; unsigned int svev_cap = 0; std::vector<grom_sv_event> h_svev;
+    int last_lseq_applied = 0;       // l_qseq of the last read plus its hard clips (the reference's cdp_lseq once that read is applied)
     // SV / indel evidence (sv_evidence.cuh)
     int32_t *d_item_cnt = nullptr; size_t cap_item_cnt = 0;
     SvItem *d_items = nullptr; size_t cap_items = 0;
@@ -1088,7 +1180,7 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
     for (int i = 0; i < B_COUNT; i++) h->rb[i].release();
     cudaFree(h->d_fasta); cudaFree(h->d_arrays); cudaFree(h->d_state); cudaFree(h->d_prep); cudaFree(h->d_tile_first);
     cudaFree(h->d_max_span); cudaFree(h->d_counters); cudaFree(h->d_scan_status); cudaFree(h->d_ticket);
-    cudaFree(h->d_cand); cudaFree(h->d_ncand); cudaFree(h->d_ins); cudaFree(h->d_ins_pos); cudaFree(h->d_del);
+    cudaFree(h->d_cand); cudaFree(h->d_ncand); cudaFree(h->d_ins); cudaFree(h->d_ins_pos); cudaFree(h->d_del); cudaFree(h->d_svev);
     for (int i = 0; i < 12; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     cudaFree(h->d_item_cnt); cudaFree(h->d_items); cudaFree(h->d_sv_tiles); cudaFree(h->d_sv_dirty); cudaFree(h->d_sv_small); cudaFree(h->d_pool);
     cudaFree(h->d_cl_int); cudaFree(h->d_cl_dist);
@@ -1129,6 +1221,14 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
     const int first_pos = grom_first_pos(&g_params);
     for (int64_t i = 0; i < n && b->pos[i] < first_pos; i++) h->n_leading++;
     h->last_pos = b->pos[n - 1]; h->last_lseq = b->l_qseq[n - 1];
+    {
+        // hard clips of the last read extend its length once it is applied (src/GROM.c:6997-7000; first max_cigar_ops operations)
+        int hsum = 0;
+        const uint64_t c0 = b->cigar_off[n - 1];
+        const int nc = std::min<int>(b->n_cigar[n - 1], g_params.max_cigar_ops);
+        for (int k = 0; k < nc; k++) if ((b->cigar[c0 + k] & 15) == 5) hsum += (int)(b->cigar[c0 + k] >> 4);
+        h->last_lseq_applied = h->last_lseq + hsum;
+    }
     h->n_reads += n; h->n_cigar += b->n_cigar_total;
     h->n_slots += (b->n_base_slots + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN;
     h->ran = false;
@@ -1166,6 +1266,7 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     if (!h->d_ins) { h->ins_cap = 1u << 18; CK(cudaMalloc(&h->d_ins, sizeof(grom_ins_cand) * (size_t)h->ins_cap)); }
     if (!h->d_ins_pos) { h->ins_pos_cap = 1u << 20; CK(cudaMalloc(&h->d_ins_pos, sizeof(int2) * (size_t)h->ins_pos_cap)); }
     if (!h->d_del) { h->del_cap = 1u << 19; CK(cudaMalloc(&h->d_del, sizeof(grom_del_event) * (size_t)h->del_cap)); }
+    if (!h->d_svev) { h->svev_cap = (unsigned int)std::min<int64_t>(std::max<int64_t>(h->Ppad / 16, 1 << 16), 1 << 22); CK(cudaMalloc(&h->d_svev, sizeof(grom_sv_event) * (size_t)h->svev_cap)); }
     const int64_t n_cnt_pad = (n + 1023) & ~(int64_t)1023;
     const int64_t n_cnt_tiles = (n_cnt_pad + SCAN_TILE - 1) / SCAN_TILE;
     if ((size_t)n_cnt_pad > h->cap_item_cnt) { cudaFree(h->d_item_cnt); h->cap_item_cnt = (size_t)n_cnt_pad + (size_t)n_cnt_pad / 8; CK(cudaMalloc(&h->d_item_cnt, sizeof(int32_t) * h->cap_item_cnt)); }
@@ -1264,6 +1365,14 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
                                                                                                    h->d_fasta, P, Ppad, h->d_arrays, sca); launches++;
     CK(cudaEventRecord(h->ev[6], s));
     k_indel_gate<<<(h->ins_pos_cap + 127) / 128, 128, 0, s>>>(h->d_ins_pos, (const unsigned int *)(h->d_sv_small + 4), h->ins_pos_cap, R, P, Ppad, h->d_arrays, sca); launches++;
+    {
+        SvGateArgs G;
+        G.cl_w = SD.cl_w; G.cl_rs = SD.cl_rs; G.cl_re = SD.cl_re; G.cl_mchr = SD.cl_mchr; G.other_len = SD.other_len; G.cl_dist = SD.cl_dist;
+        G.ev = h->d_svev; G.cap = h->svev_cap; G.n_ev = h->d_ncand + 3; G.i0 = h->n_leading; G.n_reads = h->n_reads;
+        G.last_lseq = h->last_lseq; G.last_lseq_applied = h->last_lseq_applied; G.state = h->d_state;
+        k_sv_gate<<<(h->ins_pos_cap + 127) / 128, 128, 0, s>>>(h->d_ins_pos, (const unsigned int *)(h->d_sv_small + 4), h->ins_pos_cap, R, Ppad, h->d_arrays, sca, G); launches++;
+        if (scan_last >= scan_first) { k_ins_sv_gate<<<(unsigned)(((int64_t)scan_last - scan_first + 256) / 256), 256, 0, s>>>(Ppad, h->d_arrays, sca, G); launches++; }
+    }
     CK(cudaEventRecord(h->ev[7], s));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(s));
@@ -1320,6 +1429,17 @@ extern "C" int gromgpu_chr_result(gromgpu_chr *h, gromgpu_result *out)
     if (nd) CK(cudaMemcpy(h->h_del.data(), h->d_del, sizeof(grom_del_event) * (size_t)nd, cudaMemcpyDeviceToHost));
     std::sort(h->h_del.begin(), h->h_del.end(), [](const grom_del_event &a, const grom_del_event &b) { return a.pos != b.pos ? a.pos < b.pos : a.kind < b.kind; });
     h->res.n_del = nd; h->res.del_ev = h->h_del.data();
+    unsigned int ns = 0;
+    CK(cudaMemcpy(&ns, h->d_ncand + 3, sizeof(ns), cudaMemcpyDeviceToHost));
+    if (ns > h->svev_cap) return fail("gromgpu_chr_result: %u structural-variant gate events exceed the buffer of %u", ns, h->svev_cap);
+    h->h_svev.resize(ns);
+    if (ns) CK(cudaMemcpy(h->h_svev.data(), h->d_svev, sizeof(grom_sv_event) * (size_t)ns, cudaMemcpyDeviceToHost));
+    {
+        // scan order: by position, then in the order the reference evaluates the gates at one position
+        static const int key[GROM_SV_CLASSES] = { 6, 7, 5, 4, 8, 10, 9, 11, 2, 3, 0, 1 };
+        std::sort(h->h_svev.begin(), h->h_svev.end(), [](const grom_sv_event &a, const grom_sv_event &b) { return a.pos != b.pos ? a.pos < b.pos : key[a.cls] < key[b.cls]; });
+    }
+    h->res.n_sv = ns; h->res.sv_ev = h->h_svev.data();
     *out = h->res;
     return 0;
 }

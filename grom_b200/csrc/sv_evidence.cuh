@@ -505,7 +505,9 @@ __global__ void __launch_bounds__(SV_T) k_sv_apply(const SvItem *__restrict__ it
         if (mask & (1u << CL_INDEL_D_R)) { arrays[(int64_t)GA_INDEL_D_R * Ppad + p] = S.w[CL_INDEL_D_R][t]; arrays[(int64_t)GA_INDEL_D_RDIST * Ppad + p] = S.idist[2][t]; }
         if (mask & (1u << 13)) D.other_len[p] = S.oth_n[t];
         const int af = c_prm.add_factor, md = c_prm.min_disc;
-        const int km = (S.w[CL_INDEL_I][t] / af >= md ? 1 : 0) | (S.w[CL_INDEL_D_F][t] / af >= md ? 2 : 0) | (S.w[CL_INDEL_D_R][t] / af >= md ? 4 : 0);
+        int km = (S.w[CL_INDEL_I][t] / af >= md ? 1 : 0) | (S.w[CL_INDEL_D_F][t] / af >= md ? 2 : 0) | (S.w[CL_INDEL_D_R][t] / af >= md ? 4 : 0);
+#pragma unroll
+        for (int c = 0; c < 10; c++) if (S.w[c][t] / af >= md) km |= 8 << c;            // breakpoint classes whose weight reaches the gate
         if (km) {
             const int k = atomicAdd(D.n_ins_pos, 1);
             if (k < D.ins_pos_cap) D.ins_pos[k] = make_int2(p, km); else atomicExch(D.err, 2);

@@ -14,7 +14,7 @@ from typing import Optional
 
 import numpy as np
 
-from .params import CNV_CALL_DTYPE, DEL_EVENT_DTYPE, GA, GA_COUNT, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE
+from .params import CNV_CALL_DTYPE, DEL_EVENT_DTYPE, SV_EVENT_DTYPE, GA, GA_COUNT, INS_CAND_DTYPE, Params, SNV_CAND_DTYPE
 from .reads import CReadBatch, ReadBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -36,7 +36,7 @@ class Stats(C.Structure):
 
 class CResult(C.Structure):
     _fields_ = [("scan_first", C.c_int32), ("scan_last", C.c_int32), ("n_snv", C.c_int64), ("snv", C.c_void_p),
-                ("snv_ave_rd", C.c_double), ("n_ins", C.c_int64), ("ins", C.c_void_p), ("n_del", C.c_int64), ("del_ev", C.c_void_p)]
+                ("snv_ave_rd", C.c_double), ("n_ins", C.c_int64), ("ins", C.c_void_p), ("n_del", C.c_int64), ("del_ev", C.c_void_p), ("n_sv", C.c_int64), ("sv_ev", C.c_void_p)]
 
 
 def lib() -> C.CDLL:
@@ -138,6 +138,7 @@ class ChrResult:
     snv_ave_rd: float
     ins: np.ndarray = None    # INS_CAND_DTYPE small-insertion candidates, ascending position
     del_ev: np.ndarray = None  # DEL_EVENT_DTYPE small-deletion scan events (position, start before end)
+    sv_ev: np.ndarray = None   # SV_EVENT_DTYPE structural-variant gate events, scan order
 
 
 class Chromosome:
@@ -183,7 +184,12 @@ class Chromosome:
             dev = np.frombuffer(buf, dtype=DEL_EVENT_DTYPE, count=r.n_del).copy()
         else:
             dev = np.zeros(0, dtype=DEL_EVENT_DTYPE)
-        return ChrResult(r.scan_first, r.scan_last, snv, r.snv_ave_rd, ins, dev)
+        if r.n_sv:
+            buf = (C.c_char * (r.n_sv * SV_EVENT_DTYPE.itemsize)).from_address(r.sv_ev)
+            sve = np.frombuffer(buf, dtype=SV_EVENT_DTYPE, count=r.n_sv).copy()
+        else:
+            sve = np.zeros(0, dtype=SV_EVENT_DTYPE)
+        return ChrResult(r.scan_first, r.scan_last, snv, r.snv_ave_rd, ins, dev, sve)
 
     def finish(self) -> ChrResult:
         self.run()

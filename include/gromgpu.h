@@ -63,6 +63,8 @@ typedef struct gromgpu_result {
     const grom_ins_cand *ins;           /* host memory owned by the handle */
     int64_t n_del;                      /* small-deletion scan events (src/GROM.c:11454-11745), by position, start before end */
     const grom_del_event *del_ev;       /* feed to gromhost_vcf_smalldel() */
+    int64_t n_sv;                       /* structural-variant gate events (src/GROM.c:11750-13541) in scan order */
+    const grom_sv_event *sv_ev;         /* feed to gromhost_sv_lists() */
 } gromgpu_result;
 
 /* Select the device, upload both 1001x1001 tables (row-major double) and the parameters.

@@ -101,9 +101,57 @@ def main_cnv():
     shutil.rmtree(tmp)
 
 
+def main_sv():
+    """g3_svlists.npz: candidate lists of the reference at the end of the per-position scan (hook at src/GROM.c:15164) for (a) the
+    committed g1 BAM and (b) a data set with planted clusters of every structural-variant class, stored together with the gate
+    events (the input of the host list builder) so the fixture does not depend on numpy's RNG stream."""
+    from grom_b200 import hostlib
+    from grom_b200.params import Params
+    tmp = tempfile.mkdtemp()
+    out = {}
+    # (a) g1
+    fa = os.path.join(tmp, "g1.fa")
+    with gzip.open(os.path.join(HERE, "g1.fa.gz"), "rb") as f, open(fa, "wb") as g:
+        g.write(f.read())
+    bam = os.path.join(tmp, "g1.bam")
+    shutil.copy(os.path.join(HERE, "g1.bam"), bam); shutil.copy(os.path.join(HERE, "g1.bam.bai"), bam + ".bai")
+    dump = os.path.join(tmp, "dump_g1")
+    po.run_reference(bam, fa, os.path.join(tmp, "g1.vcf"), dump_dir=dump, kind="ref")
+    for name, _ in CONTIGS:
+        for k, v in po.load_svlist_dump(dump, name.lower()).items():
+            out[f"g1_{name.lower()}_{k}"] = v
+    # (b) all classes
+    spec = synth.SynthSpec(contigs=[("chrA", 400_000), ("chrB", 150_000), ("chrZ", 50_000)], depth=30, seed=14, dup_frac=0.05, sa_frac=0.5,
+                           disc_frac=0.03, sv_sites_per_mb=10.0, munmap_frac=0.01, sv_classes=25)
+    cs = synth.simulate(spec)
+    fa2, bam2 = synth.write_dataset(os.path.join(tmp, "g3"), cs)
+    dump2 = os.path.join(tmp, "dump_g3")
+    po.run_reference(bam2, fa2, os.path.join(tmp, "g3.vcf"), dump_dir=dump2, kind="ref")
+    m = po.read_mean_file(bam2)
+    out["g3_mean"] = np.array([m[k] for k in ("insert_mean", "lseq", "insert_min", "insert_max", "mapped_reads")])
+    prm = Params.default(insert_mean=max(m["insert_mean"], m["lseq"]), insert_min=m["insert_min"], insert_max=m["insert_max"], lseq=m["lseq"])
+    hez, mq = po.reference_tables(20)
+    with hostlib.Bam(bam2) as b:
+        for tid, c in enumerate(cs[:2]):
+            r = po.run_chr(prm, b.read_target(tid), c.chars, hez, mq)
+            out[f"g3_{c.name.lower()}_events"] = r.sv_ev
+            ref = po.load_svlist_dump(dump2, c.name.lower())
+            mine = po.normalise_sv_lists(hostlib.sv_lists(prm, r.sv_ev))
+            for k, v in ref.items():
+                assert v.tobytes() == mine[k].tobytes(), (c.name, k)
+                out[f"g3_{c.name.lower()}_{k}"] = v
+            print(c.name, {k: len(v) for k, v in ref.items()})
+    np.savez_compressed(os.path.join(HERE, "g3_svlists.npz"), **out)
+    print("g3_svlists: size %.2f MB" % (os.path.getsize(os.path.join(HERE, "g3_svlists.npz")) / 1e6))
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "cnv":
+    if len(sys.argv) > 1 and sys.argv[1] == "sv":
+        main_sv()
+    elif len(sys.argv) > 1 and sys.argv[1] == "cnv":
         main_cnv()
     else:
         main()
         main_cnv()
+        main_sv()

@@ -40,6 +40,8 @@ def check_against_oracle(prm, batch, fasta, hez, mq, slices=None):
     for f in ("pos", "dist", "pr", "hez", "conc", "weight", "rd", "sc", "other_len", "seq"):
         assert np.array_equal(res.ins[f], ref.ins[f]), ("insertion candidate", f)
     assert np.array_equal(res.del_ev, ref.del_ev), "small-deletion scan events differ"
+    assert len(res.sv_ev) == len(ref.sv_ev), ("structural-variant gate events", len(res.sv_ev), len(ref.sv_ev))
+    assert res.sv_ev.tobytes() == ref.sv_ev.tobytes(), "structural-variant gate events differ"
     if len(ref.snv) or ref.scan_first >= 0:
         assert res.snv_ave_rd == ref.snv_ave_rd or (np.isnan(res.snv_ave_rd) and np.isnan(ref.snv_ave_rd))
     return res, got, state, st, ref
@@ -233,3 +235,21 @@ def test_size_independent_properties_large():
     hom = hom[(hom > prm.first_pos + 200) & (hom < r1.scan_last - 200)]
     called = np.isin(hom, r1.snv["pos"])
     assert called.mean() > 0.97
+
+
+def test_sv_gate_events_all_classes():
+    """Planted clusters of every class (deletion, tandem duplication, both inversion orientations, translocation, insertion): the gate
+    events of the CUDA path equal the oracle's, and the host list builder turns both into the same candidate lists."""
+    spec = synth.SynthSpec(contigs=[("chrA", 400_000), ("chrB", 150_000)], depth=30, seed=14, dup_frac=0.05, sa_frac=0.5, disc_frac=0.03,
+                           sv_sites_per_mb=10.0, munmap_frac=0.01, sv_classes=25)
+    cs = synth.simulate(spec)
+    prm = Params.default(insert_mean=400, insert_min=150, insert_max=530, lseq=150)
+    hez, mq = tables_7digit()
+    seen = set()
+    for c in cs:
+        res = check_against_oracle(prm, c.batch, c.chars, hez, mq)[0]
+        seen |= set(res.sv_ev["cls"].tolist())
+        a = hostlib.sv_lists(prm, res.sv_ev)
+        assert sum(len(v) for v in a.values()) > 0
+        assert (a["dup"]["end"]["pos"] >= 0).any() and (a["del"]["end"]["pos"] >= 0).any()     # pairs were completed
+    assert seen == set(range(12)), seen
