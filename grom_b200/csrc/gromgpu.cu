@@ -751,17 +751,17 @@ struct SvGateArgs {
     grom_sv_event *ev; unsigned int cap; unsigned int *n_ev;
     int64_t i0, n_reads; int last_lseq, last_lseq_applied; const uint8_t *state;
 };
-__device__ __forceinline__ void sv_emit(const SvGateArgs &G, int pos, int cls, double bin, double hez, double dist, int w, int rd, int conc, int rs, int re, int ol, int mchr)
+__device__ __forceinline__ void sv_emit(const SvGateArgs &G, int pos, int cls, double bin, double hez, double dist, int w, int rd, int conc, int rs, int re, int ol, int mchr, int dsum = 0)
 {
     const unsigned int k = atomicAdd(G.n_ev, 1u);
     if (k >= G.cap) return;
     grom_sv_event e;
     e.pos = pos; e.cls = cls; e.binom = bin; e.hez = hez; e.dist = dist; e.weight = w; e.rd = rd; e.conc = conc; e.read_start = rs; e.read_end = re;
-    e.other_len = ol; e.mchr = mchr; e.reserved = 0;
+    e.other_len = ol; e.mchr = mchr; e.reserved = dsum;
     G.ev[k] = e;
 }
 __global__ void __launch_bounds__(128) k_sv_gate(const int2 *__restrict__ pos_list, const unsigned int *__restrict__ n_list, unsigned int list_cap,
-                                                  DevReads R, int64_t Ppad, const int32_t *__restrict__ arrays, SnvScanArgs sc, SvGateArgs G)
+                                                  DevReads R, int64_t P, int64_t Ppad, const int32_t *__restrict__ arrays, SnvScanArgs sc, SvGateArgs G)
 {
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= min(*n_list, list_cap)) return;
@@ -804,9 +804,13 @@ __global__ void __launch_bounds__(128) k_sv_gate(const int2 *__restrict__ pos_li
             if ((double)ratio <= c_prm.max_evidence_ratio)
                 hz = ((w + side) / af < rd) ? sc.hez[(size_t)rd * TD + (w + side) / af] : sc.hez[(size_t)rd * TD + rd];
         }
-        if (bin <= c_prm.pval_threshold1)
+        if (bin <= c_prm.pval_threshold1) {
+            int dsum = 0;
+            if (c >= GROM_SV_INV_F1 && c <= GROM_SV_INV_R2)          // depth around the breakpoint (src/GROM.c:15921-15934)
+                for (int64_t y = max(rs, 0); y < min((int64_t)re + c_prm.lseq, P); y++) dsum += arrays[(int64_t)GA_RD_RD * Ppad + y] + arrays[(int64_t)GA_RD_LOW * Ppad + y];
             sv_emit(G, ip, c, bin, hz, G.cl_dist[(int64_t)c * Ppad + p], w, rd, arrays[(int64_t)GA_CONC * Ppad + p], rs, re, G.other_len[p],
-                    c >= GROM_SV_CTX_F ? G.cl_mchr[(int64_t)(c - GROM_SV_CTX_F) * Ppad + p] : 0);
+                    c >= GROM_SV_CTX_F ? G.cl_mchr[(int64_t)(c - GROM_SV_CTX_F) * Ppad + p] : 0, dsum);
+        }
     }
 }
 // insertion gates (src/GROM.c:11750-11961): soft-clip weight + short-pair range adds on either side, dense over the scanned range
@@ -1370,7 +1374,7 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
         G.cl_w = SD.cl_w; G.cl_rs = SD.cl_rs; G.cl_re = SD.cl_re; G.cl_mchr = SD.cl_mchr; G.other_len = SD.other_len; G.cl_dist = SD.cl_dist;
         G.ev = h->d_svev; G.cap = h->svev_cap; G.n_ev = h->d_ncand + 3; G.i0 = h->n_leading; G.n_reads = h->n_reads;
         G.last_lseq = h->last_lseq; G.last_lseq_applied = h->last_lseq_applied; G.state = h->d_state;
-        k_sv_gate<<<(h->ins_pos_cap + 127) / 128, 128, 0, s>>>(h->d_ins_pos, (const unsigned int *)(h->d_sv_small + 4), h->ins_pos_cap, R, Ppad, h->d_arrays, sca, G); launches++;
+        k_sv_gate<<<(h->ins_pos_cap + 127) / 128, 128, 0, s>>>(h->d_ins_pos, (const unsigned int *)(h->d_sv_small + 4), h->ins_pos_cap, R, P, Ppad, h->d_arrays, sca, G); launches++;
         if (scan_last >= scan_first) { k_ins_sv_gate<<<(unsigned)(((int64_t)scan_last - scan_first + 256) / 256), 256, 0, s>>>(Ppad, h->d_arrays, sca, G); launches++; }
     }
     CK(cudaEventRecord(h->ev[7], s));

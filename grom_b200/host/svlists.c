@@ -36,7 +36,7 @@ static int cmp_event(const void *a, const void *b)
 static void side_from_event(grom_sv_side *s, const grom_sv_event *e)
 {
     s->pos = e->pos; s->weight = e->weight; s->rd = e->rd; s->conc = e->conc; s->read_start = e->read_start; s->read_end = e->read_end;
-    s->other_len = e->other_len; s->reserved = 0; s->binom = e->binom; s->hez = e->hez;
+    s->other_len = e->other_len; s->reserved = e->reserved; s->binom = e->binom; s->hez = e->hez;
 }
 
 /* The reference's in-line list search (src/GROM.c:12271-12346, also bisect_list 20360-20434) over the start positions collected so

@@ -86,10 +86,10 @@ typedef struct {
     int s_conc, e_conc, s_w, e_w, s_rd, e_rd, s_sc, e_sc, s_ol, e_ol;
 } delrec;
 
-int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
-                              const grom_del_event *ev, int64_t n, char *buf, int64_t cap)
+/* pairing state machine over the small-deletion events in (position, start-before-end) order, src/GROM.c:11475-11745;
+ * returns the list (n + 2 entries allocated) and the index the reference's cdp_indel_d_list_index ends on */
+static delrec *smalldel_list(const grom_params *p, const grom_del_event *ev, int64_t n, int *idx_out)
 {
-    /* ---- pairing state machine over the events in (position, start-before-end) order, src/GROM.c:11475-11745 */
     delrec *L = (delrec *)calloc((size_t)n + 2, sizeof(delrec));
     for (int64_t i = 0; i < n + 2; i++) L[i].end = -1;
     int idx = -1;
@@ -115,18 +115,52 @@ int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const 
             }
         }
     }
-    /* ---- emission, src/GROM.c:16351-16490 (the loop stops before the entry the index points at) */
+    *idx_out = idx;
+    return L;
+}
+static int smalldel_passes(const grom_params *p, const delrec *d)
+{
+    return d->s_pr <= p->pval_threshold && d->e_pr <= p->pval_threshold &&
+           (double)d->s_w / (double)d->s_rd > p->min_indel_ratio * (double)p->add_factor &&
+           (double)d->e_w / (double)d->e_rd > p->min_indel_ratio * (double)p->add_factor;
+}
+/* share of either interval covered by the other, as the reference computes it (src/GROM.c:16366-16393, 16517-16544); a = the
+ * paired-end deletion [as, ae], b = the small deletion [bs, be]; ae_quirk replaces ae in one numerator (src/GROM.c:16378) */
+static void overlap_ratios(int as, int ae, int bs, int be, int ae_quirk, int quirk, double *r_small, double *r_pair)
+{
+    *r_small = 0; *r_pair = 0;
+    if (as >= bs && as <= be) {
+        if (ae >= be) { *r_small = (double)(be - as) / (double)(be - bs); *r_pair = (double)(be - as) / (double)(ae - as); }
+        else { *r_small = (double)(ae - as) / (double)(be - bs); *r_pair = (double)((quirk ? ae_quirk : ae) - as) / (double)(ae - as); }
+    } else if (bs >= as && bs <= ae) {
+        if (ae >= be) { *r_small = (double)(be - bs) / (double)(be - bs); *r_pair = (double)(be - bs) / (double)(ae - as); }
+        else { *r_small = (double)(ae - bs) / (double)(be - bs); *r_pair = (double)(ae - bs) / (double)(ae - as); }
+    }
+}
+/* emission of the small deletions, src/GROM.c:16351-16490 (the loop stops before the entry the index points at); del2 = the merged
+ * paired-end deletion list, which suppresses a small deletion it overlaps by half when its evidence is stronger (NULL: no list) */
+static int64_t smalldel_emit(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len, const delrec *L, int idx,
+                             const grom_sv_pair *del2, int64_t n_del2, char *buf, int64_t cap)
+{
     int64_t w = 0;
+    const int reach = p->insert_max - 2 * p->lseq;
     for (int a = 0; a < idx; a++) {
         const delrec *d = &L[a];
-        if (!(d->s_pr <= p->pval_threshold && d->e_pr <= p->pval_threshold &&
-              (double)d->s_w / (double)d->s_rd > p->min_indel_ratio * (double)p->add_factor &&
-              (double)d->e_w / (double)d->e_rd > p->min_indel_ratio * (double)p->add_factor)) continue;
+        if (!smalldel_passes(p, d)) continue;
+        int covered = 0;
+        for (int64_t b = 0; b < n_del2; b++) {
+            const grom_sv_pair *q = &del2[b];
+            if (!(abs(q->start.pos - d->start) < reach && abs(q->end.pos - d->end) < reach)) continue;
+            double r1, r2;
+            overlap_ratios(q->start.pos, q->end.pos, d->start, d->end, a < n_del2 ? del2[a].end.pos : -1, 1, &r1, &r2);
+            if (r1 >= 0.5 && r2 >= 0.5 && q->start.binom * q->end.binom < d->s_pr * d->e_pr) covered = 1;
+        }
+        if (covered) continue;
         if (d->start < 0 || d->end < 0 || d->end >= chr_len) continue;
         const int hp = homopolymer(fasta, chr_len, d->start, d->end, 1);
         if (hp > 10) continue;
         const int cn = d->end - d->start + 1;
-        if (cap - w < 2048) { free(L); return -1; }
+        if (cap - w < 2048) return -1;
         char ref[128];
         if (cn > 0 && cn < 99) {
             memcpy(ref, fasta + d->start, (size_t)cn); ref[cn] = 0;
@@ -139,8 +173,180 @@ int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const 
                           d->s_conc, d->e_conc, d->s_ol, d->e_ol, d->s_rd, d->e_rd, d->s_sc, d->e_sc, hp);
         }
     }
+    return w;
+}
+
+int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                              const grom_del_event *ev, int64_t n, char *buf, int64_t cap)
+{
+    int idx;
+    delrec *L = smalldel_list(p, ev, n, &idx);
+    const int64_t w = smalldel_emit(p, chr_name, fasta, chr_len, L, idx, NULL, 0, buf, cap);
     free(L);
     return w;
+}
+
+/* ---- structural variants: list -> list2 merge and records, src/GROM.c:15164-16570 ---------------------------------------------- */
+
+/* Candidates whose start gates lie within ins_max - 2 lseq of each other describe one event: keep the one whose worse side has the
+ * smaller p-value, then the larger weights; exact ties average the positions (src/GROM.c:15172-15329, identical for all four lists) */
+static int64_t merge_pairs(const grom_params *p, const grom_sv_pair *l, int64_t n, grom_sv_pair **out)
+{
+    grom_sv_pair *m = (grom_sv_pair *)calloc((size_t)n + 1, sizeof(grom_sv_pair));
+    int64_t n2 = 0;
+    int begun = 0, first_s = 0, last_s = 0, first_e = 0, last_e = 0;
+    double first_d = 0, last_d = 0;
+    const int reach = p->insert_max - 2 * p->lseq;
+    for (int64_t a = 0; a < n; a++) {
+        const grom_sv_pair *c = &l[a];
+        if (begun) {
+            grom_sv_pair *k = &m[n2 - 1];
+            if (c->start.pos > last_s + reach) { begun = 0; first_s = last_s = first_e = last_e = 0; first_d = last_d = 0; }
+            else {
+                const double worst_c = c->end.binom > c->start.binom ? c->end.binom : c->start.binom;
+                const double worst_k = k->end.binom > k->start.binom ? k->end.binom : k->start.binom;
+                if (worst_c <= worst_k && c->start.pos >= 0 && c->end.pos >= 0 && k->start.weight <= c->start.weight && k->end.weight <= c->end.weight) {
+                    int take = 1;
+                    if (c->start.binom == k->start.binom && c->end.binom == k->end.binom) {
+                        take = (k->start.weight < c->start.weight && k->end.weight <= c->end.weight) || (k->start.weight <= c->start.weight && k->end.weight < c->end.weight);
+                        if (!take && k->start.weight == c->start.weight && k->end.weight == c->end.weight) {
+                            last_s = c->start.pos; last_e = c->end.pos; last_d = c->dist;
+                            const int ks = (first_s + last_s) / 2, ke = (first_e + last_e) / 2;
+                            *k = *c;
+                            k->start.pos = ks; k->end.pos = ke; k->dist = (first_d + last_d) / 2.0;
+                        }
+                    }
+                    if (take) { first_s = last_s = c->start.pos; first_e = last_e = c->end.pos; first_d = last_d = c->dist; *k = *c; }
+                }
+            }
+        }
+        if (!begun && c->start.pos >= 0 && c->end.pos >= 0 && n2 < 100000 - 1) {           /* g_sv_list2_len */
+            begun = 1; first_s = last_s = c->start.pos; first_e = last_e = c->end.pos; first_d = last_d = c->dist;
+            m[n2++] = *c;
+        }
+    }
+    *out = m;
+    return n2;
+}
+
+static int pair_passes(const grom_params *p, const grom_sv_pair *q, int with_hez)
+{
+    const double t = p->pval_threshold, r = p->min_sv_ratio * (double)p->add_factor;
+    return (q->start.binom <= t || (with_hez && q->start.hez <= t)) && (q->end.binom <= t || (with_hez && q->end.hez <= t)) &&
+           (double)q->start.weight / (double)q->start.rd >= r && (double)q->end.weight / (double)q->end.rd >= r;
+}
+static int64_t pair_record(const grom_params *p, const char *chr_name, const char *alt, const grom_sv_pair *q, char *buf, int64_t cap)
+{
+    if (cap < 1024) return -1;
+    return snprintf(buf, (size_t)cap, "%s\t%d\t.\t.\t<%s>\t.\t.\tEND=%d\tSPR:EPR:SEV:EEV:SRD:ERD:SCO:ECO:SOT:EOT:SFR:SLR:EFR:ELR\t%e:%e:%.1f:%.1f:%d:%d:%d:%d:%d:%d:%d:%d:%d:%d\n",
+                    chr_name, q->start.pos + 1, alt, q->end.pos + 1, q->start.binom, q->end.binom, (double)q->start.weight / (double)p->add_factor,
+                    (double)q->end.weight / (double)p->add_factor, q->start.rd, q->end.rd, q->start.conc, q->end.conc, q->start.other_len, q->end.other_len,
+                    q->start.read_start + 1, q->start.read_end + 1, q->end.read_start + 1, q->end.read_end + 1);
+}
+/* inversions: a candidate of one orientation yields to an overlapping one of the other orientation with stronger evidence, and the
+ * depth around its two breakpoints must agree within g_max_inv_rd_diff (src/GROM.c:15897-16007); side.reserved carries the depth
+ * sum over [read_start, read_end + lseq) that the CUDA library attaches to inversion gate events */
+static int64_t inv_records(const grom_params *p, const char *chr_name, const grom_sv_pair *mine, int64_t n, const grom_sv_pair *other, int64_t n_other,
+                           int other_wins_ties, char *buf, int64_t cap)
+{
+    int64_t w = 0;
+    const int reach = p->insert_max - 2 * p->lseq;
+    for (int64_t a = 0; a < n; a++) {
+        const grom_sv_pair *q = &mine[a];
+        if (!pair_passes(p, q, 0)) continue;
+        int covered = 0;
+        for (int64_t b = 0; b < n_other && !covered; b++) {
+            const grom_sv_pair *o = &other[b];
+            if (!(abs(q->start.pos - o->start.pos) < reach && abs(q->end.pos - o->end.pos) < reach)) continue;
+            if (!((q->start.pos >= o->start.pos && q->start.pos <= o->end.pos) || (o->start.pos >= q->start.pos && o->start.pos <= q->end.pos))) continue;
+            const double po = o->start.binom * o->end.binom, pq = q->start.binom * q->end.binom;
+            if (other_wins_ties ? po <= pq : po < pq) covered = 1;
+        }
+        const double d1 = (double)q->start.reserved / (q->start.read_end + p->lseq - q->start.read_start);
+        const double d2 = (double)q->end.reserved / (q->end.read_end + p->lseq - q->end.read_start);
+        if (covered || !(d1 / d2 <= 1.75 && d2 / d1 <= 1.75)) continue;                     /* g_max_inv_rd_diff */
+        const int64_t k = pair_record(p, chr_name, "INV", q, buf + w, cap - w);
+        if (k < 0) return -1;
+        w += k;
+    }
+    return w;
+}
+/* insertions: groups within ins_max - 2 lseq keep the entry whose both sides are at least as significant (src/GROM.c:16013-16090) */
+static int64_t ins_records(const grom_params *p, const char *chr_name, const grom_sv_pair *l, int64_t n, char *buf, int64_t cap)
+{
+    grom_sv_pair *m = (grom_sv_pair *)calloc((size_t)n + 1, sizeof(grom_sv_pair));
+    int64_t n2 = 0, w = 0;
+    int begun = 0;
+    const int reach = p->insert_max - 2 * p->lseq;
+    for (int64_t a = 0; a + 1 < n; a++) {                                                  /* the reference stops before its last entry */
+        const grom_sv_pair *c = &l[a];
+        if (begun) {
+            grom_sv_pair *k = &m[n2 - 1];
+            if (c->start.pos > k->start.pos + reach || c->start.pos > k->end.pos + reach || c->end.pos > k->start.pos + reach || c->end.pos > k->end.pos + reach) begun = 0;
+            else if (c->start.binom <= k->start.binom && c->start.pos >= 0 && c->end.binom <= k->end.binom && c->end.pos >= 0) *k = *c;
+        }
+        if (!begun && c->start.pos >= 0 && c->end.pos >= 0 && n - 1 < 100000 - 1) { begun = 1; m[n2++] = *c; }
+    }
+    for (int64_t a = 0; a < n2; a++) {
+        const grom_sv_pair *q = &m[a];
+        if (!(q->start.binom <= p->pval_insertion && q->end.binom <= p->pval_insertion && abs(q->end.pos - q->start.pos) <= 10)) continue;   /* g_max_ins_range */
+        if (cap - w < 1024) { free(m); return -1; }
+        w += snprintf(buf + w, (size_t)(cap - w), "%s\t%d\t.\t.\t<INS>\t.\t.\tEND=%d\tSPR:EPR:SEV:EEV:SRD:ERD:SCO:ECO:SOT:EOT\t%e:%e:%.1f:%.1f:%d:%d:%d:%d:%d:%d\n", chr_name,
+                      q->start.pos + 1, q->start.pos + 1, q->start.binom, q->end.binom, (double)q->start.weight / (double)p->add_factor,
+                      (double)q->end.weight / (double)p->add_factor, q->start.rd, q->end.rd, q->start.conc, q->end.conc, q->start.other_len, q->end.other_len);
+    }
+    free(m);
+    return w;
+}
+
+/* All records of one contig in the reference's order (src/GROM.c:15046-17500): SNV, <DUP>, <INV> (forward then reverse orientation),
+ * <INS>, small insertions, small deletions (minus those a stronger paired-end deletion covers), <DEL>, read-depth <DEL> / <DUP>.
+ * Translocation candidates go to the .ctx.vcf path, which is outside this library. */
+int64_t gromhost_vcf_contig(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                            const grom_snv_cand *snv, int64_t n_snv, double snv_ave_rd, const grom_ins_cand *ins, int64_t n_ins,
+                            const grom_del_event *del_ev, int64_t n_del_ev, const grom_sv_event *sv_ev, int64_t n_sv_ev,
+                            const grom_cnv_call *cnv, int64_t n_cnv, char *buf, int64_t cap)
+{
+    int64_t w = 0, k;
+#define ADD(call) do { k = (call); if (k < 0) { w = -1; goto done; } w += k; } while (0)
+    gromhost_sv_lists_t L;
+    grom_sv_pair *dup2 = NULL, *del2 = NULL, *invf2 = NULL, *invr2 = NULL;
+    delrec *small = NULL;
+    if (gromhost_sv_lists(p, sv_ev, n_sv_ev, &L) != 0) return -2;
+    const int64_t n_dup2 = merge_pairs(p, L.dup, L.n_dup, &dup2), n_del2 = merge_pairs(p, L.del, L.n_del, &del2);
+    const int64_t n_invf2 = merge_pairs(p, L.inv_f, L.n_inv_f, &invf2), n_invr2 = merge_pairs(p, L.inv_r, L.n_inv_r, &invr2);
+    ADD(gromhost_vcf_snv(p, chr_name, fasta, snv, n_snv, snv_ave_rd, buf + w, cap - w));
+    for (int64_t a = 0; a < n_dup2; a++) if (pair_passes(p, &dup2[a], 1)) ADD(pair_record(p, chr_name, "DUP", &dup2[a], buf + w, cap - w));
+    ADD(inv_records(p, chr_name, invf2, n_invf2, invr2, n_invr2, 0, buf + w, cap - w));
+    ADD(inv_records(p, chr_name, invr2, n_invr2, invf2, n_invf2, 1, buf + w, cap - w));
+    ADD(ins_records(p, chr_name, L.ins, L.n_ins, buf + w, cap - w));
+    ADD(gromhost_vcf_ins(p, chr_name, fasta, chr_len, ins, n_ins, buf + w, cap - w));
+    {
+        int idx;
+        small = smalldel_list(p, del_ev, n_del_ev, &idx);
+        ADD(smalldel_emit(p, chr_name, fasta, chr_len, small, idx, del2, n_del2, buf + w, cap - w));
+        /* paired-end deletions, unless a small deletion with at least as strong evidence covers them (src/GROM.c:16497-16560) */
+        const int reach = p->insert_max - 2 * p->lseq;
+        for (int64_t a = 0; a < n_del2; a++) {
+            const grom_sv_pair *q = &del2[a];
+            if (!pair_passes(p, q, 1)) continue;
+            int covered = 0;
+            for (int b = 0; b < idx && !covered; b++) {
+                const delrec *d = &small[b];
+                if (!(smalldel_passes(p, d) && abs(q->start.pos - d->start) < reach && abs(q->end.pos - d->end) < reach)) continue;
+                double r1, r2;
+                overlap_ratios(q->start.pos, q->end.pos, d->start, d->end, 0, 0, &r1, &r2);
+                if (r1 >= 0.5 && r2 >= 0.5 && d->s_pr * d->e_pr <= q->start.binom * q->end.binom) covered = 1;
+            }
+            if (!covered) ADD(pair_record(p, chr_name, "DEL", q, buf + w, cap - w));
+        }
+    }
+    ADD(gromhost_vcf_cnv(p, chr_name, fasta, chr_len, cnv, n_cnv, buf + w, cap - w));
+done:
+    free(dup2); free(del2); free(invf2); free(invr2); free(small);
+    gromhost_sv_lists_free(&L);
+    return w;
+#undef ADD
 }
 
 /* read-depth CNV calls: emission filter and text of src/GROM.c:17197-17240, 17280, 17414 */

@@ -192,3 +192,14 @@ def sv_lists(params, events: np.ndarray) -> dict:
            "ctx_r": take(out.ctx_r, out.n_ctx_r, SV_EVENT_DTYPE)}
     L.gromhost_sv_lists_free(C.byref(out))
     return res
+
+
+def vcf_contig(params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, snv_ave_rd: float, ins: np.ndarray, del_ev: np.ndarray,
+               sv_ev: np.ndarray, cnv_calls: np.ndarray) -> str:
+    """Every record of one contig in the reference's output order (gromhost_vcf_contig)."""
+    from .params import CNV_CALL_DTYPE, DEL_EVENT_DTYPE, INS_CAND_DTYPE, SNV_CAND_DTYPE, SV_EVENT_DTYPE
+    a = [np.ascontiguousarray(x, dtype=dt) for x, dt in ((snv, SNV_CAND_DTYPE), (ins, INS_CAND_DTYPE), (del_ev, DEL_EVENT_DTYPE),
+                                                          (sv_ev, SV_EVENT_DTYPE), (cnv_calls, CNV_CALL_DTYPE))]
+    return _vcf("gromhost_vcf_contig", params, chr_name, fasta, C.c_int64(len(fasta)), C.c_void_p(a[0].ctypes.data), C.c_int64(len(a[0])),
+                C.c_double(snv_ave_rd), C.c_void_p(a[1].ctypes.data), C.c_int64(len(a[1])), C.c_void_p(a[2].ctypes.data), C.c_int64(len(a[2])),
+                C.c_void_p(a[3].ctypes.data), C.c_int64(len(a[3])), C.c_void_p(a[4].ctypes.data), C.c_int64(len(a[4])))

@@ -174,13 +174,15 @@ typedef struct grom_sv_event {
     int32_t read_start, read_end;
     int32_t other_len;
     int32_t mchr;               /* ctx: mate contig */
-    int32_t reserved;
+    int32_t reserved;           /* inversion classes: sum of the CNV depth (rd_rd + rd_low_mq_rd) over [read_start, read_end + lseq), which the
+                                   emission compares between the two breakpoints (src/GROM.c:15921-15934); 0 otherwise */
 } grom_sv_event;
 
 /* one side of a breakpoint pair as the reference's *_list_start_* / *_list_end_* arrays hold it */
 typedef struct grom_sv_side {
     int32_t pos;                /* -1 = side not found */
-    int32_t weight, rd, conc, read_start, read_end, other_len, reserved;
+    int32_t weight, rd, conc, read_start, read_end, other_len;
+    int32_t reserved;           /* the event's depth sum (inversions) */
     double  binom, hez;
 } grom_sv_side;
 /* entry of cdp_dup_list / cdp_del_list / cdp_inv_f_list / cdp_inv_r_list / cdp_ins_list before the list -> list2 merge */

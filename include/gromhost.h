@@ -90,6 +90,15 @@ typedef struct gromhost_sv_lists_t {
 int  gromhost_sv_lists(const grom_params *p, const grom_sv_event *events, int64_t n_events, gromhost_sv_lists_t *out);
 void gromhost_sv_lists_free(gromhost_sv_lists_t *l);
 
+/* Every record of one contig in the reference's output order (src/GROM.c:15046-17500): SNV, <DUP>, <INV>, <INS>, small insertions,
+ * small deletions, <DEL>, read-depth <DEL>/<DUP>; includes the list -> list2 merge of the structural-variant candidates
+ * (src/GROM.c:15164-16090) and the mutual suppression of small and paired-end deletions (16351-16560).  Inputs are the pieces of
+ * gromgpu_result / gromgpu_cnv_result.  Returns bytes written, -1 if buf is too small. */
+int64_t gromhost_vcf_contig(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
+                            const grom_snv_cand *snv, int64_t n_snv, double snv_ave_rd, const grom_ins_cand *ins, int64_t n_ins,
+                            const grom_del_event *del_ev, int64_t n_del_ev, const grom_sv_event *sv_ev, int64_t n_sv_ev,
+                            const grom_cnv_call *cnv, int64_t n_cnv, char *buf, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -382,8 +382,15 @@ int oracle_run_chr(const grom_params *p, const grom_read_batch *b, const char *f
                         if (ratio <= p->max_evidence_ratio)
                             hz = ((w + side) / af < rd) ? hez_tbl[(size_t)rd * TD + (w + side) / af] : hez_tbl[(size_t)rd * TD + rd];
                     }
-                    if (bin <= p->pval_threshold1)
+                    if (bin <= p->pval_threshold1) {
                         SV_EMIT(c, bin, hz, S.cdist[c][x], w, S.crs[c][x], S.cre[c][x], c >= CL_CTX_F ? S.cmchr[c - CL_CTX_F][x] : 0);
+                        if (c >= CL_INV_F1 && c <= CL_INV_R2 && out->sv_ev && out->n_sv <= out->sv_cap) {
+                            /* depth around the breakpoint, compared between both ends at emission (src/GROM.c:15921-15934) */
+                            long sum = 0;
+                            for (int64_t y = S.crs[c][x]; y < (int64_t)S.cre[c][x] + p->lseq; y++) if (y >= 0 && y < P) sum += A.a[GA_RD_RD][y] + A.a[GA_RD_LOW][y];
+                            out->sv_ev[out->n_sv - 1].reserved = (int32_t)sum;
+                        }
+                    }
                 }
             }
 #undef SV_EMIT

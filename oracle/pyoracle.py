@@ -430,6 +430,7 @@ def normalise_sv_lists(lists: dict) -> dict:
             a["reserved"] = 0
         else:
             for side in ("start", "end"):
+                a[side]["reserved"] = 0
                 dead = a[side]["pos"] == -1
                 for f in ("binom", "hez", "conc", "rd", "weight", "read_start", "read_end", "other_len"):
                     a[side][f][dead] = 0

@@ -18,8 +18,10 @@ ap.add_argument("--disc", type=float, default=0.03)
 ap.add_argument("--len", type=int, default=300000)
 ap.add_argument("--sv", type=float, default=10.0)
 ap.add_argument("--svc", type=float, default=0.0, help="planted clusters per Mb of each further SV class")
+ap.add_argument("--cnv", type=float, default=0.0)
+ap.add_argument("--depth", type=float, default=30.0)
 a = ap.parse_args()
-spec = synth.SynthSpec(contigs=[("chrA", a.len), ("chrB", a.len // 2), ("chrZ", 50000)], depth=30, seed=a.seed, dup_frac=0.05,
+spec = synth.SynthSpec(contigs=[("chrA", a.len), ("chrB", a.len // 2), ("chrZ", 50000)], depth=a.depth, seed=a.seed, dup_frac=0.05, cnv_per_mb=a.cnv, cnv_min=15000, cnv_max=30000,
                        sa_frac=a.sa, disc_frac=a.disc, sv_sites_per_mb=a.sv, munmap_frac=0.01, sv_classes=a.svc)
 cs = synth.simulate(spec)
 fa, bam = synth.write_dataset("/tmp/cmpref", cs)
@@ -88,6 +90,26 @@ with hostlib.Bam(bam) as b:
                 for i in range(n):
                     if ref_l[k][i].tobytes() != mine_l[k][i].tobytes():
                         print("    first difference at", i, "\n     ref ", ref_l[k][i], "\n     mine", mine_l[k][i]); break
+        # the complete record text of the contig, in the reference's order
+        cn = po.cnv_run(prm, name, c.chars, r["gc"], r["acgt"], r["rd_mq"], r["rd_rd"], r["rd_low"], seed=1)
+        from grom_b200.params import CNV_CALL_DTYPE
+        calls = np.zeros(len(cn.dels) + len(cn.dups), dtype=CNV_CALL_DTYPE)
+        for k, src in enumerate((cn.dels, cn.dups)):
+            sl = slice(0, len(cn.dels)) if k == 0 else slice(len(cn.dels), None)
+            calls["start"][sl] = src["start"]; calls["end"][sl] = src["end"]; calls["kind"][sl] = k; calls["z"][sl] = src["z"]
+            calls["pvalue"][sl] = src["p"]; calls["cn"][sl] = src["cn"]; calls["cn_sd"][sl] = src["cs"]
+        mine_all = po.normalise_records(hostlib.vcf_contig(prm, name, c.chars, r.snv, r.snv_ave_rd, r.ins, r.del_ev, r.sv_ev, calls).splitlines(keepends=True))
+        ref_all = po.normalise_records([l for l in vcf if l.startswith(name + "\t")])
+        same = mine_all == ref_all
+        kinds = {}
+        for l in ref_all:
+            t = l.split("\t")[4]; kinds[t if t.startswith("<") else "seq"] = kinds.get(t if t.startswith("<") else "seq", 0) + 1
+        print(f"  FULL contig records: ref {len(ref_all)} mine {len(mine_all)} identical {same}   {kinds}")
+        if not same:
+            bad_total += 1
+            import difflib
+            for l in list(difflib.unified_diff(ref_all, mine_all, lineterm="", n=0))[:12]:
+                print("     ", l.rstrip()[:200])
 print("TOTAL MISMATCHES", bad_total)
 allrec = [l for l in open("/tmp/cmpref.vcf") if not l.startswith("#")]
 print("reference records:", len(allrec), "of which SV/CNV classes not yet produced:", sum(1 for l in allrec if l.split("\t")[4].startswith("<") and "SSC:ESC" not in l and "SSC:HP" not in l))
