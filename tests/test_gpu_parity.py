@@ -22,6 +22,7 @@ def run_gpu(prm, batch_or_slices, fasta, hez, mq, tid=0):
         for b in (batch_or_slices if isinstance(batch_or_slices, list) else [batch_or_slices]):
             ch.push_reads(b); n += b.n_reads
         res = ch.finish()
+        run_gpu.cnv = ch.cnv()
         run_gpu.clusters = ch.fetch_clusters()
         return res, ch.fetch_all(), ch.read_state(n), ch.stats()
 
@@ -92,6 +93,9 @@ def test_gpu_reproduces_reference_golden(tag, rmdup):
         assert hostlib.vcf_snv(prm, n, fasta[name], res.snv, res.snv_ave_rd).splitlines(keepends=True) == [l for l in vcf if l.startswith(n + "\t") and l.split("\t")[2] == ""]
         mine = hostlib.vcf_smalldel(prm, n, fasta[name], res.del_ev).splitlines(keepends=True)
         assert mine == [l for l in vcf if l.startswith(n + "\t") and "\tSPR:EPR:SEV:EEV:SRD:ERD:SCO:ECO:SOT:EOT:SSC:ESC:HP\t" in l]
+        # and the complete record text of the contig (all classes incl. SV merge and read-depth CNV), in the reference's order
+        full = hostlib.vcf_contig(prm, n, fasta[name], res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, run_gpu.cnv.calls)
+        assert po.normalise_records(full.splitlines(keepends=True)) == po.normalise_records([l for l in vcf if l.startswith(n + "\t")])
 
 
 @pytest.mark.parametrize("seed,rmdup,read_len,depth", [(1, 0, 150, 30), (2, 1, 150, 30), (3, 1, 100, 60), (4, 0, 250, 10)])
@@ -251,5 +255,11 @@ def test_sv_gate_events_all_classes():
         seen |= set(res.sv_ev["cls"].tolist())
         a = hostlib.sv_lists(prm, res.sv_ev)
         assert sum(len(v) for v in a.values()) > 0
+        ref = po.run_chr(prm, c.batch, c.chars, hez, mq)
+        ocnv = po.cnv_run(prm, c.name.lower(), c.chars, ref["gc"], ref["acgt"], ref["rd_mq"], ref["rd_rd"], ref["rd_low"])
+        full_gpu = hostlib.vcf_contig(prm, c.name.lower(), c.chars, res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, run_gpu.cnv.calls)
+        full_cpu = hostlib.vcf_contig(prm, c.name.lower(), c.chars, ref.snv, ref.snv_ave_rd, ref.ins, ref.del_ev, ref.sv_ev, run_gpu.cnv.calls)
+        assert full_gpu == full_cpu and "<DUP>" in full_gpu and "<INV>" in full_gpu and "<DEL>" in full_gpu
+        assert len(run_gpu.cnv.calls) == len(ocnv.dels) + len(ocnv.dups)
         assert (a["dup"]["end"]["pos"] >= 0).any() and (a["del"]["end"]["pos"] >= 0).any()     # pairs were completed
     assert seen == set(range(12)), seen
