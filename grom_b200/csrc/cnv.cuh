@@ -375,18 +375,18 @@ __global__ void __launch_bounds__(256) k_sweep(const uint32_t *__restrict__ rec,
     }
 }
 // ordered sum over the frames: one thread per window length walks the frames in order (loads batched ahead of the dependent adds)
-__global__ void __launch_bounds__(128) k_sweep_sum(const double *__restrict__ X, int64_t n_frames, int n_len, double *__restrict__ wsq, long long *__restrict__ wcnt)
+__global__ void __launch_bounds__(64) k_sweep_sum(const double *__restrict__ X, int64_t n_frames, int n_len, double *__restrict__ wsq, long long *__restrict__ wcnt)
 {
     const int L = blockIdx.x * blockDim.x + threadIdx.x;
     if (L >= n_len) return;
     double sum = 0.0;
     long long cnt = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += 8) {
-        double v[8];
+    for (int64_t f0 = 0; f0 < n_frames; f0 += 32) {
+        double v[32];
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = f0 + i < n_frames ? X[(f0 + i) * (int64_t)n_len + L] : __longlong_as_double(0x7ff8000000000000LL);
+        for (int i = 0; i < 32; i++) v[i] = f0 + i < n_frames ? __ldcs(X + (f0 + i) * (int64_t)n_len + L) : __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
-        for (int i = 0; i < 8; i++) if (v[i] == v[i]) { sum = __dadd_rn(sum, v[i]); cnt++; }
+        for (int i = 0; i < 32; i++) if (v[i] == v[i]) { sum = __dadd_rn(sum, v[i]); cnt++; }
     }
     wsq[L] = sum; wcnt[L] = cnt;
 }
@@ -542,44 +542,67 @@ __global__ void __launch_bounds__(256) k_seed_rank(const uint32_t *__restrict__ 
     uint32_t rank = part[threadIdx.x];
     for (int j = 0; j < 4; j++) { if (w0 + j < words) wp[(int64_t)kind * words + w0 + j] = rank; rank += __popc(bits[j]); }
 }
-// one thread per reference position: evaluate the seed (both carried classes when it is uncovered)
-__global__ void __launch_bounds__(128) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
-                                                   uint32_t *__restrict__ land, uint32_t cap, int64_t lo, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                   unsigned int *__restrict__ n_calls, int second_round)
+// one thread per seed (blockIdx.y = deletions / duplications): rank -> position through the per-word ranks, then evaluate the seed
+// (both carried classes when it is uncovered).  Seeds that run past the bound are appended to `todo` for the second round, which
+// runs one thread per (kind, rank, class) entry of that list.
+struct SeedTodo { uint32_t rank; uint8_t kind, variant; uint16_t pad; };
+__device__ __forceinline__ int64_t seed_position(const uint32_t *__restrict__ sd, const uint32_t *__restrict__ wpk, int64_t words, uint32_t rank)
 {
-    const int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= Cdel.end) return;
-    for (int kind = 0; kind < 2; kind++) {
-        const uint32_t word = seeds[(int64_t)kind * words + (p >> 5)];
-        if (!((word >> (p & 31)) & 1)) continue;
-        const uint32_t rank = wp[(int64_t)kind * words + (p >> 5)] + __popc(word & ((1u << (p & 31)) - 1u));
-        if (rank >= cap) continue;
-        const SegCtx &C = kind ? Cdup : Cdel;
+    int64_t a = 0, b = words;                                  // first word whose exclusive rank exceeds `rank`, minus one
+    while (a < b) { const int64_t m = (a + b) >> 1; if (wpk[m] <= rank) a = m + 1; else b = m; }
+    const int64_t w = a - 1;
+    return (w << 5) + __fns(sd[w], 0, (int)(rank - wpk[w]) + 1);
+}
+__device__ __forceinline__ uint32_t seed_outcome(const SegCtx &C, int64_t p, int mi, SeedCall *__restrict__ calls, uint32_t call_cap, unsigned int *__restrict__ n_calls)
+{
+    const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
+    const Outcome o = eval_seed<true>(C, p, mi);
+    if (o.kind == SEG_RESUME) return (uint32_t)(o.next - p);
+    if (o.kind == SEG_CALL) {
+        const unsigned int k = atomicAdd(n_calls, 1u);
+        if (k < call_cap) { calls[k].c_end = o.c_end; calls[k].c_z = o.c_z; return ((uint32_t)SEG_CALL << LAND_SHIFT) | k; }
+    }
+    return unres;
+}
+__global__ void __launch_bounds__(128) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+                                                   uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
+                                                   unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ todo, uint32_t todo_cap)
+{
+    const int kind = blockIdx.y;
+    const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rank >= (kind ? n_dup : n_del) || rank >= cap) return;
+    const SegCtx &C = kind ? Cdup : Cdel;
+    const int64_t p = seed_position(seeds + (int64_t)kind * words, wp + (int64_t)kind * words, words, rank);
+    uint32_t res[2] = {LAND_NOT, LAND_NOT};
+    const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
+    if (p < C.end) {
         const int c0 = C.cls(p);
-        uint32_t res[2] = {LAND_NOT, LAND_NOT};
-        const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
-        if (second_round) {
-            res[0] = land[((int64_t)kind * cap + rank) * 2]; res[1] = land[((int64_t)kind * cap + rank) * 2 + 1];
-            if (res[0] != unres && res[1] != unres) continue;
-        }
         for (int v = 0; v < 2; v++) {
             if (c0 != 2 && v == 1) { res[1] = res[0]; break; }
             const int mi = c0 == 2 ? v : c0;
-            if (second_round && res[v] != unres) continue;
             if (!C.beyond(p, mi)) continue;
-            const Outcome o = eval_seed<true>(C, p, mi);
-            uint32_t e;
-            if (o.kind == SEG_RESUME) e = (uint32_t)(o.next - p);
-            else if (o.kind == SEG_CALL) {
-                const unsigned int k = atomicAdd(n_calls, 1u);
-                if (k < call_cap) { calls[k].c_end = o.c_end; calls[k].c_z = o.c_z; e = ((uint32_t)SEG_CALL << LAND_SHIFT) | k; }
-                else e = unres;
-            } else e = unres;
-            if (e == unres) atomicAdd(n_calls + 1, 1u);
-            res[v] = e;
+            res[v] = seed_outcome(C, p, mi, calls, call_cap, n_calls);
+            if (res[v] == unres) {
+                const unsigned int k = atomicAdd(n_calls + 1, 1u);
+                if (k < todo_cap) { SeedTodo t; t.rank = rank; t.kind = (uint8_t)kind; t.variant = (uint8_t)v; t.pad = 0; todo[k] = t; }
+            }
         }
-        land[((int64_t)kind * cap + rank) * 2] = res[0]; land[((int64_t)kind * cap + rank) * 2 + 1] = res[1];
     }
+    land[((int64_t)kind * cap + rank) * 2] = res[0]; land[((int64_t)kind * cap + rank) * 2 + 1] = res[1];
+}
+__global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+                                                   uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
+                                                   unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t n_todo)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_todo) return;
+    const SeedTodo t = todo[i];
+    const SegCtx &C = t.kind ? Cdup : Cdel;
+    const int64_t p = seed_position(seeds + (int64_t)t.kind * words, wp + (int64_t)t.kind * words, words, t.rank);
+    const int c0 = C.cls(p);
+    const uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
+    land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] = e;
+    if (c0 != 2) land[((int64_t)t.kind * cap + t.rank) * 2 + 1] = e;
 }
 
 // ---- K8: depth and GC bin of the called segments, packed back to back (copy-number step, src/GROM.c:20071-20224)

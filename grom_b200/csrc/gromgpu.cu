@@ -1505,6 +1505,7 @@ struct CnvState {
     int q = 0;
     std::vector<double> sd_tbl;
     cnv::Grow tmp[16];
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr;   // packed records travel to the host while the sweep runs
 };
 static void cnv_state_free(CnvState *c)
 {
@@ -1512,6 +1513,9 @@ static void cnv_state_free(CnvState *c)
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_z) cudaEventDestroy(c->ev_z);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     if (c->h_seed) cudaFreeHost(c->h_seed);
     if (c->h_wp) cudaFreeHost(c->h_wp);
@@ -1595,6 +1599,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMalloc(&c.d_rep, sizeof(RepRec) * c.rep_cap)); CK(cudaMalloc(&c.d_nrep, sizeof(unsigned int)));
         CK(cudaMalloc(&c.d_tile, 4 * n_tiles));
         CK(cudaMallocHost(&c.h_rec, sizeof(uint32_t) * P)); CK(cudaMallocHost(&c.h_seed, sizeof(uint32_t) * 2 * words));
+        CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c.ev_z, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.ev_copied, cudaEventDisableTiming));
         c.nb = (int)((words + SEED_WORDS - 1) / SEED_WORDS); c.land_cap = (uint32_t)(P / 4 + 1024);
         CK(cudaMalloc(&c.d_blk, sizeof(uint32_t) * (2 * c.nb + 2))); CK(cudaMalloc(&c.d_wp, sizeof(uint32_t) * 2 * words));
         CK(cudaMalloc(&c.d_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
@@ -1877,8 +1883,11 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     k_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_gc, A_acgt, P, lo, hi, q, T.n, ti_mask, c.d_rec, tl_z); n_launch++;
     k_carry_scan<<<1, 1024, 0, s>>>(tl_z, ti_z, (int)n_tiles); n_launch++;
     k_z<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, A_gc, P, lo, hi, q, T, ti_z, c.d_rec, c.d_seed, c.d_seed + words); n_launch++;
-    CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(c.ev_z, s));
+    CK(cudaStreamWaitEvent(c.copy_stream, c.ev_z, 0));
+    CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, c.copy_stream));
+    CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, c.copy_stream));
+    CK(cudaEventRecord(c.ev_copied, c.copy_stream));
     uint32_t seed_tot[2] = {0, 0};
     k_seed_blocksum<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb); n_launch++;
     k_seed_blockscan<<<2, 1024, 0, s>>>(c.d_blk, c.nb, c.d_blk + 2 * c.nb); n_launch++;
@@ -1888,13 +1897,14 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     if (n_frames) {
         CK(cudaMemcpyAsync(t_sw.p, sw.data(), sizeof(SweepBlock) * n_sb, cudaMemcpyHostToDevice, s));
         k_sweep<<<(unsigned)((n_frames * 32 + 255) / 256), 256, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>()); n_launch++;
-        k_sweep_sum<<<(unsigned)((n_len + 127) / 128), 128, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>()); n_launch++;
+        k_sweep_sum<<<(unsigned)((n_len + 63) / 64), 64, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>()); n_launch++;
         CK(cudaMemcpyAsync(wsq.data(), t_wsq.p, sizeof(double) * n_len, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(wcnt.data(), t_wcnt.p, sizeof(long long) * n_len, cudaMemcpyDeviceToHost, s));
     }
     dev_end();
     CK(cudaGetLastError());
     mark("stage3 kernels+D2H");
+    CK(cudaEventSynchronize(c.ev_copied));
     for (int L = Lmin; L <= Lmax; L++) {
         c.win_cnt[L] = wcnt[L - Lmin];
         c.win_sd[L] = wcnt[L - Lmin] > 1 ? sqrt(wsq[L - Lmin] / (double)(wcnt[L - Lmin] - 1)) : 0.0;
@@ -1942,14 +1952,19 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
             CK(cudaMemsetAsync(c.d_nspec, 0, 2 * sizeof(unsigned int), s));
-            k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 0); n_launch++;
+            const uint32_t todo_cap = 32768;
+            Grow &t_todo = c.tmp[15];
+            if (!t_todo.ensure(sizeof(SeedTodo) * todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
+            const uint32_t most = std::max(seed_tot[0], seed_tot[1]);
+            if (most) { k_seed_eval<<<dim3((most + 127) / 128, 2), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
+                                                                              c.d_nspec, t_todo.as<SeedTodo>(), todo_cap); n_launch++; }
             unsigned int cnt2[2] = {0, 0};
             CK(cudaMemcpyAsync(cnt2, c.d_nspec, sizeof(cnt2), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            if (cnt2[1] > 0 && cnt2[1] <= 32768 && SEED_BOUND2 < Lmax) {
+            if (cnt2[1] > 0 && cnt2[1] <= todo_cap && SEED_BOUND2 < Lmax) {
                 // few seeds ran past the first bound (typically the uncovered stretch before the first applied read): give them a longer leash
                 ctx[0].bound = ctx[1].bound = SEED_BOUND2;
-                k_seed_eval<<<(unsigned)((hi - Lmin - lo + 127) / 128), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, lo, c.d_spec, c.spec_cap, c.d_nspec, 1); n_launch++;
+                k_seed_eval2<<<(cnt2[1] + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), cnt2[1]); n_launch++;
             }
             for (int k = 0; k < 2; k++) if (seed_tot[k]) CK(cudaMemcpyAsync(c.h_land + (size_t)k * 2 * c.land_cap, c.d_land + (size_t)k * 2 * c.land_cap, sizeof(uint32_t) * 2 * seed_tot[k], cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(&n_spec, c.d_nspec, sizeof(n_spec), cudaMemcpyDeviceToHost, s));

@@ -35,3 +35,12 @@ with gpu.Chromosome(0, c.chars) as ch:
         t = time.time(); g = ch.cnv(); dt = time.time() - t
         print(json.dumps(dict(cnv_ms_total=round(g.ms_total, 2), cnv_ms_device=round(g.ms_device, 2), cnv_ms_host=round(g.ms_host, 2), wall_ms=round(dt * 1e3, 2),
                               calls=len(g.calls), samples=g.n_samples, frames=g.n_frames, repeats=g.n_repeats, biased=g.biased_repeat)))
+    # end-to-end breakdown with pageable-vs-pinned note: the bench pins its batch; here the arrays are numpy (pageable)
+    import ctypes
+    cuda = ctypes.CDLL("libcudart.so")
+    def sync(): cuda.cudaDeviceSynchronize()
+    for r in range(2):
+        sync(); t0 = time.time(); ch.reset(c.chars); sync(); t1 = time.time(); ch.push_reads(c.batch); sync(); t2 = time.time()
+        ch.run(); sync(); t3 = time.time(); res = ch.result(); t4 = time.time(); g = ch.cnv(); t5 = time.time()
+        print(json.dumps(dict(e2e_ms=dict(reset=round((t1 - t0) * 1e3, 2), push=round((t2 - t1) * 1e3, 2), run=round((t3 - t2) * 1e3, 2),
+                                          result=round((t4 - t3) * 1e3, 2), cnv=round((t5 - t4) * 1e3, 2)))))
