@@ -405,14 +405,14 @@ struct SegCtx {
     __host__ __device__ inline double z(int64_t p) const { const double v = rec_z(rec[p], q, sd); return dup ? -v : v; }
 };
 enum { SEG_RESUME = 0, SEG_CALL = 1, SEG_UNRESOLVED = 2 };
-struct Outcome { int kind; int64_t next, c_end; double c_z; };
+struct Outcome { int kind; int64_t next, c_end; double c_z; int64_t far; };   // far: one past the last position the sliding phase looked at
 constexpr int SEED_BOUND = 1024, SEED_BOUND2 = 8192;   // first round for every seed; second round for the unresolved ones when they are few
 
 template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCtx &C, const int64_t pos, int mi)
 {
 #define CNV_STEP(var, p) do { const int c_ = C.cls(p); if (c_ != 2) var = c_; } while (0)
     const int64_t Lmin = C.Lmin, Lmax = C.Lmax, end = C.end, max_gap = Lmax + 500;
-    Outcome o; o.kind = SEG_RESUME; o.next = pos + 1; o.c_end = 0; o.c_z = 0;
+    Outcome o; o.kind = SEG_RESUME; o.next = pos + 1; o.c_end = 0; o.c_z = 0; o.far = 0;
     bool stop = false, begun = false;
     int64_t wlen = 0, cnt = 0, cnt2 = 0, pa, c_start = 0, c_end = 0, last_good = 0;
     double tot = 0, c_z = 0, tz;
@@ -471,6 +471,7 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
             }
             pa++;
         }
+        o.far = pa;
     }
     if (!begun) return o;                                                  // gave up while growing (or never scored): resume at seed + 1
     int64_t t = c_end;                                                     // trim the end back to a stretch that is still mostly beyond
@@ -542,6 +543,78 @@ __global__ void __launch_bounds__(256) k_seed_rank(const uint32_t *__restrict__ 
     uint32_t rank = part[threadIdx.x];
     for (int j = 0; j < 4; j++) { if (w0 + j < words) wp[(int64_t)kind * words + w0 + j] = rank; rank += __popc(bits[j]); }
 }
+// ---- the hop on the device.  Node = (seed rank, carried class); its successor is a pure function of the node's outcome: where
+// the outer loop resumes, which seed it meets next and which class it carries there (src/GROM.c:19370-19389).  With the successor
+// array in hand the visited path is found by pointer doubling: J_k = J_{k-1} o J_{k-1}, then marks spread from the start node
+// through J_{K-1} .. J_0, which reaches exactly the nodes at every path index.  Unresolved nodes are sinks (self loops).
+__device__ __forceinline__ uint32_t next_node(const SegCtx &C, const uint32_t *__restrict__ sd, const uint32_t *__restrict__ wpk, int64_t x, int s, uint32_t n_seeds)
+{
+    const int64_t end = C.end;
+    if (x >= end) return 2 * n_seeds;                                            // END
+    int64_t w = x >> 5;
+    uint32_t bits = sd[w] & (0xffffffffu << (x & 31));
+    const int64_t wend = (end + 31) >> 5;
+    while (!bits) { if (++w >= wend) return 2 * n_seeds; bits = sd[w]; }
+    const int bit = __ffs(bits) - 1;
+    const int64_t q = (w << 5) + bit;
+    if (q >= end) return 2 * n_seeds;
+    int v = C.cls(q);
+    if (v == 2) { v = s; for (int64_t b = q - 1; b >= x; b--) { const int c = C.cls(b); if (c != 2) { v = c; break; } } }
+    return 2 * (wpk[w] + __popc(sd[w] & ((1u << bit) - 1u))) + (uint32_t)v;
+}
+__device__ __forceinline__ uint32_t successor(const SegCtx &C, const uint32_t *__restrict__ sd, const uint32_t *__restrict__ wpk, int64_t p, int c0, int v, uint32_t e,
+                                              const SeedCall *__restrict__ calls, uint32_t rank, uint32_t n_seeds)
+{
+    const uint32_t kind = e >> LAND_SHIFT, low = e & ((1u << LAND_SHIFT) - 1u);
+    const int s = c0 != 2 ? c0 : v;                                              // class carried past this seed
+    if (e == LAND_NOT) return next_node(C, sd, wpk, p + 1, s, n_seeds);
+    if (kind == SEG_RESUME) return next_node(C, sd, wpk, p + low, s, n_seeds);
+    if (kind == SEG_CALL) return next_node(C, sd, wpk, calls[low].c_end + 2, s, n_seeds);
+    return 2 * rank + (uint32_t)v;                                               // unresolved: sink
+}
+__global__ void __launch_bounds__(256) k_hop_double(const uint32_t *__restrict__ a, uint32_t *__restrict__ b, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = a[a[i]];
+}
+__global__ void __launch_bounds__(256) k_hop_mark(const uint32_t *__restrict__ j, uint8_t *__restrict__ flag, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) flag[j[i]] = 1;
+}
+// start (or restart after a host-evaluated sink): flag the node the outer loop meets first from position x carrying class s
+__global__ void k_hop_start(SegCtx C, const uint32_t *sd, const uint32_t *wpk, int64_t x, int s, uint32_t n_seeds, uint32_t base, uint8_t *flag)
+{
+    flag[base + next_node(C, sd, wpk, x, s, n_seeds)] = 1;
+}
+// mark the node (seed at pos, class) as collected
+__global__ void k_hop_done(const uint32_t *sd, const uint32_t *wpk, int64_t pos, int variant, uint8_t *done)
+{
+    done[2 * (wpk[pos >> 5] + __popc(sd[pos >> 5] & ((1u << (pos & 31)) - 1u))) + variant] = 1;
+}
+struct HopCall { int64_t pos, c_end; double c_z; };
+struct HopSink { int64_t pos; int32_t variant, found; };
+__global__ void __launch_bounds__(256) k_hop_collect(const uint8_t *__restrict__ flag, uint8_t *__restrict__ done, const uint32_t *__restrict__ land, const uint32_t *__restrict__ sd,
+                                                     const uint32_t *__restrict__ wpk, int64_t words, uint32_t n_seeds, const SeedCall *__restrict__ calls,
+                                                     HopCall *__restrict__ out, uint32_t out_cap, unsigned int *__restrict__ n_out, HopSink *__restrict__ sink)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;               // node id inside this kind
+    if (i >= 2 * n_seeds || !flag[i] || done[i]) return;
+    done[i] = 1;
+    const uint32_t e = land[i];
+    if (e == LAND_NOT) return;
+    const uint32_t kind = e >> LAND_SHIFT, low = e & ((1u << LAND_SHIFT) - 1u);
+    if (kind == SEG_RESUME) return;
+    int64_t a = 0, b = words;
+    const uint32_t rank = i >> 1;
+    while (a < b) { const int64_t m = (a + b) >> 1; if (wpk[m] <= rank) a = m + 1; else b = m; }
+    const int64_t w = a - 1, pos = (w << 5) + __fns(sd[w], 0, (int)(rank - wpk[w]) + 1);
+    if (kind == SEG_CALL) {
+        const unsigned int k = atomicAdd(n_out, 1u);
+        if (k < out_cap) { out[k].pos = pos; out[k].c_end = calls[low].c_end; out[k].c_z = calls[low].c_z; }
+    } else { sink->pos = pos; sink->variant = (int)(i & 1); sink->found = 1; done[i] = 0; }
+}
+
 // one thread per seed (blockIdx.y = deletions / duplications): rank -> position through the per-word ranks, then evaluate the seed
 // (both carried classes when it is uncovered).  Seeds that run past the bound are appended to `todo` for the second round, which
 // runs one thread per (kind, rank, class) entry of that list.
@@ -566,7 +639,7 @@ __device__ __forceinline__ uint32_t seed_outcome(const SegCtx &C, int64_t p, int
 }
 __global__ void __launch_bounds__(128) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                   unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ todo, uint32_t todo_cap)
+                                                   unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ todo, uint32_t todo_cap, uint32_t *__restrict__ jump0)
 {
     const int kind = blockIdx.y;
     const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
@@ -589,10 +662,20 @@ __global__ void __launch_bounds__(128) k_seed_eval(SegCtx Cdel, SegCtx Cdup, con
         }
     }
     land[((int64_t)kind * cap + rank) * 2] = res[0]; land[((int64_t)kind * cap + rank) * 2 + 1] = res[1];
+    if (jump0) {
+        // successors; node ids are local to the kind, the table stores them behind the kind's base offset (2 * n_del + 1 for duplications)
+        const uint32_t n_seeds = kind ? n_dup : n_del, base = kind ? 2 * n_del + 1 : 0;
+        const uint32_t *sd = seeds + (int64_t)kind * words, *wpk = wp + (int64_t)kind * words;
+        const int c0 = p < C.end ? C.cls(p) : 0;
+        for (int v = 0; v < 2; v++)
+            jump0[base + 2 * rank + v] = base + (p < C.end ? successor(C, sd, wpk, p, c0, v, res[v], calls, rank, n_seeds) : 2 * n_seeds);
+        if (rank == 0) jump0[base + 2 * n_seeds] = base + 2 * n_seeds;      // END loops on itself
+    }
 }
 __global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                   unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t n_todo)
+                                                   unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t n_todo, uint32_t n_del, uint32_t n_dup,
+                                                   uint32_t *__restrict__ jump0)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_todo) return;
@@ -603,12 +686,20 @@ __global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, con
     const uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
     land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] = e;
     if (c0 != 2) land[((int64_t)t.kind * cap + t.rank) * 2 + 1] = e;
+    if (jump0) {
+        const uint32_t n_seeds = t.kind ? n_dup : n_del, base = t.kind ? 2 * n_del + 1 : 0;
+        const uint32_t *sd = seeds + (int64_t)t.kind * words, *wpk = wp + (int64_t)t.kind * words;
+        const uint32_t nx = base + successor(C, sd, wpk, p, c0, t.variant, e, calls, t.rank, n_seeds);
+        jump0[base + 2 * t.rank + t.variant] = nx;
+        if (c0 != 2) jump0[base + 2 * t.rank + 1] = base + successor(C, sd, wpk, p, c0, 1, e, calls, t.rank, n_seeds);
+    }
 }
 
 // ---- K8: depth and GC bin of the called segments, packed back to back (copy-number step, src/GROM.c:20071-20224)
 // out_gc: bits 0-6 GC bin, bit 7 = ACGT context >= 99 %
 __global__ void __launch_bounds__(256) k_gather(const int32_t *__restrict__ depth, const int32_t *__restrict__ gc, const int32_t *__restrict__ acgt, const int64_t *__restrict__ seg_start,
-                                                const int64_t *__restrict__ seg_first, int n_seg, int64_t total, int32_t *__restrict__ out_depth, uint8_t *__restrict__ out_gc)
+                                                const int64_t *__restrict__ seg_first, int n_seg, int64_t total, int32_t *__restrict__ out_depth, uint8_t *__restrict__ out_gc,
+                                                const uint32_t *__restrict__ rec, uint32_t *__restrict__ out_rec)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= total) return;
@@ -616,6 +707,7 @@ __global__ void __launch_bounds__(256) k_gather(const int32_t *__restrict__ dept
     while (a < b) { const int m = (a + b + 1) >> 1; if (seg_first[m] <= j) a = m; else b = m - 1; }
     const int64_t p = seg_start[a] + (j - seg_first[a]);
     out_depth[j] = depth[p]; out_gc[j] = (uint8_t)((gc[p] & 0x7f) | (acgt[p] >= MIN_ACGT ? 0x80 : 0));
+    if (out_rec) out_rec[j] = rec[p];
 }
 
 // =====================================================================================================================

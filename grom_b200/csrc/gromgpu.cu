@@ -1504,7 +1504,7 @@ struct CnvState {
     int64_t P = 0, words = 0;
     int q = 0;
     std::vector<double> sd_tbl;
-    cnv::Grow tmp[16];
+    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec;
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr;   // packed records travel to the host while the sweep runs
 };
 static void cnv_state_free(CnvState *c)
@@ -1513,6 +1513,7 @@ static void cnv_state_free(CnvState *c)
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
+    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec}) if (g->p) cudaFree(g->p);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_z) cudaEventDestroy(c->ev_z);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
@@ -1607,7 +1608,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * words)); CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
         c.spec_cap = (uint32_t)std::min<int64_t>(P / 8 + 1024, (int64_t)1 << 28);
         CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
-        CK(cudaMalloc(&c.d_nspec, 2 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (Lmax + 1)));
+        CK(cudaMalloc(&c.d_nspec, 4 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (Lmax + 1)));
     }
 
     // ---- stage 1: pre-statistics + repeat runs
@@ -1728,19 +1729,22 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     SampleList rsl[SEG];
     double rs_ave[SEG] = {0}, rs_sd[SEG] = {0};
     std::vector<unsigned> biased_idx;
-    auto gather = [&](const std::vector<int64_t> &starts, const std::vector<int64_t> &firsts, std::vector<int32_t> &o_depth, std::vector<uint8_t> &o_gc) -> int {
+    auto gather = [&](const std::vector<int64_t> &starts, const std::vector<int64_t> &firsts, std::vector<int32_t> &o_depth, std::vector<uint8_t> &o_gc, std::vector<uint32_t> *o_rec = nullptr) -> int {
         const int n_seg = (int)starts.size();
         const int64_t total = firsts.back();
         o_depth.resize(total); o_gc.resize(total);
+        if (o_rec) o_rec->resize(total);
         if (!total) return 0;
         Grow &a = c.tmp[3], &b = c.tmp[4], &od = c.tmp[5], &og = c.tmp[6];
-        if (!a.ensure(sizeof(int64_t) * n_seg) || !b.ensure(sizeof(int64_t) * (n_seg + 1)) || !od.ensure(sizeof(int32_t) * total) || !og.ensure(total)) return fail("gromgpu_chr_cnv: out of device memory");
+        if (!a.ensure(sizeof(int64_t) * n_seg) || !b.ensure(sizeof(int64_t) * (n_seg + 1)) || !od.ensure(sizeof(int32_t) * total) || !og.ensure(total) ||
+            (o_rec && !c.gather_rec.ensure(sizeof(uint32_t) * total))) return fail("gromgpu_chr_cnv: out of device memory");
         dev_begin();
         CK(cudaMemcpyAsync(a.p, starts.data(), sizeof(int64_t) * n_seg, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.p, firsts.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, s));
-        k_gather<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c.d_depth, A_gc, A_acgt, a.as<int64_t>(), b.as<int64_t>(), n_seg, total, od.as<int32_t>(), og.as<uint8_t>()); n_launch++;
+        k_gather<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c.d_depth, A_gc, A_acgt, a.as<int64_t>(), b.as<int64_t>(), n_seg, total, od.as<int32_t>(), og.as<uint8_t>(), c.d_rec, o_rec ? c.gather_rec.as<uint32_t>() : nullptr); n_launch++;
         CK(cudaMemcpyAsync(o_depth.data(), od.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(o_gc.data(), og.p, total, cudaMemcpyDeviceToHost, s));
+        if (o_rec) CK(cudaMemcpyAsync(o_rec->data(), c.gather_rec.p, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, s));
         dev_end();
         CK(cudaGetLastError());
         return 0;
@@ -1883,17 +1887,11 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     k_mask<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, c.d_mq8, A_gc, A_acgt, P, lo, hi, q, T.n, ti_mask, c.d_rec, tl_z); n_launch++;
     k_carry_scan<<<1, 1024, 0, s>>>(tl_z, ti_z, (int)n_tiles); n_launch++;
     k_z<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, A_gc, P, lo, hi, q, T, ti_z, c.d_rec, c.d_seed, c.d_seed + words); n_launch++;
-    CK(cudaEventRecord(c.ev_z, s));
-    CK(cudaStreamWaitEvent(c.copy_stream, c.ev_z, 0));
-    CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, c.copy_stream));
-    CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, c.copy_stream));
-    CK(cudaEventRecord(c.ev_copied, c.copy_stream));
     uint32_t seed_tot[2] = {0, 0};
     k_seed_blocksum<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb); n_launch++;
     k_seed_blockscan<<<2, 1024, 0, s>>>(c.d_blk, c.nb, c.d_blk + 2 * c.nb); n_launch++;
     k_seed_rank<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb, c.d_wp); n_launch++;
     CK(cudaMemcpyAsync(seed_tot, c.d_blk + 2 * c.nb, sizeof(seed_tot), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(c.h_wp, c.d_wp, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
     if (n_frames) {
         CK(cudaMemcpyAsync(t_sw.p, sw.data(), sizeof(SweepBlock) * n_sb, cudaMemcpyHostToDevice, s));
         k_sweep<<<(unsigned)((n_frames * 32 + 255) / 256), 256, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>()); n_launch++;
@@ -1904,7 +1902,19 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     dev_end();
     CK(cudaGetLastError());
     mark("stage3 kernels+D2H");
-    CK(cudaEventSynchronize(c.ev_copied));
+    // the packed records stay on the device; only the rare paths below (biased-repeat override, seed tables that outgrew their
+    // buffers) pull all of them to the host
+    bool have_host_rec = false;
+    auto pull_records = [&]() -> int {
+        if (have_host_rec) return 0;
+        CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(c.h_wp, c.d_wp, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        d2h += 4 * P + 16 * words;
+        have_host_rec = true;
+        return 0;
+    };
     for (int L = Lmin; L <= Lmax; L++) {
         c.win_cnt[L] = wcnt[L - Lmin];
         c.win_sd[L] = wcnt[L - Lmin] > 1 ? sqrt(wsq[L - Lmin] / (double)(wcnt[L - Lmin] - 1)) : 0.0;
@@ -1912,6 +1922,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
 
     // most-biased repeat override of the z list, after the sweep like the reference (src/GROM.c:19023-19150)
     if (biased != -1) {
+        if (pull_records()) return -1;
         for (size_t k = 0; k < biased_idx.size(); k++) {
             const RepRec &r = reps[biased_idx[k]];
             for (int64_t j = rp_first[k]; j < rp_first[k + 1]; j++) {
@@ -1951,47 +1962,114 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         if (have_land) {
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
-            CK(cudaMemsetAsync(c.d_nspec, 0, 2 * sizeof(unsigned int), s));
+            CK(cudaMemsetAsync(c.d_nspec, 0, 4 * sizeof(unsigned int), s));
             const uint32_t todo_cap = 32768;
             Grow &t_todo = c.tmp[15];
             if (!t_todo.ensure(sizeof(SeedTodo) * todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
+            // jump table: level k holds the node reached after 2^k hops; node ids of the duplication scan sit behind the deletion scan's
+            const uint32_t n_nodes = 2 * seed_tot[0] + 1 + 2 * seed_tot[1] + 1, base[2] = {0u, 2 * seed_tot[0] + 1};
+            int levels = 1;
+            while ((1ull << levels) < (unsigned long long)2 * std::max(seed_tot[0], seed_tot[1]) + 2) levels++;
+            if (!c.jump.ensure(sizeof(uint32_t) * (size_t)levels * n_nodes) || !c.flags.ensure(2 * (size_t)n_nodes) ||
+                !c.hop_out.ensure(sizeof(HopCall) * (size_t)c.spec_cap) || !c.hop_sink.ensure(2 * sizeof(HopSink))) return fail("gromgpu_chr_cnv: out of device memory for the jump table");
+            uint32_t *J = c.jump.as<uint32_t>();
+            uint8_t *flag = c.flags.as<uint8_t>(), *done = flag + n_nodes;
             const uint32_t most = std::max(seed_tot[0], seed_tot[1]);
             if (most) { k_seed_eval<<<dim3((most + 127) / 128, 2), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
-                                                                              c.d_nspec, t_todo.as<SeedTodo>(), todo_cap); n_launch++; }
+                                                                              c.d_nspec, t_todo.as<SeedTodo>(), todo_cap, J); n_launch++; }
             unsigned int cnt2[2] = {0, 0};
             CK(cudaMemcpyAsync(cnt2, c.d_nspec, sizeof(cnt2), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             if (cnt2[1] > 0 && cnt2[1] <= todo_cap && SEED_BOUND2 < Lmax) {
                 // few seeds ran past the first bound (typically the uncovered stretch before the first applied read): give them a longer leash
                 ctx[0].bound = ctx[1].bound = SEED_BOUND2;
-                k_seed_eval2<<<(cnt2[1] + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), cnt2[1]); n_launch++;
+                k_seed_eval2<<<(cnt2[1] + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), cnt2[1],
+                                                                seed_tot[0], seed_tot[1], J); n_launch++;
             }
-            for (int k = 0; k < 2; k++) if (seed_tot[k]) CK(cudaMemcpyAsync(c.h_land + (size_t)k * 2 * c.land_cap, c.d_land + (size_t)k * 2 * c.land_cap, sizeof(uint32_t) * 2 * seed_tot[k], cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(&n_spec, c.d_nspec, sizeof(n_spec), cudaMemcpyDeviceToHost, s));
+            if (most == 0) CK(cudaMemsetAsync(J, 0, sizeof(uint32_t) * n_nodes, s));
+            if (seed_tot[0] == 0 || seed_tot[1] == 0) {                // a scan without seeds: its END node loops on itself
+                const uint32_t e0 = base[0] + 2 * seed_tot[0], e1 = base[1] + 2 * seed_tot[1];
+                if (seed_tot[0] == 0) CK(cudaMemcpyAsync(J + e0, &e0, 4, cudaMemcpyHostToDevice, s));
+                if (seed_tot[1] == 0) CK(cudaMemcpyAsync(J + e1, &e1, 4, cudaMemcpyHostToDevice, s));
+            }
+            for (int k = 1; k < levels; k++) { k_hop_double<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)(k - 1) * n_nodes, J + (size_t)k * n_nodes, n_nodes); n_launch++; }
+            CK(cudaMemsetAsync(flag, 0, 2 * (size_t)n_nodes, s));
+            CK(cudaMemsetAsync(c.hop_sink.p, 0, 2 * sizeof(HopSink), s));
+            unsigned int *n_hop = c.d_nspec + 2;                        // [2]: calls collected per scan
+            for (int k = 0; k < 2; k++) { k_hop_start<<<1, 1, 0, s>>>(ctx[k], c.d_seed + k * words, c.d_wp + k * words, lo, 0, seed_tot[k], base[k], flag); n_launch++; }
+            std::vector<Call> by_host[2];
+            std::vector<uint32_t> window;
+            for (int round = 0; round < 100000; round++) {
+                for (int k = levels - 1; k >= 0; k--) { k_hop_mark<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)k * n_nodes, flag, n_nodes); n_launch++; }
+                for (int k = 0; k < 2; k++) if (seed_tot[k]) {
+                    k_hop_collect<<<(2 * seed_tot[k] + 255) / 256, 256, 0, s>>>(flag + base[k], done + base[k], c.d_land + (size_t)k * 2 * c.land_cap, c.d_seed + k * words, c.d_wp + k * words, words,
+                                                                                 seed_tot[k], c.d_spec, c.hop_out.as<HopCall>() + (size_t)k * (c.spec_cap / 2), c.spec_cap / 2, n_hop + k,
+                                                                                 c.hop_sink.as<HopSink>() + k); n_launch++;
+                }
+                HopSink sink[2];
+                CK(cudaMemcpyAsync(sink, c.hop_sink.p, sizeof(sink), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                if (!sink[0].found && !sink[1].found) break;
+                // a seed the device left unresolved lies on the path (a genuine multi-kb event): evaluate it here on a window of records
+                for (int k = 0; k < 2; k++) if (sink[k].found) {
+                    const int64_t pos = sink[k].pos;
+                    Outcome o;
+                    int c0 = 0;
+                    for (int64_t span = 3 * (int64_t)Lmax + 2048;; span *= 2) {
+                        const int64_t w1 = std::min<int64_t>(P, pos + span);
+                        window.resize(w1 - pos);
+                        CK(cudaMemcpy(window.data(), c.d_rec + pos, sizeof(uint32_t) * (w1 - pos), cudaMemcpyDeviceToHost));
+                        d2h += 4 * (w1 - pos);
+                        SegCtx hc = ctx[k];
+                        hc.rec = window.data() - pos; hc.len = w1; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data();
+                        c0 = hc.cls(pos);
+                        o = eval_seed<false>(hc, pos, c0 != 2 ? c0 : sink[k].variant);
+                        if (w1 == P || o.far < w1) break;
+                    }
+                    if (o.kind == SEG_CALL) by_host[k].push_back({pos, o.c_end, o.c_z});
+                    const HopSink zero = {0, 0, 0};
+                    CK(cudaMemcpyAsync(c.hop_sink.as<HopSink>() + k, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
+                    // the sink stays flagged and is marked done, the path continues from where the evaluation lands
+                    uint32_t rank_node = 0;      // node id is recovered on the device from (pos, variant): restart by position
+                    (void)rank_node;
+                    k_hop_done<<<1, 1, 0, s>>>(c.d_seed + k * words, c.d_wp + k * words, pos, sink[k].variant, done + base[k]); n_launch++;
+                    k_hop_start<<<1, 1, 0, s>>>(ctx[k], c.d_seed + k * words, c.d_wp + k * words, o.next, c0 != 2 ? c0 : sink[k].variant, seed_tot[k], base[k], flag); n_launch++;
+                }
+            }
+            unsigned int n_got[2] = {0, 0};
+            CK(cudaMemcpyAsync(n_got, n_hop, sizeof(n_got), cudaMemcpyDeviceToHost, s));
             dev_end();
             CK(cudaGetLastError());
-            n_spec = std::min(n_spec, c.spec_cap);
-            seed_tot_all = (int64_t)seed_tot[0] + seed_tot[1]; n_spec_all = n_spec;
-            if (n_spec) CK(cudaMemcpy(c.h_spec, c.d_spec, sizeof(SeedCall) * n_spec, cudaMemcpyDeviceToHost));
+            for (int k = 0; k < 2; k++) {
+                if (n_got[k] > c.spec_cap / 2) return fail("gromgpu_chr_cnv: %u calls exceed the buffer", n_got[k]);
+                std::vector<HopCall> got(n_got[k]);
+                if (n_got[k]) CK(cudaMemcpy(got.data(), c.hop_out.as<HopCall>() + (size_t)k * (c.spec_cap / 2), sizeof(HopCall) * n_got[k], cudaMemcpyDeviceToHost));
+                d2h += (int64_t)sizeof(HopCall) * n_got[k];
+                for (const HopCall &g : got) found[k].push_back({g.pos, g.c_end, g.c_z});
+                for (const Call &g : by_host[k]) found[k].push_back(g);
+                std::sort(found[k].begin(), found[k].end(), [](const Call &a, const Call &b) { return a.start < b.start; });
+            }
+            seed_tot_all = 0; n_spec_all = 0;
+            if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u, jump table %d levels x %u nodes; calls from the device %u + %u, evaluated on the host %zu + %zu\n", seed_tot[0], seed_tot[1],
+                               levels, n_nodes, n_got[0], n_got[1], by_host[0].size(), by_host[1].size());
+        } else {
+            // seed tables outgrew their buffers: the whole scan runs on the host over the packed records
+            if (pull_records()) return -1;
+            Segmenter sg[2];
+            for (int k = 0; k < 2; k++) {
+                sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
+            }
+            const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));
+            std::thread th([&]() { sg[1].run(found[1], per_scan); });
+            sg[0].run(found[0], per_scan);
+            th.join();
         }
-        mark("seed evaluation device");
-        Segmenter sg[2];
-        for (int k = 0; k < 2; k++) {
-            sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
-            if (have_land) { sg[k].wp = c.h_wp + k * words; sg[k].land = c.h_land + (size_t)k * 2 * c.land_cap; sg[k].spec = c.h_spec; }
-        }
-        const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));
-        std::thread th([&]() { sg[1].run(found[1], per_scan); });
-        sg[0].run(found[0], per_scan);
-        th.join();
-        if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u, speculative calls %u; table/host evaluations del %ld/%ld dup %ld/%ld host span %ld %ld\n", seed_tot[0], seed_tot[1], n_spec,
-                           sg[0].n_table, sg[0].n_host, sg[1].n_table, sg[1].n_host, sg[0].host_span, sg[1].host_span);
     }
     mark("segmentation host");
     std::vector<int64_t> seg_start, seg_first(1, 0);
     for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) { seg_start.push_back(cl.start); seg_first.push_back(seg_first.back() + std::max<int64_t>(0, cl.end - cl.start)); }
-    std::vector<int32_t> g_depth; std::vector<uint8_t> g_gc;
-    if (!seg_start.empty() && gather(seg_start, seg_first, g_depth, g_gc)) return -1;
+    std::vector<int32_t> g_depth; std::vector<uint8_t> g_gc; std::vector<uint32_t> g_rec;
+    if (!seg_start.empty() && gather(seg_start, seg_first, g_depth, g_gc, &g_rec)) return -1;
     mark("gather");
     {
         // copy number per call (src/GROM.c:20071-20224): independent per call, spread over a few host threads
@@ -2006,7 +2084,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 buf.clear();
                 for (int64_t j = seg_first[si]; j < seg_first[si + 1]; j++) {
                     const int64_t p = cl.start + (j - seg_first[si]);
-                    const uint32_t r = c.h_rec[p];
+                    const uint32_t r = g_rec[j];
+                    (void)p;
                     if (r & R_MASK) continue;
                     const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (g_gc[j] & 0x7f);
                     if (ave[l] > 0) buf.push_back((double)g_depth[j] / ave[l]);
@@ -2041,8 +2120,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     out->n_calls = (int64_t)c.calls.size(); out->calls = c.calls.data();
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    d2h += (int64_t)sizeof(cnv::PreOut) * n_blk + 8 * HIST_ALL + (int64_t)sizeof(RepRec) * n_rep + (int64_t)sizeof(Sample) * n_samples + 4 * P + 16 * words +
-           8 * ((int64_t)seed_tot_all) + 16 * (int64_t)n_spec_all + 5 * (int64_t)(g_depth.size() + rp_depth.size()) + 16 * (int64_t)n_len;
+    d2h += (int64_t)sizeof(cnv::PreOut) * n_blk + 8 * HIST_ALL + (int64_t)sizeof(RepRec) * n_rep + (int64_t)sizeof(Sample) * n_samples +
+           8 * ((int64_t)seed_tot_all) + 16 * (int64_t)n_spec_all + 9 * (int64_t)g_depth.size() + 5 * (int64_t)rp_depth.size() + 16 * (int64_t)n_len;
     out->launches = n_launch; out->d2h_bytes = d2h;
     out->ms_device = (float)ms_dev; out->ms_total = (float)ms_total; out->ms_host = (float)(ms_total - ms_dev);
     return 0;
