@@ -84,20 +84,31 @@ __global__ void __launch_bounds__(256) k_pre(const int32_t *__restrict__ mqsum, 
     __syncthreads();
     const int64_t p0 = (int64_t)blockIdx.x * BLK_UNIT, p1 = min(p0 + BLK_UNIT, P);
     unsigned long long s_blk = 0, s_acgt = 0, n_acgt = 0, s_ave = 0, n_ave = 0;
-    for (int64_t p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
-        const int d = rd[p] + low[p];
-        const int m = d > 0 ? mqsum[p] / d : mqsum[p];
-        depth[p] = d; mq8[p] = (uint8_t)min(max(m, 0), 255);
-        s_blk += (unsigned)d;
-        const char c = fasta[p] & 0xDF;
-        if (c == 'A' || c == 'C' || c == 'G' || c == 'T') { s_acgt += (unsigned)d; n_acgt++; }
-        if (p >= lo && p < hi && acgt[p] >= MIN_ACGT) {
-            s_ave += (unsigned)d; n_ave++;
-            if (d < HIST) atomicAdd(&sh[d], 1u);
-            else atomicAdd(&hist[min(d, HIST_ALL - 1)], 1ull);
+    // the trip count is warp-uniform (BLK_UNIT rounded up to the block size) so that the warp-aggregated histogram update below can
+    // use full-mask collectives
+    for (int64_t b = p0; b < p1; b += blockDim.x) {
+        const int64_t p = b + threadIdx.x;
+        int hbin = -1;
+        if (p < p1) {
+            const int d = rd[p] + low[p];
+            const int m = d > 0 ? mqsum[p] / d : mqsum[p];
+            depth[p] = d; mq8[p] = (uint8_t)min(max(m, 0), 255);
+            s_blk += (unsigned)d;
+            const char c = fasta[p] & 0xDF;
+            if (c == 'A' || c == 'C' || c == 'G' || c == 'T') { s_acgt += (unsigned)d; n_acgt++; }
+            if (p >= lo && p < hi && acgt[p] >= MIN_ACGT) { s_ave += (unsigned)d; n_ave++; hbin = min(d, HIST_ALL - 1); }
+        }
+        // neighbouring positions mostly share their depth: one atomic per distinct value in the warp
+        const unsigned peers = __match_any_sync(0xffffffffu, hbin);
+        if (hbin >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) {
+            if (hbin < HIST) atomicAdd(&sh[hbin], (unsigned)__popc(peers)); else atomicAdd(&hist[hbin], (unsigned long long)__popc(peers));
         }
     }
-    atomicAdd(&red[0], s_blk); atomicAdd(&red[1], s_acgt); atomicAdd(&red[2], n_acgt); atomicAdd(&red[3], s_ave); atomicAdd(&red[4], n_ave);
+    for (int o = 16; o; o >>= 1) {
+        s_blk += __shfl_xor_sync(0xffffffffu, s_blk, o); s_acgt += __shfl_xor_sync(0xffffffffu, s_acgt, o); n_acgt += __shfl_xor_sync(0xffffffffu, n_acgt, o);
+        s_ave += __shfl_xor_sync(0xffffffffu, s_ave, o); n_ave += __shfl_xor_sync(0xffffffffu, n_ave, o);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[0], s_blk); atomicAdd(&red[1], s_acgt); atomicAdd(&red[2], n_acgt); atomicAdd(&red[3], s_ave); atomicAdd(&red[4], n_ave); }
     __syncthreads();
     if (threadIdx.x == 0) { PreOut o; o.blk_sum = red[0]; o.acgt_sum = red[1]; o.acgt_cnt = red[2]; o.ave_sum = red[3]; o.ave_cnt = red[4]; out[blockIdx.x] = o; }
     for (int i = threadIdx.x; i < HIST; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
