@@ -50,7 +50,7 @@ def parse():
 
 
 def workload_name(a):
-    return f"synthetic {a.depth:g}x paired-end 2x150 contig of {a.mb:g} Mb per GPU (chr20-sized), -M, SNV scan"
+    return f"synthetic {a.depth:g}x paired-end 2x150 contig of {a.mb:g} Mb per GPU (chr20-sized), -M, SNV/indel/SV gates + read-depth CNV"
 
 
 def params_for_bench():

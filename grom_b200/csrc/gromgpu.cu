@@ -325,8 +325,11 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+#ifndef MBAR_BACKOFF
+#define MBAR_BACKOFF
+#endif
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) { } }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) { MBAR_BACKOFF } }
 __device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 #define QCAP (CHUNK * 160)        // quality bytes per stage (64 reads of 2x150 data); the 4-bit area is half of it
