@@ -203,3 +203,26 @@ def vcf_contig(params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, snv_av
     return _vcf("gromhost_vcf_contig", params, chr_name, fasta, C.c_int64(len(fasta)), C.c_void_p(a[0].ctypes.data), C.c_int64(len(a[0])),
                 C.c_double(snv_ave_rd), C.c_void_p(a[1].ctypes.data), C.c_int64(len(a[1])), C.c_void_p(a[2].ctypes.data), C.c_int64(len(a[2])),
                 C.c_void_p(a[3].ctypes.data), C.c_int64(len(a[3])), C.c_void_p(a[4].ctypes.data), C.c_int64(len(a[4])))
+
+
+def library_stats(batches, rd_min_mapq: int = 20) -> dict:
+    """find_insert_mean (reference src/GROM.c:1205-1318) over per-contig batches in contig order."""
+    L = lib()
+    L.gromhost_libstats_new.restype = C.c_void_p
+    L.gromhost_libstats_add.argtypes = [C.c_void_p, C.c_void_p]
+    L.gromhost_libstats_finish.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.gromhost_libstats_free.argtypes = [C.c_void_p]
+    L.gromhost_libstats_free.restype = None
+    h = L.gromhost_libstats_new(rd_min_mapq)
+    try:
+        for b in batches:
+            cb = b.as_c()
+            if L.gromhost_libstats_add(h, C.byref(cb)):
+                break
+        v = [C.c_int(), C.c_int(), C.c_int(), C.c_int()]
+        m = C.c_int64()
+        if L.gromhost_libstats_finish(h, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3]), C.byref(m)) != 0:
+            raise RuntimeError("no reads to estimate the insert size from")
+        return dict(insert_mean=v[0].value, lseq=v[1].value, insert_min=v[2].value, insert_max=v[3].value, mapped_reads=m.value)
+    finally:
+        L.gromhost_libstats_free(h)

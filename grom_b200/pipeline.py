@@ -1,0 +1,76 @@
+"""Per-genome driver over the C ABI: the analogue of the reference's find_disc_svs loop (src/GROM.c:20900-21130).
+
+    BAM  --gromhost_bam_read_target-->  packed batches  --gromhost_libstats-->  insert statistics (find_insert_mean)
+    per contig:  gromgpu_chr_begin / push_reads / chr_finish / chr_cnv  -->  gromhost_vcf_contig  -->  record text
+
+Contigs are processed in BAM header order (the order the reference concatenates per-contig outputs in, src/GROM.c:21121-21126);
+with `ranks` > 1 they are assigned largest-first (`partition.assign_contigs`) and only this rank's share is processed.
+No CPU fallback: `gpu.init` fails without a CUDA device.
+"""
+from __future__ import annotations
+
+import gzip
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import gpu, hostlib
+from .params import Params
+from .partition import assign_contigs, skip_contig
+
+
+def read_fasta(path: str) -> Dict[str, np.ndarray]:
+    """FASTA -> {first word of the header: uint8 characters, case preserved} (the reference loader, src/GROM.c:21009-21045)."""
+    op = gzip.open if path.endswith(".gz") else open
+    out: Dict[str, np.ndarray] = {}
+    name, parts = None, []
+    with op(path, "rb") as f:
+        for line in f:
+            if line.startswith(b">"):
+                if name is not None:
+                    out[name] = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+                name = line[1:].split()[0].decode(); parts = []
+            else:
+                parts.append(line.rstrip(b"\r\n"))
+    if name is not None:
+        out[name] = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    return out
+
+
+def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = None, device: int = 0, rank: int = 0, ranks: int = 1,
+                  table_dir: Optional[str] = None) -> Tuple[Dict[int, str], Params]:
+    """Returns ({tid: record text of that contig}, the parameters incl. the library statistics measured from the BAM)."""
+    prm = params if params is not None else Params.default()
+    fasta = {k.lower(): v for k, v in read_fasta(fasta_path).items()}
+    with hostlib.Bam(bam_path) as bam:
+        batches = [bam.read_target(t) for t in range(len(bam.names))]
+        st = hostlib.library_stats(batches, prm.min_mapq)
+        prm.insert_mean = max(st["insert_mean"], st["lseq"])            # src/GROM.c:22260
+        prm.insert_min, prm.insert_max, prm.lseq = st["insert_min"], st["insert_max"], st["lseq"]
+        prm.rd_min_mapq = prm.min_mapq                                    # src/GROM.c:22102
+        hez, mq = hostlib.tables(table_dir, prm.min_mapq)
+        gpu.init(device, hez, mq, prm)
+        todo = [t for t, n in enumerate(bam.names) if n.lower() in fasta and not skip_contig(n, prm.gender)]
+        mine = set(todo[i] for i in assign_contigs([bam.lens[t] for t in todo], ranks)[rank])
+        text: Dict[int, str] = {}
+        for t in todo:
+            if t not in mine:
+                continue
+            name = bam.names[t].lower()
+            chars = fasta[name]
+            with gpu.Chromosome(t, chars) as ch:
+                ch.push_reads(batches[t])
+                res = ch.finish()
+                cnv = ch.cnv(params=prm)
+            text[t] = hostlib.vcf_contig(prm, name, chars, res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, cnv.calls)
+    return text, prm
+
+
+VCF_HEADER = "##fileformat=VCFv4.2\n##source=grom-b200\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE\n"
+
+
+def write_vcf(path: str, per_contig: Dict[int, str]):
+    with open(path, "w") as f:
+        f.write(VCF_HEADER)
+        for t in sorted(per_contig):
+            f.write(per_contig[t])

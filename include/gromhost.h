@@ -79,6 +79,14 @@ int64_t gromhost_vcf_smalldel(const grom_params *p, const char *chr_name, const 
 int64_t gromhost_vcf_cnv(const grom_params *p, const char *chr_name, const char *fasta, int64_t chr_len,
                          const grom_cnv_call *calls, int64_t n, char *buf, int64_t cap);
 
+/* ---- library statistics (grom_b200/host/libstats.c) = find_insert_mean, src/GROM.c:1205-1318: feed the per-contig batches in contig
+ * order; finish returns the values the reference caches in <bam>.mean (insert_mean is NOT yet raised to lseq, src/GROM.c:22260). */
+typedef struct gromhost_libstats gromhost_libstats;
+gromhost_libstats *gromhost_libstats_new(int rd_min_mapq);
+int  gromhost_libstats_add(gromhost_libstats *s, const grom_read_batch *b);        /* 1 = sample full (10,000,000 inserts) */
+int  gromhost_libstats_finish(gromhost_libstats *s, int *insert_mean, int *lseq, int *insert_min, int *insert_max, int64_t *mapped_reads);
+void gromhost_libstats_free(gromhost_libstats *s);
+
 /* ---- structural-variant candidate lists (grom_b200/host/svlists.c): the state of cdp_dup_list / cdp_del_list / cdp_inv_f_list /
  * cdp_inv_r_list / cdp_ins_list / cdp_ctx_f_list / cdp_ctx_r_list at src/GROM.c:15164, rebuilt from the gate events of
  * gromgpu_chr_result (any order; sorted into scan order here).  Arrays are malloc'ed, release with gromhost_sv_lists_free. */
