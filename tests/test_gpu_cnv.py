@@ -103,3 +103,43 @@ def test_cnv_short_contig_is_empty():
         ch.run()
         g = ch.cnv()
     assert len(g.calls) == 0 and g.n_samples == 0
+
+
+def test_cnv_size_independent_properties_large():
+    """8 Mb / 30x with planted copy-number segments: properties that hold at any size -- a second run is identical, calls are sorted and
+    disjoint per kind, every window length up to the frame size has observations, the mask covers exactly what it must, the planted
+    one-copy losses are recovered -- plus errors of the C ABI."""
+    spec = synth.SynthSpec(contigs=[("chrL", 8_000_000)], depth=30, seed=31, simple=True, cnv_per_mb=0.5, cnv_min=20000, cnv_max=60000)
+    c = synth.simulate(spec)[0]
+    prm = Params.default()
+    hez, mq = tables_7digit()
+    gpu.init(0, hez, mq, prm)
+    with gpu.Chromosome(0, c.chars) as ch:
+        with pytest.raises(gpu.GromGpuError, match="chr_run first"):
+            ch.cnv()
+        ch.push_reads(c.batch)
+        ch.run()
+        g1 = ch.cnv(); z1 = ch.cnv_fetch("z"); m1 = ch.cnv_fetch("mask"); d1 = ch.cnv_fetch("depth")
+        g2 = ch.cnv(); z2 = ch.cnv_fetch("z")
+        with pytest.raises(gpu.GromGpuError, match="bad range"):
+            ch.cnv_fetch("z", 10, len(c.chars) + 5)
+        rd = ch.fetch("rd_rd") + ch.fetch("rd_low")
+        acgt = ch.fetch("acgt")
+    assert g1.calls.tobytes() == g2.calls.tobytes() and np.array_equal(z1, z2) and np.array_equal(g1.win_sd, g2.win_sd)
+    assert np.array_equal(d1, rd)
+    M = prm.insert_mean
+    lo, hi = M - 1, len(c.chars) - (2 * M - 1)
+    assert m1[:lo].all() and m1[hi:].all() and np.all(m1[lo:hi][acgt[lo:hi] < 99] == 1) and (m1 == 0).mean() > 0.9
+    assert np.all(z1[m1 == 1] == 0)
+    assert np.all(g1.win_cnt[prm.min_rd_window_len:] > 1) and np.all(g1.win_sd[prm.min_rd_window_len:] > 0)
+    # longer windows average more positions: the null sd shrinks (monotone up to sampling noise)
+    assert g1.win_sd[100] > g1.win_sd[1000] > g1.win_sd[10000]
+    for kind in (0, 1):
+        k = g1.calls[g1.calls["kind"] == kind]
+        assert np.all(np.diff(k["start"]) > 0) and np.all(k["start"][1:] > k["end"][:-1]) and np.all(k["end"] >= k["start"])
+        assert np.all((k["z"] >= 3) & (k["pvalue"] < 0.5))        # the reference's erf variant can push strong calls to 0 or slightly below
+    dels = g1.calls[g1.calls["kind"] == 0]
+    for a, b, cn in c.truth["cnv"]:
+        if cn == 1:      # one-copy loss: most of the segment is inside deletion calls
+            cov = sum(max(0, min(b, int(e)) - max(a, int(s))) for s, e in zip(dels["start"], dels["end"]))
+            assert cov > 0.8 * (b - a), (a, b, cov)
