@@ -2,7 +2,7 @@
 compare the CNV path state (pre-statistics, distributions, z list, window sd table, calls, VCF records) with the oracle."""
 import argparse, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from grom_b200 import hostlib
 from grom_b200.params import GA, Params
 from oracle import pyoracle as po

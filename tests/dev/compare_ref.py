@@ -2,7 +2,7 @@
 per-position value with the oracle (needs oracle/_ref/GROM_ref; build container only)."""
 import argparse, os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from grom_b200 import hostlib
 from grom_b200.params import GA_NAMES, Params
 from oracle import pyoracle as po
