@@ -11,7 +11,7 @@
  *   helpers                     bisect_left/right(_double), grom_rand        src/GROM.c:21630-21860, 1185-1203
  *
  * Sequential on purpose: it is the checker.  Pinned against the white-box reference's cnvpre_/cnv_ dumps
- * (oracle/hooks.h) by tests/test_oracle_vs_reference.py and tests/dev/compare_ref.py.
+ *  (oracle/hooks.h): committed fixture tests/golden/g2_cnv.npz (tests/test_oracle_cnv_golden.py), live runs tests/dev/compare_cnv.py.
  */
 #include <math.h>
 #include <stdint.h>
