@@ -697,6 +697,7 @@ __global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, con
     const uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
     land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] = e;
     if (c0 != 2) land[((int64_t)t.kind * cap + t.rank) * 2 + 1] = e;
+    if (e == ((uint32_t)SEG_UNRESOLVED << LAND_SHIFT)) atomicAdd(n_calls + 4, 1u);       // still open after the longer leash
     if (jump0) {
         const uint32_t n_seeds = t.kind ? n_dup : n_del, base = t.kind ? 2 * n_del + 1 : 0;
         const uint32_t *sd = seeds + (int64_t)t.kind * words, *wpk = wp + (int64_t)t.kind * words;

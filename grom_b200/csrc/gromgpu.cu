@@ -1611,7 +1611,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * words)); CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
         c.spec_cap = (uint32_t)std::min<int64_t>(P / 8 + 1024, (int64_t)1 << 28);
         CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
-        CK(cudaMalloc(&c.d_nspec, 4 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (Lmax + 1)));
+        CK(cudaMalloc(&c.d_nspec, 6 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (Lmax + 1)));
     }
 
     // ---- stage 1: pre-statistics + repeat runs
@@ -1961,11 +1961,12 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         // every seed evaluated on the device (bounded); a seed list that outgrew its buffer, or the biased-repeat override (it rewrites
         // z on the host copy after the sweep), leaves the evaluation to the host
         unsigned int n_spec = 0;
+        bool device_hop = false;
         const bool have_land = seed_tot[0] <= c.land_cap && seed_tot[1] <= c.land_cap && (int64_t)Lmax + SEED_BOUND < ((int64_t)1 << LAND_SHIFT) && hi - Lmin > lo;
         if (have_land) {
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
-            CK(cudaMemsetAsync(c.d_nspec, 0, 4 * sizeof(unsigned int), s));
+            CK(cudaMemsetAsync(c.d_nspec, 0, 6 * sizeof(unsigned int), s));
             const uint32_t todo_cap = 32768;
             Grow &t_todo = c.tmp[15];
             if (!t_todo.ensure(sizeof(SeedTodo) * todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
@@ -1989,6 +1990,13 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 k_seed_eval2<<<(cnt2[1] + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), cnt2[1],
                                                                 seed_tot[0], seed_tot[1], J); n_launch++;
             }
+            // every unresolved seed on the path costs one host round trip: when many are left (no second round, or a genome full of
+            // long events) the scan is cheaper on the host, in parallel pieces
+            unsigned int still_open = cnt2[1];
+            if (cnt2[1] > 0 && cnt2[1] <= todo_cap && SEED_BOUND2 < Lmax) CK(cudaMemcpyAsync(&still_open, c.d_nspec + 4, sizeof(still_open), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            device_hop = still_open <= 4096 && !getenv("GROMGPU_CNV_HOST_SCAN");      // the variable forces the host scan (tests)
+            if (device_hop) {
             if (most == 0) CK(cudaMemsetAsync(J, 0, sizeof(uint32_t) * n_nodes, s));
             if (seed_tot[0] == 0 || seed_tot[1] == 0) {                // a scan without seeds: its END node loops on itself
                 const uint32_t e0 = base[0] + 2 * seed_tot[0], e1 = base[1] + 2 * seed_tot[1];
@@ -2002,7 +2010,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             for (int k = 0; k < 2; k++) { k_hop_start<<<1, 1, 0, s>>>(ctx[k], c.d_seed + k * words, c.d_wp + k * words, lo, 0, seed_tot[k], base[k], flag); n_launch++; }
             std::vector<Call> by_host[2];
             std::vector<uint32_t> window;
-            for (int round = 0; round < 100000; round++) {
+            for (int round = 0;; round++) {
+                if (round > 8192) return fail("gromgpu_chr_cnv: the device hop did not terminate");
                 for (int k = levels - 1; k >= 0; k--) { k_hop_mark<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)k * n_nodes, flag, n_nodes); n_launch++; }
                 for (int k = 0; k < 2; k++) if (seed_tot[k]) {
                     k_hop_collect<<<(2 * seed_tot[k] + 255) / 256, 256, 0, s>>>(flag + base[k], done + base[k], c.d_land + (size_t)k * 2 * c.land_cap, c.d_seed + k * words, c.d_wp + k * words, words,
@@ -2055,7 +2064,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             seed_tot_all = 0; n_spec_all = 0;
             if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u, jump table %d levels x %u nodes; calls from the device %u + %u, evaluated on the host %zu + %zu\n", seed_tot[0], seed_tot[1],
                                levels, n_nodes, n_got[0], n_got[1], by_host[0].size(), by_host[1].size());
-        } else {
+            } else { dev_end(); if (trace) fprintf(stderr, "[cnv] %u seeds left unresolved: scanning on the host\n", still_open); }
+        }
+        if (!have_land || !device_hop) {
             // seed tables outgrew their buffers: the whole scan runs on the host over the packed records
             if (pull_records()) return -1;
             Segmenter sg[2];

@@ -90,6 +90,24 @@ def test_cnv_biased_repeat_override():
     _check(o, g, z, mask, mqm, prm)
 
 
+def test_cnv_host_scan_fallback_gives_the_same_calls(monkeypatch):
+    """The segmentation has two routes: hop on the device over the successor table, or (seed tables too large / too many unresolved
+    seeds) the host scan in parallel pieces over the packed records.  Both must agree."""
+    c = _dataset(seed=5, length=3_000_000, depth=30, cnv_per_mb=0.7)
+    prm = Params.default()
+    hez, mq = tables_7digit()
+    gpu.init(0, hez, mq, prm)
+    with gpu.Chromosome(0, c.chars) as ch:
+        ch.push_reads(c.batch)
+        ch.run()
+        a = ch.cnv()
+        monkeypatch.setenv("GROMGPU_CNV_HOST_SCAN", "1")
+        b = ch.cnv()
+        monkeypatch.delenv("GROMGPU_CNV_HOST_SCAN")
+    assert len(a.calls) > 20 and a.calls.tobytes() == b.calls.tobytes()
+    assert np.array_equal(a.win_sd, b.win_sd)
+
+
 def test_cnv_short_contig_is_empty():
     """A contig shorter than the GC window has no analysed span (lo >= hi): no calls, no error."""
     rng = np.random.default_rng(3)
