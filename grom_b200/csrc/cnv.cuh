@@ -410,10 +410,27 @@ __global__ void __launch_bounds__(64) k_sweep_sum(const double *__restrict__ X, 
 // plus the few evaluations the device left unresolved).
 struct SegCtx {
     const uint32_t *rec; int64_t len, end; int q, Lmin, Lmax, bound; const double *sd, *win_sd; bool dup;
+    const double *wtab;          // MAPQ weight per mean MAPQ value [256]: the expression of rec_z evaluated once per value (same doubles, no division per base)
     __host__ __device__ inline int cls(int64_t p) const { return (rec[p] >> R_CLASS) & 3; }
     __host__ __device__ inline bool beyond(int64_t p, int mi) const { return (rec[p] & (dup ? (mi ? R_DUP1 : R_DUP0) : (mi ? R_DEL1 : R_DEL0))) != 0; }
     __host__ __device__ inline bool win_gt1(int64_t p, int mi) const { return (rec[p] & (mi ? R_WIN1 : R_WIN0)) != 0; }
-    __host__ __device__ inline double z(int64_t p) const { const double v = rec_z(rec[p], q, sd); return dup ? -v : v; }
+    __host__ __device__ inline double z(int64_t p) const
+    {
+        const uint32_t r = rec[p];
+        if (!(r & R_NZ)) return 0.0;
+        const double w = (r & R_OVR) ? 1.0 : (((r >> R_CLASS) & 3) == 0 ? wtab[(r >> R_MQ) & 255] : 0.5);
+        const double v = w * sd[(r >> R_K) & 1023];
+        return ((r & R_NEG) != 0) != dup ? -v : v;
+    }
+    // score >= 3 ?  The division is only carried out when the quotient can be anywhere near the threshold (a 1 % margin dwarfs
+    // the rounding of the product and the quotient), so the outcome is the reference's in every case.
+    __host__ __device__ inline bool scores(double tot, int64_t cnt, double sdw, double *score) const
+    {
+        const double den = cnt * sdw;
+        if (!(tot >= 2.97 * den)) return false;
+        *score = tot / den;
+        return *score >= 3;
+    }
 };
 enum { SEG_RESUME = 0, SEG_CALL = 1, SEG_UNRESOLVED = 2 };
 struct Outcome { int kind; int64_t next, c_end; double c_z; int64_t far; };   // far: one past the last position the sliding phase looked at
@@ -436,8 +453,8 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
     }
     cnt = Lmin;
     for (int64_t a = pos; a < pos + Lmin; a++) { cnt -= C.rec[a] & R_MASK; tot += C.z(a); }
-    if (cnt > 0 && tot > 0 && C.win_sd[Lmin] > 0 && tot / (cnt * C.win_sd[Lmin]) >= 3) {   // tot <= 0 cannot score (exact)
-        begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tot / (cnt * C.win_sd[Lmin]);
+    if (cnt > 0 && tot > 0 && C.win_sd[Lmin] > 0 && C.scores(tot, cnt, C.win_sd[Lmin], &tz)) {   // tot <= 0 cannot score (exact)
+        begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tz;
     }
     for (pa = pos + Lmin; pa < pos + Lmax; pa++) {
         wlen++;
@@ -450,8 +467,8 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
             ok = C.beyond(pa, mi);
             if (ok) {
                 cnt2++;
-                if (tot > 0 && C.win_sd[wlen] > 0 && tot / (cnt * C.win_sd[wlen]) >= 3) {
-                    last_good = pa; tz = tot / (cnt * C.win_sd[wlen]);
+                if (tot > 0 && C.win_sd[wlen] > 0 && C.scores(tot, cnt, C.win_sd[wlen], &tz)) {
+                    last_good = pa;
                     if (!begun) { begun = true; c_start = pos; c_end = pa; c_z = tz; }
                     else { c_end = pa; if (tz > c_z) c_z = tz; }
                 }
@@ -476,8 +493,8 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
                 CNV_STEP(mi, pa);
                 if (!(C.rec[pa] & R_MASK) && C.win_gt1(pa, mi)) { tot += C.z(pa); cnt++; }
             }
-            if (cnt > 0 && tot > 0 && C.win_sd[Lmax] > 0 && tot / (cnt * C.win_sd[Lmax]) >= 3) {
-                last_good = pa; c_end = pa; tz = tot / (cnt * C.win_sd[Lmax]);
+            if (cnt > 0 && tot > 0 && C.win_sd[Lmax] > 0 && C.scores(tot, cnt, C.win_sd[Lmax], &tz)) {
+                last_good = pa; c_end = pa;
                 if (tz > c_z) c_z = tz;
             }
             pa++;

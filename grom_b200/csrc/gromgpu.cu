@@ -1506,7 +1506,7 @@ struct CnvState {
     std::vector<double> win_sd, bin_d; std::vector<int64_t> win_cnt, bin_n;
     int64_t P = 0, words = 0;
     int q = 0;
-    std::vector<double> sd_tbl;
+    std::vector<double> sd_tbl, wtab;
     cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec;
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr;   // packed records travel to the host while the sweep runs
 };
@@ -1852,8 +1852,10 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     }
     Grow &t_cum = c.tmp[7], &t_n = c.tmp[8], &t_small = c.tmp[9], &t_dbl = c.tmp[10];
     if (!t_cum.ensure(sizeof(int32_t) * cum.size()) || !t_n.ensure(sizeof(int32_t) * NLIST) || !t_small.ensure(sizeof(int32_t) * 2 * NLIST) ||
-        !t_dbl.ensure(sizeof(double) * (3 * NLIST + 2 * P2S))) return fail("gromgpu_chr_cnv: out of device memory");
-    std::vector<double> dbl(3 * NLIST + 2 * P2S);
+        !t_dbl.ensure(sizeof(double) * (3 * NLIST + 2 * P2S + 256))) return fail("gromgpu_chr_cnv: out of device memory");
+    std::vector<double> dbl(3 * NLIST + 2 * P2S + 256);
+    c.wtab.resize(256);
+    for (int m = 0; m < 256; m++) c.wtab[m] = dbl[3 * NLIST + 2 * P2S + m] = 0.5 + (1.0 - 0.5) * (m - q) / (double)(RD_MAX_MAPQ - q);      // rec_z's weight, per mean MAPQ
     std::copy(ave.begin(), ave.end(), dbl.begin()); std::copy(del_thr.begin(), del_thr.end(), dbl.begin() + NLIST); std::copy(dup_thr.begin(), dup_thr.end(), dbl.begin() + 2 * NLIST);
     std::copy(p2s_p, p2s_p + P2S, dbl.begin() + 3 * NLIST); std::copy(p2s_sd, p2s_sd + P2S, dbl.begin() + 3 * NLIST + P2S);
     Tables T;
@@ -1957,7 +1959,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     int64_t seed_tot_all = 0, n_spec_all = 0;
     {
         SegCtx ctx[2];
-        for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].dup = k == 1; }
+        for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].dup = k == 1; ctx[k].wtab = T.p2s_sd + P2S; }
         // every seed evaluated on the device (bounded); a seed list that outgrew its buffer, or the biased-repeat override (it rewrites
         // z on the host copy after the sweep), leaves the evaluation to the host
         unsigned int n_spec = 0;
@@ -2033,7 +2035,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                         CK(cudaMemcpy(window.data(), c.d_rec + pos, sizeof(uint32_t) * (w1 - pos), cudaMemcpyDeviceToHost));
                         d2h += 4 * (w1 - pos);
                         SegCtx hc = ctx[k];
-                        hc.rec = window.data() - pos; hc.len = w1; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data();
+                        hc.rec = window.data() - pos; hc.len = w1; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data(); hc.wtab = c.wtab.data();
                         c0 = hc.cls(pos);
                         o = eval_seed<false>(hc, pos, c0 != 2 ? c0 : sink[k].variant);
                         if (w1 == P || o.far < w1) break;
@@ -2071,7 +2073,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             if (pull_records()) return -1;
             Segmenter sg[2];
             for (int k = 0; k < 2; k++) {
-                sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
+                sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].C.wtab = c.wtab.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
             }
             const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));
             std::thread th([&]() { sg[1].run(found[1], per_scan); });
