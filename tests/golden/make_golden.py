@@ -146,8 +146,51 @@ def main_sv():
     shutil.rmtree(tmp)
 
 
+def main_vcf():
+    """g4_vcf.npz: every input of the per-contig record writer (candidates, events, read-depth calls, FASTA) for a contig on which the
+    reference emits every record class (SNV, <DUP>, <INV>, <INS>, small INS / DEL, <DEL>, read-depth <DEL>/<DUP>), and its VCF text."""
+    from grom_b200 import hostlib
+    from grom_b200.params import CNV_CALL_DTYPE, Params
+    spec = synth.SynthSpec(contigs=[("chrA", 1_500_000), ("chrB", 200_000), ("chrZ", 50_000)], depth=40, seed=17, dup_frac=0.05, sa_frac=0.5,
+                           disc_frac=0.03, sv_sites_per_mb=10.0, munmap_frac=0.01, sv_classes=12, cnv_per_mb=0.7, cnv_min=15000, cnv_max=30000)
+    cs = synth.simulate(spec)
+    tmp = tempfile.mkdtemp()
+    fa, bam = synth.write_dataset(os.path.join(tmp, "g4"), cs)
+    vcf = os.path.join(tmp, "g4.vcf")
+    po.run_reference(bam, fa, vcf, kind="dist", seed=1)
+    m = po.read_mean_file(bam)
+    prm = Params.default(insert_mean=max(m["insert_mean"], m["lseq"]), insert_min=m["insert_min"], insert_max=m["insert_max"], lseq=m["lseq"])
+    hez, mq = po.reference_tables(20)
+    c = cs[0]
+    with hostlib.Bam(bam) as b:
+        r = po.run_chr(prm, b.read_target(0), c.chars, hez, mq)
+    cn = po.cnv_run(prm, "chra", c.chars, r["gc"], r["acgt"], r["rd_mq"], r["rd_rd"], r["rd_low"])
+    calls = np.zeros(len(cn.dels) + len(cn.dups), dtype=CNV_CALL_DTYPE)
+    for k, src in enumerate((cn.dels, cn.dups)):
+        sl = slice(0, len(cn.dels)) if k == 0 else slice(len(cn.dels), None)
+        calls["start"][sl] = src["start"]; calls["end"][sl] = src["end"]; calls["kind"][sl] = k; calls["z"][sl] = src["z"]
+        calls["pvalue"][sl] = src["p"]; calls["cn"][sl] = src["cn"]; calls["cn_sd"][sl] = src["cs"]
+    ref = [l for l in open(vcf) if l.startswith("chra\t")]
+    mine = hostlib.vcf_contig(prm, "chra", c.chars, r.snv, r.snv_ave_rd, r.ins, r.del_ev, r.sv_ev, calls).splitlines(keepends=True)
+    assert po.normalise_records(mine) == po.normalise_records(ref)
+    kinds = {}
+    for l in ref:
+        f = l.split("\t")
+        k = f[4] + ("/cnv" if f[8] == "SD:Z:CN:CS" else "") if f[4].startswith("<") else ("snv" if f[2] == "" else "indel")
+        kinds[k] = kinds.get(k, 0) + 1
+    print("g4 record classes:", kinds)
+    assert all(k in kinds for k in ("snv", "indel", "<DUP>", "<INV>", "<INS>", "<DEL>", "<DEL>/cnv")), kinds
+    np.savez_compressed(os.path.join(HERE, "g4_vcf.npz"), fasta=c.chars, snv=r.snv, snv_ave_rd=np.array(r.snv_ave_rd), ins=r.ins, del_ev=r.del_ev,
+                        sv_ev=r.sv_ev, cnv=calls, vcf=np.array("".join(ref)),
+                        mean=np.array([m[k] for k in ("insert_mean", "lseq", "insert_min", "insert_max", "mapped_reads")]))
+    print("g4_vcf: %d records, %.2f MB" % (len(ref), os.path.getsize(os.path.join(HERE, "g4_vcf.npz")) / 1e6))
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "sv":
+    if len(sys.argv) > 1 and sys.argv[1] == "vcf":
+        main_vcf()
+    elif len(sys.argv) > 1 and sys.argv[1] == "sv":
         main_sv()
     elif len(sys.argv) > 1 and sys.argv[1] == "cnv":
         main_cnv()
@@ -155,3 +198,4 @@ if __name__ == "__main__":
         main()
         main_cnv()
         main_sv()
+        main_vcf()

@@ -55,3 +55,20 @@ def test_smalldel_state_machine_edge_cases():
     ev["pos"] = [1000, 1004, 3000]; ev["kind"] = [0, 1, 0]; ev["pr"] = 1e-9; ev["weight"] = 60; ev["rd"] = 20; ev["rdist"] = 5
     out = hostlib.vcf_smalldel(prm, "c", fa, ev).splitlines()
     assert len(out) == 1 and out[0].startswith("c\t1001\t.\t" + bytes(fa[1000:1005]).decode() + "\t.\t.\t.\tEND=1005\t")
+
+
+def test_contig_writer_all_record_classes_against_reference_vcf():
+    """tests/golden/g4_vcf.npz: the inputs of gromhost_vcf_contig for a contig on which the reference (prebuilt dist/GROM) emits every
+    record class, and the reference's own text: 1,695 records incl. <DUP>, <INV>, <INS>, paired-end and read-depth <DEL>."""
+    g = np.load(os.path.join(GOLDEN, "g4_vcf.npz"))
+    m = g["mean"]
+    from grom_b200.params import Params
+    prm = Params.default(insert_mean=int(max(m[0], m[1])), lseq=int(m[1]), insert_min=int(m[2]), insert_max=int(m[3]))
+    mine = hostlib.vcf_contig(prm, "chra", g["fasta"], g["snv"], float(g["snv_ave_rd"]), g["ins"], g["del_ev"], g["sv_ev"], g["cnv"])
+    ref = str(g["vcf"]).splitlines(keepends=True)
+    assert po.normalise_records(mine.splitlines(keepends=True)) == po.normalise_records(ref)
+    for tag in ("<DUP>", "<INV>", "<INS>", "<DEL>", "SD:Z:CN:CS", "SSC:ESC:HP", "SSC:HP"):
+        assert any(tag in l for l in ref), tag
+    # per-class writers agree with the one-call writer on their share
+    assert hostlib.vcf_snv(prm, "chra", g["fasta"], g["snv"], float(g["snv_ave_rd"])) == "".join(l for l in ref if l.split("\t")[2] == "")
+    assert hostlib.vcf_cnv(prm, "chra", g["cnv"]) == "".join(l for l in ref if "\tSD:Z:CN:CS\t" in l)

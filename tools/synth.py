@@ -406,7 +406,7 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
                 kind = k % 5
                 a = int(rng.integers(20000, max(20001, length - 60000))); dl = int(rng.integers(1500, 20000))
                 tgt = int(rng.integers(5000, max(5001, contig_lens[other] - 5000)))
-                lo = np.searchsorted(fs, a - 380); hi2 = np.searchsorted(fs, a - 100)
+                lo = np.searchsorted(fs, a - 380); hi2 = np.searchsorted(fs, a - (20 if kind == 4 else 100))
                 for p in range(lo, hi2):
                     ia, ib = 2 * p, 2 * p + 1
                     if ia in cig or ib in cig or (flag[ia] | flag[ib]) & (FUNMAP | FMUNMAP) or mtid[ia] != tid or not (flag[ia] & FPROPER):
