@@ -424,7 +424,7 @@ struct SegCtx {
     }
     // score >= 3 ?  The division is only carried out when the quotient can be anywhere near the threshold (a 1 % margin dwarfs
     // the rounding of the product and the quotient), so the outcome is the reference's in every case.
-    __host__ __device__ inline bool scores(double tot, int64_t cnt, double sdw, double *score) const
+    __host__ __device__ inline bool scores(double tot, int cnt, double sdw, double *score) const
     {
         const double den = cnt * sdw;
         if (!(tot >= 2.97 * den)) return false;
@@ -442,7 +442,8 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
     const int64_t Lmin = C.Lmin, Lmax = C.Lmax, end = C.end, max_gap = Lmax + 500;
     Outcome o; o.kind = SEG_RESUME; o.next = pos + 1; o.c_end = 0; o.c_z = 0; o.far = 0;
     bool stop = false, begun = false;
-    int64_t wlen = 0, cnt = 0, cnt2 = 0, pa, c_start = 0, c_end = 0, last_good = 0;
+    int wlen = 0, cnt = 0, cnt2 = 0;                        // window length and counters fit 32 bits (Lmax positions at most)
+    int64_t pa, c_start = 0, c_end = 0, last_good = 0;
     double tot = 0, c_z = 0, tz;
     for (pa = pos; pa < pos + Lmin; pa++) {
         wlen++;
@@ -451,8 +452,8 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
         if (ok) cnt2++;
         else if (2 * cnt2 < wlen) { o.next = pa + 1; return o; }            // give up inside the first window: resume after the offender
     }
-    cnt = Lmin;
-    for (int64_t a = pos; a < pos + Lmin; a++) { cnt -= C.rec[a] & R_MASK; tot += C.z(a); }
+    cnt = (int)Lmin;
+    for (int64_t a = pos; a < pos + Lmin; a++) { cnt -= (int)(C.rec[a] & R_MASK); tot += C.z(a); }
     if (cnt > 0 && tot > 0 && C.win_sd[Lmin] > 0 && C.scores(tot, cnt, C.win_sd[Lmin], &tz)) {   // tot <= 0 cannot score (exact)
         begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tz;
     }
@@ -665,7 +666,7 @@ __device__ __forceinline__ uint32_t seed_outcome(const SegCtx &C, int64_t p, int
     }
     return unres;
 }
-__global__ void __launch_bounds__(128) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+__global__ void __launch_bounds__(128, 8) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
                                                    unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ todo, uint32_t todo_cap, uint32_t *__restrict__ jump0)
 {
