@@ -1964,7 +1964,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         // z on the host copy after the sweep), leaves the evaluation to the host
         unsigned int n_spec = 0;
         bool device_hop = false;
-        const bool have_land = seed_tot[0] <= c.land_cap && seed_tot[1] <= c.land_cap && (int64_t)Lmax + SEED_BOUND < ((int64_t)1 << LAND_SHIFT) && hi - Lmin > lo;
+        const bool have_land = !getenv("GROMGPU_CNV_NO_SEED_TABLES") && seed_tot[0] <= c.land_cap && seed_tot[1] <= c.land_cap && (int64_t)Lmax + SEED_BOUND < ((int64_t)1 << LAND_SHIFT) && hi - Lmin > lo;
         if (have_land) {
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
@@ -1976,10 +1976,12 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             const uint32_t n_nodes = 2 * seed_tot[0] + 1 + 2 * seed_tot[1] + 1, base[2] = {0u, 2 * seed_tot[0] + 1};
             int levels = 1;
             while ((1ull << levels) < (unsigned long long)2 * std::max(seed_tot[0], seed_tot[1]) + 2) levels++;
-            if (!c.jump.ensure(sizeof(uint32_t) * (size_t)levels * n_nodes) || !c.flags.ensure(2 * (size_t)n_nodes) ||
-                !c.hop_out.ensure(sizeof(HopCall) * (size_t)c.spec_cap) || !c.hop_sink.ensure(2 * sizeof(HopSink))) return fail("gromgpu_chr_cnv: out of device memory for the jump table");
-            uint32_t *J = c.jump.as<uint32_t>();
-            uint8_t *flag = c.flags.as<uint8_t>(), *done = flag + n_nodes;
+            // no room for the jump table (levels x nodes words): the seed tables still serve the host scan below
+            const bool jump_ok = !getenv("GROMGPU_CNV_HOST_SCAN") && c.jump.ensure(sizeof(uint32_t) * (size_t)levels * n_nodes) && c.flags.ensure(2 * (size_t)n_nodes) &&
+                                 c.hop_out.ensure(sizeof(HopCall) * (size_t)c.spec_cap) && c.hop_sink.ensure(2 * sizeof(HopSink));
+            if (!jump_ok) cudaGetLastError();
+            uint32_t *J = jump_ok ? c.jump.as<uint32_t>() : nullptr;
+            uint8_t *flag = jump_ok ? c.flags.as<uint8_t>() : nullptr, *done = jump_ok ? flag + n_nodes : nullptr;
             const uint32_t most = std::max(seed_tot[0], seed_tot[1]);
             if (most) { k_seed_eval<<<dim3((most + 127) / 128, 2), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
                                                                               c.d_nspec, t_todo.as<SeedTodo>(), todo_cap, J); n_launch++; }
@@ -1997,7 +1999,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             unsigned int still_open = cnt2[1];
             if (cnt2[1] > 0 && cnt2[1] <= todo_cap && SEED_BOUND2 < Lmax) CK(cudaMemcpyAsync(&still_open, c.d_nspec + 4, sizeof(still_open), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            device_hop = still_open <= 4096 && !getenv("GROMGPU_CNV_HOST_SCAN");      // the variable forces the host scan (tests)
+            device_hop = jump_ok && still_open <= 4096;       // GROMGPU_CNV_HOST_SCAN forces the host scan (tests)
             if (device_hop) {
             if (most == 0) CK(cudaMemsetAsync(J, 0, sizeof(uint32_t) * n_nodes, s));
             if (seed_tot[0] == 0 || seed_tot[1] == 0) {                // a scan without seeds: its END node loops on itself
@@ -2069,11 +2071,22 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             } else { dev_end(); if (trace) fprintf(stderr, "[cnv] %u seeds left unresolved: scanning on the host\n", still_open); }
         }
         if (!have_land || !device_hop) {
-            // seed tables outgrew their buffers: the whole scan runs on the host over the packed records
+            // host scan over the packed records, in parallel pieces; with the device-evaluated seed tables when they exist (the hop is
+            // then a table walk and only unresolved seeds are evaluated here), without them every seed is evaluated on the host
             if (pull_records()) return -1;
+            unsigned int n_spec_host = 0;
+            if (have_land) {
+                for (int k = 0; k < 2; k++) if (seed_tot[k]) CK(cudaMemcpyAsync(c.h_land + (size_t)k * 2 * c.land_cap, c.d_land + (size_t)k * 2 * c.land_cap, sizeof(uint32_t) * 2 * seed_tot[k], cudaMemcpyDeviceToHost, s));
+                CK(cudaMemcpyAsync(&n_spec_host, c.d_nspec, sizeof(n_spec_host), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                n_spec_host = std::min(n_spec_host, c.spec_cap);
+                if (n_spec_host) CK(cudaMemcpy(c.h_spec, c.d_spec, sizeof(SeedCall) * n_spec_host, cudaMemcpyDeviceToHost));
+                d2h += 8 * ((int64_t)seed_tot[0] + seed_tot[1]) + 16 * (int64_t)n_spec_host;
+            }
             Segmenter sg[2];
             for (int k = 0; k < 2; k++) {
                 sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].C.wtab = c.wtab.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
+                if (have_land) { sg[k].wp = c.h_wp + k * words; sg[k].land = c.h_land + (size_t)k * 2 * c.land_cap; sg[k].spec = c.h_spec; }
             }
             const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));
             std::thread th([&]() { sg[1].run(found[1], per_scan); });

@@ -101,10 +101,13 @@ def test_cnv_host_scan_fallback_gives_the_same_calls(monkeypatch):
         ch.push_reads(c.batch)
         ch.run()
         a = ch.cnv()
-        monkeypatch.setenv("GROMGPU_CNV_HOST_SCAN", "1")
+        monkeypatch.setenv("GROMGPU_CNV_HOST_SCAN", "1")             # host walk over the device-evaluated seed tables
         b = ch.cnv()
         monkeypatch.delenv("GROMGPU_CNV_HOST_SCAN")
-    assert len(a.calls) > 20 and a.calls.tobytes() == b.calls.tobytes()
+        monkeypatch.setenv("GROMGPU_CNV_NO_SEED_TABLES", "1")        # every seed evaluated on the host
+        d = ch.cnv()
+        monkeypatch.delenv("GROMGPU_CNV_NO_SEED_TABLES")
+    assert len(a.calls) > 20 and a.calls.tobytes() == b.calls.tobytes() == d.calls.tobytes()
     assert np.array_equal(a.win_sd, b.win_sd)
 
 
