@@ -226,3 +226,37 @@ def library_stats(batches, rd_min_mapq: int = 20) -> dict:
         return dict(insert_mean=v[0].value, lseq=v[1].value, insert_min=v[2].value, insert_max=v[3].value, mapped_reads=m.value)
     finally:
         L.gromhost_libstats_free(h)
+
+
+def ctx_contig(params, tid: int, sv_ev: np.ndarray) -> np.ndarray:
+    """Translocation records of one contig (candidate merge + emission filter, reference src/GROM.c:16098-16246) from its gate events."""
+    from .params import CTX_RECORD_DTYPE, SV_EVENT_DTYPE
+    L = lib()
+    L.gromhost_ctx_contig.restype = C.c_int64
+    L.gromhost_ctx_contig.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+    lists = sv_lists(params, sv_ev)
+    f, r = np.ascontiguousarray(lists["ctx_f"], dtype=SV_EVENT_DTYPE), np.ascontiguousarray(lists["ctx_r"], dtype=SV_EVENT_DTYPE)
+    out = np.zeros(len(f) + len(r) + 1, dtype=CTX_RECORD_DTYPE)
+    n = L.gromhost_ctx_contig(C.byref(params), tid, f.ctypes.data, len(f), r.ctypes.data, len(r), out.ctypes.data, len(out))
+    if n < 0:
+        raise RuntimeError("gromhost_ctx_contig failed")
+    return out[:n].copy()
+
+
+def ctx_vcf(params, target_names, records: np.ndarray) -> str:
+    """Mate pairing across contigs and the .ctx.vcf records (reference src/GROM.c:22470-22745); records = concatenation of
+    ctx_contig() results in contig processing order."""
+    from .params import CTX_RECORD_DTYPE
+    L = lib()
+    L.gromhost_ctx_vcf.restype = C.c_int64
+    names = [n.lower().encode() for n in target_names]
+    arr = (C.c_char_p * len(names))(*names)
+    rec = np.ascontiguousarray(records, dtype=CTX_RECORD_DTYPE).copy()
+    cap = 1 << 16
+    while True:
+        buf = C.create_string_buffer(cap)
+        n = L.gromhost_ctx_vcf(C.byref(params), arr, len(names), C.c_void_p(rec.ctypes.data), C.c_int64(len(rec)), buf, C.c_int64(cap))
+        if n >= 0:
+            return buf.raw[:n].decode()
+        cap *= 4
+        rec = np.ascontiguousarray(records, dtype=CTX_RECORD_DTYPE).copy()

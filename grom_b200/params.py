@@ -87,6 +87,11 @@ SV_SIDE_DTYPE = np.dtype([("pos", np.int32), ("weight", np.int32), ("rd", np.int
 SV_PAIR_DTYPE = np.dtype([("start", SV_SIDE_DTYPE), ("end", SV_SIDE_DTYPE), ("dist", np.float64)], align=True)
 assert SV_SIDE_DTYPE.itemsize == 48 and SV_PAIR_DTYPE.itemsize == 104, (SV_SIDE_DTYPE.itemsize, SV_PAIR_DTYPE.itemsize)
 
+CTX_RECORD_DTYPE = np.dtype([("type", np.int32), ("chr", np.int32), ("pos", np.int32), ("rd", np.int32), ("conc", np.int32), ("other_len", np.int32),
+                             ("mchr", np.int32), ("mpos", np.int32), ("read_start", np.int32), ("read_end", np.int32), ("mate_id", np.int32),
+                             ("keep", np.int32), ("binom", np.float64), ("evidence", np.float64), ("hez", np.float64)], align=True)
+assert CTX_RECORD_DTYPE.itemsize == 72, CTX_RECORD_DTYPE.itemsize
+
 CNV_CALL_DTYPE = np.dtype([("start", np.int64), ("end", np.int64), ("kind", np.int32), ("reserved", np.int32), ("z", np.float64),
                            ("pvalue", np.float64), ("cn", np.float64), ("cn_sd", np.float64)], align=True)
 assert CNV_CALL_DTYPE.itemsize == 56, CNV_CALL_DTYPE.itemsize

@@ -38,8 +38,9 @@ def read_fasta(path: str) -> Dict[str, np.ndarray]:
 
 
 def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = None, device: int = 0, rank: int = 0, ranks: int = 1,
-                  table_dir: Optional[str] = None) -> Tuple[Dict[int, str], Params]:
-    """Returns ({tid: record text of that contig}, the parameters incl. the library statistics measured from the BAM)."""
+                  table_dir: Optional[str] = None, ctx_out: Optional[Dict[int, np.ndarray]] = None) -> Tuple[Dict[int, str], Params]:
+    """Returns ({tid: record text of that contig}, the parameters incl. the library statistics measured from the BAM).  If `ctx_out` is
+    given it receives {tid: translocation records of that contig} for `ctx_vcf_text` (the pairing needs the records of all contigs)."""
     prm = params if params is not None else Params.default()
     fasta = {k.lower(): v for k, v in read_fasta(fasta_path).items()}
     with hostlib.Bam(bam_path) as bam:
@@ -63,7 +64,17 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
                 res = ch.finish()
                 cnv = ch.cnv(params=prm)
             text[t] = hostlib.vcf_contig(prm, name, chars, res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, cnv.calls)
+            if ctx_out is not None:
+                ctx_out[t] = hostlib.ctx_contig(prm, t, res.sv_ev)
     return text, prm
+
+
+def ctx_vcf_text(params: Params, target_names: List[str], per_contig: Dict[int, np.ndarray]) -> str:
+    """Body of <out>.ctx.vcf: mate pairing over the translocation records of all contigs (all ranks), in contig order."""
+    from .params import CTX_RECORD_DTYPE
+    recs = [per_contig[t] for t in sorted(per_contig)]
+    allrec = np.concatenate(recs) if recs else np.zeros(0, dtype=CTX_RECORD_DTYPE)
+    return hostlib.ctx_vcf(params, target_names, allrec)
 
 
 VCF_HEADER = "##fileformat=VCFv4.2\n##source=grom-b200\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE\n"
@@ -74,3 +85,9 @@ def write_vcf(path: str, per_contig: Dict[int, str]):
         f.write(VCF_HEADER)
         for t in sorted(per_contig):
             f.write(per_contig[t])
+
+
+def write_ctx_vcf(path: str, body: str):
+    with open(path, "w") as f:
+        f.write("##fileformat=VCFv4.2\n##source=grom-b200\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\n")
+        f.write(body)

@@ -98,6 +98,21 @@ typedef struct gromhost_sv_lists_t {
 int  gromhost_sv_lists(const grom_params *p, const grom_sv_event *events, int64_t n_events, gromhost_sv_lists_t *out);
 void gromhost_sv_lists_free(gromhost_sv_lists_t *l);
 
+/* ---- translocations (grom_b200/host/ctx.c): per-contig candidate merge + filter (src/GROM.c:16098-16246), then the genome-level mate
+ * pairing and the <out>.ctx.vcf records (src/GROM.c:22470-22745).  target_names: BAM target names, lower-cased, indexed by tid. */
+typedef struct grom_ctx_record {
+    int32_t type;               /* 6 = CTX_F, 7 = CTX_R (the reference's g_sv_types index) */
+    int32_t chr, pos;           /* contig (tid) and 0-based position */
+    int32_t rd, conc, other_len;
+    int32_t mchr, mpos;         /* mate contig and signed mate position (sign = mate strand); pairing overwrites mpos with the mate's position */
+    int32_t read_start, read_end;
+    int32_t mate_id, keep;      /* filled by gromhost_ctx_vcf */
+    double  binom, evidence, hez;   /* rounded through "%e" / "%.1f" text like the reference's intermediate file */
+} grom_ctx_record;
+int64_t gromhost_ctx_contig(const grom_params *p, int tid, const grom_sv_event *ctx_f, int64_t n_f, const grom_sv_event *ctx_r, int64_t n_r,
+                            grom_ctx_record *out, int64_t cap);
+int64_t gromhost_ctx_vcf(const grom_params *p, const char *const *target_names, int n_targets, grom_ctx_record *rec, int64_t n, char *buf, int64_t cap);
+
 /* Every record of one contig in the reference's output order (src/GROM.c:15046-17500): SNV, <DUP>, <INV>, <INS>, small insertions,
  * small deletions, <DEL>, read-depth <DEL>/<DUP>; includes the list -> list2 merge of the structural-variant candidates
  * (src/GROM.c:15164-16090) and the mutual suppression of small and paired-end deletions (16351-16560).  Inputs are the pieces of

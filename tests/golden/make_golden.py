@@ -187,8 +187,41 @@ def main_vcf():
     shutil.rmtree(tmp)
 
 
+def main_ctx():
+    """g5_ctx.npz: translocation gate events of every contig of a data set with reciprocal inter-contig clusters, and the reference's
+    <out>.ctx.vcf records (white-box build == prebuilt binary)."""
+    from grom_b200 import hostlib
+    from grom_b200.params import Params
+    spec = synth.SynthSpec(contigs=[("chrA", 300_000), ("chrB", 300_000), ("chrZ", 50_000)], depth=30, seed=31, sv_classes=20, disc_frac=0.005)
+    cs = synth.simulate(spec)
+    tmp = tempfile.mkdtemp()
+    fa, bam = synth.write_dataset(os.path.join(tmp, "g5"), cs)
+    po.run_reference(bam, fa, os.path.join(tmp, "g5.vcf"), kind="ref")
+    ref = [l for l in open(os.path.join(tmp, "g5.ctx.vcf")) if not l.startswith("#")]
+    po.run_reference(bam, fa, os.path.join(tmp, "g5d.vcf"), kind="dist")
+    assert ref == [l for l in open(os.path.join(tmp, "g5d.ctx.vcf")) if not l.startswith("#")] and len(ref) >= 4
+    m = po.read_mean_file(bam)
+    prm = Params.default(insert_mean=max(m["insert_mean"], m["lseq"]), insert_min=m["insert_min"], insert_max=m["insert_max"], lseq=m["lseq"])
+    hez, mq = po.reference_tables(20)
+    out = dict(vcf=np.array("".join(ref)), names=np.array([c.name for c in cs]),
+               mean=np.array([m[k] for k in ("insert_mean", "lseq", "insert_min", "insert_max", "mapped_reads")]))
+    recs = []
+    with hostlib.Bam(bam) as b:
+        for tid, c in enumerate(cs):
+            r = po.run_chr(prm, b.read_target(tid), c.chars, hez, mq)
+            ev = r.sv_ev[r.sv_ev["cls"] >= 8]
+            out[f"events_{tid}"] = ev[ev["cls"] <= 9]
+            recs.append(hostlib.ctx_contig(prm, tid, r.sv_ev))
+    assert hostlib.ctx_vcf(prm, [c.name for c in cs], np.concatenate(recs)).splitlines(keepends=True) == ref
+    np.savez_compressed(os.path.join(HERE, "g5_ctx.npz"), **out)
+    print("g5_ctx: %d records, %d candidates, %.2f MB" % (len(ref), sum(len(x) for x in recs), os.path.getsize(os.path.join(HERE, "g5_ctx.npz")) / 1e6))
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "vcf":
+    if len(sys.argv) > 1 and sys.argv[1] == "ctx":
+        main_ctx()
+    elif len(sys.argv) > 1 and sys.argv[1] == "vcf":
         main_vcf()
     elif len(sys.argv) > 1 and sys.argv[1] == "sv":
         main_sv()
@@ -199,3 +232,4 @@ if __name__ == "__main__":
         main_cnv()
         main_sv()
         main_vcf()
+        main_ctx()

@@ -26,3 +26,24 @@ def test_pipeline_reproduces_reference_vcf(tmp_path, tag, rmdup):
     out = tmp_path / "out.vcf"
     pipeline.write_vcf(str(out), text)
     assert [l for l in open(out) if not l.startswith("#")] == mine
+
+
+def test_pipeline_translocations(tmp_path):
+    """BAM + FASTA with reciprocal inter-contig clusters: the .ctx.vcf body from the GPU pipeline == the one the host stages produce from
+    the oracle's gate events (which tests/test_sv_lists_golden.py pins on the reference's own .ctx.vcf)."""
+    from util import tables_7digit
+    from grom_b200 import hostlib
+    from tools import synth
+    spec = synth.SynthSpec(contigs=[("chrA", 300_000), ("chrB", 300_000), ("chrZ", 50_000)], depth=30, seed=31, sv_classes=20, disc_frac=0.005)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "ctx"), cs)
+    ctx = {}
+    text, prm = pipeline.call_variants(bam, fa, Params.default(), ctx_out=ctx)
+    body = pipeline.ctx_vcf_text(prm, [c.name for c in cs], ctx)
+    hez, mq = hostlib.tables(None, prm.min_mapq)
+    want = []
+    with hostlib.Bam(bam) as b:
+        for tid, c in enumerate(cs):
+            r = po.run_chr(prm, b.read_target(tid), c.chars, hez, mq)
+            want.append(hostlib.ctx_contig(prm, tid, r.sv_ev))
+    assert body == hostlib.ctx_vcf(prm, [c.name for c in cs], np.concatenate(want)) and body.count("SVTYPE=BND") >= 4

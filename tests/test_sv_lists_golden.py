@@ -56,3 +56,19 @@ def test_oracle_gates_and_list_builder_on_golden_bam():
             assert mine[k].tobytes() == ref.tobytes(), (name, k, len(mine[k]), len(ref))
             n += len(ref)
     assert n >= 0          # the small random g1 contigs have few (or no) passing gates; the rich case is g3 above
+
+
+def test_translocation_records_against_reference_ctx_vcf():
+    """tests/golden/g5_ctx.npz: per-contig translocation gate events -> candidate merge + filter (gromhost_ctx_contig) -> mate pairing
+    across contigs and BND records (gromhost_ctx_vcf) == the reference's <out>.ctx.vcf."""
+    g = np.load(os.path.join(GOLDEN, "g5_ctx.npz"))
+    m = g["mean"]
+    prm = Params.default(insert_mean=int(max(m[0], m[1])), lseq=int(m[1]), insert_min=int(m[2]), insert_max=int(m[3]))
+    names = [str(x) for x in g["names"]]
+    recs = [hostlib.ctx_contig(prm, tid, g[f"events_{tid}"]) for tid in range(len(names))]
+    text = hostlib.ctx_vcf(prm, names, np.concatenate(recs))
+    assert text == str(g["vcf"]) and text.count("SVTYPE=BND") >= 4
+    ids = [int(l.split("\t")[2]) for l in text.splitlines()]
+    mates = [int(l.split("MATEID=")[1].split("\t")[0]) for l in text.splitlines()]
+    assert sorted(ids) == sorted(mates)                       # every kept record's mate is kept too
+    assert hostlib.ctx_vcf(prm, names, np.concatenate(recs)[:0]) == ""

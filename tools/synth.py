@@ -450,9 +450,23 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
                         codes[ia, :rl] = hap[0][pos[ia]:pos[ia] + rl]
                     else:                # translocation: both mates are reported on the other contig
                         j = int(rng.integers(0, 120))
+                        if other > tid and (other, a, tgt, tid) not in _CTX_PLANTS.setdefault(spec.seed, []):
+                            _CTX_PLANTS[spec.seed].append((other, a, tgt, tid))      # the other contig gets the reciprocal reads
                         mtid[ia] = other; mpos[ia] = tgt + j; tlen[ia] = 0; flag[ia] = FPAIRED | FMREVERSE | FREAD1
                         mtid[ib] = other; mpos[ib] = tgt + 5000 + j; tlen[ib] = 0; flag[ib] = FPAIRED | FREVERSE | FREAD2
                     codes[ib, :rl] = hap[0][pos[ib]:pos[ib] + rl]
+            # reciprocal side of the translocations planted on earlier contigs: reverse reads just after the target point whose mates
+            # are reported back on the source contig, just before its breakpoint
+            for (dst, a_src, tgt_here, src) in [x for x in _CTX_PLANTS.get(spec.seed, []) if len(x) == 4 and x[0] == tid]:
+                lo = np.searchsorted(fs, tgt_here - 300); hi2 = np.searchsorted(fs, tgt_here - 100)
+                for p in range(lo, hi2):
+                    ia, ib = 2 * p, 2 * p + 1
+                    if ia in cig or ib in cig or (flag[ia] | flag[ib]) & (FUNMAP | FMUNMAP) or mtid[ia] != tid or not (flag[ia] & FPROPER):
+                        continue
+                    if not (tgt_here <= pos[ib] < tgt_here + 130):
+                        continue
+                    mtid[ib] = src; mpos[ib] = a_src - 300 + int(pos[ib] - tgt_here); tlen[ib] = 0; flag[ib] = FPAIRED | FREVERSE | FREAD2
+                    mtid[ia] = src; mpos[ia] = a_src + 5000; tlen[ia] = 0; flag[ia] = FPAIRED | FMREVERSE | FREAD1
         truth = {"snv_pos": snv_pos, "snv_het": het, "sv": np.array(truth_sv, dtype=np.int64).reshape(-1, 2), "cnv": cnv_truth}
     else:
         truth = {"snv_pos": snv_pos, "snv_het": het, "cnv": cnv_truth}
@@ -545,10 +559,12 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
 
 
 _AT_RUNS: Dict[str, Tuple[np.ndarray, np.ndarray]] = {}
+_CTX_PLANTS: Dict[int, list] = {}
 
 
 def simulate(spec: SynthSpec) -> List[SynthContig]:
     rng = np.random.default_rng(spec.seed)
+    _CTX_PLANTS.pop(spec.seed, None)
     lens = [l for _, l in spec.contigs]
     out = []
     for tid, (name, length) in enumerate(spec.contigs):
