@@ -259,15 +259,22 @@ def main_b200(a):
         lanes = [(ch, stream), (ch2, stream2)]
         done_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
         counts = [0, 0]
+        lane_log = []                                           # (lane, ms waiting for the bus incl. reset, ms upload, ms compute) per step
         bus = threading.Lock()                                  # one upload at a time: the PCIe link is the shared resource
 
         def lane(k, n_steps, record):
             torch.cuda.set_device(local)
             h, st_k = lanes[k]
             for _ in range(n_steps):
+                t_a = time.perf_counter()
+                h.reset(fasta_np)
                 with bus:
-                    h.reset(fasta_np); h.push_reads(pinned); st_k.synchronize()
-                rr = h.finish(); cc = h.cnv()
+                    t_b = time.perf_counter()
+                    h.push_reads(pinned); st_k.synchronize()
+                    t_c = time.perf_counter()
+                rr = h.finish(); t_d = time.perf_counter(); cc = h.cnv()
+                lane_log.append((k, round((t_b - t_a) * 1e3, 1), round((t_c - t_b) * 1e3, 1), round((t_d - t_c) * 1e3, 1), round((time.perf_counter() - t_d) * 1e3, 1),
+                                 round(cc.ms_device, 1), round(cc.ms_host, 1)))
                 counts[k] = len(rr.snv) + len(cc.calls)
             if record:
                 done_ev[k].record(st_k)
@@ -288,6 +295,8 @@ def main_b200(a):
         barrier()
         ms_e2e = max(p0.elapsed_time(done_ev[0]), p0.elapsed_time(done_ev[1]) if a.steps > 1 else 0.0)
         assert counts[0] == len(res.snv) + len(cn.calls)
+        if rank == 0:
+            sys.stderr.write("e2e lanes (lane, wait, upload, finish, cnv, cnv device, cnv host ms): %s\n" % lane_log[-min(8, len(lane_log)):])
         ch2.close()
         if rank == 0:
             sampler.window(t_region0, time.time())

@@ -1089,6 +1089,7 @@ struct gromgpu_chr {
     std::vector<grom_snv_cand> h_cand;
     struct CnvState *cnv = nullptr;
     cudaEvent_t ev[12];
+    cudaEvent_t ev_push[2] = {nullptr, nullptr}; unsigned push_seq = 0;
     bool ran = false;
     gromgpu_stats stats;
     gromgpu_result res;
@@ -1151,6 +1152,7 @@ extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, 
     CK(cudaMalloc(&h->d_ticket, sizeof(unsigned int) * 8));
     CK(cudaMalloc(&h->d_ncand, sizeof(unsigned int) * 4));
     for (int i = 0; i < 12; i++) CK(cudaEventCreate(&h->ev[i]));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&h->ev_push[i], cudaEventDisableTiming));
     CK(cudaMalloc(&h->d_cl_int, sizeof(int32_t) * 36 * (size_t)h->Ppad));
     CK(cudaMalloc(&h->d_cl_dist, sizeof(double) * 10 * (size_t)h->Ppad));
     CK(cudaMemsetAsync(h->d_cl_int, 0, sizeof(int32_t) * 36 * (size_t)h->Ppad, h->stream));
@@ -1189,6 +1191,7 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
     cudaFree(h->d_max_span); cudaFree(h->d_counters); cudaFree(h->d_scan_status); cudaFree(h->d_ticket);
     cudaFree(h->d_cand); cudaFree(h->d_ncand); cudaFree(h->d_ins); cudaFree(h->d_ins_pos); cudaFree(h->d_del); cudaFree(h->d_svev);
     for (int i = 0; i < 12; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    for (int i = 0; i < 2; i++) if (h->ev_push[i]) cudaEventDestroy(h->ev_push[i]);
     cudaFree(h->d_item_cnt); cudaFree(h->d_items); cudaFree(h->d_sv_tiles); cudaFree(h->d_sv_dirty); cudaFree(h->d_sv_small); cudaFree(h->d_pool);
     cudaFree(h->d_cl_int); cudaFree(h->d_cl_dist);
     cnv_state_free(h->cnv);
@@ -1216,7 +1219,20 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
         DevBuf &d = h->rb[f[k].id];
         const size_t need = (size_t)(f[k].have + f[k].cnt) * f[k].elt + 64;
         if (d.ensure(need, h->stream)) return -1;
-        if (f[k].cnt) CK(cudaMemcpyAsync((char *)d.p + (size_t)f[k].have * f[k].elt, f[k].src, (size_t)f[k].cnt * f[k].elt, cudaMemcpyHostToDevice, h->stream));
+        if (f[k].cnt) {
+            // in pieces, at most a few in flight: the copy engine serves requests in submission order, so a multi-GB transfer queued
+            // at once would stall every small copy of a second contig that is computing on another stream
+            static const size_t piece = []() { const char *e = getenv("GROMGPU_PUSH_PIECE_MB"); const long mb = e ? atol(e) : 4; return (size_t)(mb > 0 ? mb : 4) << 20; }();
+            const size_t total = (size_t)f[k].cnt * f[k].elt;
+            for (size_t o = 0; o < total; o += piece) {
+                CK(cudaMemcpyAsync((char *)d.p + (size_t)f[k].have * f[k].elt + o, (const char *)f[k].src + o, std::min(piece, total - o), cudaMemcpyHostToDevice, h->stream));
+                if (total > piece) {
+                    CK(cudaEventRecord(h->ev_push[h->push_seq & 1], h->stream));
+                    h->push_seq++;
+                    if (h->push_seq >= 2) CK(cudaEventSynchronize(h->ev_push[h->push_seq & 1]));       // the piece before the last one has landed
+                }
+            }
+        }
         d.size = (size_t)(f[k].have + f[k].cnt) * f[k].elt;
     }
     if (h->n_cigar || h->n_slots) {
