@@ -411,30 +411,42 @@ __global__ void __launch_bounds__(64) k_sweep_sum(const double *__restrict__ X, 
 struct SegCtx {
     const uint32_t *rec; int64_t len, end; int q, Lmin, Lmax, bound; const double *sd, *win_sd; bool dup;
     const double *wtab;          // MAPQ weight per mean MAPQ value [256]: the expression of rec_z evaluated once per value (same doubles, no division per base)
+    const double *win_thr;       // [Lmax + 1] 2.97 * win_sd[L], +inf where win_sd[L] <= 0: the cheap side of scores()
+    const double *zarr;          // device only: z of the deletion scan per position, unpacked once (k_zfill); nullptr = unpack from rec
     __host__ __device__ inline int cls(int64_t p) const { return (rec[p] >> R_CLASS) & 3; }
-    __host__ __device__ inline bool beyond(int64_t p, int mi) const { return (rec[p] & (dup ? (mi ? R_DUP1 : R_DUP0) : (mi ? R_DEL1 : R_DEL0))) != 0; }
+    __host__ __device__ inline uint32_t beyond_bit(int mi) const { return dup ? (mi ? R_DUP1 : R_DUP0) : (mi ? R_DEL1 : R_DEL0); }
+    __host__ __device__ inline bool beyond(int64_t p, int mi) const { return (rec[p] & beyond_bit(mi)) != 0; }
     __host__ __device__ inline bool win_gt1(int64_t p, int mi) const { return (rec[p] & (mi ? R_WIN1 : R_WIN0)) != 0; }
-    __host__ __device__ inline double z(int64_t p) const
+    // z of the deletion scan (the duplication scan sees the opposite sign)
+    __host__ __device__ inline double z_del_of(const uint32_t r) const
     {
-        const uint32_t r = rec[p];
         if (!(r & R_NZ)) return 0.0;
         const double w = (r & R_OVR) ? 1.0 : (((r >> R_CLASS) & 3) == 0 ? wtab[(r >> R_MQ) & 255] : 0.5);
+#ifdef __CUDA_ARCH__
+        const double v = __dmul_rn(w, sd[(r >> R_K) & 1023]);
+#else
         const double v = w * sd[(r >> R_K) & 1023];
-        return ((r & R_NEG) != 0) != dup ? -v : v;
+#endif
+        return (r & R_NEG) ? -v : v;
+    }
+    __host__ __device__ inline double z(int64_t p) const
+    {
+        const double v = zarr ? zarr[p] : z_del_of(rec[p]);
+        return dup ? 0.0 - v : v;            // 0.0 - v: exact, and keeps a zero positive like the reference's literal 0.0
     }
     // score >= 3 ?  The division is only carried out when the quotient can be anywhere near the threshold (a 1 % margin dwarfs
-    // the rounding of the product and the quotient), so the outcome is the reference's in every case.
-    __host__ __device__ inline bool scores(double tot, int cnt, double sdw, double *score) const
+    // the rounding of the products and the quotient), so the outcome is the reference's in every case; tot > 0 and win_sd > 0,
+    // which the reference tests first, follow from score >= 3 and from the +inf entries of win_thr.
+    __host__ __device__ inline bool scores(double tot, int cnt, int L, double *score) const
     {
-        const double den = cnt * sdw;
-        if (!(tot >= 2.97 * den)) return false;
-        *score = tot / den;
+        if (!(tot >= cnt * win_thr[L])) return false;
+        *score = tot / (cnt * win_sd[L]);
         return *score >= 3;
     }
 };
 enum { SEG_RESUME = 0, SEG_CALL = 1, SEG_UNRESOLVED = 2 };
 struct Outcome { int kind; int64_t next, c_end; double c_z; int64_t far; };   // far: one past the last position the sliding phase looked at
-constexpr int SEED_BOUND = 1024, SEED_BOUND2 = 8192;   // first round for every seed; second round for the unresolved ones when they are few
+constexpr int SEED_BOUND = 1024;       // first round, every seed; the second round gives the compacted unresolved ones the full growth phase (Lmax)
 
 template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCtx &C, const int64_t pos, int mi)
 {
@@ -445,37 +457,52 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
     int wlen = 0, cnt = 0, cnt2 = 0;                        // window length and counters fit 32 bits (Lmax positions at most)
     int64_t pa, c_start = 0, c_end = 0, last_good = 0;
     double tot = 0, c_z = 0, tz;
-    for (pa = pos; pa < pos + Lmin; pa++) {
+    const uint32_t *rp = C.rec + pos;                        // the first two phases index relative to the seed (32-bit offsets)
+    const double *zp = C.zarr ? C.zarr + pos : nullptr;
+    auto zrel = [&](int i, uint32_t r) { const double v = zp ? zp[i] : C.z_del_of(r); return C.dup ? 0.0 - v : v; };
+    const int iLmin = (int)Lmin, iLmax = (int)Lmax;
+    for (int i = 0; i < iLmin; i++) {
         wlen++;
         bool ok = false;
-        if (!(C.rec[pa] & R_MASK)) { CNV_STEP(mi, pa); ok = C.beyond(pa, mi); }
+        const uint32_t r = rp[i];
+        if (!(r & R_MASK)) { const int c_ = (r >> R_CLASS) & 3; if (c_ != 2) mi = c_; ok = (r & C.beyond_bit(mi)) != 0; }
         if (ok) cnt2++;
-        else if (2 * cnt2 < wlen) { o.next = pa + 1; return o; }            // give up inside the first window: resume after the offender
+        else if (2 * cnt2 < wlen) { o.next = pos + i + 1; return o; }       // give up inside the first window: resume after the offender
     }
-    cnt = (int)Lmin;
-    for (int64_t a = pos; a < pos + Lmin; a++) { cnt -= (int)(C.rec[a] & R_MASK); tot += C.z(a); }
-    if (cnt > 0 && tot > 0 && C.win_sd[Lmin] > 0 && C.scores(tot, cnt, C.win_sd[Lmin], &tz)) {   // tot <= 0 cannot score (exact)
+    cnt = iLmin;
+    for (int i = 0; i < iLmin; i++) { const uint32_t r = rp[i]; cnt -= (int)(r & R_MASK); tot += zrel(i, r); }
+    if (cnt > 0 && C.scores(tot, cnt, iLmin, &tz)) {
         begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tz;
     }
-    for (pa = pos + Lmin; pa < pos + Lmax; pa++) {
-        wlen++;
-        if (BOUNDED && wlen > C.bound) { o.kind = SEG_UNRESOLVED; return o; }
-        if (pa >= end) { stop = true; break; }
-        bool ok = false;
-        if (!(C.rec[pa] & R_MASK)) {
-            CNV_STEP(mi, pa);
-            tot += C.z(pa); cnt++;
-            ok = C.beyond(pa, mi);
-            if (ok) {
-                cnt2++;
-                if (tot > 0 && C.win_sd[wlen] > 0 && C.scores(tot, cnt, C.win_sd[wlen], &tz)) {
-                    last_good = pa;
-                    if (!begun) { begun = true; c_start = pos; c_end = pa; c_z = tz; }
-                    else { c_end = pa; if (tz > c_z) c_z = tz; }
+    {
+        const int i_end = end - pos < (int64_t)iLmax ? (int)(end - pos) : iLmax;      // first offset at or past `end` (>= Lmin is not guaranteed)
+        int good = -1;                                                               // last scoring offset of this phase
+        const uint32_t m0 = C.beyond_bit(0), m1 = C.beyond_bit(1);
+        for (int i = iLmin; i < iLmax; i++) {
+            wlen++;
+            if (BOUNDED && wlen > C.bound) { o.kind = SEG_UNRESOLVED; return o; }
+            if (i >= i_end) { stop = true; break; }
+            bool ok = false;
+            const uint32_t r = rp[i];
+            if (!(r & R_MASK)) {
+                const int c_ = (r >> R_CLASS) & 3; if (c_ != 2) mi = c_;
+                tot += zrel(i, r); cnt++;
+                ok = (r & (mi ? m1 : m0)) != 0;
+                if (ok) {
+                    cnt2++;
+                    if (C.scores(tot, cnt, wlen, &tz)) {
+                        good = i;
+                        if (tz > c_z) c_z = tz;                                      // c_z starts at 0 and every scoring tz is >= 3
+                    }
                 }
             }
+            if (!ok && 2 * cnt2 < wlen) { stop = true; break; }
         }
-        if (!ok && 2 * cnt2 < wlen) { stop = true; break; }
+        if (good >= 0) {
+            last_good = pos + good;
+            if (!begun) { begun = true; c_start = pos; }
+            c_end = pos + good;
+        }
     }
     if (!stop && begun) {
         if (BOUNDED) { o.kind = SEG_UNRESOLVED; return o; }
@@ -494,7 +521,7 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
                 CNV_STEP(mi, pa);
                 if (!(C.rec[pa] & R_MASK) && C.win_gt1(pa, mi)) { tot += C.z(pa); cnt++; }
             }
-            if (cnt > 0 && tot > 0 && C.win_sd[Lmax] > 0 && C.scores(tot, cnt, C.win_sd[Lmax], &tz)) {
+            if (cnt > 0 && C.scores(tot, cnt, iLmax, &tz)) {
                 last_good = pa; c_end = pa;
                 if (tz > c_z) c_z = tz;
             }
@@ -611,37 +638,49 @@ __global__ void __launch_bounds__(256) k_hop_mark(const uint32_t *__restrict__ j
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && flag[i]) flag[j[i]] = 1;
 }
-// start (or restart after a host-evaluated sink): flag the node the outer loop meets first from position x carrying class s
-__global__ void k_hop_start(SegCtx C, const uint32_t *sd, const uint32_t *wpk, int64_t x, int s, uint32_t n_seeds, uint32_t base, uint8_t *flag)
-{
-    flag[base + next_node(C, sd, wpk, x, s, n_seeds)] = 1;
-}
-// mark the node (seed at pos, class) as collected
-__global__ void k_hop_done(const uint32_t *sd, const uint32_t *wpk, int64_t pos, int variant, uint8_t *done)
-{
-    done[2 * (wpk[pos >> 5] + __popc(sd[pos >> 5] & ((1u << (pos & 31)) - 1u))) + variant] = 1;
-}
 struct HopCall { int64_t pos, c_end; double c_z; };
-struct HopSink { int64_t pos; int32_t variant, found; };
-__global__ void __launch_bounds__(256) k_hop_collect(const uint8_t *__restrict__ flag, uint8_t *__restrict__ done, const uint32_t *__restrict__ land, const uint32_t *__restrict__ sd,
+struct HopSink { int64_t pos; int32_t variant, found; };        // found: 1 = the path stops at an unresolved seed, 0 = it ran to the end
+// calls of the flagged (= visited) nodes; unresolved nodes on the path were evaluated by the host (k_hop_advance)
+__global__ void __launch_bounds__(256) k_hop_collect(const uint8_t *__restrict__ flag, const uint32_t *__restrict__ land, const uint32_t *__restrict__ sd,
                                                      const uint32_t *__restrict__ wpk, int64_t words, uint32_t n_seeds, const SeedCall *__restrict__ calls,
-                                                     HopCall *__restrict__ out, uint32_t out_cap, unsigned int *__restrict__ n_out, HopSink *__restrict__ sink)
+                                                     HopCall *__restrict__ out, uint32_t out_cap, unsigned int *__restrict__ n_out)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;               // node id inside this kind
-    if (i >= 2 * n_seeds || !flag[i] || done[i]) return;
-    done[i] = 1;
+    if (i >= 2 * n_seeds || !flag[i]) return;
     const uint32_t e = land[i];
-    if (e == LAND_NOT) return;
-    const uint32_t kind = e >> LAND_SHIFT, low = e & ((1u << LAND_SHIFT) - 1u);
-    if (kind == SEG_RESUME) return;
+    if (e == LAND_NOT || (e >> LAND_SHIFT) != SEG_CALL) return;
+    const uint32_t low = e & ((1u << LAND_SHIFT) - 1u), rank = i >> 1;
     int64_t a = 0, b = words;
-    const uint32_t rank = i >> 1;
     while (a < b) { const int64_t m = (a + b) >> 1; if (wpk[m] <= rank) a = m + 1; else b = m; }
     const int64_t w = a - 1, pos = (w << 5) + __fns(sd[w], 0, (int)(rank - wpk[w]) + 1);
-    if (kind == SEG_CALL) {
-        const unsigned int k = atomicAdd(n_out, 1u);
-        if (k < out_cap) { out[k].pos = pos; out[k].c_end = calls[low].c_end; out[k].c_z = calls[low].c_z; }
-    } else { sink->pos = pos; sink->variant = (int)(i & 1); sink->found = 1; done[i] = 0; }
+    const unsigned int k = atomicAdd(n_out, 1u);
+    if (k < out_cap) { out[k].pos = pos; out[k].c_end = calls[low].c_end; out[k].c_z = calls[low].c_z; }
+}
+// One leg of the path per scan (thread 0 deletions, thread 1 duplications): flag the node the outer loop meets first from position x
+// carrying class s -- the marks later spread from these leg starts -- and follow the top level of the jump table to the leg's fixed
+// point: the END node, or an unresolved seed (a sink), which the host evaluates before the next leg starts behind it.
+struct HopLeg { int64_t x; int32_t s, active; };
+__global__ void k_hop_advance(SegCtx C0, SegCtx C1, const uint32_t *__restrict__ seeds, const uint32_t *__restrict__ wp, int64_t words, const uint32_t *__restrict__ jtop,
+                              HopLeg leg0, HopLeg leg1, uint32_t n0, uint32_t n1, uint8_t *__restrict__ flag, HopSink *__restrict__ sink)
+{
+    const int k = threadIdx.x;
+    const HopLeg leg = k ? leg1 : leg0;
+    if (!leg.active) return;
+    const SegCtx &C = k ? C1 : C0;
+    const uint32_t n_seeds = k ? n1 : n0, base = k ? 2 * n0 + 1 : 0;
+    const uint32_t *sd = seeds + (int64_t)k * words, *wpk = wp + (int64_t)k * words;
+    uint32_t node = base + next_node(C, sd, wpk, leg.x, leg.s, n_seeds);
+    flag[node] = 1;
+    for (;;) { const uint32_t nx = jtop[node]; if (nx == node) break; node = nx; }
+    HopSink r; r.pos = 0; r.variant = 0; r.found = 0;
+    if (node != base + 2 * n_seeds) {
+        const uint32_t i = node - base, rank = i >> 1;
+        int64_t a = 0, b = words;
+        while (a < b) { const int64_t m = (a + b) >> 1; if (wpk[m] <= rank) a = m + 1; else b = m; }
+        const int64_t w = a - 1;
+        r.pos = (w << 5) + __fns(sd[w], 0, (int)(rank - wpk[w]) + 1); r.variant = (int)(i & 1); r.found = 1;
+    }
+    sink[k] = r;
 }
 
 // one thread per seed (blockIdx.y = deletions / duplications): rank -> position through the per-word ranks, then evaluate the seed
@@ -701,21 +740,48 @@ __global__ void __launch_bounds__(128, 8) k_seed_eval(SegCtx Cdel, SegCtx Cdup, 
         if (rank == 0) jump0[base + 2 * n_seeds] = base + 2 * n_seeds;      // END loops on itself
     }
 }
+// Second round over the compacted open seeds (full growth phase, one thread each).  Deep inside a long event every seed walks the
+// whole growth phase only to stay open (it enters the sliding phase), and none of them is ever visited: the path meets the first
+// open seed of the event, the host evaluates it and the call jumps past the rest.  So the round runs in two passes over blocks of
+// OPEN_BLOCK positions: pass 0 evaluates the first open seed of every block; pass 1 evaluates the others unless the block's first
+// seed and the next block's both stayed open.  Skipping is only a guess about cost -- a skipped seed stays open, and an open seed
+// on the path is evaluated exactly by the host like any other.
+constexpr int OPEN_BLOCK_SHIFT = 8;
+enum { OPEN_NONE = 0, OPEN_STAYS = 1, OPEN_CLOSED = 2 };
+__global__ void __launch_bounds__(256) k_open_first(const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp, const SeedTodo *__restrict__ todo,
+                                                    uint32_t n_todo, uint32_t *__restrict__ first, int64_t n_blocks)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_todo) return;
+    const SeedTodo t = todo[i];
+    const int64_t p = seed_position(seeds + (int64_t)t.kind * words, wp + (int64_t)t.kind * words, words, t.rank);
+    atomicMin(first + (int64_t)(t.kind * 2 + t.variant) * n_blocks + (p >> OPEN_BLOCK_SHIFT), (uint32_t)p);
+}
 __global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
                                                    unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t n_todo, uint32_t n_del, uint32_t n_dup,
-                                                   uint32_t *__restrict__ jump0)
+                                                   uint32_t *__restrict__ jump0, int pass, const uint32_t *__restrict__ first, uint8_t *__restrict__ state, int64_t n_blocks)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_todo) return;
     const SeedTodo t = todo[i];
     const SegCtx &C = t.kind ? Cdup : Cdel;
     const int64_t p = seed_position(seeds + (int64_t)t.kind * words, wp + (int64_t)t.kind * words, words, t.rank);
+    const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
+    const int64_t key = (int64_t)(t.kind * 2 + t.variant) * n_blocks + (p >> OPEN_BLOCK_SHIFT);
+    if (pass == 2) { if (land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] != unres) return; }    // sweep of whatever is still open
+    else if (pass >= 0) {
+        const bool is_first = first[key] == (uint32_t)p;
+        if (is_first != (pass == 0)) return;
+        if (pass == 1 && state[key] == OPEN_STAYS && (p >> OPEN_BLOCK_SHIFT) + 1 < n_blocks && state[key + 1] == OPEN_STAYS) { atomicAdd(n_calls + 5, 1u); return; }
+    }
     const int c0 = C.cls(p);
     const uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
+    if (pass == 0) state[key] = e == unres ? OPEN_STAYS : OPEN_CLOSED;
+    if (e == unres) return;                                                                // enters the sliding phase: a long call, left to the host
     land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] = e;
     if (c0 != 2) land[((int64_t)t.kind * cap + t.rank) * 2 + 1] = e;
-    if (e == ((uint32_t)SEG_UNRESOLVED << LAND_SHIFT)) atomicAdd(n_calls + 4, 1u);       // still open after the longer leash
+    atomicAdd(n_calls + 4, 1u);                                                            // seeds closed by the second round
     if (jump0) {
         const uint32_t n_seeds = t.kind ? n_dup : n_del, base = t.kind ? 2 * n_del + 1 : 0;
         const uint32_t *sd = seeds + (int64_t)t.kind * words, *wpk = wp + (int64_t)t.kind * words;

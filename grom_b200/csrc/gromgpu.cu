@@ -19,6 +19,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <algorithm>
+#include <limits>
 #include <vector>
 #include <chrono>
 #include <thread>
@@ -255,13 +256,18 @@ __global__ void __launch_bounds__(256) k_tile_index(const int32_t *pos, int64_t 
 //    the read-name slots, evaluated in BAM order because the staged read list is in BAM order.
 struct PileAcc {
     int m_hi, m_low, m_fs, m_pir, m_all;                // reference-matching bases (m_low is derived: m_all - m_hi)
-    int snv[4], low[4], pir[4], fs[4];                  // everything else
+    // Everything else is touched by ~0.2 % of the bases.  These 16 counters and the name slots are indexed with run-time values on
+    // purpose: that places them in (L1-resident) local memory and keeps the fast loop's accumulators in registers without spills.
     int bq, bq_all, mq, mq_all;
     int rd_mq, rd_rd, rd_low;
-    uint64_t nm0, nm1, nm2; int nm_cnt;
 };
+struct PileRare {
+    int v[16];                                          // [0..3] snv, [4..7] low, [8..11] pir, [12..15] fs per base
+    uint64_t nm[3]; int nm_cnt;
+};
+enum { RA_SNV = 0, RA_LOW = 4, RA_PIR = 8, RA_FS = 12 };
 
-__device__ __forceinline__ void pile_generic(PileAcc &a, uint64_t hash, uint32_t misc, int code, int qv, int qi, int lseq, int rc4,
+__device__ __forceinline__ void pile_generic(PileAcc &a, PileRare &x, uint64_t hash, uint32_t misc, int code, int qv, int qi, int lseq, int rc4,
                                           bool hi, int min_snv)
 {
     const int mq = misc & 0xff;
@@ -271,31 +277,25 @@ __device__ __forceinline__ void pile_generic(PileAcc &a, uint64_t hash, uint32_t
         const bool mism = (code != rc4);
         if (mism) {
             // first min_snv (<= 3) distinct names seen on mismatching high-quality bases (src/GROM.c:6805-6824)
-            if (a.nm_cnt > 0 && a.nm0 == hash) skip = true;
-            else if (a.nm_cnt > 1 && a.nm1 == hash) skip = true;
-            else if (a.nm_cnt > 2 && a.nm2 == hash) skip = true;
-            else if (a.nm_cnt < min_snv && (misc & PR_NAMEOK)) {
-                if (a.nm_cnt == 0) a.nm0 = hash; else if (a.nm_cnt == 1) a.nm1 = hash; else a.nm2 = hash;
-                a.nm_cnt++;
-            }
+            const int n = x.nm_cnt;
+            for (int k = 0; k < n; k++) skip = skip || x.nm[k] == hash;
+            if (!skip && n < min_snv && (misc & PR_NAMEOK)) { x.nm[n] = hash; x.nm_cnt = n + 1; }
         }
         if (!skip && bi >= 0) {
             const bool fwd = !(misc & PR_REV);
             const int pir = (mism || fwd) ? qi : lseq - qi;
             a.bq += qv; a.bq_all += qv; a.mq += mq; a.mq_all += mq;
-#pragma unroll
-            for (int k = 0; k < 4; k++) if (bi == k) { a.snv[k] += 1; a.pir[k] += pir; a.fs[k] += fwd ? 1 : 0; }
+            x.v[RA_SNV + bi] += 1; x.v[RA_PIR + bi] += pir; x.v[RA_FS + bi] += fwd ? 1 : 0;
         }
     } else if (bi >= 0) {
         a.bq_all += qv; a.mq_all += mq;
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (bi == k) a.low[k] += 1;
+        x.v[RA_LOW + bi] += 1;
     }
 }
 
 // classify one base (code, quality) of one read at this thread's position and fold it into the accumulators;
 // qi = query offset, lseq = read length seen by the position-in-read rule
-__device__ __forceinline__ void pile_apply(PileAcc &a, int code, int qv, uint64_t hash, uint32_t misc, int qi, int lseq, int rc4,
+__device__ __forceinline__ void pile_apply(PileAcc &a, PileRare &x, int code, int qv, uint64_t hash, uint32_t misc, int qi, int lseq, int rc4,
                                            bool ref_acgt, bool mq_ok, int bqmin, int min_snv)
 {
     const bool hi = mq_ok && qv >= bqmin;
@@ -305,7 +305,7 @@ __device__ __forceinline__ void pile_apply(PileAcc &a, int code, int qv, uint64_
         a.bq_all += qv; a.mq_all += mq; a.m_all += 1;
         if (hi) { a.bq += qv; a.mq += mq; a.m_hi += 1; a.m_pir += fwd ? qi : lseq - qi; a.m_fs += fwd ? 1 : 0; }
     } else {
-        pile_generic(a, hash, misc, code, qv, qi, lseq, rc4, hi, min_snv);
+        pile_generic(a, x, hash, misc, code, qv, qi, lseq, rc4, hi, min_snv);
     }
 }
 
@@ -497,11 +497,11 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
         const int rc4m = ref_acgt ? rc4 : 0x10;                                // 0x10: never equals a nibble
         const int wlo = (int)(tile_lo + (threadIdx.x & ~31));
         const int ip = (int)p;
-        PileAcc a;
+        PileAcc a; PileRare x;
         a.m_hi = a.m_low = a.m_fs = a.m_pir = a.m_all = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) { a.snv[k] = a.low[k] = a.pir[k] = a.fs[k] = 0; }
-        a.bq = a.bq_all = a.mq = a.mq_all = a.rd_mq = a.rd_rd = a.rd_low = 0; a.nm0 = a.nm1 = a.nm2 = 0; a.nm_cnt = 0;
+        for (int k = 0; k < 16; k++) x.v[k] = 0;
+        a.bq = a.bq_all = a.mq = a.mq_all = a.rd_mq = a.rd_rd = a.rd_low = 0; x.nm[0] = x.nm[1] = x.nm[2] = 0; x.nm_cnt = 0;
         int rd_cnt = 0;
 
         for (;; c++) {
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
                 (void)byte;
                 if (slow) {
                     const StageC C = S.c[buf][t];
-                    pile_generic(a, C.hash, (uint32_t)B.mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u), nib, qv, off, D.lq, rc4,
+                    pile_generic(a, x, C.hash, (uint32_t)B.mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u), nib, qv, off, D.lq, rc4,
                                  qv >= B.bq_eff, min_snv);
                 }
                 if (D.flags & SF_COMPLEX) {
@@ -587,7 +587,7 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
                                         if (!glob) { qv2 = lds_u8(A.qa + xq); byte2 = lds_u8(A.sa + (xq >> 1)); }
                                         else { const uint64_t slot = ((uint64_t)E.base16 << 4) + (uint64_t)xq; qv2 = __ldg(R.qual + slot); byte2 = __ldg(R.seq4 + (slot >> 1)); }
                                         const int code2 = (byte2 >> ((~xq & 1) << 2)) & 15;
-                                        pile_apply(a, code2, qv2, C.hash, gmisc, xq, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv);
+                                        pile_apply(a, x, code2, qv2, C.hash, gmisc, xq, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv);
                                     }
                                     qi += len; rp += len;
                                 }
@@ -603,20 +603,23 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
             if (lane == 0) mbar_arrive(smem_u32(&S.empty[buf]));
             if (last) { c++; break; }
         }
+        int snv[4], low[4], pir[4], fs[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { snv[k] = x.v[RA_SNV + k]; low[k] = x.v[RA_LOW + k]; pir[k] = x.v[RA_PIR + k]; fs[k] = x.v[RA_FS + k]; }
         if (live) {
             // fold the matching-base registers into the per-base counters
             a.m_low = a.m_all - a.m_hi;
             a.rd_low += rd_cnt - a.rd_rd;
             const int rb = (rc4 == 1) ? 0 : (rc4 == 2) ? 1 : (rc4 == 4) ? 2 : 3;
 #pragma unroll
-            for (int k = 0; k < 4; k++) if (ref_acgt && rb == k) { a.snv[k] += a.m_hi; a.low[k] += a.m_low; a.pir[k] += a.m_pir; a.fs[k] += a.m_fs; }
+            for (int k = 0; k < 4; k++) if (ref_acgt && rb == k) { snv[k] += a.m_hi; low[k] += a.m_low; pir[k] += a.m_pir; fs[k] += a.m_fs; }
             int32_t *o = arrays + p;
-            const int tot = a.snv[0] + a.snv[1] + a.snv[2] + a.snv[3];
-            const int lowt = a.low[0] + a.low[1] + a.low[2] + a.low[3];
+            const int tot = snv[0] + snv[1] + snv[2] + snv[3];
+            const int lowt = low[0] + low[1] + low[2] + low[3];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                o[(int64_t)(GA_SNV_A + k) * Ppad] = a.snv[k]; o[(int64_t)(GA_SNVLOW_A + k) * Ppad] = a.low[k];
-                o[(int64_t)(GA_PIR_A + k) * Ppad] = a.pir[k]; o[(int64_t)(GA_FS_A + k) * Ppad] = a.fs[k];
+                o[(int64_t)(GA_SNV_A + k) * Ppad] = snv[k]; o[(int64_t)(GA_SNVLOW_A + k) * Ppad] = low[k];
+                o[(int64_t)(GA_PIR_A + k) * Ppad] = pir[k]; o[(int64_t)(GA_FS_A + k) * Ppad] = fs[k];
             }
             o[(int64_t)GA_BQ * Ppad] = a.bq; o[(int64_t)GA_BQ_ALL * Ppad] = a.bq_all;
             o[(int64_t)GA_MQ * Ppad] = a.mq; o[(int64_t)GA_MQ_ALL * Ppad] = a.mq_all;
@@ -626,8 +629,8 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
         // ---- SNV gate on the counts still in registers (src/GROM.c:11096-11199); candidates are compacted by warp ballot
         bool is_cand = false;
         int c_base = 0; double c_ratio = 0, c_pr = 0, c_hez = 0;
-        const int total = a.snv[0] + a.snv[1] + a.snv[2] + a.snv[3];
-        const int rc_all = total + a.low[0] + a.low[1] + a.low[2] + a.low[3];
+        const int total = snv[0] + snv[1] + snv[2] + snv[3];
+        const int rc_all = total + low[0] + low[1] + low[2] + low[3];
         if (live) {
             const char fc = fasta[p];
             const bool is_n = (fc == 'N' || fc == 'n');
@@ -635,16 +638,16 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
             if (ip >= sc.scan_first && ip <= sc.scan_last && !is_n) {
                 bool any = false;
 #pragma unroll
-                for (int k = 0; k < 4; k++) any = any || (a.snv[k] >= c_prm.min_snv && rc4 != (1 << k));
+                for (int k = 0; k < 4; k++) any = any || (snv[k] >= c_prm.min_snv && rc4 != (1 << k));
                 if (any && arrays[(int64_t)GA_RD * Ppad + p] + arrays[(int64_t)GA_INDEL_SC_RD * Ppad + p] > 0) {
                     const bool bq_ok = (double)a.bq_all / (double)rc_all >= c_prm.min_ave_bq;
                     const int T = c_prm.max_trials, TD = T + 1;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const double ratio = (double)((float)a.snv[k] / (float)total);
-                        if (rc4 != (1 << k) && ratio >= c_prm.min_snv_ratio && a.snv[k] >= c_prm.min_snv && bq_ok) {
+                        const double ratio = (double)((float)snv[k] / (float)total);
+                        if (rc4 != (1 << k) && ratio >= c_prm.min_snv_ratio && snv[k] >= c_prm.min_snv && bq_ok) {
                             if (!is_cand || ratio > c_ratio) {
-                                const size_t idx = (total > T) ? (size_t)T * TD + (size_t)(a.snv[k] * T / total) : (size_t)total * TD + (size_t)a.snv[k];
+                                const size_t idx = (total > T) ? (size_t)T * TD + (size_t)(snv[k] * T / total) : (size_t)total * TD + (size_t)snv[k];
                                 c_base = k; c_ratio = ratio; c_pr = sc.mqt[idx]; c_hez = sc.hez[idx];
                                 is_cand = true;
                             }
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const Pr
                 grom_snv_cand *cd = sc.cand + slot;
                 cd->pos = ip; cd->base = c_base; cd->ratio = c_ratio; cd->pr = c_pr; cd->hez = c_hez; cd->reserved = 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++) { cd->v[GA_SNV_A + k] = a.snv[k]; cd->v[GA_SNVLOW_A + k] = a.low[k]; cd->v[GA_PIR_A + k] = a.pir[k]; cd->v[GA_FS_A + k] = a.fs[k]; }
+                for (int k = 0; k < 4; k++) { cd->v[GA_SNV_A + k] = snv[k]; cd->v[GA_SNVLOW_A + k] = low[k]; cd->v[GA_PIR_A + k] = pir[k]; cd->v[GA_FS_A + k] = fs[k]; }
                 cd->v[GA_BQ] = a.bq; cd->v[GA_BQ_ALL] = a.bq_all; cd->v[GA_MQ] = a.mq; cd->v[GA_MQ_ALL] = a.mq_all;
                 cd->v[GA_BQ_RC] = total; cd->v[GA_MQ_RC] = total; cd->v[GA_RC_ALL] = rc_all;
             }
@@ -1519,11 +1522,11 @@ struct CnvState {
     uint32_t *d_blk = nullptr, *d_wp = nullptr, *d_land = nullptr; uint32_t land_cap = 0, spec_cap = 0; int nb = 0;
     cnv::SeedCall *d_spec = nullptr; unsigned int *d_nspec = nullptr; double *d_winsd = nullptr;
     std::vector<grom_cnv_call> calls;
-    std::vector<double> win_sd, bin_d; std::vector<int64_t> win_cnt, bin_n;
+    std::vector<double> win_sd, win_thr, bin_d; std::vector<int64_t> win_cnt, bin_n;
     int64_t P = 0, words = 0;
     int q = 0;
     std::vector<double> sd_tbl, wtab;
-    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec;
+    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, open_first, open_state;
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr;   // packed records travel to the host while the sweep runs
 };
 static void cnv_state_free(CnvState *c)
@@ -1532,7 +1535,7 @@ static void cnv_state_free(CnvState *c)
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
-    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec}) if (g->p) cudaFree(g->p);
+    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->open_first, &c->open_state}) if (g->p) cudaFree(g->p);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_z) cudaEventDestroy(c->ev_z);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
@@ -1627,7 +1630,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * words)); CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
         c.spec_cap = (uint32_t)std::min<int64_t>(P / 8 + 1024, (int64_t)1 << 28);
         CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
-        CK(cudaMalloc(&c.d_nspec, 6 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (Lmax + 1)));
+        CK(cudaMalloc(&c.d_nspec, 8 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * 2 * (Lmax + 1)));      // win_sd, then win_thr
     }
 
     // ---- stage 1: pre-statistics + repeat runs
@@ -1940,6 +1943,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         c.win_cnt[L] = wcnt[L - Lmin];
         c.win_sd[L] = wcnt[L - Lmin] > 1 ? sqrt(wsq[L - Lmin] / (double)(wcnt[L - Lmin] - 1)) : 0.0;
     }
+    // pre-filter of SegCtx::scores: 2.97 sd per window length, +inf where the reference's `win_sd > 0` test fails
+    c.win_thr.assign(Lmax + 1, std::numeric_limits<double>::infinity());
+    for (int L = Lmin; L <= Lmax; L++) if (c.win_sd[L] > 0) c.win_thr[L] = 2.97 * c.win_sd[L];
 
     // most-biased repeat override of the z list, after the sweep like the reference (src/GROM.c:19023-19150)
     if (biased != -1) {
@@ -1975,7 +1981,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     int64_t seed_tot_all = 0, n_spec_all = 0;
     {
         SegCtx ctx[2];
-        for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].dup = k == 1; ctx[k].wtab = T.p2s_sd + P2S; }
+        for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].win_thr = c.d_winsd + (Lmax + 1); ctx[k].zarr = nullptr; ctx[k].dup = k == 1; ctx[k].wtab = T.p2s_sd + P2S; }
         // every seed evaluated on the device (bounded); a seed list that outgrew its buffer, or the biased-repeat override (it rewrites
         // z on the host copy after the sweep), leaves the evaluation to the host
         unsigned int n_spec = 0;
@@ -1984,38 +1990,31 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         if (have_land) {
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
-            CK(cudaMemsetAsync(c.d_nspec, 0, 6 * sizeof(unsigned int), s));
-            const uint32_t todo_cap = 32768;
+            CK(cudaMemcpyAsync(c.d_winsd + (Lmax + 1), c.win_thr.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
+            CK(cudaMemsetAsync(c.d_nspec, 0, 8 * sizeof(unsigned int), s));
+            // every (seed, carried class) can stay open after the first round (a contig full of long events): room for all of them
+            const uint32_t todo_cap = (uint32_t)std::min<uint64_t>(2ull * ((uint64_t)seed_tot[0] + seed_tot[1]) + 64, 1ull << 28);
             Grow &t_todo = c.tmp[15];
-            if (!t_todo.ensure(sizeof(SeedTodo) * todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
+            if (!t_todo.ensure(sizeof(SeedTodo) * (size_t)todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
             // jump table: level k holds the node reached after 2^k hops; node ids of the duplication scan sit behind the deletion scan's
             const uint32_t n_nodes = 2 * seed_tot[0] + 1 + 2 * seed_tot[1] + 1, base[2] = {0u, 2 * seed_tot[0] + 1};
             int levels = 1;
             while ((1ull << levels) < (unsigned long long)2 * std::max(seed_tot[0], seed_tot[1]) + 2) levels++;
             // no room for the jump table (levels x nodes words): the seed tables still serve the host scan below
-            const bool jump_ok = !getenv("GROMGPU_CNV_HOST_SCAN") && c.jump.ensure(sizeof(uint32_t) * (size_t)levels * n_nodes) && c.flags.ensure(2 * (size_t)n_nodes) &&
+            const bool jump_ok = !getenv("GROMGPU_CNV_HOST_SCAN") && c.jump.ensure(sizeof(uint32_t) * (size_t)levels * n_nodes) && c.flags.ensure((size_t)n_nodes) &&
                                  c.hop_out.ensure(sizeof(HopCall) * (size_t)c.spec_cap) && c.hop_sink.ensure(2 * sizeof(HopSink));
             if (!jump_ok) cudaGetLastError();
             uint32_t *J = jump_ok ? c.jump.as<uint32_t>() : nullptr;
-            uint8_t *flag = jump_ok ? c.flags.as<uint8_t>() : nullptr, *done = jump_ok ? flag + n_nodes : nullptr;
+            uint8_t *flag = jump_ok ? c.flags.as<uint8_t>() : nullptr;
             const uint32_t most = std::max(seed_tot[0], seed_tot[1]);
             if (most) { k_seed_eval<<<dim3((most + 127) / 128, 2), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
                                                                               c.d_nspec, t_todo.as<SeedTodo>(), todo_cap, J); n_launch++; }
             unsigned int cnt2[2] = {0, 0};
             CK(cudaMemcpyAsync(cnt2, c.d_nspec, sizeof(cnt2), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            if (cnt2[1] > 0 && cnt2[1] <= todo_cap && SEED_BOUND2 < Lmax) {
-                // few seeds ran past the first bound (typically the uncovered stretch before the first applied read): give them a longer leash
-                ctx[0].bound = ctx[1].bound = SEED_BOUND2;
-                k_seed_eval2<<<(cnt2[1] + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), cnt2[1],
-                                                                seed_tot[0], seed_tot[1], J); n_launch++;
-            }
-            // every unresolved seed on the path costs one host round trip: when many are left (no second round, or a genome full of
-            // long events) the scan is cheaper on the host, in parallel pieces
-            unsigned int still_open = cnt2[1];
-            if (cnt2[1] > 0 && cnt2[1] <= todo_cap && SEED_BOUND2 < Lmax) CK(cudaMemcpyAsync(&still_open, c.d_nspec + 4, sizeof(still_open), cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-            device_hop = jump_ok && still_open <= 4096;       // GROMGPU_CNV_HOST_SCAN forces the host scan (tests)
+            mark("  seeds, first round");
+            const unsigned int n_todo = std::min(cnt2[1], todo_cap);
+            device_hop = jump_ok;                              // GROMGPU_CNV_HOST_SCAN forces the host scan (tests)
             if (device_hop) {
             if (most == 0) CK(cudaMemsetAsync(J, 0, sizeof(uint32_t) * n_nodes, s));
             if (seed_tot[0] == 0 || seed_tot[1] == 0) {                // a scan without seeds: its END node loops on itself
@@ -2023,50 +2022,87 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 if (seed_tot[0] == 0) CK(cudaMemcpyAsync(J + e0, &e0, 4, cudaMemcpyHostToDevice, s));
                 if (seed_tot[1] == 0) CK(cudaMemcpyAsync(J + e1, &e1, 4, cudaMemcpyHostToDevice, s));
             }
+            // Seeds that ran past the first bound (inside genuine events, or the uncovered start of the contig) are compacted and get the
+            // full growth phase, one thread each.  What is still open afterwards enters the sliding phase, i.e. is a call longer than
+            // the largest window: only the first such seed of each event lies on the path, and the host evaluates that one.
+            const int64_t n_oblk = (P >> OPEN_BLOCK_SHIFT) + 1;
+            bool two_pass = false;
+            auto second_round = [&](int pass) {
+                k_seed_eval2<<<(n_todo + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), n_todo,
+                                                               seed_tot[0], seed_tot[1], J, pass, c.open_first.as<uint32_t>(), c.open_state.as<uint8_t>(), n_oblk); n_launch++;
+            };
+            if (n_todo) {
+                ctx[0].bound = ctx[1].bound = Lmax;
+                // many open seeds mean long events: two passes, the second skips the interior of what the first found to stay open
+                two_pass = n_todo > 65536 && c.open_first.ensure(sizeof(uint32_t) * 4 * (size_t)n_oblk) && c.open_state.ensure(4 * (size_t)n_oblk);
+                if (two_pass) {
+                    CK(cudaMemsetAsync(c.open_first.p, 0xff, sizeof(uint32_t) * 4 * (size_t)n_oblk, s));
+                    CK(cudaMemsetAsync(c.open_state.p, 0, 4 * (size_t)n_oblk, s));
+                    k_open_first<<<(n_todo + 255) / 256, 256, 0, s>>>(c.d_seed, words, c.d_wp, t_todo.as<SeedTodo>(), n_todo, c.open_first.as<uint32_t>(), n_oblk); n_launch++;
+                    if (trace) { CK(cudaStreamSynchronize(s)); mark("    open-block table"); }
+                    second_round(0);
+                    if (trace) { CK(cudaStreamSynchronize(s)); mark("    pass 0"); }
+                    second_round(1);
+                } else { cudaGetLastError(); second_round(-1); }
+                if (trace) {
+                    unsigned int dbg[8];
+                    CK(cudaMemcpyAsync(dbg, c.d_nspec, sizeof(dbg), cudaMemcpyDeviceToHost, s));
+                    CK(cudaStreamSynchronize(s)); mark("  seeds, second round");
+                    fprintf(stderr, "[cnv]   second round: %u open seeds, %u closed, %u skipped as interior\n", n_todo, dbg[4], dbg[5]);
+                }
+            }
             for (int k = 1; k < levels; k++) { k_hop_double<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)(k - 1) * n_nodes, J + (size_t)k * n_nodes, n_nodes); n_launch++; }
-            CK(cudaMemsetAsync(flag, 0, 2 * (size_t)n_nodes, s));
-            CK(cudaMemsetAsync(c.hop_sink.p, 0, 2 * sizeof(HopSink), s));
+            CK(cudaMemsetAsync(flag, 0, (size_t)n_nodes, s));
             unsigned int *n_hop = c.d_nspec + 2;                        // [2]: calls collected per scan
-            for (int k = 0; k < 2; k++) { k_hop_start<<<1, 1, 0, s>>>(ctx[k], c.d_seed + k * words, c.d_wp + k * words, lo, 0, seed_tot[k], base[k], flag); n_launch++; }
+            // The path is found leg by leg: open seeds are sinks of the jump table, so its top level leads from a leg's start straight to
+            // the first open seed on the path; that seed is evaluated here on a window of records and the next leg starts where the
+            // evaluation lands.  One tiny launch and one round trip per leg.
             std::vector<Call> by_host[2];
             std::vector<uint32_t> window;
-            for (int round = 0;; round++) {
-                if (round > 8192) return fail("gromgpu_chr_cnv: the device hop did not terminate");
-                for (int k = levels - 1; k >= 0; k--) { k_hop_mark<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)k * n_nodes, flag, n_nodes); n_launch++; }
-                for (int k = 0; k < 2; k++) if (seed_tot[k]) {
-                    k_hop_collect<<<(2 * seed_tot[k] + 255) / 256, 256, 0, s>>>(flag + base[k], done + base[k], c.d_land + (size_t)k * 2 * c.land_cap, c.d_seed + k * words, c.d_wp + k * words, words,
-                                                                                 seed_tot[k], c.d_spec, c.hop_out.as<HopCall>() + (size_t)k * (c.spec_cap / 2), c.spec_cap / 2, n_hop + k,
-                                                                                 c.hop_sink.as<HopSink>() + k); n_launch++;
-                }
+            HopLeg leg[2] = {{lo, 0, 1}, {lo, 0, 1}};
+            int64_t n_legs = 0;
+            int no_call = 0; bool swept = false;
+            while (leg[0].active || leg[1].active) {
+                if (++n_legs > (int64_t)2 * most + 4) return fail("gromgpu_chr_cnv: the device hop did not terminate");
+                k_hop_advance<<<1, 2, 0, s>>>(ctx[0], ctx[1], c.d_seed, c.d_wp, words, J + (size_t)(levels - 1) * n_nodes, leg[0], leg[1], seed_tot[0], seed_tot[1], flag,
+                                              c.hop_sink.as<HopSink>()); n_launch++;
                 HopSink sink[2];
                 CK(cudaMemcpyAsync(sink, c.hop_sink.p, sizeof(sink), cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));
-                if (!sink[0].found && !sink[1].found) break;
-                // a seed the device left unresolved lies on the path (a genuine multi-kb event): evaluate it here on a window of records
-                for (int k = 0; k < 2; k++) if (sink[k].found) {
+                for (int k = 0; k < 2; k++) if (leg[k].active) {
+                    if (!sink[k].found) { leg[k].active = 0; continue; }
                     const int64_t pos = sink[k].pos;
                     Outcome o;
                     int c0 = 0;
-                    for (int64_t span = 3 * (int64_t)Lmax + 2048;; span *= 2) {
+                    for (int64_t span = std::max<int64_t>(3 * (int64_t)Lmax + 2048, 1 << 17);; span *= 2) {
                         const int64_t w1 = std::min<int64_t>(P, pos + span);
                         window.resize(w1 - pos);
-                        CK(cudaMemcpy(window.data(), c.d_rec + pos, sizeof(uint32_t) * (w1 - pos), cudaMemcpyDeviceToHost));
+                        CK(cudaMemcpyAsync(window.data(), c.d_rec + pos, sizeof(uint32_t) * (w1 - pos), cudaMemcpyDeviceToHost, s));
+                        CK(cudaStreamSynchronize(s));
                         d2h += 4 * (w1 - pos);
                         SegCtx hc = ctx[k];
-                        hc.rec = window.data() - pos; hc.len = w1; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data(); hc.wtab = c.wtab.data();
+                        hc.rec = window.data() - pos; hc.len = w1; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data(); hc.win_thr = c.win_thr.data(); hc.wtab = c.wtab.data();
                         c0 = hc.cls(pos);
                         o = eval_seed<false>(hc, pos, c0 != 2 ? c0 : sink[k].variant);
                         if (w1 == P || o.far < w1) break;
                     }
-                    if (o.kind == SEG_CALL) by_host[k].push_back({pos, o.c_end, o.c_z});
-                    const HopSink zero = {0, 0, 0};
-                    CK(cudaMemcpyAsync(c.hop_sink.as<HopSink>() + k, &zero, sizeof(zero), cudaMemcpyHostToDevice, s));
-                    // the sink stays flagged and is marked done, the path continues from where the evaluation lands
-                    uint32_t rank_node = 0;      // node id is recovered on the device from (pos, variant): restart by position
-                    (void)rank_node;
-                    k_hop_done<<<1, 1, 0, s>>>(c.d_seed + k * words, c.d_wp + k * words, pos, sink[k].variant, done + base[k]); n_launch++;
-                    k_hop_start<<<1, 1, 0, s>>>(ctx[k], c.d_seed + k * words, c.d_wp + k * words, o.next, c0 != 2 ? c0 : sink[k].variant, seed_tot[k], base[k], flag); n_launch++;
+                    if (o.kind == SEG_CALL) by_host[k].push_back({pos, o.c_end, o.c_z}); else no_call++;
+                    leg[k].x = o.next; leg[k].s = c0 != 2 ? c0 : sink[k].variant;
                 }
+                if (two_pass && no_call > 32) {
+                    // the guess was wrong somewhere (skipped seeds that are no calls keep turning up on the path): close whatever is still open
+                    second_round(2);
+                    for (int k = 1; k < levels; k++) { k_hop_double<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)(k - 1) * n_nodes, J + (size_t)k * n_nodes, n_nodes); n_launch++; }
+                    two_pass = false; swept = true;
+                }
+            }
+            unsigned int still_open = 0;
+            if (trace) { CK(cudaMemcpyAsync(&still_open, c.d_nspec + 4, sizeof(still_open), cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); still_open = cnt2[1] - still_open; }
+            mark("  jump table + legs");
+            for (int k = levels - 1; k >= 0; k--) { k_hop_mark<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)k * n_nodes, flag, n_nodes); n_launch++; }
+            for (int k = 0; k < 2; k++) if (seed_tot[k]) {
+                k_hop_collect<<<(2 * seed_tot[k] + 255) / 256, 256, 0, s>>>(flag + base[k], c.d_land + (size_t)k * 2 * c.land_cap, c.d_seed + k * words, c.d_wp + k * words, words,
+                                                                             seed_tot[k], c.d_spec, c.hop_out.as<HopCall>() + (size_t)k * (c.spec_cap / 2), c.spec_cap / 2, n_hop + k); n_launch++;
             }
             unsigned int n_got[2] = {0, 0};
             CK(cudaMemcpyAsync(n_got, n_hop, sizeof(n_got), cudaMemcpyDeviceToHost, s));
@@ -2082,9 +2118,10 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 std::sort(found[k].begin(), found[k].end(), [](const Call &a, const Call &b) { return a.start < b.start; });
             }
             seed_tot_all = 0; n_spec_all = 0;
-            if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u, jump table %d levels x %u nodes; calls from the device %u + %u, evaluated on the host %zu + %zu\n", seed_tot[0], seed_tot[1],
-                               levels, n_nodes, n_got[0], n_got[1], by_host[0].size(), by_host[1].size());
-            } else { dev_end(); if (trace) fprintf(stderr, "[cnv] %u seeds left unresolved: scanning on the host\n", still_open); }
+            if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u (%u left unresolved), jump table %d levels x %u nodes, %lld legs; calls from the device %u + %u, from host-evaluated seeds %zu + %zu\n",
+                               seed_tot[0], seed_tot[1], still_open, levels, n_nodes, (long long)n_legs, n_got[0], n_got[1], by_host[0].size(), by_host[1].size());
+            if (trace) fprintf(stderr, "[cnv] %u seeds open after the first round%s\n", cnt2[1], swept ? "; the second round needed a sweep" : "");
+            } else { dev_end(); if (trace) fprintf(stderr, "[cnv] no jump table: scanning on the host\n"); }
         }
         if (!have_land || !device_hop) {
             // host scan over the packed records, in parallel pieces; with the device-evaluated seed tables when they exist (the hop is
@@ -2101,7 +2138,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             }
             Segmenter sg[2];
             for (int k = 0; k < 2; k++) {
-                sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].C.wtab = c.wtab.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
+                sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].C.win_thr = c.win_thr.data(); sg[k].C.wtab = c.wtab.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
                 if (have_land) { sg[k].wp = c.h_wp + k * words; sg[k].land = c.h_land + (size_t)k * 2 * c.land_cap; sg[k].spec = c.h_spec; }
             }
             const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));

@@ -12,9 +12,11 @@ ap.add_argument("--depth", type=float, default=30.0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--simple", type=int, default=1)
 ap.add_argument("--rmdup", type=int, default=1)
+ap.add_argument("--cnv-per-mb", type=float, default=0.0)
+ap.add_argument("--skip-e2e", type=int, default=0)
 a = ap.parse_args()
 t = time.time()
-spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05, simple_disc_frac=0.01, names=False)
+spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05, simple_disc_frac=0.01, names=False, cnv_per_mb=a.cnv_per_mb)
 c = synth.simulate(spec)[0]
 print("generated", c.batch.n_reads, "reads in", round(time.time() - t, 1), "s", flush=True)
 prm = Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=a.rmdup)
@@ -36,6 +38,7 @@ with gpu.Chromosome(0, c.chars) as ch:
         print(json.dumps(dict(cnv_ms_total=round(g.ms_total, 2), cnv_ms_device=round(g.ms_device, 2), cnv_ms_host=round(g.ms_host, 2), wall_ms=round(dt * 1e3, 2),
                               calls=len(g.calls), samples=g.n_samples, frames=g.n_frames, repeats=g.n_repeats, biased=g.biased_repeat)))
     # end-to-end breakdown with pageable-vs-pinned note: the bench pins its batch; here the arrays are numpy (pageable)
+    if a.skip_e2e: sys.exit(0)
     import ctypes
     cuda = ctypes.CDLL("libcudart.so")
     def sync(): cuda.cudaDeviceSynchronize()
