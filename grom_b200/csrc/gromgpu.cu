@@ -333,10 +333,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { while
 __device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 
 #define QCAP (CHUNK * 160)        // quality bytes per stage (64 reads of 2x150 data); the 4-bit area is half of it
+#ifndef NSTAGE
 #define NSTAGE 3
+#endif
 #define NWARP (TILE / 32)         // consumer warps, one reference position per thread
 #define PILE_THREADS (TILE + 32)  // + 1 producer warp
-#define SUBTILES 8                // consecutive tiles handled by one CTA (keeps the producer pipeline full across tiles)
+#ifndef PILE_MIN_CTAS
+#define PILE_MIN_CTAS 3
+#endif
+#ifndef SUBTILES
+#define SUBTILES 8
+#endif
+//                              // consecutive tiles handled by one CTA (keeps the producer pipeline full across tiles)
 
 // Per staged read the producer warp leaves three 16-byte records of plain ints in shared memory so that the
 // position threads need no bit unpacking (all values are warp-uniform broadcasts):
@@ -377,7 +385,7 @@ struct __align__(128) PileSmem {
     int last[NSTAGE];
 };
 
-__global__ void __launch_bounds__(PILE_THREADS, 3) k_pileup(DevReads R, const PrepRec *__restrict__ prep, const int64_t *__restrict__ tile_first,
+__global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads R, const PrepRec *__restrict__ prep, const int64_t *__restrict__ tile_first,
                                                           const int *__restrict__ max_span_p, int64_t n_tiles,
                                                           const char *__restrict__ fasta, int64_t P, int64_t Ppad, int32_t *__restrict__ arrays,
                                                           SnvScanArgs sc)
@@ -1038,6 +1046,94 @@ __global__ void k_fix_offsets(uint64_t *cigar_off, uint64_t *base_off, int64_t n
     if (i < n) { cigar_off[i] += cig_base; base_off[i] += slot_base; }
 }
 
+// ---- transport-compact forms of the read batch (include/grom_reads.h: GROM_LAYOUT_*): the canonical device arrays are rebuilt here
+// canonical offsets: cigar_off = exclusive sum of n_cigar, base_off = exclusive sum of l_qseq rounded up to GROM_BASE_ALIGN
+#define OFF_BLOCK 1024
+__device__ __forceinline__ uint64_t pad_slots(int l) { return ((uint64_t)(l > 0 ? l : 0) + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN; }
+__device__ __forceinline__ void block_excl_scan2(uint64_t &a, uint64_t &b, uint64_t *sh /* [2 * 32 + 2] */, uint64_t &tot_a, uint64_t &tot_b)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint64_t ia = a, ib = b;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t ya = __shfl_up_sync(0xffffffffu, ia, d), yb = __shfl_up_sync(0xffffffffu, ib, d); if (lane >= d) { ia += ya; ib += yb; } }
+    if (lane == 31) { sh[wid] = ia; sh[32 + wid] = ib; }
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t wa = lane < nw ? sh[lane] : 0, wb = lane < nw ? sh[32 + lane] : 0;
+        const uint64_t oa = wa, ob = wb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t ya = __shfl_up_sync(0xffffffffu, wa, d), yb = __shfl_up_sync(0xffffffffu, wb, d); if (lane >= d) { wa += ya; wb += yb; } }
+        if (lane < nw) { sh[lane] = wa - oa; sh[32 + lane] = wb - ob; }
+        if (lane == 31) { sh[64] = wa; sh[65] = wb; }
+    }
+    __syncthreads();
+    a = ia - a + sh[wid]; b = ib - b + sh[32 + wid];
+    tot_a = sh[64]; tot_b = sh[65];
+    __syncthreads();
+}
+__global__ void __launch_bounds__(256) k_off_sums(const uint16_t *__restrict__ n_cigar, const int32_t *__restrict__ l_qseq, int64_t n, uint64_t *__restrict__ bsum)
+{
+    __shared__ uint64_t sh[66];
+    const int64_t i0 = (int64_t)blockIdx.x * OFF_BLOCK + threadIdx.x * 4;
+    uint64_t a = 0, b = 0, ta, tb;
+    for (int k = 0; k < 4; k++) if (i0 + k < n) { a += n_cigar[i0 + k]; b += pad_slots(l_qseq[i0 + k]); }
+    block_excl_scan2(a, b, sh, ta, tb);
+    if (threadIdx.x == 0) { bsum[2 * (int64_t)blockIdx.x] = ta; bsum[2 * (int64_t)blockIdx.x + 1] = tb; }
+}
+__global__ void __launch_bounds__(1024) k_off_scan(uint64_t *bsum, int64_t nblk)
+{
+    __shared__ uint64_t sh[66];
+    const int64_t per = (nblk + blockDim.x - 1) / blockDim.x, j0 = (int64_t)threadIdx.x * per, j1 = min(j0 + per, nblk);
+    uint64_t a = 0, b = 0, ta, tb;
+    for (int64_t j = j0; j < j1; j++) { a += bsum[2 * j]; b += bsum[2 * j + 1]; }
+    block_excl_scan2(a, b, sh, ta, tb);
+    for (int64_t j = j0; j < j1; j++) { const uint64_t va = bsum[2 * j], vb = bsum[2 * j + 1]; bsum[2 * j] = a; bsum[2 * j + 1] = b; a += va; b += vb; }
+}
+__global__ void __launch_bounds__(256) k_off_write(const uint16_t *__restrict__ n_cigar, const int32_t *__restrict__ l_qseq, int64_t n, const uint64_t *__restrict__ bsum,
+                                                   uint64_t cig_base, uint64_t slot_base, uint64_t *__restrict__ cigar_off, uint64_t *__restrict__ base_off)
+{
+    __shared__ uint64_t sh[66];
+    const int64_t i0 = (int64_t)blockIdx.x * OFF_BLOCK + threadIdx.x * 4;
+    uint64_t va[4], vb[4], a = 0, b = 0, ta, tb;
+    for (int k = 0; k < 4; k++) { va[k] = vb[k] = 0; if (i0 + k < n) { va[k] = n_cigar[i0 + k]; vb[k] = pad_slots(l_qseq[i0 + k]); } a += va[k]; b += vb[k]; }
+    block_excl_scan2(a, b, sh, ta, tb);
+    a += cig_base + bsum[2 * (int64_t)blockIdx.x]; b += slot_base + bsum[2 * (int64_t)blockIdx.x + 1];
+    for (int k = 0; k < 4; k++) if (i0 + k < n) { cigar_off[i0 + k] = a; base_off[i0 + k] = b; a += va[k]; b += vb[k]; }
+}
+// 4-bit dictionary-coded qualities -> one byte per base slot (16 slots per thread)
+struct QualLut { uint8_t v[16]; };
+__global__ void __launch_bounds__(256) k_expand_qual(const uint8_t *__restrict__ q4, int64_t n_slots, QualLut lut, uint8_t *__restrict__ qual)
+{
+    __shared__ uint8_t sl[16];
+    if (threadIdx.x < 16) sl[threadIdx.x] = lut.v[threadIdx.x];
+    __syncthreads();
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, s0 = g * 16;
+    if (s0 >= n_slots) return;
+    if (s0 + 16 <= n_slots) {
+        const uint2 w = *reinterpret_cast<const uint2 *>(q4 + (s0 >> 1));
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t half = (k < 2 ? w.x : w.y) >> ((k & 1) * 16);          // two source bytes = four slots
+            const uint32_t b0 = half & 0xff, b1 = (half >> 8) & 0xff;
+            o[k] = (uint32_t)sl[b0 >> 4] | ((uint32_t)sl[b0 & 15] << 8) | ((uint32_t)sl[b1 >> 4] << 16) | ((uint32_t)sl[b1 & 15] << 24);
+        }
+        *reinterpret_cast<uint4 *>(qual + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int64_t t = s0; t < n_slots; t++) qual[t] = sl[(q4[t >> 1] >> ((~t & 1) << 2)) & 15];
+    }
+}
+// sparse first-SA-entry fields -> dense per-read arrays (already preset to "none")
+struct SaSparse { const int32_t *idx, *pos, *sadj, *eadj, *indel; const int16_t *mapq; const uint8_t *strand, *same; };
+__global__ void __launch_bounds__(256) k_scatter_sa(SaSparse S, int64_t n_sa, int64_t n, int32_t *pos, int32_t *sadj, int32_t *eadj, int32_t *indel, uint8_t *strand, int16_t *mapq, uint8_t *same)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_sa) return;
+    const int64_t i = S.idx[k];
+    if (i < 0 || i >= n) return;
+    pos[i] = S.pos[k]; sadj[i] = S.sadj[k]; eadj[i] = S.eadj[k]; indel[i] = S.indel[k]; strand[i] = S.strand[k]; mapq[i] = S.mapq[k]; same[i] = S.same[k];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct DevBuf {
     void *p = nullptr; size_t cap = 0, size = 0;
@@ -1057,7 +1153,8 @@ struct DevBuf {
 };
 
 enum { B_POS, B_MPOS, B_TLEN, B_MTID, B_LQSEQ, B_FLAG, B_NCIGAR, B_MAPQ, B_QLEN, B_HASH, B_CIGOFF, B_BASEOFF, B_CIGAR, B_SEQ4, B_QUAL,
-       B_SAPOS, B_SASADJ, B_SAEADJ, B_SAINDEL, B_SASTRAND, B_SAMAPQ, B_SASAME, B_COUNT };
+       B_SAPOS, B_SASADJ, B_SAEADJ, B_SAINDEL, B_SASTRAND, B_SAMAPQ, B_SASAME, B_COUNT,
+       B_QUAL4 = B_COUNT, B_SATMP, B_OFFTMP, B_ALL };      // the last three: staging of the transport-compact forms
 
 struct CnvState;
 static void cnv_state_free(CnvState *c);
@@ -1067,7 +1164,7 @@ struct gromgpu_chr {
     cudaStream_t stream = nullptr;
     char *d_fasta = nullptr;
     int32_t *d_arrays = nullptr;
-    DevBuf rb[B_COUNT];
+    DevBuf rb[B_ALL];
     int64_t n_reads = 0, n_cigar = 0, n_slots = 0;
     int32_t last_pos = -1, last_lseq = 0;
     int64_t n_leading = 0;             // reads before W/4+1 (they advance the reference's window index, src/GROM.c:5845)
@@ -1189,7 +1286,7 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
 {
     if (!h) return;
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < B_COUNT; i++) h->rb[i].release();
+    for (int i = 0; i < B_ALL; i++) h->rb[i].release();
     cudaFree(h->d_fasta); cudaFree(h->d_arrays); cudaFree(h->d_state); cudaFree(h->d_prep); cudaFree(h->d_tile_first);
     cudaFree(h->d_max_span); cudaFree(h->d_counters); cudaFree(h->d_scan_status); cudaFree(h->d_ticket);
     cudaFree(h->d_cand); cudaFree(h->d_ncand); cudaFree(h->d_ins); cudaFree(h->d_ins_pos); cudaFree(h->d_del); cudaFree(h->d_svev);
@@ -1208,40 +1305,95 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
     if (n == 0) return 0;
     if (b->pos[0] < h->last_pos) return fail("gromgpu_push_reads: reads are not in coordinate order");
     if ((h->n_cigar + b->n_cigar_total) > 0xffffffffLL) return fail("gromgpu_push_reads: more than 2^32 CIGAR operations on one chromosome");
+    const int lay = b->layout_flags;
+    const bool lay_off = lay & GROM_LAYOUT_CANONICAL_OFFSETS, lay_q4 = (lay & GROM_LAYOUT_QUAL4) && b->qual4, lay_sa = (lay & GROM_LAYOUT_SPARSE_SA) != 0;
+    if (!lay_sa && !b->sa_pos) return fail("gromgpu_push_reads: SA arrays missing");
+    if (!lay_off && (!b->cigar_off || !b->base_off)) return fail("gromgpu_push_reads: offset arrays missing (and GROM_LAYOUT_CANONICAL_OFFSETS not set)");
+    if (!lay_q4 && !b->qual) return fail("gromgpu_push_reads: qualities missing");
+    if (lay_sa && (b->n_sa < 0 || b->n_sa > n || (b->n_sa && !b->sa_index))) return fail("gromgpu_push_reads: bad sparse SA list");
+    // src == nullptr: the array is rebuilt on the device from a transport-compact form (below)
     struct { int id; const void *src; size_t elt; int64_t cnt, have; } f[B_COUNT] = {
         { B_POS, b->pos, 4, n, h->n_reads }, { B_MPOS, b->mpos, 4, n, h->n_reads }, { B_TLEN, b->tlen, 4, n, h->n_reads },
         { B_MTID, b->mtid, 4, n, h->n_reads }, { B_LQSEQ, b->l_qseq, 4, n, h->n_reads }, { B_FLAG, b->flag, 2, n, h->n_reads },
         { B_NCIGAR, b->n_cigar, 2, n, h->n_reads }, { B_MAPQ, b->mapq, 1, n, h->n_reads }, { B_QLEN, b->qname_len, 1, n, h->n_reads },
-        { B_HASH, b->qname_hash, 8, n, h->n_reads }, { B_CIGOFF, b->cigar_off, 8, n, h->n_reads }, { B_BASEOFF, b->base_off, 8, n, h->n_reads },
+        { B_HASH, b->qname_hash, 8, n, h->n_reads }, { B_CIGOFF, lay_off ? nullptr : b->cigar_off, 8, n, h->n_reads }, { B_BASEOFF, lay_off ? nullptr : b->base_off, 8, n, h->n_reads },
         { B_CIGAR, b->cigar, 4, b->n_cigar_total, h->n_cigar }, { B_SEQ4, b->seq4, 1, (b->n_base_slots + 1) / 2, h->n_slots / 2 },
-        { B_QUAL, b->qual, 1, b->n_base_slots, h->n_slots },
-        { B_SAPOS, b->sa_pos, 4, n, h->n_reads }, { B_SASADJ, b->sa_start_adj, 4, n, h->n_reads }, { B_SAEADJ, b->sa_end_adj, 4, n, h->n_reads },
-        { B_SAINDEL, b->sa_end_adj_indel, 4, n, h->n_reads }, { B_SASTRAND, b->sa_strand, 1, n, h->n_reads }, { B_SAMAPQ, b->sa_mapq, 2, n, h->n_reads },
-        { B_SASAME, b->sa_same_chr, 1, n, h->n_reads } };
+        { B_QUAL, lay_q4 ? nullptr : b->qual, 1, b->n_base_slots, h->n_slots },
+        { B_SAPOS, lay_sa ? nullptr : b->sa_pos, 4, n, h->n_reads }, { B_SASADJ, lay_sa ? nullptr : b->sa_start_adj, 4, n, h->n_reads }, { B_SAEADJ, lay_sa ? nullptr : b->sa_end_adj, 4, n, h->n_reads },
+        { B_SAINDEL, lay_sa ? nullptr : b->sa_end_adj_indel, 4, n, h->n_reads }, { B_SASTRAND, lay_sa ? nullptr : b->sa_strand, 1, n, h->n_reads }, { B_SAMAPQ, lay_sa ? nullptr : b->sa_mapq, 2, n, h->n_reads },
+        { B_SASAME, lay_sa ? nullptr : b->sa_same_chr, 1, n, h->n_reads } };
+    // in pieces, at most a few in flight: the copy engine serves requests in submission order, so a multi-GB transfer queued
+    // at once would stall every small copy of a second contig that is computing on another stream
+    auto upload = [&](void *dst, const void *src, size_t total) -> int {
+        static const size_t piece = []() { const char *e = getenv("GROMGPU_PUSH_PIECE_MB"); const long mb = e ? atol(e) : 4; return (size_t)(mb > 0 ? mb : 4) << 20; }();
+        for (size_t o = 0; o < total; o += piece) {
+            CK(cudaMemcpyAsync((char *)dst + o, (const char *)src + o, std::min(piece, total - o), cudaMemcpyHostToDevice, h->stream));
+            if (total > piece) {
+                CK(cudaEventRecord(h->ev_push[h->push_seq & 1], h->stream));
+                h->push_seq++;
+                if (h->push_seq >= 2) CK(cudaEventSynchronize(h->ev_push[h->push_seq & 1]));       // the piece before the last one has landed
+            }
+        }
+        return 0;
+    };
     for (int k = 0; k < B_COUNT; k++) {
         DevBuf &d = h->rb[f[k].id];
         const size_t need = (size_t)(f[k].have + f[k].cnt) * f[k].elt + 64;
         if (d.ensure(need, h->stream)) return -1;
-        if (f[k].cnt) {
-            // in pieces, at most a few in flight: the copy engine serves requests in submission order, so a multi-GB transfer queued
-            // at once would stall every small copy of a second contig that is computing on another stream
-            static const size_t piece = []() { const char *e = getenv("GROMGPU_PUSH_PIECE_MB"); const long mb = e ? atol(e) : 4; return (size_t)(mb > 0 ? mb : 4) << 20; }();
-            const size_t total = (size_t)f[k].cnt * f[k].elt;
-            for (size_t o = 0; o < total; o += piece) {
-                CK(cudaMemcpyAsync((char *)d.p + (size_t)f[k].have * f[k].elt + o, (const char *)f[k].src + o, std::min(piece, total - o), cudaMemcpyHostToDevice, h->stream));
-                if (total > piece) {
-                    CK(cudaEventRecord(h->ev_push[h->push_seq & 1], h->stream));
-                    h->push_seq++;
-                    if (h->push_seq >= 2) CK(cudaEventSynchronize(h->ev_push[h->push_seq & 1]));       // the piece before the last one has landed
-                }
-            }
-        }
+        if (f[k].cnt && f[k].src && upload((char *)d.p + (size_t)f[k].have * f[k].elt, f[k].src, (size_t)f[k].cnt * f[k].elt)) return -1;
         d.size = (size_t)(f[k].have + f[k].cnt) * f[k].elt;
     }
-    if (h->n_cigar || h->n_slots) {
+    if (lay_off) {
+        const int64_t nblk = (n + OFF_BLOCK - 1) / OFF_BLOCK;
+        DevBuf &t = h->rb[B_OFFTMP];
+        if (t.ensure(sizeof(uint64_t) * 2 * (size_t)nblk + 64, h->stream)) return -1;
+        const uint16_t *nc = (const uint16_t *)h->rb[B_NCIGAR].p + h->n_reads; const int32_t *lq = (const int32_t *)h->rb[B_LQSEQ].p + h->n_reads;
+        k_off_sums<<<(unsigned)nblk, 256, 0, h->stream>>>(nc, lq, n, (uint64_t *)t.p);
+        k_off_scan<<<1, 1024, 0, h->stream>>>((uint64_t *)t.p, nblk);
+        k_off_write<<<(unsigned)nblk, 256, 0, h->stream>>>(nc, lq, n, (const uint64_t *)t.p, (uint64_t)h->n_cigar, (uint64_t)h->n_slots,
+                                                          (uint64_t *)h->rb[B_CIGOFF].p + h->n_reads, (uint64_t *)h->rb[B_BASEOFF].p + h->n_reads);
+        CK(cudaGetLastError());
+    } else if (h->n_cigar || h->n_slots) {
         k_fix_offsets<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((uint64_t *)h->rb[B_CIGOFF].p + h->n_reads, (uint64_t *)h->rb[B_BASEOFF].p + h->n_reads,
                                                                            n, (uint64_t)h->n_cigar, (uint64_t)h->n_slots);
         CK(cudaGetLastError());
+    }
+    if (lay_q4 && b->n_base_slots) {
+        DevBuf &t = h->rb[B_QUAL4];
+        const size_t nb = (size_t)(b->n_base_slots + 1) / 2;
+        if (t.ensure(nb + 64, h->stream)) return -1;
+        if (upload(t.p, b->qual4, nb)) return -1;
+        QualLut lut; memcpy(lut.v, b->qual_lut, 16);
+        k_expand_qual<<<(unsigned)((b->n_base_slots + 16 * 256 - 1) / (16 * 256)), 256, 0, h->stream>>>((const uint8_t *)t.p, b->n_base_slots, lut, (uint8_t *)h->rb[B_QUAL].p + h->n_slots);
+        CK(cudaGetLastError());
+    }
+    if (lay_sa) {
+        int32_t *d_pos = (int32_t *)h->rb[B_SAPOS].p + h->n_reads;
+        CK(cudaMemsetAsync(d_pos, 0xff, sizeof(int32_t) * (size_t)n, h->stream));              // sa_pos = -1: no entry
+        for (int id : {B_SASADJ, B_SAEADJ, B_SAINDEL}) CK(cudaMemsetAsync((int32_t *)h->rb[id].p + h->n_reads, 0, sizeof(int32_t) * (size_t)n, h->stream));
+        CK(cudaMemsetAsync((uint8_t *)h->rb[B_SASTRAND].p + h->n_reads, 0, (size_t)n, h->stream));
+        CK(cudaMemsetAsync((int16_t *)h->rb[B_SAMAPQ].p + h->n_reads, 0xff, sizeof(int16_t) * (size_t)n, h->stream));     // -1 like sa_pos
+        CK(cudaMemsetAsync((uint8_t *)h->rb[B_SASAME].p + h->n_reads, 0, (size_t)n, h->stream));
+        const int64_t m = b->n_sa;
+        if (m) {
+            DevBuf &t = h->rb[B_SATMP];
+            const size_t m4 = ((size_t)m * 4 + 15) & ~(size_t)15, m2 = ((size_t)m * 2 + 15) & ~(size_t)15, m1 = ((size_t)m + 15) & ~(size_t)15;
+            if (t.ensure(5 * m4 + m2 + 2 * m1 + 64, h->stream)) return -1;
+            char *q = (char *)t.p;
+            SaSparse S;
+            S.idx = (const int32_t *)q; if (upload(q, b->sa_index, (size_t)m * 4)) return -1; q += m4;
+            S.pos = (const int32_t *)q; if (upload(q, b->sas_pos, (size_t)m * 4)) return -1; q += m4;
+            S.sadj = (const int32_t *)q; if (upload(q, b->sas_start_adj, (size_t)m * 4)) return -1; q += m4;
+            S.eadj = (const int32_t *)q; if (upload(q, b->sas_end_adj, (size_t)m * 4)) return -1; q += m4;
+            S.indel = (const int32_t *)q; if (upload(q, b->sas_end_adj_indel, (size_t)m * 4)) return -1; q += m4;
+            S.mapq = (const int16_t *)q; if (upload(q, b->sas_mapq, (size_t)m * 2)) return -1; q += m2;
+            S.strand = (const uint8_t *)q; if (upload(q, b->sas_strand, (size_t)m)) return -1; q += m1;
+            S.same = (const uint8_t *)q; if (upload(q, b->sas_same_chr, (size_t)m)) return -1;
+            k_scatter_sa<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(S, m, n, d_pos, (int32_t *)h->rb[B_SASADJ].p + h->n_reads, (int32_t *)h->rb[B_SAEADJ].p + h->n_reads,
+                                                                             (int32_t *)h->rb[B_SAINDEL].p + h->n_reads, (uint8_t *)h->rb[B_SASTRAND].p + h->n_reads,
+                                                                             (int16_t *)h->rb[B_SAMAPQ].p + h->n_reads, (uint8_t *)h->rb[B_SASAME].p + h->n_reads);
+            CK(cudaGetLastError());
+        }
     }
     // host-side bookkeeping the scan range needs (src/GROM.c:6406, 11075-11083)
     const int first_pos = grom_first_pos(&g_params);
@@ -1250,7 +1402,7 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
     {
         // hard clips of the last read extend its length once it is applied (src/GROM.c:6997-7000; first max_cigar_ops operations)
         int hsum = 0;
-        const uint64_t c0 = b->cigar_off[n - 1];
+        const uint64_t c0 = lay_off ? (uint64_t)(b->n_cigar_total - b->n_cigar[n - 1]) : b->cigar_off[n - 1];
         const int nc = std::min<int>(b->n_cigar[n - 1], g_params.max_cigar_ops);
         for (int k = 0; k < nc; k++) if ((b->cigar[c0 + k] & 15) == 5) hsum += (int)(b->cigar[c0 + k] >> 4);
         h->last_lseq_applied = h->last_lseq + hsum;

@@ -18,7 +18,7 @@ from .params import CNV_CALL_DTYPE, DEL_EVENT_DTYPE, SV_EVENT_DTYPE, GA, GA_COUN
 from .reads import CReadBatch, ReadBatch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgromgpu.so")
+LIB_PATH = os.environ.get("GROMGPU_LIB") or os.path.join(_HERE, "libgromgpu.so")     # override: kernel tuning builds (tools/)
 _LIB = None
 
 

@@ -174,6 +174,8 @@ struct grom_batch {
     uint8_t *mapq, *qname_len, *sa_strand, *sa_same_chr;
     uint64_t *qname_hash, *cigar_off, *base_off, *qname_off;
     uint32_t *cigar; uint8_t *seq4, *qual; char *qname_pool;
+    /* transport-compact forms (grom_reads.h GROM_LAYOUT_*), built once the canonical arrays are filled */
+    uint8_t *qual4; int32_t *sa_index, *sas_pos, *sas_start_adj, *sas_end_adj, *sas_end_adj_indel; int16_t *sas_mapq; uint8_t *sas_strand, *sas_same_chr;
 };
 
 void gromhost_batch_view(const grom_batch *bt, grom_read_batch *view) { *view = bt->v; }
@@ -185,7 +187,57 @@ void gromhost_batch_free(grom_batch *t)
     free(t->sa_start_adj); free(t->sa_end_adj); free(t->sa_end_adj_indel); free(t->flag); free(t->n_cigar);
     free(t->sa_mapq); free(t->mapq); free(t->qname_len); free(t->sa_strand); free(t->sa_same_chr);
     free(t->qname_hash); free(t->cigar_off); free(t->base_off); free(t->qname_off); free(t->cigar);
-    free(t->seq4); free(t->qual); free(t->qname_pool); free(t);
+    free(t->seq4); free(t->qual); free(t->qname_pool);
+    free(t->qual4); free(t->sa_index); free(t->sas_pos); free(t->sas_start_adj); free(t->sas_end_adj); free(t->sas_end_adj_indel);
+    free(t->sas_mapq); free(t->sas_strand); free(t->sas_same_chr); free(t);
+}
+
+/* What crosses PCIe can be smaller than the canonical arrays (all lossless; the CUDA library rebuilds the canonical device
+ * arrays): the offsets are running sums by construction here; base qualities of current instruments take a handful of distinct
+ * values, so a 16-entry dictionary halves them; the first-SA-entry fields exist for a small minority of reads. */
+static void batch_compact(grom_batch *t, int n_threads)
+{
+    grom_read_batch *v = &t->v;
+    const int64_t n = v->n_reads, ns = v->n_base_slots;
+    int flags = GROM_LAYOUT_CANONICAL_OFFSETS;
+    if (ns > 0 && (ns & 1) == 0) {
+        int64_t hist[256]; memset(hist, 0, sizeof(hist));
+        #pragma omp parallel num_threads(n_threads)
+        {
+            int64_t h[256]; memset(h, 0, sizeof(h));
+            #pragma omp for schedule(static) nowait
+            for (int64_t s = 0; s < ns; s++) h[t->qual[s]]++;
+            #pragma omp critical
+            for (int k = 0; k < 256; k++) hist[k] += h[k];
+        }
+        int nv = 0; uint8_t inv[256]; memset(inv, 0, sizeof(inv));
+        for (int k = 0; k < 256; k++) if (hist[k]) { if (nv < 16) { v->qual_lut[nv] = (uint8_t)k; inv[k] = (uint8_t)nv; } nv++; }
+        if (nv <= 16 && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
+            #pragma omp parallel for schedule(static) num_threads(n_threads)
+            for (int64_t s = 0; s < ns; s += 2) t->qual4[s >> 1] = (uint8_t)((inv[t->qual[s]] << 4) | inv[t->qual[s + 1]]);
+            v->qual4 = t->qual4; flags |= GROM_LAYOUT_QUAL4;
+        } else memset(v->qual_lut, 0, 16);
+    }
+    int64_t m = 0;
+#define SA_SET(i) (t->sa_pos[i] != -1 || t->sa_mapq[i] != -1 || t->sa_strand[i] || t->sa_same_chr[i] || t->sa_start_adj[i] || t->sa_end_adj[i] || t->sa_end_adj_indel[i])
+    for (int64_t i = 0; i < n; i++) m += SA_SET(i);
+    t->sa_index = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1)); t->sas_pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1));
+    t->sas_start_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1)); t->sas_end_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1));
+    t->sas_end_adj_indel = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1)); t->sas_mapq = (int16_t *)malloc(sizeof(int16_t) * (size_t)(m + 1));
+    t->sas_strand = (uint8_t *)malloc((size_t)(m + 1)); t->sas_same_chr = (uint8_t *)malloc((size_t)(m + 1));
+    if (t->sa_index && t->sas_pos && t->sas_start_adj && t->sas_end_adj && t->sas_end_adj_indel && t->sas_mapq && t->sas_strand && t->sas_same_chr) {
+        int64_t k = 0;
+        for (int64_t i = 0; i < n; i++) if (SA_SET(i)) {                /* parse_sa leaves every other read at (-1, 0, -1, 0, 0, 0, 0) */
+            t->sa_index[k] = (int32_t)i; t->sas_pos[k] = t->sa_pos[i]; t->sas_start_adj[k] = t->sa_start_adj[i]; t->sas_end_adj[k] = t->sa_end_adj[i];
+            t->sas_end_adj_indel[k] = t->sa_end_adj_indel[i]; t->sas_mapq[k] = t->sa_mapq[i]; t->sas_strand[k] = t->sa_strand[i]; t->sas_same_chr[k] = t->sa_same_chr[i];
+            k++;
+        }
+        v->n_sa = m; v->sa_index = t->sa_index; v->sas_pos = t->sas_pos; v->sas_start_adj = t->sas_start_adj; v->sas_end_adj = t->sas_end_adj;
+        v->sas_end_adj_indel = t->sas_end_adj_indel; v->sas_mapq = t->sas_mapq; v->sas_strand = t->sas_strand; v->sas_same_chr = t->sas_same_chr;
+        flags |= GROM_LAYOUT_SPARSE_SA;
+    }
+    v->layout_flags = flags;
+#undef SA_SET
 }
 
 static void batch_publish(grom_batch *t)
@@ -410,6 +462,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     free(recoff); free(u); free(blk);
     t->v.n_reads = n_reads; t->v.n_cigar_total = n_cig; t->v.n_base_slots = n_slots;
     batch_publish(t);
+    batch_compact(t, n_threads);
     *out = t;
     return 0;
 }

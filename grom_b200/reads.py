@@ -28,7 +28,7 @@ FPAIRED, FPROPER, FUNMAP, FMUNMAP, FREVERSE, FMREVERSE, FREAD1, FREAD2, FSECONDA
 class CReadBatch(C.Structure):
     _fields_ = [
         ("n_reads", C.c_int64), ("n_cigar_total", C.c_int64), ("n_base_slots", C.c_int64),
-        ("tid", C.c_int32), ("reserved", C.c_int32),
+        ("tid", C.c_int32), ("layout_flags", C.c_int32),
         ("pos", C.c_void_p), ("mpos", C.c_void_p), ("tlen", C.c_void_p), ("mtid", C.c_void_p),
         ("l_qseq", C.c_void_p), ("flag", C.c_void_p), ("n_cigar", C.c_void_p), ("mapq", C.c_void_p),
         ("qname_len", C.c_void_p), ("qname_hash", C.c_void_p), ("cigar_off", C.c_void_p),
@@ -36,7 +36,16 @@ class CReadBatch(C.Structure):
         ("sa_pos", C.c_void_p), ("sa_start_adj", C.c_void_p), ("sa_end_adj", C.c_void_p),
         ("sa_end_adj_indel", C.c_void_p), ("sa_strand", C.c_void_p), ("sa_mapq", C.c_void_p),
         ("sa_same_chr", C.c_void_p), ("qname_off", C.c_void_p), ("qname_pool", C.c_void_p),
+        # transport-compact forms (include/grom_reads.h: GROM_LAYOUT_*)
+        ("qual4", C.c_void_p), ("qual_lut", C.c_uint8 * 16), ("n_sa", C.c_int64), ("sa_index", C.c_void_p),
+        ("sas_pos", C.c_void_p), ("sas_start_adj", C.c_void_p), ("sas_end_adj", C.c_void_p), ("sas_end_adj_indel", C.c_void_p),
+        ("sas_mapq", C.c_void_p), ("sas_strand", C.c_void_p), ("sas_same_chr", C.c_void_p),
     ]
+
+
+LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SPARSE_SA = 1, 2, 4
+SA_FIELDS = ["sa_pos", "sa_start_adj", "sa_end_adj", "sa_end_adj_indel", "sa_strand", "sa_mapq", "sa_same_chr"]
+SA_NONE = {"sa_pos": -1, "sa_mapq": -1}         # what a read without SA / XP entry carries (everything else 0)
 
 
 _DTYPES = {
@@ -96,6 +105,12 @@ class ReadBatch:
     qname_pool: Optional[np.ndarray] = None     # uint8
     aux_off: Optional[np.ndarray] = None        # uint64 [n+1]  raw BAM aux bytes (tooling only)
     aux_pool: Optional[np.ndarray] = None       # uint8
+    # transport-compact forms (compact()): what the CUDA library uploads instead of the canonical arrays
+    layout_flags: int = 0
+    qual4: Optional[np.ndarray] = None          # uint8, two base slots per byte (nibble order of seq4), indices into qual_lut
+    qual_lut: Optional[np.ndarray] = None       # uint8 [16]
+    sa_index: Optional[np.ndarray] = None       # int32, reads that have an SA / XP entry
+    sa_sparse: Optional[dict] = None            # SA_FIELDS -> arrays of len(sa_index)
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -132,7 +147,93 @@ class ReadBatch:
             setattr(c, k, getattr(self, k).ctypes.data)
         c.qname_off = self.qname_off.ctypes.data if self.qname_off is not None else None
         c.qname_pool = self.qname_pool.ctypes.data if self.qname_pool is not None else None
+        c.layout_flags = int(self.layout_flags)
+        if self.layout_flags & LAYOUT_QUAL4:
+            c.qual4 = self.qual4.ctypes.data
+            for k in range(16):
+                c.qual_lut[k] = int(self.qual_lut[k])
+        if self.layout_flags & LAYOUT_SPARSE_SA:
+            c.n_sa = int(self.sa_index.shape[0])
+            c.sa_index = self.sa_index.ctypes.data
+            for k in SA_FIELDS:
+                setattr(c, "sas_" + k[3:], self.sa_sparse[k].ctypes.data)
         return c
+
+    def has_canonical_offsets(self) -> bool:
+        """cigar_off / base_off are the running sums the batcher produces (GROM_LAYOUT_CANONICAL_OFFSETS)."""
+        n = self.n_reads
+        if n == 0:
+            return True
+        co = np.concatenate([[0], np.cumsum(self.n_cigar.astype(np.uint64))[:-1]]).astype(np.uint64)
+        pad = (self.l_qseq.astype(np.int64) + BASE_ALIGN - 1) // BASE_ALIGN * BASE_ALIGN
+        bo = np.concatenate([[0], np.cumsum(pad)[:-1]]).astype(np.uint64)
+        return bool(np.array_equal(co, self.cigar_off) and np.array_equal(bo, self.base_off))
+
+    def repack_canonical(self) -> "ReadBatch":
+        """Same reads with cigar[] / base slots laid out back to back (each read's slots rounded up to BASE_ALIGN): the
+        layout the host batcher produces.  Tooling for batches assembled by other means."""
+        self.normalise()
+        n = self.n_reads
+        lq = self.l_qseq.astype(np.int64)
+        pad = (lq + BASE_ALIGN - 1) // BASE_ALIGN * BASE_ALIGN
+        bo = np.concatenate([[0], np.cumsum(pad)]).astype(np.int64)
+        nc = self.n_cigar.astype(np.int64)
+        co = np.concatenate([[0], np.cumsum(nc)]).astype(np.int64)
+        within = np.arange(int(lq.sum())) - np.repeat(np.cumsum(lq) - lq, lq)
+        src = np.repeat(self.base_off.astype(np.int64), lq) + within
+        dst = np.repeat(bo[:-1], lq) + within
+        code = np.zeros(int(bo[-1]), dtype=np.uint8); qual = np.zeros(int(bo[-1]), dtype=np.uint8)
+        code[dst] = (self.seq4[src >> 1] >> ((~src & 1) << 2)) & 15
+        qual[dst] = self.qual[src]
+        cw = np.arange(int(nc.sum())) - np.repeat(co[:-1], nc)
+        self.cigar = self.cigar[np.repeat(self.cigar_off.astype(np.int64), nc) + cw]
+        self.seq4 = ((code[0::2] << 4) | code[1::2]).astype(np.uint8)
+        self.qual = qual
+        self.cigar_off, self.base_off = co[:-1].astype(np.uint64), bo[:-1].astype(np.uint64)
+        self.layout_flags = 0
+        return self.normalise()
+
+    def compact(self) -> "ReadBatch":
+        """Attach the transport-compact forms the data allow (lossless; the canonical arrays stay in place for host users):
+        offsets derived on the device, 4-bit dictionary-coded qualities when the batch holds <= 16 distinct values, and the
+        first-SA-entry fields only for the reads that have one."""
+        self.normalise()
+        flags = 0
+        if self.has_canonical_offsets():
+            flags |= LAYOUT_CANONICAL_OFFSETS
+        vals = np.flatnonzero(np.bincount(self.qual, minlength=256)).astype(np.uint8) if self.qual.size else np.zeros(0, np.uint8)
+        if 0 < vals.size <= 16 and self.qual.size % 2 == 0:
+            lut = np.zeros(16, dtype=np.uint8); lut[:vals.size] = vals
+            inv = np.zeros(256, dtype=np.uint8); inv[vals] = np.arange(vals.size, dtype=np.uint8)
+            code = inv[self.qual]
+            self.qual4 = np.ascontiguousarray((code[0::2] << 4) | code[1::2])
+            self.qual_lut = lut
+            flags |= LAYOUT_QUAL4
+        has = np.zeros(self.n_reads, dtype=bool)
+        for k in SA_FIELDS:
+            has |= getattr(self, k) != SA_NONE.get(k, 0)
+        self.sa_index = np.flatnonzero(has).astype(np.int32)
+        self.sa_sparse = {k: np.ascontiguousarray(getattr(self, k)[self.sa_index]) for k in SA_FIELDS}
+        flags |= LAYOUT_SPARSE_SA
+        self.layout_flags = flags
+        return self
+
+    def transport_bytes(self) -> int:
+        """Bytes the CUDA library copies host -> device for this batch (gromgpu_push_reads)."""
+        f = self.layout_flags
+        skip = set()
+        if f & LAYOUT_CANONICAL_OFFSETS:
+            skip |= {"cigar_off", "base_off"}
+        if f & LAYOUT_QUAL4:
+            skip.add("qual")
+        if f & LAYOUT_SPARSE_SA:
+            skip |= set(SA_FIELDS)
+        n = sum(getattr(self, k).nbytes for k in _DTYPES if k not in skip)
+        if f & LAYOUT_QUAL4:
+            n += self.qual4.nbytes
+        if f & LAYOUT_SPARSE_SA:
+            n += self.sa_index.nbytes + sum(v.nbytes for v in self.sa_sparse.values())
+        return int(n)
 
     # ------------------------------------------------------------------ helpers
     def bases(self, i: int) -> np.ndarray:
@@ -187,6 +288,13 @@ def batch_from_c(view: CReadBatch, keep_names: bool) -> ReadBatch:
             cnt = n
         kw[k] = arr(getattr(view, k), dt, cnt)
     b = ReadBatch(tid=view.tid, **kw)
+    b.layout_flags = int(view.layout_flags)
+    if view.layout_flags & LAYOUT_QUAL4:
+        b.qual4 = arr(view.qual4, np.uint8, view.n_base_slots // 2)
+        b.qual_lut = np.array(list(view.qual_lut), dtype=np.uint8)
+    if view.layout_flags & LAYOUT_SPARSE_SA:
+        b.sa_index = arr(view.sa_index, np.int32, view.n_sa)
+        b.sa_sparse = {k: arr(getattr(view, "sas_" + k[3:]), _DTYPES[k], view.n_sa) for k in SA_FIELDS}
     if keep_names and view.qname_off:
         b.qname_off = arr(view.qname_off, np.uint64, n + 1)
         b.qname_pool = arr(view.qname_pool, np.uint8, int(b.qname_off[-1]) if n else 0)

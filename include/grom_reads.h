@@ -45,7 +45,7 @@ typedef struct grom_read_batch {
     int64_t n_cigar_total;      /* entries in cigar[] */
     int64_t n_base_slots;       /* entries in qual[]; seq4 has (n_base_slots+1)/2 bytes */
     int32_t tid;                /* BAM target id shared by every read of the batch */
-    int32_t reserved;
+    int32_t layout_flags;       /* 0 = canonical arrays only; GROM_LAYOUT_* bits announce the transport-compact forms below */
     const int32_t  *pos;        /* 0-based leftmost position (core.pos) */
     const int32_t  *mpos;       /* core.mpos */
     const int32_t  *tlen;       /* core.isize */
@@ -71,7 +71,24 @@ typedef struct grom_read_batch {
     /* host-only, optional (NULL allowed): read names for BAM serialisation */
     const uint64_t *qname_off;  /* [n_reads+1] */
     const char     *qname_pool;
+    /* ---- transport-compact forms (read only when the matching layout_flags bit is set).  They carry the same information
+     * in fewer bytes across PCIe; the CUDA library rebuilds the canonical device arrays from them (bit-identical), so
+     * nothing downstream changes.  319 -> 203 bytes per 150 bp read with all three. */
+    const uint8_t  *qual4;      /* GROM_LAYOUT_QUAL4: per base slot a 4-bit index into qual_lut, nibble order of seq4
+                                   (usable when the batch holds <= 16 distinct quality values); qual may then be NULL */
+    uint8_t         qual_lut[16];
+    int64_t         n_sa;       /* GROM_LAYOUT_SPARSE_SA: the first-SA-entry fields of only the n_sa reads that have one, */
+    const int32_t  *sa_index;   /*   read indices ascending; every other read has sa_pos = sa_mapq = -1 and zeros elsewhere. */
+    const int32_t  *sas_pos, *sas_start_adj, *sas_end_adj, *sas_end_adj_indel;   /* [n_sa]; the dense sa_* arrays may then be NULL */
+    const int16_t  *sas_mapq;
+    const uint8_t  *sas_strand, *sas_same_chr;
 } grom_read_batch;
+
+/* GROM_LAYOUT_CANONICAL_OFFSETS: cigar_off[i] = sum of n_cigar[0..i) and base_off[i] = sum of l_qseq[0..i) each rounded up to
+ * GROM_BASE_ALIGN (what the host batcher always produces); the two offset arrays are then derived on the device and may be NULL */
+#define GROM_LAYOUT_CANONICAL_OFFSETS 1
+#define GROM_LAYOUT_QUAL4             2
+#define GROM_LAYOUT_SPARSE_SA         4
 
 static inline uint64_t grom_qname_hash(const char *s, int len)
 {

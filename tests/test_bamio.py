@@ -5,7 +5,7 @@ import numpy as np
 
 from util import GOLDEN, golden_batches
 from grom_b200 import hostlib
-from grom_b200.reads import fnv1a64
+from grom_b200.reads import LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SPARSE_SA, SA_FIELDS, _DTYPES, fnv1a64
 from tools import synth
 
 
@@ -27,6 +27,14 @@ def test_roundtrip_all_fields(tmp_path):
                 assert r.qname(i) == o.qname(i)
             assert np.all(r.base_off % 32 == 0)
             assert (r.sa_pos >= 0).sum() > 0
+            # the batcher also hands over the transport-compact forms (grom_reads.h GROM_LAYOUT_*): they decode to its canonical arrays
+            assert r.layout_flags == LAYOUT_CANONICAL_OFFSETS | LAYOUT_QUAL4 | LAYOUT_SPARSE_SA and r.has_canonical_offsets()
+            slot = np.arange(r.n_base_slots)
+            assert np.array_equal(r.qual_lut[(r.qual4[slot >> 1] >> ((~slot & 1) << 2)) & 15], r.qual)
+            assert np.array_equal(r.sa_index, np.flatnonzero(r.sa_pos != -1))
+            for k in SA_FIELDS:
+                assert np.array_equal(r.sa_sparse[k], getattr(r, k)[r.sa_index]), k
+            assert r.transport_bytes() < 0.7 * sum(getattr(r, k).nbytes for k in _DTYPES)
 
 
 def test_reader_without_index(tmp_path):

@@ -14,6 +14,7 @@ ap.add_argument("--simple", type=int, default=1)
 ap.add_argument("--rmdup", type=int, default=1)
 ap.add_argument("--cnv-per-mb", type=float, default=0.0)
 ap.add_argument("--skip-e2e", type=int, default=0)
+ap.add_argument("--skip-cnv", type=int, default=0)
 a = ap.parse_args()
 t = time.time()
 spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05, simple_disc_frac=0.01, names=False, cnv_per_mb=a.cnv_per_mb)
@@ -33,7 +34,7 @@ with gpu.Chromosome(0, c.chars) as ch:
     alg = s.bytes_reads + 104 * P   # 26 arrays written by the pileup kernel
     print(f"pileup: {alg/1e9:.3f} GB algorithmic / {s.ms_pileup:.3f} ms = {alg/s.ms_pileup/1e6:.1f} GB/s; "
           f"aligned bases/s (device total) = {s.aligned_bases/s.ms_total/1e-3/1e9:.2f} G")
-    for r in range(2):
+    for r in range(0 if a.skip_cnv else 2):
         t = time.time(); g = ch.cnv(); dt = time.time() - t
         print(json.dumps(dict(cnv_ms_total=round(g.ms_total, 2), cnv_ms_device=round(g.ms_device, 2), cnv_ms_host=round(g.ms_host, 2), wall_ms=round(dt * 1e3, 2),
                               calls=len(g.calls), samples=g.n_samples, frames=g.n_frames, repeats=g.n_repeats, biased=g.biased_repeat)))
