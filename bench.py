@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--depth", type=float, default=30.0)
     ap.add_argument("--cpu-sample-mb", type=float, default=1.5, help="contig length of each CPU-baseline sample contig")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3, help="contigs in flight in the end-to-end measurement")
     ap.add_argument("--canonical-upload", action="store_true", help="upload the canonical arrays only (no transport-compact forms)")
     return ap.parse_args()
 
@@ -172,6 +173,8 @@ def pin_batch(batch):
     out.layout_flags = batch.layout_flags
     if batch.qual4 is not None:
         out.qual4, out.qual_lut = pin(batch.qual4), batch.qual_lut
+    if batch.seq2 is not None:
+        out.seq2, out.seq_exc_slot, out.seq_exc_code = pin(batch.seq2), pin(batch.seq_exc_slot), pin(batch.seq_exc_code)
     if batch.sa_index is not None:
         out.sa_index, out.sa_sparse = pin(batch.sa_index), {k: pin(v) for k, v in batch.sa_sparse.items()}
     return out, keep, out.transport_bytes()
@@ -262,20 +265,28 @@ def main_b200(a):
         ms_e2e_seq = e0.elapsed_time(e1)
         assert len(r2.snv) == len(res.snv) and len(cn2.calls) == len(cn.calls)
         import threading
-        stream2 = torch.cuda.Stream()
-        gpu.set_stream(stream2.cuda_stream)
-        ch2 = gpu.Chromosome(c.batch.tid, fasta_np)
+        n_lanes = max(1, a.lanes)
+        lanes = [(ch, stream)]
+        for _ in range(n_lanes - 1):
+            st_x = torch.cuda.Stream()
+            gpu.set_stream(st_x.cuda_stream)
+            lanes.append((gpu.Chromosome(c.batch.tid, fasta_np), st_x))
         gpu.set_stream(stream.cuda_stream)
-        lanes = [(ch, stream), (ch2, stream2)]
-        done_ev = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
-        counts = [0, 0]
-        lane_log = []                                           # (lane, ms waiting for the bus incl. reset, ms upload, ms compute) per step
+        done_ev = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+        counts = [None] * n_lanes
+        lane_log = []                                           # (lane, ms waiting for the bus incl. reset, ms upload, ms finish, ms cnv, cnv device, cnv host) per step
         bus = threading.Lock()                                  # one upload at a time: the PCIe link is the shared resource
+        todo = [0]
+        todo_lock = threading.Lock()
 
         def lane(k, n_steps, record):
             torch.cuda.set_device(local)
             h, st_k = lanes[k]
-            for _ in range(n_steps):
+            while True:
+                with todo_lock:                                 # steps are handed out as lanes become free
+                    if todo[0] >= n_steps:
+                        break
+                    todo[0] += 1
                 t_a = time.perf_counter()
                 h.reset(fasta_np)
                 with bus:
@@ -290,24 +301,27 @@ def main_b200(a):
                 done_ev[k].record(st_k)
 
         def run_pipelined(n_steps, record):
-            share = [(n_steps + 1) // 2, n_steps // 2]
-            th = [threading.Thread(target=lane, args=(k, share[k], record)) for k in range(2)]
+            todo[0] = 0
+            th = [threading.Thread(target=lane, args=(k, n_steps, record)) for k in range(n_lanes)]
             for t in th:
                 t.start()
             for t in th:
                 t.join()
-        run_pipelined(2, False)                                # warm both lanes (first call allocates)
+        for _ in range(2):
+            run_pipelined(n_lanes, False)                      # warm every lane (first call allocates)
         barrier()
         p0 = torch.cuda.Event(enable_timing=True)
         p0.record(stream)
-        stream2.wait_stream(stream)
+        for _, st_x in lanes[1:]:
+            st_x.wait_stream(stream)
         run_pipelined(a.steps, True)
         barrier()
-        ms_e2e = max(p0.elapsed_time(done_ev[0]), p0.elapsed_time(done_ev[1]) if a.steps > 1 else 0.0)
-        assert counts[0] == len(res.snv) + len(cn.calls)
+        ms_e2e = max(p0.elapsed_time(e) for e in done_ev)
+        assert all(x is None or x == len(res.snv) + len(cn.calls) for x in counts) and any(x is not None for x in counts)
         if rank == 0:
             sys.stderr.write("e2e lanes (lane, wait, upload, finish, cnv, cnv device, cnv host ms): %s\n" % lane_log[-min(8, len(lane_log)):])
-        ch2.close()
+        for h_x, _ in lanes[1:]:
+            h_x.close()
         if rank == 0:
             sampler.window(t_region0, time.time())
         clocks = sampler.stop() if rank == 0 else None
@@ -357,8 +371,8 @@ def main_b200(a):
             "e2e": {"value": total_bases * a.steps / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(read_bytes + P),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps,
                     "upload_form": ("canonical arrays" if not pinned.layout_flags else "transport-compact (include/grom_reads.h GROM_LAYOUT_*): "
-                                    + ", ".join(n for bit, n in ((1, "offsets derived on the device"), (2, "4-bit dictionary qualities"), (4, "sparse SA fields")) if pinned.layout_flags & bit)),
-                    "mode": "two contigs in flight (two streams / host threads): the upload of step i+1 overlaps the kernels and host part of step i",
+                                    + ", ".join(n for bit, n in ((1, "offsets derived on the device"), (2, "4-bit dictionary qualities"), (8, "2-bit bases + exception list"), (4, "sparse SA fields")) if pinned.layout_flags & bit)),
+                    "mode": f"{max(1, a.lanes)} contigs in flight (one stream / host thread each, uploads serialised): the upload of step i+1 overlaps the kernels and host part of step i",
                     "one_at_a_time": {"value": bases * a.steps / (ms_e2e_seq * 1e-3), "ms_per_step": ms_e2e_seq / a.steps}},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_pileup", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

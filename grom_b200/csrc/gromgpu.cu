@@ -1123,6 +1123,54 @@ __global__ void __launch_bounds__(256) k_expand_qual(const uint8_t *__restrict__
         for (int64_t t = s0; t < n_slots; t++) qual[t] = sl[(q4[t >> 1] >> ((~t & 1) << 2)) & 15];
     }
 }
+// 2-bit bases -> BAM nibbles (16 slots per thread), exceptions (non-ACGT codes) patched in, padding slots of every read zeroed
+__global__ void __launch_bounds__(256) k_expand_seq(const uint8_t *__restrict__ s2, int64_t n_slots, uint8_t *__restrict__ seq4)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, s0 = g * 16;
+    if (s0 >= n_slots) return;
+    if (s0 + 16 <= n_slots) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(s2 + (s0 >> 2));
+        uint32_t o[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t b = (w >> (8 * (2 * k + (j >> 1)))) & 0xff;              // source byte: four slots, first in the top bits
+                const uint32_t two = (j & 1) ? (b & 15) : (b >> 4);                     // two slots
+                acc |= (((1u << (two >> 2)) << 4) | (1u << (two & 3))) << (8 * j);
+            }
+            o[k] = acc;
+        }
+        *reinterpret_cast<uint2 *>(seq4 + (s0 >> 1)) = make_uint2(o[0], o[1]);
+    } else {
+        for (int64_t t = s0; t < n_slots; t += 2) {
+            const uint32_t c0 = (s2[t >> 2] >> ((~t & 3) << 1)) & 3, c1 = t + 1 < n_slots ? (s2[(t + 1) >> 2] >> ((~(t + 1) & 3) << 1)) & 3 : 0;
+            seq4[t >> 1] = (uint8_t)(((1u << c0) << 4) | (t + 1 < n_slots ? (1u << c1) : 0u));
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_seq_exceptions(const uint64_t *__restrict__ slot, const uint8_t *__restrict__ code, int64_t n_exc, int64_t n_slots, uint8_t *__restrict__ seq4)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_exc) return;
+    const uint64_t s = slot[k];
+    if (s >= (uint64_t)n_slots) return;
+    // neighbouring exceptions share bytes: atomics on the aligned word (seq4 regions start 16-byte aligned)
+    unsigned int *w = reinterpret_cast<unsigned int *>(seq4 + ((s >> 1) & ~(uint64_t)3));
+    const unsigned sh = (unsigned)(((s >> 1) & 3) * 8 + ((~s & 1) << 2));
+    atomicAnd(w, ~(15u << sh));
+    atomicOr(w, ((unsigned)code[k] & 15u) << sh);
+}
+__global__ void __launch_bounds__(256) k_seq_zero_pad(const int32_t *__restrict__ l_qseq, const uint64_t *__restrict__ base_off, int64_t n, uint8_t *__restrict__ seq4)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t b = base_off[i], e = b + pad_slots(l_qseq[i]);
+    uint64_t s = b + (uint64_t)max(l_qseq[i], 0);
+    if (s < e && (s & 1)) { seq4[s >> 1] &= 0xf0; s++; }                               // this read owns every slot of [b, e)
+    for (; s < e; s += 2) seq4[s >> 1] = 0;
+}
 // sparse first-SA-entry fields -> dense per-read arrays (already preset to "none")
 struct SaSparse { const int32_t *idx, *pos, *sadj, *eadj, *indel; const int16_t *mapq; const uint8_t *strand, *same; };
 __global__ void __launch_bounds__(256) k_scatter_sa(SaSparse S, int64_t n_sa, int64_t n, int32_t *pos, int32_t *sadj, int32_t *eadj, int32_t *indel, uint8_t *strand, int16_t *mapq, uint8_t *same)
@@ -1154,7 +1202,7 @@ struct DevBuf {
 
 enum { B_POS, B_MPOS, B_TLEN, B_MTID, B_LQSEQ, B_FLAG, B_NCIGAR, B_MAPQ, B_QLEN, B_HASH, B_CIGOFF, B_BASEOFF, B_CIGAR, B_SEQ4, B_QUAL,
        B_SAPOS, B_SASADJ, B_SAEADJ, B_SAINDEL, B_SASTRAND, B_SAMAPQ, B_SASAME, B_COUNT,
-       B_QUAL4 = B_COUNT, B_SATMP, B_OFFTMP, B_ALL };      // the last three: staging of the transport-compact forms
+       B_QUAL4 = B_COUNT, B_SATMP, B_OFFTMP, B_SEQ2, B_ALL };      // the last four: staging of the transport-compact forms
 
 struct CnvState;
 static void cnv_state_free(CnvState *c);
@@ -1306,7 +1354,10 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
     if (b->pos[0] < h->last_pos) return fail("gromgpu_push_reads: reads are not in coordinate order");
     if ((h->n_cigar + b->n_cigar_total) > 0xffffffffLL) return fail("gromgpu_push_reads: more than 2^32 CIGAR operations on one chromosome");
     const int lay = b->layout_flags;
-    const bool lay_off = lay & GROM_LAYOUT_CANONICAL_OFFSETS, lay_q4 = (lay & GROM_LAYOUT_QUAL4) && b->qual4, lay_sa = (lay & GROM_LAYOUT_SPARSE_SA) != 0;
+    const bool lay_off = lay & GROM_LAYOUT_CANONICAL_OFFSETS, lay_q4 = (lay & GROM_LAYOUT_QUAL4) && b->qual4, lay_sa = (lay & GROM_LAYOUT_SPARSE_SA) != 0,
+               lay_s2 = (lay & GROM_LAYOUT_SEQ2) && b->seq2;
+    if (!lay_s2 && !b->seq4) return fail("gromgpu_push_reads: bases missing");
+    if (lay_s2 && (b->n_seq_exc < 0 || (b->n_seq_exc && (!b->seq_exc_slot || !b->seq_exc_code)))) return fail("gromgpu_push_reads: bad base exception list");
     if (!lay_sa && !b->sa_pos) return fail("gromgpu_push_reads: SA arrays missing");
     if (!lay_off && (!b->cigar_off || !b->base_off)) return fail("gromgpu_push_reads: offset arrays missing (and GROM_LAYOUT_CANONICAL_OFFSETS not set)");
     if (!lay_q4 && !b->qual) return fail("gromgpu_push_reads: qualities missing");
@@ -1317,7 +1368,7 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
         { B_MTID, b->mtid, 4, n, h->n_reads }, { B_LQSEQ, b->l_qseq, 4, n, h->n_reads }, { B_FLAG, b->flag, 2, n, h->n_reads },
         { B_NCIGAR, b->n_cigar, 2, n, h->n_reads }, { B_MAPQ, b->mapq, 1, n, h->n_reads }, { B_QLEN, b->qname_len, 1, n, h->n_reads },
         { B_HASH, b->qname_hash, 8, n, h->n_reads }, { B_CIGOFF, lay_off ? nullptr : b->cigar_off, 8, n, h->n_reads }, { B_BASEOFF, lay_off ? nullptr : b->base_off, 8, n, h->n_reads },
-        { B_CIGAR, b->cigar, 4, b->n_cigar_total, h->n_cigar }, { B_SEQ4, b->seq4, 1, (b->n_base_slots + 1) / 2, h->n_slots / 2 },
+        { B_CIGAR, b->cigar, 4, b->n_cigar_total, h->n_cigar }, { B_SEQ4, lay_s2 ? nullptr : b->seq4, 1, (b->n_base_slots + 1) / 2, h->n_slots / 2 },
         { B_QUAL, lay_q4 ? nullptr : b->qual, 1, b->n_base_slots, h->n_slots },
         { B_SAPOS, lay_sa ? nullptr : b->sa_pos, 4, n, h->n_reads }, { B_SASADJ, lay_sa ? nullptr : b->sa_start_adj, 4, n, h->n_reads }, { B_SAEADJ, lay_sa ? nullptr : b->sa_end_adj, 4, n, h->n_reads },
         { B_SAINDEL, lay_sa ? nullptr : b->sa_end_adj_indel, 4, n, h->n_reads }, { B_SASTRAND, lay_sa ? nullptr : b->sa_strand, 1, n, h->n_reads }, { B_SAMAPQ, lay_sa ? nullptr : b->sa_mapq, 2, n, h->n_reads },
@@ -1365,6 +1416,23 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
         if (upload(t.p, b->qual4, nb)) return -1;
         QualLut lut; memcpy(lut.v, b->qual_lut, 16);
         k_expand_qual<<<(unsigned)((b->n_base_slots + 16 * 256 - 1) / (16 * 256)), 256, 0, h->stream>>>((const uint8_t *)t.p, b->n_base_slots, lut, (uint8_t *)h->rb[B_QUAL].p + h->n_slots);
+        CK(cudaGetLastError());
+    }
+    if (lay_s2 && b->n_base_slots) {
+        DevBuf &t = h->rb[B_SEQ2];
+        const size_t nb = ((size_t)(b->n_base_slots + 3) / 4 + 15) & ~(size_t)15, ne = (size_t)b->n_seq_exc;
+        if (t.ensure(nb + ne * 9 + 64, h->stream)) return -1;
+        if (upload(t.p, b->seq2, (size_t)(b->n_base_slots + 3) / 4)) return -1;
+        uint8_t *d_seq = (uint8_t *)h->rb[B_SEQ4].p + h->n_slots / 2;
+        k_expand_seq<<<(unsigned)((b->n_base_slots + 16 * 256 - 1) / (16 * 256)), 256, 0, h->stream>>>((const uint8_t *)t.p, b->n_base_slots, d_seq);
+        if (ne) {
+            uint64_t *d_slot = (uint64_t *)((char *)t.p + nb); uint8_t *d_code = (uint8_t *)(d_slot + ne);
+            if (upload(d_slot, b->seq_exc_slot, ne * 8) || upload(d_code, b->seq_exc_code, ne)) return -1;
+            k_seq_exceptions<<<(unsigned)((ne + 255) / 256), 256, 0, h->stream>>>(d_slot, d_code, (int64_t)ne, b->n_base_slots, d_seq);
+        }
+        // offsets of this push relative to its own first slot: the canonical ones minus slot_base (already added above)
+        k_seq_zero_pad<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((const int32_t *)h->rb[B_LQSEQ].p + h->n_reads, (const uint64_t *)h->rb[B_BASEOFF].p + h->n_reads, n,
+                                                                            (uint8_t *)h->rb[B_SEQ4].p);
         CK(cudaGetLastError());
     }
     if (lay_sa) {

@@ -175,6 +175,7 @@ struct grom_batch {
     uint64_t *qname_hash, *cigar_off, *base_off, *qname_off;
     uint32_t *cigar; uint8_t *seq4, *qual; char *qname_pool;
     /* transport-compact forms (grom_reads.h GROM_LAYOUT_*), built once the canonical arrays are filled */
+    uint8_t *seq2, *seq_exc_code; uint64_t *seq_exc_slot;
     uint8_t *qual4; int32_t *sa_index, *sas_pos, *sas_start_adj, *sas_end_adj, *sas_end_adj_indel; int16_t *sas_mapq; uint8_t *sas_strand, *sas_same_chr;
 };
 
@@ -188,6 +189,7 @@ void gromhost_batch_free(grom_batch *t)
     free(t->sa_mapq); free(t->mapq); free(t->qname_len); free(t->sa_strand); free(t->sa_same_chr);
     free(t->qname_hash); free(t->cigar_off); free(t->base_off); free(t->qname_off); free(t->cigar);
     free(t->seq4); free(t->qual); free(t->qname_pool);
+    free(t->seq2); free(t->seq_exc_code); free(t->seq_exc_slot);
     free(t->qual4); free(t->sa_index); free(t->sas_pos); free(t->sas_start_adj); free(t->sas_end_adj); free(t->sas_end_adj_indel);
     free(t->sas_mapq); free(t->sas_strand); free(t->sas_same_chr); free(t);
 }
@@ -217,6 +219,46 @@ static void batch_compact(grom_batch *t, int n_threads)
             for (int64_t s = 0; s < ns; s += 2) t->qual4[s >> 1] = (uint8_t)((inv[t->qual[s]] << 4) | inv[t->qual[s + 1]]);
             v->qual4 = t->qual4; flags |= GROM_LAYOUT_QUAL4;
         } else memset(v->qual_lut, 0, 16);
+    }
+    /* bases: 2 bits per slot, everything that is not A/C/G/T listed with its BAM code (two passes: count per read, then fill) */
+    if (ns > 0 && (ns & 3) == 0) {
+        int64_t *exc_at = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
+        t->seq2 = (uint8_t *)calloc((size_t)(ns / 4 + 16), 1);
+        if (exc_at && t->seq2) {
+            #pragma omp parallel for schedule(static) num_threads(n_threads)
+            for (int64_t i = 0; i < n; i++) {
+                const uint64_t b0 = t->base_off[i]; const int lq = t->l_qseq[i]; int64_t c = 0;
+                for (int k = 0; k < lq; k++) {
+                    const uint64_t sl = b0 + (uint64_t)k;
+                    const int code = (t->seq4[sl >> 1] >> ((~sl & 1) << 2)) & 15;
+                    const int two = code == 1 ? 0 : code == 2 ? 1 : code == 4 ? 2 : code == 8 ? 3 : -1;
+                    if (two < 0) c++;
+                    else if (two) t->seq2[sl >> 2] |= (uint8_t)(two << ((~sl & 3) << 1));        /* a read's slots start on a 32-slot boundary: bytes are not shared */
+                }
+                exc_at[i + 1] = c;
+            }
+            exc_at[0] = 0;
+            for (int64_t i = 0; i < n; i++) exc_at[i + 1] += exc_at[i];
+            const int64_t ne = exc_at[n];
+            if (ne <= ns / 16) {
+                t->seq_exc_slot = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(ne + 1)); t->seq_exc_code = (uint8_t *)malloc((size_t)(ne + 1));
+                if (t->seq_exc_slot && t->seq_exc_code) {
+                    #pragma omp parallel for schedule(static) num_threads(n_threads)
+                    for (int64_t i = 0; i < n; i++) {
+                        if (exc_at[i + 1] == exc_at[i]) continue;
+                        const uint64_t b0 = t->base_off[i]; const int lq = t->l_qseq[i]; int64_t w = exc_at[i];
+                        for (int k = 0; k < lq; k++) {
+                            const uint64_t sl = b0 + (uint64_t)k;
+                            const int code = (t->seq4[sl >> 1] >> ((~sl & 1) << 2)) & 15;
+                            if (code != 1 && code != 2 && code != 4 && code != 8) { t->seq_exc_slot[w] = sl; t->seq_exc_code[w] = (uint8_t)code; w++; }
+                        }
+                    }
+                    v->seq2 = t->seq2; v->n_seq_exc = ne; v->seq_exc_slot = t->seq_exc_slot; v->seq_exc_code = t->seq_exc_code;
+                    flags |= GROM_LAYOUT_SEQ2;
+                }
+            }
+        }
+        free(exc_at);
     }
     int64_t m = 0;
 #define SA_SET(i) (t->sa_pos[i] != -1 || t->sa_mapq[i] != -1 || t->sa_strand[i] || t->sa_same_chr[i] || t->sa_start_adj[i] || t->sa_end_adj[i] || t->sa_end_adj_indel[i])

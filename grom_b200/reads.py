@@ -40,10 +40,11 @@ class CReadBatch(C.Structure):
         ("qual4", C.c_void_p), ("qual_lut", C.c_uint8 * 16), ("n_sa", C.c_int64), ("sa_index", C.c_void_p),
         ("sas_pos", C.c_void_p), ("sas_start_adj", C.c_void_p), ("sas_end_adj", C.c_void_p), ("sas_end_adj_indel", C.c_void_p),
         ("sas_mapq", C.c_void_p), ("sas_strand", C.c_void_p), ("sas_same_chr", C.c_void_p),
+        ("seq2", C.c_void_p), ("n_seq_exc", C.c_int64), ("seq_exc_slot", C.c_void_p), ("seq_exc_code", C.c_void_p),
     ]
 
 
-LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SPARSE_SA = 1, 2, 4
+LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SPARSE_SA, LAYOUT_SEQ2 = 1, 2, 4, 8
 SA_FIELDS = ["sa_pos", "sa_start_adj", "sa_end_adj", "sa_end_adj_indel", "sa_strand", "sa_mapq", "sa_same_chr"]
 SA_NONE = {"sa_pos": -1, "sa_mapq": -1}         # what a read without SA / XP entry carries (everything else 0)
 
@@ -111,6 +112,9 @@ class ReadBatch:
     qual_lut: Optional[np.ndarray] = None       # uint8 [16]
     sa_index: Optional[np.ndarray] = None       # int32, reads that have an SA / XP entry
     sa_sparse: Optional[dict] = None            # SA_FIELDS -> arrays of len(sa_index)
+    seq2: Optional[np.ndarray] = None           # uint8, four base slots per byte (A C G T = 0..3), first slot in the top bits
+    seq_exc_slot: Optional[np.ndarray] = None   # uint64 base slots holding something other than A/C/G/T ...
+    seq_exc_code: Optional[np.ndarray] = None   # uint8  ... and its BAM 4-bit code
     _keep: list = field(default_factory=list, repr=False)
 
     @property
@@ -152,6 +156,11 @@ class ReadBatch:
             c.qual4 = self.qual4.ctypes.data
             for k in range(16):
                 c.qual_lut[k] = int(self.qual_lut[k])
+        if self.layout_flags & LAYOUT_SEQ2:
+            c.seq2 = self.seq2.ctypes.data
+            c.n_seq_exc = int(self.seq_exc_slot.shape[0])
+            c.seq_exc_slot = self.seq_exc_slot.ctypes.data
+            c.seq_exc_code = self.seq_exc_code.ctypes.data
         if self.layout_flags & LAYOUT_SPARSE_SA:
             c.n_sa = int(self.sa_index.shape[0])
             c.sa_index = self.sa_index.ctypes.data
@@ -209,6 +218,23 @@ class ReadBatch:
             self.qual4 = np.ascontiguousarray((code[0::2] << 4) | code[1::2])
             self.qual_lut = lut
             flags |= LAYOUT_QUAL4
+        if (flags & LAYOUT_CANONICAL_OFFSETS) and self.qual.size and self.qual.size % 4 == 0:
+            ns = self.qual.size
+            slot = np.arange(ns, dtype=np.int64)
+            code = (self.seq4[slot >> 1] >> ((~slot & 1) << 2)) & 15
+            lq = self.l_qseq.astype(np.int64)
+            owned = np.zeros(ns + 1, dtype=np.int32)                    # slots below l_qseq of their read (the rest is padding)
+            np.add.at(owned, self.base_off.astype(np.int64), 1); np.add.at(owned, self.base_off.astype(np.int64) + lq, -1)
+            owned = np.cumsum(owned[:-1]) > 0
+            two_of = np.full(16, 255, dtype=np.uint8); two_of[[1, 2, 4, 8]] = [0, 1, 2, 3]
+            two = two_of[code]
+            exc = owned & (two == 255)
+            if int(exc.sum()) <= ns // 16:
+                two = np.where(owned & (two != 255), two, 0).astype(np.uint8)
+                self.seq2 = np.ascontiguousarray((two[0::4] << 6) | (two[1::4] << 4) | (two[2::4] << 2) | two[3::4])
+                self.seq_exc_slot = np.flatnonzero(exc).astype(np.uint64)
+                self.seq_exc_code = np.ascontiguousarray(code[exc].astype(np.uint8))
+                flags |= LAYOUT_SEQ2
         has = np.zeros(self.n_reads, dtype=bool)
         for k in SA_FIELDS:
             has |= getattr(self, k) != SA_NONE.get(k, 0)
@@ -226,11 +252,15 @@ class ReadBatch:
             skip |= {"cigar_off", "base_off"}
         if f & LAYOUT_QUAL4:
             skip.add("qual")
+        if f & LAYOUT_SEQ2:
+            skip.add("seq4")
         if f & LAYOUT_SPARSE_SA:
             skip |= set(SA_FIELDS)
         n = sum(getattr(self, k).nbytes for k in _DTYPES if k not in skip)
         if f & LAYOUT_QUAL4:
             n += self.qual4.nbytes
+        if f & LAYOUT_SEQ2:
+            n += self.seq2.nbytes + self.seq_exc_slot.nbytes + self.seq_exc_code.nbytes
         if f & LAYOUT_SPARSE_SA:
             n += self.sa_index.nbytes + sum(v.nbytes for v in self.sa_sparse.values())
         return int(n)
@@ -292,6 +322,10 @@ def batch_from_c(view: CReadBatch, keep_names: bool) -> ReadBatch:
     if view.layout_flags & LAYOUT_QUAL4:
         b.qual4 = arr(view.qual4, np.uint8, view.n_base_slots // 2)
         b.qual_lut = np.array(list(view.qual_lut), dtype=np.uint8)
+    if view.layout_flags & LAYOUT_SEQ2:
+        b.seq2 = arr(view.seq2, np.uint8, view.n_base_slots // 4)
+        b.seq_exc_slot = arr(view.seq_exc_slot, np.uint64, view.n_seq_exc)
+        b.seq_exc_code = arr(view.seq_exc_code, np.uint8, view.n_seq_exc)
     if view.layout_flags & LAYOUT_SPARSE_SA:
         b.sa_index = arr(view.sa_index, np.int32, view.n_sa)
         b.sa_sparse = {k: arr(getattr(view, "sas_" + k[3:]), _DTYPES[k], view.n_sa) for k in SA_FIELDS}

@@ -73,7 +73,7 @@ typedef struct grom_read_batch {
     const char     *qname_pool;
     /* ---- transport-compact forms (read only when the matching layout_flags bit is set).  They carry the same information
      * in fewer bytes across PCIe; the CUDA library rebuilds the canonical device arrays from them (bit-identical), so
-     * nothing downstream changes.  319 -> 203 bytes per 150 bp read with all three. */
+     * nothing downstream changes.  319 -> 163 bytes per 150 bp read with all four. */
     const uint8_t  *qual4;      /* GROM_LAYOUT_QUAL4: per base slot a 4-bit index into qual_lut, nibble order of seq4
                                    (usable when the batch holds <= 16 distinct quality values); qual may then be NULL */
     uint8_t         qual_lut[16];
@@ -82,6 +82,12 @@ typedef struct grom_read_batch {
     const int32_t  *sas_pos, *sas_start_adj, *sas_end_adj, *sas_end_adj_indel;   /* [n_sa]; the dense sa_* arrays may then be NULL */
     const int16_t  *sas_mapq;
     const uint8_t  *sas_strand, *sas_same_chr;
+    const uint8_t  *seq2;       /* GROM_LAYOUT_SEQ2: 2 bits per base slot (A C G T = 0 1 2 3 = log2 of the BAM code), slot s in byte s>>2 at
+                                   bits ((~s&3)<<1); every base that is not A/C/G/T is listed as an exception with its 4-bit BAM code.
+                                   Padding slots (beyond l_qseq) become code 0 on the device like in the canonical array */
+    int64_t         n_seq_exc;
+    const uint64_t *seq_exc_slot;   /* [n_seq_exc] base slot (same index space as base_off) */
+    const uint8_t  *seq_exc_code;   /* [n_seq_exc] BAM 4-bit code */
 } grom_read_batch;
 
 /* GROM_LAYOUT_CANONICAL_OFFSETS: cigar_off[i] = sum of n_cigar[0..i) and base_off[i] = sum of l_qseq[0..i) each rounded up to
@@ -89,6 +95,7 @@ typedef struct grom_read_batch {
 #define GROM_LAYOUT_CANONICAL_OFFSETS 1
 #define GROM_LAYOUT_QUAL4             2
 #define GROM_LAYOUT_SPARSE_SA         4
+#define GROM_LAYOUT_SEQ2              8
 
 static inline uint64_t grom_qname_hash(const char *s, int len)
 {
