@@ -1283,12 +1283,36 @@ extern "C" int gromgpu_set_stream(void *s)
     return 0;
 }
 
-extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, int64_t len)
+extern "C" int gromgpu_stream_create(void **out)
+{
+    if (!g_inited) return fail("gromgpu_stream_create: call gromgpu_init first");
+    cudaStream_t s = nullptr;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = (void *)s;
+    return 0;
+}
+extern "C" void gromgpu_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+extern "C" int64_t gromgpu_device_free_bytes(void)
+{
+    size_t fr = 0, tot = 0;
+    return cudaMemGetInfo(&fr, &tot) == cudaSuccess ? (int64_t)fr : -1;
+}
+extern "C" int64_t gromgpu_chr_bytes_estimate(int64_t len, int64_t n_reads, int64_t n_base_slots)
+{
+    const int64_t Ppad = (len + 1023) & ~(int64_t)1023;
+    // per position: GA_COUNT count arrays, 36 int + 10 double of cluster state, FASTA, CNV records / depth / scratch (~60 B);
+    // per read: the canonical arrays (~80 B + bases), prepared records, state; pools and candidate buffers ~4 GB
+    return Ppad * ((int64_t)sizeof(int32_t) * (GA_COUNT + 36) + 80 + 1 + 60) + n_reads * 160 + n_base_slots * 2 + ((int64_t)4 << 30);
+}
+extern "C" int gromgpu_chr_begin_on(gromgpu_chr **out, int tid, const char *fasta, int64_t len, void *stream);
+extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, int64_t len) { return gromgpu_chr_begin_on(out, tid, fasta, len, (void *)g_stream); }
+
+extern "C" int gromgpu_chr_begin_on(gromgpu_chr **out, int tid, const char *fasta, int64_t len, void *stream)
 {
     if (!g_inited) return fail("gromgpu_chr_begin: call gromgpu_init first");
     if (len <= 0 || len > 0x7fffffff) return fail("gromgpu_chr_begin: chromosome length %lld unsupported", (long long)len);
     gromgpu_chr *h = new gromgpu_chr();
-    h->tid = tid; h->P = len; h->Ppad = (len + 1023) & ~(int64_t)1023; h->stream = g_stream;
+    h->tid = tid; h->P = len; h->Ppad = (len + 1023) & ~(int64_t)1023; h->stream = stream ? (cudaStream_t)stream : g_stream;
     memset(&h->stats, 0, sizeof(h->stats)); memset(&h->res, 0, sizeof(h->res));
     for (int i = 0; i < 12; i++) h->ev[i] = nullptr;
     *out = h;
@@ -1327,6 +1351,13 @@ extern "C" int gromgpu_chr_reset(gromgpu_chr *h, const char *fasta)
     if (fasta) CK(cudaMemcpyAsync(h->d_fasta, fasta, (size_t)h->P, cudaMemcpyHostToDevice, h->stream));
     for (int i = 0; i < B_COUNT; i++) h->rb[i].size = 0;
     h->n_reads = h->n_cigar = h->n_slots = 0; h->last_pos = -1; h->last_lseq = 0; h->n_leading = 0; h->ran = false;
+    return 0;
+}
+
+extern "C" int gromgpu_chr_sync(gromgpu_chr *h)
+{
+    if (!h) return fail("gromgpu_chr_sync: null handle");
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

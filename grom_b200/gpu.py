@@ -63,6 +63,14 @@ def lib() -> C.CDLL:
         L.gromgpu_cnv_fetch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_int64]
         L.gromgpu_chr_free.argtypes = [C.c_void_p]
         L.gromgpu_chr_free.restype = None
+        L.gromgpu_chr_sync.argtypes = [C.c_void_p]
+        L.gromgpu_stream_create.argtypes = [C.POINTER(C.c_void_p)]
+        L.gromgpu_stream_destroy.argtypes = [C.c_void_p]
+        L.gromgpu_stream_destroy.restype = None
+        L.gromgpu_chr_begin_on.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+        L.gromgpu_chr_bytes_estimate.argtypes = [C.c_int64, C.c_int64, C.c_int64]
+        L.gromgpu_chr_bytes_estimate.restype = C.c_int64
+        L.gromgpu_device_free_bytes.restype = C.c_int64
         L.gromgpu_shutdown.restype = None
         _LIB = L
     return _LIB
@@ -141,12 +149,34 @@ class ChrResult:
     sv_ev: np.ndarray = None   # SV_EVENT_DTYPE structural-variant gate events, scan order
 
 
+def stream_create() -> int:
+    s = C.c_void_p()
+    _ck(lib().gromgpu_stream_create(C.byref(s)))
+    return s.value
+
+
+def stream_destroy(s: Optional[int]):
+    if s:
+        lib().gromgpu_stream_destroy(C.c_void_p(s))
+
+
+def chr_bytes_estimate(length: int, n_reads: int, n_base_slots: int) -> int:
+    return int(lib().gromgpu_chr_bytes_estimate(length, n_reads, n_base_slots))
+
+
+def device_free_bytes() -> int:
+    return int(lib().gromgpu_device_free_bytes())
+
+
 class Chromosome:
-    def __init__(self, tid: int, fasta: np.ndarray):
+    def __init__(self, tid: int, fasta: np.ndarray, stream: Optional[int] = None):
         fa = np.ascontiguousarray(fasta, dtype=np.uint8)
         self.length = int(fa.shape[0])
         self._h = C.c_void_p()
-        _ck(lib().gromgpu_chr_begin(C.byref(self._h), tid, fa.ctypes.data, self.length))
+        if stream:
+            _ck(lib().gromgpu_chr_begin_on(C.byref(self._h), tid, fa.ctypes.data, self.length, C.c_void_p(stream)))
+        else:
+            _ck(lib().gromgpu_chr_begin(C.byref(self._h), tid, fa.ctypes.data, self.length))
 
     def push_reads(self, batch: ReadBatch):
         cb = batch.as_c()
@@ -162,6 +192,9 @@ class Chromosome:
             assert fasta.dtype == np.uint8 and fasta.shape[0] == self.length and fasta.flags.c_contiguous
             ptr = fasta.ctypes.data
         _ck(lib().gromgpu_chr_reset(self._h, ptr))
+
+    def sync(self):
+        _ck(lib().gromgpu_chr_sync(self._h))
 
     def run(self):
         _ck(lib().gromgpu_chr_run(self._h))

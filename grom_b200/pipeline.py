@@ -10,6 +10,7 @@ No CPU fallback: `gpu.init` fails without a CUDA device.
 from __future__ import annotations
 
 import gzip
+import threading
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -37,10 +38,32 @@ def read_fasta(path: str) -> Dict[str, np.ndarray]:
     return out
 
 
+class _InFlight:
+    """Admission control for the contigs in flight on one GPU: a contig starts when a lane is free and the device memory its handle
+    will hold (gromgpu_chr_bytes_estimate) fits beside the ones already running; a contig that fits nowhere runs alone."""
+
+    def __init__(self, budget: int):
+        self.budget, self.used, self.running = budget, 0, 0
+        self.cv = threading.Condition()
+
+    def acquire(self, need: int):
+        with self.cv:
+            while self.running and self.used + need > self.budget:
+                self.cv.wait()
+            self.used += need; self.running += 1
+
+    def release(self, need: int):
+        with self.cv:
+            self.used -= need; self.running -= 1
+            self.cv.notify_all()
+
+
 def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = None, device: int = 0, rank: int = 0, ranks: int = 1,
-                  table_dir: Optional[str] = None, ctx_out: Optional[Dict[int, np.ndarray]] = None) -> Tuple[Dict[int, str], Params]:
+                  table_dir: Optional[str] = None, ctx_out: Optional[Dict[int, np.ndarray]] = None, lanes: int = 3) -> Tuple[Dict[int, str], Params]:
     """Returns ({tid: record text of that contig}, the parameters incl. the library statistics measured from the BAM).  If `ctx_out` is
-    given it receives {tid: translocation records of that contig} for `ctx_vcf_text` (the pairing needs the records of all contigs)."""
+    given it receives {tid: translocation records of that contig} for `ctx_vcf_text` (the pairing needs the records of all contigs).
+    Up to `lanes` contigs are in flight on the GPU (one host thread and one stream each; uploads take turns on the PCIe link), so the
+    upload of one contig overlaps the kernels and the host stages of the others; results do not depend on `lanes`."""
     prm = params if params is not None else Params.default()
     fasta = {k.lower(): v for k, v in read_fasta(fasta_path).items()}
     with hostlib.Bam(bam_path) as bam:
@@ -54,18 +77,53 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
         todo = [t for t, n in enumerate(bam.names) if n.lower() in fasta and not skip_contig(n, prm.gender)]
         mine = set(todo[i] for i in assign_contigs([bam.lens[t] for t in todo], ranks)[rank])
         text: Dict[int, str] = {}
-        for t in todo:
-            if t not in mine:
-                continue
+        work = [t for t in todo if t in mine]
+        work.sort(key=lambda t: -bam.lens[t])                              # largest first, like the reference's -P scheduler (src/GROM.c:22318-22336)
+        n_lanes = max(1, min(lanes, len(work)))
+        inflight = _InFlight(int(0.9 * gpu.device_free_bytes()))
+        bus, pick, errors = threading.Lock(), threading.Lock(), []
+
+        def one_contig(t: int, stream: Optional[int]):
             name = bam.names[t].lower()
             chars = fasta[name]
-            with gpu.Chromosome(t, chars) as ch:
-                ch.push_reads(batches[t])
-                res = ch.finish()
-                cnv = ch.cnv(params=prm)
+            need = gpu.chr_bytes_estimate(len(chars), batches[t].n_reads, batches[t].n_base_slots)
+            inflight.acquire(need)
+            try:
+                with gpu.Chromosome(t, chars, stream=stream) as ch:
+                    with bus:
+                        ch.push_reads(batches[t]); ch.sync()
+                    res = ch.finish()
+                    cnv = ch.cnv(params=prm)
+            finally:
+                inflight.release(need)
             text[t] = hostlib.vcf_contig(prm, name, chars, res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, cnv.calls)
             if ctx_out is not None:
                 ctx_out[t] = hostlib.ctx_contig(prm, t, res.sv_ev)
+
+        def lane():
+            stream = gpu.stream_create() if n_lanes > 1 else None
+            try:
+                while not errors:
+                    with pick:
+                        if not work:
+                            return
+                        t = work.pop(0)
+                    one_contig(t, stream)
+            except BaseException as e:                                      # surfaced by the caller's thread below
+                errors.append(e)
+            finally:
+                gpu.stream_destroy(stream)
+
+        if n_lanes <= 1:
+            lane()
+        else:
+            th = [threading.Thread(target=lane) for _ in range(n_lanes)]
+            for x in th:
+                x.start()
+            for x in th:
+                x.join()
+        if errors:
+            raise errors[0]
     return text, prm
 
 

@@ -82,6 +82,20 @@ int gromgpu_set_stream(void *cuda_stream);
  * Replaces the per-call allocation + zeroing of src/GROM.c:1884-1908, 2931-5719. */
 int gromgpu_chr_begin(gromgpu_chr **h, int tid, const char *fasta, int64_t len);
 
+/* Several chromosomes in flight (one host thread and one stream each): the upload of one overlaps the kernels and the host
+ * stages of the others -- the shape of the per-genome driver, where the reference forks one process per chromosome (-P,
+ * src/GROM.c:22340-22398).  gromgpu_chr_begin_on binds the handle to the given stream (cudaStream_t as void*, e.g. one made
+ * by gromgpu_stream_create); calls on different handles may then be made concurrently from different threads. */
+int gromgpu_stream_create(void **cuda_stream);
+void gromgpu_stream_destroy(void *cuda_stream);
+int gromgpu_chr_begin_on(gromgpu_chr **h, int tid, const char *fasta, int64_t len, void *cuda_stream);
+/* Device memory a handle for a chromosome of this length with this many reads / base slots will hold (admission control
+ * for the in-flight set), and what is free on the device right now. */
+/* Block until everything queued on the handle's stream (uploads of gromgpu_push_reads included) has completed. */
+int gromgpu_chr_sync(gromgpu_chr *h);
+int64_t gromgpu_chr_bytes_estimate(int64_t len, int64_t n_reads, int64_t n_base_slots);
+int64_t gromgpu_device_free_bytes(void);
+
 /* Forget the pushed reads (device buffers are kept) and, if fasta != NULL, upload new characters of the
  * same length: lets one handle be reused for the next chromosome-sized unit without reallocating. */
 int gromgpu_chr_reset(gromgpu_chr *h, const char *fasta);

@@ -26,6 +26,9 @@ def test_pipeline_reproduces_reference_vcf(tmp_path, tag, rmdup):
     out = tmp_path / "out.vcf"
     pipeline.write_vcf(str(out), text)
     assert [l for l in open(out) if not l.startswith("#")] == mine
+    # one contig at a time == three contigs in flight (threads / streams; the golden BAM has three contigs)
+    serial, _ = pipeline.call_variants(os.path.join(GOLDEN, "g1.bam"), os.path.join(GOLDEN, "g1.fa.gz"), Params.default(rmdup=rmdup), lanes=1)
+    assert serial == text and len(text) == 3
 
 
 def test_pipeline_translocations(tmp_path):
