@@ -296,14 +296,15 @@ __device__ __forceinline__ void pile_generic(PileAcc &a, PileRare &x, uint64_t h
 // classify one base (code, quality) of one read at this thread's position and fold it into the accumulators;
 // qi = query offset, lseq = read length seen by the position-in-read rule
 __device__ __forceinline__ void pile_apply(PileAcc &a, PileRare &x, int code, int qv, uint64_t hash, uint32_t misc, int qi, int lseq, int rc4,
-                                           bool ref_acgt, bool mq_ok, int bqmin, int min_snv)
+                                           bool ref_acgt, bool mq_ok, int bqmin, int min_snv, int p_rel)
 {
     const bool hi = mq_ok && qv >= bqmin;
     if (ref_acgt && code == rc4) {
         const int mq = misc & 0xff;
         const bool fwd = !(misc & PR_REV);
         a.bq_all += qv; a.mq_all += mq; a.m_all += 1;
-        if (hi) { a.bq += qv; a.mq += mq; a.m_hi += 1; a.m_pir += fwd ? qi : lseq - qi; a.m_fs += fwd ? 1 : 0; }
+        // m_pir holds the sum of (position in read) -+ p_rel, p_rel = position - tile start; the epilogue adds p_rel * (forward - reverse)
+        if (hi) { a.bq += qv; a.mq += mq; a.m_hi += 1; a.m_pir += fwd ? qi - p_rel : lseq - qi + p_rel; a.m_fs += fwd ? 1 : 0; }
     } else {
         pile_generic(a, x, hash, misc, code, qv, qi, lseq, rc4, hi, min_snv);
     }
@@ -348,8 +349,14 @@ __device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 
 
 // Per staged read the producer warp leaves three 16-byte records of plain ints in shared memory so that the
 // position threads need no bit unpacking (all values are warp-uniform broadcasts):
-struct __align__(16) StageA { int pos; uint32_t lq_fast; uint32_t qa; uint32_t sa; };   // lq_fast = 0 unless single-M read fully inside the contig
-struct __align__(16) StageB { int mq; int bq_eff; int fwd01; int rdhi01; };             // bq_eff = -b if mapq >= -q else 256 (never reached)
+struct __align__(16) StageA { int pos; uint32_t lq_fast; uint32_t qa; int bq_eff; };     // lq_fast = 0 unless single-M read fully inside the contig; bq_eff = -b if mapq >= -q else 256 (never reached)
+// Per-read constants of the fast path, packed so that one add updates several counters (fields are unpacked into the 32-bit
+// accumulators once per stage: <= CHUNK = 64 reads, so a count stays below 2^8 and a MAPQ sum below 2^16):
+//   u_cov  = 1 | (mapq >= rd_min_mapq) << 8 | mapq << 16     added where the read covers the position           (CNV depth)
+//   u_all  = 1 | mapq << 16                                  added where the base equals the A/C/G/T reference  (all qualities)
+//   u_hi   = 1 | forward << 8 | mapq << 16                   ... and passes -q / -b
+//   v_pir  = forward ? -(pos - tile_lo) : l_qseq + (pos - tile_lo): position in read = +-(p - tile_lo) + v_pir (src/GROM.c:6853-6864)
+struct __align__(16) StageB { uint32_t u_cov, u_all, u_hi; int v_pir; };
 struct __align__(16) StageD { int pir_c; int pir_s; int lq; uint32_t flags; };          // position-in-read = off * pir_s + pir_c (src/GROM.c:6853-6864)
 struct __align__(16) StageC { uint64_t hash; uint32_t cig_off, n_cigar; };
 struct __align__(8)  StageE { uint32_t base16; int ext_end; };
@@ -408,46 +415,68 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
         // plain ints + bulk copies (TMA) of their bases
         const int max_span = *max_span_p;
         int c = 0;
+        auto load_pair = [&](int64_t first, PrepRec &r0, PrepRec &r1) {
+            const int64_t i0 = first + 2 * lane, i1 = i0 + 1;
+            r0.pos = r1.pos = INT32_MAX; r0.misc = r1.misc = 0; r0.ext_end = r1.ext_end = INT32_MIN; r0.base16 = r1.base16 = 0;
+            r0.hash = r1.hash = 0; r0.cig_off = r1.cig_off = r0.n_cigar = r1.n_cigar = 0;
+            if (i0 < R.n) r0 = prep[i0];
+            if (i1 < R.n) r1 = prep[i1];
+        };
+        int64_t next = tile_begin < tile_end ? tile_first[tile_begin] : 0;
+        PrepRec r0, r1;
+        load_pair(next, r0, r1);
         for (int64_t tile = tile_begin; tile < tile_end; tile++) {
             const int64_t tile_lo = tile * TILE, tile_hi = min(tile_lo + TILE, P);
-            int64_t next = tile_first[tile];
+            const int64_t next_tile_first = tile + 1 < tile_end ? tile_first[tile + 1] : 0;     // in flight while this tile's chunks are staged
             for (;; c++) {
                 const int buf = c % NSTAGE;
-                if (c >= NSTAGE) mbar_wait(smem_u32(&S.empty[buf]), (uint32_t)((c / NSTAGE - 1) & 1));
                 const int64_t i0 = next + 2 * lane, i1 = i0 + 1;
                 const bool v0 = i0 < R.n, v1 = i1 < R.n;
-                PrepRec r0, r1;
-                r0.pos = r1.pos = INT32_MAX; r0.misc = r1.misc = 0; r0.ext_end = r1.ext_end = INT32_MIN; r0.base16 = r1.base16 = 0;
-                r0.hash = r1.hash = 0; r0.cig_off = r1.cig_off = r0.n_cigar = r1.n_cigar = 0;
-                if (v0) r0 = prep[i0];
-                if (v1) r1 = prep[i1];
                 const bool use0 = v0 && (r0.misc & PR_APPLIED) && (int64_t)r0.ext_end > tile_lo && (int64_t)r0.pos < tile_hi;
                 const bool use1 = v1 && (r1.misc & PR_APPLIED) && (int64_t)r1.ext_end > tile_lo && (int64_t)r1.pos < tile_hi;
-                uint32_t sz0 = use0 ? (((r0.misc >> 16) + 31u) & ~31u) : 0u, sz1 = use1 ? (((r1.misc >> 16) + 31u) & ~31u) : 0u;
-                const bool big0 = sz0 > QCAP, big1 = sz1 > QCAP;
-                if (big0) sz0 = 0;
-                if (big1) sz1 = 0;
-                uint32_t incl = sz0 + sz1;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-                const uint32_t off0 = incl - sz0 - sz1, off1 = off0 + sz0;
-                const bool fit0 = v0 && off0 + sz0 <= QCAP, fit1 = v1 && off1 + sz1 <= QCAP;
-                const unsigned bf0 = __ballot_sync(0xffffffffu, fit0), bf1 = __ballot_sync(0xffffffffu, fit1);
-                const int count = __popc(bf0) + __popc(bf1);              // reads consumed from the stream
-                const unsigned anypast = __ballot_sync(0xffffffffu, (fit0 && (int64_t)r0.pos >= tile_hi) || (fit1 && (int64_t)r1.pos >= tile_hi));
+                const uint32_t sz0 = use0 ? (((r0.misc >> 16) + 31u) & ~31u) : 0u, sz1 = use1 ? (((r1.misc >> 16) + 31u) & ~31u) : 0u;
+                const bool big0 = sz0 > QCAP, big1 = sz1 > QCAP;               // longer than a stage: the position threads read its bases from global memory
+                const bool want0 = use0 && !big0 && sz0, want1 = use1 && !big1 && sz1;
+                // The bases of consecutive reads lie back to back in the batch, so the stage takes ONE contiguous span per array (two bulk
+                // copies per stage): from the first read that is needed to the last one that still fits, whatever lies between included.
+                // (Offsets that do not ascend end the chunk early; the read then opens the next one.)
+                const unsigned bw0 = __ballot_sync(0xffffffffu, want0), bw1 = __ballot_sync(0xffffffffu, want1);
+                const unsigned firstbits = bw0 | bw1;
+                uint32_t base_first = 0;
+                if (firstbits) {
+                    const int fl = __ffs(firstbits) - 1;
+                    const uint32_t cand = (bw0 >> fl) & 1u ? r0.base16 : r1.base16;
+                    base_first = __shfl_sync(0xffffffffu, cand, fl);
+                }
+                const int64_t rel0 = ((int64_t)r0.base16 - (int64_t)base_first) * 16, rel1 = ((int64_t)r1.base16 - (int64_t)base_first) * 16;
+                const bool fit0 = v0 && (!want0 || (rel0 >= 0 && rel0 + sz0 <= QCAP)), fit1 = v1 && (!want1 || (rel1 >= 0 && rel1 + sz1 <= QCAP));
+                // reads consumed from the stream: the leading run of reads that fit (lane order = read order i0, i1 per lane)
+                const unsigned nf0 = ~__ballot_sync(0xffffffffu, fit0), nf1 = ~__ballot_sync(0xffffffffu, fit1);
+                int count;
+                {
+                    const int l0 = nf0 ? __ffs(nf0) - 1 : 32, l1 = nf1 ? __ffs(nf1) - 1 : 32;       // first lane whose read 0 / read 1 does not fit
+                    count = l0 <= l1 ? 2 * l0 : 2 * l1 + 1;
+                    if (l0 == 32 && l1 == 32) count = 64;
+                }
+                const bool in0 = 2 * lane < count, in1 = 2 * lane + 1 < count;
+                const unsigned anypast = __ballot_sync(0xffffffffu, (in0 && v0 && (int64_t)r0.pos >= tile_hi) || (in1 && v1 && (int64_t)r1.pos >= tile_hi));
                 const bool last = (anypast != 0u) || (next + count >= R.n);
-                const bool st0 = fit0 && use0, st1 = fit1 && use1;         // staged (compacted) reads
+                const bool st0 = in0 && use0, st1 = in1 && use1;          // staged (compacted) reads
                 const unsigned bs0 = __ballot_sync(0xffffffffu, st0), bs1 = __ballot_sync(0xffffffffu, st1);
                 const unsigned lt = (1u << lane) - 1u;
                 const int idx0 = __popc(bs0 & lt) + __popc(bs1 & lt), idx1 = idx0 + (st0 ? 1 : 0);
-                uint32_t bytes = (st0 ? sz0 + (sz0 >> 1) : 0u) + (st1 ? sz1 + (sz1 >> 1) : 0u);
-                bytes = __reduce_add_sync(0xffffffffu, bytes);
+                uint32_t span = 0;
+                if (st0 && want0) span = (uint32_t)rel0 + sz0;
+                if (st1 && want1) span = max(span, (uint32_t)rel1 + sz1);
+                span = __reduce_max_sync(0xffffffffu, span);
+                // the records of the chunk after this one travel while this one is staged
+                const int64_t next_after = last ? next_tile_first : next + count;
+                PrepRec n0, n1;
+                load_pair(next_after, n0, n1);
+                if (c >= NSTAGE) mbar_wait(smem_u32(&S.empty[buf]), (uint32_t)((c / NSTAGE - 1) & 1));
                 const uint32_t bar = smem_u32(&S.full[buf]);
                 const uint32_t qbase = smem_u32(&S.qual[buf][0]), sbase = smem_u32(&S.seq[buf][0]);
                 // per consumer warp: staged reads with pos in (wlo - max_span, whi]
-                if (lane < NWARP) {
-                    // filled below by every lane cooperatively through ballots; placeholder to keep lanes converged
-                }
 #pragma unroll
                 for (int w = 0; w < NWARP; w++) {
                     const int wlo = (int)tile_lo + 32 * w, key = wlo - max_span, whi = wlo + 31;
@@ -459,14 +488,16 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                 for (int h = 0; h < 2; h++) {
                     const PrepRec &r = h ? r1 : r0;
                     const bool st = h ? st1 : st0, big = h ? big1 : big0;
-                    const uint32_t off = h ? off1 : off0;
+                    const uint32_t off = (uint32_t)(h ? rel1 : rel0);
                     const int t = h ? idx1 : idx0;
                     if (st) {
                         const int mq = r.misc & 0xff, lq = (int)(r.misc >> 16);
                         const bool rev = r.misc & PR_REV;
                         const bool fast = (r.misc & PR_SIMPLE) && !big && (int64_t)r.pos + lq < P;
-                        StageA A; A.pos = r.pos; A.lq_fast = fast ? (uint32_t)lq : 0u; A.qa = qbase + off; A.sa = sbase + (off >> 1);
-                        StageB B; B.mq = mq; B.bq_eff = (mq >= q) ? bqmin : 256; B.fwd01 = rev ? 0 : 1; B.rdhi01 = (mq >= rdq) ? 1 : 0;
+                        const int rel = r.pos - (int)tile_lo;
+                        StageA A; A.pos = r.pos; A.lq_fast = fast ? (uint32_t)lq : 0u; A.qa = qbase + off; A.bq_eff = (mq >= q) ? bqmin : 256;
+                        StageB B; B.u_cov = 1u | ((mq >= rdq) ? 0x100u : 0u) | ((uint32_t)mq << 16); B.u_all = 1u | ((uint32_t)mq << 16);
+                        B.u_hi = 1u | (rev ? 0u : 0x100u) | ((uint32_t)mq << 16); B.v_pir = rev ? lq + rel : -rel;
                         StageD D; D.pir_c = rev ? lq : 0; D.pir_s = rev ? -1 : 1; D.lq = lq;
                         D.flags = (fast ? 0u : SF_COMPLEX) | (big ? SF_GLOBAL : 0u) | (rev ? SF_REV : 0u) | ((r.misc & PR_NAMEOK) ? SF_NAMEOK : 0u) | ((mq >= q) ? SF_MQOK : 0u);
                         StageC C; C.hash = r.hash; C.cig_off = r.cig_off; C.n_cigar = r.n_cigar;
@@ -474,18 +505,14 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                         S.a[buf][t] = A; S.b[buf][t] = B; S.d[buf][t] = D; S.c[buf][t] = C; S.e[buf][t] = E;
                     }
                 }
-                if (lane == 0) { S.last[buf] = last ? 1 : 0; mbar_expect_tx(bar, bytes); }
+                if (lane == 0) { S.last[buf] = last ? 1 : 0; mbar_expect_tx(bar, span + (span >> 1)); }
                 else mbar_arrive(bar);
                 __syncwarp();
-                if (st0 && sz0) {
-                    bulk_g2s(qbase + off0, R.qual + ((uint64_t)r0.base16 << 4), sz0, bar);
-                    bulk_g2s(sbase + (off0 >> 1), R.seq4 + ((uint64_t)r0.base16 << 3), sz0 >> 1, bar);
+                if (lane == 0 && span) {
+                    bulk_g2s(qbase, R.qual + ((uint64_t)base_first << 4), span, bar);
+                    bulk_g2s(sbase, R.seq4 + ((uint64_t)base_first << 3), span >> 1, bar);
                 }
-                if (st1 && sz1) {
-                    bulk_g2s(qbase + off1, R.qual + ((uint64_t)r1.base16 << 4), sz1, bar);
-                    bulk_g2s(sbase + (off1 >> 1), R.seq4 + ((uint64_t)r1.base16 << 3), sz1 >> 1, bar);
-                }
-                next += count;
+                next = next_after; r0 = n0; r1 = n1;
                 if (last) { c++; break; }
             }
         }
@@ -517,56 +544,52 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
             mbar_wait(smem_u32(&S.full[buf]), (uint32_t)((c / NSTAGE) & 1));
             const bool last = S.last[buf] != 0;
             const int2 rng = S.rng[buf][wid];
+            const uint32_t kb = smem_u32(&S.seq[buf][0]) - (smem_u32(&S.qual[buf][0]) >> 1);     // nibble byte of quality address x: (x >> 1) + kb
+            uint32_t acc_cov = 0, acc_all = 0, acc_hi = 0;
 #pragma unroll 2
             for (int t = rng.x; t < rng.y; t++) {
                 const StageA A = S.a[buf][t];
                 const StageB B = S.b[buf][t];
-                const StageD D = S.d[buf][t];
                 // fast path for one staged read, hand-written so that every accumulate is a single predicated add
-                int off, qv, byte, nib, slow;
+                int off, qv, nib, slow;
                 asm("{\n"
                     " .reg .pred ph, pm, pmh, ps;\n"
-                    " .reg .b32 aq, as, sh, pv;\n"
-                    " sub.s32 %0, %16, %17;\n"                       // off = ip - pos
-                    " setp.lt.u32 ph, %0, %18;\n"                    // hit = off <u lq_fast
-                    " add.u32 aq, %19, %0;\n"
+                    " .reg .b32 aq, as, sh, by;\n"
+                    " sub.s32 %0, %10, %11;\n"                       // off = ip - pos
+                    " setp.lt.u32 ph, %0, %12;\n"                    // hit = off <u lq_fast
+                    " add.u32 aq, %13, %0;\n"
                     " @ph ld.shared.u8 %1, [aq];\n"                  // quality
-                    " shr.s32 as, %0, 1;\n"
-                    " add.u32 as, as, %20;\n"
-                    " @ph ld.shared.u8 %2, [as];\n"                  // two 4-bit base codes
-                    " not.b32 sh, %0;\n"
+                    " shr.u32 as, aq, 1;\n"
+                    " add.u32 as, as, %15;\n"
+                    " @ph ld.shared.u8 by, [as];\n"                  // two 4-bit base codes
+                    " not.b32 sh, aq;\n"
+                    " and.b32 sh, sh, 1;\n"
                     " shl.b32 sh, sh, 2;\n"
-                    " and.b32 sh, sh, 4;\n"
-                    " shr.u32 %3, %2, sh;\n"
-                    " and.b32 %3, %3, 15;\n"                         // this base's code
-                    " setp.eq.and.s32 pm, %3, %27, ph;\n"            // equals the (A/C/G/T) reference base
-                    " setp.ge.and.s32 pmh, %1, %22, pm;\n"           // ... with mapq >= -q and base quality >= -b
+                    " shr.u32 %2, by, sh;\n"
+                    " and.b32 %2, %2, 15;\n"                         // this base's code
+                    " setp.eq.and.s32 pm, %2, %20, ph;\n"            // equals the (A/C/G/T) reference base
+                    " setp.ge.and.s32 pmh, %1, %14, pm;\n"           // ... with mapq >= -q and base quality >= -b
+                    " @ph add.u32 %4, %4, %16;\n"                    // covered: depth count | high-MAPQ count | MAPQ sum
                     " @pm add.s32 %5, %5, %1;\n"                     // bq_all
-                    " @pm add.s32 %6, %6, %21;\n"                    // mq_all
-                    " @pm add.s32 %7, %7, 1;\n"                      // m_all
-                    " @pmh add.s32 %8, %8, %1;\n"                    // bq
-                    " @pmh add.s32 %9, %9, %21;\n"                   // mq
-                    " @pmh add.s32 %10, %10, 1;\n"                   // m_hi
-                    " mad.lo.s32 pv, %0, %26, %25;\n"                // position in read
-                    " @pmh add.s32 %11, %11, pv;\n"                  // m_pir
-                    " @pmh add.s32 %12, %12, %23;\n"                 // m_fs
-                    " @ph add.s32 %13, %13, 1;\n"                    // rd_cnt
-                    " @ph add.s32 %14, %14, %21;\n"                  // rd_mq
-                    " @ph add.s32 %15, %15, %24;\n"                  // rd_rd
+                    " @pm add.u32 %6, %6, %17;\n"                    // matches | MAPQ sum
+                    " @pmh add.s32 %7, %7, %1;\n"                    // bq
+                    " @pmh add.u32 %8, %8, %18;\n"                   // passing matches | forward | MAPQ sum
+                    " @pmh add.s32 %9, %9, %19;\n"                   // position-in-read constant
                     " not.pred ps, pm;\n"
-                    " and.pred ps, ps, ph;\n"
-                    " selp.s32 %4, 1, 0, ps;\n"                      // covered but not a plain match: generic rule
+                    " and.pred ps, ps, ph;\n"                        // covered but not a plain match: generic rule
+                    " setp.eq.or.u32 ps, %12, 0, ps;\n"              // ... or a read that needs the CIGAR walk
+                    " selp.s32 %3, 1, 0, ps;\n"
                     "}"
-                    : "=r"(off), "=r"(qv), "=r"(byte), "=r"(nib), "=r"(slow),
-                      "+r"(a.bq_all), "+r"(a.mq_all), "+r"(a.m_all), "+r"(a.bq), "+r"(a.mq), "+r"(a.m_hi), "+r"(a.m_pir), "+r"(a.m_fs),
-                      "+r"(rd_cnt), "+r"(a.rd_mq), "+r"(a.rd_rd)
-                    : "r"(ip), "r"(A.pos), "r"(A.lq_fast), "r"(A.qa), "r"(A.sa), "r"(B.mq), "r"(B.bq_eff), "r"(B.fwd01), "r"(B.rdhi01),
-                      "r"(D.pir_c), "r"(D.pir_s), "r"(rc4m));
-                (void)byte;
+                    : "=r"(off), "=r"(qv), "=r"(nib), "=r"(slow),
+                      "+r"(acc_cov), "+r"(a.bq_all), "+r"(acc_all), "+r"(a.bq), "+r"(acc_hi), "+r"(a.m_pir)
+                    : "r"(ip), "r"(A.pos), "r"(A.lq_fast), "r"(A.qa), "r"(A.bq_eff), "r"(kb), "r"(B.u_cov), "r"(B.u_all), "r"(B.u_hi), "r"(B.v_pir), "r"(rc4m));
                 if (slow) {
+                const StageD D = S.d[buf][t];
+                const int r_mq = (int)(B.u_cov >> 16);
+                if ((unsigned)off < A.lq_fast) {
                     const StageC C = S.c[buf][t];
-                    pile_generic(a, x, C.hash, (uint32_t)B.mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u), nib, qv, off, D.lq, rc4,
-                                 qv >= B.bq_eff, min_snv);
+                    pile_generic(a, x, C.hash, (uint32_t)r_mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u), nib, qv, off, D.lq, rc4,
+                                 qv >= A.bq_eff, min_snv);
                 }
                 if (D.flags & SF_COMPLEX) {
                     // general CIGAR (or unstaged bases / depth bound not met): every lane walks the same op list; pileup offsets
@@ -576,7 +599,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                     if (E.ext_end > wlo && live) {
                         const bool glob = D.flags & SF_GLOBAL;
                         const bool mq_ok = D.flags & SF_MQOK;
-                        const uint32_t gmisc = (uint32_t)B.mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u);
+                        const uint32_t gmisc = (uint32_t)r_mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u);
                         const int ncig_all = (int)C.n_cigar, ncig = min(ncig_all, max_cig);
                         int qi = 0, rp = A.pos, rdp = A.pos, lseq = D.lq;
                         for (int k = 0; k < ncig_all; k++) {
@@ -585,17 +608,17 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                             const bool in_pile = k < ncig;
                             if (op == OP_M || op == OP_EQ || op == OP_X) {
                                 const int od = ip - rdp;
-                                if ((unsigned)od < (unsigned)len && rdp >= 0 && (int64_t)rdp + len < P) { a.rd_mq += B.mq; rd_cnt++; a.rd_rd += B.rdhi01; }
+                                if ((unsigned)od < (unsigned)len && rdp >= 0 && (int64_t)rdp + len < P) { a.rd_mq += r_mq; rd_cnt++; a.rd_rd += (int)((B.u_cov >> 8) & 1u); }
                                 rdp += len;
                                 if (in_pile) {
                                     const int o = ip - rp;
                                     if ((unsigned)o < (unsigned)len && qi + o < D.lq) {
                                         const int xq = qi + o;
                                         int qv2, byte2;
-                                        if (!glob) { qv2 = lds_u8(A.qa + xq); byte2 = lds_u8(A.sa + (xq >> 1)); }
+                                        if (!glob) { qv2 = lds_u8(A.qa + xq); byte2 = lds_u8(((A.qa + xq) >> 1) + kb); }
                                         else { const uint64_t slot = ((uint64_t)E.base16 << 4) + (uint64_t)xq; qv2 = __ldg(R.qual + slot); byte2 = __ldg(R.seq4 + (slot >> 1)); }
                                         const int code2 = (byte2 >> ((~xq & 1) << 2)) & 15;
-                                        pile_apply(a, x, code2, qv2, C.hash, gmisc, xq, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv);
+                                        pile_apply(a, x, code2, qv2, C.hash, gmisc, xq, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv, (int)threadIdx.x);
                                     }
                                     qi += len; rp += len;
                                 }
@@ -606,9 +629,14 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                         }
                     }
                 }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.empty[buf]));
+            // unpack the stage's packed counters into the 32-bit accumulators
+            rd_cnt += (int)(acc_cov & 0xffu); a.rd_rd += (int)((acc_cov >> 8) & 0xffu); a.rd_mq += (int)(acc_cov >> 16);
+            a.m_all += (int)(acc_all & 0xffffu); a.mq_all += (int)(acc_all >> 16);
+            a.m_hi += (int)(acc_hi & 0xffu); a.m_fs += (int)((acc_hi >> 8) & 0xffu); a.mq += (int)(acc_hi >> 16);
             if (last) { c++; break; }
         }
         int snv[4], low[4], pir[4], fs[4];
@@ -617,6 +645,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
         if (live) {
             // fold the matching-base registers into the per-base counters
             a.m_low = a.m_all - a.m_hi;
+            a.m_pir += (int)threadIdx.x * (2 * a.m_fs - a.m_hi);               // position in read of the matching bases (see StageB::v_pir)
             a.rd_low += rd_cnt - a.rd_rd;
             const int rb = (rc4 == 1) ? 0 : (rc4 == 2) ? 1 : (rc4 == 4) ? 2 : 3;
 #pragma unroll
