@@ -315,6 +315,7 @@ __device__ __forceinline__ void pile_apply(PileAcc &a, PileRare &x, int code, in
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
@@ -473,17 +474,25 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                 const int64_t next_after = last ? next_tile_first : next + count;
                 PrepRec n0, n1;
                 load_pair(next_after, n0, n1);
-                if (c >= NSTAGE) mbar_wait(smem_u32(&S.empty[buf]), (uint32_t)((c / NSTAGE - 1) & 1));
-                const uint32_t bar = smem_u32(&S.full[buf]);
-                const uint32_t qbase = smem_u32(&S.qual[buf][0]), sbase = smem_u32(&S.seq[buf][0]);
-                // per consumer warp: staged reads with pos in (wlo - max_span, whi]
+                // per consumer warp: staged reads with pos in (wlo - max_span, whi] (lane w keeps the range of warp w)
+                int2 my_rng = make_int2(0, 0);
 #pragma unroll
                 for (int w = 0; w < NWARP; w++) {
                     const int wlo = (int)tile_lo + 32 * w, key = wlo - max_span, whi = wlo + 31;
                     const int t0 = __popc(__ballot_sync(0xffffffffu, st0 && r0.pos <= key)) + __popc(__ballot_sync(0xffffffffu, st1 && r1.pos <= key));
                     const int t1 = __popc(__ballot_sync(0xffffffffu, st0 && r0.pos <= whi)) + __popc(__ballot_sync(0xffffffffu, st1 && r1.pos <= whi));
-                    if (lane == w) S.rng[buf][w] = make_int2(t0, t1);
+                    if (lane == w) my_rng = make_int2(t0, t1);
                 }
+                // everything above ran while the position threads were still reading this stage's previous contents
+                if (c >= NSTAGE) mbar_wait(smem_u32(&S.empty[buf]), (uint32_t)((c / NSTAGE - 1) & 1));
+                const uint32_t bar = smem_u32(&S.full[buf]);
+                const uint32_t qbase = smem_u32(&S.qual[buf][0]), sbase = smem_u32(&S.seq[buf][0]);
+                if (lane == 0 && span) {
+                    mbar_expect_tx_only(bar, span + (span >> 1));
+                    bulk_g2s(qbase, R.qual + ((uint64_t)base_first << 4), span, bar);
+                    bulk_g2s(sbase, R.seq4 + ((uint64_t)base_first << 3), span >> 1, bar);
+                }
+                if (lane < NWARP) S.rng[buf][lane] = my_rng;
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const PrepRec &r = h ? r1 : r0;
@@ -505,13 +514,8 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                         S.a[buf][t] = A; S.b[buf][t] = B; S.d[buf][t] = D; S.c[buf][t] = C; S.e[buf][t] = E;
                     }
                 }
-                if (lane == 0) { S.last[buf] = last ? 1 : 0; mbar_expect_tx(bar, span + (span >> 1)); }
-                else mbar_arrive(bar);
-                __syncwarp();
-                if (lane == 0 && span) {
-                    bulk_g2s(qbase, R.qual + ((uint64_t)base_first << 4), span, bar);
-                    bulk_g2s(sbase, R.seq4 + ((uint64_t)base_first << 3), span >> 1, bar);
-                }
+                if (lane == 0) S.last[buf] = last ? 1 : 0;
+                mbar_arrive(bar);                                  // 32 arrivals publish the records; the bulk copies complete the transaction bytes
                 next = next_after; r0 = n0; r1 = n1;
                 if (last) { c++; break; }
             }
