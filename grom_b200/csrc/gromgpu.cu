@@ -254,6 +254,12 @@ __global__ void __launch_bounds__(256) k_tile_index(const int32_t *pos, int64_t 
 //    (m_hi, m_low, m_fs, m_pir) and every update is one predicated add.
 //  * generic path (mismatches, non-ACGT codes, N/IUPAC reference letters): the reference's full rule including
 //    the read-name slots, evaluated in BAM order because the staged read list is in BAM order.
+// Stage totals: the packed per-stage counters are unpacked into these once per stage.  With PILE_LOCAL_TOTALS they are indexed
+// through a run-time zero (c_prm.reserved0), which places them in local memory and frees eight registers of the fast loop.
+#ifndef PILE_LOCAL_TOTALS
+#define PILE_LOCAL_TOTALS 0
+#endif
+enum { F_MHI, F_MFS, F_MALL, F_MQ, F_MQALL, F_RDMQ, F_RDRD, F_RDCNT, F_COUNT };
 struct PileAcc {
     int m_hi, m_low, m_fs, m_pir, m_all;                // reference-matching bases (m_low is derived: m_all - m_hi)
     // Everything else is touched by ~0.2 % of the bases.  These 16 counters and the name slots are indexed with run-time values on
@@ -265,10 +271,11 @@ struct PileRare {
     int v[16];                                          // [0..3] snv, [4..7] low, [8..11] pir, [12..15] fs per base
     uint64_t nm[3]; int nm_cnt;
 };
+struct PileTotals { int f[F_COUNT]; };
 enum { RA_SNV = 0, RA_LOW = 4, RA_PIR = 8, RA_FS = 12 };
 
-__device__ __forceinline__ void pile_generic(PileAcc &a, PileRare &x, uint64_t hash, uint32_t misc, int code, int qv, int qi, int lseq, int rc4,
-                                          bool hi, int min_snv)
+__device__ __forceinline__ void pile_generic(PileAcc &a, PileRare &x, PileTotals &tt, uint64_t hash, uint32_t misc, int code, int qv, int qi, int lseq, int rc4,
+                                          bool hi, int min_snv, int zz)
 {
     const int mq = misc & 0xff;
     const int bi = (code == 1) ? 0 : (code == 2) ? 1 : (code == 4) ? 2 : (code == 8) ? 3 : -1;
@@ -284,29 +291,29 @@ __device__ __forceinline__ void pile_generic(PileAcc &a, PileRare &x, uint64_t h
         if (!skip && bi >= 0) {
             const bool fwd = !(misc & PR_REV);
             const int pir = (mism || fwd) ? qi : lseq - qi;
-            a.bq += qv; a.bq_all += qv; a.mq += mq; a.mq_all += mq;
+            a.bq += qv; a.bq_all += qv; tt.f[F_MQ + zz] += mq; tt.f[F_MQALL + zz] += mq;
             x.v[RA_SNV + bi] += 1; x.v[RA_PIR + bi] += pir; x.v[RA_FS + bi] += fwd ? 1 : 0;
         }
     } else if (bi >= 0) {
-        a.bq_all += qv; a.mq_all += mq;
+        a.bq_all += qv; tt.f[F_MQALL + zz] += mq;
         x.v[RA_LOW + bi] += 1;
     }
 }
 
 // classify one base (code, quality) of one read at this thread's position and fold it into the accumulators;
 // qi = query offset, lseq = read length seen by the position-in-read rule
-__device__ __forceinline__ void pile_apply(PileAcc &a, PileRare &x, int code, int qv, uint64_t hash, uint32_t misc, int qi, int lseq, int rc4,
-                                           bool ref_acgt, bool mq_ok, int bqmin, int min_snv, int p_rel)
+__device__ __forceinline__ void pile_apply(PileAcc &a, PileRare &x, PileTotals &tt, int code, int qv, uint64_t hash, uint32_t misc, int qi, int lseq, int rc4,
+                                           bool ref_acgt, bool mq_ok, int bqmin, int min_snv, int p_rel, int zz)
 {
     const bool hi = mq_ok && qv >= bqmin;
     if (ref_acgt && code == rc4) {
         const int mq = misc & 0xff;
         const bool fwd = !(misc & PR_REV);
-        a.bq_all += qv; a.mq_all += mq; a.m_all += 1;
+        a.bq_all += qv; tt.f[F_MQALL + zz] += mq; tt.f[F_MALL + zz] += 1;
         // m_pir holds the sum of (position in read) -+ p_rel, p_rel = position - tile start; the epilogue adds p_rel * (forward - reverse)
-        if (hi) { a.bq += qv; a.mq += mq; a.m_hi += 1; a.m_pir += fwd ? qi - p_rel : lseq - qi + p_rel; a.m_fs += fwd ? 1 : 0; }
+        if (hi) { a.bq += qv; tt.f[F_MQ + zz] += mq; tt.f[F_MHI + zz] += 1; a.m_pir += fwd ? qi - p_rel : lseq - qi + p_rel; tt.f[F_MFS + zz] += fwd ? 1 : 0; }
     } else {
-        pile_generic(a, x, hash, misc, code, qv, qi, lseq, rc4, hi, min_snv);
+        pile_generic(a, x, tt, hash, misc, code, qv, qi, lseq, rc4, hi, min_snv, zz);
     }
 }
 
@@ -336,7 +343,7 @@ __device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 
 
 #define QCAP (CHUNK * 160)        // quality bytes per stage (64 reads of 2x150 data); the 4-bit area is half of it
 #ifndef NSTAGE
-#define NSTAGE 3
+#define NSTAGE 2           // two stages measured faster than three (less shared memory per CTA leaves more L1; profiles/README.md)
 #endif
 #define NWARP (TILE / 32)         // consumer warps, one reference position per thread
 #define PILE_THREADS (TILE + 32)  // + 1 producer warp
@@ -525,6 +532,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
 
     // ================= position threads
     const int max_cig = c_prm.max_cigar_ops;
+    const int zz = PILE_LOCAL_TOTALS ? c_prm.reserved0 : 0;          // always 0
     unsigned long long dsum = 0; unsigned int dcnt = 0;
     int c = 0;
     for (int64_t tile = tile_begin; tile < tile_end; tile++) {
@@ -536,12 +544,13 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
         const int rc4m = ref_acgt ? rc4 : 0x10;                                // 0x10: never equals a nibble
         const int wlo = (int)(tile_lo + (threadIdx.x & ~31));
         const int ip = (int)p;
-        PileAcc a; PileRare x;
+        PileAcc a; PileRare x; PileTotals tt;
         a.m_hi = a.m_low = a.m_fs = a.m_pir = a.m_all = 0;
 #pragma unroll
         for (int k = 0; k < 16; k++) x.v[k] = 0;
         a.bq = a.bq_all = a.mq = a.mq_all = a.rd_mq = a.rd_rd = a.rd_low = 0; x.nm[0] = x.nm[1] = x.nm[2] = 0; x.nm_cnt = 0;
-        int rd_cnt = 0;
+#pragma unroll
+        for (int k = 0; k < F_COUNT; k++) tt.f[k] = 0;
 
         for (;; c++) {
             const int buf = c % NSTAGE;
@@ -592,8 +601,8 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                 const int r_mq = (int)(B.u_cov >> 16);
                 if ((unsigned)off < A.lq_fast) {
                     const StageC C = S.c[buf][t];
-                    pile_generic(a, x, C.hash, (uint32_t)r_mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u), nib, qv, off, D.lq, rc4,
-                                 qv >= A.bq_eff, min_snv);
+                    pile_generic(a, x, tt, C.hash, (uint32_t)r_mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u), nib, qv, off, D.lq, rc4,
+                                 qv >= A.bq_eff, min_snv, zz);
                 }
                 if (D.flags & SF_COMPLEX) {
                     // general CIGAR (or unstaged bases / depth bound not met): every lane walks the same op list; pileup offsets
@@ -612,7 +621,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                             const bool in_pile = k < ncig;
                             if (op == OP_M || op == OP_EQ || op == OP_X) {
                                 const int od = ip - rdp;
-                                if ((unsigned)od < (unsigned)len && rdp >= 0 && (int64_t)rdp + len < P) { a.rd_mq += r_mq; rd_cnt++; a.rd_rd += (int)((B.u_cov >> 8) & 1u); }
+                                if ((unsigned)od < (unsigned)len && rdp >= 0 && (int64_t)rdp + len < P) { tt.f[F_RDMQ + zz] += r_mq; tt.f[F_RDCNT + zz] += 1; tt.f[F_RDRD + zz] += (int)((B.u_cov >> 8) & 1u); }
                                 rdp += len;
                                 if (in_pile) {
                                     const int o = ip - rp;
@@ -622,7 +631,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                                         if (!glob) { qv2 = lds_u8(A.qa + xq); byte2 = lds_u8(((A.qa + xq) >> 1) + kb); }
                                         else { const uint64_t slot = ((uint64_t)E.base16 << 4) + (uint64_t)xq; qv2 = __ldg(R.qual + slot); byte2 = __ldg(R.seq4 + (slot >> 1)); }
                                         const int code2 = (byte2 >> ((~xq & 1) << 2)) & 15;
-                                        pile_apply(a, x, code2, qv2, C.hash, gmisc, xq, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv, (int)threadIdx.x);
+                                        pile_apply(a, x, tt, code2, qv2, C.hash, gmisc, xq, lseq, rc4, ref_acgt, mq_ok, bqmin, min_snv, (int)threadIdx.x, zz);
                                     }
                                     qi += len; rp += len;
                                 }
@@ -638,11 +647,14 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.empty[buf]));
             // unpack the stage's packed counters into the 32-bit accumulators
-            rd_cnt += (int)(acc_cov & 0xffu); a.rd_rd += (int)((acc_cov >> 8) & 0xffu); a.rd_mq += (int)(acc_cov >> 16);
-            a.m_all += (int)(acc_all & 0xffffu); a.mq_all += (int)(acc_all >> 16);
-            a.m_hi += (int)(acc_hi & 0xffu); a.m_fs += (int)((acc_hi >> 8) & 0xffu); a.mq += (int)(acc_hi >> 16);
+            tt.f[F_RDCNT + zz] += (int)(acc_cov & 0xffu); tt.f[F_RDRD + zz] += (int)((acc_cov >> 8) & 0xffu); tt.f[F_RDMQ + zz] += (int)(acc_cov >> 16);
+            tt.f[F_MALL + zz] += (int)(acc_all & 0xffffu); tt.f[F_MQALL + zz] += (int)(acc_all >> 16);
+            tt.f[F_MHI + zz] += (int)(acc_hi & 0xffu); tt.f[F_MFS + zz] += (int)((acc_hi >> 8) & 0xffu); tt.f[F_MQ + zz] += (int)(acc_hi >> 16);
             if (last) { c++; break; }
         }
+        a.m_hi += tt.f[F_MHI]; a.m_fs += tt.f[F_MFS]; a.m_all += tt.f[F_MALL]; a.mq += tt.f[F_MQ]; a.mq_all += tt.f[F_MQALL];
+        a.rd_mq += tt.f[F_RDMQ]; a.rd_rd += tt.f[F_RDRD];
+        const int rd_cnt = tt.f[F_RDCNT];
         int snv[4], low[4], pir[4], fs[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) { snv[k] = x.v[RA_SNV + k]; low[k] = x.v[RA_LOW + k]; pir[k] = x.v[RA_PIR + k]; fs[k] = x.v[RA_FS + k]; }
