@@ -77,7 +77,9 @@ struct DevReads {
 };
 
 #define TILE 256           // positions per CTA in the pileup kernel (one per thread)
-#define CHUNK 64           // read records staged per shared-memory refill (two per lane of the producer warp)
+#ifndef CHUNK
+#define CHUNK 32           // read records staged per shared-memory refill (CHUNK / 32 per lane of the producer warp; a multiple of 32, <= 224: packed counters)
+#endif
 
 // reference character -> BAM 4-bit code of toupper(char), 16 if the character is not a code letter
 __device__ __forceinline__ int ref_code(unsigned char c)
@@ -343,7 +345,7 @@ __device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 
 
 #define QCAP (CHUNK * 160)        // quality bytes per stage (64 reads of 2x150 data); the 4-bit area is half of it
 #ifndef NSTAGE
-#define NSTAGE 2           // two stages measured faster than three (less shared memory per CTA leaves more L1; profiles/README.md)
+#define NSTAGE 4           // 4 stages of 32 reads measured fastest (profiles/README.md: finer stages, and less shared memory per CTA leaves more L1)
 #endif
 #define NWARP (TILE / 32)         // consumer warps, one reference position per thread
 #define PILE_THREADS (TILE + 32)  // + 1 producer warp
@@ -351,7 +353,7 @@ __device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 
 #define PILE_MIN_CTAS 3
 #endif
 #ifndef SUBTILES
-#define SUBTILES 8
+#define SUBTILES 16
 #endif
 //                              // consecutive tiles handled by one CTA (keeps the producer pipeline full across tiles)
 
@@ -423,71 +425,84 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
         // plain ints + bulk copies (TMA) of their bases
         const int max_span = *max_span_p;
         int c = 0;
-        auto load_pair = [&](int64_t first, PrepRec &r0, PrepRec &r1) {
-            const int64_t i0 = first + 2 * lane, i1 = i0 + 1;
-            r0.pos = r1.pos = INT32_MAX; r0.misc = r1.misc = 0; r0.ext_end = r1.ext_end = INT32_MIN; r0.base16 = r1.base16 = 0;
-            r0.hash = r1.hash = 0; r0.cig_off = r1.cig_off = r0.n_cigar = r1.n_cigar = 0;
-            if (i0 < R.n) r0 = prep[i0];
-            if (i1 < R.n) r1 = prep[i1];
+        constexpr int RPL = CHUNK / 32;                           // records per lane and chunk
+        auto load_group = [&](int64_t first, PrepRec (&r)[RPL]) {
+#pragma unroll
+            for (int h = 0; h < RPL; h++) {
+                const int64_t i = first + RPL * lane + h;
+                r[h].pos = INT32_MAX; r[h].misc = 0; r[h].ext_end = INT32_MIN; r[h].base16 = 0; r[h].hash = 0; r[h].cig_off = r[h].n_cigar = 0;
+                if (i < R.n) r[h] = prep[i];
+            }
         };
         int64_t next = tile_begin < tile_end ? tile_first[tile_begin] : 0;
-        PrepRec r0, r1;
-        load_pair(next, r0, r1);
+        PrepRec r[RPL];
+        load_group(next, r);
         for (int64_t tile = tile_begin; tile < tile_end; tile++) {
             const int64_t tile_lo = tile * TILE, tile_hi = min(tile_lo + TILE, P);
             const int64_t next_tile_first = tile + 1 < tile_end ? tile_first[tile + 1] : 0;     // in flight while this tile's chunks are staged
             for (;; c++) {
                 const int buf = c % NSTAGE;
-                const int64_t i0 = next + 2 * lane, i1 = i0 + 1;
-                const bool v0 = i0 < R.n, v1 = i1 < R.n;
-                const bool use0 = v0 && (r0.misc & PR_APPLIED) && (int64_t)r0.ext_end > tile_lo && (int64_t)r0.pos < tile_hi;
-                const bool use1 = v1 && (r1.misc & PR_APPLIED) && (int64_t)r1.ext_end > tile_lo && (int64_t)r1.pos < tile_hi;
-                const uint32_t sz0 = use0 ? (((r0.misc >> 16) + 31u) & ~31u) : 0u, sz1 = use1 ? (((r1.misc >> 16) + 31u) & ~31u) : 0u;
-                const bool big0 = sz0 > QCAP, big1 = sz1 > QCAP;               // longer than a stage: the position threads read its bases from global memory
-                const bool want0 = use0 && !big0 && sz0, want1 = use1 && !big1 && sz1;
+                bool v[RPL], use[RPL], big[RPL], want[RPL], st[RPL];
+                uint32_t sz[RPL]; int64_t rel[RPL];
                 // The bases of consecutive reads lie back to back in the batch, so the stage takes ONE contiguous span per array (two bulk
                 // copies per stage): from the first read that is needed to the last one that still fits, whatever lies between included.
                 // (Offsets that do not ascend end the chunk early; the read then opens the next one.)
-                const unsigned bw0 = __ballot_sync(0xffffffffu, want0), bw1 = __ballot_sync(0xffffffffu, want1);
-                const unsigned firstbits = bw0 | bw1;
+                int first_idx = CHUNK;
+#pragma unroll
+                for (int h = 0; h < RPL; h++) {
+                    v[h] = next + RPL * lane + h < R.n;
+                    use[h] = v[h] && (r[h].misc & PR_APPLIED) && (int64_t)r[h].ext_end > tile_lo && (int64_t)r[h].pos < tile_hi;
+                    sz[h] = use[h] ? (((r[h].misc >> 16) + 31u) & ~31u) : 0u;
+                    big[h] = sz[h] > QCAP;                             // longer than a stage: the position threads read its bases from global memory
+                    want[h] = use[h] && !big[h] && sz[h];
+                    const unsigned bw = __ballot_sync(0xffffffffu, want[h]);
+                    if (bw) first_idx = min(first_idx, RPL * (__ffs(bw) - 1) + h);
+                }
                 uint32_t base_first = 0;
-                if (firstbits) {
-                    const int fl = __ffs(firstbits) - 1;
-                    const uint32_t cand = (bw0 >> fl) & 1u ? r0.base16 : r1.base16;
-                    base_first = __shfl_sync(0xffffffffu, cand, fl);
+                if (first_idx < CHUNK) {
+                    uint32_t cand = 0;
+#pragma unroll
+                    for (int h = 0; h < RPL; h++) if (first_idx % RPL == h) cand = r[h].base16;
+                    base_first = __shfl_sync(0xffffffffu, cand, first_idx / RPL);
                 }
-                const int64_t rel0 = ((int64_t)r0.base16 - (int64_t)base_first) * 16, rel1 = ((int64_t)r1.base16 - (int64_t)base_first) * 16;
-                const bool fit0 = v0 && (!want0 || (rel0 >= 0 && rel0 + sz0 <= QCAP)), fit1 = v1 && (!want1 || (rel1 >= 0 && rel1 + sz1 <= QCAP));
-                // reads consumed from the stream: the leading run of reads that fit (lane order = read order i0, i1 per lane)
-                const unsigned nf0 = ~__ballot_sync(0xffffffffu, fit0), nf1 = ~__ballot_sync(0xffffffffu, fit1);
-                int count;
-                {
-                    const int l0 = nf0 ? __ffs(nf0) - 1 : 32, l1 = nf1 ? __ffs(nf1) - 1 : 32;       // first lane whose read 0 / read 1 does not fit
-                    count = l0 <= l1 ? 2 * l0 : 2 * l1 + 1;
-                    if (l0 == 32 && l1 == 32) count = 64;
+                // reads consumed from the stream: the leading run of reads that fit (read order = RPL * lane + h)
+                int count = CHUNK;
+#pragma unroll
+                for (int h = 0; h < RPL; h++) {
+                    rel[h] = ((int64_t)r[h].base16 - (int64_t)base_first) * 16;
+                    const bool fit = v[h] && (!want[h] || (rel[h] >= 0 && rel[h] + sz[h] <= QCAP));
+                    const unsigned nf = ~__ballot_sync(0xffffffffu, fit);
+                    if (nf) count = min(count, RPL * (__ffs(nf) - 1) + h);
                 }
-                const bool in0 = 2 * lane < count, in1 = 2 * lane + 1 < count;
-                const unsigned anypast = __ballot_sync(0xffffffffu, (in0 && v0 && (int64_t)r0.pos >= tile_hi) || (in1 && v1 && (int64_t)r1.pos >= tile_hi));
-                const bool last = (anypast != 0u) || (next + count >= R.n);
-                const bool st0 = in0 && use0, st1 = in1 && use1;          // staged (compacted) reads
-                const unsigned bs0 = __ballot_sync(0xffffffffu, st0), bs1 = __ballot_sync(0xffffffffu, st1);
-                const unsigned lt = (1u << lane) - 1u;
-                const int idx0 = __popc(bs0 & lt) + __popc(bs1 & lt), idx1 = idx0 + (st0 ? 1 : 0);
+                bool past = false;
                 uint32_t span = 0;
-                if (st0 && want0) span = (uint32_t)rel0 + sz0;
-                if (st1 && want1) span = max(span, (uint32_t)rel1 + sz1);
+                int below = 0;                                          // staged reads in lower lanes
+                const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+                for (int h = 0; h < RPL; h++) {
+                    const bool in = RPL * lane + h < count;
+                    past = past || (in && v[h] && (int64_t)r[h].pos >= tile_hi);
+                    st[h] = in && use[h];                               // staged (compacted) reads
+                    below += __popc(__ballot_sync(0xffffffffu, st[h]) & lt);
+                    if (st[h] && want[h]) span = max(span, (uint32_t)rel[h] + sz[h]);
+                }
+                const bool last = (__ballot_sync(0xffffffffu, past) != 0u) || (next + count >= R.n);
                 span = __reduce_max_sync(0xffffffffu, span);
                 // the records of the chunk after this one travel while this one is staged
                 const int64_t next_after = last ? next_tile_first : next + count;
-                PrepRec n0, n1;
-                load_pair(next_after, n0, n1);
+                PrepRec nx[RPL];
+                load_group(next_after, nx);
                 // per consumer warp: staged reads with pos in (wlo - max_span, whi] (lane w keeps the range of warp w)
                 int2 my_rng = make_int2(0, 0);
 #pragma unroll
                 for (int w = 0; w < NWARP; w++) {
                     const int wlo = (int)tile_lo + 32 * w, key = wlo - max_span, whi = wlo + 31;
-                    const int t0 = __popc(__ballot_sync(0xffffffffu, st0 && r0.pos <= key)) + __popc(__ballot_sync(0xffffffffu, st1 && r1.pos <= key));
-                    const int t1 = __popc(__ballot_sync(0xffffffffu, st0 && r0.pos <= whi)) + __popc(__ballot_sync(0xffffffffu, st1 && r1.pos <= whi));
+                    int t0 = 0, t1 = 0;
+#pragma unroll
+                    for (int h = 0; h < RPL; h++) {
+                        t0 += __popc(__ballot_sync(0xffffffffu, st[h] && r[h].pos <= key));
+                        t1 += __popc(__ballot_sync(0xffffffffu, st[h] && r[h].pos <= whi));
+                    }
                     if (lane == w) my_rng = make_int2(t0, t1);
                 }
                 // everything above ran while the position threads were still reading this stage's previous contents
@@ -500,30 +515,32 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                     bulk_g2s(sbase, R.seq4 + ((uint64_t)base_first << 3), span >> 1, bar);
                 }
                 if (lane < NWARP) S.rng[buf][lane] = my_rng;
+                int t = below;
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const PrepRec &r = h ? r1 : r0;
-                    const bool st = h ? st1 : st0, big = h ? big1 : big0;
-                    const uint32_t off = (uint32_t)(h ? rel1 : rel0);
-                    const int t = h ? idx1 : idx0;
-                    if (st) {
-                        const int mq = r.misc & 0xff, lq = (int)(r.misc >> 16);
-                        const bool rev = r.misc & PR_REV;
-                        const bool fast = (r.misc & PR_SIMPLE) && !big && (int64_t)r.pos + lq < P;
-                        const int rel = r.pos - (int)tile_lo;
-                        StageA A; A.pos = r.pos; A.lq_fast = fast ? (uint32_t)lq : 0u; A.qa = qbase + off; A.bq_eff = (mq >= q) ? bqmin : 256;
+                for (int h = 0; h < RPL; h++) {
+                    if (st[h]) {
+                        const PrepRec &rr = r[h];
+                        const uint32_t off = (uint32_t)rel[h];
+                        const int mq = rr.misc & 0xff, lq = (int)(rr.misc >> 16);
+                        const bool rev = rr.misc & PR_REV;
+                        const bool fast = (rr.misc & PR_SIMPLE) && !big[h] && (int64_t)rr.pos + lq < P;
+                        const int prel = rr.pos - (int)tile_lo;
+                        StageA A; A.pos = rr.pos; A.lq_fast = fast ? (uint32_t)lq : 0u; A.qa = qbase + off; A.bq_eff = (mq >= q) ? bqmin : 256;
                         StageB B; B.u_cov = 1u | ((mq >= rdq) ? 0x100u : 0u) | ((uint32_t)mq << 16); B.u_all = 1u | ((uint32_t)mq << 16);
-                        B.u_hi = 1u | (rev ? 0u : 0x100u) | ((uint32_t)mq << 16); B.v_pir = rev ? lq + rel : -rel;
+                        B.u_hi = 1u | (rev ? 0u : 0x100u) | ((uint32_t)mq << 16); B.v_pir = rev ? lq + prel : -prel;
                         StageD D; D.pir_c = rev ? lq : 0; D.pir_s = rev ? -1 : 1; D.lq = lq;
-                        D.flags = (fast ? 0u : SF_COMPLEX) | (big ? SF_GLOBAL : 0u) | (rev ? SF_REV : 0u) | ((r.misc & PR_NAMEOK) ? SF_NAMEOK : 0u) | ((mq >= q) ? SF_MQOK : 0u);
-                        StageC C; C.hash = r.hash; C.cig_off = r.cig_off; C.n_cigar = r.n_cigar;
-                        StageE E; E.base16 = r.base16; E.ext_end = r.ext_end;
+                        D.flags = (fast ? 0u : SF_COMPLEX) | (big[h] ? SF_GLOBAL : 0u) | (rev ? SF_REV : 0u) | ((rr.misc & PR_NAMEOK) ? SF_NAMEOK : 0u) | ((mq >= q) ? SF_MQOK : 0u);
+                        StageC C; C.hash = rr.hash; C.cig_off = rr.cig_off; C.n_cigar = rr.n_cigar;
+                        StageE E; E.base16 = rr.base16; E.ext_end = rr.ext_end;
                         S.a[buf][t] = A; S.b[buf][t] = B; S.d[buf][t] = D; S.c[buf][t] = C; S.e[buf][t] = E;
+                        t++;
                     }
                 }
                 if (lane == 0) S.last[buf] = last ? 1 : 0;
                 mbar_arrive(bar);                                  // 32 arrivals publish the records; the bulk copies complete the transaction bytes
-                next = next_after; r0 = n0; r1 = n1;
+                next = next_after;
+#pragma unroll
+                for (int h = 0; h < RPL; h++) r[h] = nx[h];
                 if (last) { c++; break; }
             }
         }
