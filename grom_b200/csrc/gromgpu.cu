@@ -1840,11 +1840,13 @@ struct CnvState {
     int q = 0;
     std::vector<double> sd_tbl, wtab;
     cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, open_first, open_state;
+    void *h_gather = nullptr; size_t h_gather_cap = 0;      // pinned landing area of the gathered call ranges (depth, GC byte, record per position)
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr;   // packed records travel to the host while the sweep runs
 };
 static void cnv_state_free(CnvState *c)
 {
     if (!c) return;
+    if (c->h_gather) cudaFreeHost(c->h_gather);
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
@@ -2064,11 +2066,10 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     SampleList rsl[SEG];
     double rs_ave[SEG] = {0}, rs_sd[SEG] = {0};
     std::vector<unsigned> biased_idx;
-    auto gather = [&](const std::vector<int64_t> &starts, const std::vector<int64_t> &firsts, std::vector<int32_t> &o_depth, std::vector<uint8_t> &o_gc, std::vector<uint32_t> *o_rec = nullptr) -> int {
+    auto gather = [&](const std::vector<int64_t> &starts, const std::vector<int64_t> &firsts, std::vector<int32_t> &o_depth, std::vector<uint8_t> &o_gc, std::vector<uint32_t> *o_rec = nullptr, void **pinned_out = nullptr) -> int {
         const int n_seg = (int)starts.size();
         const int64_t total = firsts.back();
-        o_depth.resize(total); o_gc.resize(total);
-        if (o_rec) o_rec->resize(total);
+        if (!pinned_out) { o_depth.resize(total); o_gc.resize(total); if (o_rec) o_rec->resize(total); }
         if (!total) return 0;
         Grow &a = c.tmp[3], &b = c.tmp[4], &od = c.tmp[5], &og = c.tmp[6];
         if (!a.ensure(sizeof(int64_t) * n_seg) || !b.ensure(sizeof(int64_t) * (n_seg + 1)) || !od.ensure(sizeof(int32_t) * total) || !og.ensure(total) ||
@@ -2077,6 +2078,24 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMemcpyAsync(a.p, starts.data(), sizeof(int64_t) * n_seg, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(b.p, firsts.data(), sizeof(int64_t) * (n_seg + 1), cudaMemcpyHostToDevice, s));
         k_gather<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c.d_depth, A_gc, A_acgt, a.as<int64_t>(), b.as<int64_t>(), n_seg, total, od.as<int32_t>(), og.as<uint8_t>(), c.d_rec, o_rec ? c.gather_rec.as<uint32_t>() : nullptr); n_launch++;
+        if (pinned_out) {
+            // copy-number ranges: straight into a pinned landing area (no zero-filled vectors, no pageable staging)
+            const size_t need = (size_t)total * 9 + 64;
+            if (need > c.h_gather_cap) {
+                if (c.h_gather) cudaFreeHost(c.h_gather);
+                c.h_gather = nullptr; c.h_gather_cap = 0;
+                CK(cudaMallocHost(&c.h_gather, need + need / 4));
+                c.h_gather_cap = need + need / 4;
+            }
+            int32_t *pd = (int32_t *)c.h_gather; uint32_t *pr = (uint32_t *)(pd + total); uint8_t *pg = (uint8_t *)(pr + total);
+            CK(cudaMemcpyAsync(pd, od.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(pr, c.gather_rec.p, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(pg, og.p, total, cudaMemcpyDeviceToHost, s));
+            pinned_out[0] = pd; pinned_out[1] = pr; pinned_out[2] = pg;
+            dev_end();
+            CK(cudaGetLastError());
+            return 0;
+        }
         CK(cudaMemcpyAsync(o_depth.data(), od.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(o_gc.data(), og.p, total, cudaMemcpyDeviceToHost, s));
         if (o_rec) CK(cudaMemcpyAsync(o_rec->data(), c.gather_rec.p, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, s));
@@ -2140,26 +2159,34 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         size_t k = 0;
         for (int d = 0; d <= mx; d++) for (int j = 0; j < h[d]; j++) v[k++] = d;
     };
-    for (auto &l : lists) sort_depths(l.v);
+    // the per-list work below is independent per list: a few host threads share it
+    auto par_lists = [&](auto &&fn) {
+        const int T = (int)std::max<unsigned>(1, std::min<unsigned>(8, std::thread::hardware_concurrency()));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; t++) pool.emplace_back([&, t]() { for (int l = t; l < NLIST; l += T) fn(l); });
+        for (int l = 0; l < NLIST; l += T) fn(l);
+        for (auto &x : pool) x.join();
+    };
+    par_lists([&](int l) { sort_depths(lists[l].v); });
     {
         // thin bins (20 <= n < 100) borrow the original samples of the two bins on either side (src/GROM.c:18481-18548)
         std::vector<std::vector<int>> grown(NLIST);
-        for (int m = 0; m < 2; m++)
-            for (int b = 2; b < NB - 2; b++) {
-                const auto &me = lists[m * NB + b].v;
-                if ((long)me.size() < MIN_WINDOWS || (long)me.size() >= NO_COMBINE) continue;
-                std::vector<int> g(me);
-                for (int a = b - 2; a <= b + 2; a++) if (a != b) for (int x : lists[m * NB + a].v) if ((long)g.size() < cap) g.push_back(x);
-                sort_depths(g);
-                grown[m * NB + b] = std::move(g);
-            }
+        par_lists([&](int l) {
+            const int m = l / NB, b = l % NB;
+            if (m >= 2 || b < 2 || b >= NB - 2) return;
+            const auto &me = lists[l].v;
+            if ((long)me.size() < MIN_WINDOWS || (long)me.size() >= NO_COMBINE) return;
+            std::vector<int> g(me);
+            for (int a = b - 2; a <= b + 2; a++) if (a != b) for (int x : lists[m * NB + a].v) if ((long)g.size() < cap) g.push_back(x);
+            sort_depths(g);
+            grown[l] = std::move(g);
+        });
         for (int l = 0; l < NLIST; l++) if (!grown[l].empty()) lists[l].v = std::move(grown[l]);
     }
     const double del_f = 1.0 - 0.6 / ploidy, dup_f = 1.0 + 0.6 / ploidy;
     std::vector<double> ave(NLIST, 0.0), sdv(NLIST, 0.0), del_thr(NLIST, 0.0), dup_thr(NLIST, 0.0);
-    std::vector<int32_t> nlist(NLIST, 0), small(2 * NLIST, 0);
-    int D = 0;
-    for (int l = 0; l < NLIST; l++) {
+    std::vector<int32_t> nlist(NLIST, 0), small(2 * NLIST, 0), top(NLIST, 0);
+    par_lists([&](int l) {
         const auto &v = lists[l].v;
         const long n = (long)v.size();
         nlist[l] = (int32_t)n;
@@ -2169,19 +2196,20 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             ave[l] = sm / n; del_thr[l] = del_f * ave[l]; dup_thr[l] = dup_f * ave[l];
             for (long j = 0; j < n; j++) var += (v[j] - ave[l]) * (v[j] - ave[l]);
             sdv[l] = n > 1 ? sqrt(var / (n - 1)) : var;
-            D = std::max(D, v.back());
+            top[l] = v.back();
             small[2 * l] = v[0]; small[2 * l + 1] = n > 1 ? v[1] : v[0];
         }
         c.bin_d[l] = ave[l]; c.bin_d[NLIST + l] = sdv[l]; c.bin_d[2 * NLIST + l] = del_thr[l]; c.bin_d[3 * NLIST + l] = dup_thr[l]; c.bin_n[l] = n;
-    }
-    if (D < 0) D = 0;
+    });
+    int D = 0;
+    for (int l = 0; l < NLIST; l++) D = std::max(D, top[l]);
     if ((int64_t)NLIST * (D + 1) > (int64_t)1 << 30) return fail("gromgpu_chr_cnv: sampled depth %d is too large for the rank tables", D);
     std::vector<int32_t> cum((size_t)NLIST * (D + 1), 0);
-    for (int l = 0; l < NLIST; l++) {
+    par_lists([&](int l) {
         int32_t *row = cum.data() + (size_t)l * (D + 1);
         for (int x : lists[l].v) row[x]++;
         for (int d = 1; d <= D; d++) row[d] += row[d - 1];
-    }
+    });
     Grow &t_cum = c.tmp[7], &t_n = c.tmp[8], &t_small = c.tmp[9], &t_dbl = c.tmp[10];
     if (!t_cum.ensure(sizeof(int32_t) * cum.size()) || !t_n.ensure(sizeof(int32_t) * NLIST) || !t_small.ensure(sizeof(int32_t) * 2 * NLIST) ||
         !t_dbl.ensure(sizeof(double) * (3 * NLIST + 2 * P2S + 256))) return fail("gromgpu_chr_cnv: out of device memory");
@@ -2464,7 +2492,10 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     std::vector<int64_t> seg_start, seg_first(1, 0);
     for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) { seg_start.push_back(cl.start); seg_first.push_back(seg_first.back() + std::max<int64_t>(0, cl.end - cl.start)); }
     std::vector<int32_t> g_depth; std::vector<uint8_t> g_gc; std::vector<uint32_t> g_rec;
-    if (!seg_start.empty() && gather(seg_start, seg_first, g_depth, g_gc, &g_rec)) return -1;
+    void *g_pin[3] = {nullptr, nullptr, nullptr};
+    if (!seg_start.empty() && gather(seg_start, seg_first, g_depth, g_gc, &g_rec, g_pin)) return -1;
+    const int32_t *gp_depth = (const int32_t *)g_pin[0]; const uint32_t *gp_rec = (const uint32_t *)g_pin[1]; const uint8_t *gp_gc = (const uint8_t *)g_pin[2];
+    const int64_t g_total = seg_first.back();
     mark("gather");
     {
         // copy number per call (src/GROM.c:20071-20224): independent per call, spread over a few host threads
@@ -2479,11 +2510,11 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 buf.clear();
                 for (int64_t j = seg_first[si]; j < seg_first[si + 1]; j++) {
                     const int64_t p = cl.start + (j - seg_first[si]);
-                    const uint32_t r = g_rec[j];
+                    const uint32_t r = gp_rec[j];
                     (void)p;
                     if (r & R_MASK) continue;
-                    const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (g_gc[j] & 0x7f);
-                    if (ave[l] > 0) buf.push_back((double)g_depth[j] / ave[l]);
+                    const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (gp_gc[j] & 0x7f);
+                    if (ave[l] > 0) buf.push_back((double)gp_depth[j] / ave[l]);
                 }
                 const long n = (long)buf.size();
                 if (n > 0) {
@@ -2506,17 +2537,18 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 c.calls[si] = o;
             }
         };
-        const size_t nc = flat.size(), T = std::max<size_t>(1, std::min<size_t>(8, std::min<size_t>(std::thread::hardware_concurrency(), nc / 64 + 1)));
+        const size_t nc = flat.size(), T = std::max<size_t>(1, std::min<size_t>(16, std::min<size_t>(std::thread::hardware_concurrency(), nc / 64 + 1)));
         std::vector<std::thread> pool;
         for (size_t t = 1; t < T; t++) pool.emplace_back(work, nc * t / T, nc * (t + 1) / T);
         work(0, nc / T);
         for (auto &x : pool) x.join();
     }
+    mark("copy number");
     out->n_calls = (int64_t)c.calls.size(); out->calls = c.calls.data();
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     d2h += (int64_t)sizeof(cnv::PreOut) * n_blk + 8 * HIST_ALL + (int64_t)sizeof(RepRec) * n_rep + (int64_t)sizeof(Sample) * n_samples +
-           8 * ((int64_t)seed_tot_all) + 16 * (int64_t)n_spec_all + 9 * (int64_t)g_depth.size() + 5 * (int64_t)rp_depth.size() + 16 * (int64_t)n_len;
+           8 * ((int64_t)seed_tot_all) + 16 * (int64_t)n_spec_all + 9 * g_total + 5 * (int64_t)rp_depth.size() + 16 * (int64_t)n_len;
     out->launches = n_launch; out->d2h_bytes = d2h;
     out->ms_device = (float)ms_dev; out->ms_total = (float)ms_total; out->ms_host = (float)(ms_total - ms_dev);
     return 0;
