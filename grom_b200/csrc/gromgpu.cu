@@ -951,22 +951,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_inplace(int32_t *data_bas
     __syncthreads();
     const int warp_excl = wid ? s_warp[wid - 1] : 0;
     const int tile_sum = s_warp[SCAN_THREADS / 32 - 1];
-    if (threadIdx.x == 0) {
+    if (wid == 0) {
+        // decoupled look-back by one warp: 32 predecessors per round trip (lane l looks at tile - 1 - l), up to the nearest tile
+        // whose inclusive prefix is known
+        if (lane == 0) atomicExch(status + tile, ((tile == 0 ? 2ull : 1ull) << 32) | (unsigned int)tile_sum);
         int excl = 0;
-        if (tile == 0) {
-            atomicExch(status + tile, (2ull << 32) | (unsigned int)tile_sum);
-        } else {
-            atomicExch(status + tile, (1ull << 32) | (unsigned int)tile_sum);
-            for (int j = tile - 1; j >= 0; j--) {
-                unsigned long long s;
-                do { s = *((volatile unsigned long long *)(status + j)); } while ((s >> 32) == 0);
-                excl += (int)(unsigned int)s;
-                if ((s >> 32) == 2) break;
+        if (tile > 0) {
+            for (int j = tile - 1;; j -= 32) {
+                const int idx = j - lane;
+                unsigned long long st = 2ull << 32;                       // before the first tile: inclusive prefix 0
+                if (idx >= 0) { do { st = *((volatile unsigned long long *)(status + idx)); } while ((st >> 32) == 0); }
+                const unsigned done = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+                const int stop = done ? __ffs(done) - 1 : 31;             // nearest predecessor with an inclusive prefix
+                int part = lane <= stop ? (int)(unsigned int)st : 0;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                excl += part;
+                if (done) break;
             }
-            __threadfence();
-            atomicExch(status + tile, (2ull << 32) | (unsigned int)(excl + tile_sum));
+            if (lane == 0) { __threadfence(); atomicExch(status + tile, (2ull << 32) | (unsigned int)(excl + tile_sum)); }
         }
-        s_excl = excl;
+        if (lane == 0) s_excl = excl;
     }
     __syncthreads();
     const int off = s_excl + warp_excl + (incl - mine);
