@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
             const int2 rng = S.rng[buf][wid];
             const uint32_t kb = smem_u32(&S.seq[buf][0]) - (smem_u32(&S.qual[buf][0]) >> 1);     // nibble byte of quality address x: (x >> 1) + kb
             uint32_t acc_cov = 0, acc_all = 0, acc_hi = 0;
-#pragma unroll 2
+#pragma unroll 1                                          // measured: 1 beats 2 by 9 %, 3 and 4 are far slower (the slow paths are duplicated into the loop body)
             for (int t = rng.x; t < rng.y; t++) {
                 const StageA A = S.a[buf][t];
                 const StageB B = S.b[buf][t];
