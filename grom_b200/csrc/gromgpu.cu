@@ -76,7 +76,9 @@ struct DevReads {
     const uint8_t *seq4, *qual;
 };
 
+#ifndef TILE
 #define TILE 256           // positions per CTA in the pileup kernel (one per thread)
+#endif
 #ifndef CHUNK
 #define CHUNK 32           // read records staged per shared-memory refill (CHUNK / 32 per lane of the producer warp; a multiple of 32, <= 224: packed counters)
 #endif
