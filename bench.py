@@ -173,6 +173,8 @@ def pin_batch(batch):
     out.layout_flags = batch.layout_flags
     if batch.qual4 is not None:
         out.qual4, out.qual_lut = pin(batch.qual4), batch.qual_lut
+    if batch.qual2 is not None:
+        out.qual2, out.qual_lut = pin(batch.qual2), batch.qual_lut
     if batch.seq2 is not None:
         out.seq2, out.seq_exc_slot, out.seq_exc_code = pin(batch.seq2), pin(batch.seq_exc_slot), pin(batch.seq_exc_code)
     if batch.sa_index is not None:
@@ -371,7 +373,7 @@ def main_b200(a):
             "e2e": {"value": total_bases * a.steps / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(read_bytes + P),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps,
                     "upload_form": ("canonical arrays" if not pinned.layout_flags else "transport-compact (include/grom_reads.h GROM_LAYOUT_*): "
-                                    + ", ".join(n for bit, n in ((1, "offsets derived on the device"), (2, "4-bit dictionary qualities"), (8, "2-bit bases + exception list"), (4, "sparse SA fields")) if pinned.layout_flags & bit)),
+                                    + ", ".join(n for bit, n in ((1, "offsets derived on the device"), (2, "4-bit dictionary qualities"), (16, "2-bit dictionary qualities"), (8, "2-bit bases + exception list"), (4, "sparse SA fields")) if pinned.layout_flags & bit)),
                     "mode": f"{max(1, a.lanes)} contigs in flight (one stream / host thread each, uploads serialised): the upload of step i+1 overlaps the kernels and host part of step i",
                     "one_at_a_time": {"value": bases * a.steps / (ms_e2e_seq * 1e-3), "ms_per_step": ms_e2e_seq / a.steps}},
             "gpu_launches": int(launches),

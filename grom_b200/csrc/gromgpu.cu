@@ -1192,6 +1192,26 @@ __global__ void __launch_bounds__(256) k_expand_qual(const uint8_t *__restrict__
         for (int64_t t = s0; t < n_slots; t++) qual[t] = sl[(q4[t >> 1] >> ((~t & 1) << 2)) & 15];
     }
 }
+// 2-bit dictionary-coded qualities -> one byte per base slot (16 slots per thread); padding slots are zeroed by k_seq_zero_pad
+__global__ void __launch_bounds__(256) k_expand_qual2(const uint8_t *__restrict__ q2, int64_t n_slots, QualLut lut, uint8_t *__restrict__ qual)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, s0 = g * 16;
+    if (s0 >= n_slots) return;
+    const uint32_t l0 = lut.v[0], l1 = lut.v[1], l2 = lut.v[2], l3 = lut.v[3];
+    auto dec = [&](uint32_t c) { return c == 0 ? l0 : c == 1 ? l1 : c == 2 ? l2 : l3; };
+    if (s0 + 16 <= n_slots) {
+        const uint32_t w = *reinterpret_cast<const uint32_t *>(q2 + (s0 >> 2));
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t b = (w >> (8 * k)) & 0xff;                                  // four slots, first in the top bits
+            o[k] = dec(b >> 6) | (dec((b >> 4) & 3) << 8) | (dec((b >> 2) & 3) << 16) | (dec(b & 3) << 24);
+        }
+        *reinterpret_cast<uint4 *>(qual + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int64_t t = s0; t < n_slots; t++) qual[t] = (uint8_t)dec((q2[t >> 2] >> ((~t & 3) << 1)) & 3);
+    }
+}
 // 2-bit bases -> BAM nibbles (16 slots per thread), exceptions (non-ACGT codes) patched in, padding slots of every read zeroed
 __global__ void __launch_bounds__(256) k_expand_seq(const uint8_t *__restrict__ s2, int64_t n_slots, uint8_t *__restrict__ seq4)
 {
@@ -1231,13 +1251,16 @@ __global__ void __launch_bounds__(256) k_seq_exceptions(const uint64_t *__restri
     atomicAnd(w, ~(15u << sh));
     atomicOr(w, ((unsigned)code[k] & 15u) << sh);
 }
-__global__ void __launch_bounds__(256) k_seq_zero_pad(const int32_t *__restrict__ l_qseq, const uint64_t *__restrict__ base_off, int64_t n, uint8_t *__restrict__ seq4)
+__global__ void __launch_bounds__(256) k_seq_zero_pad(const int32_t *__restrict__ l_qseq, const uint64_t *__restrict__ base_off, int64_t n, uint8_t *__restrict__ seq4,
+                                                      uint8_t *__restrict__ qual)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t b = base_off[i], e = b + pad_slots(l_qseq[i]);
     uint64_t s = b + (uint64_t)max(l_qseq[i], 0);
-    if (s < e && (s & 1)) { seq4[s >> 1] &= 0xf0; s++; }                               // this read owns every slot of [b, e)
+    if (qual) for (uint64_t t = s; t < e; t++) qual[t] = 0;                            // this read owns every slot of [b, e)
+    if (!seq4) return;
+    if (s < e && (s & 1)) { seq4[s >> 1] &= 0xf0; s++; }
     for (; s < e; s += 2) seq4[s >> 1] = 0;
 }
 // sparse first-SA-entry fields -> dense per-read arrays (already preset to "none")
@@ -1271,7 +1294,7 @@ struct DevBuf {
 
 enum { B_POS, B_MPOS, B_TLEN, B_MTID, B_LQSEQ, B_FLAG, B_NCIGAR, B_MAPQ, B_QLEN, B_HASH, B_CIGOFF, B_BASEOFF, B_CIGAR, B_SEQ4, B_QUAL,
        B_SAPOS, B_SASADJ, B_SAEADJ, B_SAINDEL, B_SASTRAND, B_SAMAPQ, B_SASAME, B_COUNT,
-       B_QUAL4 = B_COUNT, B_SATMP, B_OFFTMP, B_SEQ2, B_ALL };      // the last four: staging of the transport-compact forms
+       B_QUAL4 = B_COUNT, B_SATMP, B_OFFTMP, B_SEQ2, B_ALL };     // B_QUAL4 also stages qual2      // the last four: staging of the transport-compact forms
 
 struct CnvState;
 static void cnv_state_free(CnvState *c);
@@ -1454,13 +1477,13 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
     if (b->pos[0] < h->last_pos) return fail("gromgpu_push_reads: reads are not in coordinate order");
     if ((h->n_cigar + b->n_cigar_total) > 0xffffffffLL) return fail("gromgpu_push_reads: more than 2^32 CIGAR operations on one chromosome");
     const int lay = b->layout_flags;
-    const bool lay_off = lay & GROM_LAYOUT_CANONICAL_OFFSETS, lay_q4 = (lay & GROM_LAYOUT_QUAL4) && b->qual4, lay_sa = (lay & GROM_LAYOUT_SPARSE_SA) != 0,
+    const bool lay_off = lay & GROM_LAYOUT_CANONICAL_OFFSETS, lay_q2 = (lay & GROM_LAYOUT_QUAL2) && b->qual2, lay_q4 = !lay_q2 && (lay & GROM_LAYOUT_QUAL4) && b->qual4, lay_sa = (lay & GROM_LAYOUT_SPARSE_SA) != 0,
                lay_s2 = (lay & GROM_LAYOUT_SEQ2) && b->seq2;
     if (!lay_s2 && !b->seq4) return fail("gromgpu_push_reads: bases missing");
     if (lay_s2 && (b->n_seq_exc < 0 || (b->n_seq_exc && (!b->seq_exc_slot || !b->seq_exc_code)))) return fail("gromgpu_push_reads: bad base exception list");
     if (!lay_sa && !b->sa_pos) return fail("gromgpu_push_reads: SA arrays missing");
     if (!lay_off && (!b->cigar_off || !b->base_off)) return fail("gromgpu_push_reads: offset arrays missing (and GROM_LAYOUT_CANONICAL_OFFSETS not set)");
-    if (!lay_q4 && !b->qual) return fail("gromgpu_push_reads: qualities missing");
+    if (!lay_q4 && !lay_q2 && !b->qual) return fail("gromgpu_push_reads: qualities missing");
     if (lay_sa && (b->n_sa < 0 || b->n_sa > n || (b->n_sa && !b->sa_index))) return fail("gromgpu_push_reads: bad sparse SA list");
     // src == nullptr: the array is rebuilt on the device from a transport-compact form (below)
     struct { int id; const void *src; size_t elt; int64_t cnt, have; } f[B_COUNT] = {
@@ -1469,7 +1492,7 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
         { B_NCIGAR, b->n_cigar, 2, n, h->n_reads }, { B_MAPQ, b->mapq, 1, n, h->n_reads }, { B_QLEN, b->qname_len, 1, n, h->n_reads },
         { B_HASH, b->qname_hash, 8, n, h->n_reads }, { B_CIGOFF, lay_off ? nullptr : b->cigar_off, 8, n, h->n_reads }, { B_BASEOFF, lay_off ? nullptr : b->base_off, 8, n, h->n_reads },
         { B_CIGAR, b->cigar, 4, b->n_cigar_total, h->n_cigar }, { B_SEQ4, lay_s2 ? nullptr : b->seq4, 1, (b->n_base_slots + 1) / 2, h->n_slots / 2 },
-        { B_QUAL, lay_q4 ? nullptr : b->qual, 1, b->n_base_slots, h->n_slots },
+        { B_QUAL, (lay_q4 || lay_q2) ? nullptr : b->qual, 1, b->n_base_slots, h->n_slots },
         { B_SAPOS, lay_sa ? nullptr : b->sa_pos, 4, n, h->n_reads }, { B_SASADJ, lay_sa ? nullptr : b->sa_start_adj, 4, n, h->n_reads }, { B_SAEADJ, lay_sa ? nullptr : b->sa_end_adj, 4, n, h->n_reads },
         { B_SAINDEL, lay_sa ? nullptr : b->sa_end_adj_indel, 4, n, h->n_reads }, { B_SASTRAND, lay_sa ? nullptr : b->sa_strand, 1, n, h->n_reads }, { B_SAMAPQ, lay_sa ? nullptr : b->sa_mapq, 2, n, h->n_reads },
         { B_SASAME, lay_sa ? nullptr : b->sa_same_chr, 1, n, h->n_reads } };
@@ -1530,9 +1553,20 @@ extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
             if (upload(d_slot, b->seq_exc_slot, ne * 8) || upload(d_code, b->seq_exc_code, ne)) return -1;
             k_seq_exceptions<<<(unsigned)((ne + 255) / 256), 256, 0, h->stream>>>(d_slot, d_code, (int64_t)ne, b->n_base_slots, d_seq);
         }
-        // offsets of this push relative to its own first slot: the canonical ones minus slot_base (already added above)
+    }
+    if (lay_q2 && b->n_base_slots) {
+        DevBuf &t = h->rb[B_QUAL4];
+        const size_t nb = (size_t)(b->n_base_slots + 3) / 4;
+        if (t.ensure(nb + 64, h->stream)) return -1;
+        if (upload(t.p, b->qual2, nb)) return -1;
+        QualLut lut; memcpy(lut.v, b->qual_lut, 16);
+        k_expand_qual2<<<(unsigned)((b->n_base_slots + 16 * 256 - 1) / (16 * 256)), 256, 0, h->stream>>>((const uint8_t *)t.p, b->n_base_slots, lut, (uint8_t *)h->rb[B_QUAL].p + h->n_slots);
+        CK(cudaGetLastError());
+    }
+    if ((lay_s2 || lay_q2) && b->n_base_slots) {
+        // padding slots of every read back to 0 like in the canonical arrays (offsets are absolute by now)
         k_seq_zero_pad<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((const int32_t *)h->rb[B_LQSEQ].p + h->n_reads, (const uint64_t *)h->rb[B_BASEOFF].p + h->n_reads, n,
-                                                                            (uint8_t *)h->rb[B_SEQ4].p);
+                                                                            lay_s2 ? (uint8_t *)h->rb[B_SEQ4].p : nullptr, lay_q2 ? (uint8_t *)h->rb[B_QUAL].p : nullptr);
         CK(cudaGetLastError());
     }
     if (lay_sa) {

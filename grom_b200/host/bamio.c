@@ -175,7 +175,7 @@ struct grom_batch {
     uint64_t *qname_hash, *cigar_off, *base_off, *qname_off;
     uint32_t *cigar; uint8_t *seq4, *qual; char *qname_pool;
     /* transport-compact forms (grom_reads.h GROM_LAYOUT_*), built once the canonical arrays are filled */
-    uint8_t *seq2, *seq_exc_code; uint64_t *seq_exc_slot;
+    uint8_t *seq2, *seq_exc_code, *qual2; uint64_t *seq_exc_slot;
     uint8_t *qual4; int32_t *sa_index, *sas_pos, *sas_start_adj, *sas_end_adj, *sas_end_adj_indel; int16_t *sas_mapq; uint8_t *sas_strand, *sas_same_chr;
 };
 
@@ -189,7 +189,7 @@ void gromhost_batch_free(grom_batch *t)
     free(t->sa_mapq); free(t->mapq); free(t->qname_len); free(t->sa_strand); free(t->sa_same_chr);
     free(t->qname_hash); free(t->cigar_off); free(t->base_off); free(t->qname_off); free(t->cigar);
     free(t->seq4); free(t->qual); free(t->qname_pool);
-    free(t->seq2); free(t->seq_exc_code); free(t->seq_exc_slot);
+    free(t->seq2); free(t->seq_exc_code); free(t->seq_exc_slot); free(t->qual2);
     free(t->qual4); free(t->sa_index); free(t->sas_pos); free(t->sas_start_adj); free(t->sas_end_adj); free(t->sas_end_adj_indel);
     free(t->sas_mapq); free(t->sas_strand); free(t->sas_same_chr); free(t);
 }
@@ -202,19 +202,39 @@ static void batch_compact(grom_batch *t, int n_threads)
     grom_read_batch *v = &t->v;
     const int64_t n = v->n_reads, ns = v->n_base_slots;
     int flags = GROM_LAYOUT_CANONICAL_OFFSETS;
-    if (ns > 0 && (ns & 1) == 0) {
+    if (ns > 0 && (ns & 3) == 0) {
+        /* distinct qualities of the bases (padding slots aside): <= 4 -> 2 bits per slot, <= 16 -> 4 bits, else the bytes travel */
         int64_t hist[256]; memset(hist, 0, sizeof(hist));
         #pragma omp parallel num_threads(n_threads)
         {
             int64_t h[256]; memset(h, 0, sizeof(h));
             #pragma omp for schedule(static) nowait
-            for (int64_t s = 0; s < ns; s++) h[t->qual[s]]++;
+            for (int64_t i = 0; i < n; i++) { const uint8_t *q = t->qual + t->base_off[i]; const int lq = t->l_qseq[i]; for (int k = 0; k < lq; k++) h[q[k]]++; }
             #pragma omp critical
             for (int k = 0; k < 256; k++) hist[k] += h[k];
         }
         int nv = 0; uint8_t inv[256]; memset(inv, 0, sizeof(inv));
         for (int k = 0; k < 256; k++) if (hist[k]) { if (nv < 16) { v->qual_lut[nv] = (uint8_t)k; inv[k] = (uint8_t)nv; } nv++; }
-        if (nv <= 16 && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
+        if (nv >= 1 && nv <= 4 && (t->qual2 = (uint8_t *)calloc((size_t)(ns / 4 + 16), 1))) {
+            #pragma omp parallel for schedule(static) num_threads(n_threads)
+            for (int64_t i = 0; i < n; i++) {
+                const uint64_t b0 = t->base_off[i]; const int lq = t->l_qseq[i];
+                for (int k = 0; k < lq; k++) { const uint64_t sl = b0 + (uint64_t)k; t->qual2[sl >> 2] |= (uint8_t)(inv[t->qual[sl]] << ((~sl & 3) << 1)); }
+            }
+            v->qual2 = t->qual2; flags |= GROM_LAYOUT_QUAL2;
+        } else if (nv >= 1 && nv <= 16 && !hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
+            /* 4-bit form: padding slots (0 in the canonical array) must decode to 0 as well, so 0 takes a dictionary entry */
+            if (nv == 16) { free(t->qual4); t->qual4 = NULL; memset(v->qual_lut, 0, 16); }
+            else {
+                for (int k = nv; k > 0; k--) v->qual_lut[k] = v->qual_lut[k - 1];
+                v->qual_lut[0] = 0;
+                for (int k = 0; k < 256; k++) if (hist[k]) inv[k]++;
+                inv[0] = 0;
+                #pragma omp parallel for schedule(static) num_threads(n_threads)
+                for (int64_t s = 0; s < ns; s += 2) t->qual4[s >> 1] = (uint8_t)((inv[t->qual[s]] << 4) | inv[t->qual[s + 1]]);
+                v->qual4 = t->qual4; flags |= GROM_LAYOUT_QUAL4;
+            }
+        } else if (nv >= 1 && nv <= 16 && hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
             #pragma omp parallel for schedule(static) num_threads(n_threads)
             for (int64_t s = 0; s < ns; s += 2) t->qual4[s >> 1] = (uint8_t)((inv[t->qual[s]] << 4) | inv[t->qual[s + 1]]);
             v->qual4 = t->qual4; flags |= GROM_LAYOUT_QUAL4;

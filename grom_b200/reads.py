@@ -41,10 +41,11 @@ class CReadBatch(C.Structure):
         ("sas_pos", C.c_void_p), ("sas_start_adj", C.c_void_p), ("sas_end_adj", C.c_void_p), ("sas_end_adj_indel", C.c_void_p),
         ("sas_mapq", C.c_void_p), ("sas_strand", C.c_void_p), ("sas_same_chr", C.c_void_p),
         ("seq2", C.c_void_p), ("n_seq_exc", C.c_int64), ("seq_exc_slot", C.c_void_p), ("seq_exc_code", C.c_void_p),
+        ("qual2", C.c_void_p),
     ]
 
 
-LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SPARSE_SA, LAYOUT_SEQ2 = 1, 2, 4, 8
+LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SPARSE_SA, LAYOUT_SEQ2, LAYOUT_QUAL2 = 1, 2, 4, 8, 16
 SA_FIELDS = ["sa_pos", "sa_start_adj", "sa_end_adj", "sa_end_adj_indel", "sa_strand", "sa_mapq", "sa_same_chr"]
 SA_NONE = {"sa_pos": -1, "sa_mapq": -1}         # what a read without SA / XP entry carries (everything else 0)
 
@@ -112,6 +113,7 @@ class ReadBatch:
     qual_lut: Optional[np.ndarray] = None       # uint8 [16]
     sa_index: Optional[np.ndarray] = None       # int32, reads that have an SA / XP entry
     sa_sparse: Optional[dict] = None            # SA_FIELDS -> arrays of len(sa_index)
+    qual2: Optional[np.ndarray] = None          # uint8, four base slots per byte, indices into qual_lut[0..3] (preferred over qual4)
     seq2: Optional[np.ndarray] = None           # uint8, four base slots per byte (A C G T = 0..3), first slot in the top bits
     seq_exc_slot: Optional[np.ndarray] = None   # uint64 base slots holding something other than A/C/G/T ...
     seq_exc_code: Optional[np.ndarray] = None   # uint8  ... and its BAM 4-bit code
@@ -154,6 +156,10 @@ class ReadBatch:
         c.layout_flags = int(self.layout_flags)
         if self.layout_flags & LAYOUT_QUAL4:
             c.qual4 = self.qual4.ctypes.data
+            for k in range(16):
+                c.qual_lut[k] = int(self.qual_lut[k])
+        if self.layout_flags & LAYOUT_QUAL2:
+            c.qual2 = self.qual2.ctypes.data
             for k in range(16):
                 c.qual_lut[k] = int(self.qual_lut[k])
         if self.layout_flags & LAYOUT_SEQ2:
@@ -210,22 +216,34 @@ class ReadBatch:
         flags = 0
         if self.has_canonical_offsets():
             flags |= LAYOUT_CANONICAL_OFFSETS
+        owned = None
+        if (flags & LAYOUT_CANONICAL_OFFSETS) and self.qual.size and self.qual.size % 4 == 0:
+            ns = self.qual.size
+            lq = self.l_qseq.astype(np.int64)
+            owned = np.zeros(ns + 1, dtype=np.int32)                    # slots below l_qseq of their read (the rest is padding)
+            np.add.at(owned, self.base_off.astype(np.int64), 1); np.add.at(owned, self.base_off.astype(np.int64) + lq, -1)
+            owned = np.cumsum(owned[:-1]) > 0
         vals = np.flatnonzero(np.bincount(self.qual, minlength=256)).astype(np.uint8) if self.qual.size else np.zeros(0, np.uint8)
-        if 0 < vals.size <= 16 and self.qual.size % 2 == 0:
+        base_vals = np.flatnonzero(np.bincount(self.qual[owned], minlength=256)).astype(np.uint8) if owned is not None else vals
+        if owned is not None and 0 < base_vals.size <= 4:
+            # <= 4 distinct qualities on the bases themselves (padding aside): 2 bits per slot; the device zeroes the padding again
+            lut = np.zeros(16, dtype=np.uint8); lut[:base_vals.size] = base_vals
+            inv = np.zeros(256, dtype=np.uint8); inv[base_vals] = np.arange(base_vals.size, dtype=np.uint8)
+            code = np.where(owned, inv[self.qual], 0).astype(np.uint8)
+            self.qual2 = np.ascontiguousarray((code[0::4] << 6) | (code[1::4] << 4) | (code[2::4] << 2) | code[3::4])
+            self.qual_lut = lut
+            flags |= LAYOUT_QUAL2
+        elif 0 < vals.size <= 16 and self.qual.size % 2 == 0:
             lut = np.zeros(16, dtype=np.uint8); lut[:vals.size] = vals
             inv = np.zeros(256, dtype=np.uint8); inv[vals] = np.arange(vals.size, dtype=np.uint8)
             code = inv[self.qual]
             self.qual4 = np.ascontiguousarray((code[0::2] << 4) | code[1::2])
             self.qual_lut = lut
             flags |= LAYOUT_QUAL4
-        if (flags & LAYOUT_CANONICAL_OFFSETS) and self.qual.size and self.qual.size % 4 == 0:
+        if owned is not None:
             ns = self.qual.size
             slot = np.arange(ns, dtype=np.int64)
             code = (self.seq4[slot >> 1] >> ((~slot & 1) << 2)) & 15
-            lq = self.l_qseq.astype(np.int64)
-            owned = np.zeros(ns + 1, dtype=np.int32)                    # slots below l_qseq of their read (the rest is padding)
-            np.add.at(owned, self.base_off.astype(np.int64), 1); np.add.at(owned, self.base_off.astype(np.int64) + lq, -1)
-            owned = np.cumsum(owned[:-1]) > 0
             two_of = np.full(16, 255, dtype=np.uint8); two_of[[1, 2, 4, 8]] = [0, 1, 2, 3]
             two = two_of[code]
             exc = owned & (two == 255)
@@ -250,14 +268,16 @@ class ReadBatch:
         skip = set()
         if f & LAYOUT_CANONICAL_OFFSETS:
             skip |= {"cigar_off", "base_off"}
-        if f & LAYOUT_QUAL4:
+        if f & (LAYOUT_QUAL4 | LAYOUT_QUAL2):
             skip.add("qual")
         if f & LAYOUT_SEQ2:
             skip.add("seq4")
         if f & LAYOUT_SPARSE_SA:
             skip |= set(SA_FIELDS)
         n = sum(getattr(self, k).nbytes for k in _DTYPES if k not in skip)
-        if f & LAYOUT_QUAL4:
+        if f & LAYOUT_QUAL2:
+            n += self.qual2.nbytes
+        elif f & LAYOUT_QUAL4:
             n += self.qual4.nbytes
         if f & LAYOUT_SEQ2:
             n += self.seq2.nbytes + self.seq_exc_slot.nbytes + self.seq_exc_code.nbytes
@@ -321,6 +341,9 @@ def batch_from_c(view: CReadBatch, keep_names: bool) -> ReadBatch:
     b.layout_flags = int(view.layout_flags)
     if view.layout_flags & LAYOUT_QUAL4:
         b.qual4 = arr(view.qual4, np.uint8, view.n_base_slots // 2)
+        b.qual_lut = np.array(list(view.qual_lut), dtype=np.uint8)
+    if view.layout_flags & LAYOUT_QUAL2:
+        b.qual2 = arr(view.qual2, np.uint8, view.n_base_slots // 4)
         b.qual_lut = np.array(list(view.qual_lut), dtype=np.uint8)
     if view.layout_flags & LAYOUT_SEQ2:
         b.seq2 = arr(view.seq2, np.uint8, view.n_base_slots // 4)

@@ -73,7 +73,7 @@ typedef struct grom_read_batch {
     const char     *qname_pool;
     /* ---- transport-compact forms (read only when the matching layout_flags bit is set).  They carry the same information
      * in fewer bytes across PCIe; the CUDA library rebuilds the canonical device arrays from them (bit-identical), so
-     * nothing downstream changes.  319 -> 163 bytes per 150 bp read with all four. */
+     * nothing downstream changes.  319 -> 163 bytes per 150 bp read with offsets + qual4 + seq2 + sparse SA, 123 with qual2. */
     const uint8_t  *qual4;      /* GROM_LAYOUT_QUAL4: per base slot a 4-bit index into qual_lut, nibble order of seq4
                                    (usable when the batch holds <= 16 distinct quality values); qual may then be NULL */
     uint8_t         qual_lut[16];
@@ -88,6 +88,9 @@ typedef struct grom_read_batch {
     int64_t         n_seq_exc;
     const uint64_t *seq_exc_slot;   /* [n_seq_exc] base slot (same index space as base_off) */
     const uint8_t  *seq_exc_code;   /* [n_seq_exc] BAM 4-bit code */
+    const uint8_t  *qual2;      /* GROM_LAYOUT_QUAL2: like qual4 with 2-bit indices into qual_lut[0..3], slot s in byte s>>2 at bits ((~s&3)<<1)
+                                   (usable when the bases of the batch -- padding slots aside -- carry <= 4 distinct qualities, e.g. the four
+                                   bins of current Illumina instruments); padding slots become 0 on the device.  Preferred over qual4 */
 } grom_read_batch;
 
 /* GROM_LAYOUT_CANONICAL_OFFSETS: cigar_off[i] = sum of n_cigar[0..i) and base_off[i] = sum of l_qseq[0..i) each rounded up to
@@ -96,6 +99,7 @@ typedef struct grom_read_batch {
 #define GROM_LAYOUT_QUAL4             2
 #define GROM_LAYOUT_SPARSE_SA         4
 #define GROM_LAYOUT_SEQ2              8
+#define GROM_LAYOUT_QUAL2            16
 
 static inline uint64_t grom_qname_hash(const char *s, int len)
 {

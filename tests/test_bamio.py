@@ -5,7 +5,7 @@ import numpy as np
 
 from util import GOLDEN, golden_batches
 from grom_b200 import hostlib
-from grom_b200.reads import LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SEQ2, LAYOUT_SPARSE_SA, SA_FIELDS, _DTYPES, fnv1a64
+from grom_b200.reads import LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL2, LAYOUT_QUAL4, LAYOUT_SEQ2, LAYOUT_SPARSE_SA, SA_FIELDS, _DTYPES, fnv1a64
 from tools import synth
 
 
@@ -28,17 +28,17 @@ def test_roundtrip_all_fields(tmp_path):
             assert np.all(r.base_off % 32 == 0)
             assert (r.sa_pos >= 0).sum() > 0
             # the batcher also hands over the transport-compact forms (grom_reads.h GROM_LAYOUT_*): they decode to its canonical arrays
-            assert r.layout_flags == LAYOUT_CANONICAL_OFFSETS | LAYOUT_QUAL4 | LAYOUT_SPARSE_SA | LAYOUT_SEQ2 and r.has_canonical_offsets()
+            assert r.layout_flags == LAYOUT_CANONICAL_OFFSETS | LAYOUT_QUAL2 | LAYOUT_SPARSE_SA | LAYOUT_SEQ2 and r.has_canonical_offsets()
             slot = np.arange(r.n_base_slots)
             nib = (1 << ((r.seq2[slot >> 2] >> ((~slot & 3) << 1)) & 3)).astype(np.uint8)
             nib[r.seq_exc_slot.astype(np.int64)] = r.seq_exc_code
+            dec2 = r.qual_lut[(r.qual2[slot >> 2] >> ((~slot & 3) << 1)) & 3]
             for i in range(0, r.n_reads, 53):
-                o = int(r.base_off[i]); assert np.array_equal(nib[o:o + int(r.l_qseq[i])], r.bases(i))
+                o = int(r.base_off[i]); assert np.array_equal(nib[o:o + int(r.l_qseq[i])], r.bases(i)) and np.array_equal(dec2[o:o + int(r.l_qseq[i])], r.quals(i))
             # ... and equal what the numpy side derives from the same canonical arrays
             mine = synth.slice_batch(r, 0, r.n_reads).compact()
             assert np.array_equal(mine.seq2, r.seq2) and np.array_equal(mine.seq_exc_slot, r.seq_exc_slot) and np.array_equal(mine.seq_exc_code, r.seq_exc_code)
-            assert np.array_equal(mine.qual4, r.qual4) and np.array_equal(mine.qual_lut, r.qual_lut) and np.array_equal(mine.sa_index, r.sa_index)
-            assert np.array_equal(r.qual_lut[(r.qual4[slot >> 1] >> ((~slot & 1) << 2)) & 15], r.qual)
+            assert np.array_equal(mine.qual2, r.qual2) and np.array_equal(mine.qual_lut, r.qual_lut) and np.array_equal(mine.sa_index, r.sa_index)
             assert np.array_equal(r.sa_index, np.flatnonzero(r.sa_pos != -1))
             for k in SA_FIELDS:
                 assert np.array_equal(r.sa_sparse[k], getattr(r, k)[r.sa_index]), k

@@ -126,31 +126,36 @@ def test_multi_push_equals_single_push():
 
 
 def test_transport_compact_forms_equal_canonical_upload():
-    """include/grom_reads.h GROM_LAYOUT_*: offsets derived on the device, 4-bit dictionary qualities, 2-bit bases with an exception list, sparse SA fields --
+    """include/grom_reads.h GROM_LAYOUT_*: offsets derived on the device, 2-bit / 4-bit dictionary qualities, 2-bit bases with an exception list, sparse SA fields --
     pushed whole and in slices -- give the oracle's arrays, flags, candidates and events like the canonical arrays do."""
-    from grom_b200.reads import LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL4, LAYOUT_SEQ2, LAYOUT_SPARSE_SA
-    from test_reads_compact import plant_non_acgt
+    from grom_b200.reads import LAYOUT_CANONICAL_OFFSETS, LAYOUT_QUAL2, LAYOUT_QUAL4, LAYOUT_SEQ2, LAYOUT_SPARSE_SA
+    from test_reads_compact import more_qualities, plant_non_acgt
     spec = synth.SynthSpec(contigs=[("chrA", 200_000)], depth=25, seed=17, dup_frac=0.05, clip_frac=0.04, hardclip_frac=0.01, refskip_frac=0.003,
                            disc_frac=0.03, sa_frac=0.8, munmap_frac=0.01, sv_sites_per_mb=10)
     c = synth.simulate(spec)[0]
     hez, mq = tables()
     prm = Params.default(insert_min=170, insert_max=520, rmdup=1)
     b = plant_non_acgt(c.batch.repack_canonical(), n_runs=2000).compact()
-    assert b.layout_flags == LAYOUT_CANONICAL_OFFSETS | LAYOUT_QUAL4 | LAYOUT_SPARSE_SA | LAYOUT_SEQ2
+    assert b.layout_flags == LAYOUT_CANONICAL_OFFSETS | LAYOUT_QUAL2 | LAYOUT_SPARSE_SA | LAYOUT_SEQ2
     assert 0 < len(b.sa_index) < b.n_reads and len(b.seq_exc_slot) > 5000
     check_against_oracle(prm, b, c.chars, hez, mq)
     n = b.n_reads
     cuts = [0, n // 7, n // 7 + 3, n // 2, n]
     slices = [synth.slice_batch(c.batch, a, e).compact() for a, e in zip(cuts[:-1], cuts[1:])]
-    slices[2].layout_flags &= ~LAYOUT_QUAL4                       # mixed forms across pushes
+    slices[2].layout_flags &= ~LAYOUT_QUAL2                       # mixed forms across pushes
     slices[3].layout_flags &= ~LAYOUT_SEQ2
     slices[1].layout_flags = 0
     check_against_oracle(prm, c.batch, c.chars, hez, mq, slices=slices)
+    # nine distinct qualities: the 4-bit dictionary
+    c.batch.layout_flags = 0; c.batch.qual2 = None
+    b4 = more_qualities(c.batch).compact()
+    assert (b4.layout_flags & LAYOUT_QUAL4) and not (b4.layout_flags & LAYOUT_QUAL2)
+    check_against_oracle(prm, b4, c.chars, hez, mq)
     # more than 16 distinct qualities: the dictionary form is not offered, the rest still is
-    c.batch.layout_flags = 0
+    c.batch.layout_flags = 0; c.batch.qual4 = None
     c.batch.qual[: 40] = np.arange(40, dtype=np.uint8) + 2
     b2 = c.batch.compact()
-    assert not (b2.layout_flags & LAYOUT_QUAL4) and (b2.layout_flags & LAYOUT_SPARSE_SA)
+    assert not (b2.layout_flags & (LAYOUT_QUAL4 | LAYOUT_QUAL2)) and (b2.layout_flags & LAYOUT_SPARSE_SA)
     check_against_oracle(prm, b2, c.chars, hez, mq)
 
 
