@@ -1195,21 +1195,19 @@ __global__ void __launch_bounds__(256) k_expand_qual(const uint8_t *__restrict__
 // 2-bit dictionary-coded qualities -> one byte per base slot (16 slots per thread); padding slots are zeroed by k_seq_zero_pad
 __global__ void __launch_bounds__(256) k_expand_qual2(const uint8_t *__restrict__ q2, int64_t n_slots, QualLut lut, uint8_t *__restrict__ qual)
 {
+    __shared__ uint32_t four[256];                                                    // one source byte (four slots, first in the top bits) -> four quality bytes
+    {
+        const uint32_t b = threadIdx.x;
+        four[b] = (uint32_t)lut.v[b >> 6] | ((uint32_t)lut.v[(b >> 4) & 3] << 8) | ((uint32_t)lut.v[(b >> 2) & 3] << 16) | ((uint32_t)lut.v[b & 3] << 24);
+    }
+    __syncthreads();
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, s0 = g * 16;
     if (s0 >= n_slots) return;
-    const uint32_t l0 = lut.v[0], l1 = lut.v[1], l2 = lut.v[2], l3 = lut.v[3];
-    auto dec = [&](uint32_t c) { return c == 0 ? l0 : c == 1 ? l1 : c == 2 ? l2 : l3; };
     if (s0 + 16 <= n_slots) {
         const uint32_t w = *reinterpret_cast<const uint32_t *>(q2 + (s0 >> 2));
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t b = (w >> (8 * k)) & 0xff;                                  // four slots, first in the top bits
-            o[k] = dec(b >> 6) | (dec((b >> 4) & 3) << 8) | (dec((b >> 2) & 3) << 16) | (dec(b & 3) << 24);
-        }
-        *reinterpret_cast<uint4 *>(qual + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(qual + s0) = make_uint4(four[w & 0xff], four[(w >> 8) & 0xff], four[(w >> 16) & 0xff], four[w >> 24]);
     } else {
-        for (int64_t t = s0; t < n_slots; t++) qual[t] = (uint8_t)dec((q2[t >> 2] >> ((~t & 3) << 1)) & 3);
+        for (int64_t t = s0; t < n_slots; t++) qual[t] = lut.v[(q2[t >> 2] >> ((~t & 3) << 1)) & 3];
     }
 }
 // 2-bit bases -> BAM nibbles (16 slots per thread), exceptions (non-ACGT codes) patched in, padding slots of every read zeroed
@@ -1258,7 +1256,12 @@ __global__ void __launch_bounds__(256) k_seq_zero_pad(const int32_t *__restrict_
     if (i >= n) return;
     const uint64_t b = base_off[i], e = b + pad_slots(l_qseq[i]);
     uint64_t s = b + (uint64_t)max(l_qseq[i], 0);
-    if (qual) for (uint64_t t = s; t < e; t++) qual[t] = 0;                            // this read owns every slot of [b, e)
+    if (qual) {                                                                        // this read owns every slot of [b, e)
+        uint64_t t = s;
+        for (; t < e && (t & 3); t++) qual[t] = 0;
+        for (; t + 4 <= e; t += 4) *reinterpret_cast<uint32_t *>(qual + t) = 0u;
+        for (; t < e; t++) qual[t] = 0;
+    }
     if (!seq4) return;
     if (s < e && (s & 1)) { seq4[s >> 1] &= 0xf0; s++; }
     for (; s < e; s += 2) seq4[s >> 1] = 0;
