@@ -14,7 +14,7 @@ from tools import synth
 pytestmark = pytest.mark.skipif(not po.have_reference("ref"), reason="oracle/_ref/GROM_ref not built")
 
 
-@pytest.mark.parametrize("seed,rmdup,read_len", [(31, 0, 150), (32, 1, 100)])
+@pytest.mark.parametrize("seed,rmdup,read_len", [(31, 0, 150), (32, 1, 100), (33, 1, 75), (34, 0, 250)])
 def test_live_reference_dump_parity(tmp_path, seed, rmdup, read_len):
     spec = synth.SynthSpec(contigs=[("chrQ", 120_000), ("chrR", 50_000), ("chrZ", 10_000)], depth=25, seed=seed,
                            read_len=read_len, ins_mean=3.0 * read_len, ins_sd=30, ins_floor=read_len + 20,
