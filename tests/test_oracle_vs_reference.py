@@ -14,19 +14,20 @@ from tools import synth
 pytestmark = pytest.mark.skipif(not po.have_reference("ref"), reason="oracle/_ref/GROM_ref not built")
 
 
-@pytest.mark.parametrize("seed,rmdup,read_len", [(31, 0, 150), (32, 1, 100), (33, 1, 75), (34, 0, 250)])
-def test_live_reference_dump_parity(tmp_path, seed, rmdup, read_len):
+@pytest.mark.parametrize("seed,rmdup,read_len,q,bq", [(31, 0, 150, 20, 20), (32, 1, 100, 20, 20), (33, 1, 75, 20, 20), (34, 0, 250, 20, 20),
+                                                       (35, 1, 150, 30, 26), (36, 0, 100, 4, 10)])
+def test_live_reference_dump_parity(tmp_path, seed, rmdup, read_len, q, bq):
     spec = synth.SynthSpec(contigs=[("chrQ", 120_000), ("chrR", 50_000), ("chrZ", 10_000)], depth=25, seed=seed,
                            read_len=read_len, ins_mean=3.0 * read_len, ins_sd=30, ins_floor=read_len + 20,
                            dup_frac=0.05, clip_frac=0.04, disc_frac=0.03, sa_frac=0.8, munmap_frac=0.01)
     cs = synth.simulate(spec)
     fa, bam = synth.write_dataset(str(tmp_path / "d"), cs)
     dump = str(tmp_path / "dump")
-    po.run_reference(bam, fa, str(tmp_path / "o.vcf"), args=(["-M"] if rmdup else []), dump_dir=dump)
+    po.run_reference(bam, fa, str(tmp_path / "o.vcf"), args=(["-M"] if rmdup else []) + (["-q", q, "-b", bq] if (q, bq) != (20, 20) else []), dump_dir=dump)
     m = po.read_mean_file(bam)
     prm = Params.default(insert_mean=max(m["insert_mean"], m["lseq"]), insert_min=m["insert_min"], insert_max=m["insert_max"],
-                         lseq=m["lseq"], rmdup=rmdup)
-    hez, mq = po.reference_tables(20)
+                         lseq=m["lseq"], rmdup=rmdup, min_mapq=q, rd_min_mapq=q, min_base_qual=bq)   # -q sets both, src/GROM.c:22102
+    hez, mq = po.reference_tables(q)
     vcf = [l for l in open(str(tmp_path / "o.vcf")) if not l.startswith("#")]
     with hostlib.Bam(bam) as b:
         for tid, c in enumerate(cs):
