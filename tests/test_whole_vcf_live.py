@@ -63,3 +63,27 @@ def test_whole_vcf_body_against_live_reference(tmp_path, seed, read_len, flags):
                 f = l.split("\t")
                 kinds.add(f[4] + ("/cnv" if f[8] == "SD:Z:CN:CS" else "") if f[4].startswith("<") else ("snv" if f[2] == "" else "indel"))
     assert {"snv", "indel", "<DEL>"} <= kinds and len(kinds) >= 5, kinds
+
+
+@pytest.mark.parametrize("seed,rmdup,n_contigs", [(51, 0, 3), (52, 1, 4)])
+def test_translocation_records_against_live_reference(tmp_path, seed, rmdup, n_contigs):
+    """<out>.ctx.vcf: per-contig candidate merge + filter (gromhost_ctx_contig) and genome-level mate pairing (gromhost_ctx_vcf,
+    src/GROM.c:22400-22770) on fresh data with reciprocal inter-contig clusters; three and four contigs, with and without -M."""
+    contigs = [("chrA", 300_000), ("chrB", 300_000), ("chrC", 200_000), ("chrZ", 50_000)]
+    contigs = contigs[:n_contigs - 1] + contigs[-1:]
+    spec = synth.SynthSpec(contigs=contigs, depth=30, seed=seed, sv_classes=20, disc_frac=0.005, dup_frac=0.05 if rmdup else 0.0)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "d"), cs)
+    po.run_reference(bam, fa, str(tmp_path / "o.vcf"), args=(["-M"] if rmdup else []))
+    ref = [l for l in open(str(tmp_path / "o.ctx.vcf")) if not l.startswith("#")]
+    m = po.read_mean_file(bam)
+    prm = Params.default(insert_mean=max(m["insert_mean"], m["lseq"]), insert_min=m["insert_min"], insert_max=m["insert_max"],
+                         lseq=m["lseq"], rmdup=rmdup)
+    hez, mq = po.reference_tables(20)
+    recs = []
+    with hostlib.Bam(bam) as b:
+        for tid, c in enumerate(cs):
+            r = po.run_chr(prm, b.read_target(tid), c.chars, hez, mq)
+            recs.append(hostlib.ctx_contig(prm, tid, r.sv_ev))
+    assert hostlib.ctx_vcf(prm, [c.name for c in cs], np.concatenate(recs)).splitlines(keepends=True) == ref
+    assert len(ref) >= 4 and all("SVTYPE=BND" in l for l in ref)
