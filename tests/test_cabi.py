@@ -32,6 +32,13 @@ def test_gromhost_exports_every_declared_symbol():
         assert hasattr(L, n), f"libgromhost.so does not export {n}"
 
 
+def test_integration_doc_lists_every_declared_symbol():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for header, prefix in (("gromgpu.h", "gromgpu_"), ("gromhost.h", "gromhost_")):
+        for n in _declared(header, prefix):
+            assert "`" + n + "`" in doc, f"INTEGRATION.md does not mention {n}"
+
+
 def test_params_struct_matches_header():
     # sizeof(grom_params) as the C compiler sees it == ctypes mirror
     import subprocess, tempfile
