@@ -48,11 +48,16 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="contigs in flight in the end-to-end measurement")
     ap.add_argument("--canonical-upload", action="store_true", help="upload the canonical arrays only (no transport-compact forms)")
+    ap.add_argument("--parity-mb", type=float, default=4.0, help="length of the contig (same generator) checked against the oracle after the timed loops; 0 = skip")
+    ap.add_argument("--simple", action="store_true", help="round-1 workload: single-M reads only (kernel best case; not config 3)")
+    ap.add_argument("--cnv-per-mb", type=float, default=0.25)
     return ap.parse_args()
 
 
 def workload_name(a):
-    return f"synthetic {a.depth:g}x paired-end 2x150 contig of {a.mb:g} Mb per GPU (chr20-sized), -M, SNV/indel/SV gates + read-depth CNV"
+    return (f"config 3: synthetic {a.depth:g}x paired-end 2x150 contig of {a.mb:g} Mb per GPU (chr20-sized) with every evidence class "
+            f"(soft/hard clips, SA tags, small indels, discordant pairs of all orientations, planted DEL/DUP/INV/CTX/INS clusters, "
+            f"copy-number segments, 3 % low MAPQ, 5 % PCR duplicates), -M, SNV/indel/SV gates + read-depth CNV")
 
 
 def params_for_bench():
@@ -206,8 +211,11 @@ def main_b200(a):
     hez, mq = hostlib.tables(None, prm.min_mapq)
     # synthetic chr20-sized contig of this rank (rank-specific seed); inputs (>3 GB) far exceed the 126 MB L2
     P = int(a.mb * 1e6)
-    spec = synth.SynthSpec(contigs=[(f"chr{20 + rank}", P)], depth=a.depth, seed=20 + rank, simple=True, dup_frac=0.05, names=False,
-                           simple_disc_frac=0.01)
+    from tools import workloads
+    if a.simple:
+        spec = synth.SynthSpec(contigs=[(f"chr{20 + rank}", P)], depth=a.depth, seed=20 + rank, simple=True, dup_frac=0.05, names=False, simple_disc_frac=0.01)
+    else:
+        spec = workloads.chr20_spec(mb=a.mb, depth=a.depth, seed=20 + rank, name=f"chr{20 + rank}", cnv_per_mb=a.cnv_per_mb)
     t0 = time.time()
     c = synth.simulate(spec)[0]
     gen_s = time.time() - t0
@@ -358,6 +366,37 @@ def main_b200(a):
                 traffic = tj.get("dram_bytes_per_launch_scaled_to_mb", {}).get(f"{a.mb:g}") or tj.get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        # ---- after the timed loops: the same generator at --parity-mb through the same library, every array / candidate / call against the oracle
+        parity, parity_counts, decode = "skipped", None, None
+        if a.parity_mb > 0:
+            t_p = time.time()
+            spec_p = workloads.chr20_spec(mb=a.parity_mb, depth=a.depth, seed=2020, name="chr20p", names=True, cnv_per_mb=max(a.cnv_per_mb, 0.5))
+            cp = synth.simulate(spec_p)
+            from tools import parity as parity_mod
+            try:
+                parity_counts = parity_mod.compare_gpu_oracle(prm, cp[0], hez, mq, device=local)
+                parity = "ok"
+            except AssertionError as e:
+                parity = f"FAILED: {e}"
+            parity_counts = dict(parity_counts or {}, seconds=round(time.time() - t_p, 1), contig_mb=a.parity_mb,
+                                 what="all 56 per-position arrays, -M flags, 10 breakpoint clusters, SNV / indel / SV gate records, CNV mask + z + window table + calls, bit-exact vs oracle/")
+            # ---- host batcher (BAM decode) throughput on the same data, reported separately (north star)
+            tmpd = tempfile.mkdtemp(prefix="grom_dec_")
+            try:
+                fa_p, bam_p = synth.write_dataset(os.path.join(tmpd, "p"), cp)
+                nthr = int(os.environ.get("OMP_NUM_THREADS", "0")) or (os.cpu_count() or 1)
+                best = None
+                for _ in range(3):
+                    t_d = time.perf_counter()
+                    with hostlib.Bam(bam_p) as bf:
+                        bt = bf.read_target(0)
+                    dt = time.perf_counter() - t_d
+                    best = dt if best is None else min(best, dt)
+                ab = cp[0].batch.aligned_bases()
+                decode = {"bases_per_s": ab / best, "threads": nthr, "reads_per_s": bt.n_reads / best, "bam_bytes": os.path.getsize(bam_p),
+                          "what": f"gromhost_bam_read_target (BGZF inflate + record parse + SA pre-parse -> packed SoA batch) on a {a.parity_mb:g} Mb / {a.depth:g}x BAM, best of 3"}
+            finally:
+                shutil.rmtree(tmpd, ignore_errors=True)
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             r = cpu_reference_run(a, 1, 0)
@@ -368,7 +407,7 @@ def main_b200(a):
             "warmup": max(3, a.warmup), "ms_per_step": ms_steps_max / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload_name(a), "contig_len": P, "reads_per_gpu": int(st.n_reads), "aligned_bases_per_gpu": bases,
-                       "flags": "-M (duplicate filter on), defaults otherwise", "step": "evidence + SNV/indel scan (gromgpu_chr_run) + read-depth CNV path (gromgpu_chr_cnv, incl. its host segmentation)", "discordant_pairs": "1 % (deletion-like / same-strand / mate-unmapped)", "l2": "inputs (>3 GB reads + 6.7 GB arrays per step) exceed the 126 MB L2; no flush needed",
+                       "flags": "-M (duplicate filter on), defaults otherwise", "generator": ("tools/workloads.py chr20_spec" if not a.simple else "simple (single-M reads)"), "step": "evidence + SNV/indel scan (gromgpu_chr_run) + read-depth CNV path (gromgpu_chr_cnv, incl. its host segmentation)", "l2": "inputs (>3 GB reads + 6.7 GB arrays per step) exceed the 126 MB L2; no flush needed",
                        "partition": "one contig per GPU, no data-path collective", "host_gen_s": round(gen_s, 1)},
             "e2e": {"value": total_bases * a.steps / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(read_bytes + P),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps,
@@ -381,6 +420,7 @@ def main_b200(a):
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": ms_pile},
             "kernels_ms_per_step": {**{k: v / a.steps for k, v in per.items()}, **{k: v / a.steps for k, v in cnv_ms.items()}},
             "cpu_baseline": cpu,
+            "parity_check": parity, "parity_detail": parity_counts, "decode": decode,
             "clocks": clocks,
             "results": {"snv_candidates": int(len(res.snv)), "dups": int(st.n_dups), "applied_reads": int(st.n_applied),
                         "sv_items": int(st.n_sv_items), "small_ins": int(len(res.ins)),

@@ -40,6 +40,9 @@ static int fail(const char *fmt, ...)
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return -1;
 }
+// CUDA's current device is per host thread: every entry point selects the library's device first (g_params, c_prm and the two
+// tables live on ONE device per process -- one process per GPU, like one rank of torch.distributed)
+#define ON_DEV() do { if (g_device >= 0) { cudaError_t e_ = cudaSetDevice(g_device); if (e_ != cudaSuccess) return fail("cudaSetDevice(%d) failed: %s", g_device, cudaGetErrorString(e_)); } } while (0)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 // ------------------------------------------------------------------------------------------------ globals
@@ -114,11 +117,14 @@ __device__ __forceinline__ int dup_svtype(int tid, int mtid, int pos, int mpos, 
 // key run is always kept, so "an earlier kept read with this key exists" == "an earlier read with this key
 // exists").  Reads of one position are adjacent in BAM order, so each thread scans its own short run
 // backwards.  state: 0 not applied, 1 applied, 2 duplicate.
-__global__ void __launch_bounds__(256) k_read_state(DevReads R, int tid, int first_pos, uint8_t *state)
+__global__ void __launch_bounds__(256) k_read_state(DevReads R, int tid, int first_pos, uint8_t *state, unsigned long long *bad /* [0] out of order [1] l_qseq > 65535 */)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R.n) return;
     const int pos = R.pos[i], flag = R.flag[i];
+    // input validation rides along: the pileup relies on coordinate order and keeps l_qseq in 16 bits
+    if (i > 0 && R.pos[i - 1] > pos) atomicAdd(bad, 1ull);
+    if ((unsigned)R.l_qseq[i] > 65535u) atomicAdd(bad + 1, 1ull);
     uint8_t st = 1;
     if (pos < first_pos || (flag & (F_UNMAP | F_DUP))) st = 0;
     else if (c_prm.rmdup > 0 && (flag & F_PAIRED) && !(flag & F_MUNMAP) && R.mapq[i] >= c_prm.min_mapq) {
@@ -343,7 +349,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 #endif
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) { MBAR_BACKOFF } }
-__device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ int lds_u8(uint32_t addr) { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 
 #define QCAP (CHUNK * 160)        // quality bytes per stage (64 reads of 2x150 data); the 4-bit area is half of it
 #ifndef NSTAGE
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                 const StageB B = S.b[buf][t];
                 // fast path for one staged read, hand-written so that every accumulate is a single predicated add
                 int off, qv, nib, slow;
-                asm("{\n"
+                asm volatile("{\n"
                     " .reg .pred ph, pm, pmh, ps;\n"
                     " .reg .b32 aq, as, sh, by;\n"
                     " sub.s32 %0, %10, %11;\n"                       // off = ip - pos
@@ -984,66 +990,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_inplace(int32_t *data_bas
     }
 }
 
-// ---- K2: per-position SNV gate with warp-ballot compaction (src/GROM.c:11096-11199) and the depth
-// reduction for the emission filter (src/GROM.c:15035-15043).
-__global__ void __launch_bounds__(256) k_snv_scan(const int32_t *__restrict__ arrays, const char *__restrict__ fasta, int64_t P, int64_t Ppad,
-                                                   int scan_first, int scan_last, int64_t depth_bound,
-                                                   const double *__restrict__ hez, const double *__restrict__ mqt,
-                                                   grom_snv_cand *cand, unsigned int cand_cap, unsigned int *n_cand,
-                                                   unsigned long long *depth_sum /* [0] sum [1] count */)
-{
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    bool is_cand = false;
-    grom_snv_cand c;
-    unsigned long long dsum = 0; unsigned dcnt = 0;
-    if (p < P) {
-        const char fc = fasta[p];
-        const bool is_n = (fc == 'N' || fc == 'n');
-        const int32_t *a = arrays + p;
-        if (p < depth_bound && !is_n) { dsum = (unsigned long long)((long long)a[(int64_t)GA_RD_RD * Ppad] + (long long)a[(int64_t)GA_RD_LOW * Ppad]); dcnt = 1; }
-        if (p >= scan_first && p <= scan_last && !is_n && a[(int64_t)GA_RD * Ppad] + a[(int64_t)GA_INDEL_SC_RD * Ppad] > 0) {
-            int cnt[4], total = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) { cnt[k] = a[(int64_t)(GA_SNV_A + k) * Ppad]; total += cnt[k]; }
-            const int rc4 = ref_code((unsigned char)fc);
-            const int bq_all = a[(int64_t)GA_BQ_ALL * Ppad], rc_all = a[(int64_t)GA_RC_ALL * Ppad];
-            const bool bq_ok = (double)bq_all / (double)rc_all >= c_prm.min_ave_bq;
-            const int T = c_prm.max_trials, TD = T + 1;
-            double best = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const double ratio = (double)((float)cnt[k] / (float)total);
-                if (rc4 != (1 << k) && ratio >= c_prm.min_snv_ratio && cnt[k] >= c_prm.min_snv && bq_ok) {
-                    if (!is_cand || ratio > best) {
-                        const size_t idx = (total > T) ? (size_t)T * TD + (size_t)(cnt[k] * T / total) : (size_t)total * TD + (size_t)cnt[k];
-                        c.base = k; c.ratio = ratio; c.pr = mqt[idx]; c.hez = hez[idx];
-                        best = ratio; is_cand = true;
-                    }
-                }
-            }
-            if (is_cand) {
-                c.pos = (int32_t)p; c.reserved = 0;
-#pragma unroll
-                for (int t = 0; t < GA_PILEUP_COUNT; t++) c.v[t] = a[(int64_t)t * Ppad];
-            }
-        }
-    }
-    const unsigned ball = __ballot_sync(0xffffffffu, is_cand);
-    if (ball) {
-        unsigned basei = 0;
-        if (lane == 0) basei = atomicAdd(n_cand, (unsigned)__popc(ball));
-        basei = __shfl_sync(0xffffffffu, basei, 0);
-        if (is_cand) {
-            const unsigned slot = basei + (unsigned)__popc(ball & ((1u << lane) - 1u));
-            if (slot < cand_cap) cand[slot] = c;
-        }
-    }
-    // depth reduction: warp shuffle, one atomic per warp
-    for (int d = 16; d; d >>= 1) { dsum += __shfl_xor_sync(0xffffffffu, dsum, d); dcnt += __shfl_xor_sync(0xffffffffu, dcnt, d); }
-    if (lane == 0 && dcnt) { atomicAdd(depth_sum, dsum); atomicAdd(depth_sum + 1, (unsigned long long)dcnt); }
-}
-
 // ---- K5a: GC / ACGT percentage of the triangular window (src/GROM.c:1766-1859).  count(r) = sum_{|d|<M} (M-|d|) is(r+d)
 // is a second difference of the double prefix sum of the indicator, so each CTA scans a tile + halo of the FASTA in
 // shared memory twice (S1, then S2; tile-local constants cancel in the symmetric second difference).
@@ -1329,6 +1275,9 @@ struct gromgpu_chr {
     int32_t *d_cl_int = nullptr;                     // cl_w[10] cl_rs[10] cl_re[10] cl_mchr[2] other_len[1] ins_src[3]  (36 x Ppad int32)
     double *d_cl_dist = nullptr;                     // [10][Ppad]
     int64_t n_items = 0;
+    unsigned int need_cand = 0, need_ins = 0, need_ins_pos = 0, need_del = 0, need_svev = 0; int64_t need_items = 0; int need_pool = 0;   // what the last pass asked for
+    unsigned long long *h_counts = nullptr;          // pinned landing area of the per-pass counters
+    unsigned int n_cnt[4] = {0, 0, 0, 0};            // SNV / insertion / deletion / SV-gate counts of the last pass
     std::vector<grom_snv_cand> h_cand;
     struct CnvState *cnv = nullptr;
     cudaEvent_t ev[12];
@@ -1346,6 +1295,7 @@ extern "C" int gromgpu_init(int device, const double *hez_tbl, const double *mq_
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail("gromgpu_init: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail("gromgpu_init: device %d out of range (%d devices)", device, ndev);
+    if (g_inited && device != g_device) return fail("gromgpu_init: already initialised on device %d; one device per process (tables and parameters live there)", g_device);
     CK(cudaSetDevice(device));
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail("gromgpu_init: device %d is sm_%d%d; this build targets sm_100a only", device, prop.major, prop.minor);
@@ -1381,15 +1331,17 @@ extern "C" int gromgpu_set_stream(void *s)
 extern "C" int gromgpu_stream_create(void **out)
 {
     if (!g_inited) return fail("gromgpu_stream_create: call gromgpu_init first");
+    ON_DEV();
     cudaStream_t s = nullptr;
     CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     *out = (void *)s;
     return 0;
 }
-extern "C" void gromgpu_stream_destroy(void *s) { if (s) cudaStreamDestroy((cudaStream_t)s); }
+extern "C" void gromgpu_stream_destroy(void *s) { if (s) { if (g_device >= 0) cudaSetDevice(g_device); cudaStreamDestroy((cudaStream_t)s); } }
 extern "C" int64_t gromgpu_device_free_bytes(void)
 {
     size_t fr = 0, tot = 0;
+    if (g_device >= 0) cudaSetDevice(g_device);
     return cudaMemGetInfo(&fr, &tot) == cudaSuccess ? (int64_t)fr : -1;
 }
 extern "C" int64_t gromgpu_chr_bytes_estimate(int64_t len, int64_t n_reads, int64_t n_base_slots)
@@ -1405,6 +1357,7 @@ extern "C" int gromgpu_chr_begin(gromgpu_chr **out, int tid, const char *fasta, 
 extern "C" int gromgpu_chr_begin_on(gromgpu_chr **out, int tid, const char *fasta, int64_t len, void *stream)
 {
     if (!g_inited) return fail("gromgpu_chr_begin: call gromgpu_init first");
+    ON_DEV();
     if (len <= 0 || len > 0x7fffffff) return fail("gromgpu_chr_begin: chromosome length %lld unsupported", (long long)len);
     gromgpu_chr *h = new gromgpu_chr();
     h->tid = tid; h->P = len; h->Ppad = (len + 1023) & ~(int64_t)1023; h->stream = stream ? (cudaStream_t)stream : g_stream;
@@ -1426,6 +1379,7 @@ extern "C" int gromgpu_chr_begin_on(gromgpu_chr **out, int tid, const char *fast
     CK(cudaMemsetAsync(h->d_cl_dist, 0, sizeof(double) * 10 * (size_t)h->Ppad, h->stream));
     CK(cudaMemsetAsync(h->d_arrays, 0, sizeof(int32_t) * (size_t)GA_COUNT * (size_t)h->Ppad, h->stream));
     CK(cudaMalloc(&h->d_sv_small, sizeof(int) * 8));
+    CK(cudaMallocHost(&h->h_counts, 256));
     // one slab of 50 side slots per position that ever holds a second cluster of some class: every position for small
     // contigs, at most 2 M slabs (3.2 GB) for chromosome-sized ones; exhaustion is reported as an error, never ignored
     h->pool_cap = (int)std::min<int64_t>(h->Ppad, std::max<int64_t>(h->Ppad / 32, 2 << 20));
@@ -1443,6 +1397,7 @@ extern "C" int gromgpu_chr_begin_on(gromgpu_chr **out, int tid, const char *fast
 extern "C" int gromgpu_chr_reset(gromgpu_chr *h, const char *fasta)
 {
     if (!h) return fail("gromgpu_chr_reset: null handle");
+    ON_DEV();
     if (fasta) CK(cudaMemcpyAsync(h->d_fasta, fasta, (size_t)h->P, cudaMemcpyHostToDevice, h->stream));
     for (int i = 0; i < B_COUNT; i++) h->rb[i].size = 0;
     h->n_reads = h->n_cigar = h->n_slots = 0; h->last_pos = -1; h->last_lseq = 0; h->n_leading = 0; h->ran = false;
@@ -1452,6 +1407,7 @@ extern "C" int gromgpu_chr_reset(gromgpu_chr *h, const char *fasta)
 extern "C" int gromgpu_chr_sync(gromgpu_chr *h)
 {
     if (!h) return fail("gromgpu_chr_sync: null handle");
+    ON_DEV();
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1459,6 +1415,7 @@ extern "C" int gromgpu_chr_sync(gromgpu_chr *h)
 extern "C" void gromgpu_chr_free(gromgpu_chr *h)
 {
     if (!h) return;
+    if (g_device >= 0) cudaSetDevice(g_device);
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < B_ALL; i++) h->rb[i].release();
     cudaFree(h->d_fasta); cudaFree(h->d_arrays); cudaFree(h->d_state); cudaFree(h->d_prep); cudaFree(h->d_tile_first);
@@ -1468,6 +1425,7 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
     for (int i = 0; i < 2; i++) if (h->ev_push[i]) cudaEventDestroy(h->ev_push[i]);
     cudaFree(h->d_item_cnt); cudaFree(h->d_items); cudaFree(h->d_sv_tiles); cudaFree(h->d_sv_dirty); cudaFree(h->d_sv_small); cudaFree(h->d_pool);
     cudaFree(h->d_cl_int); cudaFree(h->d_cl_dist);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
     cnv_state_free(h->cnv);
     delete h;
 }
@@ -1475,6 +1433,7 @@ extern "C" void gromgpu_chr_free(gromgpu_chr *h)
 extern "C" int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b)
 {
     if (!h || !b) return fail("gromgpu_push_reads: null argument");
+    ON_DEV();
     const int64_t n = b->n_reads;
     if (n == 0) return 0;
     if (b->pos[0] < h->last_pos) return fail("gromgpu_push_reads: reads are not in coordinate order");
@@ -1630,9 +1589,11 @@ static DevReads dev_reads(const gromgpu_chr *h)
     return R;
 }
 
-extern "C" int gromgpu_chr_run(gromgpu_chr *h)
+// One pass over everything pushed so far.  Result buffers (candidates, gate events, evidence items, listed positions) keep their
+// size from the previous run; the device counts what it would have written, and a pass that outgrew a buffer is repeated by
+// gromgpu_chr_run with larger ones (the pass resets all of its state first, so it is idempotent).
+static int chr_run_once(gromgpu_chr *h, bool *again)
 {
-    if (!h) return fail("gromgpu_chr_run: null handle");
     cudaStream_t s = h->stream;
     const int64_t n = h->n_reads, P = h->P, Ppad = h->Ppad;
     const int64_t n_tiles = (P + TILE - 1) / TILE;
@@ -1645,11 +1606,31 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
         CK(cudaMalloc(&h->d_prep, h->cap_state * sizeof(PrepRec)));
     }
     if ((size_t)n_tiles > h->cap_tiles) { cudaFree(h->d_tile_first); h->cap_tiles = (size_t)n_tiles; CK(cudaMalloc(&h->d_tile_first, sizeof(int64_t) * h->cap_tiles)); }
-    if (!h->d_cand) { h->cand_cap = 1u << 20; CK(cudaMalloc(&h->d_cand, sizeof(grom_snv_cand) * (size_t)h->cand_cap)); }
-    if (!h->d_ins) { h->ins_cap = 1u << 18; CK(cudaMalloc(&h->d_ins, sizeof(grom_ins_cand) * (size_t)h->ins_cap)); }
-    if (!h->d_ins_pos) { h->ins_pos_cap = 1u << 20; CK(cudaMalloc(&h->d_ins_pos, sizeof(int2) * (size_t)h->ins_pos_cap)); }
-    if (!h->d_del) { h->del_cap = 1u << 19; CK(cudaMalloc(&h->d_del, sizeof(grom_del_event) * (size_t)h->del_cap)); }
-    if (!h->d_svev) { h->svev_cap = (unsigned int)std::min<int64_t>(std::max<int64_t>(h->Ppad / 16, 1 << 16), 1 << 22); CK(cudaMalloc(&h->d_svev, sizeof(grom_sv_event) * (size_t)h->svev_cap)); }
+    // first sizes scale with the contig; a run that needs more is repeated with what it asked for (gromgpu_chr_run)
+    const bool tiny = getenv("GROMGPU_TEST_SMALL_BUFFERS") != nullptr;          // tests: first sizes of a few entries, so the repeat path runs
+    auto want = [&](unsigned int &cap, unsigned int &need, int64_t first) { if (!cap) cap = tiny ? 16u : (unsigned int)std::min<int64_t>(first, 1 << 30); if (need > cap) cap = (unsigned int)std::min<uint64_t>((uint64_t)need + need / 4 + 1024, 0x7fffffffu); need = 0; };
+    { const unsigned int c0 = h->cand_cap; want(h->cand_cap, h->need_cand, std::max<int64_t>(1 << 20, Ppad / 64));
+      if (h->cand_cap != c0) { cudaFree(h->d_cand); h->d_cand = nullptr; CK(cudaMalloc(&h->d_cand, sizeof(grom_snv_cand) * (size_t)h->cand_cap)); } }
+    { const unsigned int c0 = h->ins_cap; want(h->ins_cap, h->need_ins, std::max<int64_t>(1 << 18, Ppad / 256));
+      if (h->ins_cap != c0) { cudaFree(h->d_ins); h->d_ins = nullptr; CK(cudaMalloc(&h->d_ins, sizeof(grom_ins_cand) * (size_t)h->ins_cap)); } }
+    { const unsigned int c0 = h->ins_pos_cap; want(h->ins_pos_cap, h->need_ins_pos, std::max<int64_t>(1 << 20, Ppad / 32));
+      if (h->ins_pos_cap != c0) { cudaFree(h->d_ins_pos); h->d_ins_pos = nullptr; CK(cudaMalloc(&h->d_ins_pos, sizeof(int2) * (size_t)h->ins_pos_cap)); } }
+    { const unsigned int c0 = h->del_cap; want(h->del_cap, h->need_del, std::max<int64_t>(1 << 19, Ppad / 128));
+      if (h->del_cap != c0) { cudaFree(h->d_del); h->d_del = nullptr; CK(cudaMalloc(&h->d_del, sizeof(grom_del_event) * (size_t)h->del_cap)); } }
+    { const unsigned int c0 = h->svev_cap; want(h->svev_cap, h->need_svev, std::max<int64_t>(1 << 16, Ppad / 16));
+      if (h->svev_cap != c0) { cudaFree(h->d_svev); h->d_svev = nullptr; CK(cudaMalloc(&h->d_svev, sizeof(grom_sv_event) * (size_t)h->svev_cap)); } }
+    {   // evidence items: a few per discordant / clipped / indel-carrying read
+        const size_t first = tiny ? 64 : (size_t)n / 4 + 65536, need = (size_t)h->need_items + (size_t)h->need_items / 4 + 1024;
+        const size_t capw = h->need_items > (int64_t)h->cap_items ? need : (h->cap_items ? h->cap_items : first);
+        if (capw != h->cap_items) { cudaFree(h->d_items); h->d_items = nullptr; h->cap_items = capw; CK(cudaMalloc(&h->d_items, sizeof(SvItem) * h->cap_items)); }
+        h->need_items = 0;
+    }
+    if (h->need_pool > h->pool_cap) {
+        cudaFree(h->d_pool); h->d_pool = nullptr;
+        h->pool_cap = (int)std::min<int64_t>(Ppad, (int64_t)h->need_pool + h->need_pool / 4 + 1024);
+        CK(cudaMalloc(&h->d_pool, sizeof(SvOther) * SV_OTHER * (size_t)h->pool_cap));
+    }
+    h->need_pool = 0;
     const int64_t n_cnt_pad = (n + 1023) & ~(int64_t)1023;
     const int64_t n_cnt_tiles = (n_cnt_pad + SCAN_TILE - 1) / SCAN_TILE;
     if ((size_t)n_cnt_pad > h->cap_item_cnt) { cudaFree(h->d_item_cnt); h->cap_item_cnt = (size_t)n_cnt_pad + (size_t)n_cnt_pad / 8; CK(cudaMalloc(&h->d_item_cnt, sizeof(int32_t) * h->cap_item_cnt)); }
@@ -1693,13 +1674,14 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
         const int M = g_params.insert_mean;
         const size_t smem = sizeof(int) * 2 * (size_t)(GC_TILE + 2 * M + 1);
         if (smem > 200 * 1024) return fail("gromgpu_chr_run: insert_mean %d too large for the GC pre-pass tile", M);
-        CK(cudaFuncSetAttribute(k_gc_prepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        static size_t gc_smem_set = 0;                 // the attribute sticks to the function: set it only when the window grows
+        if (smem > gc_smem_set) { CK(cudaFuncSetAttribute(k_gc_prepass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); gc_smem_set = smem; }
         k_gc_prepass<<<(unsigned)((P + GC_TILE - 1) / GC_TILE), GC_THREADS, smem, s>>>(h->d_fasta, P, M, h->d_arrays + (int64_t)GA_GC * Ppad,
                                                                                        h->d_arrays + (int64_t)GA_ACGT * Ppad); launches++;
     }
     CK(cudaEventRecord(h->ev[8], s));
     const unsigned rb = (unsigned)((n + 255) / 256);
-    if (n) { k_read_state<<<rb, 256, 0, s>>>(R, h->tid, first_pos, h->d_state); launches++; }
+    if (n) { k_read_state<<<rb, 256, 0, s>>>(R, h->tid, first_pos, h->d_state, h->d_counters + 6); launches++; }
     CK(cudaEventRecord(h->ev[2], s));
     if (n) { k_read_prep<<<rb, 256, 0, s>>>(R, h->tid, P, Ppad, h->d_state, h->d_prep, h->d_arrays, h->d_max_span, h->d_counters); launches++; }
     CK(cudaEventRecord(h->ev[3], s));
@@ -1721,16 +1703,10 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
         k_sv_count<<<rb, 256, 0, s>>>(R, SA, h->tid, h->n_leading, h->d_state, P, h->d_item_cnt); launches++;
         ScanList sl0; memset(&sl0, 0, sizeof(sl0));
         k_scan_inplace<<<dim3((unsigned)n_cnt_tiles, 1), SCAN_THREADS, 0, s>>>(h->d_item_cnt, sl0, n_cnt_pad, h->d_scan_status + (size_t)n_scan_tiles * 5, h->d_ticket + 5); launches++;
-        int32_t total_items = 0;
-        CK(cudaMemcpyAsync(&total_items, h->d_item_cnt + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        h->n_items = total_items;
-        if ((size_t)total_items > h->cap_items) { cudaFree(h->d_items); h->cap_items = (size_t)total_items + (size_t)total_items / 4 + 1024; CK(cudaMalloc(&h->d_items, sizeof(SvItem) * h->cap_items)); }
-        k_sv_emit<<<rb, 256, 0, s>>>(R, SA, h->tid, h->n_leading, h->d_state, h->d_item_cnt, h->d_items, h->d_arrays, P, Ppad, h->d_sv_small); launches++;
-        if (total_items > 0) {
-            k_sv_tiles<<<(unsigned)((n_sv_tiles + 255) / 256), 256, 0, s>>>(R.pos, n, h->d_item_cnt, h->d_sv_small, n_sv_tiles, h->d_sv_tiles); launches++;
-            k_sv_apply<<<(unsigned)n_sv_tiles, SV_T, sizeof(SvTileState), s>>>(h->d_items, h->d_sv_tiles, P, Ppad, h->d_arrays, SD, h->d_sv_dirty); launches++;
-        }
+        // no round trip for the item total: the emitter stops at the buffer's end and the total is read with the other counters
+        k_sv_emit<<<rb, 256, 0, s>>>(R, SA, h->tid, h->n_leading, h->d_state, h->d_item_cnt, h->d_items, (int64_t)h->cap_items, h->d_arrays, P, Ppad, h->d_sv_small); launches++;
+        k_sv_tiles<<<(unsigned)((n_sv_tiles + 255) / 256), 256, 0, s>>>(R.pos, n, h->d_item_cnt, h->d_sv_small, n_sv_tiles, (int64_t)h->cap_items, h->d_sv_tiles); launches++;
+        k_sv_apply<<<(unsigned)n_sv_tiles, SV_T, sizeof(SvTileState), s>>>(h->d_items, h->d_sv_tiles, P, Ppad, h->d_arrays, SD, h->d_sv_dirty); launches++;
     }
     CK(cudaEventRecord(h->ev[9], s));
     {
@@ -1758,7 +1734,29 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     }
     CK(cudaEventRecord(h->ev[7], s));
     CK(cudaGetLastError());
+    // every counter of the pass in one pinned landing area
+    unsigned long long *cnt = h->h_counts;                         // [0..7] counters
+    unsigned int *ncnt = (unsigned int *)(cnt + 8);                // [0..3] candidates / events
+    int *small = (int *)(ncnt + 4);                                // [0..7] reach, pool, error, listed positions
+    int32_t *items_total = small + 8;
+    CK(cudaMemcpyAsync(cnt, h->d_counters, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ncnt, h->d_ncand, sizeof(unsigned int) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(small, h->d_sv_small, sizeof(int) * 8, cudaMemcpyDeviceToHost, s));
+    *items_total = 0;
+    if (n) CK(cudaMemcpyAsync(items_total, h->d_item_cnt + (n - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    if (cnt[6]) return fail("gromgpu_chr_run: %llu reads are out of coordinate order", cnt[6]);
+    if (cnt[7]) return fail("gromgpu_chr_run: %llu reads are longer than 65535 bases (unsupported)", cnt[7]);
+    if (*items_total < 0) return fail("gromgpu_chr_run: more than 2^31 evidence items on one chromosome");
+    h->n_items = *items_total;
+    if ((size_t)*items_total > h->cap_items) { h->need_items = *items_total; *again = true; }
+    if (ncnt[0] > h->cand_cap) { h->need_cand = ncnt[0]; *again = true; }
+    if (ncnt[1] > h->ins_cap) { h->need_ins = ncnt[1]; *again = true; }
+    if (ncnt[2] > h->del_cap) { h->need_del = ncnt[2]; *again = true; }
+    if (ncnt[3] > h->svev_cap) { h->need_svev = ncnt[3]; *again = true; }
+    if ((unsigned int)small[4] > h->ins_pos_cap) { h->need_ins_pos = (unsigned int)small[4]; *again = true; }
+    if (small[2] > h->pool_cap) { if (h->pool_cap >= Ppad) return fail("gromgpu_chr_run: other-slot pool of %d position slabs exhausted", h->pool_cap); h->need_pool = small[2]; *again = true; }
+    if (*again) return 0;
     float ms;
     gromgpu_stats &st = h->stats;
     cudaEventElapsedTime(&ms, h->ev[0], h->ev[7]); st.ms_total = ms;
@@ -1772,15 +1770,9 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]); st.ms_pileup = ms;
     st.ms_snvscan = 0.f;      // the SNV gate runs in the pileup kernel's epilogue
     st.launches = launches;
-    unsigned long long cnt[8];
-    CK(cudaMemcpy(cnt, h->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost));
-    {
-        int small[4];
-        CK(cudaMemcpy(small, h->d_sv_small, sizeof(small), cudaMemcpyDeviceToHost));
-        if (small[3] == 1) return fail("gromgpu_chr_run: other-slot pool of %d position slabs exhausted", h->pool_cap);
-        if (small[3] == 2) return fail("gromgpu_chr_run: more than %u positions with insertion evidence", h->ins_pos_cap);
-        st.n_sv_items = h->n_items; st.n_other_slabs = small[2];
-    }
+    if (small[3]) return fail("gromgpu_chr_run: device error flag %d after a pass whose buffers were large enough", small[3]);
+    st.n_sv_items = h->n_items; st.n_other_slabs = small[2];
+    h->n_cnt[0] = ncnt[0]; h->n_cnt[1] = ncnt[1]; h->n_cnt[2] = ncnt[2]; h->n_cnt[3] = ncnt[3];
     st.n_reads = n; st.n_applied = (int64_t)cnt[0]; st.n_dups = (int64_t)cnt[1]; st.aligned_bases = (int64_t)cnt[2]; st.bytes_reads = (int64_t)cnt[3];
     h->res.scan_first = scan_first; h->res.scan_last = scan_last;
     h->res.snv_ave_rd = (double)(long)cnt[4] / (double)(long)cnt[5];
@@ -1788,32 +1780,41 @@ extern "C" int gromgpu_chr_run(gromgpu_chr *h)
     return 0;
 }
 
+extern "C" int gromgpu_chr_run(gromgpu_chr *h)
+{
+    if (!h) return fail("gromgpu_chr_run: null handle");
+    ON_DEV();
+    for (int attempt = 0; attempt < 6; attempt++) {
+        bool again = false;
+        if (chr_run_once(h, &again)) return -1;
+        if (!again) return 0;
+    }
+    return fail("gromgpu_chr_run: result buffers still too small after five repeats");
+}
+
 extern "C" int gromgpu_chr_result(gromgpu_chr *h, gromgpu_result *out)
 {
     if (!h || !h->ran) return fail("gromgpu_chr_result: call gromgpu_chr_run first");
-    unsigned int nc = 0;
-    CK(cudaMemcpy(&nc, h->d_ncand, sizeof(nc), cudaMemcpyDeviceToHost));
+    ON_DEV();
+    const unsigned int nc = h->n_cnt[0];
     if (nc > h->cand_cap) return fail("gromgpu_chr_result: %u SNV candidates exceed the buffer of %u", nc, h->cand_cap);
     h->h_cand.resize(nc);
     if (nc) CK(cudaMemcpy(h->h_cand.data(), h->d_cand, sizeof(grom_snv_cand) * (size_t)nc, cudaMemcpyDeviceToHost));
     std::sort(h->h_cand.begin(), h->h_cand.end(), [](const grom_snv_cand &a, const grom_snv_cand &b) { return a.pos < b.pos; });
     h->res.n_snv = nc; h->res.snv = h->h_cand.data();
-    unsigned int ni = 0;
-    CK(cudaMemcpy(&ni, h->d_ncand + 1, sizeof(ni), cudaMemcpyDeviceToHost));
+    const unsigned int ni = h->n_cnt[1];
     if (ni > h->ins_cap) return fail("gromgpu_chr_result: %u insertion candidates exceed the buffer of %u", ni, h->ins_cap);
     h->h_ins.resize(ni);
     if (ni) CK(cudaMemcpy(h->h_ins.data(), h->d_ins, sizeof(grom_ins_cand) * (size_t)ni, cudaMemcpyDeviceToHost));
     std::sort(h->h_ins.begin(), h->h_ins.end(), [](const grom_ins_cand &a, const grom_ins_cand &b) { return a.pos < b.pos; });
     h->res.n_ins = ni; h->res.ins = h->h_ins.data();
-    unsigned int nd = 0;
-    CK(cudaMemcpy(&nd, h->d_ncand + 2, sizeof(nd), cudaMemcpyDeviceToHost));
+    const unsigned int nd = h->n_cnt[2];
     if (nd > h->del_cap) return fail("gromgpu_chr_result: %u deletion events exceed the buffer of %u", nd, h->del_cap);
     h->h_del.resize(nd);
     if (nd) CK(cudaMemcpy(h->h_del.data(), h->d_del, sizeof(grom_del_event) * (size_t)nd, cudaMemcpyDeviceToHost));
     std::sort(h->h_del.begin(), h->h_del.end(), [](const grom_del_event &a, const grom_del_event &b) { return a.pos != b.pos ? a.pos < b.pos : a.kind < b.kind; });
     h->res.n_del = nd; h->res.del_ev = h->h_del.data();
-    unsigned int ns = 0;
-    CK(cudaMemcpy(&ns, h->d_ncand + 3, sizeof(ns), cudaMemcpyDeviceToHost));
+    const unsigned int ns = h->n_cnt[3];
     if (ns > h->svev_cap) return fail("gromgpu_chr_result: %u structural-variant gate events exceed the buffer of %u", ns, h->svev_cap);
     h->h_svev.resize(ns);
     if (ns) CK(cudaMemcpy(h->h_svev.data(), h->d_svev, sizeof(grom_sv_event) * (size_t)ns, cudaMemcpyDeviceToHost));
@@ -1843,6 +1844,7 @@ extern "C" int gromgpu_chr_stats(const gromgpu_chr *h, gromgpu_stats *out)
 extern "C" int gromgpu_debug_fetch(gromgpu_chr *h, int ga, int32_t *dst, int64_t p0, int64_t p1)
 {
     if (!h || !h->ran) return fail("gromgpu_debug_fetch: call gromgpu_chr_run first");
+    ON_DEV();
     if (ga < 0 || ga >= GA_COUNT || p0 < 0 || p1 > h->P || p0 > p1) return fail("gromgpu_debug_fetch: bad array %d or range [%lld,%lld)", ga, (long long)p0, (long long)p1);
     CK(cudaMemcpy(dst, h->d_arrays + (int64_t)ga * h->Ppad + p0, sizeof(int32_t) * (size_t)(p1 - p0), cudaMemcpyDeviceToHost));
     return 0;
@@ -1851,6 +1853,7 @@ extern "C" int gromgpu_debug_fetch(gromgpu_chr *h, int ga, int32_t *dst, int64_t
 extern "C" int gromgpu_debug_fetch_cluster(gromgpu_chr *h, int what, int cls, void *dst, int64_t p0, int64_t p1)
 {
     if (!h || !h->ran) return fail("gromgpu_debug_fetch_cluster: call gromgpu_chr_run first");
+    ON_DEV();
     if (p0 < 0 || p1 > h->P || p0 > p1 || what < 0 || what > 5 || cls < 0 || cls >= 10) return fail("gromgpu_debug_fetch_cluster: bad arguments");
     const int64_t Ppad = h->Ppad; const size_t cntp = (size_t)(p1 - p0);
     if (what == 3) { CK(cudaMemcpy(dst, h->d_cl_dist + (int64_t)cls * Ppad + p0, sizeof(double) * cntp, cudaMemcpyDeviceToHost)); return 0; }
@@ -1863,6 +1866,7 @@ extern "C" int gromgpu_debug_fetch_cluster(gromgpu_chr *h, int what, int cls, vo
 extern "C" int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0, int64_t i1)
 {
     if (!h || !h->ran) return fail("gromgpu_fetch_read_state: call gromgpu_chr_run first");
+    ON_DEV();
     if (i0 < 0 || i1 > h->n_reads || i0 > i1) return fail("gromgpu_fetch_read_state: bad range");
     CK(cudaMemcpy(dst, h->d_state + i0, (size_t)(i1 - i0), cudaMemcpyDeviceToHost));
     return 0;
@@ -1885,7 +1889,7 @@ struct CnvState {
     std::vector<double> sd_tbl, wtab;
     cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, open_first, open_state;
     void *h_gather = nullptr; size_t h_gather_cap = 0;      // pinned landing area of the gathered call ranges (depth, GC byte, record per position)
-    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr;   // packed records travel to the host while the sweep runs
+    cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr, e0 = nullptr, e1 = nullptr;   // packed records travel to the host while the sweep runs
 };
 static void cnv_state_free(CnvState *c)
 {
@@ -1898,6 +1902,8 @@ static void cnv_state_free(CnvState *c)
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_z) cudaEventDestroy(c->ev_z);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->e0) cudaEventDestroy(c->e0);
+    if (c->e1) cudaEventDestroy(c->e1);
     if (c->h_rec) cudaFreeHost(c->h_rec);
     if (c->h_seed) cudaFreeHost(c->h_seed);
     if (c->h_wp) cudaFreeHost(c->h_wp);
@@ -1932,6 +1938,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
 {
     using namespace cnv;
     if (!h || !h->ran) return fail("gromgpu_chr_cnv: call gromgpu_chr_run first");
+    ON_DEV();
     if (!out || !p2s_p || !p2s_sd) return fail("gromgpu_chr_cnv: null argument");
     if (n_p2s != P2S) return fail("gromgpu_chr_cnv: the p-value table must have %d entries (got %d)", P2S, n_p2s);
     if (ploidy <= 0) return fail("gromgpu_chr_cnv: ploidy must be positive");
@@ -1952,8 +1959,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     out->bin_ave = c.bin_d.data(); out->bin_sd = c.bin_d.data() + NLIST; out->bin_del_thr = c.bin_d.data() + 2 * NLIST; out->bin_dup_thr = c.bin_d.data() + 3 * NLIST;
     out->bin_n = c.bin_n.data();
     if (hi <= lo) return 0;                                            // contig shorter than the GC window: nothing is analysed
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    if (!c.e0) { CK(cudaEventCreate(&c.e0)); CK(cudaEventCreate(&c.e1)); }
+    cudaEvent_t e0 = c.e0, e1 = c.e1;
     const auto t_begin = std::chrono::steady_clock::now();
     double ms_dev = 0;
     int n_launch = 0;
@@ -2589,7 +2596,6 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     }
     mark("copy number");
     out->n_calls = (int64_t)c.calls.size(); out->calls = c.calls.data();
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     const double ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     d2h += (int64_t)sizeof(cnv::PreOut) * n_blk + 8 * HIST_ALL + (int64_t)sizeof(RepRec) * n_rep + (int64_t)sizeof(Sample) * n_samples +
            8 * ((int64_t)seed_tot_all) + 16 * (int64_t)n_spec_all + 9 * g_total + 5 * (int64_t)rp_depth.size() + 16 * (int64_t)n_len;
@@ -2609,6 +2615,7 @@ __global__ void k_cnv_decode(const uint32_t *__restrict__ rec, const double *__r
 extern "C" int gromgpu_cnv_fetch(gromgpu_chr *h, int what, void *dst, int64_t p0, int64_t p1)
 {
     if (!h || !h->cnv || !h->cnv->d_rec) return fail("gromgpu_cnv_fetch: call gromgpu_chr_cnv first");
+    ON_DEV();
     if (p0 < 0 || p1 > h->P || p0 > p1) return fail("gromgpu_cnv_fetch: bad range");
     CnvState &c = *h->cnv;
     const int64_t n = p1 - p0;

@@ -56,6 +56,7 @@ struct SvReadArrays {                 // per-read SA fields (include/grom_reads.
 template <bool EMIT>
 struct SvEmitter {
     int32_t *arrays; int64_t P, Ppad; SvItem *out; int n;      // n = items emitted / counted so far
+    int64_t room;                                              // items the buffer still holds from `out` on (a pass that runs out is repeated)
     int max_fwd, max_bwd, pos;
     __device__ __forceinline__ void diff(int ga, int64_t lo, int64_t hi, int val)
     {
@@ -76,7 +77,7 @@ struct SvEmitter {
         if (EMIT) {
             SvItem it; it.lo = (int)lo; it.hi = (int)hi; it.x = x; it.v = v; it.mchr = mchr; it.tol = tol; it.add = add;
             it.meta = (uint32_t)cls | ((uint32_t)mode << 4) | ((uint32_t)anchor << 6) | (clipped ? SVM_CLIPPED : 0u) | extra;
-            out[n] = it;
+            if (n < room) out[n] = it;
             max_fwd = max(max_fwd, (int)hi - pos); max_bwd = max(max_bwd, pos - (int)lo);
         }
         n++;
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(256) k_sv_count(DevReads R, SvReadArrays SA, i
     if (i >= R.n) return;
     int c = 0;
     if (state[i] == 1) {
-        SvEmitter<false> em; em.arrays = nullptr; em.P = P; em.Ppad = 0; em.out = nullptr; em.n = 0; em.max_fwd = em.max_bwd = 0; em.pos = 0;
+        SvEmitter<false> em; em.arrays = nullptr; em.P = P; em.Ppad = 0; em.out = nullptr; em.n = 0; em.room = 0; em.max_fwd = em.max_bwd = 0; em.pos = 0;
         sv_read_items<false>(R, SA, i, tid, n_leading, em);
         c = em.n;
     }
@@ -293,12 +294,13 @@ __global__ void __launch_bounds__(256) k_sv_count(DevReads R, SvReadArrays SA, i
 
 // item_cnt holds the INCLUSIVE prefix sum on entry
 __global__ void __launch_bounds__(256) k_sv_emit(DevReads R, SvReadArrays SA, int tid, int64_t n_leading, const uint8_t *state, const int32_t *item_incl,
-                                                  SvItem *items, int32_t *arrays, int64_t P, int64_t Ppad, int *reach /* [0] fwd [1] bwd */)
+                                                  SvItem *items, int64_t items_cap, int32_t *arrays, int64_t P, int64_t Ppad, int *reach /* [0] fwd [1] bwd */)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int mf = 0, mb = 0;
     if (i < R.n && state[i] == 1) {
-        SvEmitter<true> em; em.arrays = arrays; em.P = P; em.Ppad = Ppad; em.out = items + (i ? item_incl[i - 1] : 0); em.n = 0; em.max_fwd = em.max_bwd = 0; em.pos = 0;
+        const int64_t first = i ? item_incl[i - 1] : 0;
+        SvEmitter<true> em; em.arrays = arrays; em.P = P; em.Ppad = Ppad; em.out = items + first; em.room = items_cap - first; em.n = 0; em.max_fwd = em.max_bwd = 0; em.pos = 0;
         sv_read_items<true>(R, SA, i, tid, n_leading, em);
         mf = em.max_fwd; mb = em.max_bwd;
     }
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(256) k_sv_emit(DevReads R, SvReadArrays SA, in
 }
 
 // per tile: slice [lo, hi) of the item list whose reads lie within reach of the tile
-__global__ void __launch_bounds__(256) k_sv_tiles(const int32_t *pos, int64_t n, const int32_t *item_incl, const int *reach, int64_t n_tiles, int2 *tile_rng)
+__global__ void __launch_bounds__(256) k_sv_tiles(const int32_t *pos, int64_t n, const int32_t *item_incl, const int *reach, int64_t n_tiles, int64_t items_cap, int2 *tile_rng)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256) k_sv_tiles(const int32_t *pos, int64_t n,
     hi = n;
     while (lo < hi) { const int64_t m = (lo + hi) >> 1; if ((int64_t)pos[m] < b) lo = m + 1; else hi = m; }
     const int64_t r1 = lo;
-    tile_rng[t] = make_int2(r0 ? item_incl[r0 - 1] : 0, r1 ? item_incl[r1 - 1] : 0);
+    tile_rng[t] = make_int2((int)min((int64_t)(r0 ? item_incl[r0 - 1] : 0), items_cap), (int)min((int64_t)(r1 ? item_incl[r1 - 1] : 0), items_cap));
 }
 
 // ---- per-position fold ----------------------------------------------------------------------------------------------

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
 
 
 _PARAMS: Optional[Params] = None
+_P2S = None                 # the caller's p-value -> sd table (gromhost_pval2sd), built once
 
 
 class GromGpuError(RuntimeError):
@@ -260,8 +261,11 @@ class Chromosome:
 
     def cnv(self, ploidy: Optional[int] = None, params=None) -> "CnvResult":
         """Read-depth CNV path (gromgpu_chr_cnv) on the depth arrays of the last run()."""
-        from . import hostlib
-        pv, sd = hostlib.pval2sd()
+        global _P2S
+        if _P2S is None:
+            from . import hostlib
+            _P2S = hostlib.pval2sd()
+        pv, sd = _P2S
         r = CCnvResult()
         params = params if params is not None else _PARAMS
         pl = ploidy if ploidy is not None else params.ploidy

@@ -137,6 +137,8 @@ def _vcf(fn_name, params, chr_name, fasta, *args):
         n = fn(C.byref(params), chr_name.encode(), fa.ctypes.data_as(C.c_char_p), *args, buf, C.c_int64(cap))
         if n >= 0:
             return buf.raw[:n].decode()
+        if n != -1 or cap > (1 << 34):                 # -1 = buffer too small; anything else is an error of the writer
+            raise RuntimeError(f"{fn_name} failed with code {n}")
         cap *= 4
 
 
@@ -258,5 +260,7 @@ def ctx_vcf(params, target_names, records: np.ndarray) -> str:
         n = L.gromhost_ctx_vcf(C.byref(params), arr, len(names), C.c_void_p(rec.ctypes.data), C.c_int64(len(rec)), buf, C.c_int64(cap))
         if n >= 0:
             return buf.raw[:n].decode()
+        if n != -1 or cap > (1 << 34):
+            raise RuntimeError(f"gromhost_ctx_vcf failed with code {n}")
         cap *= 4
         rec = np.ascontiguousarray(records, dtype=CTX_RECORD_DTYPE).copy()

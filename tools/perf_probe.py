@@ -15,12 +15,19 @@ ap.add_argument("--rmdup", type=int, default=1)
 ap.add_argument("--cnv-per-mb", type=float, default=0.0)
 ap.add_argument("--skip-e2e", type=int, default=0)
 ap.add_argument("--skip-cnv", type=int, default=0)
+ap.add_argument("--workload", default="config3", choices=["config3", "simple"], help="config3 = tools/workloads.chr20_spec (what bench.py runs)")
+ap.add_argument("--ploidy", type=int, default=2)
+ap.add_argument("--A", type=int, default=2)
 a = ap.parse_args()
 t = time.time()
-spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05, simple_disc_frac=0.01, names=False, cnv_per_mb=a.cnv_per_mb)
+if a.workload == "config3":
+    from tools import workloads
+    spec = workloads.chr20_spec(mb=a.mb, depth=a.depth, seed=20, name="chrP", cnv_per_mb=a.cnv_per_mb if a.cnv_per_mb > 0 else 0.25)
+else:
+    spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05, simple_disc_frac=0.01, names=False, cnv_per_mb=a.cnv_per_mb)
 c = synth.simulate(spec)[0]
 print("generated", c.batch.n_reads, "reads in", round(time.time() - t, 1), "s", flush=True)
-prm = Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=a.rmdup)
+prm = Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=a.rmdup, ploidy=a.ploidy, windows_sampling_factor=a.A)
 hez, mq = hostlib.tables(None, prm.min_mapq)
 gpu.init(0, hez, mq, prm)
 with gpu.Chromosome(0, c.chars) as ch:

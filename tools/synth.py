@@ -517,9 +517,7 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
             tid=tid, pos=pos, mpos=mpos, tlen=tlen, mtid=mtid, l_qseq=l_qseq, flag=flag, n_cigar=n_cigar, mapq=mapq,
             qname_len=np.full(n, 12, dtype=np.uint8), qname_hash=z, cigar_off=cigar_off.astype(np.uint64),
             base_off=(np.arange(n, dtype=np.uint64) * np.uint64(S)), cigar=cigar, seq4=_pack_nibbles(codes).reshape(-1),
-            qual=qual.reshape(-1), sa_pos=np.full(n, -1, dtype=np.int32), sa_start_adj=np.zeros(n, np.int32),
-            sa_end_adj=np.zeros(n, np.int32), sa_end_adj_indel=np.zeros(n, np.int32), sa_strand=np.zeros(n, np.uint8),
-            sa_mapq=np.full(n, -1, np.int16), sa_same_chr=np.zeros(n, np.uint8)).normalise()
+            qual=qual.reshape(-1), **_sa_arrays(n, sa_info, inv)).normalise()
         return SynthContig(name=name, chars=chars, batch=batch, truth=truth)
     base = np.char.add(f"{name}.", pair_id.astype(str))
     if not spec.simple and spec.long_name_frac > 0:
@@ -534,13 +532,7 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
     # aux
     aux_off = np.zeros(n + 1, dtype=np.uint64)
     aux_bytes = bytearray()
-    sa = dict(sa_pos=np.full(n, -1, dtype=np.int32), sa_start_adj=np.zeros(n, np.int32), sa_end_adj=np.zeros(n, np.int32),
-              sa_end_adj_indel=np.zeros(n, np.int32), sa_strand=np.zeros(n, np.uint8), sa_mapq=np.full(n, -1, np.int16),
-              sa_same_chr=np.zeros(n, np.uint8))
-    for i, v in sa_info.items():
-        j = int(inv[i])
-        sa["sa_pos"][j], sa["sa_strand"][j], sa["sa_mapq"][j], sa["sa_same_chr"][j] = v[0], v[1], v[2], v[3]
-        sa["sa_start_adj"][j], sa["sa_end_adj"][j], sa["sa_end_adj_indel"][j] = v[4], v[5], v[6]
+    sa = _sa_arrays(n, sa_info, inv)
     if aux:
         alen = np.zeros(n, dtype=np.int64)
         items = sorted(((int(inv[i]), v) for i, v in aux.items()))
@@ -556,6 +548,18 @@ def _simulate_contig(tid: int, name: str, length: int, spec: SynthSpec, n_contig
         qual=qual.reshape(-1), qname_off=qname_off, qname_pool=pool,
         aux_off=aux_off, aux_pool=np.frombuffer(bytes(aux_bytes), dtype=np.uint8).copy(), **sa).normalise()
     return SynthContig(name=name, chars=chars, batch=batch, truth=truth)
+
+
+def _sa_arrays(n: int, sa_info: Dict[int, tuple], inv: np.ndarray) -> Dict[str, np.ndarray]:
+    """the pre-parsed first SA entry per read (what the host batcher extracts from the aux block), in sorted read order"""
+    sa = dict(sa_pos=np.full(n, -1, dtype=np.int32), sa_start_adj=np.zeros(n, np.int32), sa_end_adj=np.zeros(n, np.int32),
+              sa_end_adj_indel=np.zeros(n, np.int32), sa_strand=np.zeros(n, np.uint8), sa_mapq=np.full(n, -1, np.int16),
+              sa_same_chr=np.zeros(n, np.uint8))
+    for i, v in sa_info.items():
+        j = int(inv[i])
+        sa["sa_pos"][j], sa["sa_strand"][j], sa["sa_mapq"][j], sa["sa_same_chr"][j] = v[0], v[1], v[2], v[3]
+        sa["sa_start_adj"][j], sa["sa_end_adj"][j], sa["sa_end_adj_indel"][j] = v[4], v[5], v[6]
+    return sa
 
 
 _AT_RUNS: Dict[str, Tuple[np.ndarray, np.ndarray]] = {}
