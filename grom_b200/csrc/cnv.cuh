@@ -326,8 +326,8 @@ __global__ void __launch_bounds__(256) k_z(const int32_t *__restrict__ depth, co
 }
 
 // ---- K7: window-length sweep (src/GROM.c:18967-19018).  The walk over a sample block, repeated at each -A offset without resetting
-// the running frame, is cut into frames of Lmax elements.  One warp owns one frame: 32 elements are fetched and decoded in parallel,
-// then folded into the running sum one by one in element order (the reference's summation order), so every prefix mean is bit-exact.
+// the running frame, is cut into frames of Lmax elements; every prefix mean of a frame is summed in element order (the reference's
+// summation order), so each of the 9,901 values per frame is the reference's double.
 struct SweepBlock { int64_t start, end; int64_t first_frame, n_frames; };
 __device__ __forceinline__ void sweep_advance(int &a, int64_t &p, int64_t n, int64_t s, int64_t e, int A, int Lmax)
 {
@@ -338,68 +338,128 @@ __device__ __forceinline__ void sweep_advance(int &a, int64_t &p, int64_t n, int
         n -= rem; a++; p = s + (int64_t)a * Lmax / A;
     }
 }
-__global__ void __launch_bounds__(256) k_sweep(const uint32_t *__restrict__ rec, const SweepBlock *__restrict__ blocks, int n_blocks, int64_t n_frames,
-                                               int A, int Lmin, int Lmax, int q, const double *__restrict__ p2s_sd, double *__restrict__ X)
+// One warp owns 32 consecutive frames, one lane per frame.  Per chunk of 32 elements: (A) the 32 x 32 records are fetched row by row
+// (coalesced: a row is 32 consecutive elements of one frame's walk), decoded and parked in shared memory; (B) every lane folds ITS frame's
+// 32 values into its running sum in element order -- one dependent DADD per element, the reference's summation order -- leaving the
+// prefix sums in place; (C) the tile is read back transposed: lane = window length, so the division, the square and the store of
+// X[frame][L] run in parallel over 32 lengths and the stores are coalesced rows.
+#define SWEEP_PITCH 33
+__global__ void __launch_bounds__(32) k_sweep(const uint32_t *__restrict__ rec, const SweepBlock *__restrict__ blocks, int n_blocks, int64_t n_frames,
+                                              int A, int Lmin, int Lmax, int q, const double *__restrict__ p2s_sd, const double *__restrict__ wtab_g, double *__restrict__ X)
 {
     __shared__ double sd[P2S];
-    for (int i = threadIdx.x; i < P2S; i += blockDim.x) sd[i] = p2s_sd[i];
-    __syncthreads();
-    const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (f >= n_frames) return;
-    int b = 0;
-    while (b + 1 < n_blocks && blocks[b + 1].first_frame <= f) b++;
-    const int64_t s = blocks[b].start, e = blocks[b].end;
+    __shared__ double wtab[256];
+    __shared__ double zt[32 * SWEEP_PITCH];
+    __shared__ int st_a[32], st_p[32], st_s[32], st_e[32], st_n0[32];
+    __shared__ unsigned st_um[32], st_vm[32];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < P2S; i += 32) sd[i] = p2s_sd[i];
+    for (int i = lane; i < 256; i += 32) wtab[i] = wtab_g[i];
+    const int64_t f0 = (int64_t)blockIdx.x * 32, f = f0 + lane;
+    const int n_rows = (int)min((int64_t)32, n_frames - f0);
     const int n_len = Lmax - Lmin + 1;
-    int a = 0;
-    int64_t p = s;
-    sweep_advance(a, p, (f - blocks[b].first_frame) * (int64_t)Lmax, s, e, A, Lmax);
+    // this lane's frame: block, walk state at the frame start
+    int a = A; int64_t p = 0, s = 0, e = 0;
+    if (f < n_frames) {
+        int lo_b = 0, hi_b = n_blocks - 1;                       // last block whose first frame is <= f
+        while (lo_b < hi_b) { const int m = (lo_b + hi_b + 1) >> 1; if (blocks[m].first_frame <= f) lo_b = m; else hi_b = m - 1; }
+        s = blocks[lo_b].start; e = blocks[lo_b].end; a = 0; p = s;
+        sweep_advance(a, p, (f - blocks[lo_b].first_frame) * (int64_t)Lmax, s, e, A, Lmax);
+    }
+    st_s[lane] = (int)s; st_e[lane] = (int)e;
     double tot = 0.0;
-    long long n_us = 0;
+    int n_us = 0;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    double *row = X + f * (int64_t)n_len;
     for (int w0 = 0; w0 < Lmax; w0 += 32) {
-        int la = a; int64_t lp = p;
-        sweep_advance(la, lp, lane, s, e, A, Lmax);
-        const bool valid = la < A && w0 + lane < Lmax;
-        const uint32_t r = valid ? rec[lp] : R_MASK;
-        const bool us = valid && rec_usable(r);
-        const double z = us ? rec_z(r, q, sd) : 0.0;
-        const unsigned um = __ballot_sync(0xffffffffu, us);
-        double mine = tot;
-        if (um) {
-            for (int i = 0; i < 32; i++) {
-                const double zi = __shfl_sync(0xffffffffu, z, i);
-                if ((um >> i) & 1) tot = __dadd_rn(tot, zi);
-                if (lane == i) mine = tot;
+        st_a[lane] = a; st_p[lane] = (int)p;
+        __syncwarp();
+        unsigned my_um = 0, my_vm = 0;
+        const bool in_len = w0 + lane < Lmax;
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {                           // (A) row r = frame f0 + r, this lane = element w0 + lane of its walk
+            int la = st_a[r]; int64_t lp = st_p[r];
+            sweep_advance(la, lp, lane, (int64_t)st_s[r], (int64_t)st_e[r], A, Lmax);
+            const bool valid = la < A && in_len;
+            const uint32_t rr = valid ? __ldg(rec + lp) : R_MASK;
+            const bool us = valid && rec_usable(rr);
+            double z = 0.0;
+            if (us && (rr & R_NZ)) {
+                const double wt = (rr & R_OVR) ? 1.0 : (((rr >> R_CLASS) & 3) == 0 ? wtab[(rr >> R_MQ) & 255] : 0.5);
+                z = __dmul_rn(wt, sd[(rr >> R_K) & 1023]);
+                if (rr & R_NEG) z = -z;
+            }
+            const unsigned um = __ballot_sync(0xffffffffu, us), vm = __ballot_sync(0xffffffffu, valid);
+            zt[r * SWEEP_PITCH + lane] = z;
+            if (lane == r) { my_um = um; my_vm = vm; }
+        }
+        __syncwarp();
+        const int n0 = n_us;                                      // (B) the ordered fold of this lane's frame
+        double *mine = zt + lane * SWEEP_PITCH;
+#pragma unroll
+        for (int j = 0; j < 32; j++) { if ((my_um >> j) & 1u) tot = __dadd_rn(tot, mine[j]); mine[j] = tot; }
+        n_us += __popc(my_um);
+        st_um[lane] = my_um; st_vm[lane] = my_vm; st_n0[lane] = n0;
+        __syncwarp();
+        const int w = w0 + lane + 1;                              // (C) lane = window length
+        if (w >= Lmin && w <= Lmax) {
+            const unsigned below = 0xffffffffu >> (31 - lane);
+#pragma unroll 4
+            for (int r = 0; r < n_rows; r++) {
+                const int n = st_n0[r] + __popc(st_um[r] & below);
+                double x2 = nan;
+                if (((st_vm[r] >> lane) & 1u) && n > 0) { const double x = zt[r * SWEEP_PITCH + lane] / (double)n; x2 = __dmul_rn(x, x); }
+                __stcs(X + (f0 + r) * (int64_t)n_len + (w - Lmin), x2);
             }
         }
-        const long long n_mine = n_us + __popc(um & (0xffffffffu >> (31 - lane)));
-        n_us += __popc(um);
-        const int w = w0 + lane + 1;
-        if (w >= Lmin && w <= Lmax) {
-            double x2 = nan;
-            if (valid && n_mine > 0) { const double x = mine / (double)n_mine; x2 = __dmul_rn(x, x); }
-            row[w - Lmin] = x2;
-        }
+        __syncwarp();
         sweep_advance(a, p, 32, s, e, A, Lmax);
     }
 }
-// ordered sum over the frames: one thread per window length walks the frames in order (loads batched ahead of the dependent adds)
-__global__ void __launch_bounds__(64) k_sweep_sum(const double *__restrict__ X, int64_t n_frames, int n_len, double *__restrict__ wsq, long long *__restrict__ wcnt)
+// ordered sum over the frames per window length: a CTA owns 32 lengths; all eight warps stream tiles of 64 frames x 32 lengths into a
+// four-stage shared-memory ring (8-byte async copies), warp 0 adds them in frame order (one lane per length)
+#define SSUM_FR 64
+#define SSUM_ST 4
+__global__ void __launch_bounds__(256) k_sweep_sum(const double *__restrict__ X, int64_t n_frames, int n_len, double *__restrict__ wsq, long long *__restrict__ wcnt)
 {
-    const int L = blockIdx.x * blockDim.x + threadIdx.x;
-    if (L >= n_len) return;
+    extern __shared__ __align__(16) double ssum_buf[];           // [SSUM_ST][SSUM_FR][32]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int L = blockIdx.x * 32 + lane;
+    const bool l_ok = L < n_len;
+    const int64_t n_tiles = (n_frames + SSUM_FR - 1) / SSUM_FR;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    auto issue = [&](int64_t t) {
+        if (t < n_tiles) {
+            double *dst = ssum_buf + (size_t)(t % SSUM_ST) * SSUM_FR * 32;
+#pragma unroll
+            for (int k = 0; k < SSUM_FR / 8; k++) {
+                const int row = wid + 8 * k;
+                const int64_t fr = t * SSUM_FR + row;
+                double *d = dst + row * 32 + lane;
+                if (l_ok && fr < n_frames) {
+                    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(d);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(X + fr * (int64_t)n_len + L) : "memory");
+                } else *d = nan;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int t = 0; t < SSUM_ST - 1; t++) issue(t);
     double sum = 0.0;
     long long cnt = 0;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += 32) {
-        double v[32];
+    for (int64_t t = 0; t < n_tiles; t++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(SSUM_ST - 2) : "memory");
+        __syncthreads();                                          // tile t has landed for everyone; warp 0 is done with tile t - 1
+        issue(t + SSUM_ST - 1);                                   // into the buffer tile t - 1 occupied
+        if (wid == 0) {
+            const double *src = ssum_buf + (size_t)(t % SSUM_ST) * SSUM_FR * 32 + lane;
+            double v[SSUM_FR];
 #pragma unroll
-        for (int i = 0; i < 32; i++) v[i] = f0 + i < n_frames ? __ldcs(X + (f0 + i) * (int64_t)n_len + L) : __longlong_as_double(0x7ff8000000000000LL);
+            for (int i = 0; i < SSUM_FR; i++) v[i] = src[i * 32];
 #pragma unroll
-        for (int i = 0; i < 32; i++) if (v[i] == v[i]) { sum = __dadd_rn(sum, v[i]); cnt++; }
+            for (int i = 0; i < SSUM_FR; i++) if (v[i] == v[i]) { sum = __dadd_rn(sum, v[i]); cnt++; }
+        }
     }
-    wsq[L] = sum; wcnt[L] = cnt;
+    if (wid == 0 && l_ok) { wsq[L] = sum; wcnt[L] = cnt; }
 }
 
 // ---- greedy segmentation (src/GROM.c:19361-19678 deletions, 19702-20010 duplications) --------------------------------------------

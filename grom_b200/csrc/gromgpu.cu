@@ -1309,6 +1309,7 @@ extern "C" int gromgpu_init(int device, const double *hez_tbl, const double *mq_
     g_params = *p;
     CK(cudaMemcpyToSymbol(c_prm, p, sizeof(grom_params)));
     CK(cudaFuncSetAttribute(k_pileup, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PileSmem)));
+    CK(cudaFuncSetAttribute(cnv::k_sweep_sum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SSUM_ST * SSUM_FR * 32 * sizeof(double))));
     g_device = device; g_inited = true;
     return 0;
 }
@@ -2310,8 +2311,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     CK(cudaMemcpyAsync(seed_tot, c.d_blk + 2 * c.nb, sizeof(seed_tot), cudaMemcpyDeviceToHost, s));
     if (n_frames) {
         CK(cudaMemcpyAsync(t_sw.p, sw.data(), sizeof(SweepBlock) * n_sb, cudaMemcpyHostToDevice, s));
-        k_sweep<<<(unsigned)((n_frames * 32 + 255) / 256), 256, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, t_X.as<double>()); n_launch++;
-        k_sweep_sum<<<(unsigned)((n_len + 63) / 64), 64, 0, s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>()); n_launch++;
+        k_sweep<<<(unsigned)((n_frames + 31) / 32), 32, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, T.p2s_sd + P2S, t_X.as<double>()); n_launch++;
+        k_sweep_sum<<<(unsigned)((n_len + 31) / 32), 256, SSUM_ST * SSUM_FR * 32 * sizeof(double), s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>()); n_launch++;
         CK(cudaMemcpyAsync(wsq.data(), t_wsq.p, sizeof(double) * n_len, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(wcnt.data(), t_wcnt.p, sizeof(long long) * n_len, cudaMemcpyDeviceToHost, s));
     }
