@@ -108,37 +108,82 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU baseline
+HOT_TIMERS = (0, 1, 2, 3, 4, 7, 8)      # window management, -M, evidence, per-position scan, CNV depth, CNV pre-statistics, detect_del_dup (src/GROM.c:52-65, 18210-18220)
+
+
+def bench_config(a):
+    """The `config` object of the JSON line: the workload only (identical in both arms; run details live under other keys)."""
+    return {"workload": workload_name(a), "contig_len": int(a.mb * 1e6), "depth": a.depth, "flags": "-M (duplicate filter on), defaults otherwise",
+            "generator": ("tools/workloads.py chr20_spec" if not a.simple else "simple (single-M reads)"),
+            "step": "evidence + SNV/indel/SV scan (gromgpu_chr_run) + read-depth CNV path (gromgpu_chr_cnv, incl. its host parts)",
+            "partition": "one contig per GPU, no data-path collective",
+            "l2": "inputs (>3 GB reads + 6.7 GB arrays per step) exceed the 126 MB L2; no flush needed"}
+
+
 def cpu_reference_run(a, steps: int, warmup: int):
-    """Time the reference's own implementation (oracle/_ref/GROM_ref = reference src/GROM.c built with a zlib-only
-    samtools shim) on a bounded sample: P = cores/2 contigs (+ a dummy last contig, which -P >= 2 silently skips,
-    reference src/GROM.c:20999) processed by `-P P -M`, 2 threads per process (src/GROM.c:575)."""
-    from oracle import pyoracle as po
-    from tools import synth
-    if not po.have_reference("ref"):
+    """Time the reference's own implementation (oracle/_ref/GROM_ref_timing = reference src/GROM.c built with its own -DDO_TIMING
+    instrumentation over a zlib-only samtools shim) on a bounded sample of the bench workload: P = cores/2 contigs of the config-3
+    generator (+ a dummy last contig, which -P >= 2 silently skips, reference src/GROM.c:20999) processed by `-M -P P`, 2 threads per
+    process (src/GROM.c:575).  Returns the whole-program figure (wall clock) and the hot-path-only one (sum of the reference's stage
+    timers 0-4, 7, 8 over its children).  The sample is generated and written by a child process: this process maps no library of the repo."""
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    exe = os.path.join(ref_dir, "GROM_ref_timing")
+    if not os.path.exists(exe):
+        exe = os.path.join(ref_dir, "GROM_ref")
+    if not os.path.exists(exe):
         return None
     cores = os.cpu_count() or 2
     nproc = max(1, min(cores // 2, 32))
-    L = int(a.cpu_sample_mb * 1e6)
-    contigs = [(f"chr{i + 1}", L) for i in range(nproc)] + [("chrzz", 60_000)]
-    spec = synth.SynthSpec(contigs=contigs, depth=a.depth, seed=4242, simple=True, dup_frac=0.05)
-    cs = synth.simulate(spec)
     tmp = tempfile.mkdtemp(prefix="grom_cpu_")
     try:
-        fa, bam = synth.write_dataset(os.path.join(tmp, "sample"), cs)
-        bases = sum(c.batch.aligned_bases() for c in cs[:-1]) if nproc >= 2 else sum(c.batch.aligned_bases() for c in cs)
-        po.reference_tables(20)                         # tables pre-generated next to the binary
-        times = []
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_sample.py"), "--out", tmp, "--contigs", str(nproc), "--mb", str(a.cpu_sample_mb),
+                            "--depth", str(a.depth)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("tools/make_sample.py failed: " + r.stderr[-400:])
+        meta = json.loads(r.stdout.strip().splitlines()[-1])
+        bases = meta["aligned_bases"]
+        # the binary looks for its probability tables beside itself (src/GROM.c:21333, 21527): run a copy from the scratch directory
+        run_exe = os.path.join(tmp, os.path.basename(exe))
+        shutil.copy(exe, run_exe)
+        for f in os.listdir(ref_dir):
+            if f.endswith(".txt"):
+                os.symlink(os.path.join(ref_dir, f), os.path.join(tmp, f))
+        hz = None
+        tsc = os.path.join(ref_dir, "tsc_hz")
+        if os.path.exists(tsc):
+            hz = float(subprocess.run([tsc], stdout=subprocess.PIPE, text=True).stdout.strip() or 0) or None
+        times, hot = [], []
         for it in range(warmup + steps):
+            for ext in (".mean", ".info"):
+                for q in (meta["bam"] + ext, meta["fasta"] + ext):
+                    if os.path.exists(q):
+                        os.remove(q)
             t0 = time.perf_counter()
-            po.run_reference(bam, fa, os.path.join(tmp, "out.vcf"), args=["-M", "-P", str(nproc)], kind="ref")
+            pr = subprocess.run([run_exe, "-i", meta["bam"], "-r", meta["fasta"], "-o", os.path.join(tmp, "out.vcf"), "-M", "-P", str(nproc)],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             dt = time.perf_counter() - t0
+            if pr.returncode != 0:
+                raise RuntimeError(f"{os.path.basename(exe)} exited {pr.returncode}")
             if it >= warmup:
                 times.append(dt)
+                cyc = 0
+                for line in pr.stdout.splitlines():
+                    w = line.split()
+                    if len(w) == 3 and w[0] == "timer" and w[1].isdigit() and int(w[1]) in HOT_TIMERS:
+                        cyc += int(w[2])
+                hot.append(cyc)
         sec = float(np.mean(times))
-        return {"value": bases / sec, "unit": UNIT, "cores": 2 * nproc if nproc >= 1 else 1, "kind": "reference",
-                "sample": f"GROM_ref -M -P {nproc} on {nproc} synthetic contigs x {a.cpu_sample_mb:g} Mb at {a.depth:g}x "
-                          f"({bases / 1e6:.0f} M aligned bases, whole program incl. BAM decode), {sec:.2f} s wall, host has {cores} cores",
-                "seconds": sec, "aligned_bases": bases}
+        out = {"value": bases / sec, "unit": UNIT, "cores": 2 * nproc, "kind": "reference",
+               "sample": f"{os.path.basename(exe)} -M -P {nproc} on {nproc} contigs x {a.cpu_sample_mb:g} Mb of the config-3 generator at {a.depth:g}x "
+                         f"({bases / 1e6:.0f} M aligned bases; whole program incl. two BAM decode passes, tables, VCF text), {sec:.2f} s wall, host has {cores} cores",
+               "seconds": sec, "aligned_bases": bases}
+        if hz and hot and hot[0] > 0:
+            cpu_s = float(np.mean(hot)) / hz                   # CPU-seconds inside the hot path, all children together
+            out["hot_path"] = {"cpu_seconds": cpu_s, "bases_per_s_per_process": bases / cpu_s, "bases_per_s_all_processes": bases / (cpu_s / nproc),
+                               "processes": nproc, "timers": list(HOT_TIMERS), "tsc_hz": hz,
+                               "what": "sum of the reference's own -DDO_TIMING stage timers (rdtsc) over its -P children: window management, -M, evidence "
+                                       "accumulation, per-position scan, CNV depth, CNV pre-statistics, detect_del_dup; no BAM decode, FASTA load or VCF text"}
+        return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -147,15 +192,16 @@ def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    r = cpu_reference_run(a, max(1, a.steps), min(a.warmup, 1))
+    r = cpu_reference_run(a, max(1, min(a.steps, 5)), min(a.warmup, 1))
     if r is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/GROM_ref was not built (needs /root/reference at build time)"}))
         return 0
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": {"workload": workload_name(a), "sample": r["sample"]},
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "data": "synthetic", "config": bench_config(a),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "hot_path") if k in r},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "each timed step = one whole run of the reference on the bounded sample (at most 5 are run, whatever --steps says)"}
     print(json.dumps(line))
     return 0
 
@@ -220,7 +266,8 @@ def main_b200(a):
     c = synth.simulate(spec)[0]
     gen_s = time.time() - t0
     # the batch in the form the host batcher hands over: canonical arrays + the transport-compact forms the data allow
-    pinned, keep, read_bytes = pin_batch(c.batch if a.canonical_upload else c.batch.compact())
+    # (repack_canonical = the layout the batcher produces natively: every read's bases start on a 32-slot boundary, offsets are running sums)
+    pinned, keep, read_bytes = pin_batch(c.batch if a.canonical_upload else c.batch.repack_canonical().compact())
     fasta_pinned = torch.from_numpy(c.chars).pin_memory()
     fasta_np = fasta_pinned.numpy()
 
@@ -401,14 +448,13 @@ def main_b200(a):
         if world == 1 and not a.no_cpu_baseline:
             r = cpu_reference_run(a, 1, 0)
             if r:
-                cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "hot_path") if k in r}
         line = {
             "metric": METRIC, "value": total_bases * a.steps / (ms_steps_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(3, a.warmup), "ms_per_step": ms_steps_max / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "contig_len": P, "reads_per_gpu": int(st.n_reads), "aligned_bases_per_gpu": bases,
-                       "flags": "-M (duplicate filter on), defaults otherwise", "generator": ("tools/workloads.py chr20_spec" if not a.simple else "simple (single-M reads)"), "step": "evidence + SNV/indel scan (gromgpu_chr_run) + read-depth CNV path (gromgpu_chr_cnv, incl. its host segmentation)", "l2": "inputs (>3 GB reads + 6.7 GB arrays per step) exceed the 126 MB L2; no flush needed",
-                       "partition": "one contig per GPU, no data-path collective", "host_gen_s": round(gen_s, 1)},
+            "config": bench_config(a),
+            "run": {"reads_per_gpu": int(st.n_reads), "aligned_bases_per_gpu": bases, "host_gen_s": round(gen_s, 1)},
             "e2e": {"value": total_bases * a.steps / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(read_bytes + P),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps,
                     "upload_form": ("canonical arrays" if not pinned.layout_flags else "transport-compact (include/grom_reads.h GROM_LAYOUT_*): "

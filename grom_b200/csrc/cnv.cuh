@@ -198,45 +198,92 @@ __global__ void __launch_bounds__(1024) k_carry_scan(const uint8_t *__restrict__
     for (int t = a; t < b; t++) { tile_in[t] = c; if (tile_last[t] != 2) c = tile_last[t]; }
 }
 
+// Both kernels below give each thread CITEMS = 8 consecutive positions of a 2048-position tile (vector loads) and need, per position, the
+// class of the LAST "setter" position before it (the reference's ddd_last_low_mq carried through uncovered stretches).  That is an
+// exclusive max-scan of setter indices over the tile -- inside the thread, then across the block -- never a backward walk: a tile
+// inside a zero-coverage stretch (full-loss segment, N run) costs the same as any other.
+constexpr int CITEMS = CTILE / 256;
+static_assert(CITEMS == 8, "the carry kernels load 8 positions per thread");
+__device__ __forceinline__ int block_excl_max_256(int v, int *s_w /* [8] */)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl = max(incl, y); }
+    int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = -1;
+    if (lane == 31) s_w[w] = incl;
+    __syncthreads();
+    int base = -1;
+    for (int k = 0; k < w; k++) base = max(base, s_w[k]);
+    __syncthreads();
+    return max(base, excl);
+}
+template <class T> __device__ __forceinline__ void load8(const T *__restrict__ a, int64_t p0, int64_t n, T (&v)[8], T fill)
+{
+    if (p0 + 8 <= n) {
+        if (sizeof(T) == 4) { const int4 x = *reinterpret_cast<const int4 *>(a + p0), y = *reinterpret_cast<const int4 *>(a + p0 + 4);
+            v[0] = (T)x.x; v[1] = (T)x.y; v[2] = (T)x.z; v[3] = (T)x.w; v[4] = (T)y.x; v[5] = (T)y.y; v[6] = (T)y.z; v[7] = (T)y.w; }
+        else { const uint2 x = *reinterpret_cast<const uint2 *>(a + p0);
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (T)(((k < 4 ? x.x : x.y) >> (8 * (k & 3))) & 0xff); }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = p0 + k < n ? a[p0 + k] : fill;
+    }
+}
+
 // ---- K5: mask (src/GROM.c:18681-18720), class, list-size bits; summary of the z-stage setters per tile
 __global__ void __launch_bounds__(256) k_mask(const int32_t *__restrict__ depth, const uint8_t *__restrict__ mq8, const int32_t *__restrict__ gc,
                                               const int32_t *__restrict__ acgt, int64_t P, int64_t lo, int64_t hi, int q, const int32_t *__restrict__ nlist,
                                               const uint8_t *__restrict__ tile_in, uint32_t *__restrict__ rec, uint8_t *__restrict__ tile_last_z)
 {
+    __shared__ int s_w[8];
     __shared__ int best;
     if (threadIdx.x == 0) best = -1;
-    __syncthreads();
-    const int64_t t0 = (int64_t)blockIdx.x * CTILE;
+    const int64_t t0 = (int64_t)blockIdx.x * CTILE, p0 = t0 + (int64_t)threadIdx.x * CITEMS;
+    int d[8], g[8], ac[8]; uint8_t m[8];
+    load8(depth, p0, P, d, 0); load8(gc, p0, P, g, 0); load8(acgt, p0, P, ac, 0); load8(mq8, p0, P, m, (uint8_t)0);
+    // last mask-stage setter (covered, enough ACGT context, inside the analysed span) strictly before each position
+    int before[8], last = -1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int64_t p = p0 + k;
+        before[k] = last;
+        if (p >= lo && p < hi && ac[k] >= MIN_ACGT && d[k] > 0) last = threadIdx.x * CITEMS + k;
+    }
+    const int carry = block_excl_max_256(last, s_w);
+    const int cin = tile_in[blockIdx.x];
     int mine = -1;
-    for (int i = threadIdx.x; i < CTILE; i += blockDim.x) {
-        const int64_t p = t0 + i;
-        if (p >= P) break;
-        const int d = depth[p], m = mq8[p];
-        const int cls = m >= q ? 0 : (d > 0 ? 1 : 2);
-        uint32_t r = (uint32_t)cls << R_CLASS | (uint32_t)m << R_MQ | R_MASK;
-        if (p >= lo) {
-            const int g = gc[p];
-            if (nlist[g] > 1) r |= R_WIN0;
-            if (nlist[NB + g] > 1) r |= R_WIN1;
+    uint32_t out[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int64_t p = p0 + k;
+        const int cls = m[k] >= q ? 0 : (d[k] > 0 ? 1 : 2);
+        uint32_t r = (uint32_t)cls << R_CLASS | (uint32_t)m[k] << R_MQ | R_MASK;
+        if (p >= lo && p < P) {
+            if (nlist[g[k]] > 1) r |= R_WIN0;
+            if (nlist[NB + g[k]] > 1) r |= R_WIN1;
         }
         if (p >= lo && p < hi) {
-            const int g = gc[p];
-            if (acgt[p] >= MIN_ACGT) {
+            if (ac[k] >= MIN_ACGT) {
                 int mi;
-                if (d > 0) mi = m >= q ? 0 : 1;
+                if (d[k] > 0) mi = m[k] >= q ? 0 : 1;
                 else {
-                    // uncovered: the list of the last covered position with enough ACGT context (walk back inside the tile, else the tile's carry-in)
-                    mi = -1;
-                    for (int64_t b = p - 1; b >= t0 && b >= lo; b--) if (acgt[b] >= MIN_ACGT && depth[b] > 0) { mi = mq8[b] >= q ? 0 : 1; break; }
-                    if (mi < 0) mi = tile_in[blockIdx.x];
+                    // uncovered: the list of the last covered position with enough ACGT context (in the tile, else the tile's carry-in)
+                    const int idx = max(before[k], carry);
+                    mi = idx >= 0 ? (mq8[t0 + idx] >= q ? 0 : 1) : cin;
                 }
-                if (nlist[mi * NB + g] >= NO_COMBINE) r &= ~R_MASK;
+                if (nlist[mi * NB + g[k]] >= NO_COMBINE) r &= ~R_MASK;
             }
-            if (rec_usable(r)) { r |= R_USABLE; if (cls != 2) mine = max(mine, i); }
+            if (rec_usable(r)) { r |= R_USABLE; if (cls != 2) mine = max(mine, threadIdx.x * CITEMS + k); }
         }
-        rec[p] = r;
+        out[k] = r;
     }
-    if (mine >= 0) atomicMax(&best, mine);
+    if (p0 + 8 <= P) { *reinterpret_cast<uint4 *>(rec + p0) = make_uint4(out[0], out[1], out[2], out[3]); *reinterpret_cast<uint4 *>(rec + p0 + 4) = make_uint4(out[4], out[5], out[6], out[7]); }
+    else { for (int k = 0; k < 8; k++) if (p0 + k < P) rec[p0 + k] = out[k]; }
+    mine = __reduce_max_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine >= 0) atomicMax(&best, mine);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint8_t v = 2;
@@ -267,62 +314,80 @@ __global__ void __launch_bounds__(256) k_z(const int32_t *__restrict__ depth, co
                                            uint32_t *__restrict__ seed_del, uint32_t *__restrict__ seed_dup)
 {
     __shared__ double sp[P2S];
+    __shared__ int s_w[8];
+    __shared__ uint8_t s_cls[CTILE];                 // class of every position of the tile (read back at the carried setter index)
     for (int i = threadIdx.x; i < P2S; i += blockDim.x) sp[i] = T.p2s_p[i];
-    __syncthreads();
-    const int64_t t0 = (int64_t)blockIdx.x * CTILE;
-    for (int i = threadIdx.x; i < CTILE; i += blockDim.x) {
-        const int64_t p = t0 + i;
-        uint32_t r = 0;
+    const int64_t t0 = (int64_t)blockIdx.x * CTILE, p0 = t0 + (int64_t)threadIdx.x * CITEMS;
+    int d[8], g[8]; uint32_t r[8];
+    load8(depth, p0, P, d, 0); load8(gc, p0, P, g, 0); load8(rec, p0, P, r, (uint32_t)R_MASK);
+    int before[8], last = -1;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        before[k] = last;
+        const int cls = (r[k] >> R_CLASS) & 3;
+        s_cls[threadIdx.x * CITEMS + k] = (uint8_t)cls;
+        if ((r[k] & R_USABLE) && cls != 2 && p0 + k < P) last = threadIdx.x * CITEMS + k;
+    }
+    const int carry = block_excl_max_256(last, s_w);          // (its barriers also publish sp and s_cls)
+    const int cin = tile_in[blockIdx.x];
+    unsigned bits_del = 0, bits_dup = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int64_t p = p0 + k;
+        uint32_t rr = r[k];
         bool s_del = false, s_dup = false;
         if (p < P) {
-            r = rec[p];
-            const int d = depth[p];
+            const int dd = d[k];
             if (p >= lo) {
                 // thresholds of the position's GC bin; past the analysed span the reference reads bin 0 of a zero-filled array
-                const int g = gc[p];
-                if ((double)d <= T.del_thr[g]) r |= R_DEL0;
-                if ((double)d <= T.del_thr[NB + g]) r |= R_DEL1;
-                if ((double)d >= T.dup_thr[g]) r |= R_DUP0;
-                if ((double)d >= T.dup_thr[NB + g]) r |= R_DUP1;
+                const int gg = g[k];
+                if ((double)dd <= T.del_thr[gg]) rr |= R_DEL0;
+                if ((double)dd <= T.del_thr[NB + gg]) rr |= R_DEL1;
+                if ((double)dd >= T.dup_thr[gg]) rr |= R_DUP0;
+                if ((double)dd >= T.dup_thr[NB + gg]) rr |= R_DUP1;
             }
             if (p >= lo && p < hi) {
-                const int g = gc[p];
-                const int cls = (r >> R_CLASS) & 3;
-                s_del = cls == 0 ? (r & R_DEL0) : cls == 1 ? (r & R_DEL1) : (r & (R_DEL0 | R_DEL1));
-                s_dup = cls == 0 ? (r & R_DUP0) : cls == 1 ? (r & R_DUP1) : (r & (R_DUP0 | R_DUP1));
-                if (r & R_USABLE) {
+                const int gg = g[k];
+                const int cls = (rr >> R_CLASS) & 3;
+                s_del = cls == 0 ? (rr & R_DEL0) : cls == 1 ? (rr & R_DEL1) : (rr & (R_DEL0 | R_DEL1));
+                s_dup = cls == 0 ? (rr & R_DUP0) : cls == 1 ? (rr & R_DUP1) : (rr & (R_DUP0 | R_DUP1));
+                if (rr & R_USABLE) {
                     int mi;
                     if (cls == 0) mi = 0;
                     else if (cls == 1) mi = 1;
-                    else {
-                        mi = -1;
-                        for (int64_t b = p - 1; b >= t0 && b >= lo; b--) { const uint32_t rb = rec[b]; if ((rb & R_USABLE) && ((rb >> R_CLASS) & 3) != 2) { mi = (rb >> R_CLASS) & 3; break; } }
-                        if (mi < 0) mi = tile_in[blockIdx.x];
-                    }
-                    const int list = mi * NB + g, n = T.n[list];
+                    else { const int idx = max(before[k], carry); mi = idx >= 0 ? (int)s_cls[idx] : cin; }
+                    const int list = mi * NB + gg, n = T.n[list];
                     if (n > 0) {
                         const double ave = T.ave[list];
                         int i1, i2;
                         bool neg;
-                        if ((double)d < ave) { i1 = rank_le(T, list, d); i2 = rank_lt(T, list, d); neg = false; }
+                        if ((double)dd < ave) { i1 = rank_le(T, list, dd); i2 = rank_lt(T, list, dd); neg = false; }
                         else {
-                            if ((double)d > 2 * ave) i1 = rank_lt(T, list, (int)(2 * ave)); else i1 = rank_lt(T, list, d);
-                            i2 = rank_le(T, list, d);
+                            if ((double)dd > 2 * ave) i1 = rank_lt(T, list, (int)(2 * ave)); else i1 = rank_lt(T, list, dd);
+                            i2 = rank_le(T, list, dd);
                             i1 = n - i1; i2 = n - i2; neg = true;
                         }
                         const double prob = ((i1 <= 0 ? 0.5 : (double)i1) + (i2 <= 0 ? 0.5 : (double)i2)) / (double)(2 * (long long)n);
                         int a = 0, b = P2S;                       // first table entry > prob (bisect_right over the ascending p-value table)
-                        while (a < b) { const int m = (a + b) >> 1; if (prob < sp[m]) b = m; else a = m + 1; }
+                        while (a < b) { const int mm = (a + b) >> 1; if (prob < sp[mm]) b = mm; else a = mm + 1; }
                         if (a >= P2S) a = P2S - 1;
-                        r |= R_NZ | (neg ? R_NEG : 0u) | ((uint32_t)a << R_K);
+                        rr |= R_NZ | (neg ? R_NEG : 0u) | ((uint32_t)a << R_K);
                     }
                 }
             }
-            rec[p] = r;
         }
-        const unsigned bd = __ballot_sync(0xffffffffu, s_del), bu = __ballot_sync(0xffffffffu, s_dup);
-        if ((threadIdx.x & 31) == 0 && p < ((P + 31) / 32) * 32) { seed_del[p >> 5] = bd; seed_dup[p >> 5] = bu; }
+        r[k] = rr;
+        if (s_del) bits_del |= 1u << k;
+        if (s_dup) bits_dup |= 1u << k;
     }
+    if (p0 + 8 <= P) { *reinterpret_cast<uint4 *>(rec + p0) = make_uint4(r[0], r[1], r[2], r[3]); *reinterpret_cast<uint4 *>(rec + p0 + 4) = make_uint4(r[4], r[5], r[6], r[7]); }
+    else { for (int k = 0; k < 8; k++) if (p0 + k < P) rec[p0 + k] = r[k]; }
+    // seed words: four threads (32 positions) share one word of each bitmap
+    const int lane = threadIdx.x & 31, sub = lane & 3;
+    unsigned wd = bits_del << (8 * sub), wu = bits_dup << (8 * sub);
+    wd |= __shfl_xor_sync(0xffffffffu, wd, 1); wd |= __shfl_xor_sync(0xffffffffu, wd, 2);
+    wu |= __shfl_xor_sync(0xffffffffu, wu, 1); wu |= __shfl_xor_sync(0xffffffffu, wu, 2);
+    if (sub == 0 && p0 < ((P + 31) / 32) * 32) { seed_del[p0 >> 5] = wd; seed_dup[p0 >> 5] = wu; }
 }
 
 // ---- K7: window-length sweep (src/GROM.c:18967-19018).  The walk over a sample block, repeated at each -A offset without resetting
@@ -338,81 +403,111 @@ __device__ __forceinline__ void sweep_advance(int &a, int64_t &p, int64_t n, int
         n -= rem; a++; p = s + (int64_t)a * Lmax / A;
     }
 }
-// One warp owns 32 consecutive frames, one lane per frame.  Per chunk of 32 elements: (A) the 32 x 32 records are fetched row by row
-// (coalesced: a row is 32 consecutive elements of one frame's walk), decoded and parked in shared memory; (B) every lane folds ITS frame's
-// 32 values into its running sum in element order -- one dependent DADD per element, the reference's summation order -- leaving the
-// prefix sums in place; (C) the tile is read back transposed: lane = window length, so the division, the square and the store of
-// X[frame][L] run in parallel over 32 lengths and the stores are coalesced rows.
-#define SWEEP_PITCH 33
-__global__ void __launch_bounds__(32) k_sweep(const uint32_t *__restrict__ rec, const SweepBlock *__restrict__ blocks, int n_blocks, int64_t n_frames,
+// A CTA owns 32 consecutive frames and walks them in chunks of SW_CH elements through a double-buffered shared-memory tile
+// [32 frames][SW_CH]:
+//  (A) all eight warps fetch the records row by row (a row = SW_CH consecutive elements of one frame's walk: coalesced), decode z and park it;
+//  (B) warp 0, one lane per frame, folds ITS frame's SW_CH values into its running sum in element order -- one dependent DADD per
+//      element, the reference's summation order -- leaving the prefix sums in place;
+//  (C) all warps read the tile back transposed (lane = window length): division, square and the coalesced store of X[frame][L].
+// (B) of chunk c overlaps (A) of chunk c + 1 (the other buffer), so the serial chain hides behind the fetches.
+#define SW_CH 64
+#define SW_PITCH (SW_CH + 1)
+#define SW_WARPS 8
+__global__ void __launch_bounds__(32 * SW_WARPS) k_sweep(const uint32_t *__restrict__ rec, const SweepBlock *__restrict__ blocks, int n_blocks, int64_t n_frames,
                                               int A, int Lmin, int Lmax, int q, const double *__restrict__ p2s_sd, const double *__restrict__ wtab_g, double *__restrict__ X)
 {
     __shared__ double sd[P2S];
     __shared__ double wtab[256];
-    __shared__ double zt[32 * SWEEP_PITCH];
-    __shared__ int st_a[32], st_p[32], st_s[32], st_e[32], st_n0[32];
-    __shared__ unsigned st_um[32], st_vm[32];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < P2S; i += 32) sd[i] = p2s_sd[i];
-    for (int i = lane; i < 256; i += 32) wtab[i] = wtab_g[i];
-    const int64_t f0 = (int64_t)blockIdx.x * 32, f = f0 + lane;
+    __shared__ double zt[2][32 * SW_PITCH];
+    __shared__ int st_a[2][32], st_p[2][32], st_s[32], st_e[32], st_n0[2][32];
+    __shared__ unsigned st_um[2][32][SW_CH / 32], st_vm[2][32][SW_CH / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < P2S; i += blockDim.x) sd[i] = p2s_sd[i];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) wtab[i] = wtab_g[i];
+    const int64_t f0 = (int64_t)blockIdx.x * 32;
     const int n_rows = (int)min((int64_t)32, n_frames - f0);
     const int n_len = Lmax - Lmin + 1;
-    // this lane's frame: block, walk state at the frame start
+    const int n_chunks = (Lmax + SW_CH - 1) / SW_CH;
+    // warp 0: lane = frame; walk state at the frame start
     int a = A; int64_t p = 0, s = 0, e = 0;
-    if (f < n_frames) {
-        int lo_b = 0, hi_b = n_blocks - 1;                       // last block whose first frame is <= f
-        while (lo_b < hi_b) { const int m = (lo_b + hi_b + 1) >> 1; if (blocks[m].first_frame <= f) lo_b = m; else hi_b = m - 1; }
-        s = blocks[lo_b].start; e = blocks[lo_b].end; a = 0; p = s;
-        sweep_advance(a, p, (f - blocks[lo_b].first_frame) * (int64_t)Lmax, s, e, A, Lmax);
-    }
-    st_s[lane] = (int)s; st_e[lane] = (int)e;
     double tot = 0.0;
     int n_us = 0;
+    if (wid == 0) {
+        const int64_t f = f0 + lane;
+        if (f < n_frames) {
+            int lo_b = 0, hi_b = n_blocks - 1;                   // last block whose first frame is <= f
+            while (lo_b < hi_b) { const int m = (lo_b + hi_b + 1) >> 1; if (blocks[m].first_frame <= f) lo_b = m; else hi_b = m - 1; }
+            s = blocks[lo_b].start; e = blocks[lo_b].end; a = 0; p = s;
+            sweep_advance(a, p, (f - blocks[lo_b].first_frame) * (int64_t)Lmax, s, e, A, Lmax);
+        }
+        st_s[lane] = (int)s; st_e[lane] = (int)e; st_a[0][lane] = a; st_p[0][lane] = (int)p;
+    }
+    __syncthreads();
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int w0 = 0; w0 < Lmax; w0 += 32) {
-        st_a[lane] = a; st_p[lane] = (int)p;
-        __syncwarp();
-        unsigned my_um = 0, my_vm = 0;
-        const bool in_len = w0 + lane < Lmax;
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {                           // (A) row r = frame f0 + r, this lane = element w0 + lane of its walk
-            int la = st_a[r]; int64_t lp = st_p[r];
-            sweep_advance(la, lp, lane, (int64_t)st_s[r], (int64_t)st_e[r], A, Lmax);
-            const bool valid = la < A && in_len;
-            const uint32_t rr = valid ? __ldg(rec + lp) : R_MASK;
-            const bool us = valid && rec_usable(rr);
-            double z = 0.0;
-            if (us && (rr & R_NZ)) {
-                const double wt = (rr & R_OVR) ? 1.0 : (((rr >> R_CLASS) & 3) == 0 ? wtab[(rr >> R_MQ) & 255] : 0.5);
-                z = __dmul_rn(wt, sd[(rr >> R_K) & 1023]);
-                if (rr & R_NEG) z = -z;
-            }
-            const unsigned um = __ballot_sync(0xffffffffu, us), vm = __ballot_sync(0xffffffffu, valid);
-            zt[r * SWEEP_PITCH + lane] = z;
-            if (lane == r) { my_um = um; my_vm = vm; }
-        }
-        __syncwarp();
-        const int n0 = n_us;                                      // (B) the ordered fold of this lane's frame
-        double *mine = zt + lane * SWEEP_PITCH;
+    auto fetch = [&](int c, int w_first, int w_step) {            // (A) chunk c -> buffer c & 1, rows split over warps w_first, w_first + w_step ...
+        const int b = c & 1, w0 = c * SW_CH;
+        for (int r = w_first; r < 32; r += w_step) {
+            const int ra = st_a[b][r]; const int64_t rp = st_p[b][r], rs = st_s[r], re = st_e[r];
 #pragma unroll
-        for (int j = 0; j < 32; j++) { if ((my_um >> j) & 1u) tot = __dadd_rn(tot, mine[j]); mine[j] = tot; }
-        n_us += __popc(my_um);
-        st_um[lane] = my_um; st_vm[lane] = my_vm; st_n0[lane] = n0;
-        __syncwarp();
-        const int w = w0 + lane + 1;                              // (C) lane = window length
-        if (w >= Lmin && w <= Lmax) {
-            const unsigned below = 0xffffffffu >> (31 - lane);
-#pragma unroll 4
-            for (int r = 0; r < n_rows; r++) {
-                const int n = st_n0[r] + __popc(st_um[r] & below);
-                double x2 = nan;
-                if (((st_vm[r] >> lane) & 1u) && n > 0) { const double x = zt[r * SWEEP_PITCH + lane] / (double)n; x2 = __dmul_rn(x, x); }
-                __stcs(X + (f0 + r) * (int64_t)n_len + (w - Lmin), x2);
+            for (int h = 0; h < SW_CH / 32; h++) {
+                const int j = h * 32 + lane;
+                int la = ra; int64_t lp = rp;
+                sweep_advance(la, lp, j, rs, re, A, Lmax);
+                const bool valid = la < A && w0 + j < Lmax;
+                const uint32_t rr = valid ? __ldg(rec + lp) : R_MASK;
+                const bool us = valid && rec_usable(rr);
+                double z = 0.0;
+                if (us && (rr & R_NZ)) {
+                    const double wt = (rr & R_OVR) ? 1.0 : (((rr >> R_CLASS) & 3) == 0 ? wtab[(rr >> R_MQ) & 255] : 0.5);
+                    z = __dmul_rn(wt, sd[(rr >> R_K) & 1023]);
+                    if (rr & R_NEG) z = -z;
+                }
+                const unsigned um = __ballot_sync(0xffffffffu, us), vm = __ballot_sync(0xffffffffu, valid);
+                zt[b][r * SW_PITCH + j] = z;
+                if (lane == 0) { st_um[b][r][h] = um; st_vm[b][r][h] = vm; }
             }
         }
-        __syncwarp();
-        sweep_advance(a, p, 32, s, e, A, Lmax);
+    };
+    auto next_state = [&](int c) {                                // warp 0: walk state at the start of chunk c (the lane's state is chunk c - 1's)
+        sweep_advance(a, p, SW_CH, s, e, A, Lmax);
+        st_a[c & 1][lane] = a; st_p[c & 1][lane] = (int)p;
+    };
+    fetch(0, wid, SW_WARPS);
+    if (wid == 0) next_state(1);
+    __syncthreads();
+    for (int c = 0; c < n_chunks; c++) {
+        const int b = c & 1, w0 = c * SW_CH;
+        if (wid == 0) {                                           // (B) the ordered fold of chunk c ...
+            double *mine = zt[b] + lane * SW_PITCH;
+            st_n0[b][lane] = n_us;
+#pragma unroll
+            for (int h = 0; h < SW_CH / 32; h++) {
+                const unsigned um = st_um[b][lane][h];
+#pragma unroll
+                for (int j = 0; j < 32; j++) { if ((um >> j) & 1u) tot = __dadd_rn(tot, mine[h * 32 + j]); mine[h * 32 + j] = tot; }
+                n_us += __popc(um);
+            }
+        } else if (c + 1 < n_chunks) fetch(c + 1, wid - 1, SW_WARPS - 1);      // ... while the other warps fetch chunk c + 1 into the other buffer
+        __syncthreads();
+        if (wid == 0 && c + 2 < n_chunks) next_state(c + 2);      // slot (c + 2) & 1 == b: its last readers (fetch of chunk c) are long done
+        {                                                         // (C) lane = window length
+#pragma unroll
+            for (int h = 0; h < SW_CH / 32; h++) {
+                const int j = h * 32 + lane, w = w0 + j + 1;
+                if (w >= Lmin && w <= Lmax) {
+                    const unsigned below = 0xffffffffu >> (31 - lane);
+                    for (int r = wid; r < n_rows; r += SW_WARPS) {
+                        int n = st_n0[b][r];
+                        for (int hh = 0; hh < h; hh++) n += __popc(st_um[b][r][hh]);
+                        n += __popc(st_um[b][r][h] & below);
+                        double x2 = nan;
+                        if (((st_vm[b][r][h] >> lane) & 1u) && n > 0) { const double x = zt[b][r * SW_PITCH + j] / (double)n; x2 = __dmul_rn(x, x); }
+                        __stcs(X + (f0 + r) * (int64_t)n_len + (w - Lmin), x2);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                          // tile b is drained: the next iteration's fetch (chunk c + 2) may overwrite it
     }
 }
 // ordered sum over the frames per window length: a CTA owns 32 lengths; all eight warps stream tiles of 64 frames x 32 lengths into a
@@ -470,6 +565,7 @@ __global__ void __launch_bounds__(256) k_sweep_sum(const double *__restrict__ X,
 // plus the few evaluations the device left unresolved).
 struct SegCtx {
     const uint32_t *rec; int64_t len, end; int q, Lmin, Lmax, bound; const double *sd, *win_sd; bool dup;
+    int64_t slide_max = 0;       // bounded evaluation: positions the sliding phase may advance before the seed is left open (0: never enters it)
     const double *wtab;          // MAPQ weight per mean MAPQ value [256]: the expression of rec_z evaluated once per value (same doubles, no division per base)
     const double *win_thr;       // [Lmax + 1] 2.97 * win_sd[L], +inf where win_sd[L] <= 0: the cheap side of scores()
     const double *zarr;          // device only: z of the deletion scan per position, unpacked once (k_zfill); nullptr = unpack from rec
@@ -506,7 +602,8 @@ struct SegCtx {
 };
 enum { SEG_RESUME = 0, SEG_CALL = 1, SEG_UNRESOLVED = 2 };
 struct Outcome { int kind; int64_t next, c_end; double c_z; int64_t far; };   // far: one past the last position the sliding phase looked at
-constexpr int SEED_BOUND = 1024;       // first round, every seed; the second round gives the compacted unresolved ones the full growth phase (Lmax)
+constexpr int SEED_BOUND0 = 128;       // first round, pass one (every seed)
+constexpr int SEED_BOUND = 1024;       // first round, every seed: closes everything but genuine events and long uncovered stretches (chance dips of the coverage end within a few hundred positions); what runs past it is "open"
 
 template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCtx &C, const int64_t pos, int mi)
 {
@@ -565,10 +662,11 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
         }
     }
     if (!stop && begun) {
-        if (BOUNDED) { o.kind = SEG_UNRESOLVED; return o; }
+        if (BOUNDED && C.slide_max <= 0) { o.kind = SEG_UNRESOLVED; return o; }
         int mi_b = mi;
         pa = pos + Lmax; tot = 0; cnt = 0;
         while (pa < C.len && pa - last_good <= max_gap) {
+            if (BOUNDED && pa - (pos + Lmax) > C.slide_max) { o.kind = SEG_UNRESOLVED; return o; }
             if (pa == pos + Lmax) {
                 for (int64_t pb = pa - Lmax + 1; pb < pa + 1; pb++) {
                     CNV_STEP(mi_b, pb);
@@ -743,10 +841,54 @@ __global__ void k_hop_advance(SegCtx C0, SegCtx C1, const uint32_t *__restrict__
     sink[k] = r;
 }
 
-// one thread per seed (blockIdx.y = deletions / duplications): rank -> position through the per-word ranks, then evaluate the seed
-// (both carried classes when it is uncovered).  Seeds that run past the bound are appended to `todo` for the second round, which
-// runs one thread per (kind, rank, class) entry of that list.
-struct SeedTodo { uint32_t rank; uint8_t kind, variant; uint16_t pad; };
+// positions [a, b] of a call made at a head -> the `cover` bitmap of its kind (seeds under it are jumped over by the path)
+__device__ __forceinline__ void cover_mark(uint32_t *__restrict__ cov, int64_t a, int64_t b, int lane, int n_lanes)
+{
+    if (b < a) return;
+    const int64_t w0 = a >> 5, w1 = b >> 5;
+    for (int64_t w = w0 + lane; w <= w1; w += n_lanes) {
+        uint32_t m = 0xffffffffu;
+        if (w == w0) m &= 0xffffffffu << (a & 31);
+        if (w == w1) m &= 0xffffffffu >> (31 - (b & 31));
+        if (m == 0xffffffffu) cov[w] = m; else atomicOr(cov + w, m);
+    }
+}
+__device__ __forceinline__ void head_publish(const SegCtx &C, int kind, uint32_t rank, int variant, int64_t p, uint32_t e, const uint32_t *__restrict__ seeds, int64_t words,
+                                             const uint32_t *__restrict__ wp, uint32_t *__restrict__ land, uint32_t cap, const SeedCall *__restrict__ calls,
+                                             uint32_t n_del, uint32_t n_dup, uint32_t *__restrict__ jump0)
+{
+    const int c0 = C.cls(p);
+    land[((int64_t)kind * cap + rank) * 2 + variant] = e;
+    if (c0 != 2) land[((int64_t)kind * cap + rank) * 2 + 1] = e;
+    if (jump0) {
+        const uint32_t n_seeds = kind ? n_dup : n_del, base = kind ? 2 * n_del + 1 : 0;
+        const uint32_t *sd = seeds + (int64_t)kind * words, *wpk = wp + (int64_t)kind * words;
+        jump0[base + 2 * rank + variant] = base + successor(C, sd, wpk, p, c0, variant, e, calls, rank, n_seeds);
+        if (c0 != 2) jump0[base + 2 * rank + 1] = base + successor(C, sd, wpk, p, c0, 1, e, calls, rank, n_seeds);
+    }
+}
+// bitmap of the positions that carry a z value (R_NZ), with per-word ranks (k_seed_rank): "does this stretch hold any z at all" in O(1)
+__global__ void __launch_bounds__(256) k_nz_bits(const uint32_t *__restrict__ rec, int64_t P, uint32_t *__restrict__ nz)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned b = __ballot_sync(0xffffffffu, p < P && (rec[p] & R_NZ));
+    if ((threadIdx.x & 31) == 0 && p < ((P + 31) / 32) * 32) nz[p >> 5] = b;
+}
+__device__ __forceinline__ uint32_t nz_rank(const uint32_t *__restrict__ nz, const uint32_t *__restrict__ nzwp, int64_t words, int64_t x)
+{
+    const int64_t w = x >> 5;
+    if (w >= words) return nzwp[words - 1] + __popc(nz[words - 1]);
+    return nzwp[w] + __popc(nz[w] & ((1u << (x & 31)) - 1u));
+}
+
+// Seed evaluation, first round, in two passes.  Pass one, every seed, bounded to SEED_BOUND0 positions (the first window and a little
+// more: almost every seed gives up after a handful of positions): a CTA owns 256 words of the seed bitmap of one kind (blockIdx.y =
+// deletions / duplications), the set bits are compacted into shared memory, so consecutive threads take consecutive seeds and a seed's
+// rank is the block's first rank + its index (no search).  Each seed is evaluated under its own class, or under both carried classes
+// when it is uncovered; outcomes go to `land`, successors to level 0 of the jump table.  Seeds that ran past the bound -- they sit
+// together inside events, whole CTAs of them -- go to a list, and pass two (k_seed_eval_mid, bound SEED_BOUND) takes that list one
+// thread per entry, spread evenly over the device; what runs past that bound too is "open": `todo` list + open bitmaps [kind][class].
+struct SeedTodo { uint32_t rank; uint8_t kind, variant; uint16_t pad; int32_t pos; };
 __device__ __forceinline__ int64_t seed_position(const uint32_t *__restrict__ sd, const uint32_t *__restrict__ wpk, int64_t words, uint32_t rank)
 {
     int64_t a = 0, b = words;                                  // first word whose exclusive rank exceeds `rank`, minus one
@@ -765,90 +907,204 @@ __device__ __forceinline__ uint32_t seed_outcome(const SegCtx &C, int64_t p, int
     }
     return unres;
 }
-__global__ void __launch_bounds__(128, 8) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+constexpr int SEED_CTA_WORDS = 256;
+__global__ void __launch_bounds__(256) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                   unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ todo, uint32_t todo_cap, uint32_t *__restrict__ jump0)
+                                                   unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ mid, uint32_t mid_cap, uint32_t *__restrict__ jump0)
 {
+    __shared__ uint16_t lst[SEED_CTA_WORDS * 32];
+    __shared__ uint32_t s_warp[8];
     const int kind = blockIdx.y;
-    const uint32_t rank = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rank >= (kind ? n_dup : n_del) || rank >= cap) return;
     const SegCtx &C = kind ? Cdup : Cdel;
-    const int64_t p = seed_position(seeds + (int64_t)kind * words, wp + (int64_t)kind * words, words, rank);
-    uint32_t res[2] = {LAND_NOT, LAND_NOT};
+    const uint32_t *sd = seeds + (int64_t)kind * words, *wpk = wp + (int64_t)kind * words;
+    const int64_t w0 = (int64_t)blockIdx.x * SEED_CTA_WORDS, w = w0 + threadIdx.x;
+    const uint32_t bits = w < words ? sd[w] : 0u;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t incl = __popc(bits);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (k < wid) base += s_warp[k]; total += s_warp[k]; }
+    {
+        uint32_t o = base + incl - __popc(bits), b = bits;
+        while (b) { const int bit = __ffs(b) - 1; b &= b - 1; lst[o++] = (uint16_t)((threadIdx.x << 5) | bit); }
+    }
+    __syncthreads();
+    if (!total) return;
+    const uint32_t rank0 = wpk[w0], n_seeds = kind ? n_dup : n_del, jbase = kind ? 2 * n_del + 1 : 0;
     const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
-    if (p < C.end) {
+    for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const uint32_t rank = rank0 + idx;
+        if (rank >= cap) break;
+        const uint32_t loc = lst[idx];
+        const int64_t p = ((w0 + (loc >> 5)) << 5) + (loc & 31);
+        uint32_t res[2] = {LAND_NOT, LAND_NOT};
+        int c0 = 0;
+        if (p < C.end) {
+            c0 = C.cls(p);
+            for (int v = 0; v < 2; v++) {
+                if (c0 != 2 && v == 1) { res[1] = res[0]; break; }
+                const int mi = c0 == 2 ? v : c0;
+                if (!C.beyond(p, mi)) continue;
+                res[v] = seed_outcome(C, p, mi, calls, call_cap, n_calls);
+                if (res[v] == unres) {
+                    // past the short bound of this pass: queued for the evenly spread pass over such seeds (k_seed_eval_mid)
+                    const unsigned int k = atomicAdd(n_calls + 8, 1u);
+                    if (k < mid_cap) { SeedTodo t; t.rank = rank; t.kind = (uint8_t)kind; t.variant = (uint8_t)v; t.pad = 0; t.pos = (int32_t)p; mid[k] = t; }
+                }
+            }
+        }
+        land[((int64_t)kind * cap + rank) * 2] = res[0]; land[((int64_t)kind * cap + rank) * 2 + 1] = res[1];
+        if (jump0) {
+            // successors; node ids are local to the kind, the table stores them behind the kind's base offset (2 * n_del + 1 for duplications)
+            for (int v = 0; v < 2; v++)
+                jump0[jbase + 2 * rank + v] = jbase + (p < C.end ? successor(C, sd, wpk, p, c0, v, res[v], calls, rank, n_seeds) : 2 * n_seeds);
+        }
+    }
+    if (jump0 && blockIdx.x == 0 && threadIdx.x == 0) jump0[jbase + 2 * n_seeds] = jbase + 2 * n_seeds;      // END loops on itself
+}
+
+__global__ void __launch_bounds__(128) k_seed_eval_mid(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+                                                       uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
+                                                       unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ mid, uint32_t mid_cap, SeedTodo *__restrict__ todo, uint32_t todo_cap,
+                                                       uint32_t *__restrict__ jump0, uint32_t *__restrict__ open_bits, const uint32_t *__restrict__ nz, const uint32_t *__restrict__ nzwp)
+{
+    const uint32_t n_mid = min(n_calls[8], mid_cap);
+    const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_mid; i += gridDim.x * blockDim.x) {
+        const SeedTodo t = mid[i];
+        const SegCtx &C = t.kind ? Cdup : Cdel;
+        const int64_t p = t.pos;
         const int c0 = C.cls(p);
-        for (int v = 0; v < 2; v++) {
-            if (c0 != 2 && v == 1) { res[1] = res[0]; break; }
-            const int mi = c0 == 2 ? v : c0;
-            if (!C.beyond(p, mi)) continue;
-            res[v] = seed_outcome(C, p, mi, calls, call_cap, n_calls);
-            if (res[v] == unres) {
-                const unsigned int k = atomicAdd(n_calls + 1, 1u);
-                if (k < todo_cap) { SeedTodo t; t.rank = rank; t.kind = (uint8_t)kind; t.variant = (uint8_t)v; t.pad = 0; todo[k] = t; }
+        uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
+        if (e == unres) {
+            // It passed the first window.  If no position of everything the growth phase can reach carries a z value (an uncovered
+            // stretch: full-copy loss, the start of the contig), the running sum stays exactly 0, no window length can score and
+            // the reference resumes at the next position after walking all of it (src/GROM.c:19402-19470): O(1) here.
+            const int64_t reach = min(C.len, p + max((int64_t)C.Lmin, min((int64_t)C.Lmax, C.end - p)));
+            if (nz_rank(nz, nzwp, words, reach) == nz_rank(nz, nzwp, words, p)) { e = 1u; atomicAdd(n_calls + 7, 1u); }
+        }
+        if (e == unres) {
+            const unsigned int k = atomicAdd(n_calls + 1, 1u);
+            if (k < todo_cap) todo[k] = t;
+            atomicOr(open_bits + ((int64_t)(t.kind * 2 + t.variant)) * words + (p >> 5), 1u << (p & 31));
+            if (c0 != 2) atomicOr(open_bits + ((int64_t)(t.kind * 2 + 1)) * words + (p >> 5), 1u << (p & 31));
+            continue;
+        }
+        head_publish(C, t.kind, t.rank, t.variant, p, e, seeds, words, wp, land, cap, calls, n_del, n_dup, jump0);
+    }
+}
+
+// Open seeds (ran past the bound: inside genuine events, or the uncovered stretch before the first applied read) come in runs, and the
+// path enters a run at its head -- the call made there jumps over the rest.  A head is an open seed with no open seed of its
+// (kind, class) in the HEAD_GAP positions before it; for every head the extent of its run (last open bit before a gap of HEAD_GAP) is
+// measured by the warp.  Heads are evaluated exactly (unbounded) by the host, all of them in parallel, over windows of records
+// fetched in one go; open seeds that turn out to lie on the path all the same are evaluated one by one like before (k_hop_advance).
+constexpr int HEAD_GAP = 64;
+struct SeedHead { uint32_t rank; uint8_t kind, variant; uint16_t pad; int32_t pos, run_end; };
+__global__ void __launch_bounds__(256) k_open_heads(const SeedTodo *__restrict__ todo, const unsigned int *__restrict__ n_todo_p, uint32_t todo_cap, const uint32_t *__restrict__ open_bits,
+                                                    int64_t words, SeedHead *__restrict__ heads, uint32_t head_cap, unsigned int *__restrict__ n_heads)
+{
+    const uint32_t n_todo = min(*n_todo_p, todo_cap);
+    const int lane = threadIdx.x & 31;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n_todo; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        bool head = false;
+        SeedTodo t; t.rank = 0; t.kind = 0; t.variant = 0; t.pad = 0; t.pos = 0;
+        if (i < n_todo) {
+            t = todo[i];
+            const uint32_t *ob = open_bits + (int64_t)(t.kind * 2 + t.variant) * words;
+            const int64_t p = t.pos, a = max((int64_t)0, p - HEAD_GAP);
+            head = true;
+            for (int64_t w = a >> 5; w <= (p >> 5) && head; w++) {
+                uint32_t m = ob[w];
+                if (w == (a >> 5)) m &= 0xffffffffu << (a & 31);
+                if (w == (p >> 5)) m &= (p & 31) ? (0xffffffffu >> (32 - (p & 31))) : 0u;
+                if (m) head = false;
+            }
+        }
+        unsigned hb = __ballot_sync(0xffffffffu, head);
+        while (hb) {
+            const int src = __ffs(hb) - 1; hb &= hb - 1;
+            const int kind = __shfl_sync(0xffffffffu, (int)t.kind, src), variant = __shfl_sync(0xffffffffu, (int)t.variant, src);
+            const int pos = __shfl_sync(0xffffffffu, t.pos, src);
+            const uint32_t *ob = open_bits + (int64_t)(kind * 2 + variant) * words;
+            // last open position of the run: scan 32 words per step until two consecutive empty words follow the last set bit
+            int64_t last = pos;
+            for (int64_t wbase = pos >> 5;; wbase += 32) {
+                const int64_t w = wbase + lane;
+                uint32_t m = w < words ? ob[w] : 0u;
+                if (w == (pos >> 5)) m &= 0xffffffffu << (pos & 31);
+                const unsigned nz = __ballot_sync(0xffffffffu, m != 0);
+                // first pair of consecutive empty words at or after the word holding `last`
+                bool stop = false;
+                for (int k = 0; k < 32; k++) {
+                    const uint32_t mk = __shfl_sync(0xffffffffu, m, k);
+                    const int64_t wk = wbase + k;
+                    if (mk) last = (wk << 5) + (31 - __clz(mk));
+                    else if ((wk << 5) - last > HEAD_GAP) { stop = true; break; }
+                }
+                (void)nz;
+                if (stop || wbase + 32 >= words) break;
+            }
+            if (lane == src) {
+                const unsigned int k = atomicAdd(n_heads, 1u);
+                if (k < head_cap) { SeedHead h; h.rank = t.rank; h.kind = t.kind; h.variant = t.variant; h.pad = 0; h.pos = t.pos; h.run_end = (int32_t)last; heads[k] = h; }
             }
         }
     }
-    land[((int64_t)kind * cap + rank) * 2] = res[0]; land[((int64_t)kind * cap + rank) * 2 + 1] = res[1];
-    if (jump0) {
-        // successors; node ids are local to the kind, the table stores them behind the kind's base offset (2 * n_del + 1 for duplications)
-        const uint32_t n_seeds = kind ? n_dup : n_del, base = kind ? 2 * n_del + 1 : 0;
-        const uint32_t *sd = seeds + (int64_t)kind * words, *wpk = wp + (int64_t)kind * words;
-        const int c0 = p < C.end ? C.cls(p) : 0;
-        for (int v = 0; v < 2; v++)
-            jump0[base + 2 * rank + v] = base + (p < C.end ? successor(C, sd, wpk, p, c0, v, res[v], calls, rank, n_seeds) : 2 * n_seeds);
-        if (rank == 0) jump0[base + 2 * n_seeds] = base + 2 * n_seeds;      // END loops on itself
-    }
 }
-// Second round over the compacted open seeds (full growth phase, one thread each).  Deep inside a long event every seed walks the
-// whole growth phase only to stay open (it enters the sliding phase), and none of them is ever visited: the path meets the first
-// open seed of the event, the host evaluates it and the call jumps past the rest.  So the round runs in two passes over blocks of
-// OPEN_BLOCK positions: pass 0 evaluates the first open seed of every block; pass 1 evaluates the others unless the block's first
-// seed and the next block's both stayed open.  Skipping is only a guess about cost -- a skipped seed stays open, and an open seed
-// on the path is evaluated exactly by the host like any other.
-constexpr int OPEN_BLOCK_SHIFT = 8;
-enum { OPEN_NONE = 0, OPEN_STAYS = 1, OPEN_CLOSED = 2 };
-__global__ void __launch_bounds__(256) k_open_first(const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp, const SeedTodo *__restrict__ todo,
-                                                    uint32_t n_todo, uint32_t *__restrict__ first, int64_t n_blocks)
+// outcomes of the host-evaluated heads -> land, speculative call list, level 0 of the jump table, cover bitmap (one warp per head)
+struct HeadOutcome { uint32_t rank; uint8_t kind, variant; uint16_t seg; int32_t pos, rel_next; int64_t c_end; double c_z; };
+__global__ void __launch_bounds__(128) k_apply_heads(SegCtx Cdel, SegCtx Cdup, const HeadOutcome *__restrict__ ho, uint32_t n, const uint32_t *__restrict__ seeds, int64_t words,
+                                                     const uint32_t *__restrict__ wp, uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
+                                                     unsigned int *__restrict__ n_calls, uint32_t n_del, uint32_t n_dup, uint32_t *__restrict__ jump0, uint32_t *__restrict__ cover)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_todo) return;
-    const SeedTodo t = todo[i];
-    const int64_t p = seed_position(seeds + (int64_t)t.kind * words, wp + (int64_t)t.kind * words, words, t.rank);
-    atomicMin(first + (int64_t)(t.kind * 2 + t.variant) * n_blocks + (p >> OPEN_BLOCK_SHIFT), (uint32_t)p);
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const HeadOutcome h = ho[i];
+    const SegCtx &C = h.kind ? Cdup : Cdel;
+    uint32_t e = 0;
+    int ok = 1;
+    if (lane == 0) {
+        if (h.seg == SEG_RESUME) e = (uint32_t)h.rel_next;
+        else {
+            const unsigned int k = atomicAdd(n_calls, 1u);
+            if (k >= call_cap) ok = 0;                              // stays open: the path evaluates it if it gets there
+            else { calls[k].c_end = h.c_end; calls[k].c_z = h.c_z; e = ((uint32_t)SEG_CALL << LAND_SHIFT) | k; }
+        }
+        if (ok) head_publish(C, h.kind, h.rank, h.variant, h.pos, e, seeds, words, wp, land, cap, calls, n_del, n_dup, jump0);
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    if (ok && h.seg == SEG_CALL) cover_mark(cover + (int64_t)h.kind * words, h.pos, h.c_end, lane, 32);
 }
+
+// Second round: the open seeds that are neither run heads nor under a call made at a head (the path jumps over those) get the full
+// growth phase, one thread each.  What enters the sliding phase stays open (a call longer than the largest window) and is evaluated by
+// the host if the path ever reaches it.
 __global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                   unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t n_todo, uint32_t n_del, uint32_t n_dup,
-                                                   uint32_t *__restrict__ jump0, int pass, const uint32_t *__restrict__ first, uint8_t *__restrict__ state, int64_t n_blocks)
+                                                   unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t todo_cap, uint32_t n_del, uint32_t n_dup,
+                                                   uint32_t *__restrict__ jump0, const uint32_t *__restrict__ cover)
 {
+    const uint32_t n_todo = min(n_calls[1], todo_cap);
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_todo) return;
     const SeedTodo t = todo[i];
     const SegCtx &C = t.kind ? Cdup : Cdel;
-    const int64_t p = seed_position(seeds + (int64_t)t.kind * words, wp + (int64_t)t.kind * words, words, t.rank);
     const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
-    const int64_t key = (int64_t)(t.kind * 2 + t.variant) * n_blocks + (p >> OPEN_BLOCK_SHIFT);
-    if (pass == 2) { if (land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] != unres) return; }    // sweep of whatever is still open
-    else if (pass >= 0) {
-        const bool is_first = first[key] == (uint32_t)p;
-        if (is_first != (pass == 0)) return;
-        if (pass == 1 && state[key] == OPEN_STAYS && (p >> OPEN_BLOCK_SHIFT) + 1 < n_blocks && state[key + 1] == OPEN_STAYS) { atomicAdd(n_calls + 5, 1u); return; }
-    }
+    if (land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] != unres) return;                 // a head, already closed
+    const int64_t p = t.pos;
+    if ((cover[(int64_t)t.kind * words + (p >> 5)] >> (p & 31)) & 1u) { atomicAdd(n_calls + 5, 1u); return; }      // under a call made at a head
     const int c0 = C.cls(p);
     const uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
-    if (pass == 0) state[key] = e == unres ? OPEN_STAYS : OPEN_CLOSED;
-    if (e == unres) return;                                                                // enters the sliding phase: a long call, left to the host
-    land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] = e;
-    if (c0 != 2) land[((int64_t)t.kind * cap + t.rank) * 2 + 1] = e;
-    atomicAdd(n_calls + 4, 1u);                                                            // seeds closed by the second round
-    if (jump0) {
-        const uint32_t n_seeds = t.kind ? n_dup : n_del, base = t.kind ? 2 * n_del + 1 : 0;
-        const uint32_t *sd = seeds + (int64_t)t.kind * words, *wpk = wp + (int64_t)t.kind * words;
-        const uint32_t nx = base + successor(C, sd, wpk, p, c0, t.variant, e, calls, t.rank, n_seeds);
-        jump0[base + 2 * t.rank + t.variant] = nx;
-        if (c0 != 2) jump0[base + 2 * t.rank + 1] = base + successor(C, sd, wpk, p, c0, 1, e, calls, t.rank, n_seeds);
-    }
+    if (e == unres) return;
+    atomicAdd(n_calls + 4, 1u);                                                                  // seeds closed by the second round
+    head_publish(C, t.kind, t.rank, t.variant, p, e, seeds, words, wp, land, cap, calls, n_del, n_dup, jump0);
 }
 
 // ---- K8: depth and GC bin of the called segments, packed back to back (copy-number step, src/GROM.c:20071-20224)
@@ -908,11 +1164,8 @@ struct Grow {                  // grow-only device buffer kept across calls
 
 // the reference's qsort on the copy-number ratios: glibc merge sort with the comparator `*(int*)a - *(int*)b`, i.e. ordered by the
 // low word of each double with wrapping subtraction (src/GROM.c:1105, 20113)
-inline void lowword_msort(double *b, size_t n, double *tmp)
+inline void lowword_merge(double *b, size_t n1, size_t n, double *tmp)
 {
-    if (n <= 1) return;
-    const size_t n1 = n / 2, n2 = n - n1;
-    lowword_msort(b, n1, tmp); lowword_msort(b + n1, n2, tmp);
     size_t i = 0, j = n1, k = 0;
     auto key = [](const double &d) { uint64_t u; memcpy(&u, &d, 8); return (uint32_t)u; };
     while (i < n1 && j < n) {
@@ -920,6 +1173,24 @@ inline void lowword_msort(double *b, size_t n, double *tmp)
     }
     while (i < n1) tmp[k++] = b[i++];
     memcpy(b, tmp, k * sizeof(double));
+}
+inline void lowword_msort(double *b, size_t n, double *tmp)
+{
+    if (n <= 1) return;
+    const size_t n1 = n / 2, n2 = n - n1;
+    lowword_msort(b, n1, tmp); lowword_msort(b + n1, n2, tmp);
+    lowword_merge(b, n1, n, tmp);
+}
+// the same merge tree with the two halves of the top `fork` levels sorted by different threads: every merge sees the same two
+// inputs as in the sequential order of evaluation, so the result is identical (the comparator is not transitive, the tree is what counts)
+inline void lowword_msort_par(double *b, size_t n, double *tmp, int fork)
+{
+    if (fork <= 0 || n < 8192) { lowword_msort(b, n, tmp); return; }
+    const size_t n1 = n / 2, n2 = n - n1;
+    std::thread left([=]() { lowword_msort_par(b, n1, tmp, fork - 1); });
+    lowword_msort_par(b + n1, n2, tmp + n1, fork - 1);
+    left.join();
+    lowword_merge(b, n1, n, tmp);
 }
 
 // the sequential part that is left: hop from seed to seed (src/GROM.c:19370-19389, 19670-19676)

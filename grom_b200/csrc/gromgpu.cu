@@ -19,6 +19,7 @@
 #include <string.h>
 #include <stdarg.h>
 #include <algorithm>
+#include <atomic>
 #include <limits>
 #include <vector>
 #include <chrono>
@@ -245,14 +246,17 @@ __global__ void __launch_bounds__(256) k_read_prep(DevReads R, int tid, int64_t 
     }
 }
 
-// ---- tile -> index of the first read that can overlap it: lower_bound(pos, tile_start - max_span)
-__global__ void __launch_bounds__(256) k_tile_index(const int32_t *pos, int64_t n, const int *max_span, int64_t n_tiles, int64_t *tile_first)
+// ---- tile -> index of the first read that reaches it: lower_bound(pos, tile_start - max_span), then forward past the reads that end
+// before the tile (one long-span read -- a spliced alignment, a long deletion -- raises max_span for the whole contig, but only the tiles
+// under it pay for it)
+__global__ void __launch_bounds__(256) k_tile_index(const int32_t *pos, const PrepRec *__restrict__ prep, int64_t n, const int *max_span, int64_t n_tiles, int64_t *tile_first)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
-    const int64_t key = t * TILE - (int64_t)(*max_span);
+    const int64_t tile_lo = t * TILE, key = tile_lo - (int64_t)(*max_span);
     int64_t lo = 0, hi = n;
     while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)pos[mid] < key) lo = mid + 1; else hi = mid; }
+    while (lo < n && (int64_t)pos[lo] < tile_lo && (!(prep[lo].misc & PR_APPLIED) || (int64_t)prep[lo].ext_end <= tile_lo)) lo++;
     tile_first[t] = lo;
 }
 
@@ -378,6 +382,7 @@ struct __align__(16) StageB { uint32_t u_cov, u_all, u_hi; int v_pir; };
 struct __align__(16) StageD { int pir_c; int pir_s; int lq; uint32_t flags; };          // position-in-read = off * pir_s + pir_c (src/GROM.c:6853-6864)
 struct __align__(16) StageC { uint64_t hash; uint32_t cig_off, n_cigar; };
 struct __align__(8)  StageE { uint32_t base16; int ext_end; };
+struct __align__(16) StageF { uint32_t op[4]; };                  // the CIGAR of a read with <= 4 operations (clipped reads, one indel): no global loads in the per-lane walk
 #define SF_COMPLEX 1u             // needs the general CIGAR walk (or CNV-depth bound fails, or bases are not staged)
 #define SF_GLOBAL  2u             // bases longer than a stage: read them from global memory
 #define SF_REV     4u
@@ -405,6 +410,7 @@ struct __align__(128) PileSmem {
     StageD d[NSTAGE][CHUNK];
     StageC c[NSTAGE][CHUNK];
     StageE e[NSTAGE][CHUNK];
+    StageF f[NSTAGE][CHUNK];
     int2 rng[NSTAGE][NWARP];      // per consumer warp: slice [t0, t1) of the staged reads that can reach its 32 positions
     uint64_t full[NSTAGE], empty[NSTAGE];
     int last[NSTAGE];
@@ -466,6 +472,17 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                     const unsigned bw = __ballot_sync(0xffffffffu, want[h]);
                     if (bw) first_idx = min(first_idx, RPL * (__ffs(bw) - 1) + h);
                 }
+                // short CIGARs of the reads that need the general walk travel with the stage (loads issued here, consumed after the waits below)
+                StageF cg4[RPL];
+#pragma unroll
+                for (int h = 0; h < RPL; h++) {
+                    cg4[h].op[0] = cg4[h].op[1] = cg4[h].op[2] = cg4[h].op[3] = 0u;
+                    const bool fast_h = (r[h].misc & PR_SIMPLE) && !big[h] && (int64_t)r[h].pos + (int64_t)(r[h].misc >> 16) < P;     // same test as below
+                    if (use[h] && !fast_h && r[h].n_cigar <= 4u) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if ((uint32_t)k < r[h].n_cigar) cg4[h].op[k] = __ldg(R.cigar + r[h].cig_off + k);
+                    }
+                }
                 uint32_t base_first = 0;
                 if (first_idx < CHUNK) {
                     uint32_t cand = 0;
@@ -500,18 +517,18 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                 const int64_t next_after = last ? next_tile_first : next + count;
                 PrepRec nx[RPL];
                 load_group(next_after, nx);
-                // per consumer warp: staged reads with pos in (wlo - max_span, whi] (lane w keeps the range of warp w)
+                // per consumer warp: staged reads from the first one that reaches the warp's 32 positions (ext_end > wlo) to the last one that
+                // starts at or before them (lane w keeps the range of warp w).  No dependence on the contig-wide max_span.
+                static_assert(RPL == 1, "the per-warp slices index the compacted stage by lane");
                 int2 my_rng = make_int2(0, 0);
+                const unsigned stmask = __ballot_sync(0xffffffffu, st[0]);
 #pragma unroll
                 for (int w = 0; w < NWARP; w++) {
-                    const int wlo = (int)tile_lo + 32 * w, key = wlo - max_span, whi = wlo + 31;
-                    int t0 = 0, t1 = 0;
-#pragma unroll
-                    for (int h = 0; h < RPL; h++) {
-                        t0 += __popc(__ballot_sync(0xffffffffu, st[h] && r[h].pos <= key));
-                        t1 += __popc(__ballot_sync(0xffffffffu, st[h] && r[h].pos <= whi));
-                    }
-                    if (lane == w) my_rng = make_int2(t0, t1);
+                    const int wlo = (int)tile_lo + 32 * w, whi = wlo + 31;
+                    const int t1 = __popc(__ballot_sync(0xffffffffu, st[0] && r[0].pos <= whi));
+                    const unsigned reach = __ballot_sync(0xffffffffu, st[0] && r[0].ext_end > wlo);
+                    const int t0 = reach ? __popc(stmask & ((1u << (__ffs(reach) - 1)) - 1u)) : t1;
+                    if (lane == w) my_rng = make_int2(min(t0, t1), t1);
                 }
                 // everything above ran while the position threads were still reading this stage's previous contents
                 if (c >= NSTAGE) mbar_wait(smem_u32(&S.empty[buf]), (uint32_t)((c / NSTAGE - 1) & 1));
@@ -540,7 +557,7 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                         D.flags = (fast ? 0u : SF_COMPLEX) | (big[h] ? SF_GLOBAL : 0u) | (rev ? SF_REV : 0u) | ((rr.misc & PR_NAMEOK) ? SF_NAMEOK : 0u) | ((mq >= q) ? SF_MQOK : 0u);
                         StageC C; C.hash = rr.hash; C.cig_off = rr.cig_off; C.n_cigar = rr.n_cigar;
                         StageE E; E.base16 = rr.base16; E.ext_end = rr.ext_end;
-                        S.a[buf][t] = A; S.b[buf][t] = B; S.d[buf][t] = D; S.c[buf][t] = C; S.e[buf][t] = E;
+                        S.a[buf][t] = A; S.b[buf][t] = B; S.d[buf][t] = D; S.c[buf][t] = C; S.e[buf][t] = E; S.f[buf][t] = cg4[h];
                         t++;
                     }
                 }
@@ -640,8 +657,10 @@ __global__ void __launch_bounds__(PILE_THREADS, PILE_MIN_CTAS) k_pileup(DevReads
                         const uint32_t gmisc = (uint32_t)r_mq | ((D.flags & SF_REV) ? PR_REV : 0u) | ((D.flags & SF_NAMEOK) ? PR_NAMEOK : 0u);
                         const int ncig_all = (int)C.n_cigar, ncig = min(ncig_all, max_cig);
                         int qi = 0, rp = A.pos, rdp = A.pos, lseq = D.lq;
+                        const bool staged_cigar = ncig_all <= 4;
+                        const StageF F = S.f[buf][t];
                         for (int k = 0; k < ncig_all; k++) {
-                            const uint32_t cg = __ldg(R.cigar + C.cig_off + k);
+                            const uint32_t cg = staged_cigar ? (k == 0 ? F.op[0] : k == 1 ? F.op[1] : k == 2 ? F.op[2] : F.op[3]) : __ldg(R.cigar + C.cig_off + k);
                             const int op = cg & 15, len = (int)(cg >> 4);
                             const bool in_pile = k < ncig;
                             if (op == OP_M || op == OP_EQ || op == OP_X) {
@@ -1686,7 +1705,7 @@ static int chr_run_once(gromgpu_chr *h, bool *again)
     CK(cudaEventRecord(h->ev[2], s));
     if (n) { k_read_prep<<<rb, 256, 0, s>>>(R, h->tid, P, Ppad, h->d_state, h->d_prep, h->d_arrays, h->d_max_span, h->d_counters); launches++; }
     CK(cudaEventRecord(h->ev[3], s));
-    k_tile_index<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(R.pos, n, h->d_max_span, n_tiles, h->d_tile_first); launches++;
+    k_tile_index<<<(unsigned)((n_tiles + 255) / 256), 256, 0, s>>>(R.pos, h->d_prep, n, h->d_max_span, n_tiles, h->d_tile_first); launches++;
     CK(cudaEventRecord(h->ev[4], s));
     // ---- SV / indel evidence: items in BAM order, per-tile fold, then the five range-add prefix scans
     SvDev SD;
@@ -1888,7 +1907,10 @@ struct CnvState {
     int64_t P = 0, words = 0;
     int q = 0;
     std::vector<double> sd_tbl, wtab;
-    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, open_first, open_state;
+    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, heads, head_out, mid;
+    uint32_t *d_open = nullptr;                              // [2 kinds][2 classes][words]: seeds still open after the first round
+    cnv::SeedHead *h_heads = nullptr; cnv::HeadOutcome *h_head_out = nullptr;      // pinned
+    uint32_t *h_win = nullptr; size_t h_win_cap = 0;         // pinned landing area of the record windows of the run heads
     void *h_gather = nullptr; size_t h_gather_cap = 0;      // pinned landing area of the gathered call ranges (depth, GC byte, record per position)
     cudaStream_t copy_stream = nullptr; cudaEvent_t ev_z = nullptr, ev_copied = nullptr, e0 = nullptr, e1 = nullptr;   // packed records travel to the host while the sweep runs
 };
@@ -1899,7 +1921,11 @@ static void cnv_state_free(CnvState *c)
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
-    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->open_first, &c->open_state}) if (g->p) cudaFree(g->p);
+    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->heads, &c->head_out, &c->mid}) if (g->p) cudaFree(g->p);
+    cudaFree(c->d_open);
+    if (c->h_heads) cudaFreeHost(c->h_heads);
+    if (c->h_head_out) cudaFreeHost(c->h_head_out);
+    if (c->h_win) cudaFreeHost(c->h_win);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_z) cudaEventDestroy(c->ev_z);
     if (c->ev_copied) cudaEventDestroy(c->ev_copied);
@@ -1983,7 +2009,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     c.words = words;
     if (!c.d_depth) {
         CK(cudaMalloc(&c.d_depth, sizeof(int32_t) * P)); CK(cudaMalloc(&c.d_mq8, P)); CK(cudaMalloc(&c.d_rec, sizeof(uint32_t) * P));
-        CK(cudaMalloc(&c.d_seed, sizeof(uint32_t) * 2 * words)); CK(cudaMalloc(&c.d_pre, sizeof(PreOut) * n_blk));
+        CK(cudaMalloc(&c.d_seed, sizeof(uint32_t) * 3 * words));      // deletion seeds, duplication seeds, positions with a z value
+        CK(cudaMalloc(&c.d_pre, sizeof(PreOut) * n_blk));
+        CK(cudaMalloc(&c.d_open, sizeof(uint32_t) * 6 * words));       // [2][2][words] open seeds + [2][words] positions under calls made at run heads
         CK(cudaMalloc(&c.d_hist, sizeof(unsigned long long) * HIST_ALL));
         c.rep_cap = (unsigned int)(P / 20 + 2);
         CK(cudaMalloc(&c.d_rep, sizeof(RepRec) * c.rep_cap)); CK(cudaMalloc(&c.d_nrep, sizeof(unsigned int)));
@@ -1992,12 +2020,12 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c.ev_z, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.ev_copied, cudaEventDisableTiming));
         c.nb = (int)((words + SEED_WORDS - 1) / SEED_WORDS); c.land_cap = (uint32_t)(P / 4 + 1024);
-        CK(cudaMalloc(&c.d_blk, sizeof(uint32_t) * (2 * c.nb + 2))); CK(cudaMalloc(&c.d_wp, sizeof(uint32_t) * 2 * words));
+        CK(cudaMalloc(&c.d_blk, sizeof(uint32_t) * (3 * c.nb + 4))); CK(cudaMalloc(&c.d_wp, sizeof(uint32_t) * 3 * words));
         CK(cudaMalloc(&c.d_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
         CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * words)); CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
         c.spec_cap = (uint32_t)std::min<int64_t>(P / 8 + 1024, (int64_t)1 << 28);
         CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
-        CK(cudaMalloc(&c.d_nspec, 8 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * 2 * (Lmax + 1)));      // win_sd, then win_thr
+        CK(cudaMalloc(&c.d_nspec, 16 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * 2 * (Lmax + 1)));      // win_sd, then win_thr
     }
 
     // ---- stage 1: pre-statistics + repeat runs
@@ -2306,12 +2334,12 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     k_z<<<(unsigned)n_tiles, 256, 0, s>>>(c.d_depth, A_gc, P, lo, hi, q, T, ti_z, c.d_rec, c.d_seed, c.d_seed + words); n_launch++;
     uint32_t seed_tot[2] = {0, 0};
     k_seed_blocksum<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb); n_launch++;
-    k_seed_blockscan<<<2, 1024, 0, s>>>(c.d_blk, c.nb, c.d_blk + 2 * c.nb); n_launch++;
+    k_seed_blockscan<<<2, 1024, 0, s>>>(c.d_blk, c.nb, c.d_blk + 3 * c.nb); n_launch++;
     k_seed_rank<<<dim3((unsigned)c.nb, 2), 256, 0, s>>>(c.d_seed, words, c.d_blk, c.nb, c.d_wp); n_launch++;
-    CK(cudaMemcpyAsync(seed_tot, c.d_blk + 2 * c.nb, sizeof(seed_tot), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(seed_tot, c.d_blk + 3 * c.nb, sizeof(seed_tot), cudaMemcpyDeviceToHost, s));
     if (n_frames) {
         CK(cudaMemcpyAsync(t_sw.p, sw.data(), sizeof(SweepBlock) * n_sb, cudaMemcpyHostToDevice, s));
-        k_sweep<<<(unsigned)((n_frames + 31) / 32), 32, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, T.p2s_sd + P2S, t_X.as<double>()); n_launch++;
+        k_sweep<<<(unsigned)((n_frames + 31) / 32), 32 * SW_WARPS, 0, s>>>(c.d_rec, t_sw.as<SweepBlock>(), n_sb, n_frames, A, Lmin, Lmax, q, T.p2s_sd, T.p2s_sd + P2S, t_X.as<double>()); n_launch++;
         k_sweep_sum<<<(unsigned)((n_len + 31) / 32), 256, SSUM_ST * SSUM_FR * 32 * sizeof(double), s>>>(t_X.as<double>(), n_frames, n_len, t_wsq.as<double>(), t_wcnt.as<long long>()); n_launch++;
         CK(cudaMemcpyAsync(wsq.data(), t_wsq.p, sizeof(double) * n_len, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(wcnt.data(), t_wcnt.p, sizeof(long long) * n_len, cudaMemcpyDeviceToHost, s));
@@ -2384,7 +2412,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(c.d_winsd + (Lmax + 1), c.win_thr.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
-            CK(cudaMemsetAsync(c.d_nspec, 0, 8 * sizeof(unsigned int), s));
+            CK(cudaMemsetAsync(c.d_nspec, 0, 16 * sizeof(unsigned int), s));
             // every (seed, carried class) can stay open after the first round (a contig full of long events): room for all of them
             const uint32_t todo_cap = (uint32_t)std::min<uint64_t>(2ull * ((uint64_t)seed_tot[0] + seed_tot[1]) + 64, 1ull << 28);
             Grow &t_todo = c.tmp[15];
@@ -2400,49 +2428,152 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             uint32_t *J = jump_ok ? c.jump.as<uint32_t>() : nullptr;
             uint8_t *flag = jump_ok ? c.flags.as<uint8_t>() : nullptr;
             const uint32_t most = std::max(seed_tot[0], seed_tot[1]);
-            if (most) { k_seed_eval<<<dim3((most + 127) / 128, 2), 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
-                                                                              c.d_nspec, t_todo.as<SeedTodo>(), todo_cap, J); n_launch++; }
-            unsigned int cnt2[2] = {0, 0};
-            CK(cudaMemcpyAsync(cnt2, c.d_nspec, sizeof(cnt2), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemsetAsync(c.d_open, 0, sizeof(uint32_t) * 4 * (size_t)words, s));
+            // positions with a z value (after the biased-repeat override, if any), ranked like the seed bitmaps
+            uint32_t *d_nz = c.d_seed + 2 * words, *d_nzwp = c.d_wp + 2 * words;
+            k_nz_bits<<<(unsigned)((words * 32 + 255) / 256), 256, 0, s>>>(c.d_rec, P, d_nz); n_launch++;
+            k_seed_blocksum<<<dim3((unsigned)c.nb, 1), 256, 0, s>>>(d_nz, words, c.d_blk + 2 * c.nb, c.nb); n_launch++;
+            k_seed_blockscan<<<1, 1024, 0, s>>>(c.d_blk + 2 * c.nb, c.nb, c.d_blk + 3 * c.nb + 2); n_launch++;
+            k_seed_rank<<<dim3((unsigned)c.nb, 1), 256, 0, s>>>(d_nz, words, c.d_blk + 2 * c.nb, c.nb, d_nzwp); n_launch++;
+            if (most) {
+                Grow &t_mid = c.mid;
+                if (!t_mid.ensure(sizeof(SeedTodo) * (size_t)todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
+                ctx[0].bound = ctx[1].bound = SEED_BOUND0;
+                k_seed_eval<<<dim3((unsigned)((words + SEED_CTA_WORDS - 1) / SEED_CTA_WORDS), 2), 256, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
+                                                                                                                   c.d_nspec, t_mid.as<SeedTodo>(), todo_cap, J); n_launch++;
+                ctx[0].bound = ctx[1].bound = SEED_BOUND;
+                k_seed_eval_mid<<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
+                                                        t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp); n_launch++;
+            }
+            // Open seeds (ran past the first round's bound: genuine events and long stretches without coverage).  The heads of their runs are
+            // evaluated exactly by the host, all in parallel, over windows of records fetched in one go (a long walk is a dependent chain:
+            // ~1 us per position for a lone GPU thread, ~10 ns on a host core); then the open seeds that no call made at a head covers get
+            // the full growth phase on the device, one thread each.  Whatever is still open after that is a sink of the jump table.
+            constexpr uint32_t HEAD_CAP = 1u << 16;
+            if (!c.heads.ensure(sizeof(SeedHead) * (size_t)HEAD_CAP) || !c.head_out.ensure(sizeof(HeadOutcome) * (size_t)HEAD_CAP)) return fail("gromgpu_chr_cnv: out of device memory");
+            if (!c.h_heads) { CK(cudaMallocHost(&c.h_heads, sizeof(SeedHead) * (size_t)HEAD_CAP + 64)); CK(cudaMallocHost(&c.h_head_out, sizeof(HeadOutcome) * (size_t)HEAD_CAP)); }
+            unsigned int *n_heads_d = c.d_nspec + 6;
+            uint32_t *d_cover = c.d_open + 4 * words;                    // [2 kinds][words]
+            CK(cudaMemsetAsync(d_cover, 0, sizeof(uint32_t) * 2 * (size_t)words, s));
+            k_open_heads<<<592, 256, 0, s>>>(t_todo.as<SeedTodo>(), c.d_nspec + 1, todo_cap, c.d_open, words, c.heads.as<SeedHead>(), HEAD_CAP, n_heads_d); n_launch++;
+            ctx[0].bound = ctx[1].bound = Lmax;                     // second round: the whole growth phase
+            unsigned int *h_cnt = (unsigned int *)((char *)c.h_heads + sizeof(SeedHead) * (size_t)HEAD_CAP);       // [0] open seeds [1] heads
+            CK(cudaMemcpyAsync(h_cnt, c.d_nspec + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(h_cnt + 1, n_heads_d, sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(c.h_heads, c.heads.p, sizeof(SeedHead) * 4096, cudaMemcpyDeviceToHost, s));                 // the usual case in the same round trip
             CK(cudaStreamSynchronize(s));
-            mark("  seeds, first round");
-            const unsigned int n_todo = std::min(cnt2[1], todo_cap);
+            const unsigned int n_open = h_cnt[0];
+            const unsigned int n_heads_all = std::min(h_cnt[1], HEAD_CAP);
+            if (n_heads_all > 4096) { CK(cudaMemcpyAsync(c.h_heads, c.heads.p, sizeof(SeedHead) * (size_t)n_heads_all, cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); }
+            unsigned int n_heads = 0;                                   // heads the device round left open, compacted to the front
+            for (unsigned int i = 0; i < n_heads_all; i++) if (!c.h_heads[i].pad) c.h_heads[n_heads++] = c.h_heads[i];
+            mark("  seeds, first round + heads (device)");
+            if (trace) for (unsigned int i = 0; i < std::min(n_heads, 6u); i++) fprintf(stderr, "[cnv]     head %u: kind %d class %d pos %d run end %d (%d positions)\n", i, c.h_heads[i].kind, c.h_heads[i].variant, c.h_heads[i].pos, c.h_heads[i].run_end, c.h_heads[i].run_end - c.h_heads[i].pos);
             device_hop = jump_ok;                              // GROMGPU_CNV_HOST_SCAN forces the host scan (tests)
+            unsigned int n_head_done = 0;
+            if (n_heads) {
+                // windows: [head, end of its run + the sliding phase's look-ahead); overlapping windows share one copy
+                const SeedHead *hd = c.h_heads;
+                std::vector<uint32_t> order(n_heads);
+                for (uint32_t i = 0; i < n_heads; i++) order[i] = i;
+                std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return hd[x].pos < hd[y].pos; });
+                const int64_t look = 2 * (int64_t)Lmax + 2048;
+                struct Seg { int64_t a, b, off; };
+                std::vector<Seg> segs; std::vector<uint32_t> seg_of(n_heads);
+                int64_t total = 0;
+                const int64_t budget = (int64_t)64 << 20;                    // records (256 MB) fetched for heads at most; the rest stays open
+                uint32_t n_take = 0;
+                for (uint32_t oi = 0; oi < n_heads; oi++) {
+                    const SeedHead &h0 = hd[order[oi]];
+                    const int64_t a0 = h0.pos, b0 = std::min<int64_t>(P, (int64_t)h0.run_end + look);
+                    if (!segs.empty() && a0 <= segs.back().b) { const int64_t grow = std::max<int64_t>(0, b0 - segs.back().b); if (total + grow > budget) break; segs.back().b += grow; total += grow; }
+                    else { if (total + (b0 - a0) > budget) break; segs.push_back({a0, b0, total}); total += b0 - a0; }
+                    seg_of[oi] = (uint32_t)segs.size() - 1; n_take = oi + 1;
+                }
+                if ((size_t)total * 4 > c.h_win_cap) {
+                    if (c.h_win) cudaFreeHost(c.h_win);
+                    c.h_win = nullptr; c.h_win_cap = 0;
+                    CK(cudaMallocHost(&c.h_win, (size_t)total * 5));
+                    c.h_win_cap = (size_t)total * 5;
+                }
+                for (const Seg &g : segs) CK(cudaMemcpyAsync(c.h_win + g.off, c.d_rec + g.a, sizeof(uint32_t) * (size_t)(g.b - g.a), cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                d2h += 4 * total + (int64_t)sizeof(SeedHead) * n_heads_all;
+                mark("  head windows D2H");
+                HeadOutcome *ho = c.h_head_out;
+                std::vector<uint8_t> ok(n_take, 0);
+                auto eval_one = [&](uint32_t oi, int64_t *call_end) {
+                    const SeedHead &h0 = hd[order[oi]];
+                    const Seg &g = segs[seg_of[oi]];
+                    SegCtx hc = ctx[h0.kind];
+                    hc.rec = c.h_win + g.off - g.a; hc.len = g.b; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data(); hc.win_thr = c.win_thr.data(); hc.wtab = c.wtab.data(); hc.zarr = nullptr;
+                    const int c0 = hc.cls(h0.pos);
+                    const Outcome o = eval_seed<false>(hc, h0.pos, c0 != 2 ? c0 : h0.variant);
+                    if (g.b < P && o.far >= g.b) return;                  // the sliding phase ran into the window's end: left open (the path evaluates it if it gets there)
+                    HeadOutcome &r = ho[oi];
+                    r.rank = h0.rank; r.kind = h0.kind; r.variant = h0.variant; r.seg = (uint16_t)o.kind; r.pos = h0.pos;
+                    r.rel_next = (int32_t)(o.next - h0.pos); r.c_end = o.c_end; r.c_z = o.c_z;
+                    ok[oi] = 1;
+                    if (o.kind == SEG_CALL) *call_end = o.c_end;
+                };
+                // Heads come in clusters (the fragments of one event); the path enters a cluster at its first head and the call made there
+                // usually jumps over most of the others.  So a cluster is walked in position order by ONE thread that skips the heads under
+                // the calls it has made so far, and the clusters are spread over the threads.  Skipped heads stay open (and end up under the
+                // cover bitmap); should the path reach one after all, it is evaluated then.
+                std::vector<uint32_t> cl_first;                               // index (in position order) of the first head of every cluster
+                for (uint32_t oi = 0; oi < n_take; oi++)
+                    if (oi == 0 || hd[order[oi]].pos - hd[order[oi - 1]].pos > 2 * (int64_t)Lmax) cl_first.push_back(oi);
+                cl_first.push_back(n_take);
+                const uint32_t n_cl = (uint32_t)cl_first.size() - 1;
+                std::atomic<uint32_t> next_cl(0);
+                auto cluster_worker = [&]() {
+                    for (;;) {
+                        const uint32_t k = next_cl.fetch_add(1);
+                        if (k >= n_cl) return;
+                        int64_t under[2] = {-1, -1};                          // end of the calls made so far, per kind
+                        for (uint32_t oi = cl_first[k]; oi < cl_first[k + 1]; oi++) {
+                            const SeedHead &h0 = hd[order[oi]];
+                            if (h0.pos <= under[h0.kind]) continue;
+                            int64_t ce = -1;
+                            eval_one(oi, &ce);
+                            if (ce + 1 > under[h0.kind]) under[h0.kind] = ce + 1;
+                        }
+                    }
+                };
+                {
+                    const unsigned T = std::max(1u, std::min<unsigned>(std::min<unsigned>(16, std::thread::hardware_concurrency()), n_cl));
+                    std::vector<std::thread> pool;
+                    for (unsigned t = 1; t < T; t++) pool.emplace_back(cluster_worker);
+                    cluster_worker();
+                    for (auto &x : pool) x.join();
+                }
+                for (uint32_t oi = 0; oi < n_take; oi++) if (ok[oi]) { if (n_head_done != oi) ho[n_head_done] = ho[oi]; n_head_done++; }
+                mark("  heads evaluated (host)");
+                if (n_head_done) {
+                    CK(cudaMemcpyAsync(c.head_out.p, ho, sizeof(HeadOutcome) * (size_t)n_head_done, cudaMemcpyHostToDevice, s));
+                    k_apply_heads<<<(n_head_done * 32 + 127) / 128, 128, 0, s>>>(ctx[0], ctx[1], c.head_out.as<HeadOutcome>(), n_head_done, c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap,
+                                                                                 c.d_nspec, seed_tot[0], seed_tot[1], J, d_cover); n_launch++;
+                }
+            }
+            if (n_open) {
+                const uint32_t n_todo = std::min(n_open, todo_cap);
+                k_seed_eval2<<<(n_todo + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), todo_cap,
+                                                               seed_tot[0], seed_tot[1], J, d_cover); n_launch++;
+                if (trace) {
+                    unsigned int dbg[8];
+                    CK(cudaMemcpyAsync(dbg, c.d_nspec, sizeof(dbg), cudaMemcpyDeviceToHost, s));
+                    CK(cudaStreamSynchronize(s));
+                    mark("  seeds, second round");
+                    fprintf(stderr, "[cnv]   %u open seeds after the first round (%u zero-stretch seeds closed in O(1) before that); %u run heads, %u left to the host; second round: %u closed, %u skipped under calls made at heads\n",
+                            n_open, dbg[7], n_heads_all, n_heads, dbg[4], dbg[5]);
+                }
+            }
             if (device_hop) {
             if (most == 0) CK(cudaMemsetAsync(J, 0, sizeof(uint32_t) * n_nodes, s));
             if (seed_tot[0] == 0 || seed_tot[1] == 0) {                // a scan without seeds: its END node loops on itself
                 const uint32_t e0 = base[0] + 2 * seed_tot[0], e1 = base[1] + 2 * seed_tot[1];
                 if (seed_tot[0] == 0) CK(cudaMemcpyAsync(J + e0, &e0, 4, cudaMemcpyHostToDevice, s));
                 if (seed_tot[1] == 0) CK(cudaMemcpyAsync(J + e1, &e1, 4, cudaMemcpyHostToDevice, s));
-            }
-            // Seeds that ran past the first bound (inside genuine events, or the uncovered start of the contig) are compacted and get the
-            // full growth phase, one thread each.  What is still open afterwards enters the sliding phase, i.e. is a call longer than
-            // the largest window: only the first such seed of each event lies on the path, and the host evaluates that one.
-            const int64_t n_oblk = (P >> OPEN_BLOCK_SHIFT) + 1;
-            bool two_pass = false;
-            auto second_round = [&](int pass) {
-                k_seed_eval2<<<(n_todo + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), n_todo,
-                                                               seed_tot[0], seed_tot[1], J, pass, c.open_first.as<uint32_t>(), c.open_state.as<uint8_t>(), n_oblk); n_launch++;
-            };
-            if (n_todo) {
-                ctx[0].bound = ctx[1].bound = Lmax;
-                // many open seeds mean long events: two passes, the second skips the interior of what the first found to stay open
-                two_pass = n_todo > 65536 && c.open_first.ensure(sizeof(uint32_t) * 4 * (size_t)n_oblk) && c.open_state.ensure(4 * (size_t)n_oblk);
-                if (two_pass) {
-                    CK(cudaMemsetAsync(c.open_first.p, 0xff, sizeof(uint32_t) * 4 * (size_t)n_oblk, s));
-                    CK(cudaMemsetAsync(c.open_state.p, 0, 4 * (size_t)n_oblk, s));
-                    k_open_first<<<(n_todo + 255) / 256, 256, 0, s>>>(c.d_seed, words, c.d_wp, t_todo.as<SeedTodo>(), n_todo, c.open_first.as<uint32_t>(), n_oblk); n_launch++;
-                    if (trace) { CK(cudaStreamSynchronize(s)); mark("    open-block table"); }
-                    second_round(0);
-                    if (trace) { CK(cudaStreamSynchronize(s)); mark("    pass 0"); }
-                    second_round(1);
-                } else { cudaGetLastError(); second_round(-1); }
-                if (trace) {
-                    unsigned int dbg[8];
-                    CK(cudaMemcpyAsync(dbg, c.d_nspec, sizeof(dbg), cudaMemcpyDeviceToHost, s));
-                    CK(cudaStreamSynchronize(s)); mark("  seeds, second round");
-                    fprintf(stderr, "[cnv]   second round: %u open seeds, %u closed, %u skipped as interior\n", n_todo, dbg[4], dbg[5]);
-                }
             }
             for (int k = 1; k < levels; k++) { k_hop_double<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)(k - 1) * n_nodes, J + (size_t)k * n_nodes, n_nodes); n_launch++; }
             CK(cudaMemsetAsync(flag, 0, (size_t)n_nodes, s));
@@ -2454,9 +2585,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             std::vector<uint32_t> window;
             HopLeg leg[2] = {{lo, 0, 1}, {lo, 0, 1}};
             int64_t n_legs = 0;
-            int no_call = 0; bool swept = false;
+            int no_call = 0; bool too_many_legs = false;
             while (leg[0].active || leg[1].active) {
-                if (++n_legs > (int64_t)2 * most + 4) return fail("gromgpu_chr_cnv: the device hop did not terminate");
+                if (++n_legs > 512) { too_many_legs = true; break; }      // open seeds keep turning up on the path: the host scan below takes over
                 k_hop_advance<<<1, 2, 0, s>>>(ctx[0], ctx[1], c.d_seed, c.d_wp, words, J + (size_t)(levels - 1) * n_nodes, leg[0], leg[1], seed_tot[0], seed_tot[1], flag,
                                               c.hop_sink.as<HopSink>()); n_launch++;
                 HopSink sink[2];
@@ -2482,16 +2613,12 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                     if (o.kind == SEG_CALL) by_host[k].push_back({pos, o.c_end, o.c_z}); else no_call++;
                     leg[k].x = o.next; leg[k].s = c0 != 2 ? c0 : sink[k].variant;
                 }
-                if (two_pass && no_call > 32) {
-                    // the guess was wrong somewhere (skipped seeds that are no calls keep turning up on the path): close whatever is still open
-                    second_round(2);
-                    for (int k = 1; k < levels; k++) { k_hop_double<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)(k - 1) * n_nodes, J + (size_t)k * n_nodes, n_nodes); n_launch++; }
-                    two_pass = false; swept = true;
-                }
             }
-            unsigned int still_open = 0;
-            if (trace) { CK(cudaMemcpyAsync(&still_open, c.d_nspec + 4, sizeof(still_open), cudaMemcpyDeviceToHost, s)); CK(cudaStreamSynchronize(s)); still_open = cnt2[1] - still_open; }
             mark("  jump table + legs");
+            if (too_many_legs) {
+                dev_end(); device_hop = false;
+                if (trace) fprintf(stderr, "[cnv] more than 512 open seeds on the path: leaving the hop to the host scan\n");
+            } else {
             for (int k = levels - 1; k >= 0; k--) { k_hop_mark<<<(n_nodes + 255) / 256, 256, 0, s>>>(J + (size_t)k * n_nodes, flag, n_nodes); n_launch++; }
             for (int k = 0; k < 2; k++) if (seed_tot[k]) {
                 k_hop_collect<<<(2 * seed_tot[k] + 255) / 256, 256, 0, s>>>(flag + base[k], c.d_land + (size_t)k * 2 * c.land_cap, c.d_seed + k * words, c.d_wp + k * words, words,
@@ -2511,9 +2638,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 std::sort(found[k].begin(), found[k].end(), [](const Call &a, const Call &b) { return a.start < b.start; });
             }
             seed_tot_all = 0; n_spec_all = 0;
-            if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u (%u left unresolved), jump table %d levels x %u nodes, %lld legs; calls from the device %u + %u, from host-evaluated seeds %zu + %zu\n",
-                               seed_tot[0], seed_tot[1], still_open, levels, n_nodes, (long long)n_legs, n_got[0], n_got[1], by_host[0].size(), by_host[1].size());
-            if (trace) fprintf(stderr, "[cnv] %u seeds open after the first round%s\n", cnt2[1], swept ? "; the second round needed a sweep" : "");
+            if (trace) fprintf(stderr, "[cnv] seeds del %u dup %u; %u open after the first round, %u run heads, %u evaluated by the host up front; jump table %d levels x %u nodes, %lld legs (%d sinks met on the path without a call); calls from the device %u + %u, from seeds met on the path %zu + %zu\n",
+                               seed_tot[0], seed_tot[1], n_open, n_heads_all, n_head_done, levels, n_nodes, (long long)n_legs, no_call, n_got[0], n_got[1], by_host[0].size(), by_host[1].size());
+            }
             } else { dev_end(); if (trace) fprintf(stderr, "[cnv] no jump table: scanning on the host\n"); }
         }
         if (!have_land || !device_hop) {
@@ -2571,7 +2698,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 const long n = (long)buf.size();
                 if (n > 0) {
                     tmp.resize(n);
-                    lowword_msort(buf.data(), n, tmp.data());
+                    lowword_msort_par(buf.data(), n, tmp.data(), n >= 65536 ? 3 : (n >= 16384 ? 2 : 0));
                     const long a = (long)(0.1 * n), b = n - a;
                     double tot = 0;
                     for (long j = a; j < b; j++) tot += buf[j];

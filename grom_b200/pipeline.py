@@ -67,14 +67,17 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
     prm = params if params is not None else Params.default()
     fasta = {k.lower(): v for k, v in read_fasta(fasta_path).items()}
     with hostlib.Bam(bam_path) as bam:
-        batches = [bam.read_target(t) for t in range(len(bam.names))]
-        st = hostlib.library_stats(batches, prm.min_mapq)
+        # library statistics first (find_insert_mean, src/GROM.c:1205-1318): the contigs stream through one at a time until the sample is full
+        st = hostlib.library_stats((bam.read_target(t) for t in range(len(bam.names))), prm.min_mapq)
         prm.insert_mean = max(st["insert_mean"], st["lseq"])            # src/GROM.c:22260
         prm.insert_min, prm.insert_max, prm.lseq = st["insert_min"], st["insert_max"], st["lseq"]
         prm.rd_min_mapq = prm.min_mapq                                    # src/GROM.c:22102
         hez, mq = hostlib.tables(table_dir, prm.min_mapq)
         gpu.init(device, hez, mq, prm)
         todo = [t for t, n in enumerate(bam.names) if n.lower() in fasta and not skip_contig(n, prm.gender)]
+        for t in todo:
+            if len(fasta[bam.names[t].lower()]) != bam.lens[t]:
+                raise ValueError(f"{bam.names[t]}: {len(fasta[bam.names[t].lower()])} bases in the FASTA, {bam.lens[t]} in the BAM header")
         mine = set(todo[i] for i in assign_contigs([bam.lens[t] for t in todo], ranks)[rank])
         text: Dict[int, str] = {}
         work = [t for t in todo if t in mine]
@@ -82,16 +85,19 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
         n_lanes = max(1, min(lanes, len(work)))
         inflight = _InFlight(int(0.9 * gpu.device_free_bytes()))
         bus, pick, errors = threading.Lock(), threading.Lock(), []
+        names, lens = list(bam.names), list(bam.lens)
 
-        def one_contig(t: int, stream: Optional[int]):
-            name = bam.names[t].lower()
+        def one_contig(lane_bam, t: int, stream: Optional[int]):
+            name = names[t].lower()
             chars = fasta[name]
-            need = gpu.chr_bytes_estimate(len(chars), batches[t].n_reads, batches[t].n_base_slots)
+            batch = lane_bam.read_target(t)                                 # decoded just before it is pushed, dropped right after
+            need = gpu.chr_bytes_estimate(len(chars), batch.n_reads, batch.n_base_slots)
             inflight.acquire(need)
             try:
                 with gpu.Chromosome(t, chars, stream=stream) as ch:
                     with bus:
-                        ch.push_reads(batches[t]); ch.sync()
+                        ch.push_reads(batch); ch.sync()
+                    del batch
                     res = ch.finish()
                     cnv = ch.cnv(params=prm)
             finally:
@@ -103,12 +109,13 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
         def lane():
             stream = gpu.stream_create() if n_lanes > 1 else None
             try:
-                while not errors:
-                    with pick:
-                        if not work:
-                            return
-                        t = work.pop(0)
-                    one_contig(t, stream)
+                with hostlib.Bam(bam_path) as lane_bam:                    # one reader per lane (the batcher seeks in its file)
+                    while not errors:
+                        with pick:
+                            if not work:
+                                return
+                            t = work.pop(0)
+                        one_contig(lane_bam, t, stream)
             except BaseException as e:                                      # surfaced by the caller's thread below
                 errors.append(e)
             finally:
