@@ -600,12 +600,32 @@ struct SegCtx {
         return *score >= 3;
     }
 };
+// z of the deletion scan per position, unpacked once from the packed records (same two factors, same __dmul_rn as z_del_of): the seed
+// evaluations then read 8 coalesced bytes per position instead of gathering from the p-value and MAPQ-weight tables lane by lane
+__global__ void __launch_bounds__(256) k_zfill(const uint32_t *__restrict__ rec, int64_t P, const double *__restrict__ sd, const double *__restrict__ wtab, double *__restrict__ z)
+{
+    __shared__ double s_sd[1024], s_w[256];
+    for (int i = threadIdx.x; i < 1024; i += 256) s_sd[i] = i < P2S ? sd[i] : 0.0;
+    s_w[threadIdx.x] = wtab[threadIdx.x];
+    __syncthreads();
+    for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < P; p += (int64_t)gridDim.x * 256) {
+        const uint32_t r = rec[p];
+        double v = 0.0;
+        if (r & R_NZ) {
+            const double w = (r & R_OVR) ? 1.0 : (((r >> R_CLASS) & 3) == 0 ? s_w[(r >> R_MQ) & 255] : 0.5);
+            v = __dmul_rn(w, s_sd[(r >> R_K) & 1023]);
+            if (r & R_NEG) v = -v;
+        }
+        z[p] = v;
+    }
+}
 enum { SEG_RESUME = 0, SEG_CALL = 1, SEG_UNRESOLVED = 2 };
 struct Outcome { int kind; int64_t next, c_end; double c_z; int64_t far; };   // far: one past the last position the sliding phase looked at
 constexpr int SEED_BOUND0 = 128;       // first round, pass one (every seed)
+constexpr bool MID_EVAL = true;      // evaluate the seeds that ran past the first bound once more at SEED_BOUND before calling them open (off: straight to the run heads + second round)
 constexpr int SEED_BOUND = 1024;       // first round, every seed: closes everything but genuine events and long uncovered stretches (chance dips of the coverage end within a few hundred positions); what runs past it is "open"
 
-template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCtx &C, const int64_t pos, int mi)
+template <bool BOUNDED, bool DUP> __host__ __device__ inline Outcome eval_seed_k(const SegCtx &C, const int64_t pos, int mi)
 {
 #define CNV_STEP(var, p) do { const int c_ = C.cls(p); if (c_ != 2) var = c_; } while (0)
     const int64_t Lmin = C.Lmin, Lmax = C.Lmax, end = C.end, max_gap = Lmax + 500;
@@ -616,13 +636,15 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
     double tot = 0, c_z = 0, tz;
     const uint32_t *rp = C.rec + pos;                        // the first two phases index relative to the seed (32-bit offsets)
     const double *zp = C.zarr ? C.zarr + pos : nullptr;
-    auto zrel = [&](int i, uint32_t r) { const double v = zp ? zp[i] : C.z_del_of(r); return C.dup ? 0.0 - v : v; };
+    const uint32_t m0 = DUP ? R_DUP0 : R_DEL0, m1 = DUP ? R_DUP1 : R_DEL1;
+    // z as the scan sees it: 0.0 - v for duplications (exact, and keeps a zero positive like the reference's literal 0.0)
+    auto zrel = [&](int i, uint32_t r) { const double v = zp ? zp[i] : C.z_del_of(r); return DUP ? 0.0 - v : v; };
     const int iLmin = (int)Lmin, iLmax = (int)Lmax;
     for (int i = 0; i < iLmin; i++) {
         wlen++;
         bool ok = false;
         const uint32_t r = rp[i];
-        if (!(r & R_MASK)) { const int c_ = (r >> R_CLASS) & 3; if (c_ != 2) mi = c_; ok = (r & C.beyond_bit(mi)) != 0; }
+        if (!(r & R_MASK)) { const int c_ = (r >> R_CLASS) & 3; if (c_ != 2) mi = c_; ok = (r & (mi ? m1 : m0)) != 0; }
         if (ok) cnt2++;
         else if (2 * cnt2 < wlen) { o.next = pos + i + 1; return o; }       // give up inside the first window: resume after the offender
     }
@@ -634,27 +656,35 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
     {
         const int i_end = end - pos < (int64_t)iLmax ? (int)(end - pos) : iLmax;      // first offset at or past `end` (>= Lmin is not guaranteed)
         int good = -1;                                                               // last scoring offset of this phase
-        const uint32_t m0 = C.beyond_bit(0), m1 = C.beyond_bit(1);
-        for (int i = iLmin; i < iLmax; i++) {
-            wlen++;
-            if (BOUNDED && wlen > C.bound) { o.kind = SEG_UNRESOLVED; return o; }
-            if (i >= i_end) { stop = true; break; }
-            bool ok = false;
+        // the loop runs up to the first of: the largest window, the bound of a bounded evaluation, the end of the analysed block
+        int i_lim = i_end < iLmax ? i_end : iLmax;
+        if (BOUNDED && C.bound < i_lim) i_lim = C.bound;
+        const double *thr = C.win_thr;
+        double dcnt = (double)cnt;                                                   // cnt as a double, kept in step (exact: small integers)
+        int i = iLmin;
+        for (; i < i_lim; i++) {
             const uint32_t r = rp[i];
+            bool ok = false;
             if (!(r & R_MASK)) {
                 const int c_ = (r >> R_CLASS) & 3; if (c_ != 2) mi = c_;
-                tot += zrel(i, r); cnt++;
+                tot += zrel(i, r); cnt++; dcnt += 1.0;
                 ok = (r & (mi ? m1 : m0)) != 0;
                 if (ok) {
                     cnt2++;
-                    if (C.scores(tot, cnt, wlen, &tz)) {
-                        good = i;
-                        if (tz > c_z) c_z = tz;                                      // c_z starts at 0 and every scoring tz is >= 3
+                    if (tot >= dcnt * thr[i + 1]) {                                  // SegCtx::scores, its cheap side inline
+                        tz = tot / (dcnt * C.win_sd[i + 1]);
+                        if (tz >= 3) { good = i; if (tz > c_z) c_z = tz; }           // c_z starts at 0 and every scoring tz is >= 3
                     }
                 }
             }
-            if (!ok && 2 * cnt2 < wlen) { stop = true; break; }
+            if (!ok && 2 * cnt2 < i + 1) { stop = true; break; }
         }
+        if (!stop && i < iLmax) {
+            // left the loop early: the bound is tested before the block's end, like the per-step order of the tests it replaces
+            if (BOUNDED && i >= C.bound) { o.kind = SEG_UNRESOLVED; return o; }
+            stop = true;
+        }
+        wlen = i + 1;
         if (good >= 0) {
             last_good = pos + good;
             if (!begun) { begun = true; c_start = pos; }
@@ -708,6 +738,10 @@ template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCt
     o.kind = SEG_CALL; o.c_end = c_end; o.c_z = c_z; o.next = c_end + 2;
     return o;
 #undef CNV_STEP
+}
+template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCtx &C, const int64_t pos, int mi)
+{
+    return C.dup ? eval_seed_k<BOUNDED, true>(C, pos, mi) : eval_seed_k<BOUNDED, false>(C, pos, mi);
 }
 
 // land[2*rank + class] (uint32): 0xFFFFFFFF not a seed under that class; top bits SEG_*; RESUME: low bits = distance to the next
@@ -881,6 +915,84 @@ __device__ __forceinline__ uint32_t nz_rank(const uint32_t *__restrict__ nz, con
     return nzwp[w] + __popc(nz[w] & ((1u << (x & 31)) - 1u));
 }
 
+// ---- tails of stretches without z values.  A seed s inside such a stretch that ends at b (the first position with a z value) sees a
+// running sum of exactly 0 up to b and the sums T_b(x) = z(b) + .. + z(x) behind it, whatever s is; only its counters differ.  Having
+// passed the first window it resumes at s + 1 unless some window scores, and a score at x needs T_b(x) >= cnt * win_thr[wlen] with
+// wlen = (x - b + 1) + (b - s) and cnt >= wlen - (masked positions in reach).  k_tail_check tests that necessary condition once per
+// stretch end, for every x and the most favourable window length (suffix minimum `gm` of L * win_thr[L]), on an approximate T with a
+// margin far above any rounding difference to the reference's sum; where it can never hold, every seed at least TAIL_KMIN positions
+// before b is closed in O(1) (the reference walks up to 2 * (b - s) positions from each of them: src/GROM.c:19402-19470).
+constexpr int TAIL_KMIN = 64;
+__global__ void __launch_bounds__(256) k_tail_ends(const uint32_t *__restrict__ nz, int64_t words, int32_t *__restrict__ ends, uint32_t cap, unsigned int *__restrict__ n_ends)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < 2 || w >= words) return;
+    const uint32_t m = nz[w];
+    if (!m || nz[w - 1] || nz[w - 2]) return;                 // the lowest z position of the word, behind at least 64 positions without one
+    const unsigned int k = atomicAdd(n_ends, 1u);
+    if (k < cap) ends[k] = (int32_t)((w << 5) + __ffs(m) - 1);
+}
+__global__ void __launch_bounds__(128) k_tail_check(const uint32_t *__restrict__ rec, const double *__restrict__ z, int64_t P, const int32_t *__restrict__ ends,
+                                                    const unsigned int *__restrict__ n_ends_p, uint32_t cap, int Lmax, const double *__restrict__ gm,
+                                                    uint32_t *__restrict__ safe, int64_t words)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_ends = min(*n_ends_p, cap);
+    for (uint32_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n_ends; e += (gridDim.x * blockDim.x) >> 5) {     // one warp per stretch end
+    const int64_t b = ends[e];
+    int Ms = 0;                                               // masked positions a seed of this tail can have before b
+    for (int64_t p = max((int64_t)0, b - Lmax) + lane; p < b; p += 32) Ms += (int)(rec[p] & R_MASK);
+    for (int o = 16; o; o >>= 1) Ms += __shfl_xor_sync(0xffffffffu, Ms, o);
+    double T = 0, A = 0;
+    int Mb = 0;
+    bool bad0 = false, bad1 = false;
+    const int64_t limit = min(P, b + Lmax - TAIL_KMIN);
+    for (int64_t x0 = b; x0 < limit; x0 += 32) {
+        const int64_t x = x0 + lane;
+        const bool valid = x < limit;
+        const uint32_t r = valid ? rec[x] : 0u;
+        int sm = (int)(r & R_MASK);
+        double sv = (valid && !sm) ? z[x] : 0.0, sa = fabs(sv);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double yv = __shfl_up_sync(0xffffffffu, sv, o), ya = __shfl_up_sync(0xffffffffu, sa, o);
+            const int ym = __shfl_up_sync(0xffffffffu, sm, o);
+            if (lane >= o) { sv += yv; sa += ya; sm += ym; }
+        }
+        if (valid) {
+            const double Tx = T + sv, margin = 1e-10 * (A + sa) + 1e-300;
+            const int Mx = Ms + Mb + sm, L = (int)(x - b) + 1 + TAIL_KMIN;
+            if (2 * Mx >= L) bad0 = bad1 = true;
+            else {
+                const double bound = gm[L] * (1.0 - (double)Mx / (double)L);
+                if (Tx + margin >= bound) bad0 = true;
+                if (margin - Tx >= bound) bad1 = true;
+            }
+        }
+        T += __shfl_sync(0xffffffffu, sv, 31); A += __shfl_sync(0xffffffffu, sa, 31); Mb += __shfl_sync(0xffffffffu, sm, 31);
+        if (__any_sync(0xffffffffu, bad0) && __any_sync(0xffffffffu, bad1)) break;
+    }
+    bad0 = __any_sync(0xffffffffu, bad0); bad1 = __any_sync(0xffffffffu, bad1);
+    if (lane == 0) {
+        if (!bad0) atomicOr(safe + (b >> 5), 1u << (b & 31));
+        if (!bad1) atomicOr(safe + words + (b >> 5), 1u << (b & 31));
+    }
+    }
+}
+// first position with a z value at or after p, looking no further than word wmax; -1 if there is none
+__device__ __forceinline__ int64_t nz_next(const uint32_t *__restrict__ nz, const uint32_t *__restrict__ nzwp, int64_t words, int64_t p, int64_t wmax)
+{
+    const int64_t w = p >> 5;
+    if (w >= words) return -1;
+    const uint32_t r = nzwp[w] + __popc(nz[w] & ((1u << (p & 31)) - 1u));
+    int64_t lo = w, hi = min(words - 1, wmax);
+    if (nzwp[hi] + __popc(nz[hi]) <= r) return -1;
+    while (lo < hi) { const int64_t m = (lo + hi) >> 1; if (nzwp[m] + __popc(nz[m]) > r) hi = m; else lo = m + 1; }
+    uint32_t bits = nz[lo];
+    if (lo == w) bits &= ~((1u << (p & 31)) - 1u);
+    return (lo << 5) + __ffs(bits) - 1;
+}
+
 // Seed evaluation, first round, in two passes.  Pass one, every seed, bounded to SEED_BOUND0 positions (the first window and a little
 // more: almost every seed gives up after a handful of positions): a CTA owns 256 words of the seed bitmap of one kind (blockIdx.y =
 // deletions / duplications), the set bits are compacted into shared memory, so consecutive threads take consecutive seeds and a seed's
@@ -910,7 +1022,7 @@ __device__ __forceinline__ uint32_t seed_outcome(const SegCtx &C, int64_t p, int
 constexpr int SEED_CTA_WORDS = 256;
 __global__ void __launch_bounds__(256) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                   unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ mid, uint32_t mid_cap, uint32_t *__restrict__ jump0)
+                                                   unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ mid, uint32_t mid_cap, uint32_t *__restrict__ jump0, uint32_t *__restrict__ u1)
 {
     __shared__ uint16_t lst[SEED_CTA_WORDS * 32];
     __shared__ uint32_t s_warp[8];
@@ -936,27 +1048,41 @@ __global__ void __launch_bounds__(256) k_seed_eval(SegCtx Cdel, SegCtx Cdup, con
     if (!total) return;
     const uint32_t rank0 = wpk[w0], n_seeds = kind ? n_dup : n_del, jbase = kind ? 2 * n_del + 1 : 0;
     const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
-    for (uint32_t idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const uint32_t rank = rank0 + idx;
-        if (rank >= cap) break;
-        const uint32_t loc = lst[idx];
-        const int64_t p = ((w0 + (loc >> 5)) << 5) + (loc & 31);
+    for (uint32_t idx0 = 0; idx0 < total; idx0 += blockDim.x) {               // uniform trip count: the appends below are warp-wide
+        const uint32_t idx = idx0 + threadIdx.x, rank = rank0 + idx;
+        const bool valid = idx < total && rank < cap;
         uint32_t res[2] = {LAND_NOT, LAND_NOT};
         int c0 = 0;
-        if (p < C.end) {
-            c0 = C.cls(p);
-            for (int v = 0; v < 2; v++) {
-                if (c0 != 2 && v == 1) { res[1] = res[0]; break; }
-                const int mi = c0 == 2 ? v : c0;
-                if (!C.beyond(p, mi)) continue;
-                res[v] = seed_outcome(C, p, mi, calls, call_cap, n_calls);
-                if (res[v] == unres) {
-                    // past the short bound of this pass: queued for the evenly spread pass over such seeds (k_seed_eval_mid)
-                    const unsigned int k = atomicAdd(n_calls + 8, 1u);
-                    if (k < mid_cap) { SeedTodo t; t.rank = rank; t.kind = (uint8_t)kind; t.variant = (uint8_t)v; t.pad = 0; t.pos = (int32_t)p; mid[k] = t; }
+        int64_t p = 0;
+        if (valid) {
+            const uint32_t loc = lst[idx];
+            p = ((w0 + (loc >> 5)) << 5) + (loc & 31);
+            if (p < C.end) {
+                c0 = C.cls(p);
+                for (int v = 0; v < 2; v++) {
+                    if (c0 != 2 && v == 1) { res[1] = res[0]; break; }
+                    const int mi = c0 == 2 ? v : c0;
+                    if (!C.beyond(p, mi)) continue;
+                    res[v] = seed_outcome(C, p, mi, calls, call_cap, n_calls);
                 }
             }
         }
+        // past the short bound of this pass: queued for the pass over such seeds (k_seed_eval_mid); a warp appends its seeds in
+        // lane order -- consecutive seeds -- so that pass finds neighbouring seeds in neighbouring lanes
+        for (int v = 0; v < 2; v++) {
+            const bool q = valid && res[v] == unres && (v == 0 || c0 == 2);
+            const unsigned m = __ballot_sync(0xffffffffu, q);
+            if (!m) continue;
+            unsigned int k0 = 0;
+            if (lane == __ffs(m) - 1) k0 = atomicAdd(n_calls + 8, (unsigned int)__popc(m));
+            k0 = __shfl_sync(0xffffffffu, k0, __ffs(m) - 1);
+            if (q) {
+                const unsigned int k = k0 + __popc(m & ((1u << lane) - 1u));
+                if (k < mid_cap) { SeedTodo t; t.rank = rank; t.kind = (uint8_t)kind; t.variant = (uint8_t)v; t.pad = 0; t.pos = (int32_t)p; mid[k] = t; }
+                atomicOr(u1 + (int64_t)kind * words + (p >> 5), 1u << (p & 31));
+            }
+        }
+        if (!valid) continue;
         land[((int64_t)kind * cap + rank) * 2] = res[0]; land[((int64_t)kind * cap + rank) * 2 + 1] = res[1];
         if (jump0) {
             // successors; node ids are local to the kind, the table stores them behind the kind's base offset (2 * n_del + 1 for duplications)
@@ -967,10 +1093,24 @@ __global__ void __launch_bounds__(256) k_seed_eval(SegCtx Cdel, SegCtx Cdup, con
     if (jump0 && blockIdx.x == 0 && threadIdx.x == 0) jump0[jbase + 2 * n_seeds] = jbase + 2 * n_seeds;      // END loops on itself
 }
 
+// Pass two over the seeds that ran past the first bound, in two launches (PHASE 0, then PHASE 1):
+//  * closed in O(1) where nothing can score: no z value within reach, or the tail of a stretch without z values whose end k_tail_check
+//    found safe;
+//  * a seed whose right-hand neighbour is also on the list is deferred to phase 1: consecutive seeds give up in order of position (the
+//    give-up rule compares the count of positions beyond the threshold with the window length, and a seed further left has at least
+//    the lead of the one to its right), so if the last seed of such a run stays open the others are left open without a walk -- which
+//    is always safe, an open seed is evaluated exactly if the path reaches it -- and only runs whose last seed closed are walked in full.
+//    Inside an event that is the walk of one seed per gap instead of every position;
+//  * everything else is walked to SEED_BOUND.
+// One thread per seed, each thread on its own grid-stride loop and no warp-wide step inside it: the seeds of a warp stop after very
+// different numbers of positions (the give-up rule is a first-passage time), and a lane that is done moves on to its next seed while
+// its neighbours still walk -- lanes that meet again in the walk's loop are issued together.
+template <int PHASE>
 __global__ void __launch_bounds__(128) k_seed_eval_mid(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                        uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                       unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ mid, uint32_t mid_cap, SeedTodo *__restrict__ todo, uint32_t todo_cap,
-                                                       uint32_t *__restrict__ jump0, uint32_t *__restrict__ open_bits, const uint32_t *__restrict__ nz, const uint32_t *__restrict__ nzwp)
+                                                       unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ mid, uint32_t mid_cap, SeedTodo *__restrict__ todo, uint32_t todo_cap,
+                                                       uint32_t *__restrict__ jump0, uint32_t *__restrict__ open_bits, const uint32_t *__restrict__ nz, const uint32_t *__restrict__ nzwp,
+                                                       const uint32_t *__restrict__ u1, const uint32_t *__restrict__ safe, uint32_t *__restrict__ run_open)
 {
     const uint32_t n_mid = min(n_calls[8], mid_cap);
     const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
@@ -979,17 +1119,45 @@ __global__ void __launch_bounds__(128) k_seed_eval_mid(SegCtx Cdel, SegCtx Cdup,
         const SegCtx &C = t.kind ? Cdup : Cdel;
         const int64_t p = t.pos;
         const int c0 = C.cls(p);
-        uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
-        if (e == unres) {
+        uint32_t e = unres;
+        bool walk = true;
+        if (PHASE == 0) {
             // It passed the first window.  If no position of everything the growth phase can reach carries a z value (an uncovered
             // stretch: full-copy loss, the start of the contig), the running sum stays exactly 0, no window length can score and
-            // the reference resumes at the next position after walking all of it (src/GROM.c:19402-19470): O(1) here.
+            // the reference resumes at the next position after walking all of it (src/GROM.c:19402-19470): O(1) here, before any walk.
             const int64_t reach = min(C.len, p + max((int64_t)C.Lmin, min((int64_t)C.Lmax, C.end - p)));
             if (nz_rank(nz, nzwp, words, reach) == nz_rank(nz, nzwp, words, p)) { e = 1u; atomicAdd(n_calls + 7, 1u); }
+            else {
+                const int64_t w = p >> 5;
+                if (!(nz[w] >> (p & 31)) && (w + 1 >= words || !nz[w + 1])) {                 // nothing within the next 32 positions: look for the end of the stretch
+                    const int64_t f = nz_next(nz, nzwp, words, p, (p + C.Lmax) >> 5);
+                    if (f >= 0 && f - p >= TAIL_KMIN && ((safe[(int64_t)t.kind * words + (f >> 5)] >> (f & 31)) & 1u)) { e = 1u; atomicAdd(n_calls + 10, 1u); }
+                }
+            }
+            if (e == unres && ((u1[(int64_t)t.kind * words + ((p + 1) >> 5)] >> ((p + 1) & 31)) & 1u)) { mid[i].pad = 1; continue; }      // deferred
+        } else {
+            if (!t.pad) continue;                                                              // dealt with in phase 0
+            // the last seed of the run of listed seeds this one sits in stayed open in phase 0: open as well, no walk
+            if ((run_open[((int64_t)(t.kind * 2 + t.variant)) * words + (p >> 5)] >> (p & 31)) & 1u) { walk = false; atomicAdd(n_calls + 11, 1u); }
+        }
+        if (e == unres && walk && MID_EVAL) e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
+        if (PHASE == 0 && e == unres) {
+            // a run end that stays open: flag the whole run of listed seeds to its left (phase 1 leaves them open without a walk)
+            const uint32_t *ub = u1 + (int64_t)t.kind * words;
+            uint32_t *ro0 = run_open + ((int64_t)(t.kind * 2 + t.variant)) * words, *ro1 = c0 != 2 ? run_open + ((int64_t)(t.kind * 2 + 1)) * words : nullptr;
+            int64_t w = p >> 5;
+            uint32_t m = 0xffffffffu >> (31 - (p & 31));                                       // bits at or below p
+            for (;;) {
+                const uint32_t inv = ~ub[w] & m;
+                if (inv) m &= ~((2u << (31 - __clz(inv))) - 1u);                               // keep the ones above the highest gap
+                if (m) { atomicOr(ro0 + w, m); if (ro1) atomicOr(ro1 + w, m); }
+                if (inv || w == 0) break;
+                w--; m = 0xffffffffu;
+            }
         }
         if (e == unres) {
             const unsigned int k = atomicAdd(n_calls + 1, 1u);
-            if (k < todo_cap) todo[k] = t;
+            if (k < todo_cap) { SeedTodo o = t; o.pad = 0; todo[k] = o; }
             atomicOr(open_bits + ((int64_t)(t.kind * 2 + t.variant)) * words + (p >> 5), 1u << (p & 31));
             if (c0 != 2) atomicOr(open_bits + ((int64_t)(t.kind * 2 + 1)) * words + (p >> 5), 1u << (p & 31));
             continue;
@@ -1086,20 +1254,44 @@ __global__ void __launch_bounds__(128) k_apply_heads(SegCtx Cdel, SegCtx Cdup, c
 // Second round: the open seeds that are neither run heads nor under a call made at a head (the path jumps over those) get the full
 // growth phase, one thread each.  What enters the sliding phase stays open (a call longer than the largest window) and is evaluated by
 // the host if the path ever reaches it.
-__global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
-                                                   uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
-                                                   unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t todo_cap, uint32_t n_del, uint32_t n_dup,
-                                                   uint32_t *__restrict__ jump0, const uint32_t *__restrict__ cover)
+// pass one: the open seeds that are still unresolved (not a head the host closed) and not under a call made at a head, compacted in
+// list order (neighbouring seeds stay in neighbouring lanes); pass two: one thread per compacted seed
+__global__ void __launch_bounds__(256) k_seed_filter2(const uint32_t *__restrict__ land, uint32_t cap, unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo,
+                                                      uint32_t todo_cap, const uint32_t *__restrict__ cover, int64_t words, SeedTodo *__restrict__ out)
 {
     const uint32_t n_todo = min(n_calls[1], todo_cap);
+    const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    bool keep = false, covered = false;
+    SeedTodo t; t.rank = 0; t.kind = 0; t.variant = 0; t.pad = 0; t.pos = 0;
+    if (i < n_todo) {
+        t = todo[i];
+        if (land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] == unres) {
+            covered = (cover[(int64_t)t.kind * words + (t.pos >> 5)] >> (t.pos & 31)) & 1u;
+            keep = !covered;
+        }
+    }
+    const unsigned mc = __ballot_sync(0xffffffffu, covered), m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0 && mc) atomicAdd(n_calls + 5, (unsigned int)__popc(mc));                       // under a call made at a head
+    if (!m) return;
+    unsigned int k0 = 0;
+    if (lane == __ffs(m) - 1) k0 = atomicAdd(n_calls + 9, (unsigned int)__popc(m));
+    k0 = __shfl_sync(0xffffffffu, k0, __ffs(m) - 1);
+    if (keep) out[k0 + __popc(m & ((1u << lane) - 1u))] = t;
+}
+__global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+                                                   uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
+                                                   unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t n_del, uint32_t n_dup,
+                                                   uint32_t *__restrict__ jump0)
+{
+    const uint32_t n_todo = n_calls[9];
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_todo) return;
     const SeedTodo t = todo[i];
     const SegCtx &C = t.kind ? Cdup : Cdel;
     const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
-    if (land[((int64_t)t.kind * cap + t.rank) * 2 + t.variant] != unres) return;                 // a head, already closed
     const int64_t p = t.pos;
-    if ((cover[(int64_t)t.kind * words + (p >> 5)] >> (p & 31)) & 1u) { atomicAdd(n_calls + 5, 1u); return; }      // under a call made at a head
     const int c0 = C.cls(p);
     const uint32_t e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
     if (e == unres) return;

@@ -22,6 +22,7 @@
 #include <atomic>
 #include <limits>
 #include <vector>
+#include <string>
 #include <chrono>
 #include <thread>
 #include "gromgpu.h"
@@ -1896,13 +1897,15 @@ extern "C" int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0
 // ================================================================================================ read-depth CNV path (cnv.cuh)
 struct CnvState {
     int32_t *d_depth = nullptr; uint8_t *d_mq8 = nullptr; uint32_t *d_rec = nullptr, *d_seed = nullptr;   // d_seed: [2][words]
+    double *d_z = nullptr;                                             // z of the deletion scan per position (k_zfill)
     cnv::PreOut *d_pre = nullptr; unsigned long long *d_hist = nullptr;
     cnv::RepRec *d_rep = nullptr; unsigned int *d_nrep = nullptr; unsigned int rep_cap = 0;
     uint8_t *d_tile = nullptr;                                         // [4][n_tiles]: last/in of the mask stage, last/in of the z stage
     uint32_t *h_rec = nullptr, *h_seed = nullptr, *h_wp = nullptr, *h_land = nullptr; cnv::SeedCall *h_spec = nullptr;   // pinned
     uint32_t *d_blk = nullptr, *d_wp = nullptr, *d_land = nullptr; uint32_t land_cap = 0, spec_cap = 0; int nb = 0;
     cnv::SeedCall *d_spec = nullptr; unsigned int *d_nspec = nullptr; double *d_winsd = nullptr;
-    std::vector<grom_cnv_call> calls;
+    uint32_t *d_u1 = nullptr; int32_t *d_ends = nullptr; static constexpr uint32_t ENDS_CAP = 1u << 20;
+    std::vector<grom_cnv_call> calls; std::vector<double> tail_gm;
     std::vector<double> win_sd, win_thr, bin_d; std::vector<int64_t> win_cnt, bin_n;
     int64_t P = 0, words = 0;
     int q = 0;
@@ -1918,7 +1921,7 @@ static void cnv_state_free(CnvState *c)
 {
     if (!c) return;
     if (c->h_gather) cudaFreeHost(c->h_gather);
-    cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
+    cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_z); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
     for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->heads, &c->head_out, &c->mid}) if (g->p) cudaFree(g->p);
@@ -1936,7 +1939,7 @@ static void cnv_state_free(CnvState *c)
     if (c->h_wp) cudaFreeHost(c->h_wp);
     if (c->h_land) cudaFreeHost(c->h_land);
     if (c->h_spec) cudaFreeHost(c->h_spec);
-    cudaFree(c->d_blk); cudaFree(c->d_wp); cudaFree(c->d_land); cudaFree(c->d_spec); cudaFree(c->d_nspec); cudaFree(c->d_winsd);
+    cudaFree(c->d_blk); cudaFree(c->d_wp); cudaFree(c->d_land); cudaFree(c->d_spec); cudaFree(c->d_nspec); cudaFree(c->d_winsd); cudaFree(c->d_u1); cudaFree(c->d_ends);
     delete c;
 }
 
@@ -2008,7 +2011,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     const int64_t n_blk = (P + BLK_UNIT - 1) / BLK_UNIT, n_tiles = (P + CTILE - 1) / CTILE, words = (P + 31) / 32;
     c.words = words;
     if (!c.d_depth) {
-        CK(cudaMalloc(&c.d_depth, sizeof(int32_t) * P)); CK(cudaMalloc(&c.d_mq8, P)); CK(cudaMalloc(&c.d_rec, sizeof(uint32_t) * P));
+        CK(cudaMalloc(&c.d_depth, sizeof(int32_t) * P)); CK(cudaMalloc(&c.d_mq8, P)); CK(cudaMalloc(&c.d_rec, sizeof(uint32_t) * P)); CK(cudaMalloc(&c.d_z, sizeof(double) * P));
         CK(cudaMalloc(&c.d_seed, sizeof(uint32_t) * 3 * words));      // deletion seeds, duplication seeds, positions with a z value
         CK(cudaMalloc(&c.d_pre, sizeof(PreOut) * n_blk));
         CK(cudaMalloc(&c.d_open, sizeof(uint32_t) * 6 * words));       // [2][2][words] open seeds + [2][words] positions under calls made at run heads
@@ -2025,7 +2028,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * words)); CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
         c.spec_cap = (uint32_t)std::min<int64_t>(P / 8 + 1024, (int64_t)1 << 28);
         CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
-        CK(cudaMalloc(&c.d_nspec, 16 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * 2 * (Lmax + 1)));      // win_sd, then win_thr
+        CK(cudaMalloc(&c.d_nspec, 16 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (3 * (Lmax + 1) + 1)));      // win_sd, win_thr, then the tail bound gm [Lmax + 2]
+        CK(cudaMalloc(&c.d_u1, sizeof(uint32_t) * 8 * words)); CK(cudaMalloc(&c.d_ends, sizeof(int32_t) * CnvState::ENDS_CAP));      // d_u1: [2][words] listed seeds, [2][words] safe stretch ends, [4][words] runs whose last seed stayed open
     }
 
     // ---- stage 1: pre-statistics + repeat runs
@@ -2402,7 +2406,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     int64_t seed_tot_all = 0, n_spec_all = 0;
     {
         SegCtx ctx[2];
-        for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].win_thr = c.d_winsd + (Lmax + 1); ctx[k].zarr = nullptr; ctx[k].dup = k == 1; ctx[k].wtab = T.p2s_sd + P2S; }
+        for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].win_thr = c.d_winsd + (Lmax + 1); ctx[k].zarr = c.d_z; ctx[k].dup = k == 1; ctx[k].wtab = T.p2s_sd + P2S; }
         // every seed evaluated on the device (bounded); a seed list that outgrew its buffer, or the biased-repeat override (it rewrites
         // z on the host copy after the sweep), leaves the evaluation to the host
         unsigned int n_spec = 0;
@@ -2412,7 +2416,15 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             dev_begin();
             CK(cudaMemcpyAsync(c.d_winsd, c.win_sd.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
             CK(cudaMemcpyAsync(c.d_winsd + (Lmax + 1), c.win_thr.data(), sizeof(double) * (Lmax + 1), cudaMemcpyHostToDevice, s));
+            {
+                // suffix minimum of L * win_thr[L]: the smallest total a window of at least L positions needs to score (k_tail_check)
+                c.tail_gm.assign(Lmax + 2, std::numeric_limits<double>::infinity());
+                for (int L = Lmax; L >= 0; L--) c.tail_gm[L] = std::min(c.tail_gm[L + 1], L >= Lmin ? (double)L * c.win_thr[L] : std::numeric_limits<double>::infinity());
+                CK(cudaMemcpyAsync(c.d_winsd + 2 * (Lmax + 1), c.tail_gm.data(), sizeof(double) * (Lmax + 2), cudaMemcpyHostToDevice, s));
+                CK(cudaMemsetAsync(c.d_u1, 0, sizeof(uint32_t) * 8 * (size_t)words, s));
+            }
             CK(cudaMemsetAsync(c.d_nspec, 0, 16 * sizeof(unsigned int), s));
+            k_zfill<<<148 * 8, 256, 0, s>>>(c.d_rec, P, T.p2s_sd, T.p2s_sd + P2S, c.d_z); n_launch++;
             // every (seed, carried class) can stay open after the first round (a contig full of long events): room for all of them
             const uint32_t todo_cap = (uint32_t)std::min<uint64_t>(2ull * ((uint64_t)seed_tot[0] + seed_tot[1]) + 64, 1ull << 28);
             Grow &t_todo = c.tmp[15];
@@ -2435,15 +2447,19 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             k_seed_blocksum<<<dim3((unsigned)c.nb, 1), 256, 0, s>>>(d_nz, words, c.d_blk + 2 * c.nb, c.nb); n_launch++;
             k_seed_blockscan<<<1, 1024, 0, s>>>(c.d_blk + 2 * c.nb, c.nb, c.d_blk + 3 * c.nb + 2); n_launch++;
             k_seed_rank<<<dim3((unsigned)c.nb, 1), 256, 0, s>>>(d_nz, words, c.d_blk + 2 * c.nb, c.nb, d_nzwp); n_launch++;
+            k_tail_ends<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_nz, words, c.d_ends, CnvState::ENDS_CAP, c.d_nspec + 12); n_launch++;
+            k_tail_check<<<148 * 8, 128, 0, s>>>(c.d_rec, c.d_z, P, c.d_ends, c.d_nspec + 12, CnvState::ENDS_CAP, Lmax, c.d_winsd + 2 * (Lmax + 1), c.d_u1 + 2 * words, words); n_launch++;
             if (most) {
                 Grow &t_mid = c.mid;
                 if (!t_mid.ensure(sizeof(SeedTodo) * (size_t)todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
                 ctx[0].bound = ctx[1].bound = SEED_BOUND0;
                 k_seed_eval<<<dim3((unsigned)((words + SEED_CTA_WORDS - 1) / SEED_CTA_WORDS), 2), 256, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
-                                                                                                                   c.d_nspec, t_mid.as<SeedTodo>(), todo_cap, J); n_launch++;
+                                                                                                                   c.d_nspec, t_mid.as<SeedTodo>(), todo_cap, J, c.d_u1); n_launch++;
                 ctx[0].bound = ctx[1].bound = SEED_BOUND;
-                k_seed_eval_mid<<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
-                                                        t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp); n_launch++;
+                k_seed_eval_mid<0><<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
+                                                           t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words); n_launch++;
+                k_seed_eval_mid<1><<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
+                                                           t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words); n_launch++;
             }
             // Open seeds (ran past the first round's bound: genuine events and long stretches without coverage).  The heads of their runs are
             // evaluated exactly by the host, all in parallel, over windows of records fetched in one go (a long walk is a dependent chain:
@@ -2557,15 +2573,51 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             }
             if (n_open) {
                 const uint32_t n_todo = std::min(n_open, todo_cap);
-                k_seed_eval2<<<(n_todo + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, t_todo.as<SeedTodo>(), todo_cap,
-                                                               seed_tot[0], seed_tot[1], J, d_cover); n_launch++;
+                k_seed_filter2<<<(n_todo + 255) / 256, 256, 0, s>>>(c.d_land, c.land_cap, c.d_nspec, t_todo.as<SeedTodo>(), todo_cap, d_cover, words, c.mid.as<SeedTodo>()); n_launch++;
+                k_seed_eval2<<<(n_todo + 63) / 64, 64, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap, c.d_nspec, c.mid.as<SeedTodo>(),
+                                                               seed_tot[0], seed_tot[1], J); n_launch++;
                 if (trace) {
-                    unsigned int dbg[8];
+                    unsigned int dbg[16];
                     CK(cudaMemcpyAsync(dbg, c.d_nspec, sizeof(dbg), cudaMemcpyDeviceToHost, s));
                     CK(cudaStreamSynchronize(s));
                     mark("  seeds, second round");
                     fprintf(stderr, "[cnv]   %u open seeds after the first round (%u zero-stretch seeds closed in O(1) before that); %u run heads, %u left to the host; second round: %u closed, %u skipped under calls made at heads\n",
                             n_open, dbg[7], n_heads_all, n_heads, dbg[4], dbg[5]);
+                    fprintf(stderr, "[cnv]   %u seeds past the first bound; %u closed as tails of stretches without z (%u stretch ends); %u left open behind an open run end\n", dbg[8], dbg[10], dbg[12], dbg[11]);
+                    if (const char *dump = getenv("GROMGPU_CNV_DUMP")) {
+                        // development aid: the open-seed list with each seed's final table entry and cover bit
+                        std::vector<SeedTodo> td(n_todo); std::vector<uint32_t> ld(4 * (size_t)c.land_cap), cov(2 * (size_t)words);
+                        CK(cudaMemcpy(td.data(), t_todo.p, sizeof(SeedTodo) * n_todo, cudaMemcpyDeviceToHost));
+                        CK(cudaMemcpy(ld.data(), c.d_land, sizeof(uint32_t) * ld.size(), cudaMemcpyDeviceToHost));
+                        CK(cudaMemcpy(cov.data(), d_cover, sizeof(uint32_t) * cov.size(), cudaMemcpyDeviceToHost));
+                        std::vector<SeedCall> sc(std::min(dbg[0], c.spec_cap));
+                        if (!sc.empty()) CK(cudaMemcpy(sc.data(), c.d_spec, sizeof(SeedCall) * sc.size(), cudaMemcpyDeviceToHost));
+                        {
+                            // ... and every seed that ran past the first bound, with its final table entry
+                            const unsigned int n_mid = std::min(dbg[8], todo_cap);
+                            std::vector<SeedTodo> md(n_mid);
+                            if (n_mid) CK(cudaMemcpy(md.data(), c.mid.p, sizeof(SeedTodo) * n_mid, cudaMemcpyDeviceToHost));
+                            std::string name = std::string(dump) + ".mid";
+                            if (FILE *f = fopen(name.c_str(), "wb")) {
+                                for (size_t mi = 0; mi < md.size(); mi += 8) {                       // a sample: every 8th
+                                    const SeedTodo &t = md[mi];
+                                    const uint32_t e = ld[((size_t)t.kind * c.land_cap + t.rank) * 2 + t.variant];
+                                    const int32_t row[4] = {t.pos, t.kind * 2 + t.variant, (int32_t)e, t.pad};
+                                    fwrite(row, sizeof(row), 1, f);
+                                }
+                                fclose(f);
+                            }
+                        }
+                        if (FILE *f = fopen(dump, "wb")) {
+                            for (const SeedTodo &t : td) {
+                                const uint32_t e = ld[((size_t)t.kind * c.land_cap + t.rank) * 2 + t.variant];
+                                const int64_t cend = (e != LAND_NOT && (e >> LAND_SHIFT) == SEG_CALL) ? sc[e & ((1u << LAND_SHIFT) - 1u)].c_end : -1;
+                                const int32_t row[6] = {t.pos, t.kind, t.variant, (int32_t)e, (int32_t)((cov[(size_t)t.kind * words + (t.pos >> 5)] >> (t.pos & 31)) & 1u), (int32_t)cend};
+                                fwrite(row, sizeof(row), 1, f);
+                            }
+                            fclose(f);
+                        }
+                    }
                 }
             }
             if (device_hop) {
@@ -2605,7 +2657,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                         CK(cudaStreamSynchronize(s));
                         d2h += 4 * (w1 - pos);
                         SegCtx hc = ctx[k];
-                        hc.rec = window.data() - pos; hc.len = w1; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data(); hc.win_thr = c.win_thr.data(); hc.wtab = c.wtab.data();
+                        hc.rec = window.data() - pos; hc.len = w1; hc.zarr = nullptr; hc.sd = c.sd_tbl.data(); hc.win_sd = c.win_sd.data(); hc.win_thr = c.win_thr.data(); hc.wtab = c.wtab.data();
                         c0 = hc.cls(pos);
                         o = eval_seed<false>(hc, pos, c0 != 2 ? c0 : sink[k].variant);
                         if (w1 == P || o.far < w1) break;
@@ -2658,7 +2710,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             }
             Segmenter sg[2];
             for (int k = 0; k < 2; k++) {
-                sg[k].C = ctx[k]; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].C.win_thr = c.win_thr.data(); sg[k].C.wtab = c.wtab.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
+                sg[k].C = ctx[k]; sg[k].C.zarr = nullptr; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].C.win_thr = c.win_thr.data(); sg[k].C.wtab = c.wtab.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
                 if (have_land) { sg[k].wp = c.h_wp + k * words; sg[k].land = c.h_land + (size_t)k * 2 * c.land_cap; sg[k].spec = c.h_spec; }
             }
             const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));
