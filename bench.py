@@ -51,18 +51,39 @@ def parse():
     ap.add_argument("--parity-mb", type=float, default=4.0, help="length of the contig (same generator) checked against the oracle after the timed loops; 0 = skip")
     ap.add_argument("--simple", action="store_true", help="round-1 workload: single-M reads only (kernel best case; not config 3)")
     ap.add_argument("--cnv-per-mb", type=float, default=0.25)
-    return ap.parse_args()
+    ap.add_argument("--workload", default="chr20", choices=["chr20", "tetra", "wgs"],
+                    help="chr20 = config 3 (default, the metric's configuration); tetra = config 5 (100x, -p 4 -A 4, one 64 Mb contig per GPU); "
+                         "wgs = config 4 (24 contigs with GRCh38 length ratios, -g 1 -M, assigned largest-first to the GPUs: strong scaling)")
+    ap.add_argument("--ploidy", type=int, default=None, help="-p (default 2; 4 under --workload tetra)")
+    ap.add_argument("--A", type=int, default=None, help="-A windows sampling factor (default 2; 4 under --workload tetra)")
+    ap.add_argument("--wgs-scale", type=float, default=1.0 / 16, help="--workload wgs: contig lengths = GRCh38 primary lengths x this (1.0 = 3.09 Gb)")
+    a = ap.parse_args()
+    if a.workload == "tetra":
+        a.depth = 100.0 if a.depth == 30.0 else a.depth
+        a.ploidy = a.ploidy or 4
+        a.A = a.A or 4
+    a.ploidy = a.ploidy or 2
+    a.A = a.A or 2
+    return a
 
 
 def workload_name(a):
+    if a.workload == "tetra":
+        return (f"config 5: synthetic {a.depth:g}x paired-end 2x150 contig of {a.mb:g} Mb per GPU, -p {a.ploidy} -A {a.A} -M (read-depth window sweep at "
+                f"{a.A} offsets per 10 kb frame, tetraploid thresholds), same evidence classes as config 3")
     return (f"config 3: synthetic {a.depth:g}x paired-end 2x150 contig of {a.mb:g} Mb per GPU (chr20-sized) with every evidence class "
             f"(soft/hard clips, SA tags, small indels, discordant pairs of all orientations, planted DEL/DUP/INV/CTX/INS clusters, "
             f"copy-number segments, 3 % low MAPQ, 5 % PCR duplicates), -M, SNV/indel/SV gates + read-depth CNV")
 
 
-def params_for_bench():
+def params_for_bench(a=None):
     from grom_b200.params import Params
-    return Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=1)
+    kw = {}
+    if a is not None:
+        kw = dict(ploidy=a.ploidy, windows_sampling_factor=a.A)
+        if a.workload == "wgs":
+            kw["gender"] = 1
+    return Params.default(insert_mean=400, insert_min=170, insert_max=520, lseq=150, rmdup=1, **kw)
 
 
 # ---------------------------------------------------------------------------------------------- clocks sampler
@@ -113,7 +134,7 @@ HOT_TIMERS = (0, 1, 2, 3, 4, 7, 8)      # window management, -M, evidence, per-p
 
 def bench_config(a):
     """The `config` object of the JSON line: the workload only (identical in both arms; run details live under other keys)."""
-    return {"workload": workload_name(a), "contig_len": int(a.mb * 1e6), "depth": a.depth, "flags": "-M (duplicate filter on), defaults otherwise",
+    return {"workload": workload_name(a), "contig_len": int(a.mb * 1e6), "depth": a.depth, "flags": "-M (duplicate filter on), defaults otherwise" if a.workload != "tetra" else f"-M -p {a.ploidy} -A {a.A}",
             "generator": ("tools/workloads.py chr20_spec" if not a.simple else "simple (single-M reads)"),
             "step": "evidence + SNV/indel/SV scan (gromgpu_chr_run) + read-depth CNV path (gromgpu_chr_cnv, incl. its host parts)",
             "partition": "one contig per GPU, no data-path collective",
@@ -153,13 +174,14 @@ def cpu_reference_run(a, steps: int, warmup: int):
         if os.path.exists(tsc):
             hz = float(subprocess.run([tsc], stdout=subprocess.PIPE, text=True).stdout.strip() or 0) or None
         times, hot = [], []
+        extra = ["-p", str(a.ploidy), "-A", str(a.A)] if a.workload == "tetra" else (["-g", "1"] if a.workload == "wgs" else [])
         for it in range(warmup + steps):
             for ext in (".mean", ".info"):
                 for q in (meta["bam"] + ext, meta["fasta"] + ext):
                     if os.path.exists(q):
                         os.remove(q)
             t0 = time.perf_counter()
-            pr = subprocess.run([run_exe, "-i", meta["bam"], "-r", meta["fasta"], "-o", os.path.join(tmp, "out.vcf"), "-M", "-P", str(nproc)],
+            pr = subprocess.run([run_exe, "-i", meta["bam"], "-r", meta["fasta"], "-o", os.path.join(tmp, "out.vcf"), "-M", "-P", str(nproc)] + extra,
                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             dt = time.perf_counter() - t0
             if pr.returncode != 0:
@@ -174,7 +196,7 @@ def cpu_reference_run(a, steps: int, warmup: int):
                 hot.append(cyc)
         sec = float(np.mean(times))
         out = {"value": bases / sec, "unit": UNIT, "cores": 2 * nproc, "kind": "reference",
-               "sample": f"{os.path.basename(exe)} -M -P {nproc} on {nproc} contigs x {a.cpu_sample_mb:g} Mb of the config-3 generator at {a.depth:g}x "
+               "sample": f"{os.path.basename(exe)} -M {' '.join(extra)} -P {nproc} on {nproc} contigs x {a.cpu_sample_mb:g} Mb of the config-3 generator at {a.depth:g}x "
                          f"({bases / 1e6:.0f} M aligned bases; whole program incl. two BAM decode passes, tables, VCF text), {sec:.2f} s wall, host has {cores} cores",
                "seconds": sec, "aligned_bases": bases}
         if hz and hot and hot[0] > 0:
@@ -253,7 +275,7 @@ def main_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    prm = params_for_bench()
+    prm = params_for_bench(a)
     hez, mq = hostlib.tables(None, prm.min_mapq)
     # synthetic chr20-sized contig of this rank (rank-specific seed); inputs (>3 GB) far exceed the 126 MB L2
     P = int(a.mb * 1e6)
@@ -489,7 +511,11 @@ if __name__ == "__main__":
 
     def print(*a, **k):                                        # noqa: A001 - the two arms print their JSON line through this
         _buf.append(" ".join(str(x) for x in a))
-    rc = main_reference(args) if args.impl == "reference" else main_b200(args)
+    if args.workload == "wgs" and args.impl != "reference":
+        from tools import wgs_bench
+        rc = wgs_bench.main_wgs(args, print)
+    else:
+        rc = main_reference(args) if args.impl == "reference" else main_b200(args)
     sys.stdout.flush()
     os.dup2(_real_stdout, 1)
     for line in _buf:

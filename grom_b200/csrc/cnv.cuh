@@ -1020,7 +1020,7 @@ __device__ __forceinline__ uint32_t seed_outcome(const SegCtx &C, int64_t p, int
     return unres;
 }
 constexpr int SEED_CTA_WORDS = 256;
-__global__ void __launch_bounds__(256) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+__global__ void __launch_bounds__(256, 4) k_seed_eval(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
                                                    unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ mid, uint32_t mid_cap, uint32_t *__restrict__ jump0, uint32_t *__restrict__ u1)
 {
@@ -1106,16 +1106,17 @@ __global__ void __launch_bounds__(256) k_seed_eval(SegCtx Cdel, SegCtx Cdup, con
 // different numbers of positions (the give-up rule is a first-passage time), and a lane that is done moves on to its next seed while
 // its neighbours still walk -- lanes that meet again in the walk's loop are issued together.
 template <int PHASE>
-__global__ void __launch_bounds__(128) k_seed_eval_mid(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+__global__ void __launch_bounds__(128, 8) k_seed_eval_mid(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                        uint32_t *__restrict__ land, uint32_t cap, uint32_t n_del, uint32_t n_dup, SeedCall *__restrict__ calls, uint32_t call_cap,
                                                        unsigned int *__restrict__ n_calls, SeedTodo *__restrict__ mid, uint32_t mid_cap, SeedTodo *__restrict__ todo, uint32_t todo_cap,
                                                        uint32_t *__restrict__ jump0, uint32_t *__restrict__ open_bits, const uint32_t *__restrict__ nz, const uint32_t *__restrict__ nzwp,
-                                                       const uint32_t *__restrict__ u1, const uint32_t *__restrict__ safe, uint32_t *__restrict__ run_open)
+                                                       const uint32_t *__restrict__ u1, const uint32_t *__restrict__ safe, uint32_t *__restrict__ run_open, SeedTodo *__restrict__ wl)
 {
-    const uint32_t n_mid = min(n_calls[8], mid_cap);
+    // PHASE 0 classifies the list, PHASE 2 walks the run ends it set aside (list `wl`, compact: full warps), PHASE 1 the deferred seeds
+    const uint32_t n_mid = PHASE == 2 ? min(n_calls[13], mid_cap) : min(n_calls[8], mid_cap);
     const uint32_t unres = (uint32_t)SEG_UNRESOLVED << LAND_SHIFT;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_mid; i += gridDim.x * blockDim.x) {
-        const SeedTodo t = mid[i];
+        const SeedTodo t = PHASE == 2 ? wl[i] : mid[i];
         const SegCtx &C = t.kind ? Cdup : Cdel;
         const int64_t p = t.pos;
         const int c0 = C.cls(p);
@@ -1135,13 +1136,14 @@ __global__ void __launch_bounds__(128) k_seed_eval_mid(SegCtx Cdel, SegCtx Cdup,
                 }
             }
             if (e == unres && ((u1[(int64_t)t.kind * words + ((p + 1) >> 5)] >> ((p + 1) & 31)) & 1u)) { mid[i].pad = 1; continue; }      // deferred
-        } else {
+            if (e == unres && MID_EVAL) { const unsigned int k = atomicAdd(n_calls + 13, 1u); if (k < mid_cap) { wl[k] = t; continue; } }         // a run end: walked by the next launch
+        } else if (PHASE == 1) {
             if (!t.pad) continue;                                                              // dealt with in phase 0
             // the last seed of the run of listed seeds this one sits in stayed open in phase 0: open as well, no walk
             if ((run_open[((int64_t)(t.kind * 2 + t.variant)) * words + (p >> 5)] >> (p & 31)) & 1u) { walk = false; atomicAdd(n_calls + 11, 1u); }
         }
-        if (e == unres && walk && MID_EVAL) e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
-        if (PHASE == 0 && e == unres) {
+        if (PHASE != 0 && e == unres && walk && MID_EVAL) e = seed_outcome(C, p, c0 == 2 ? t.variant : c0, calls, call_cap, n_calls);
+        if (PHASE != 1 && e == unres) {
             // a run end that stays open: flag the whole run of listed seeds to its left (phase 1 leaves them open without a walk)
             const uint32_t *ub = u1 + (int64_t)t.kind * words;
             uint32_t *ro0 = run_open + ((int64_t)(t.kind * 2 + t.variant)) * words, *ro1 = c0 != 2 ? run_open + ((int64_t)(t.kind * 2 + 1)) * words : nullptr;
@@ -1280,7 +1282,7 @@ __global__ void __launch_bounds__(256) k_seed_filter2(const uint32_t *__restrict
     k0 = __shfl_sync(0xffffffffu, k0, __ffs(m) - 1);
     if (keep) out[k0 + __popc(m & ((1u << lane) - 1u))] = t;
 }
-__global__ void __launch_bounds__(64) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
+__global__ void __launch_bounds__(64, 16) k_seed_eval2(SegCtx Cdel, SegCtx Cdup, const uint32_t *__restrict__ seeds, int64_t words, const uint32_t *__restrict__ wp,
                                                    uint32_t *__restrict__ land, uint32_t cap, SeedCall *__restrict__ calls, uint32_t call_cap,
                                                    unsigned int *__restrict__ n_calls, const SeedTodo *__restrict__ todo, uint32_t n_del, uint32_t n_dup,
                                                    uint32_t *__restrict__ jump0)

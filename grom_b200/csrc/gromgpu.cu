@@ -1269,7 +1269,7 @@ struct CnvState;
 static void cnv_state_free(CnvState *c);
 struct gromgpu_chr {
     int tid = 0;
-    int64_t P = 0, Ppad = 0;
+    int64_t P = 0, Ppad = 0, P_cap = 0;          // P_cap: the length the per-position buffers were allocated for (gromgpu_chr_rebind)
     cudaStream_t stream = nullptr;
     char *d_fasta = nullptr;
     int32_t *d_arrays = nullptr;
@@ -1381,7 +1381,7 @@ extern "C" int gromgpu_chr_begin_on(gromgpu_chr **out, int tid, const char *fast
     ON_DEV();
     if (len <= 0 || len > 0x7fffffff) return fail("gromgpu_chr_begin: chromosome length %lld unsupported", (long long)len);
     gromgpu_chr *h = new gromgpu_chr();
-    h->tid = tid; h->P = len; h->Ppad = (len + 1023) & ~(int64_t)1023; h->stream = stream ? (cudaStream_t)stream : g_stream;
+    h->tid = tid; h->P = len; h->P_cap = len; h->Ppad = (len + 1023) & ~(int64_t)1023; h->stream = stream ? (cudaStream_t)stream : g_stream;
     memset(&h->stats, 0, sizeof(h->stats)); memset(&h->res, 0, sizeof(h->res));
     for (int i = 0; i < 12; i++) h->ev[i] = nullptr;
     *out = h;
@@ -1422,6 +1422,27 @@ extern "C" int gromgpu_chr_reset(gromgpu_chr *h, const char *fasta)
     if (fasta) CK(cudaMemcpyAsync(h->d_fasta, fasta, (size_t)h->P, cudaMemcpyHostToDevice, h->stream));
     for (int i = 0; i < B_COUNT; i++) h->rb[i].size = 0;
     h->n_reads = h->n_cigar = h->n_slots = 0; h->last_pos = -1; h->last_lseq = 0; h->n_leading = 0; h->ran = false;
+    return 0;
+}
+
+extern "C" int gromgpu_chr_rebind(gromgpu_chr *h, int tid, const char *fasta, int64_t len)
+{
+    if (!h || !fasta) return fail("gromgpu_chr_rebind: null argument");
+    ON_DEV();
+    if (len <= 0) return fail("gromgpu_chr_rebind: chromosome length %lld unsupported", (long long)len);
+    if (len > h->P_cap) return 1;                                     // does not fit: the caller frees the handle and begins a new one
+    cudaStream_t s = h->stream;
+    h->tid = tid; h->P = len; h->Ppad = (len + 1023) & ~(int64_t)1023;
+    // the same state gromgpu_chr_begin leaves: characters uploaded, every per-position array of the (new, shorter) layout zero
+    CK(cudaMemcpyAsync(h->d_fasta, fasta, (size_t)len, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(h->d_cl_int, 0, sizeof(int32_t) * 36 * (size_t)h->Ppad, s));
+    CK(cudaMemsetAsync(h->d_cl_dist, 0, sizeof(double) * 10 * (size_t)h->Ppad, s));
+    CK(cudaMemsetAsync(h->d_arrays, 0, sizeof(int32_t) * (size_t)GA_COUNT * (size_t)h->Ppad, s));
+    CK(cudaMemsetAsync(h->d_sv_dirty, 0, sizeof(uint16_t) * h->cap_sv_tiles, s));
+    for (int i = 0; i < B_COUNT; i++) h->rb[i].size = 0;
+    h->n_reads = h->n_cigar = h->n_slots = 0; h->last_pos = -1; h->last_lseq = 0; h->n_leading = 0; h->ran = false; h->last_lseq_applied = 0;
+    h->n_items = 0;
+    memset(&h->stats, 0, sizeof(h->stats)); memset(&h->res, 0, sizeof(h->res));
     return 0;
 }
 
@@ -1905,12 +1926,13 @@ struct CnvState {
     uint32_t *d_blk = nullptr, *d_wp = nullptr, *d_land = nullptr; uint32_t land_cap = 0, spec_cap = 0; int nb = 0;
     cnv::SeedCall *d_spec = nullptr; unsigned int *d_nspec = nullptr; double *d_winsd = nullptr;
     uint32_t *d_u1 = nullptr; int32_t *d_ends = nullptr; static constexpr uint32_t ENDS_CAP = 1u << 20;
+    int64_t P_cap = 0, words_cap = 0;                                  // what the buffers were sized for (a handle rebound to a shorter contig keeps them)
     std::vector<grom_cnv_call> calls; std::vector<double> tail_gm;
     std::vector<double> win_sd, win_thr, bin_d; std::vector<int64_t> win_cnt, bin_n;
     int64_t P = 0, words = 0;
     int q = 0;
     std::vector<double> sd_tbl, wtab;
-    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, heads, head_out, mid;
+    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, heads, head_out, mid, walk;
     uint32_t *d_open = nullptr;                              // [2 kinds][2 classes][words]: seeds still open after the first round
     cnv::SeedHead *h_heads = nullptr; cnv::HeadOutcome *h_head_out = nullptr;      // pinned
     uint32_t *h_win = nullptr; size_t h_win_cap = 0;         // pinned landing area of the record windows of the run heads
@@ -1924,7 +1946,7 @@ static void cnv_state_free(CnvState *c)
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_z); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
-    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->heads, &c->head_out, &c->mid}) if (g->p) cudaFree(g->p);
+    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->heads, &c->head_out, &c->mid, &c->walk}) if (g->p) cudaFree(g->p);
     cudaFree(c->d_open);
     if (c->h_heads) cudaFreeHost(c->h_heads);
     if (c->h_head_out) cudaFreeHost(c->h_head_out);
@@ -2010,7 +2032,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     const int32_t *A_gc = h->d_arrays + (int64_t)GA_GC * Ppad, *A_acgt = h->d_arrays + (int64_t)GA_ACGT * Ppad;
     const int64_t n_blk = (P + BLK_UNIT - 1) / BLK_UNIT, n_tiles = (P + CTILE - 1) / CTILE, words = (P + 31) / 32;
     c.words = words;
+    if (c.d_depth && P > c.P_cap) return fail("gromgpu_chr_cnv: the handle's read-depth buffers hold %lld positions, the contig has %lld", (long long)c.P_cap, (long long)P);
     if (!c.d_depth) {
+        c.P_cap = P; c.words_cap = words;
         CK(cudaMalloc(&c.d_depth, sizeof(int32_t) * P)); CK(cudaMalloc(&c.d_mq8, P)); CK(cudaMalloc(&c.d_rec, sizeof(uint32_t) * P)); CK(cudaMalloc(&c.d_z, sizeof(double) * P));
         CK(cudaMalloc(&c.d_seed, sizeof(uint32_t) * 3 * words));      // deletion seeds, duplication seeds, positions with a z value
         CK(cudaMalloc(&c.d_pre, sizeof(PreOut) * n_blk));
@@ -2019,15 +2043,13 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         c.rep_cap = (unsigned int)(P / 20 + 2);
         CK(cudaMalloc(&c.d_rep, sizeof(RepRec) * c.rep_cap)); CK(cudaMalloc(&c.d_nrep, sizeof(unsigned int)));
         CK(cudaMalloc(&c.d_tile, 4 * n_tiles));
-        CK(cudaMallocHost(&c.h_rec, sizeof(uint32_t) * P)); CK(cudaMallocHost(&c.h_seed, sizeof(uint32_t) * 2 * words));
         CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&c.ev_z, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c.ev_copied, cudaEventDisableTiming));
         c.nb = (int)((words + SEED_WORDS - 1) / SEED_WORDS); c.land_cap = (uint32_t)(P / 4 + 1024);
         CK(cudaMalloc(&c.d_blk, sizeof(uint32_t) * (3 * c.nb + 4))); CK(cudaMalloc(&c.d_wp, sizeof(uint32_t) * 3 * words));
         CK(cudaMalloc(&c.d_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
-        CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * words)); CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap));
         c.spec_cap = (uint32_t)std::min<int64_t>(P / 8 + 1024, (int64_t)1 << 28);
-        CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
+        CK(cudaMalloc(&c.d_spec, sizeof(SeedCall) * (size_t)c.spec_cap));
         CK(cudaMalloc(&c.d_nspec, 16 * sizeof(unsigned int))); CK(cudaMalloc(&c.d_winsd, sizeof(double) * (3 * (Lmax + 1) + 1)));      // win_sd, win_thr, then the tail bound gm [Lmax + 2]
         CK(cudaMalloc(&c.d_u1, sizeof(uint32_t) * 8 * words)); CK(cudaMalloc(&c.d_ends, sizeof(int32_t) * CnvState::ENDS_CAP));      // d_u1: [2][words] listed seeds, [2][words] safe stretch ends, [4][words] runs whose last seed stayed open
     }
@@ -2356,6 +2378,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     bool have_host_rec = false;
     auto pull_records = [&]() -> int {
         if (have_host_rec) return 0;
+        // pinned landing areas of the rare host paths, sized for the handle's capacity, allocated the first time one of them runs
+        if (!c.h_rec) { CK(cudaMallocHost(&c.h_rec, sizeof(uint32_t) * c.P_cap)); CK(cudaMallocHost(&c.h_seed, sizeof(uint32_t) * 2 * c.words_cap)); CK(cudaMallocHost(&c.h_wp, sizeof(uint32_t) * 2 * c.words_cap)); }
         CK(cudaMemcpyAsync(c.h_rec, c.d_rec, sizeof(uint32_t) * P, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(c.h_seed, c.d_seed, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(c.h_wp, c.d_wp, sizeof(uint32_t) * 2 * words, cudaMemcpyDeviceToHost, s));
@@ -2456,10 +2480,14 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 k_seed_eval<<<dim3((unsigned)((words + SEED_CTA_WORDS - 1) / SEED_CTA_WORDS), 2), 256, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
                                                                                                                    c.d_nspec, t_mid.as<SeedTodo>(), todo_cap, J, c.d_u1); n_launch++;
                 ctx[0].bound = ctx[1].bound = SEED_BOUND;
+                Grow &t_wl = c.walk;
+                if (!t_wl.ensure(sizeof(SeedTodo) * (size_t)todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
                 k_seed_eval_mid<0><<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
-                                                           t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words); n_launch++;
+                                                           t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words, t_wl.as<SeedTodo>()); n_launch++;
+                k_seed_eval_mid<2><<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
+                                                           t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words, t_wl.as<SeedTodo>()); n_launch++;
                 k_seed_eval_mid<1><<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
-                                                           t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words); n_launch++;
+                                                           t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words, t_wl.as<SeedTodo>()); n_launch++;
             }
             // Open seeds (ran past the first round's bound: genuine events and long stretches without coverage).  The heads of their runs are
             // evaluated exactly by the host, all in parallel, over windows of records fetched in one go (a long walk is a dependent chain:
@@ -2701,6 +2729,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             if (pull_records()) return -1;
             unsigned int n_spec_host = 0;
             if (have_land) {
+                if (!c.h_land) { CK(cudaMallocHost(&c.h_land, sizeof(uint32_t) * 4 * (size_t)c.land_cap)); CK(cudaMallocHost(&c.h_spec, sizeof(SeedCall) * (size_t)c.spec_cap)); }
                 for (int k = 0; k < 2; k++) if (seed_tot[k]) CK(cudaMemcpyAsync(c.h_land + (size_t)k * 2 * c.land_cap, c.d_land + (size_t)k * 2 * c.land_cap, sizeof(uint32_t) * 2 * seed_tot[k], cudaMemcpyDeviceToHost, s));
                 CK(cudaMemcpyAsync(&n_spec_host, c.d_nspec, sizeof(n_spec_host), cudaMemcpyDeviceToHost, s));
                 CK(cudaStreamSynchronize(s));

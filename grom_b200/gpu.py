@@ -53,6 +53,7 @@ def lib() -> C.CDLL:
         L.gromgpu_push_reads.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
         L.gromgpu_chr_run.argtypes = [C.c_void_p]
         L.gromgpu_chr_reset.argtypes = [C.c_void_p, C.c_void_p]
+        L.gromgpu_chr_rebind.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
         L.gromgpu_chr_result.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.gromgpu_chr_finish.argtypes = [C.c_void_p, C.POINTER(CResult)]
         L.gromgpu_chr_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
@@ -193,6 +194,17 @@ class Chromosome:
             assert fasta.dtype == np.uint8 and fasta.shape[0] == self.length and fasta.flags.c_contiguous
             ptr = fasta.ctypes.data
         _ck(lib().gromgpu_chr_reset(self._h, ptr))
+
+    def rebind(self, tid: int, fasta: np.ndarray) -> bool:
+        """Reuse the handle (all device buffers kept) for another chromosome no longer than the one it was created for
+        (gromgpu_chr_rebind).  False = it does not fit; close() and create a new Chromosome."""
+        fa = np.ascontiguousarray(fasta, dtype=np.uint8)
+        rc = lib().gromgpu_chr_rebind(self._h, tid, fa.ctypes.data, int(fa.shape[0]))
+        if rc == 1:
+            return False
+        _ck(rc)
+        self.length = int(fa.shape[0])
+        return True
 
     def sync(self):
         _ck(lib().gromgpu_chr_sync(self._h))

@@ -87,27 +87,32 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
         bus, pick, errors = threading.Lock(), threading.Lock(), []
         names, lens = list(bam.names), list(bam.lens)
 
-        def one_contig(lane_bam, t: int, stream: Optional[int]):
+        def one_contig(lane_bam, t: int, stream: Optional[int], slot: list):
+            """slot = [handle, reserved bytes] of this lane: the handle is begun for the lane's first contig (the largest it will see,
+            the queue is sorted largest first) and rebound -- same device buffers -- for the rest (gromgpu_chr_rebind)"""
             name = names[t].lower()
             chars = fasta[name]
             batch = lane_bam.read_target(t)                                 # decoded just before it is pushed, dropped right after
-            need = gpu.chr_bytes_estimate(len(chars), batch.n_reads, batch.n_base_slots)
-            inflight.acquire(need)
-            try:
-                with gpu.Chromosome(t, chars, stream=stream) as ch:
-                    with bus:
-                        ch.push_reads(batch); ch.sync()
-                    del batch
-                    res = ch.finish()
-                    cnv = ch.cnv(params=prm)
-            finally:
-                inflight.release(need)
+            if slot[0] is None or not slot[0].rebind(t, chars):
+                if slot[0] is not None:
+                    slot[0].close(); inflight.release(slot[1]); slot[0] = None
+                need = gpu.chr_bytes_estimate(len(chars), batch.n_reads, batch.n_base_slots)
+                inflight.acquire(need)
+                slot[1] = need
+                slot[0] = gpu.Chromosome(t, chars, stream=stream)
+            ch = slot[0]
+            with bus:
+                ch.push_reads(batch); ch.sync()
+            del batch
+            res = ch.finish()
+            cnv = ch.cnv(params=prm)
             text[t] = hostlib.vcf_contig(prm, name, chars, res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, cnv.calls)
             if ctx_out is not None:
                 ctx_out[t] = hostlib.ctx_contig(prm, t, res.sv_ev)
 
         def lane():
             stream = gpu.stream_create() if n_lanes > 1 else None
+            slot = [None, 0]
             try:
                 with hostlib.Bam(bam_path) as lane_bam:                    # one reader per lane (the batcher seeks in its file)
                     while not errors:
@@ -115,10 +120,12 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
                             if not work:
                                 return
                             t = work.pop(0)
-                        one_contig(lane_bam, t, stream)
+                        one_contig(lane_bam, t, stream, slot)
             except BaseException as e:                                      # surfaced by the caller's thread below
                 errors.append(e)
             finally:
+                if slot[0] is not None:
+                    slot[0].close(); inflight.release(slot[1])
                 gpu.stream_destroy(stream)
 
         if n_lanes <= 1:

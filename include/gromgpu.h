@@ -100,6 +100,13 @@ int64_t gromgpu_device_free_bytes(void);
  * same length: lets one handle be reused for the next chromosome-sized unit without reallocating. */
 int gromgpu_chr_reset(gromgpu_chr *h, const char *fasta);
 
+/* Reuse the handle for ANOTHER chromosome that is no longer than the one it was begun for: new tid, new characters, every
+ * per-position array zeroed, all device buffers (and the read-depth state of gromgpu_chr_cnv) kept.  The per-genome driver
+ * processes its contigs largest first (src/GROM.c:22318-22336), so each lane begins one handle and rebinds it for the rest:
+ * no allocation after the first contig (the reference allocates and frees ~2-3 GB per chromosome, src/GROM.c:1884-1908).
+ * Returns 0, 1 if `len` exceeds the handle's capacity (nothing changed: free it and begin a new one), < 0 on error. */
+int gromgpu_chr_rebind(gromgpu_chr *h, int tid, const char *fasta, int64_t len);
+
 /* Append reads of this chromosome in BAM order (host pointers; may be called repeatedly with
  * consecutive slices).  Replaces the my_samread pulls at src/GROM.c:5740, 10968, 14861. */
 int gromgpu_push_reads(gromgpu_chr *h, const grom_read_batch *b);

@@ -120,3 +120,24 @@ def test_lanes_on_second_device_if_present():
         t.join()
     assert not errs, errs
     assert len(outs) == 3 and outs[0] == outs[1] == outs[2]
+
+
+def test_rebound_handle_matches_oracle():
+    """One handle begun for the largest contig and rebound (gromgpu_chr_rebind: buffers kept, arrays zeroed) for shorter ones -- the
+    per-lane flow of the genome drivers -- gives the oracle's arrays, candidates and read-depth calls on every contig; a longer contig
+    is refused (return 1) and leaves the handle usable."""
+    prm = _prm(150, rmdup=1)
+    hez, mq = hostlib.tables(None, prm.min_mapq)
+    spec = _spec(61, 150, length=500_000)
+    spec.contigs = [("chrA", 500_000), ("chrB", 320_000), ("chrC", 150_000), ("chrD", 40_000)]
+    cs = synth.simulate(spec)
+    gpu.init(0, hez, mq, prm)
+    with gpu.Chromosome(cs[0].batch.tid, cs[0].chars) as ch:
+        ch.push_reads(cs[0].batch); ch.finish(); ch.cnv(params=prm)          # leaves evidence, clusters and read-depth state of chrA behind
+        for c in (cs[2], cs[1], cs[3], cs[0]):
+            out = parity.compare_gpu_oracle(prm, c, hez, mq, handle=ch)
+            assert out["positions"] == len(c.chars)
+        big = np.full(600_000, ord("A"), dtype=np.uint8)
+        assert ch.rebind(9, big) is False
+        out = parity.compare_gpu_oracle(prm, cs[1], hez, mq, handle=ch)
+        assert out["snv"] > 10

@@ -291,6 +291,10 @@ static void *lane_main(void *arg)
     void *stream = NULL;
     if (gromgpu_stream_create(&stream)) { worker_fail(w, "gromgpu_stream_create", gromgpu_last_error()); gromhost_bam_close(bam); return NULL; }
     size_t cap = 1 << 20; char *text = (char *)malloc(cap);
+    /* one handle per lane: begun for the lane's first contig (the largest it will see: the queue is sorted largest first) and
+     * rebound -- same device buffers, new contig -- for the rest; its memory reservation is kept for as long as the handle lives */
+    gromgpu_chr *h = NULL;
+    int64_t held = 0;
     for (;;) {
         pthread_mutex_lock(&w->pick);
         const int k = (w->failed || w->next >= w->n_work) ? -1 : w->next++;
@@ -308,15 +312,23 @@ static void *lane_main(void *arg)
         double t1 = now_s();
         /* admission: the handle's device memory must fit beside the contigs already in flight; a contig that fits nowhere runs alone */
         const int64_t need = gromgpu_chr_bytes_estimate(flen, v.n_reads, v.n_base_slots);
-        pthread_mutex_lock(&w->mem);
-        while (w->running && w->mem_used + need > w->mem_budget) pthread_cond_wait(&w->mem_cv, &w->mem);
-        w->mem_used += need; w->running++;
-        pthread_mutex_unlock(&w->mem);
-        gromgpu_chr *h = NULL; gromgpu_result res; gromgpu_cnv_result cnv; gromgpu_stats st;
+        gromgpu_result res; gromgpu_cnv_result cnv; gromgpu_stats st;
         int bad = 0;
         double t2 = t1, t3 = t1, t4 = t1, t5 = t1;
         memset(&st, 0, sizeof(st)); memset(&cnv, 0, sizeof(cnv)); memset(&res, 0, sizeof(res));
-        if (gromgpu_chr_begin_on(&h, c.tid, chars, flen, stream)) bad = 1;
+        int rb = h ? gromgpu_chr_rebind(h, c.tid, chars, flen) : 1;
+        if (rb < 0) bad = 1;
+        else if (rb == 1) {
+            if (h) {                                          /* (a larger contig after a smaller one: only if the queue was not sorted) */
+                gromgpu_chr_free(h); h = NULL;
+                pthread_mutex_lock(&w->mem); w->mem_used -= held; w->running--; held = 0; pthread_cond_broadcast(&w->mem_cv); pthread_mutex_unlock(&w->mem);
+            }
+            pthread_mutex_lock(&w->mem);
+            while (w->running && w->mem_used + need > w->mem_budget) pthread_cond_wait(&w->mem_cv, &w->mem);
+            w->mem_used += need; w->running++; held = need;
+            pthread_mutex_unlock(&w->mem);
+            if (gromgpu_chr_begin_on(&h, c.tid, chars, flen, stream)) bad = 1;
+        }
         if (!bad) {
             pthread_mutex_lock(&w->bus);                      /* one upload at a time: the PCIe link is the shared resource */
             bad = gromgpu_push_reads(h, &v) || gromgpu_chr_sync(h);
@@ -363,11 +375,6 @@ static void *lane_main(void *arg)
             }
             t5 = now_s();
         }
-        if (h) gromgpu_chr_free(h);
-        pthread_mutex_lock(&w->mem);
-        w->mem_used -= need; w->running--;
-        pthread_cond_broadcast(&w->mem_cv);
-        pthread_mutex_unlock(&w->mem);
         pthread_mutex_lock(&w->pick);
         w->t_decode += t1 - t0; w->t_upload += t2 - t1; w->t_gpu_run += t3 - t2; w->t_cnv += t4 - t3; w->t_text += t5 - t4;
         w->reads += n_reads; w->bases += st.aligned_bases; w->records += nrec; w->ms_dev_run += st.ms_total; w->ms_dev_cnv += cnv.ms_device;
@@ -375,6 +382,8 @@ static void *lane_main(void *arg)
         free(chars); free(lname);
         if (bad) break;
     }
+    if (h) gromgpu_chr_free(h);
+    if (held) { pthread_mutex_lock(&w->mem); w->mem_used -= held; w->running--; pthread_cond_broadcast(&w->mem_cv); pthread_mutex_unlock(&w->mem); }
     free(text);
     gromgpu_stream_destroy(stream);
     gromhost_bam_close(bam);

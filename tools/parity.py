@@ -20,7 +20,7 @@ def compare_gpu_oracle(prm, contig, hez, mq, chr_name: str = None, cnv: bool = T
     ch = handle if handle is not None else gpu.Chromosome(contig.batch.tid, contig.chars)
     try:
         if handle is not None:
-            ch.reset(contig.chars)
+            assert ch.rebind(contig.batch.tid, contig.chars), "the handle is too small for this contig"
         ch.push_reads(contig.batch)
         res = ch.finish()
         g = ch.cnv(params=prm) if cnv else None

@@ -18,11 +18,13 @@ ap.add_argument("--skip-cnv", type=int, default=0)
 ap.add_argument("--workload", default="config3", choices=["config3", "simple"], help="config3 = tools/workloads.chr20_spec (what bench.py runs)")
 ap.add_argument("--ploidy", type=int, default=2)
 ap.add_argument("--A", type=int, default=2)
+ap.add_argument("--seed", type=int, default=20)
+ap.add_argument("--dummy", type=int, default=1_000_000)
 a = ap.parse_args()
 t = time.time()
 if a.workload == "config3":
     from tools import workloads
-    spec = workloads.chr20_spec(mb=a.mb, depth=a.depth, seed=20, name="chrP", cnv_per_mb=a.cnv_per_mb if a.cnv_per_mb > 0 else 0.25)
+    spec = workloads.chr20_spec(mb=a.mb, depth=a.depth, seed=a.seed, name="chrP", cnv_per_mb=a.cnv_per_mb if a.cnv_per_mb > 0 else 0.25, dummy_len=a.dummy)
 else:
     spec = synth.SynthSpec(contigs=[("chrP", int(a.mb * 1e6))], depth=a.depth, seed=20, simple=bool(a.simple), dup_frac=0.05, simple_disc_frac=0.01, names=False, cnv_per_mb=a.cnv_per_mb)
 c = synth.simulate(spec)[0]
