@@ -344,7 +344,9 @@ def main_b200(a):
         ms_e2e_seq = e0.elapsed_time(e1)
         assert len(r2.snv) == len(res.snv) and len(cn2.calls) == len(cn.calls)
         import threading
-        n_lanes = max(1, a.lanes)
+        # contigs in flight: as many as asked for, as long as their handles fit beside the first one (same admission rule as the genome drivers)
+        need = gpu.chr_bytes_estimate(P, c.batch.n_reads, c.batch.n_base_slots)
+        n_lanes = max(1, min(a.lanes, 1 + int(0.9 * gpu.device_free_bytes() // max(1, need))))
         lanes = [(ch, stream)]
         for _ in range(n_lanes - 1):
             st_x = torch.cuda.Stream()
@@ -481,7 +483,7 @@ def main_b200(a):
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps,
                     "upload_form": ("canonical arrays" if not pinned.layout_flags else "transport-compact (include/grom_reads.h GROM_LAYOUT_*): "
                                     + ", ".join(n for bit, n in ((1, "offsets derived on the device"), (2, "4-bit dictionary qualities"), (16, "2-bit dictionary qualities"), (8, "2-bit bases + exception list"), (4, "sparse SA fields")) if pinned.layout_flags & bit)),
-                    "mode": f"{max(1, a.lanes)} contigs in flight (one stream / host thread each, uploads serialised): the upload of step i+1 overlaps the kernels and host part of step i",
+                    "mode": f"{n_lanes} contigs in flight (one stream / host thread each, uploads serialised): the upload of step i+1 overlaps the kernels and host part of step i",
                     "one_at_a_time": {"value": bases * a.steps / (ms_e2e_seq * 1e-3), "ms_per_step": ms_e2e_seq / a.steps}},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_pileup", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -1352,7 +1352,21 @@ struct Call { int64_t start, end; double z; };
 struct DevTmpRaw { void *p = nullptr; ~DevTmpRaw() { if (p) cudaFree(p); } };
 struct Grow {                  // grow-only device buffer kept across calls
     void *p = nullptr; size_t cap = 0;
-    bool ensure(size_t n) { if (n <= cap) return true; if (p) cudaFree(p); p = nullptr; cap = n + n / 4 + 256; return cudaMalloc(&p, cap) == cudaSuccess; }
+    bool ensure(size_t n)
+    {
+        if (n <= cap && p) return true;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 4 + 256;
+        if (cudaMalloc(&p, want) != cudaSuccess) {              // with less headroom before giving up; a failed buffer never looks allocated
+            cudaGetLastError();
+            if (cudaMalloc(&p, n + 256) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+            cap = n + 256;
+            return true;
+        }
+        cap = want;
+        return true;
+    }
     template <class T> T *as() { return (T *)p; }
 };
 

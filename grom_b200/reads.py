@@ -186,23 +186,18 @@ class ReadBatch:
 
     def repack_canonical(self) -> "ReadBatch":
         """Same reads with cigar[] / base slots laid out back to back (each read's slots rounded up to BASE_ALIGN): the
-        layout the host batcher produces.  Tooling for batches assembled by other means."""
+        layout the host batcher produces.  Tooling for batches assembled by other means (compiled loops: tools-side only)."""
         self.normalise()
-        n = self.n_reads
         lq = self.l_qseq.astype(np.int64)
         pad = (lq + BASE_ALIGN - 1) // BASE_ALIGN * BASE_ALIGN
         bo = np.concatenate([[0], np.cumsum(pad)]).astype(np.int64)
         nc = self.n_cigar.astype(np.int64)
         co = np.concatenate([[0], np.cumsum(nc)]).astype(np.int64)
-        within = np.arange(int(lq.sum())) - np.repeat(np.cumsum(lq) - lq, lq)
-        src = np.repeat(self.base_off.astype(np.int64), lq) + within
-        dst = np.repeat(bo[:-1], lq) + within
-        code = np.zeros(int(bo[-1]), dtype=np.uint8); qual = np.zeros(int(bo[-1]), dtype=np.uint8)
-        code[dst] = (self.seq4[src >> 1] >> ((~src & 1) << 2)) & 15
-        qual[dst] = self.qual[src]
+        seq4 = np.zeros(int(bo[-1]) // 2, dtype=np.uint8); qual = np.zeros(int(bo[-1]), dtype=np.uint8)
+        _jit()["repack"](self.base_off.astype(np.int64), lq, bo, self.seq4, self.qual, seq4, qual)
         cw = np.arange(int(nc.sum())) - np.repeat(co[:-1], nc)
         self.cigar = self.cigar[np.repeat(self.cigar_off.astype(np.int64), nc) + cw]
-        self.seq4 = ((code[0::2] << 4) | code[1::2]).astype(np.uint8)
+        self.seq4 = seq4
         self.qual = qual
         self.cigar_off, self.base_off = co[:-1].astype(np.uint64), bo[:-1].astype(np.uint64)
         self.layout_flags = 0
@@ -210,49 +205,46 @@ class ReadBatch:
 
     def compact(self) -> "ReadBatch":
         """Attach the transport-compact forms the data allow (lossless; the canonical arrays stay in place for host users):
-        offsets derived on the device, 4-bit dictionary-coded qualities when the batch holds <= 16 distinct values, and the
-        first-SA-entry fields only for the reads that have one."""
+        offsets derived on the device, 2- or 4-bit dictionary-coded qualities when the batch holds <= 4 / <= 16 distinct values,
+        2-bit bases with an exception list, and the first-SA-entry fields only for the reads that have one."""
         self.normalise()
         flags = 0
         if self.has_canonical_offsets():
             flags |= LAYOUT_CANONICAL_OFFSETS
-        owned = None
-        if (flags & LAYOUT_CANONICAL_OFFSETS) and self.qual.size and self.qual.size % 4 == 0:
-            ns = self.qual.size
+        ns = int(self.qual.size)
+        canon = bool(flags & LAYOUT_CANONICAL_OFFSETS) and ns > 0 and ns % 4 == 0
+        if canon:
+            J = _jit()
             lq = self.l_qseq.astype(np.int64)
-            owned = np.zeros(ns + 1, dtype=np.int32)                    # slots below l_qseq of their read (the rest is padding)
-            np.add.at(owned, self.base_off.astype(np.int64), 1); np.add.at(owned, self.base_off.astype(np.int64) + lq, -1)
-            owned = np.cumsum(owned[:-1]) > 0
-        vals = np.flatnonzero(np.bincount(self.qual, minlength=256)).astype(np.uint8) if self.qual.size else np.zeros(0, np.uint8)
-        base_vals = np.flatnonzero(np.bincount(self.qual[owned], minlength=256)).astype(np.uint8) if owned is not None else vals
-        if owned is not None and 0 < base_vals.size <= 4:
-            # <= 4 distinct qualities on the bases themselves (padding aside): 2 bits per slot; the device zeroes the padding again
-            lut = np.zeros(16, dtype=np.uint8); lut[:base_vals.size] = base_vals
-            inv = np.zeros(256, dtype=np.uint8); inv[base_vals] = np.arange(base_vals.size, dtype=np.uint8)
-            code = np.where(owned, inv[self.qual], 0).astype(np.uint8)
-            self.qual2 = np.ascontiguousarray((code[0::4] << 6) | (code[1::4] << 4) | (code[2::4] << 2) | code[3::4])
-            self.qual_lut = lut
-            flags |= LAYOUT_QUAL2
-        elif 0 < vals.size <= 16 and self.qual.size % 2 == 0:
-            lut = np.zeros(16, dtype=np.uint8); lut[:vals.size] = vals
-            inv = np.zeros(256, dtype=np.uint8); inv[vals] = np.arange(vals.size, dtype=np.uint8)
-            code = inv[self.qual]
-            self.qual4 = np.ascontiguousarray((code[0::2] << 4) | code[1::2])
-            self.qual_lut = lut
-            flags |= LAYOUT_QUAL4
-        if owned is not None:
-            ns = self.qual.size
-            slot = np.arange(ns, dtype=np.int64)
-            code = (self.seq4[slot >> 1] >> ((~slot & 1) << 2)) & 15
-            two_of = np.full(16, 255, dtype=np.uint8); two_of[[1, 2, 4, 8]] = [0, 1, 2, 3]
-            two = two_of[code]
-            exc = owned & (two == 255)
-            if int(exc.sum()) <= ns // 16:
-                two = np.where(owned & (two != 255), two, 0).astype(np.uint8)
-                self.seq2 = np.ascontiguousarray((two[0::4] << 6) | (two[1::4] << 4) | (two[2::4] << 2) | two[3::4])
-                self.seq_exc_slot = np.flatnonzero(exc).astype(np.uint64)
-                self.seq_exc_code = np.ascontiguousarray(code[exc].astype(np.uint8))
+            bo = self.base_off.astype(np.int64)
+            hist, exc_cnt = J["survey"](bo, lq, self.seq4, self.qual)            # qualities on the bases themselves (padding aside), non-ACGT codes per read
+            base_vals = np.flatnonzero(hist).astype(np.uint8)
+            if 0 < base_vals.size <= 4:
+                # <= 4 distinct qualities: 2 bits per slot; the device zeroes the padding again
+                lut = np.zeros(16, dtype=np.uint8); lut[:base_vals.size] = base_vals
+                inv = np.zeros(256, dtype=np.uint8); inv[base_vals] = np.arange(base_vals.size, dtype=np.uint8)
+                self.qual2 = np.zeros(ns // 4, dtype=np.uint8); self.qual_lut = lut
+                J["pack_qual2"](bo, lq, self.qual, inv, self.qual2)
+                flags |= LAYOUT_QUAL2
+            n_exc = int(exc_cnt.sum())
+            if n_exc <= ns // 16:
+                first = np.concatenate([[0], np.cumsum(exc_cnt)]).astype(np.int64)
+                self.seq2 = np.zeros(ns // 4, dtype=np.uint8)
+                self.seq_exc_slot = np.zeros(n_exc, dtype=np.uint64); self.seq_exc_code = np.zeros(n_exc, dtype=np.uint8)
+                J["pack_seq2"](bo, lq, self.seq4, first, self.seq2, self.seq_exc_slot, self.seq_exc_code)
                 flags |= LAYOUT_SEQ2
+        if not (flags & LAYOUT_QUAL2) and ns and ns % 2 == 0:
+            vals = np.flatnonzero(np.bincount(self.qual, minlength=256)).astype(np.uint8)
+            if 0 < vals.size <= 16:
+                lut = np.zeros(16, dtype=np.uint8); lut[:vals.size] = vals
+                inv = np.zeros(256, dtype=np.uint8); inv[vals] = np.arange(vals.size, dtype=np.uint8)
+                self.qual4 = np.zeros(ns // 2, dtype=np.uint8)
+                step = 1 << 28
+                for s0 in range(0, ns, step):
+                    code = inv[self.qual[s0:s0 + step]]
+                    self.qual4[s0 // 2:(s0 + code.size) // 2] = (code[0::2] << 4) | code[1::2]
+                self.qual_lut = lut
+                flags |= LAYOUT_QUAL4
         has = np.zeros(self.n_reads, dtype=bool)
         for k in SA_FIELDS:
             has |= getattr(self, k) != SA_NONE.get(k, 0)
@@ -356,3 +348,76 @@ def batch_from_c(view: CReadBatch, keep_names: bool) -> ReadBatch:
         b.qname_off = arr(view.qname_off, np.uint64, n + 1)
         b.qname_pool = arr(view.qname_pool, np.uint8, int(b.qname_off[-1]) if n else 0)
     return b.normalise()
+
+
+# ---- compiled loops of the two tooling helpers above (repack_canonical / compact): per read, no per-base index arrays
+_JIT = None
+
+
+def _jit():
+    global _JIT
+    if _JIT is not None:
+        return _JIT
+    from numba import njit, prange
+
+    @njit(parallel=True, cache=True)
+    def repack(old_off, lq, bo, seq4_old, qual_old, seq4_new, qual_new):
+        for i in prange(lq.shape[0]):                      # a read's slots start on a BASE_ALIGN boundary: no two reads share a byte
+            o, d = old_off[i], bo[i]
+            for j in range(lq[i]):
+                s_, t_ = o + j, d + j
+                code = (seq4_old[s_ >> 1] >> ((~s_ & 1) << 2)) & 15
+                seq4_new[t_ >> 1] |= np.uint8(code << ((~t_ & 1) << 2))
+                qual_new[t_] = qual_old[s_]
+
+    @njit(parallel=True, cache=True)
+    def survey(bo, lq, seq4, qual):
+        n = lq.shape[0]
+        nb = 256
+        hist = np.zeros((nb, 256), dtype=np.int64)
+        exc = np.zeros(n, dtype=np.int64)
+        for b in prange(nb):
+            for i in range(b * n // nb, (b + 1) * n // nb):
+                d = bo[i]
+                k = 0
+                for j in range(lq[i]):
+                    t_ = d + j
+                    hist[b, qual[t_]] += 1
+                    code = (seq4[t_ >> 1] >> ((~t_ & 1) << 2)) & 15
+                    if code != 1 and code != 2 and code != 4 and code != 8:
+                        k += 1
+                exc[i] = k
+        return hist.sum(axis=0), exc
+
+    @njit(parallel=True, cache=True)
+    def pack_qual2(bo, lq, qual, inv, out):
+        for i in prange(lq.shape[0]):
+            d = bo[i]
+            for j in range(lq[i]):
+                t_ = d + j
+                out[t_ >> 2] |= np.uint8(inv[qual[t_]] << ((3 - (t_ & 3)) << 1))
+
+    @njit(parallel=True, cache=True)
+    def pack_seq2(bo, lq, seq4, first, out, exc_slot, exc_code):
+        for i in prange(lq.shape[0]):
+            d = bo[i]
+            k = first[i]
+            for j in range(lq[i]):
+                t_ = d + j
+                code = (seq4[t_ >> 1] >> ((~t_ & 1) << 2)) & 15
+                two = 255
+                if code == 1:
+                    two = 0
+                elif code == 2:
+                    two = 1
+                elif code == 4:
+                    two = 2
+                elif code == 8:
+                    two = 3
+                if two == 255:
+                    exc_slot[k] = t_; exc_code[k] = code; k += 1
+                else:
+                    out[t_ >> 2] |= np.uint8(two << ((3 - (t_ & 3)) << 1))
+
+    _JIT = {"repack": repack, "survey": survey, "pack_qual2": pack_qual2, "pack_seq2": pack_seq2}
+    return _JIT
