@@ -625,7 +625,7 @@ constexpr int SEED_BOUND0 = 128;       // first round, pass one (every seed)
 constexpr bool MID_EVAL = true;      // evaluate the seeds that ran past the first bound once more at SEED_BOUND before calling them open (off: straight to the run heads + second round)
 constexpr int SEED_BOUND = 1024;       // first round, every seed: closes everything but genuine events and long uncovered stretches (chance dips of the coverage end within a few hundred positions); what runs past it is "open"
 
-template <bool BOUNDED, bool DUP> __host__ __device__ inline Outcome eval_seed_k(const SegCtx &C, const int64_t pos, int mi)
+template <bool BOUNDED, bool DUP, bool HASZ> __host__ __device__ inline Outcome eval_seed_k(const SegCtx &C, const int64_t pos, int mi)
 {
 #define CNV_STEP(var, p) do { const int c_ = C.cls(p); if (c_ != 2) var = c_; } while (0)
     const int64_t Lmin = C.Lmin, Lmax = C.Lmax, end = C.end, max_gap = Lmax + 500;
@@ -635,11 +635,29 @@ template <bool BOUNDED, bool DUP> __host__ __device__ inline Outcome eval_seed_k
     int64_t pa, c_start = 0, c_end = 0, last_good = 0;
     double tot = 0, c_z = 0, tz;
     const uint32_t *rp = C.rec + pos;                        // the first two phases index relative to the seed (32-bit offsets)
-    const double *zp = C.zarr ? C.zarr + pos : nullptr;
+    const double *zp = HASZ ? C.zarr + pos : nullptr;         // HASZ: z unpacked per position (device); otherwise derived from the record (host)
     const uint32_t m0 = DUP ? R_DUP0 : R_DEL0, m1 = DUP ? R_DUP1 : R_DEL1;
     // z as the scan sees it: 0.0 - v for duplications (exact, and keeps a zero positive like the reference's literal 0.0)
-    auto zrel = [&](int i, uint32_t r) { const double v = zp ? zp[i] : C.z_del_of(r); return DUP ? 0.0 - v : v; };
+    auto zrel = [&](int i, uint32_t r) { const double v = HASZ ? zp[i] : C.z_del_of(r); return DUP ? 0.0 - v : v; };
     const int iLmin = (int)Lmin, iLmax = (int)Lmax;
+    cnt = iLmin;
+    if (HASZ) {
+        // one pass: the give-up test of the first window, and on the side the window's sum and mask count (the reference walks twice;
+        // the sum adds the same values in the same order, and is simply dropped when the walk gives up)
+        int w2 = 0;
+        for (int i = 0; i < iLmin; i++) {
+            const uint32_t r = rp[i];
+            const bool um = !(r & R_MASK);
+            const int c_ = (int)(r >> R_CLASS) & 3;
+            mi = (um && c_ != 2) ? c_ : mi;
+            tot += zrel(i, r);
+            cnt -= (int)(r & R_MASK);
+            const bool ok = um && (r & (mi ? m1 : m0)) != 0;
+            w2 += ok ? 1 : -1;
+            if (!ok && w2 < 0) { o.next = pos + i + 1; return o; }          // give up inside the first window: resume after the offender
+        }
+        cnt2 = (w2 + iLmin) / 2; wlen = iLmin;
+    } else {
     for (int i = 0; i < iLmin; i++) {
         wlen++;
         bool ok = false;
@@ -648,8 +666,8 @@ template <bool BOUNDED, bool DUP> __host__ __device__ inline Outcome eval_seed_k
         if (ok) cnt2++;
         else if (2 * cnt2 < wlen) { o.next = pos + i + 1; return o; }       // give up inside the first window: resume after the offender
     }
-    cnt = iLmin;
     for (int i = 0; i < iLmin; i++) { const uint32_t r = rp[i]; cnt -= (int)(r & R_MASK); tot += zrel(i, r); }
+    }
     if (cnt > 0 && C.scores(tot, cnt, iLmin, &tz)) {
         begun = true; c_start = pos; last_good = c_end = pos + Lmin; c_z = tz;
     }
@@ -662,6 +680,39 @@ template <bool BOUNDED, bool DUP> __host__ __device__ inline Outcome eval_seed_k
         const double *thr = C.win_thr;
         double dcnt = (double)cnt;                                                   // cnt as a double, kept in step (exact: small integers)
         int i = iLmin;
+        if (HASZ) {
+            // device form (z unpacked per position): the same steps with selects instead of nested branches -- a masked position adds an
+            // exact zero (z is 0 where the mask is set, and x + (+-0) == x), leaves class and counters alone and is never "ok"; the two
+            // rare events (a window that may score, giving up) stay branches
+            int w2 = 2 * cnt2 - i;                                                   // 2 * cnt2 - wlen; every step adds +-1
+            // one step; `ii` is the offset of the position, `r` / `zv` its record and z
+#define CNV_GROW_STEP(ii, r, zv)                                                                                          \
+            {                                                                                                            \
+                const bool um = !((r) & R_MASK);                                                                         \
+                const int c_ = (int)((r) >> R_CLASS) & 3;                                                                \
+                mi = (um && c_ != 2) ? c_ : mi;                                                                          \
+                tot += DUP ? 0.0 - (zv) : (zv);                                                                          \
+                dcnt += um ? 1.0 : 0.0;                                                                                  \
+                const bool ok = um && ((r) & (mi ? m1 : m0)) != 0;                                                       \
+                w2 += ok ? 1 : -1;                                                                                       \
+                if (ok) {                                                                                                \
+                    if (tot >= dcnt * thr[(ii) + 1]) {                       /* SegCtx::scores, its cheap side inline */ \
+                        tz = tot / (dcnt * C.win_sd[(ii) + 1]);                                                          \
+                        if (tz >= 3) { good = (ii); if (tz > c_z) c_z = tz; }                                            \
+                    }                                                                                                    \
+                } else if (w2 < 0) { stop = true; i = (ii); break; }                                                     \
+            }
+            // four positions per trip: their records and z values are fetched together (the walk is a dependent chain per seed; the
+            // loads are not), then folded in order
+            for (; i + 4 <= i_lim; i += 4) {
+                const uint32_t r0 = rp[i], r1 = rp[i + 1], r2 = rp[i + 2], r3 = rp[i + 3];
+                const double z0 = zp[i], z1 = zp[i + 1], z2 = zp[i + 2], z3 = zp[i + 3];
+                CNV_GROW_STEP(i, r0, z0) CNV_GROW_STEP(i + 1, r1, z1) CNV_GROW_STEP(i + 2, r2, z2) CNV_GROW_STEP(i + 3, r3, z3)
+            }
+            if (!stop) for (; i < i_lim; i++) { const uint32_t r0 = rp[i]; const double z0 = zp[i]; CNV_GROW_STEP(i, r0, z0) }
+#undef CNV_GROW_STEP
+            cnt = (int)dcnt;
+        } else
         for (; i < i_lim; i++) {
             const uint32_t r = rp[i];
             bool ok = false;
@@ -741,7 +792,11 @@ template <bool BOUNDED, bool DUP> __host__ __device__ inline Outcome eval_seed_k
 }
 template <bool BOUNDED> __host__ __device__ inline Outcome eval_seed(const SegCtx &C, const int64_t pos, int mi)
 {
-    return C.dup ? eval_seed_k<BOUNDED, true>(C, pos, mi) : eval_seed_k<BOUNDED, false>(C, pos, mi);
+#ifdef __CUDA_ARCH__
+    return C.dup ? eval_seed_k<BOUNDED, true, true>(C, pos, mi) : eval_seed_k<BOUNDED, false, true>(C, pos, mi);       // device contexts always carry zarr (k_zfill)
+#else
+    return C.dup ? eval_seed_k<BOUNDED, true, false>(C, pos, mi) : eval_seed_k<BOUNDED, false, false>(C, pos, mi);     // host contexts never do
+#endif
 }
 
 // land[2*rank + class] (uint32): 0xFFFFFFFF not a seed under that class; top bits SEG_*; RESUME: low bits = distance to the next

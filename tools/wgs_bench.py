@@ -124,11 +124,11 @@ def main_wgs(a, emit) -> int:
         def lane(k):
             torch.cuda.set_device(dev)
             try:
-                while not errors:
-                    with pick:
-                        if not work:
-                            break
-                        t = work.pop(0)
+                # lane k takes contigs k, k + n_lanes, ... of the largest-first list: its first one is the largest it ever sees, in every
+                # pass, so its handle never has to grow after the first pass (a dynamic queue would hand lanes different contigs each pass)
+                for t in work[k::n_lanes]:
+                    if errors:
+                        break
                     chars, pb, n_reads, n_slots, btid = items[t]
                     # one handle per lane, begun for the largest contig the lane sees and rebound for the others (the product drivers'
                     # flow: grom_b200/pipeline.py, tools/grom_b200.c); it stays alive across passes like it does across contigs
