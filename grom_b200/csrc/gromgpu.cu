@@ -25,6 +25,7 @@
 #include <string>
 #include <chrono>
 #include <thread>
+#include <sched.h>
 #include "gromgpu.h"
 
 #define F_PAIRED 1
@@ -1916,6 +1917,20 @@ extern "C" int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0
 
 
 // ================================================================================================ read-depth CNV path (cnv.cuh)
+// Host threads one call of gromgpu_chr_cnv may use for its host stages: the cores this process may run on (its affinity mask), shared
+// by the processes of the node and the contigs in flight in each of them when the caller says how many there are
+// (GROMGPU_HOST_THREADS = threads per call; set by the genome drivers and bench.py), never more than `most`.
+static unsigned cnv_host_threads(unsigned most)
+{
+    static const unsigned avail = []() -> unsigned {
+        if (const char *e = getenv("GROMGPU_HOST_THREADS")) { const long v = atol(e); if (v > 0) return (unsigned)v; }
+        cpu_set_t set; CPU_ZERO(&set);
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) { const int n = CPU_COUNT(&set); if (n > 0) return (unsigned)n; }
+        const unsigned h = std::thread::hardware_concurrency();
+        return h ? h : 1u;
+    }();
+    return std::max(1u, std::min(most, avail));
+}
 struct CnvState {
     int32_t *d_depth = nullptr; uint8_t *d_mq8 = nullptr; uint32_t *d_rec = nullptr, *d_seed = nullptr;   // d_seed: [2][words]
     double *d_z = nullptr;                                             // z of the deletion scan per position (k_zfill)
@@ -2267,7 +2282,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     };
     // the per-list work below is independent per list: a few host threads share it
     auto par_lists = [&](auto &&fn) {
-        const int T = (int)std::max<unsigned>(1, std::min<unsigned>(8, std::thread::hardware_concurrency()));
+        const int T = (int)cnv_host_threads(8);
         std::vector<std::thread> pool;
         for (int t = 1; t < T; t++) pool.emplace_back([&, t]() { for (int l = t; l < NLIST; l += T) fn(l); });
         for (int l = 0; l < NLIST; l += T) fn(l);
@@ -2585,7 +2600,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                     }
                 };
                 {
-                    const unsigned T = std::max(1u, std::min<unsigned>(std::min<unsigned>(16, std::thread::hardware_concurrency()), n_cl));
+                    const unsigned T = std::max(1u, std::min<unsigned>(cnv_host_threads(16), n_cl));
                     std::vector<std::thread> pool;
                     for (unsigned t = 1; t < T; t++) pool.emplace_back(cluster_worker);
                     cluster_worker();
@@ -2742,7 +2757,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 sg[k].C = ctx[k]; sg[k].C.zarr = nullptr; sg[k].C.rec = c.h_rec; sg[k].C.sd = c.sd_tbl.data(); sg[k].C.win_sd = c.win_sd.data(); sg[k].C.win_thr = c.win_thr.data(); sg[k].C.wtab = c.wtab.data(); sg[k].seeds = c.h_seed + k * words; sg[k].lo = lo;
                 if (have_land) { sg[k].wp = c.h_wp + k * words; sg[k].land = c.h_land + (size_t)k * 2 * c.land_cap; sg[k].spec = c.h_spec; }
             }
-            const int hw = (int)std::thread::hardware_concurrency(), per_scan = std::max(1, std::min(8, hw / 2));
+            const int hw = (int)cnv_host_threads(16), per_scan = std::max(1, std::min(8, hw / 2));
             std::thread th([&]() { sg[1].run(found[1], per_scan); });
             sg[0].run(found[0], per_scan);
             th.join();
@@ -2797,7 +2812,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 c.calls[si] = o;
             }
         };
-        const size_t nc = flat.size(), T = std::max<size_t>(1, std::min<size_t>(16, std::min<size_t>(std::thread::hardware_concurrency(), nc / 64 + 1)));
+        const size_t nc = flat.size(), T = std::max<size_t>(1, std::min<size_t>(cnv_host_threads(16), nc / 64 + 1));
         std::vector<std::thread> pool;
         for (size_t t = 1; t < T; t++) pool.emplace_back(work, nc * t / T, nc * (t + 1) / T);
         work(0, nc / T);

@@ -137,7 +137,10 @@ int gromgpu_fetch_read_state(gromgpu_chr *h, uint8_t *dst, int64_t i0, int64_t i
  *                  pval2sd_len, &del_index, del lists ..., &dup_index, dup lists ..., ploidy, repeat lists ..., file, chr_name)
  * at src/GROM.c:17133 plus the p-values of 17163-17190.  Call after gromgpu_chr_run (it consumes the CNV depth arrays of that
  * run, which stay untouched).  pval2sd_* are the caller's tables exactly as the reference passes them (gromhost_pval2sd()).
- * ploidy is the reference's caf_ploidy. */
+ * ploidy is the reference's caf_ploidy.
+ * Host stages of the call (sample lists, run heads of the segmentation, copy numbers) use GROMGPU_HOST_THREADS threads when that
+ * environment variable is set (the genome drivers set it to cores / (processes on the node x contigs in flight)), otherwise as many
+ * as the process's affinity mask allows (at most 16). */
 typedef struct gromgpu_cnv_result {
     int64_t n_calls;                    /* deletions in position order, then duplications */
     const grom_cnv_call *calls;         /* host memory owned by the handle; filter with -V and print via gromhost_vcf_cnv() */

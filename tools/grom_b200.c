@@ -447,6 +447,7 @@ static int run_worker(options *o, const char *argv0)
     int lanes = o->lanes < w.n_work ? o->lanes : w.n_work;
     if (lanes < 1) lanes = 1;
     if (o->threads <= 0) { long nc = sysconf(_SC_NPROCESSORS_ONLN); int per = (int)(nc / ((long)world * lanes)); ((options *)o)->threads = per > 1 ? per : 1; }
+    { char tv[32]; snprintf(tv, sizeof(tv), "%d", o->threads > 2 ? o->threads : 2); setenv("GROMGPU_HOST_THREADS", tv, 0); }   /* host stages of gromgpu_chr_cnv: same share of the cores */
     const double t0 = now_s();
     pthread_t th[64];
     if (lanes > 64) lanes = 64;
