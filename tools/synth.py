@@ -566,13 +566,19 @@ _AT_RUNS: Dict[str, Tuple[np.ndarray, np.ndarray]] = {}
 _CTX_PLANTS: Dict[int, list] = {}
 
 
-def simulate(spec: SynthSpec) -> List[SynthContig]:
+def simulate(spec: SynthSpec, references: Optional[Dict[str, np.ndarray]] = None) -> List[SynthContig]:
+    """`references` = {contig name: uint8 characters}: reads are simulated on these sequences (case and N runs as they are) instead of
+    a random one -- e.g. the reference's own tilapia FASTA."""
     rng = np.random.default_rng(spec.seed)
     _CTX_PLANTS.pop(spec.seed, None)
     lens = [l for _, l in spec.contigs]
     out = []
     for tid, (name, length) in enumerate(spec.contigs):
-        chars = make_reference(length, rng, spec.n_frac, spec.lower_frac)
+        if references is not None and name in references:
+            chars = np.ascontiguousarray(references[name], dtype=np.uint8).copy()
+            assert len(chars) == length, f"{name}: {len(chars)} characters given, {length} in the spec"
+        else:
+            chars = make_reference(length, rng, spec.n_frac, spec.lower_frac)
         if spec.at_repeats and length > 20_000:
             a = np.sort(rng.integers(5_000, length - 5_000, spec.at_repeats))
             a = a[np.concatenate([[True], np.diff(a) > 700])]
