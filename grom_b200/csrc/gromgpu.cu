@@ -2777,9 +2777,17 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         std::vector<const Call *> flat; std::vector<int> flat_kind;
         for (int k = 0; k < 2; k++) for (const Call &cl : found[k]) { flat.push_back(&cl); flat_kind.push_back(k); }
         c.calls.assign(flat.size(), grom_cnv_call());
-        auto work = [&](size_t i0, size_t i1) {
+        // calls are handed out longest first (their cost is n log n in the call's length and a few calls hold most positions)
+        std::vector<uint32_t> by_len(flat.size());
+        for (size_t i = 0; i < by_len.size(); i++) by_len[i] = (uint32_t)i;
+        std::sort(by_len.begin(), by_len.end(), [&](uint32_t a, uint32_t b) { const int64_t la = seg_first[a + 1] - seg_first[a], lb = seg_first[b + 1] - seg_first[b]; return la != lb ? la > lb : a < b; });
+        std::atomic<size_t> next_call(0);
+        auto work = [&]() {
             std::vector<double> buf, tmp;
-            for (size_t si = i0; si < i1; si++) {
+            for (;;) {
+                const size_t oi = next_call.fetch_add(1);
+                if (oi >= by_len.size()) break;
+                const size_t si = by_len[oi];
                 const Call &cl = *flat[si];
                 grom_cnv_call o; o.start = cl.start; o.end = cl.end; o.kind = flat_kind[si]; o.reserved = 0; o.z = cl.z; o.cn = -1; o.cn_sd = 0;
                 buf.clear();
@@ -2814,8 +2822,8 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         };
         const size_t nc = flat.size(), T = std::max<size_t>(1, std::min<size_t>(cnv_host_threads(16), nc / 64 + 1));
         std::vector<std::thread> pool;
-        for (size_t t = 1; t < T; t++) pool.emplace_back(work, nc * t / T, nc * (t + 1) / T);
-        work(0, nc / T);
+        for (size_t t = 1; t < T; t++) pool.emplace_back(work);
+        work();
         for (auto &x : pool) x.join();
     }
     mark("copy number");
