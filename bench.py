@@ -266,9 +266,10 @@ def main_b200(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
-    # host threads per gromgpu_chr_cnv call: the node's cores shared by the ranks of the node and the contigs each keeps in flight
+    # host threads per gromgpu_chr_cnv call: the node's cores shared by the ranks of the node (the contigs in flight of one rank are rarely in
+    # their host stages at the same time)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("GROMGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // max(1, local_world * max(1, a.lanes)))))
+    os.environ.setdefault("GROMGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // max(1, local_world))))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

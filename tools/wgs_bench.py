@@ -78,7 +78,7 @@ def main_wgs(a, emit) -> int:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("GROMGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // max(1, local_world * max(1, a.lanes)))))
+    os.environ.setdefault("GROMGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // max(1, local_world))))
     ndev = torch.cuda.device_count()
     dev = local % ndev                                              # (tests run two ranks on one GPU)
     torch.cuda.set_device(dev)
