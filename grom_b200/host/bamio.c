@@ -54,6 +54,7 @@ static int bgzf_inflate_at(FILE *f, int64_t off, uint8_t *raw, uint8_t *dst, int
     if (xlen != 6 || hdr[12] != 'B' || hdr[13] != 'C') return -1;
     int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
     int clen = bsize - 18;
+    if (bsize < 26) return -1;                         /* header + empty deflate stream + CRC32 + ISIZE */
     if ((int)fread(raw, 1, clen, f) != clen) return -1;
     uint32_t isize = rd_u32(raw + clen - 4);
     z_stream s; memset(&s, 0, sizeof(s));
@@ -465,6 +466,13 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         if (rtid == tid) {
             if (!started) { started = 1; p0 = p; }
             uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16); int32_t lq = rd_i32(u + p + 20);
+            /* the fixed part, name, CIGAR, packed bases and qualities must fit the record (a truncated or corrupt file must not make the
+             * fill pass below read past the inflated data) */
+            if (lq < 0 || 32 + (int64_t)(bmq & 0xff) + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl) {
+                free(blk); free(u); free(t);
+                return fail("%s: corrupt BAM record at uncompressed offset %lld (block_size %d cannot hold name %u + %u CIGAR ops + %d bases)",
+                            b->path, (long long)p, bl, bmq & 0xff, fnc & 0xffff, lq);
+            }
             n_reads++; n_cig += fnc & 0xffff; n_slots += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN;
             n_name += bmq & 0xff;
         } else if (started || rtid > tid || rtid < 0) {

@@ -1,6 +1,8 @@
 """Host batcher: BAM/BAI writer -> reader round trip, SA parsing rules, C-ABI surface of libgromhost."""
 import os
 
+import pytest
+
 import numpy as np
 
 from util import GOLDEN, golden_batches
@@ -74,3 +76,26 @@ def test_empty_target(tmp_path):
     with hostlib.Bam(str(tmp_path / "e.bam")) as b:
         assert b.read_target(1).n_reads == 0
         assert b.read_target(0).n_reads == cs[0].batch.n_reads
+
+
+def test_corrupt_record_is_rejected(tmp_path):
+    """A record whose block_size cannot hold its own name + CIGAR + bases (truncated / corrupt file) fails with a message instead of
+    letting the fill pass read past the inflated data."""
+    import struct
+    import zlib
+    from grom_b200 import hostlib
+
+    def bgzf(data):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        d = c.compress(data) + c.flush()
+        hdr = b"\x1f\x8b\x08\x04" + b"\0" * 6 + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(d) + 25)
+        return hdr + d + struct.pack("<II", zlib.crc32(data), len(data))
+    text = b"@SQ\tSN:c\tLN:1000\n"
+    head = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", 1) + struct.pack("<i", 2) + b"c\0" + struct.pack("<i", 1000)
+    # one record: block_size 40, but l_seq = 100 bases claimed
+    rec = struct.pack("<iiiIIiiii", 40, 0, 10, (4680 << 16) | (60 << 8) | 2, (0 << 16) | 0, 100, -1, -1, 0) + b"r\0" + b"\0" * 6
+    p = tmp_path / "bad.bam"
+    p.write_bytes(bgzf(head) + bgzf(rec) + bgzf(b""))
+    with hostlib.Bam(str(p)) as b:
+        with pytest.raises(Exception, match="corrupt BAM record"):
+            b.read_target(0)
