@@ -128,15 +128,29 @@ __device__ __forceinline__ int dinuc_type(char c0, char c1)
 __global__ void __launch_bounds__(256) k_repeats(const char *__restrict__ fasta, const int32_t *__restrict__ depth, int64_t lo, int64_t hi,
                                                  RepRec *__restrict__ out, unsigned int cap, unsigned int *__restrict__ n_out)
 {
-    const int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // pair types of the CTA's positions (one evaluation per position) plus one before and a few behind: ty[i] = type of the pair at base - 1 + i
+    constexpr int AHEAD = 30;
+    __shared__ uint8_t ty[256 + 1 + AHEAD];
+    const int64_t base = lo + (int64_t)blockIdx.x * blockDim.x;
+    for (int i = threadIdx.x; i < 256 + 1 + AHEAD; i += blockDim.x) {
+        const int64_t q = base - 1 + i;
+        ty[i] = (q >= lo && q < hi) ? (uint8_t)dinuc_type(fasta[q], fasta[q + 1]) : (uint8_t)(q < lo ? 11 : 12);      // 11 / 12: outside the span, equal to nothing
+    }
+    __syncthreads();
+    const int64_t p = base + threadIdx.x;
     if (p >= hi) return;
-    const int t = dinuc_type(fasta[p], fasta[p + 1]);
+    const int t = ty[threadIdx.x + 1];
     if (t == 10) return;
-    if (p > lo && dinuc_type(fasta[p - 1], fasta[p]) == t) return;          // not the first pair of its run
+    if (ty[threadIdx.x] == t) return;                                        // not the first pair of its run
     int64_t e = p;
     long long sum = depth[p];
-    while (e + 1 < hi && dinuc_type(fasta[e + 1], fasta[e + 2]) == t) { e++; sum += depth[e]; }
-    if (e + 1 >= hi) return;                                                 // a run still open at the end of the span is never flushed
+    for (;;) {                                                               // the thread at a run start walks the run
+        if (e + 1 >= hi) return;                                             // a run still open at the end of the span is never flushed
+        const int64_t i = e + 1 - (base - 1);
+        const int tn = i < 256 + 1 + AHEAD ? (int)ty[i] : dinuc_type(fasta[e + 1], fasta[e + 2]);
+        if (tn != t) break;
+        e++; sum += depth[e];
+    }
     if (e - p < 19) return;
     const unsigned int k = atomicAdd(n_out, 1u);             // [s, e + 1) is the reference's half-open run
     if (k < cap) { RepRec r; r.s = (int32_t)p; r.e = (int32_t)(e + 1); r.type = t; r.pad = 0; r.depth_sum = sum; out[k] = r; }

@@ -2491,7 +2491,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             if (most) {
                 Grow &t_mid = c.mid;
                 if (!t_mid.ensure(sizeof(SeedTodo) * (size_t)todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
-                ctx[0].bound = ctx[1].bound = SEED_BOUND0;
+                ctx[0].bound = ctx[1].bound = std::min(SEED_BOUND0, Lmin + 4);          // just past the first window: what survives it is classified, not walked further
                 k_seed_eval<<<dim3((unsigned)((words + SEED_CTA_WORDS - 1) / SEED_CTA_WORDS), 2), 256, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap,
                                                                                                                    c.d_nspec, t_mid.as<SeedTodo>(), todo_cap, J, c.d_u1); n_launch++;
                 ctx[0].bound = ctx[1].bound = SEED_BOUND;
