@@ -2486,8 +2486,12 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             k_seed_blocksum<<<dim3((unsigned)c.nb, 1), 256, 0, s>>>(d_nz, words, c.d_blk + 2 * c.nb, c.nb); n_launch++;
             k_seed_blockscan<<<1, 1024, 0, s>>>(c.d_blk + 2 * c.nb, c.nb, c.d_blk + 3 * c.nb + 2); n_launch++;
             k_seed_rank<<<dim3((unsigned)c.nb, 1), 256, 0, s>>>(d_nz, words, c.d_blk + 2 * c.nb, c.nb, d_nzwp); n_launch++;
-            k_tail_ends<<<(unsigned)((words + 255) / 256), 256, 0, s>>>(d_nz, words, c.d_ends, CnvState::ENDS_CAP, c.d_nspec + 12); n_launch++;
-            k_tail_check<<<148 * 8, 128, 0, s>>>(c.d_rec, c.d_z, P, c.d_ends, c.d_nspec + 12, CnvState::ENDS_CAP, Lmax, c.d_winsd + 2 * (Lmax + 1), c.d_u1 + 2 * words, words); n_launch++;
+            // the stretch-end check is a handful of warps walking 10,000 positions each (latency, not work): on a side stream, beside pass one
+            CK(cudaEventRecord(c.ev_z, s));
+            CK(cudaStreamWaitEvent(c.copy_stream, c.ev_z, 0));
+            k_tail_ends<<<(unsigned)((words + 255) / 256), 256, 0, c.copy_stream>>>(d_nz, words, c.d_ends, CnvState::ENDS_CAP, c.d_nspec + 12); n_launch++;
+            k_tail_check<<<148 * 8, 128, 0, c.copy_stream>>>(c.d_rec, c.d_z, P, c.d_ends, c.d_nspec + 12, CnvState::ENDS_CAP, Lmax, c.d_winsd + 2 * (Lmax + 1), c.d_u1 + 2 * words, words); n_launch++;
+            CK(cudaEventRecord(c.ev_copied, c.copy_stream));
             if (most) {
                 Grow &t_mid = c.mid;
                 if (!t_mid.ensure(sizeof(SeedTodo) * (size_t)todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
@@ -2497,6 +2501,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 ctx[0].bound = ctx[1].bound = SEED_BOUND;
                 Grow &t_wl = c.walk;
                 if (!t_wl.ensure(sizeof(SeedTodo) * (size_t)todo_cap)) return fail("gromgpu_chr_cnv: out of device memory");
+                CK(cudaStreamWaitEvent(s, c.ev_copied, 0));                       // safe stretch ends are in place
                 k_seed_eval_mid<0><<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
                                                            t_mid.as<SeedTodo>(), todo_cap, t_todo.as<SeedTodo>(), todo_cap, J, c.d_open, d_nz, d_nzwp, c.d_u1, c.d_u1 + 2 * words, c.d_u1 + 4 * words, t_wl.as<SeedTodo>()); n_launch++;
                 k_seed_eval_mid<2><<<148 * 8, 128, 0, s>>>(ctx[0], ctx[1], c.d_seed, words, c.d_wp, c.d_land, c.land_cap, seed_tot[0], seed_tot[1], c.d_spec, c.spec_cap, c.d_nspec,
@@ -2514,6 +2519,7 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
             unsigned int *n_heads_d = c.d_nspec + 6;
             uint32_t *d_cover = c.d_open + 4 * words;                    // [2 kinds][words]
             CK(cudaMemsetAsync(d_cover, 0, sizeof(uint32_t) * 2 * (size_t)words, s));
+            CK(cudaStreamWaitEvent(s, c.ev_copied, 0));                           // (also when there were no seeds at all)
             k_open_heads<<<592, 256, 0, s>>>(t_todo.as<SeedTodo>(), c.d_nspec + 1, todo_cap, c.d_open, words, c.heads.as<SeedHead>(), HEAD_CAP, n_heads_d); n_launch++;
             ctx[0].bound = ctx[1].bound = Lmax;                     // second round: the whole growth phase
             unsigned int *h_cnt = (unsigned int *)((char *)c.h_heads + sizeof(SeedHead) * (size_t)HEAD_CAP);       // [0] open seeds [1] heads
