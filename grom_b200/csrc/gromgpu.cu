@@ -23,6 +23,8 @@
 #include <limits>
 #include <vector>
 #include <string>
+#include <map>
+#include <tuple>
 #include <chrono>
 #include <thread>
 #include <sched.h>
@@ -1947,7 +1949,8 @@ struct CnvState {
     int64_t P = 0, words = 0;
     int q = 0;
     std::vector<double> sd_tbl, wtab;
-    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, heads, head_out, mid, walk;
+    cnv::Grow tmp[16], jump, flags, hop_out, hop_sink, gather_rec, heads, head_out, mid, walk, spec_g[5];
+    void *h_specg = nullptr; size_t h_specg_cap = 0; cudaEvent_t ev_spec = nullptr;       // early gather of the calls made at run heads (their copy numbers are computed beside the device work)
     uint32_t *d_open = nullptr;                              // [2 kinds][2 classes][words]: seeds still open after the first round
     cnv::SeedHead *h_heads = nullptr; cnv::HeadOutcome *h_head_out = nullptr;      // pinned
     uint32_t *h_win = nullptr; size_t h_win_cap = 0;         // pinned landing area of the record windows of the run heads
@@ -1961,7 +1964,9 @@ static void cnv_state_free(CnvState *c)
     cudaFree(c->d_depth); cudaFree(c->d_mq8); cudaFree(c->d_rec); cudaFree(c->d_z); cudaFree(c->d_seed); cudaFree(c->d_pre); cudaFree(c->d_hist);
     cudaFree(c->d_rep); cudaFree(c->d_nrep); cudaFree(c->d_tile);
     for (auto &g : c->tmp) if (g.p) cudaFree(g.p);
-    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->heads, &c->head_out, &c->mid, &c->walk}) if (g->p) cudaFree(g->p);
+    for (cnv::Grow *g : {&c->jump, &c->flags, &c->hop_out, &c->hop_sink, &c->gather_rec, &c->heads, &c->head_out, &c->mid, &c->walk, &c->spec_g[0], &c->spec_g[1], &c->spec_g[2], &c->spec_g[3], &c->spec_g[4]}) if (g->p) cudaFree(g->p);
+    if (c->h_specg) cudaFreeHost(c->h_specg);
+    if (c->ev_spec) cudaEventDestroy(c->ev_spec);
     cudaFree(c->d_open);
     if (c->h_heads) cudaFreeHost(c->h_heads);
     if (c->h_head_out) cudaFreeHost(c->h_head_out);
@@ -2443,6 +2448,39 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
     // ---- stage 4: greedy segmentation (two host threads: deletions, duplications) and copy number
     std::vector<Call> found[2];
     int64_t seed_tot_all = 0, n_spec_all = 0;
+    // copy number of one call from its gathered positions (src/GROM.c:20071-20153): ratios depth / bin mean over the unmasked positions,
+    // the reference's qsort (merge tree, low-word comparator), 10 %-trimmed mean times the ploidy, sd around it over all ratios
+    auto copy_number = [&](const int32_t *g_depth_, const uint32_t *g_rec_, const uint8_t *g_gc_, int64_t n_pos, std::vector<double> &buf, std::vector<double> &tmp, double *cn, double *cn_sd) {
+        *cn = -1; *cn_sd = 0;
+        buf.clear();
+        for (int64_t j = 0; j < n_pos; j++) {
+            const uint32_t r = g_rec_[j];
+            if (r & R_MASK) continue;
+            const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (g_gc_[j] & 0x7f);
+            if (ave[l] > 0) buf.push_back((double)g_depth_[j] / ave[l]);
+        }
+        const long n = (long)buf.size();
+        if (n <= 0) return;
+        tmp.resize(n);
+        lowword_msort_par(buf.data(), n, tmp.data(), n >= 65536 ? 3 : (n >= 16384 ? 2 : 0));
+        const long a = (long)(0.1 * n), b = n - a;
+        double tot = 0;
+        for (long j = a; j < b; j++) tot += buf[j];
+        if (b - a > 0) {
+            *cn = (tot / (b - a)) * ploidy;
+            double v = 0;
+            for (long j = 0; j < n; j++) { const double dd = ploidy * buf[j] - *cn; v += dd * dd; }
+            *cn_sd = sqrt(v / n);
+        }
+    };
+    // The calls made at run heads are the long ones and are known long before the path is: their positions are gathered right away and
+    // their copy numbers computed by a background thread while the device runs the second round and the hop; the final pass below
+    // takes them from here (a call that turns out not to be on the path is simply not used).
+    struct SpecCN {
+        std::thread th;
+        std::vector<int64_t> start, end, first; std::vector<int> kind; std::vector<double> cn, cn_sd;
+        ~SpecCN() { if (th.joinable()) th.join(); }
+    } spec_cn;
     {
         SegCtx ctx[2];
         for (int k = 0; k < 2; k++) { ctx[k].rec = c.d_rec; ctx[k].len = P; ctx[k].end = hi - Lmin; ctx[k].q = q; ctx[k].Lmin = Lmin; ctx[k].Lmax = Lmax; ctx[k].bound = SEED_BOUND; ctx[k].sd = T.p2s_sd; ctx[k].win_sd = c.d_winsd; ctx[k].win_thr = c.d_winsd + (Lmax + 1); ctx[k].zarr = c.d_z; ctx[k].dup = k == 1; ctx[k].wtab = T.p2s_sd + P2S; }
@@ -2618,6 +2656,64 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                     CK(cudaMemcpyAsync(c.head_out.p, ho, sizeof(HeadOutcome) * (size_t)n_head_done, cudaMemcpyHostToDevice, s));
                     k_apply_heads<<<(n_head_done * 32 + 127) / 128, 128, 0, s>>>(ctx[0], ctx[1], c.head_out.as<HeadOutcome>(), n_head_done, c.d_seed, words, c.d_wp, c.d_land, c.land_cap, c.d_spec, c.spec_cap,
                                                                                  c.d_nspec, seed_tot[0], seed_tot[1], J, d_cover); n_launch++;
+                    // early gather of the calls made here (at most 32 M positions), copy numbers beside the device work
+                    spec_cn.first.push_back(0);
+                    for (uint32_t i = 0; i < n_head_done; i++) if (ho[i].seg == SEG_CALL && ho[i].c_end > ho[i].pos) {
+                        spec_cn.kind.push_back(ho[i].kind); spec_cn.start.push_back(ho[i].pos); spec_cn.end.push_back(ho[i].c_end);
+                        spec_cn.first.push_back(spec_cn.first.back() + (ho[i].c_end - ho[i].pos));
+                    }
+                    const int n_sp = (int)spec_cn.start.size();
+                    const int64_t tot_sp = spec_cn.first.back();
+                    bool sp_ok = n_sp > 0 && tot_sp <= ((int64_t)32 << 20) && !getenv("GROMGPU_CNV_NO_EARLY_CN");
+                    if (sp_ok) {
+                        const size_t need = (size_t)tot_sp * 9 + 64;
+                        if (need > c.h_specg_cap) {
+                            if (c.h_specg) cudaFreeHost(c.h_specg);
+                            c.h_specg = nullptr; c.h_specg_cap = 0;
+                            if (cudaMallocHost(&c.h_specg, need + need / 4) == cudaSuccess) c.h_specg_cap = need + need / 4; else { cudaGetLastError(); sp_ok = false; }
+                        }
+                        if (!c.ev_spec && cudaEventCreateWithFlags(&c.ev_spec, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); sp_ok = false; }
+                        sp_ok = sp_ok && c.spec_g[0].ensure(sizeof(int64_t) * n_sp) && c.spec_g[1].ensure(sizeof(int64_t) * (n_sp + 1)) && c.spec_g[2].ensure(sizeof(int32_t) * (size_t)tot_sp) &&
+                                c.spec_g[3].ensure((size_t)tot_sp) && c.spec_g[4].ensure(sizeof(uint32_t) * (size_t)tot_sp);
+                    }
+                    if (sp_ok) {
+                        CK(cudaMemcpyAsync(c.spec_g[0].p, spec_cn.start.data(), sizeof(int64_t) * n_sp, cudaMemcpyHostToDevice, s));
+                        CK(cudaMemcpyAsync(c.spec_g[1].p, spec_cn.first.data(), sizeof(int64_t) * (n_sp + 1), cudaMemcpyHostToDevice, s));
+                        k_gather<<<(unsigned)((tot_sp + 255) / 256), 256, 0, s>>>(c.d_depth, A_gc, A_acgt, c.spec_g[0].as<int64_t>(), c.spec_g[1].as<int64_t>(), n_sp, tot_sp, c.spec_g[2].as<int32_t>(),
+                                                                                  c.spec_g[3].as<uint8_t>(), c.d_rec, c.spec_g[4].as<uint32_t>()); n_launch++;
+                        int32_t *pd = (int32_t *)c.h_specg; uint32_t *pr = (uint32_t *)(pd + tot_sp); uint8_t *pg = (uint8_t *)(pr + tot_sp);
+                        CK(cudaMemcpyAsync(pd, c.spec_g[2].p, sizeof(int32_t) * (size_t)tot_sp, cudaMemcpyDeviceToHost, s));
+                        CK(cudaMemcpyAsync(pr, c.spec_g[4].p, sizeof(uint32_t) * (size_t)tot_sp, cudaMemcpyDeviceToHost, s));
+                        CK(cudaMemcpyAsync(pg, c.spec_g[3].p, (size_t)tot_sp, cudaMemcpyDeviceToHost, s));
+                        CK(cudaEventRecord(c.ev_spec, s));
+                        d2h += 9 * tot_sp;
+                        spec_cn.cn.assign(n_sp, -1.0); spec_cn.cn_sd.assign(n_sp, 0.0);
+                        const int dev_id = g_device;
+                        cudaEvent_t ev = c.ev_spec;
+                        spec_cn.th = std::thread([&, pd, pr, pg, n_sp, dev_id, ev]() {
+                            cudaSetDevice(dev_id);
+                            if (cudaEventSynchronize(ev) != cudaSuccess) { for (int i = 0; i < n_sp; i++) spec_cn.cn_sd[i] = -1.0; return; }      // cn_sd < 0: not computed
+                            std::vector<uint32_t> order(n_sp);
+                            for (int i = 0; i < n_sp; i++) order[i] = (uint32_t)i;
+                            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return spec_cn.first[a + 1] - spec_cn.first[a] > spec_cn.first[b + 1] - spec_cn.first[b]; });
+                            std::atomic<int> next(0);
+                            auto w = [&]() {
+                                std::vector<double> buf, tmp;
+                                for (;;) {
+                                    const int oi = next.fetch_add(1);
+                                    if (oi >= n_sp) break;
+                                    const int i = (int)order[oi];
+                                    const int64_t f0 = spec_cn.first[i], np = spec_cn.first[i + 1] - f0;
+                                    copy_number(pd + f0, pr + f0, pg + f0, np, buf, tmp, &spec_cn.cn[i], &spec_cn.cn_sd[i]);
+                                }
+                            };
+                            const unsigned T = std::max(1u, std::min<unsigned>(cnv_host_threads(16) / 2, (unsigned)n_sp));
+                            std::vector<std::thread> pool;
+                            for (unsigned t = 1; t < T; t++) pool.emplace_back(w);
+                            w();
+                            for (auto &x : pool) x.join();
+                        });
+                    } else { spec_cn.start.clear(); spec_cn.end.clear(); spec_cn.kind.clear(); }
                 }
             }
             if (n_open) {
@@ -2788,6 +2884,10 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
         for (size_t i = 0; i < by_len.size(); i++) by_len[i] = (uint32_t)i;
         std::sort(by_len.begin(), by_len.end(), [&](uint32_t a, uint32_t b) { const int64_t la = seg_first[a + 1] - seg_first[a], lb = seg_first[b + 1] - seg_first[b]; return la != lb ? la > lb : a < b; });
         std::atomic<size_t> next_call(0);
+        // what the background thread has ready: (kind, start, end) -> index
+        if (spec_cn.th.joinable()) spec_cn.th.join();
+        std::map<std::tuple<int, int64_t, int64_t>, int> early;
+        for (size_t i = 0; i < spec_cn.cn.size(); i++) if (spec_cn.cn_sd[i] >= 0) early[std::make_tuple(spec_cn.kind[i], spec_cn.start[i], spec_cn.end[i])] = (int)i;
         auto work = [&]() {
             std::vector<double> buf, tmp;
             for (;;) {
@@ -2796,29 +2896,9 @@ extern "C" int gromgpu_chr_cnv(gromgpu_chr *h, const double *p2s_p, const double
                 const size_t si = by_len[oi];
                 const Call &cl = *flat[si];
                 grom_cnv_call o; o.start = cl.start; o.end = cl.end; o.kind = flat_kind[si]; o.reserved = 0; o.z = cl.z; o.cn = -1; o.cn_sd = 0;
-                buf.clear();
-                for (int64_t j = seg_first[si]; j < seg_first[si + 1]; j++) {
-                    const int64_t p = cl.start + (j - seg_first[si]);
-                    const uint32_t r = gp_rec[j];
-                    (void)p;
-                    if (r & R_MASK) continue;
-                    const int l = ((((r >> R_CLASS) & 3) == 0) ? 0 : NB) + (gp_gc[j] & 0x7f);
-                    if (ave[l] > 0) buf.push_back((double)gp_depth[j] / ave[l]);
-                }
-                const long n = (long)buf.size();
-                if (n > 0) {
-                    tmp.resize(n);
-                    lowword_msort_par(buf.data(), n, tmp.data(), n >= 65536 ? 3 : (n >= 16384 ? 2 : 0));
-                    const long a = (long)(0.1 * n), b = n - a;
-                    double tot = 0;
-                    for (long j = a; j < b; j++) tot += buf[j];
-                    if (b - a > 0) {
-                        o.cn = (tot / (b - a)) * ploidy;
-                        double v = 0;
-                        for (long j = 0; j < n; j++) { const double dd = ploidy * buf[j] - o.cn; v += dd * dd; }
-                        o.cn_sd = sqrt(v / n);
-                    }
-                }
+                const auto hit = early.find(std::make_tuple(flat_kind[si], (int64_t)cl.start, (int64_t)cl.end));
+                if (hit != early.end()) { o.cn = spec_cn.cn[hit->second]; o.cn_sd = spec_cn.cn_sd[hit->second]; }     // computed beside the device work
+                else copy_number(gp_depth + seg_first[si], gp_rec + seg_first[si], gp_gc + seg_first[si], seg_first[si + 1] - seg_first[si], buf, tmp, &o.cn, &o.cn_sd);
                 // one-sided normal tail through the reference's own erf variant, t = 1 / (1 + p + x) (src/GROM.c:17163-17172)
                 const double x = fabs(o.z) / sqrt(2.0), t = 1.0 / (1.0 + 0.3275911 + x);
                 const double erf_ = 1.0 - ((0.254829592 * t + -0.284496736 * (t * t) + 1.421413741 * pow(t, 3) + -1.453152027 * pow(t, 4) + 1.061405429 * pow(t, 5)) * exp(-(x * x)));
