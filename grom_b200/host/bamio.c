@@ -13,6 +13,7 @@
 #include <stdarg.h>
 #include <ctype.h>
 #include <zlib.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -403,6 +404,10 @@ static void parse_sa(const uint8_t *aux, int l_aux, const char *target_name,
 
 /* ------------------------------------------------------------------ read one target */
 
+/* GROMHOST_TRACE=1: phase times of gromhost_bam_read_target on stderr */
+static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+#define TRACE_MARK(what) do { if (trace) { double t_ = now_ms(); fprintf(stderr, "[bamio] %-22s %8.2f ms\n", what, t_ - t_last); t_last = t_; } } while (0)
+
 typedef struct { int64_t off; int bsize; int isize; int64_t uoff; } blkinfo;
 
 int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out)
@@ -415,6 +420,8 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     }
     grom_batch *t = (grom_batch *)calloc(1, sizeof(*t));
     t->v.tid = tid;
+    const int trace = getenv("GROMHOST_TRACE") != NULL;
+    double t_last = trace ? now_ms() : 0;
     /* 1. enumerate the compressed blocks in [vbeg, vend] */
     blkinfo *blk = NULL; int64_t nblk = 0, capblk = 0;
     if (vend != 0) {
@@ -434,6 +441,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     }
     int64_t utotal = 0;
     for (int64_t i = 0; i < nblk; i++) { blk[i].uoff = utotal; utotal += blk[i].isize; }
+    TRACE_MARK("enumerate blocks");
     uint8_t *u = (uint8_t *)malloc((size_t)utotal + 64);
     /* 2. inflate in parallel (each thread its own FILE*) */
     int bad = 0;
@@ -455,6 +463,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         free(raw); free(tmp); if (f) fclose(f);
     }
     if (bad) { free(blk); free(u); free(t); return fail("%s: BGZF inflate failed", b->path); }
+    TRACE_MARK("inflate");
     /* 3. first pass over records: count */
     int64_t p = (nblk > 0) ? (int64_t)(vbeg & 0xffff) : 0;
     int64_t n_reads = 0, n_cig = 0, n_slots = 0, n_name = 0, p0 = p;
@@ -480,6 +489,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         }
         p += 4 + bl;
     }
+    TRACE_MARK("count records");
     /* 4. allocate */
     size_t nr = (size_t)(n_reads > 0 ? n_reads : 1);
 #define AL(ptr, type, cnt) t->ptr = (type *)calloc((cnt), sizeof(type))
@@ -492,6 +502,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     AL(seq4, uint8_t, (size_t)(n_slots / 2 + 16)); AL(qual, uint8_t, (size_t)(n_slots + 16));
     if (keep_names) { AL(qname_off, uint64_t, nr + 1); AL(qname_pool, char, (size_t)(n_name + 1)); }
 #undef AL
+    TRACE_MARK("allocate");
     /* 5. offsets (sequential, cheap), then fill (parallel over reads) */
     int64_t *recoff = (int64_t *)malloc(sizeof(int64_t) * nr);
     {
@@ -507,6 +518,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         if (keep_names) t->qname_off[n_reads] = (uint64_t)nm;
     }
     const char *tname = b->names[tid];
+    TRACE_MARK("offsets");
     #pragma omp parallel for schedule(static) num_threads(n_threads)
     for (int64_t i = 0; i < n_reads; i++) {
         const uint8_t *r = u + recoff[i];
@@ -529,10 +541,13 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         parse_sa(aux, l_aux, tname, &t->sa_pos[i], &t->sa_strand[i], &t->sa_mapq[i], &t->sa_same_chr[i],
                  &t->sa_start_adj[i], &t->sa_end_adj[i], &t->sa_end_adj_indel[i]);
     }
+    TRACE_MARK("fill");
     free(recoff); free(u); free(blk);
     t->v.n_reads = n_reads; t->v.n_cigar_total = n_cig; t->v.n_base_slots = n_slots;
     batch_publish(t);
+    TRACE_MARK("free");
     batch_compact(t, n_threads);
+    TRACE_MARK("compact forms");
     *out = t;
     return 0;
 }
