@@ -14,10 +14,13 @@
 #include <ctype.h>
 #include <zlib.h>
 #include <time.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
 #include "gromhost.h"
+#include "inflate.h"
 
 static __thread char g_err[512];
 const char *gromhost_last_error(void) { return g_err; }
@@ -39,6 +42,9 @@ struct grom_bam {
     int has_index;
     uint64_t *tgt_beg;        /* per target: smallest chunk_beg in the .bai, UINT64_MAX if none */
     uint64_t *tgt_end;        /* per target: largest chunk_end */
+    const uint8_t *map;       /* the whole file, mapped read-only (or read into memory where mapping is refused) */
+    int64_t map_len;
+    int map_is_mmap;
 };
 
 static inline uint32_t rd_u32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -66,6 +72,32 @@ static int bgzf_inflate_at(FILE *f, int64_t off, uint8_t *raw, uint8_t *dst, int
     if (rc != Z_STREAM_END || s.total_out != isize) return -1;
     *bsize_out = bsize;
     return (int)isize;
+}
+
+/* inflate the deflate stream of one BGZF block (`clen` bytes, header and trailer stripped) into exactly `isize` bytes at dst and check
+ * the CRC-32 of the trailer.  The batcher's own decoder (inflate.c) runs first; what it refuses is judged by zlib. */
+static int bgzf_inflate_block(struct grom_inflate_ctx *ctx, const uint8_t *src, int clen, uint8_t *dst, int isize, uint32_t crc)
+{
+    if (!ctx || grom_inflate_raw(ctx, src, (size_t)clen, dst, (size_t)isize) != 0) {
+        z_stream s; memset(&s, 0, sizeof(s));
+        s.next_in = (Bytef *)src; s.avail_in = (uInt)clen; s.next_out = dst; s.avail_out = (uInt)isize;
+        if (inflateInit2(&s, -15) != Z_OK) return -1;
+        const int rc = inflate(&s, Z_FINISH);
+        inflateEnd(&s);
+        if (!(rc == Z_STREAM_END && s.total_out == (uLong)isize)) return -1;
+    }
+    return ((uint32_t)crc32(crc32(0L, NULL, 0), dst, (uInt)isize) == crc) ? 0 : -1;
+}
+
+/* test / tooling entry: one raw deflate stream with a known output size through the batcher's own decoder only (no zlib fallback) */
+int gromhost_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len)
+{
+    struct grom_inflate_ctx *ctx = (struct grom_inflate_ctx *)malloc(grom_inflate_ctx_size());
+    if (!ctx) return fail("out of memory");
+    grom_inflate_ctx_init(ctx);
+    const int rc = grom_inflate_raw(ctx, src, (size_t)src_len, dst, (size_t)dst_len);
+    free(ctx);
+    return rc == 0 ? 0 : fail("not a well-formed deflate stream of %lld bytes", (long long)dst_len);
 }
 
 /* sequential reader used only for the header */
@@ -149,6 +181,17 @@ int gromhost_bam_open(const char *path, grom_bam **out)
         }
         fclose(fi);
     }
+    /* the alignment blocks are read in place */
+    struct stat st;
+    if (fstat(fileno(f), &st) != 0 || st.st_size <= 0) { gromhost_bam_close(b); return fail("%s: cannot stat", path); }
+    b->map_len = (int64_t)st.st_size;
+    void *m = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fileno(f), 0);
+    if (m != MAP_FAILED) { b->map = (const uint8_t *)m; b->map_is_mmap = 1; }
+    else {
+        uint8_t *buf = (uint8_t *)malloc((size_t)st.st_size);
+        if (!buf || fseeko(f, 0, SEEK_SET) != 0 || fread(buf, 1, (size_t)st.st_size, f) != (size_t)st.st_size) { free(buf); gromhost_bam_close(b); return fail("%s: cannot map or read", path); }
+        b->map = buf;
+    }
     *out = b;
     return 0;
 }
@@ -156,6 +199,7 @@ int gromhost_bam_open(const char *path, grom_bam **out)
 void gromhost_bam_close(grom_bam *b)
 {
     if (!b) return;
+    if (b->map) { if (b->map_is_mmap) munmap((void *)b->map, (size_t)b->map_len); else free((void *)b->map); }
     for (int i = 0; i < b->n_targets; i++) free(b->names[i]);
     free(b->names); free(b->lens); free(b->tgt_beg); free(b->tgt_end); free(b->path);
     if (b->f) fclose(b->f);
@@ -194,114 +238,6 @@ void gromhost_batch_free(grom_batch *t)
     free(t->seq2); free(t->seq_exc_code); free(t->seq_exc_slot); free(t->qual2);
     free(t->qual4); free(t->sa_index); free(t->sas_pos); free(t->sas_start_adj); free(t->sas_end_adj); free(t->sas_end_adj_indel);
     free(t->sas_mapq); free(t->sas_strand); free(t->sas_same_chr); free(t);
-}
-
-/* What crosses PCIe can be smaller than the canonical arrays (all lossless; the CUDA library rebuilds the canonical device
- * arrays): the offsets are running sums by construction here; base qualities of current instruments take a handful of distinct
- * values, so a 16-entry dictionary halves them; the first-SA-entry fields exist for a small minority of reads. */
-static void batch_compact(grom_batch *t, int n_threads)
-{
-    grom_read_batch *v = &t->v;
-    const int64_t n = v->n_reads, ns = v->n_base_slots;
-    int flags = GROM_LAYOUT_CANONICAL_OFFSETS;
-    if (ns > 0 && (ns & 3) == 0) {
-        /* distinct qualities of the bases (padding slots aside): <= 4 -> 2 bits per slot, <= 16 -> 4 bits, else the bytes travel */
-        int64_t hist[256]; memset(hist, 0, sizeof(hist));
-        #pragma omp parallel num_threads(n_threads)
-        {
-            int64_t h[256]; memset(h, 0, sizeof(h));
-            #pragma omp for schedule(static) nowait
-            for (int64_t i = 0; i < n; i++) { const uint8_t *q = t->qual + t->base_off[i]; const int lq = t->l_qseq[i]; for (int k = 0; k < lq; k++) h[q[k]]++; }
-            #pragma omp critical
-            for (int k = 0; k < 256; k++) hist[k] += h[k];
-        }
-        int nv = 0; uint8_t inv[256]; memset(inv, 0, sizeof(inv));
-        for (int k = 0; k < 256; k++) if (hist[k]) { if (nv < 16) { v->qual_lut[nv] = (uint8_t)k; inv[k] = (uint8_t)nv; } nv++; }
-        if (nv >= 1 && nv <= 4 && (t->qual2 = (uint8_t *)calloc((size_t)(ns / 4 + 16), 1))) {
-            #pragma omp parallel for schedule(static) num_threads(n_threads)
-            for (int64_t i = 0; i < n; i++) {
-                const uint64_t b0 = t->base_off[i]; const int lq = t->l_qseq[i];
-                for (int k = 0; k < lq; k++) { const uint64_t sl = b0 + (uint64_t)k; t->qual2[sl >> 2] |= (uint8_t)(inv[t->qual[sl]] << ((~sl & 3) << 1)); }
-            }
-            v->qual2 = t->qual2; flags |= GROM_LAYOUT_QUAL2;
-        } else if (nv >= 1 && nv <= 16 && !hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
-            /* 4-bit form: padding slots (0 in the canonical array) must decode to 0 as well, so 0 takes a dictionary entry */
-            if (nv == 16) { free(t->qual4); t->qual4 = NULL; memset(v->qual_lut, 0, 16); }
-            else {
-                for (int k = nv; k > 0; k--) v->qual_lut[k] = v->qual_lut[k - 1];
-                v->qual_lut[0] = 0;
-                for (int k = 0; k < 256; k++) if (hist[k]) inv[k]++;
-                inv[0] = 0;
-                #pragma omp parallel for schedule(static) num_threads(n_threads)
-                for (int64_t s = 0; s < ns; s += 2) t->qual4[s >> 1] = (uint8_t)((inv[t->qual[s]] << 4) | inv[t->qual[s + 1]]);
-                v->qual4 = t->qual4; flags |= GROM_LAYOUT_QUAL4;
-            }
-        } else if (nv >= 1 && nv <= 16 && hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
-            #pragma omp parallel for schedule(static) num_threads(n_threads)
-            for (int64_t s = 0; s < ns; s += 2) t->qual4[s >> 1] = (uint8_t)((inv[t->qual[s]] << 4) | inv[t->qual[s + 1]]);
-            v->qual4 = t->qual4; flags |= GROM_LAYOUT_QUAL4;
-        } else memset(v->qual_lut, 0, 16);
-    }
-    /* bases: 2 bits per slot, everything that is not A/C/G/T listed with its BAM code (two passes: count per read, then fill) */
-    if (ns > 0 && (ns & 3) == 0) {
-        int64_t *exc_at = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n + 1));
-        t->seq2 = (uint8_t *)calloc((size_t)(ns / 4 + 16), 1);
-        if (exc_at && t->seq2) {
-            #pragma omp parallel for schedule(static) num_threads(n_threads)
-            for (int64_t i = 0; i < n; i++) {
-                const uint64_t b0 = t->base_off[i]; const int lq = t->l_qseq[i]; int64_t c = 0;
-                for (int k = 0; k < lq; k++) {
-                    const uint64_t sl = b0 + (uint64_t)k;
-                    const int code = (t->seq4[sl >> 1] >> ((~sl & 1) << 2)) & 15;
-                    const int two = code == 1 ? 0 : code == 2 ? 1 : code == 4 ? 2 : code == 8 ? 3 : -1;
-                    if (two < 0) c++;
-                    else if (two) t->seq2[sl >> 2] |= (uint8_t)(two << ((~sl & 3) << 1));        /* a read's slots start on a 32-slot boundary: bytes are not shared */
-                }
-                exc_at[i + 1] = c;
-            }
-            exc_at[0] = 0;
-            for (int64_t i = 0; i < n; i++) exc_at[i + 1] += exc_at[i];
-            const int64_t ne = exc_at[n];
-            if (ne <= ns / 16) {
-                t->seq_exc_slot = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(ne + 1)); t->seq_exc_code = (uint8_t *)malloc((size_t)(ne + 1));
-                if (t->seq_exc_slot && t->seq_exc_code) {
-                    #pragma omp parallel for schedule(static) num_threads(n_threads)
-                    for (int64_t i = 0; i < n; i++) {
-                        if (exc_at[i + 1] == exc_at[i]) continue;
-                        const uint64_t b0 = t->base_off[i]; const int lq = t->l_qseq[i]; int64_t w = exc_at[i];
-                        for (int k = 0; k < lq; k++) {
-                            const uint64_t sl = b0 + (uint64_t)k;
-                            const int code = (t->seq4[sl >> 1] >> ((~sl & 1) << 2)) & 15;
-                            if (code != 1 && code != 2 && code != 4 && code != 8) { t->seq_exc_slot[w] = sl; t->seq_exc_code[w] = (uint8_t)code; w++; }
-                        }
-                    }
-                    v->seq2 = t->seq2; v->n_seq_exc = ne; v->seq_exc_slot = t->seq_exc_slot; v->seq_exc_code = t->seq_exc_code;
-                    flags |= GROM_LAYOUT_SEQ2;
-                }
-            }
-        }
-        free(exc_at);
-    }
-    int64_t m = 0;
-#define SA_SET(i) (t->sa_pos[i] != -1 || t->sa_mapq[i] != -1 || t->sa_strand[i] || t->sa_same_chr[i] || t->sa_start_adj[i] || t->sa_end_adj[i] || t->sa_end_adj_indel[i])
-    for (int64_t i = 0; i < n; i++) m += SA_SET(i);
-    t->sa_index = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1)); t->sas_pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1));
-    t->sas_start_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1)); t->sas_end_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1));
-    t->sas_end_adj_indel = (int32_t *)malloc(sizeof(int32_t) * (size_t)(m + 1)); t->sas_mapq = (int16_t *)malloc(sizeof(int16_t) * (size_t)(m + 1));
-    t->sas_strand = (uint8_t *)malloc((size_t)(m + 1)); t->sas_same_chr = (uint8_t *)malloc((size_t)(m + 1));
-    if (t->sa_index && t->sas_pos && t->sas_start_adj && t->sas_end_adj && t->sas_end_adj_indel && t->sas_mapq && t->sas_strand && t->sas_same_chr) {
-        int64_t k = 0;
-        for (int64_t i = 0; i < n; i++) if (SA_SET(i)) {                /* parse_sa leaves every other read at (-1, 0, -1, 0, 0, 0, 0) */
-            t->sa_index[k] = (int32_t)i; t->sas_pos[k] = t->sa_pos[i]; t->sas_start_adj[k] = t->sa_start_adj[i]; t->sas_end_adj[k] = t->sa_end_adj[i];
-            t->sas_end_adj_indel[k] = t->sa_end_adj_indel[i]; t->sas_mapq[k] = t->sa_mapq[i]; t->sas_strand[k] = t->sa_strand[i]; t->sas_same_chr[k] = t->sa_same_chr[i];
-            k++;
-        }
-        v->n_sa = m; v->sa_index = t->sa_index; v->sas_pos = t->sas_pos; v->sas_start_adj = t->sas_start_adj; v->sas_end_adj = t->sas_end_adj;
-        v->sas_end_adj_indel = t->sas_end_adj_indel; v->sas_mapq = t->sas_mapq; v->sas_strand = t->sas_strand; v->sas_same_chr = t->sas_same_chr;
-        flags |= GROM_LAYOUT_SPARSE_SA;
-    }
-    v->layout_flags = flags;
-#undef SA_SET
 }
 
 static void batch_publish(grom_batch *t)
@@ -410,6 +346,52 @@ static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, 
 
 typedef struct { int64_t off; int bsize; int isize; int64_t uoff; } blkinfo;
 
+/* reads with a first XP / SA entry, collected per thread during the fill pass (a small minority of the reads) */
+typedef struct { int32_t idx, pos, start_adj, end_adj, end_adj_indel; int16_t mapq; uint8_t strand, same_chr; } sa_ent;
+typedef struct { sa_ent *e; int64_t n, cap; uint8_t present[256]; char pad[64]; } fill_local;
+
+/* the records of target `tid` in the inflated stream, in file order: offsets of the records and the running sums that become
+ * cigar_off / base_off / qname_off (the canonical offsets of include/grom_reads.h) */
+typedef struct { int64_t n, cap, n_cig, n_slots, n_name; int64_t *recoff; uint64_t *cig_off, *base_off, *name_off; } reclist;
+
+static int reclist_grow(reclist *r, int keep_names)
+{
+    int64_t cap = r->cap ? r->cap * 2 : 4096;
+    int64_t *a = (int64_t *)realloc(r->recoff, sizeof(int64_t) * (size_t)cap); if (!a) return -1; r->recoff = a;
+    uint64_t *b = (uint64_t *)realloc(r->cig_off, sizeof(uint64_t) * (size_t)cap); if (!b) return -1; r->cig_off = b;
+    uint64_t *c = (uint64_t *)realloc(r->base_off, sizeof(uint64_t) * (size_t)cap); if (!c) return -1; r->base_off = c;
+    if (keep_names) { uint64_t *d = (uint64_t *)realloc(r->name_off, sizeof(uint64_t) * (size_t)(cap + 1)); if (!d) return -1; r->name_off = d; }
+    r->cap = cap;
+    return 0;
+}
+
+/* One pass over the record chain from offset p: validates the layout of every record of the target (a truncated or corrupt file must
+ * not make the fill pass read past the inflated data) and lists them.  Returns 0, -1 (corrupt record, message set) or -2 (memory). */
+static int walk_records(const uint8_t *u, int64_t utotal, int64_t p, int tid, int keep_names, const char *path, reclist *r)
+{
+    int started = 0;
+    while (p + 36 <= utotal) {
+        const int32_t bl = rd_i32(u + p);
+        if (bl < 32 || p + 4 + bl > utotal) break;
+        const int32_t rtid = rd_i32(u + p + 4);
+        if (rtid == tid) {
+            started = 1;
+            const uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16); const int32_t lq = rd_i32(u + p + 20);
+            if (lq < 0 || 32 + (int64_t)(bmq & 0xff) + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl)
+                return fail("%s: corrupt BAM record at uncompressed offset %lld (block_size %d cannot hold name %u + %u CIGAR ops + %d bases)",
+                            path, (long long)p, bl, bmq & 0xff, fnc & 0xffff, lq);
+            if (r->n == r->cap && reclist_grow(r, keep_names) < 0) return -2;
+            r->recoff[r->n] = p; r->cig_off[r->n] = (uint64_t)r->n_cig; r->base_off[r->n] = (uint64_t)r->n_slots;
+            if (keep_names) r->name_off[r->n] = (uint64_t)r->n_name;
+            r->n++; r->n_cig += fnc & 0xffff; r->n_slots += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN; r->n_name += bmq & 0xff;
+        } else if (started || rtid > tid || rtid < 0) {
+            break;      /* coordinate-sorted: past the target (or into the unplaced tail) */
+        }
+        p += 4 + bl;
+    }
+    return 0;
+}
+
 int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out)
 {
     if (tid < 0 || tid >= b->n_targets) return fail("target id %d out of range", tid);
@@ -418,139 +400,259 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         if (b->tgt_beg[tid] == UINT64_MAX) { vbeg = vend = 0; }
         else { vbeg = b->tgt_beg[tid]; vend = b->tgt_end[tid]; }
     }
-    grom_batch *t = (grom_batch *)calloc(1, sizeof(*t));
-    t->v.tid = tid;
     const int trace = getenv("GROMHOST_TRACE") != NULL;
     double t_last = trace ? now_ms() : 0;
-    /* 1. enumerate the compressed blocks in [vbeg, vend] */
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+    /* 1. enumerate the compressed blocks in [vbeg, vend] (the file is mapped: headers and trailers are read in place) */
     blkinfo *blk = NULL; int64_t nblk = 0, capblk = 0;
+    const uint8_t *cf = b->map; const int64_t cf_len = b->map_len;
     if (vend != 0) {
         int64_t off = (int64_t)(vbeg >> 16), endoff = (vend == UINT64_MAX) ? INT64_MAX : (int64_t)(vend >> 16);
-        uint8_t hdr[18];
-        while (off <= endoff) {
-            if (fseeko(b->f, off, SEEK_SET) != 0) break;
-            if (fread(hdr, 1, 18, b->f) != 18) break;
-            if (hdr[0] != 0x1f || hdr[1] != 0x8b) { free(blk); free(t); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
-            int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
-            uint8_t tail[4];
-            if (fseeko(b->f, off + bsize - 4, SEEK_SET) != 0 || fread(tail, 1, 4, b->f) != 4) break;
+        while (off <= endoff && off + 18 <= cf_len) {
+            const uint8_t *hdr = cf + off;
+            if (hdr[0] != 0x1f || hdr[1] != 0x8b) { free(blk); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
+            const int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
+            if (bsize < 26 || !(hdr[3] & 4) || (hdr[10] | (hdr[11] << 8)) != 6 || hdr[12] != 'B' || hdr[13] != 'C') { free(blk); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
+            if (off + bsize > cf_len) break;                      /* truncated last block */
+            const uint32_t isize = rd_u32(cf + off + bsize - 4);
+            if (isize > 65536) { free(blk); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
             if (nblk == capblk) { capblk = capblk ? capblk * 2 : 1024; blk = (blkinfo *)realloc(blk, capblk * sizeof(blkinfo)); }
-            blk[nblk].off = off; blk[nblk].bsize = bsize; blk[nblk].isize = (int)rd_u32(tail); nblk++;
+            blk[nblk].off = off; blk[nblk].bsize = bsize; blk[nblk].isize = (int)isize; nblk++;
             off += bsize;
         }
     }
     int64_t utotal = 0;
     for (int64_t i = 0; i < nblk; i++) { blk[i].uoff = utotal; utotal += blk[i].isize; }
     TRACE_MARK("enumerate blocks");
+    /* 2. inflate in parallel, every block straight to its place in the inflated stream */
     uint8_t *u = (uint8_t *)malloc((size_t)utotal + 64);
-    /* 2. inflate in parallel (each thread its own FILE*) */
+    if (!u) { free(blk); return fail("out of memory (%lld bytes of inflated BAM)", (long long)utotal); }
     int bad = 0;
-#ifdef _OPENMP
-    if (n_threads <= 0) n_threads = omp_get_max_threads();
-#else
-    n_threads = 1;
-#endif
+    const char *force = getenv("GROMHOST_INFLATE");
+    const int own = !(force && !strcmp(force, "zlib"));            /* GROMHOST_INFLATE=zlib: every block through zlib */
     #pragma omp parallel num_threads(n_threads)
     {
-        FILE *f = fopen(b->path, "rb");
-        uint8_t *raw = (uint8_t *)malloc(65536 + 64), *tmp = (uint8_t *)malloc(65536);
+        struct grom_inflate_ctx *ctx = own ? (struct grom_inflate_ctx *)malloc(grom_inflate_ctx_size()) : NULL;
+        if (ctx) grom_inflate_ctx_init(ctx);
         #pragma omp for schedule(dynamic, 16)
         for (int64_t i = 0; i < nblk; i++) {
-            int bs; int n = f ? bgzf_inflate_at(f, blk[i].off, raw, tmp, &bs) : -1;
-            if (n != blk[i].isize) { bad = 1; continue; }
-            memcpy(u + blk[i].uoff, tmp, n);
-        }
-        free(raw); free(tmp); if (f) fclose(f);
-    }
-    if (bad) { free(blk); free(u); free(t); return fail("%s: BGZF inflate failed", b->path); }
-    TRACE_MARK("inflate");
-    /* 3. first pass over records: count */
-    int64_t p = (nblk > 0) ? (int64_t)(vbeg & 0xffff) : 0;
-    int64_t n_reads = 0, n_cig = 0, n_slots = 0, n_name = 0, p0 = p;
-    int started = 0;
-    while (p + 36 <= utotal) {
-        int32_t bl = rd_i32(u + p);
-        if (bl < 32 || p + 4 + bl > utotal) break;
-        int32_t rtid = rd_i32(u + p + 4);
-        if (rtid == tid) {
-            if (!started) { started = 1; p0 = p; }
-            uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16); int32_t lq = rd_i32(u + p + 20);
-            /* the fixed part, name, CIGAR, packed bases and qualities must fit the record (a truncated or corrupt file must not make the
-             * fill pass below read past the inflated data) */
-            if (lq < 0 || 32 + (int64_t)(bmq & 0xff) + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl) {
-                free(blk); free(u); free(t);
-                return fail("%s: corrupt BAM record at uncompressed offset %lld (block_size %d cannot hold name %u + %u CIGAR ops + %d bases)",
-                            b->path, (long long)p, bl, bmq & 0xff, fnc & 0xffff, lq);
+            const uint8_t *blkp = cf + blk[i].off;
+            if (bgzf_inflate_block(ctx, blkp + 18, blk[i].bsize - 26, u + blk[i].uoff, blk[i].isize, rd_u32(blkp + blk[i].bsize - 8)) < 0) {
+                #pragma omp atomic write
+                bad = 1;
             }
-            n_reads++; n_cig += fnc & 0xffff; n_slots += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN;
-            n_name += bmq & 0xff;
-        } else if (started || rtid > tid || rtid < 0) {
-            break;      /* coordinate-sorted: past the target (or into the unplaced tail) */
         }
-        p += 4 + bl;
+        free(ctx);
     }
-    TRACE_MARK("count records");
+    free(blk);
+    if (bad) { free(u); return fail("%s: BGZF inflate failed (corrupt deflate stream or CRC mismatch)", b->path); }
+    TRACE_MARK("inflate");
+    /* 3. the record chain: count, validate, offsets */
+    reclist rl; memset(&rl, 0, sizeof(rl));
+    int wrc = reclist_grow(&rl, keep_names);
+    if (wrc == 0) wrc = walk_records(u, utotal, (nblk > 0) ? (int64_t)(vbeg & 0xffff) : 0, tid, keep_names, b->path, &rl);
+    if (wrc < 0) {
+        free(rl.recoff); free(rl.cig_off); free(rl.base_off); free(rl.name_off); free(u);
+        return wrc == -2 ? fail("out of memory (record list)") : -1;
+    }
+    const int64_t n_reads = rl.n, n_cig = rl.n_cig, n_slots = rl.n_slots, n_name = rl.n_name;
+    if (keep_names) rl.name_off[n_reads] = (uint64_t)n_name;
+    TRACE_MARK("record chain");
     /* 4. allocate */
+    grom_batch *t = (grom_batch *)calloc(1, sizeof(*t));
+    t->v.tid = tid;
     size_t nr = (size_t)(n_reads > 0 ? n_reads : 1);
 #define AL(ptr, type, cnt) t->ptr = (type *)calloc((cnt), sizeof(type))
     AL(pos, int32_t, nr); AL(mpos, int32_t, nr); AL(tlen, int32_t, nr); AL(mtid, int32_t, nr); AL(l_qseq, int32_t, nr);
     AL(sa_pos, int32_t, nr); AL(sa_start_adj, int32_t, nr); AL(sa_end_adj, int32_t, nr); AL(sa_end_adj_indel, int32_t, nr);
     AL(flag, uint16_t, nr); AL(n_cigar, uint16_t, nr); AL(sa_mapq, int16_t, nr);
     AL(mapq, uint8_t, nr); AL(qname_len, uint8_t, nr); AL(sa_strand, uint8_t, nr); AL(sa_same_chr, uint8_t, nr);
-    AL(qname_hash, uint64_t, nr); AL(cigar_off, uint64_t, nr); AL(base_off, uint64_t, nr);
+    AL(qname_hash, uint64_t, nr);
     AL(cigar, uint32_t, (size_t)(n_cig > 0 ? n_cig : 1));
     AL(seq4, uint8_t, (size_t)(n_slots / 2 + 16)); AL(qual, uint8_t, (size_t)(n_slots + 16));
-    if (keep_names) { AL(qname_off, uint64_t, nr + 1); AL(qname_pool, char, (size_t)(n_name + 1)); }
+    if (keep_names) AL(qname_pool, char, (size_t)(n_name + 1));
+    t->cigar_off = rl.cig_off; t->base_off = rl.base_off; t->qname_off = rl.name_off;
+    /* transport-compact forms (include/grom_reads.h GROM_LAYOUT_*), all lossless; the CUDA library rebuilds the canonical device arrays.
+     * The offsets are running sums by construction here; base qualities of current instruments take a handful of distinct values, so a
+     * 4- or 16-entry dictionary shrinks them to 2 or 4 bits; bases travel as 2 bits + a list of everything that is not A/C/G/T; the
+     * first-SA-entry fields exist for a small minority of reads. */
+    const int64_t ns = n_slots;
+    int64_t *exc_at = NULL;
+    if (ns > 0) { AL(seq2, uint8_t, (size_t)(ns / 4 + 16)); exc_at = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_reads + 1)); }
 #undef AL
     TRACE_MARK("allocate");
-    /* 5. offsets (sequential, cheap), then fill (parallel over reads) */
-    int64_t *recoff = (int64_t *)malloc(sizeof(int64_t) * nr);
-    {
-        int64_t q = p0, ci = 0, sl = 0, nm = 0;
-        for (int64_t i = 0; i < n_reads; i++) {
-            int32_t bl = rd_i32(u + q);
-            uint32_t bmq = rd_u32(u + q + 12), fnc = rd_u32(u + q + 16); int32_t lq = rd_i32(u + q + 20);
-            recoff[i] = q; t->cigar_off[i] = (uint64_t)ci; t->base_off[i] = (uint64_t)sl;
-            if (keep_names) t->qname_off[i] = (uint64_t)nm;
-            ci += fnc & 0xffff; sl += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN; nm += bmq & 0xff;
-            q += 4 + bl;
-        }
-        if (keep_names) t->qname_off[n_reads] = (uint64_t)nm;
+    /* 5. fill, parallel over contiguous ranges of reads.  In the same pass over a record: the 2-bit form of its bases (table-driven, two
+     * nibbles per lookup) with the number of its non-A/C/G/T bases, the set of quality values seen, and the reads with an XP / SA entry. */
+    uint8_t S2[256], SX[256];
+    for (int v = 0; v < 256; v++) {
+        const int hi = v >> 4, lo = v & 15;
+        const int th = hi == 1 ? 0 : hi == 2 ? 1 : hi == 4 ? 2 : hi == 8 ? 3 : -1, tl = lo == 1 ? 0 : lo == 2 ? 1 : lo == 4 ? 2 : lo == 8 ? 3 : -1;
+        S2[v] = (uint8_t)(((th < 0 ? 0 : th) << 2) | (tl < 0 ? 0 : tl)); SX[v] = (uint8_t)((th < 0) + (tl < 0));
     }
+    const int do_seq2 = (t->seq2 != NULL && exc_at != NULL);
     const char *tname = b->names[tid];
-    TRACE_MARK("offsets");
-    #pragma omp parallel for schedule(static) num_threads(n_threads)
-    for (int64_t i = 0; i < n_reads; i++) {
-        const uint8_t *r = u + recoff[i];
-        int32_t bl = rd_i32(r);
-        uint32_t bmq = rd_u32(r + 12), fnc = rd_u32(r + 16);
-        int l_qname = bmq & 0xff, ncig = fnc & 0xffff; int32_t lq = rd_i32(r + 20);
-        t->pos[i] = rd_i32(r + 8); t->mapq[i] = (bmq >> 8) & 0xff; t->flag[i] = (uint16_t)(fnc >> 16); t->n_cigar[i] = (uint16_t)ncig;
-        t->l_qseq[i] = lq; t->mtid[i] = rd_i32(r + 24); t->mpos[i] = rd_i32(r + 28); t->tlen[i] = rd_i32(r + 32);
-        const uint8_t *d = r + 36;
-        int nl = (int)strnlen((const char *)d, l_qname);
-        t->qname_len[i] = (uint8_t)(nl > 255 ? 255 : nl);
-        t->qname_hash[i] = grom_qname_hash((const char *)d, nl);
-        if (keep_names) memcpy(t->qname_pool + t->qname_off[i], d, l_qname);
-        memcpy(t->cigar + t->cigar_off[i], d + l_qname, (size_t)ncig * 4);
-        const uint8_t *sq = d + l_qname + ncig * 4;
-        memcpy(t->seq4 + t->base_off[i] / 2, sq, (size_t)(lq + 1) / 2);
-        memcpy(t->qual + t->base_off[i], sq + (lq + 1) / 2, (size_t)lq);
-        const uint8_t *aux = sq + (lq + 1) / 2 + lq;
-        int l_aux = (int)((r + 4 + bl) - aux);
-        parse_sa(aux, l_aux, tname, &t->sa_pos[i], &t->sa_strand[i], &t->sa_mapq[i], &t->sa_same_chr[i],
-                 &t->sa_start_adj[i], &t->sa_end_adj[i], &t->sa_end_adj_indel[i]);
+    fill_local *loc = (fill_local *)calloc((size_t)n_threads, sizeof(fill_local));
+    int n_team = 1;
+    #pragma omp parallel num_threads(n_threads)
+    {
+#ifdef _OPENMP
+        const int T = omp_get_num_threads(), me = omp_get_thread_num();
+#else
+        const int T = 1, me = 0;
+#endif
+        #pragma omp single
+        n_team = T;
+        fill_local *L = &loc[me];
+        const int64_t i0 = n_reads * me / T, i1 = n_reads * (me + 1) / T;
+        for (int64_t i = i0; i < i1; i++) {
+            const uint8_t *r = u + rl.recoff[i];
+            const int32_t bl = rd_i32(r);
+            const uint32_t bmq = rd_u32(r + 12), fnc = rd_u32(r + 16);
+            const int l_qname = bmq & 0xff, ncig = fnc & 0xffff; const int32_t lq = rd_i32(r + 20);
+            t->pos[i] = rd_i32(r + 8); t->mapq[i] = (bmq >> 8) & 0xff; t->flag[i] = (uint16_t)(fnc >> 16); t->n_cigar[i] = (uint16_t)ncig;
+            t->l_qseq[i] = lq; t->mtid[i] = rd_i32(r + 24); t->mpos[i] = rd_i32(r + 28); t->tlen[i] = rd_i32(r + 32);
+            const uint8_t *d = r + 36;
+            const int nl = (int)strnlen((const char *)d, l_qname);
+            t->qname_len[i] = (uint8_t)(nl > 255 ? 255 : nl);
+            t->qname_hash[i] = grom_qname_hash((const char *)d, nl);
+            if (keep_names) memcpy(t->qname_pool + t->qname_off[i], d, l_qname);
+            memcpy(t->cigar + t->cigar_off[i], d + l_qname, (size_t)ncig * 4);
+            const uint8_t *sq = d + l_qname + ncig * 4;
+            const uint64_t b0 = t->base_off[i];
+            const int nb = (lq + 1) / 2;
+            memcpy(t->seq4 + b0 / 2, sq, (size_t)nb);
+            const uint8_t *ql = sq + nb;
+            memcpy(t->qual + b0, ql, (size_t)lq);
+            for (int k = 0; k < lq; k++) L->present[ql[k]] = 1;
+            if (do_seq2) {
+                uint8_t *o2 = t->seq2 + b0 / 4; int64_t ne = 0;
+                const int nfull = (lq & 1) ? nb - 1 : nb;                     /* bytes whose two nibbles are both bases */
+                int k = 0;
+                for (; k + 2 <= nfull; k += 2) { const uint8_t x = sq[k], y = sq[k + 1]; o2[k >> 1] = (uint8_t)((S2[x] << 4) | S2[y]); ne += SX[x] + SX[y]; }
+                if (k < nb) {                                                  /* one or two bytes left; the padding nibble of an odd length is no base */
+                    uint8_t x = sq[k], y = 0x11;
+                    if (k + 1 < nb) y = sq[k + 1];
+                    if (lq & 1) { if (k + 1 < nb) y = (uint8_t)((y & 0xf0) | 1); else x = (uint8_t)((x & 0xf0) | 1); }
+                    o2[k >> 1] = (uint8_t)((S2[x] << 4) | S2[y]); ne += SX[x] + SX[y];
+                }
+                exc_at[i + 1] = ne;
+            }
+            const uint8_t *aux = ql + lq;
+            const int l_aux = (int)((r + 4 + bl) - aux);
+            parse_sa(aux, l_aux, tname, &t->sa_pos[i], &t->sa_strand[i], &t->sa_mapq[i], &t->sa_same_chr[i],
+                     &t->sa_start_adj[i], &t->sa_end_adj[i], &t->sa_end_adj_indel[i]);
+            if (t->sa_pos[i] != -1 || t->sa_mapq[i] != -1 || t->sa_strand[i] || t->sa_same_chr[i] || t->sa_start_adj[i] || t->sa_end_adj[i] || t->sa_end_adj_indel[i]) {
+                if (L->n == L->cap) { L->cap = L->cap ? L->cap * 2 : 1024; L->e = (sa_ent *)realloc(L->e, sizeof(sa_ent) * (size_t)L->cap); }
+                sa_ent *e = &L->e[L->n++];                /* parse_sa leaves every other read at (-1, 0, -1, 0, 0, 0, 0) */
+                e->idx = (int32_t)i; e->pos = t->sa_pos[i]; e->start_adj = t->sa_start_adj[i]; e->end_adj = t->sa_end_adj[i];
+                e->end_adj_indel = t->sa_end_adj_indel[i]; e->mapq = t->sa_mapq[i]; e->strand = t->sa_strand[i]; e->same_chr = t->sa_same_chr[i];
+            }
+        }
     }
     TRACE_MARK("fill");
-    free(recoff); free(u); free(blk);
+    free(rl.recoff);
     t->v.n_reads = n_reads; t->v.n_cigar_total = n_cig; t->v.n_base_slots = n_slots;
     batch_publish(t);
-    TRACE_MARK("free");
-    batch_compact(t, n_threads);
+    grom_read_batch *v = &t->v;
+    int flags = GROM_LAYOUT_CANONICAL_OFFSETS;
+    /* 6. the forms that need a whole-batch decision.  Qualities: <= 4 distinct values on the bases (padding slots aside) -> 2 bits per
+     * slot, <= 16 -> 4 bits, else the bytes travel.  inv[0] is 0 either way, so the zero padding slots pack to 0 without a test. */
+    int hist[256]; memset(hist, 0, sizeof(hist));
+    for (int k = 0; k < n_team; k++) for (int q = 0; q < 256; q++) hist[q] |= loc[k].present[q];
+    int nv = 0, qmode = 0; uint8_t inv[256]; memset(inv, 0, sizeof(inv));
+    if (ns > 0) {
+        for (int k = 0; k < 256; k++) if (hist[k]) { if (nv < 16) { v->qual_lut[nv] = (uint8_t)k; inv[k] = (uint8_t)nv; } nv++; }
+        if (nv >= 1 && nv <= 4 && (t->qual2 = (uint8_t *)calloc((size_t)(ns / 4 + 16), 1))) qmode = 2;
+        else if (nv >= 1 && nv <= 16 && !hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
+            /* 4-bit form: padding slots (0 in the canonical array) must decode to 0 as well, so 0 takes a dictionary entry */
+            if (nv == 16) { free(t->qual4); t->qual4 = NULL; memset(v->qual_lut, 0, 16); }
+            else {
+                for (int k = nv; k > 0; k--) v->qual_lut[k] = v->qual_lut[k - 1];
+                v->qual_lut[0] = 0;
+                for (int k = 0; k < 256; k++) if (hist[k]) inv[k]++;
+                inv[0] = 0;
+                qmode = 4;
+            }
+        } else if (nv >= 1 && nv <= 16 && hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) qmode = 4;
+        else memset(v->qual_lut, 0, 16);
+    }
+    int64_t n_sa = 0;
+    for (int k = 0; k < n_team; k++) n_sa += loc[k].n;
+    t->sa_index = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1)); t->sas_pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1));
+    t->sas_start_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1)); t->sas_end_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1));
+    t->sas_end_adj_indel = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1)); t->sas_mapq = (int16_t *)malloc(sizeof(int16_t) * (size_t)(n_sa + 1));
+    t->sas_strand = (uint8_t *)malloc((size_t)(n_sa + 1)); t->sas_same_chr = (uint8_t *)malloc((size_t)(n_sa + 1));
+    const int sa_ok = t->sa_index && t->sas_pos && t->sas_start_adj && t->sas_end_adj && t->sas_end_adj_indel && t->sas_mapq && t->sas_strand && t->sas_same_chr;
+    int64_t ne = 0; int seq2_ok = 0;
+    if (do_seq2) {
+        exc_at[0] = 0;
+        for (int64_t i = 0; i < n_reads; i++) exc_at[i + 1] += exc_at[i];
+        ne = exc_at[n_reads];
+        if (ne <= ns / 16) {
+            t->seq_exc_slot = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(ne + 1)); t->seq_exc_code = (uint8_t *)malloc((size_t)(ne + 1));
+            seq2_ok = t->seq_exc_slot && t->seq_exc_code;
+        }
+    }
+    #pragma omp parallel num_threads(n_threads)
+    {
+        /* the inflated stream is no longer needed: unmapping it takes one thread a while, the others start on the packing */
+        #pragma omp single nowait
+        free(u);
+        if (qmode == 2) {
+            #pragma omp for schedule(dynamic, 1 << 16) nowait
+            for (int64_t s = 0; s < ns; s += 4) t->qual2[s >> 2] = (uint8_t)((inv[t->qual[s]] << 6) | (inv[t->qual[s + 1]] << 4) | (inv[t->qual[s + 2]] << 2) | inv[t->qual[s + 3]]);
+        } else if (qmode == 4) {
+            #pragma omp for schedule(dynamic, 1 << 16) nowait
+            for (int64_t s = 0; s < ns; s += 2) t->qual4[s >> 1] = (uint8_t)((inv[t->qual[s]] << 4) | inv[t->qual[s + 1]]);
+        }
+        if (seq2_ok) {
+            #pragma omp for schedule(dynamic, 4096) nowait
+            for (int64_t i = 0; i < n_reads; i++) {
+                if (exc_at[i + 1] == exc_at[i]) continue;
+                const uint64_t b0 = t->base_off[i]; const int lq = t->l_qseq[i]; int64_t w = exc_at[i];
+                for (int k = 0; k < lq; k++) {
+                    const uint64_t sl = b0 + (uint64_t)k;
+                    const int code = (t->seq4[sl >> 1] >> ((~sl & 1) << 2)) & 15;
+                    if (code != 1 && code != 2 && code != 4 && code != 8) { t->seq_exc_slot[w] = sl; t->seq_exc_code[w] = (uint8_t)code; w++; }
+                }
+            }
+        }
+        if (sa_ok) {
+            #pragma omp for schedule(static, 1) nowait
+            for (int k = 0; k < n_team; k++) {
+                int64_t w = 0;
+                for (int j = 0; j < k; j++) w += loc[j].n;
+                for (int64_t j = 0; j < loc[k].n; j++, w++) {
+                    const sa_ent *e = &loc[k].e[j];
+                    t->sa_index[w] = e->idx; t->sas_pos[w] = e->pos; t->sas_start_adj[w] = e->start_adj; t->sas_end_adj[w] = e->end_adj;
+                    t->sas_end_adj_indel[w] = e->end_adj_indel; t->sas_mapq[w] = e->mapq; t->sas_strand[w] = e->strand; t->sas_same_chr[w] = e->same_chr;
+                }
+            }
+        }
+    }
+    if (qmode == 2) { v->qual2 = t->qual2; flags |= GROM_LAYOUT_QUAL2; }
+    else if (qmode == 4) { v->qual4 = t->qual4; flags |= GROM_LAYOUT_QUAL4; }
+    if (seq2_ok) {
+        v->seq2 = t->seq2; v->n_seq_exc = ne; v->seq_exc_slot = t->seq_exc_slot; v->seq_exc_code = t->seq_exc_code;
+        flags |= GROM_LAYOUT_SEQ2;
+    }
+    if (sa_ok) {
+        v->n_sa = n_sa; v->sa_index = t->sa_index; v->sas_pos = t->sas_pos; v->sas_start_adj = t->sas_start_adj; v->sas_end_adj = t->sas_end_adj;
+        v->sas_end_adj_indel = t->sas_end_adj_indel; v->sas_mapq = t->sas_mapq; v->sas_strand = t->sas_strand; v->sas_same_chr = t->sas_same_chr;
+        flags |= GROM_LAYOUT_SPARSE_SA;
+    }
+    v->layout_flags = flags;
+    for (int k = 0; k < n_threads; k++) free(loc[k].e);
+    free(loc); free(exc_at);
     TRACE_MARK("compact forms");
     *out = t;
     return 0;
 }
+
 
 /* ------------------------------------------------------------------ writer (tooling) */
 

@@ -43,8 +43,49 @@ def _check(rc: int):
         raise RuntimeError(lib().gromhost_last_error().decode())
 
 
+class OwnedBatch:
+    """A batch that stays in the batcher's own memory (no numpy copy): what the C host program hands to gromgpu_push_reads.
+    `as_c()` is the view the CUDA library takes; `free()` (or leaving the `with` block) returns the memory."""
+
+    def __init__(self, handle: C.c_void_p):
+        self._h = handle
+        self.view = CReadBatch()
+        lib().gromhost_batch_view(self._h, C.byref(self.view))
+        self.tid = int(self.view.tid)
+        self.n_reads = int(self.view.n_reads)
+        self.n_base_slots = int(self.view.n_base_slots)
+        self.n_cigar_total = int(self.view.n_cigar_total)
+        self.layout_flags = int(self.view.layout_flags)
+
+    def as_c(self) -> CReadBatch:
+        if not self._h:
+            raise RuntimeError("batch already freed")
+        return self.view
+
+    def to_numpy(self, keep_names: bool = False) -> ReadBatch:
+        return batch_from_c(self.as_c(), keep_names)
+
+    def free(self):
+        if self._h:
+            lib().gromhost_batch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.free()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Bam:
-    """An open BAM; `read_target(tid)` returns the contig's reads as a ReadBatch."""
+    """An open BAM; `read_target(tid)` returns the contig's reads as a ReadBatch (numpy copy), `read_target_owned(tid)` as the
+    batcher's own memory (OwnedBatch, what the product path pushes to the GPU)."""
 
     def __init__(self, path: str):
         self._h = C.c_void_p()
@@ -63,6 +104,11 @@ class Bam:
             return batch_from_c(v, keep_names)
         finally:
             lib().gromhost_batch_free(bt)
+
+    def read_target_owned(self, tid: int, keep_names: bool = False, threads: int = 0) -> OwnedBatch:
+        bt = C.c_void_p()
+        _check(lib().gromhost_bam_read_target(self._h, tid, int(keep_names), threads, C.byref(bt)))
+        return OwnedBatch(bt)
 
     def close(self):
         if self._h:

@@ -92,7 +92,7 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
             the queue is sorted largest first) and rebound -- same device buffers -- for the rest (gromgpu_chr_rebind)"""
             name = names[t].lower()
             chars = fasta[name]
-            batch = lane_bam.read_target(t)                                 # decoded just before it is pushed, dropped right after
+            batch = lane_bam.read_target_owned(t)                           # decoded just before it is pushed (the batcher's own memory goes to the CUDA library), dropped right after
             if slot[0] is None or not slot[0].rebind(t, chars):
                 if slot[0] is not None:
                     slot[0].close(); inflight.release(slot[1]); slot[0] = None
@@ -103,7 +103,7 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
             ch = slot[0]
             with bus:
                 ch.push_reads(batch); ch.sync()
-            del batch
+            batch.free()
             res = ch.finish()
             cnv = ch.cnv(params=prm)
             text[t] = hostlib.vcf_contig(prm, name, chars, res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, cnv.calls)

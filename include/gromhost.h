@@ -38,8 +38,15 @@ int64_t gromhost_bam_target_len(const grom_bam *b, int tid);
 int  gromhost_bam_has_index(const grom_bam *b);
 
 /* decode every record of target `tid` (BAM order) into a new batch.
- * keep_names != 0 also fills qname_off/qname_pool.  n_threads <= 0: OpenMP default. */
+ * keep_names != 0 also fills qname_off/qname_pool.  n_threads <= 0: OpenMP default.
+ * The BGZF blocks of the target are inflated block-parallel by the library's own DEFLATE decoder (grom_b200/host/inflate.c; a block it
+ * refuses goes to zlib; GROMHOST_INFLATE=zlib sends every block there) and the CRC-32 of every block is verified.  GROMHOST_TRACE=1
+ * prints the phase times.  Replaces the record-at-a-time read supply of the reference (samread over bgzf/zlib, src/GROM.c:981-992). */
 int  gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out);
+
+/* One raw DEFLATE stream (RFC 1951, e.g. the payload of a BGZF block) of known output size through the library's own decoder, without
+ * the zlib second opinion: 0 = well formed and exactly dst_len bytes produced, -1 otherwise.  Test / tooling entry. */
+int  gromhost_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len);
 
 /* view of an owned batch; pointers stay valid until gromhost_batch_free() */
 void gromhost_batch_view(const grom_batch *bt, grom_read_batch *view);

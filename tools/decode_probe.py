@@ -25,8 +25,9 @@ best = None
 for _ in range(a.reps):
     t0 = time.perf_counter()
     with hostlib.Bam(stem + ".bam") as bf:
-        bt = bf.read_target(0, threads=a.threads)
+        bt = bf.read_target_owned(0, threads=a.threads)       # the product call: the batch stays in the batcher's memory
     dt = time.perf_counter() - t0
+    bt.free()
     best = dt if best is None else min(best, dt)
     print(f"{dt * 1e3:8.1f} ms  {bt.n_reads} reads", flush=True)
 print(f"best {best * 1e3:.1f} ms = {bt.n_reads / best / 1e6:.2f} M reads/s, BAM {os.path.getsize(stem + '.bam') / 1e6:.1f} MB")
