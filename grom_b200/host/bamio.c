@@ -222,8 +222,26 @@ struct grom_batch {
     uint32_t *cigar; uint8_t *seq4, *qual; char *qname_pool;
     /* transport-compact forms (grom_reads.h GROM_LAYOUT_*), built once the canonical arrays are filled */
     uint8_t *seq2, *seq_exc_code, *qual2; uint64_t *seq_exc_slot;
+    size_t big_seq4, big_qual, big_seq2, big_qual2;      /* lengths of the arrays that are zero-filled anonymous mappings (big_zalloc), 0 = malloc'd */
     uint8_t *qual4; int32_t *sa_index, *sas_pos, *sas_start_adj, *sas_end_adj, *sas_end_adj_indel; int16_t *sas_mapq; uint8_t *sas_strand, *sas_same_chr;
 };
+
+/* the large per-base arrays: zero-filled anonymous mappings, huge pages where the kernel grants them (far fewer page faults while the
+ * threads fill them); small ones come from calloc.  *len = 0 means "free() it". */
+static void *big_zalloc(size_t bytes, size_t *len)
+{
+    *len = 0;
+    if (bytes < ((size_t)8 << 20)) return calloc(bytes, 1);
+    const size_t n = (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    void *p = mmap(NULL, n, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return calloc(bytes, 1);
+#ifdef MADV_HUGEPAGE
+    if (!getenv("GROMHOST_NO_HUGEPAGE")) madvise(p, n, MADV_HUGEPAGE);
+#endif
+    *len = n;
+    return p;
+}
+static void big_free(void *p, size_t len) { if (!p) return; if (len) munmap(p, len); else free(p); }
 
 void gromhost_batch_view(const grom_batch *bt, grom_read_batch *view) { *view = bt->v; }
 
@@ -234,8 +252,8 @@ void gromhost_batch_free(grom_batch *t)
     free(t->sa_start_adj); free(t->sa_end_adj); free(t->sa_end_adj_indel); free(t->flag); free(t->n_cigar);
     free(t->sa_mapq); free(t->mapq); free(t->qname_len); free(t->sa_strand); free(t->sa_same_chr);
     free(t->qname_hash); free(t->cigar_off); free(t->base_off); free(t->qname_off); free(t->cigar);
-    free(t->seq4); free(t->qual); free(t->qname_pool);
-    free(t->seq2); free(t->seq_exc_code); free(t->seq_exc_slot); free(t->qual2);
+    big_free(t->seq4, t->big_seq4); big_free(t->qual, t->big_qual); free(t->qname_pool);
+    big_free(t->seq2, t->big_seq2); free(t->seq_exc_code); free(t->seq_exc_slot); big_free(t->qual2, t->big_qual2);
     free(t->qual4); free(t->sa_index); free(t->sas_pos); free(t->sas_start_adj); free(t->sas_end_adj); free(t->sas_end_adj_indel);
     free(t->sas_mapq); free(t->sas_strand); free(t->sas_same_chr); free(t);
 }
@@ -365,31 +383,154 @@ static int reclist_grow(reclist *r, int keep_names)
     return 0;
 }
 
-/* One pass over the record chain from offset p: validates the layout of every record of the target (a truncated or corrupt file must
- * not make the fill pass read past the inflated data) and lists them.  Returns 0, -1 (corrupt record, message set) or -2 (memory). */
-static int walk_records(const uint8_t *u, int64_t utotal, int64_t p, int tid, int keep_names, const char *path, reclist *r)
+/* One pass over the record chain from offset p up to (not including) offset `stop`: validates the layout of every record of the target
+ * (a truncated or corrupt file must not make the fill pass read past the inflated data) and lists them.  `started` says whether records
+ * of the target came before p.  Outcome in *term: 0 = arrived exactly at `stop`; 1 = the chain ended (end of data, a record past the
+ * target or in the unplaced tail); 2 = stepped over `stop` (it was no record boundary); 3 = corrupt record at *err_at; 4 = memory.
+ * *lead = the first record seen was not one of the target. */
+typedef struct { int term, lead; int64_t err_at; } walk_end;
+static void walk_records(const uint8_t *u, int64_t utotal, int64_t p, int64_t stop, int started, int tid, int keep_names, reclist *r, walk_end *w)
 {
-    int started = 0;
+    int first = 1;
+    w->term = 1; w->lead = 0; w->err_at = -1;
     while (p + 36 <= utotal) {
+        if (p >= stop) { w->term = (p == stop) ? 0 : 2; return; }
         const int32_t bl = rd_i32(u + p);
-        if (bl < 32 || p + 4 + bl > utotal) break;
+        if (bl < 32 || p + 4 + bl > utotal) return;
         const int32_t rtid = rd_i32(u + p + 4);
         if (rtid == tid) {
             started = 1;
             const uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16); const int32_t lq = rd_i32(u + p + 20);
-            if (lq < 0 || 32 + (int64_t)(bmq & 0xff) + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl)
-                return fail("%s: corrupt BAM record at uncompressed offset %lld (block_size %d cannot hold name %u + %u CIGAR ops + %d bases)",
-                            path, (long long)p, bl, bmq & 0xff, fnc & 0xffff, lq);
-            if (r->n == r->cap && reclist_grow(r, keep_names) < 0) return -2;
+            if (lq < 0 || 32 + (int64_t)(bmq & 0xff) + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl) { w->term = 3; w->err_at = p; return; }
+            if (r->n == r->cap && reclist_grow(r, keep_names) < 0) { w->term = 4; return; }
             r->recoff[r->n] = p; r->cig_off[r->n] = (uint64_t)r->n_cig; r->base_off[r->n] = (uint64_t)r->n_slots;
             if (keep_names) r->name_off[r->n] = (uint64_t)r->n_name;
             r->n++; r->n_cig += fnc & 0xffff; r->n_slots += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN; r->n_name += bmq & 0xff;
-        } else if (started || rtid > tid || rtid < 0) {
-            break;      /* coordinate-sorted: past the target (or into the unplaced tail) */
+        } else {
+            if (first) w->lead = 1;
+            if (started || rtid > tid || rtid < 0) return;      /* coordinate-sorted: past the target (or into the unplaced tail) */
         }
+        first = 0;
         p += 4 + bl;
     }
-    return 0;
+    if (p >= stop) w->term = (p == stop) ? 0 : 2;                /* the chain may end exactly where the next range begins */
+}
+
+static int corrupt_record(const char *path, const uint8_t *u, int64_t p)
+{
+    const uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16);
+    return fail("%s: corrupt BAM record at uncompressed offset %lld (block_size %d cannot hold name %u + %u CIGAR ops + %d bases)",
+                path, (long long)p, rd_i32(u + p), bmq & 0xff, fnc & 0xffff, rd_i32(u + p + 20));
+}
+
+/* does a well-formed record start at p?  (used to guess entry points into the chain; a guess is only kept when the walk of the range
+ * before it arrives exactly there) */
+static inline int record_plausible(const uint8_t *u, int64_t utotal, int64_t p, int n_targets)
+{
+    if (p + 36 > utotal) return 0;
+    const int32_t bl = rd_i32(u + p);
+    if (bl < 32 || bl > (1 << 24) || p + 4 + bl > utotal) return 0;
+    const int32_t rtid = rd_i32(u + p + 4), pos = rd_i32(u + p + 8), lq = rd_i32(u + p + 20), mtid = rd_i32(u + p + 24), mpos = rd_i32(u + p + 28);
+    if (rtid < -1 || rtid >= n_targets || mtid < -1 || mtid >= n_targets || pos < -1 || mpos < -1 || lq < 0) return 0;
+    const uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16);
+    const int l_qname = bmq & 0xff;
+    if (l_qname < 1 || 32 + (int64_t)l_qname + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl) return 0;
+    return u[p + 36 + l_qname - 1] == 0;
+}
+
+#define WALK_SYNC_CHAIN 8          /* consecutive plausible records that make an entry-point guess */
+#define WALK_PAR_MIN (8 << 20)     /* inflated bytes below which the chain is walked by one thread */
+
+/* The record chain of a target, listed by all threads: BAM records carry no synchronisation marks, so every thread but the first guesses
+ * an entry point (the first offset of its share at which WALK_SYNC_CHAIN plausible records follow one another) and walks from there; a
+ * guess counts only if the walk of the share before it arrives exactly at it, which makes it a boundary of the true chain by induction
+ * from the known first record.  Any miss falls back to the one-thread walk, so the result never depends on the guesses.
+ * Returns 0, -1 (corrupt record, message set) or -2 (memory); the lists of all shares are concatenated into *out. */
+static int walk_records_parallel(const uint8_t *u, int64_t utotal, int64_t p0, int tid, int n_targets, int keep_names, int n_threads,
+                                 const char *path, reclist *out)
+{
+    memset(out, 0, sizeof(*out));
+    int T = n_threads;
+    int64_t par_min = WALK_PAR_MIN;
+    { const char *e = getenv("GROMHOST_WALK_PAR_MIN"); if (e && *e) par_min = atoll(e); }      /* tests: force / forbid the all-thread walk */
+    if (utotal - p0 < par_min || T < 2) T = 1;
+    if (T > 64) T = 64;
+    reclist rl[64]; walk_end we[64]; int64_t start[65];
+    memset(rl, 0, sizeof(reclist) * (size_t)T);
+    int rc = 0, n_used = 0;
+    if (T > 1) {
+        start[0] = p0; start[T] = INT64_MAX;
+        #pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int k = 1; k < T; k++) {
+            const int64_t g = p0 + (utotal - p0) / T * k, lim = p0 + (utotal - p0) / T * (k + 1);
+            int64_t found = -1;
+            for (int64_t q = g; q < lim && found < 0; q++) {
+                if (!record_plausible(u, utotal, q, n_targets)) continue;
+                int64_t c = q; int ok = 1;
+                for (int j = 0; j < WALK_SYNC_CHAIN && ok; j++) {
+                    c += 4 + (int64_t)rd_i32(u + c);
+                    if (c + 36 > utotal) break;                   /* the data end inside the chain: nothing left to contradict the guess */
+                    ok = record_plausible(u, utotal, c, n_targets);
+                }
+                if (ok) found = q;
+            }
+            start[k] = found;
+        }
+        for (int k = T - 1; k >= 1; k--) if (start[k] < 0) start[k] = start[k + 1];      /* a share without an entry point joins the one before it */
+        int grow_bad = 0;
+        #pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int k = 0; k < T; k++) {
+            if (reclist_grow(&rl[k], keep_names) < 0) { we[k].term = 4; grow_bad = 1; continue; }
+            if (k > 0 && start[k] == start[k + 1]) { we[k].term = 0; we[k].lead = 0; we[k].err_at = -1; continue; }    /* empty share */
+            walk_records(u, utotal, start[k], start[k + 1], 0, tid, keep_names, &rl[k], &we[k]);
+        }
+        /* which shares are on the true chain: the first is; a share is reached when the one before arrived exactly at its start */
+        int started = 0, fallback = grow_bad;
+        for (int k = 0; k < T && !fallback; k++) {
+            if (started && we[k].lead && !(k > 0 && start[k] == start[k + 1])) break;          /* a foreign record after the target began ends the chain */
+            if (we[k].term == 2 || we[k].term == 4) { fallback = 1; break; }
+            n_used = k + 1;
+            if (rl[k].n) started = 1;
+            if (we[k].term == 3) { rc = corrupt_record(path, u, we[k].err_at); break; }
+            if (we[k].term == 1) break;
+            /* a share that began after records of the target (started) but met a foreign record first was handled above; one that began
+             * before the target and skipped foreign records is what the one-thread walk does as well */
+        }
+        if (getenv("GROMHOST_TRACE")) fprintf(stderr, "[bamio] record chain: %d shares, %d on the chain, fallback=%d\n", T, n_used, fallback);
+        if (fallback) { for (int k = 0; k < T; k++) { free(rl[k].recoff); free(rl[k].cig_off); free(rl[k].base_off); free(rl[k].name_off); } memset(rl, 0, sizeof(reclist) * (size_t)T); T = 1; n_used = 0; rc = 0; }
+    }
+    if (T == 1) {
+        if (reclist_grow(&rl[0], keep_names) < 0) { free(rl[0].recoff); free(rl[0].cig_off); free(rl[0].base_off); free(rl[0].name_off); return -2; }
+        walk_records(u, utotal, p0, INT64_MAX, 0, tid, keep_names, &rl[0], &we[0]);
+        if (we[0].term == 3) rc = corrupt_record(path, u, we[0].err_at);
+        else if (we[0].term == 4) rc = -2;
+        if (rc == 0) { *out = rl[0]; return 0; }
+        free(rl[0].recoff); free(rl[0].cig_off); free(rl[0].base_off); free(rl[0].name_off);
+        return rc;
+    }
+    if (rc == 0) {
+        int64_t base_n[65], base_c[65], base_s[65], base_m[65];
+        base_n[0] = base_c[0] = base_s[0] = base_m[0] = 0;
+        for (int k = 0; k < n_used; k++) { base_n[k + 1] = base_n[k] + rl[k].n; base_c[k + 1] = base_c[k] + rl[k].n_cig; base_s[k + 1] = base_s[k] + rl[k].n_slots; base_m[k + 1] = base_m[k] + rl[k].n_name; }
+        const int64_t n = base_n[n_used];
+        out->n = n; out->cap = n > 0 ? n : 1; out->n_cig = base_c[n_used]; out->n_slots = base_s[n_used]; out->n_name = base_m[n_used];
+        out->recoff = (int64_t *)malloc(sizeof(int64_t) * (size_t)out->cap); out->cig_off = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)out->cap);
+        out->base_off = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)out->cap);
+        out->name_off = keep_names ? (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(out->cap + 1)) : NULL;
+        if (!out->recoff || !out->cig_off || !out->base_off || (keep_names && !out->name_off)) {
+            free(out->recoff); free(out->cig_off); free(out->base_off); free(out->name_off); memset(out, 0, sizeof(*out)); rc = -2;
+        } else {
+            #pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int k = 0; k < n_used; k++) {
+                const int64_t o = base_n[k]; const uint64_t c = (uint64_t)base_c[k], sl = (uint64_t)base_s[k], m = (uint64_t)base_m[k];
+                memcpy(out->recoff + o, rl[k].recoff, sizeof(int64_t) * (size_t)rl[k].n);
+                for (int64_t i = 0; i < rl[k].n; i++) { out->cig_off[o + i] = rl[k].cig_off[i] + c; out->base_off[o + i] = rl[k].base_off[i] + sl; }
+                if (keep_names) for (int64_t i = 0; i < rl[k].n; i++) out->name_off[o + i] = rl[k].name_off[i] + m;
+            }
+        }
+    }
+    for (int k = 0; k < T; k++) { free(rl[k].recoff); free(rl[k].cig_off); free(rl[k].base_off); free(rl[k].name_off); }
+    return rc;
 }
 
 int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out)
@@ -429,8 +570,13 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     for (int64_t i = 0; i < nblk; i++) { blk[i].uoff = utotal; utotal += blk[i].isize; }
     TRACE_MARK("enumerate blocks");
     /* 2. inflate in parallel, every block straight to its place in the inflated stream */
-    uint8_t *u = (uint8_t *)malloc((size_t)utotal + 64);
-    if (!u) { free(blk); return fail("out of memory (%lld bytes of inflated BAM)", (long long)utotal); }
+    /* (anonymous mapping with huge pages where the kernel grants them: far fewer page faults while the blocks land, and a cheap unmap) */
+    const size_t u_len = ((size_t)utotal + 64 + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    uint8_t *u = (uint8_t *)mmap(NULL, u_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (u == (uint8_t *)MAP_FAILED) { free(blk); return fail("out of memory (%lld bytes of inflated BAM)", (long long)utotal); }
+#ifdef MADV_HUGEPAGE
+    if (!getenv("GROMHOST_NO_HUGEPAGE")) madvise(u, u_len, MADV_HUGEPAGE);
+#endif
     int bad = 0;
     const char *force = getenv("GROMHOST_INFLATE");
     const int own = !(force && !strcmp(force, "zlib"));            /* GROMHOST_INFLATE=zlib: every block through zlib */
@@ -449,14 +595,13 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         free(ctx);
     }
     free(blk);
-    if (bad) { free(u); return fail("%s: BGZF inflate failed (corrupt deflate stream or CRC mismatch)", b->path); }
+    if (bad) { munmap(u, u_len); return fail("%s: BGZF inflate failed (corrupt deflate stream or CRC mismatch)", b->path); }
     TRACE_MARK("inflate");
     /* 3. the record chain: count, validate, offsets */
-    reclist rl; memset(&rl, 0, sizeof(rl));
-    int wrc = reclist_grow(&rl, keep_names);
-    if (wrc == 0) wrc = walk_records(u, utotal, (nblk > 0) ? (int64_t)(vbeg & 0xffff) : 0, tid, keep_names, b->path, &rl);
+    reclist rl;
+    const int wrc = walk_records_parallel(u, utotal, (nblk > 0) ? (int64_t)(vbeg & 0xffff) : 0, tid, b->n_targets, keep_names, n_threads, b->path, &rl);
     if (wrc < 0) {
-        free(rl.recoff); free(rl.cig_off); free(rl.base_off); free(rl.name_off); free(u);
+        munmap(u, u_len);
         return wrc == -2 ? fail("out of memory (record list)") : -1;
     }
     const int64_t n_reads = rl.n, n_cig = rl.n_cig, n_slots = rl.n_slots, n_name = rl.n_name;
@@ -473,7 +618,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     AL(mapq, uint8_t, nr); AL(qname_len, uint8_t, nr); AL(sa_strand, uint8_t, nr); AL(sa_same_chr, uint8_t, nr);
     AL(qname_hash, uint64_t, nr);
     AL(cigar, uint32_t, (size_t)(n_cig > 0 ? n_cig : 1));
-    AL(seq4, uint8_t, (size_t)(n_slots / 2 + 16)); AL(qual, uint8_t, (size_t)(n_slots + 16));
+    t->seq4 = (uint8_t *)big_zalloc((size_t)(n_slots / 2 + 16), &t->big_seq4); t->qual = (uint8_t *)big_zalloc((size_t)(n_slots + 16), &t->big_qual);
     if (keep_names) AL(qname_pool, char, (size_t)(n_name + 1));
     t->cigar_off = rl.cig_off; t->base_off = rl.base_off; t->qname_off = rl.name_off;
     /* transport-compact forms (include/grom_reads.h GROM_LAYOUT_*), all lossless; the CUDA library rebuilds the canonical device arrays.
@@ -482,7 +627,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
      * first-SA-entry fields exist for a small minority of reads. */
     const int64_t ns = n_slots;
     int64_t *exc_at = NULL;
-    if (ns > 0) { AL(seq2, uint8_t, (size_t)(ns / 4 + 16)); exc_at = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_reads + 1)); }
+    if (ns > 0) { t->seq2 = (uint8_t *)big_zalloc((size_t)(ns / 4 + 16), &t->big_seq2); exc_at = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_reads + 1)); }
 #undef AL
     TRACE_MARK("allocate");
     /* 5. fill, parallel over contiguous ranges of reads.  In the same pass over a record: the 2-bit form of its bases (table-driven, two
@@ -566,7 +711,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     int nv = 0, qmode = 0; uint8_t inv[256]; memset(inv, 0, sizeof(inv));
     if (ns > 0) {
         for (int k = 0; k < 256; k++) if (hist[k]) { if (nv < 16) { v->qual_lut[nv] = (uint8_t)k; inv[k] = (uint8_t)nv; } nv++; }
-        if (nv >= 1 && nv <= 4 && (t->qual2 = (uint8_t *)calloc((size_t)(ns / 4 + 16), 1))) qmode = 2;
+        if (nv >= 1 && nv <= 4 && (t->qual2 = (uint8_t *)big_zalloc((size_t)(ns / 4 + 16), &t->big_qual2))) qmode = 2;
         else if (nv >= 1 && nv <= 16 && !hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
             /* 4-bit form: padding slots (0 in the canonical array) must decode to 0 as well, so 0 takes a dictionary entry */
             if (nv == 16) { free(t->qual4); t->qual4 = NULL; memset(v->qual_lut, 0, 16); }
@@ -601,7 +746,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     {
         /* the inflated stream is no longer needed: unmapping it takes one thread a while, the others start on the packing */
         #pragma omp single nowait
-        free(u);
+        munmap(u, u_len);
         if (qmode == 2) {
             #pragma omp for schedule(dynamic, 1 << 16) nowait
             for (int64_t s = 0; s < ns; s += 4) t->qual2[s >> 2] = (uint8_t)((inv[t->qual[s]] << 6) | (inv[t->qual[s + 1]] << 4) | (inv[t->qual[s + 2]] << 2) | inv[t->qual[s + 3]]);

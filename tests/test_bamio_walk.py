@@ -1,0 +1,116 @@
+"""The batcher lists the records of a target with all threads: entry points into the record chain are guessed and kept only when the walk
+of the share before arrives exactly at them (grom_b200/host/bamio.c walk_records_parallel).  The result must not depend on the guesses:
+forced on small files here (GROMHOST_WALK_PAR_MIN=1), with and without index, and on a file whose base qualities are built to look like
+chains of records (every guess wrong -> the one-thread walk takes over)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from grom_b200 import hostlib
+from grom_b200.reads import _DTYPES
+from tools import synth
+
+FIELDS = list(_DTYPES) + ["seq2", "qual2", "sa_index", "seq_exc_slot", "seq_exc_code"]
+
+
+def same(a, b):
+    assert a.n_reads == b.n_reads and a.layout_flags == b.layout_flags
+    for k in FIELDS:
+        x, y = getattr(a, k), getattr(b, k)
+        assert (x is None and y is None) or np.array_equal(x, y), k
+    assert np.array_equal(a.qname_off, b.qname_off) and np.array_equal(a.qname_pool, b.qname_pool)
+
+
+def read_all(bam, monkeypatch, par_min, threads):
+    monkeypatch.setenv("GROMHOST_WALK_PAR_MIN", str(par_min))
+    with hostlib.Bam(bam) as b:
+        return [b.read_target(t, keep_names=True, threads=threads) for t in range(len(b.names))]
+
+
+@pytest.mark.parametrize("indexed", [True, False])
+def test_all_thread_walk_equals_the_one_thread_walk(tmp_path, monkeypatch, capfd, indexed):
+    spec = synth.SynthSpec(contigs=[("c1", 60_000), ("c2", 150_000), ("c3", 40_000)], depth=15, seed=21, dup_frac=0.05, clip_frac=0.05, sa_frac=0.8, disc_frac=0.03)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "w"), cs)
+    if not indexed:
+        os.remove(bam + ".bai")          # every target then starts at the first record of the file: foreign records lead, and follow
+    one = read_all(bam, monkeypatch, 1 << 60, 4)
+    monkeypatch.setenv("GROMHOST_TRACE", "1")
+    for threads in (2, 4, 7):
+        capfd.readouterr()
+        par = read_all(bam, monkeypatch, 1, threads)
+        err = capfd.readouterr().err
+        assert f"record chain: {threads} shares" in err and "fallback=1" not in err
+        for a, b in zip(one, par):
+            same(a, b)
+    for c, a in zip(cs, one):
+        assert a.n_reads == c.batch.n_reads and np.array_equal(a.pos, c.batch.pos)
+
+
+def test_wrong_guesses_fall_back_to_the_one_thread_walk(tmp_path, monkeypatch, capfd):
+    """Base qualities that spell chains of well-formed records: a thread that starts looking inside a read finds the forged chain before the
+    next real record; the share before it steps over that offset, and the walk is redone by one thread."""
+    spec = synth.SynthSpec(contigs=[("c1", 120_000)], depth=12, seed=22, read_len=400, ins_mean=1000.0, ins_sd=60.0, ins_floor=500, clip_frac=0.0,
+                           hardclip_frac=0.0, indel_every=10 ** 9, refskip_frac=0.0, sv_sites_per_mb=0.0, disc_frac=0.0)
+    cs = synth.simulate(spec)
+    bt = cs[0].batch
+    fake = b""
+    for j in range(9):                   # nine forged records of 40 bytes: block_size 36, tid 0, pos j, l_read_name 2, no CIGAR, no bases, name "x\0"
+        fake += struct.pack("<iiiIIiiii", 36, 0, j, (4680 << 16) | (30 << 8) | 2, 0, 0, -1, -1, 0) + b"x\0\0\0"
+    fake = np.frombuffer(fake, dtype=np.uint8)
+    n_forged = 0
+    for i in range(bt.n_reads):
+        lq, o = int(bt.l_qseq[i]), int(bt.base_off[i])
+        if lq >= len(fake) + 8:
+            bt.qual[o + 4:o + 4 + len(fake)] = fake
+            n_forged += 1
+    assert n_forged > 0.9 * bt.n_reads
+    fa, bam = synth.write_dataset(str(tmp_path / "f"), cs)
+    one = read_all(bam, monkeypatch, 1 << 60, 4)
+    monkeypatch.setenv("GROMHOST_TRACE", "1")
+    capfd.readouterr()
+    par = read_all(bam, monkeypatch, 1, 7)           # six guesses, each inside a read with probability ~0.4 of coming before its forged chain
+    assert "fallback=1" in capfd.readouterr().err
+    same(one[0], par[0])
+    assert one[0].n_reads == bt.n_reads and np.array_equal(one[0].qual, bt.qual)
+
+
+def test_corrupt_record_is_reported_by_the_all_thread_walk(tmp_path, monkeypatch):
+    spec = synth.SynthSpec(contigs=[("c1", 100_000)], depth=12, seed=23)
+    cs = synth.simulate(spec)
+    bt = cs[0].batch
+    fa, bam = synth.write_dataset(str(tmp_path / "c"), cs)
+    # rewrite the file with l_seq of one record in the middle raised beyond its block_size (level-0 BGZF keeps the offsets simple)
+    import zlib
+    raw = open(bam, "rb").read()
+    off, data = 0, b""
+    while off + 18 <= len(raw):
+        bs = struct.unpack_from("<H", raw, off + 16)[0] + 1
+        data += zlib.decompressobj(-15).decompress(raw[off + 18:off + bs - 8]); off += bs
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, p)[0]; p += 4
+    for _ in range(n_ref):
+        ln = struct.unpack_from("<i", data, p)[0]; p += 4 + ln + 4
+    recs = []
+    while p + 4 <= len(data):
+        bl = struct.unpack_from("<i", data, p)[0]; recs.append(p); p += 4 + bl
+    victim = recs[len(recs) * 2 // 3]
+    data = bytearray(data)
+    struct.pack_into("<i", data, victim + 20, 100_000)
+
+    def bgzf(chunk):
+        co = zlib.compressobj(1, zlib.DEFLATED, -15)
+        d = co.compress(bytes(chunk)) + co.flush()
+        return (b"\x1f\x8b\x08\x04" + b"\0" * 6 + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(d) + 25) + d
+                + struct.pack("<II", zlib.crc32(bytes(chunk)), len(chunk)))
+    out = b"".join(bgzf(data[i:i + 60000]) for i in range(0, len(data), 60000)) + bgzf(b"")
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(out)
+    for par_min in (1, 1 << 60):
+        monkeypatch.setenv("GROMHOST_WALK_PAR_MIN", str(par_min))
+        with hostlib.Bam(str(bad)) as b:
+            with pytest.raises(RuntimeError, match="corrupt BAM record"):
+                b.read_target(0, threads=4)
