@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--depth", type=float, default=30.0)
     ap.add_argument("--cpu-sample-mb", type=float, default=1.5, help="contig length of each CPU-baseline sample contig")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="N > 1: do not give every rank its own cores near its GPU (bind_rank_to_cores)")
     ap.add_argument("--lanes", type=int, default=3, help="contigs in flight in the end-to-end measurement")
     ap.add_argument("--canonical-upload", action="store_true", help="upload the canonical arrays only (no transport-compact forms)")
     ap.add_argument("--parity-mb", type=float, default=4.0, help="length of the contig (same generator) checked against the oracle after the timed loops; 0 = skip")
@@ -255,6 +256,69 @@ def pin_batch(batch):
     return out, keep, out.transport_bytes()
 
 
+def _cpulist(text):
+    out = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        out.update(range(int(lo), int(hi or lo) + 1))
+    return out
+
+
+def plan_cores(allowed, gpu_nodes, node_cpus, local):
+    """Cores of local rank `local`: `allowed` = cores this process may use, gpu_nodes[i] = NUMA node of local rank i's GPU (-1 unknown),
+    node_cpus[n] = cores of NUMA node n.  Ranks whose GPUs share a node split that node's allowed cores evenly; when a node offers fewer than
+    two allowed cores per rank (or is unknown) all allowed cores are split by local rank instead.  Returns (cores, node, ranks sharing)."""
+    allowed = sorted(allowed)
+    mine = gpu_nodes[local]
+    pool, peers = allowed, list(range(len(gpu_nodes)))
+    if mine >= 0:
+        on_node = sorted(set(node_cpus.get(mine, ())) & set(allowed))
+        sharing = [i for i in range(len(gpu_nodes)) if gpu_nodes[i] == mine]
+        # every rank must come to the same decision, so the rule may only depend on its own node's numbers when all nodes pass it
+        ok = all(len(set(node_cpus.get(n, ())) & set(allowed)) >= 2 * sum(1 for x in gpu_nodes if x == n) for n in set(gpu_nodes) if n >= 0) and all(n >= 0 for n in gpu_nodes)
+        if ok:
+            pool, peers = on_node, sharing
+    k, n = peers.index(local), len(peers)
+    return pool[len(pool) * k // n:len(pool) * (k + 1) // n], mine, n
+
+
+def bind_rank_to_cores(local: int, local_world: int):
+    """N > 1 ranks on one node: give every rank its own cores, on the NUMA node its GPU hangs off where the process is allowed there.
+    The ranks share nothing on the data path but the host: without this the lane / OpenMP / CNV host threads of all ranks migrate over all
+    cores, and the pinned upload buffers (first touched by this process) may sit on the other socket from the GPU's PCIe root.  Returns a
+    description for the JSON line, or None (one rank, no sysfs, a refused affinity call: nothing is changed then)."""
+    if local_world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import torch
+
+        def gpu_node(i):
+            pr = torch.cuda.get_device_properties(i % max(1, torch.cuda.device_count()))
+            bus = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{getattr(pr, 'pci_device_id', 0):02x}.0"
+            try:
+                return int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+            except OSError:
+                return -1
+        nodes = [gpu_node(i) for i in range(local_world)]
+        node_cpus = {}
+        for n in set(nodes):
+            if n >= 0:
+                try:
+                    node_cpus[n] = _cpulist(open(f"/sys/devices/system/node/node{n}/cpulist").read())
+                except OSError:
+                    node_cpus[n] = set()
+        share, mine, n = plan_cores(os.sched_getaffinity(0), nodes, node_cpus, local)
+        if len(share) < 2:
+            return None
+        os.sched_setaffinity(0, share)
+        return {"cpus": f"{share[0]}-{share[-1]}" if share == list(range(share[0], share[-1] + 1)) else ",".join(map(str, share)),
+                "n_cpus": len(share), "gpu_numa_node": mine, "ranks_sharing_the_pool": n}
+    except Exception as e:                                   # binding is an optimisation, never a reason to fail the run
+        return {"error": str(e)[:120]}
+
+
 def main_b200(a):
     import torch
     import torch.distributed as dist
@@ -269,7 +333,11 @@ def main_b200(a):
     # host threads per gromgpu_chr_cnv call: the node's cores shared by the ranks of the node (the contigs in flight of one rank are rarely in
     # their host stages at the same time)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("GROMGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // max(1, local_world))))
+    binding = None if a.no_bind else bind_rank_to_cores(local, local_world)
+    n_mine = binding.get("n_cpus") if binding else None
+    os.environ.setdefault("GROMGPU_HOST_THREADS", str(n_mine or max(2, (os.cpu_count() or 2) // max(1, local_world))))
+    if n_mine:
+        os.environ.setdefault("OMP_NUM_THREADS", str(n_mine))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -483,7 +551,7 @@ def main_b200(a):
             "warmup": max(3, a.warmup), "ms_per_step": ms_steps_max / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": bench_config(a),
-            "run": {"reads_per_gpu": int(st.n_reads), "aligned_bases_per_gpu": bases, "host_gen_s": round(gen_s, 1)},
+            "run": {"reads_per_gpu": int(st.n_reads), "aligned_bases_per_gpu": bases, "host_gen_s": round(gen_s, 1), "host_cores_rank0": binding},
             "e2e": {"value": total_bases * a.steps / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(read_bytes + P),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_max / a.steps,
                     "upload_form": ("canonical arrays" if not pinned.layout_flags else "transport-compact (include/grom_reads.h GROM_LAYOUT_*): "

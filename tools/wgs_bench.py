@@ -78,7 +78,10 @@ def main_wgs(a, emit) -> int:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("GROMGPU_HOST_THREADS", str(max(2, (os.cpu_count() or 2) // max(1, local_world))))
+    from bench import bind_rank_to_cores
+    binding = None if getattr(a, "no_bind", False) else bind_rank_to_cores(local, local_world)      # own cores per rank, near its GPU
+    n_mine = binding.get("n_cpus") if binding else None
+    os.environ.setdefault("GROMGPU_HOST_THREADS", str(n_mine or max(2, (os.cpu_count() or 2) // max(1, local_world))))
     ndev = torch.cuda.device_count()
     dev = local % ndev                                              # (tests run two ranks on one GPU)
     torch.cuda.set_device(dev)
@@ -254,7 +257,7 @@ def main_wgs(a, emit) -> int:
             "genome_digest": digest, "records": int(sum(v["records"] for v in per.values())),
             "results": {"snv_candidates": int(sum(v["snv"] for v in per.values())), "cnv_calls": int(sum(v["cnv_calls"] for v in per.values())),
                         "sv_events": int(sum(v["sv_events"] for v in per.values())), "reads": int(sum(v["reads"] for v in per.values()))},
-            "run": {"host_gen_s": [r["gen_s"] for r in rows], "lanes": n_lanes},
+            "run": {"host_gen_s": [r["gen_s"] for r in rows], "lanes": n_lanes, "host_cores_rank0": binding},
             "clocks": clocks,
         }
         emit(json.dumps(line))
