@@ -29,6 +29,12 @@ static int fail(const char *fmt, ...)
     va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
     return -1;
 }
+/* the same for the other files of the library (not part of the public header) */
+int gromhost_fail(const char *fmt, ...)
+{
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return -1;
+}
 
 /* ------------------------------------------------------------------ BAM open */
 

@@ -32,6 +32,16 @@ def lib() -> C.CDLL:
         L.gromhost_bam_read_target.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.gromhost_batch_view.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
         L.gromhost_batch_free.argtypes = [C.c_void_p]
+        L.gromhost_fasta_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.gromhost_fasta_close.argtypes = [C.c_void_p]
+        L.gromhost_fasta_n.argtypes = [C.c_void_p]
+        L.gromhost_fasta_name.argtypes = [C.c_void_p, C.c_int]
+        L.gromhost_fasta_name.restype = C.c_char_p
+        L.gromhost_fasta_find.argtypes = [C.c_void_p, C.c_char_p]
+        L.gromhost_fasta_raw_bytes.argtypes = [C.c_void_p, C.c_int]
+        L.gromhost_fasta_raw_bytes.restype = C.c_int64
+        L.gromhost_fasta_load.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+        L.gromhost_fasta_load.restype = C.c_int64
         L.gromhost_bam_write.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_int64), C.c_int,
                                          C.POINTER(CReadBatch), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int]
         _LIB = L
@@ -113,6 +123,41 @@ class Bam:
     def close(self):
         if self._h:
             lib().gromhost_bam_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class Fasta:
+    """An indexed reference FASTA (gromhost_fasta_*): `names` are the reference's contig names (first word of the header, lower-cased,
+    at most 49 characters); `load(k)` returns the characters of contig k, case preserved, one contig in memory at a time."""
+
+    def __init__(self, path: str):
+        self._h = C.c_void_p()
+        _check(lib().gromhost_fasta_open(path.encode(), C.byref(self._h)))
+        n = lib().gromhost_fasta_n(self._h)
+        self.names = [lib().gromhost_fasta_name(self._h, k).decode("latin-1") for k in range(n)]
+
+    def find(self, name: str) -> int:
+        return int(lib().gromhost_fasta_find(self._h, name.encode("latin-1")))
+
+    def load(self, k: int) -> np.ndarray:
+        cap = int(lib().gromhost_fasta_raw_bytes(self._h, k))
+        if cap < 0:
+            raise IndexError(k)
+        buf = np.empty(max(cap, 1), dtype=np.uint8)
+        n = int(lib().gromhost_fasta_load(self._h, k, buf.ctypes.data, cap))
+        if n < 0:
+            raise RuntimeError(lib().gromhost_last_error().decode())
+        return buf[:n] if n == cap else buf[:n].copy()
+
+    def close(self):
+        if self._h:
+            lib().gromhost_fasta_close(self._h)
             self._h = C.c_void_p()
 
     def __enter__(self):

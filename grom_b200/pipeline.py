@@ -38,6 +38,31 @@ def read_fasta(path: str) -> Dict[str, np.ndarray]:
     return out
 
 
+class _LazyFasta:
+    """name (lower case) -> characters, one contig at a time through libgromhost's FASTA reader (gromhost_fasta_*, the reference's line
+    rules); gzip-compressed files go through the Python reader above, whole."""
+
+    def __init__(self, path: str):
+        self._all = None
+        if path.endswith(".gz"):
+            self._all = {k.lower(): v for k, v in read_fasta(path).items()}
+        else:
+            self._fa = hostlib.Fasta(path)
+            self._lock = threading.Lock()
+
+    def __contains__(self, name: str) -> bool:
+        return (name in self._all) if self._all is not None else self._fa.find(name) >= 0
+
+    def __getitem__(self, name: str) -> np.ndarray:
+        if self._all is not None:
+            return self._all[name]
+        with self._lock:
+            k = self._fa.find(name)
+            if k < 0:
+                raise KeyError(name)
+            return self._fa.load(k)
+
+
 class _InFlight:
     """Admission control for the contigs in flight on one GPU: a contig starts when a lane is free and the device memory its handle
     will hold (gromgpu_chr_bytes_estimate) fits beside the ones already running; a contig that fits nowhere runs alone."""
@@ -65,7 +90,7 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
     Up to `lanes` contigs are in flight on the GPU (one host thread and one stream each; uploads take turns on the PCIe link), so the
     upload of one contig overlaps the kernels and the host stages of the others; results do not depend on `lanes`."""
     prm = params if params is not None else Params.default()
-    fasta = {k.lower(): v for k, v in read_fasta(fasta_path).items()}
+    fasta = _LazyFasta(fasta_path)          # contig characters are loaded (by the C library) when a lane takes the contig, not all up front
     with hostlib.Bam(bam_path) as bam:
         # library statistics first (find_insert_mean, src/GROM.c:1205-1318): the contigs stream through one at a time until the sample is full
         st = hostlib.library_stats((bam.read_target(t) for t in range(len(bam.names))), prm.min_mapq)
@@ -75,9 +100,6 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
         hez, mq = hostlib.tables(table_dir, prm.min_mapq)
         gpu.init(device, hez, mq, prm)
         todo = [t for t, n in enumerate(bam.names) if n.lower() in fasta and not skip_contig(n, prm.gender)]
-        for t in todo:
-            if len(fasta[bam.names[t].lower()]) != bam.lens[t]:
-                raise ValueError(f"{bam.names[t]}: {len(fasta[bam.names[t].lower()])} bases in the FASTA, {bam.lens[t]} in the BAM header")
         mine = set(todo[i] for i in assign_contigs([bam.lens[t] for t in todo], ranks)[rank])
         text: Dict[int, str] = {}
         work = [t for t in todo if t in mine]
@@ -92,6 +114,8 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
             the queue is sorted largest first) and rebound -- same device buffers -- for the rest (gromgpu_chr_rebind)"""
             name = names[t].lower()
             chars = fasta[name]
+            if len(chars) != lens[t]:
+                raise ValueError(f"{names[t]}: {len(chars)} bases in the FASTA, {lens[t]} in the BAM header")
             batch = lane_bam.read_target_owned(t)                           # decoded just before it is pushed (the batcher's own memory goes to the CUDA library), dropped right after
             if slot[0] is None or not slot[0].rebind(t, chars):
                 if slot[0] is not None:

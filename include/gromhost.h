@@ -61,6 +61,20 @@ int  gromhost_bam_write(const char *path, int n_targets, const char *const *name
                         const uint64_t *const *aux_off, const uint8_t *const *aux_pool, int level);
 
 
+/* ---- reference FASTA (reference src/GROM.c:1332-1417 index pass, 21011-21045 load of one contig) ----
+ * open() maps the file and lists the contigs: name = first word of the header, lower-cased, at most 49 characters (what the reference
+ * keeps and matches BAM target names against).  load() writes the characters of contig k (case preserved, line ends removed by the
+ * reference's own rule: every line is cut behind its last alphabetic character, the cut being re-evaluated only when the line length
+ * changes) and returns their number, or -1 (cap too small: raw_bytes() is an upper bound of the length). */
+typedef struct grom_fasta grom_fasta;
+int  gromhost_fasta_open(const char *path, grom_fasta **out);
+void gromhost_fasta_close(grom_fasta *fa);
+int  gromhost_fasta_n(const grom_fasta *fa);
+const char *gromhost_fasta_name(const grom_fasta *fa, int k);
+int  gromhost_fasta_find(const grom_fasta *fa, const char *name);          /* case-insensitive; -1 = absent */
+int64_t gromhost_fasta_raw_bytes(const grom_fasta *fa, int k);
+int64_t gromhost_fasta_load(const grom_fasta *fa, int k, char *dst, int64_t cap);
+
 /* ---- statistics tables (reference src/GROM.c:21134-21626, 20705-20748) ----
  * hez / mq: row-major double[1001*1001].  _get() mirrors the reference: load
  * "<dir>/GROM_hez_binom_table_1000.txt" / "<dir>/GROM_mq_binom_table_<max(q,10)>_1000.txt"

@@ -88,58 +88,20 @@ static void ctx_name(const char *out, char *dst, size_t cap)
 }
 
 /* ------------------------------------------------------------------------------------------------ FASTA */
-typedef struct { char *name; int64_t hdr_off, seq_off, seq_end; } fa_entry;    /* name lower-cased (first word of the header) */
-typedef struct { char *path; fa_entry *e; int n; } fa_index;
+/* index and per-contig load are libgromhost's (gromhost_fasta_*: the reference's line rules, src/GROM.c:1332-1417 and 21011-21045) */
+typedef grom_fasta fa_index;
 
-static void fasta_index(const char *path, fa_index *ix)
-{
-    FILE *f = fopen(path, "rb");
-    if (!f) die("\nCould not open %s", path);
-    ix->path = strdup(path); ix->e = NULL; ix->n = 0;
-    const size_t CH = 1 << 22;
-    char *buf = (char *)malloc(CH);
-    int64_t off = 0; int at_line_start = 1, in_hdr = 0, cap = 0; size_t nl = 0; char name[1024];
-    size_t got;
-    while ((got = fread(buf, 1, CH, f)) > 0) {
-        for (size_t i = 0; i < got; i++) {
-            const char c = buf[i];
-            if (in_hdr) {
-                if (c == '\n') {
-                    name[nl] = 0;
-                    char *sp = name; while (*sp && !isspace((unsigned char)*sp)) { *sp = (char)tolower((unsigned char)*sp); sp++; }
-                    *sp = 0;
-                    ix->e[ix->n - 1].name = strdup(name); ix->e[ix->n - 1].seq_off = off + (int64_t)i + 1; in_hdr = 0; at_line_start = 1;
-                } else if (nl + 1 < sizeof(name)) name[nl++] = c;
-                continue;
-            }
-            if (at_line_start && c == '>') {
-                if (ix->n) ix->e[ix->n - 1].seq_end = off + (int64_t)i;
-                if (ix->n == cap) { cap = cap ? 2 * cap : 64; ix->e = (fa_entry *)realloc(ix->e, sizeof(fa_entry) * cap); }
-                ix->e[ix->n].hdr_off = off + (int64_t)i; ix->e[ix->n].name = NULL; ix->e[ix->n].seq_off = ix->e[ix->n].seq_end = 0; ix->n++;
-                in_hdr = 1; nl = 0;
-                continue;
-            }
-            at_line_start = (c == '\n');
-        }
-        off += (int64_t)got;
-    }
-    if (ix->n) ix->e[ix->n - 1].seq_end = off;
-    free(buf); fclose(f);
-}
-static int fasta_find(const fa_index *ix, const char *lname) { for (int i = 0; i < ix->n; i++) if (ix->e[i].name && !strcmp(ix->e[i].name, lname)) return i; return -1; }
+static int fasta_find(const fa_index *ix, const char *lname) { return gromhost_fasta_find(ix, lname); }
 /* characters of one contig, line ends removed, case preserved (the hot path compares through toupper and tests 'N'/'n' literally) */
 static char *fasta_load(const fa_index *ix, int k, int64_t *len)
 {
-    FILE *f = fopen(ix->path, "rb");
-    if (!f) die("\nCould not open %s", ix->path);
-    const int64_t raw = ix->e[k].seq_end - ix->e[k].seq_off;
+    const int64_t raw = gromhost_fasta_raw_bytes(ix, k);
+    if (raw < 0) die("FASTA contig %d out of range", k);
     char *s = (char *)malloc((size_t)raw + 1);
-    fseeko(f, (off_t)ix->e[k].seq_off, SEEK_SET);
-    if ((int64_t)fread(s, 1, (size_t)raw, f) != raw) die("%s: short read", ix->path);
-    fclose(f);
-    int64_t w = 0;
-    for (int64_t i = 0; i < raw; i++) { const char c = s[i]; if (c != '\n' && c != '\r') s[w++] = c; }
-    *len = w;
+    if (!s) die("out of memory (%lld characters of reference)", (long long)raw);
+    const int64_t n = gromhost_fasta_load(ix, k, s, raw);
+    if (n < 0) die("%s", gromhost_last_error());
+    *len = n;
     return s;
 }
 
@@ -420,7 +382,8 @@ static int run_worker(options *o, const char *argv0)
 {
     grom_bam *bam = NULL;
     if (gromhost_bam_open(o->bam, &bam)) die("\n%s", gromhost_last_error());
-    fa_index fa; fasta_index(o->fasta, &fa);
+    fa_index *fa = NULL;
+    if (gromhost_fasta_open(o->fasta, &fa)) die("\n%s", gromhost_last_error());
     if (!o->have_stats) { library_stats(o, bam, &o->st_mean, &o->st_lseq, &o->st_min, &o->st_max); o->have_stats = 1; }
     o->prm.insert_mean = o->st_mean > o->st_lseq ? o->st_mean : o->st_lseq;          /* src/GROM.c:22260 */
     o->prm.lseq = o->st_lseq; o->prm.insert_min = o->st_min; o->prm.insert_max = o->st_max;
@@ -438,10 +401,10 @@ static int run_worker(options *o, const char *argv0)
     free(hez); free(mq);
 
     worker w; memset(&w, 0, sizeof(w));
-    w.o = o; w.fa = &fa; w.p2s_p = p2s_p; w.p2s_sd = p2s_sd; w.n_p2s = n_p2s;
+    w.o = o; w.fa = fa; w.p2s_p = p2s_p; w.p2s_sd = p2s_sd; w.n_p2s = n_p2s;
     contig *all = NULL; int n_all = 0;
     const int world = o->world > 0 ? o->world : 1;
-    w.n_work = plan(bam, &fa, &o->prm, world, o->rank, &w.work, &n_all, &all);
+    w.n_work = plan(bam, fa, &o->prm, world, o->rank, &w.work, &n_all, &all);
     pthread_mutex_init(&w.pick, NULL); pthread_mutex_init(&w.bus, NULL); pthread_mutex_init(&w.mem, NULL); pthread_cond_init(&w.mem_cv, NULL);
     w.mem_budget = (int64_t)(0.9 * (double)gromgpu_device_free_bytes());
     int lanes = o->lanes < w.n_work ? o->lanes : w.n_work;
