@@ -805,6 +805,107 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
 }
 
 
+/* ------------------------------------------------------------------ library statistics straight from the file */
+
+/* find_insert_mean (reference src/GROM.c:1205-1318) over the records of the file in file order, without building batches: the BGZF
+ * blocks are inflated a window at a time by all threads, only the core fields of the records are looked at, and the scan ends with the
+ * window in which the sample fills up (the reference stops reading there as well).  Same accumulator as gromhost_libstats_add, so the
+ * result equals feeding it the per-contig batches in contig order. */
+int gromhost_bam_library_stats(grom_bam *b, int rd_min_mapq, int n_threads, int *insert_mean, int *lseq, int *insert_min, int *insert_max, int64_t *mapped_reads)
+{
+#ifdef _OPENMP
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+#else
+    n_threads = 1;
+#endif
+    const uint8_t *cf = b->map; const int64_t cf_len = b->map_len;
+    const int W = 32 * n_threads;                                   /* blocks per window */
+    blkinfo *blk = (blkinfo *)malloc(sizeof(blkinfo) * (size_t)W);
+    size_t win_cap = (size_t)W * 65536 + (1 << 20);
+    uint8_t *win = (uint8_t *)malloc(win_cap);
+    int64_t cap = (int64_t)W * 65536 / 36 + 16;
+    int32_t *pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap), *mpos = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap), *tlen = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap),
+            *mtid = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap), *lq = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap), *rt = (int32_t *)malloc(sizeof(int32_t) * (size_t)cap);
+    uint16_t *flag = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)cap); uint8_t *mapq = (uint8_t *)malloc((size_t)cap);
+    gromhost_libstats *s = gromhost_libstats_new(rd_min_mapq);
+    int rc = 0;
+    if (!blk || !win || !pos || !mpos || !tlen || !mtid || !lq || !rt || !flag || !mapq || !s) rc = fail("out of memory (library statistics)");
+    int64_t off = (int64_t)(b->first_voff >> 16), skip = (int64_t)(b->first_voff & 0xffff), carry = 0;
+    int full = 0, ended = 0;
+    while (rc == 0 && !full && !ended) {
+        int nb = 0; int64_t utotal = 0;
+        while (nb < W && off + 18 <= cf_len) {
+            const uint8_t *hdr = cf + off;
+            const int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
+            if (hdr[0] != 0x1f || hdr[1] != 0x8b || bsize < 26 || !(hdr[3] & 4) || (hdr[10] | (hdr[11] << 8)) != 6 || hdr[12] != 'B' || hdr[13] != 'C') { rc = fail("%s: bad BGZF block at %lld", b->path, (long long)off); break; }
+            if (off + bsize > cf_len) { ended = 1; break; }
+            const uint32_t isize = rd_u32(cf + off + bsize - 4);
+            if (isize > 65536) { rc = fail("%s: bad BGZF block at %lld", b->path, (long long)off); break; }
+            blk[nb].off = off; blk[nb].bsize = bsize; blk[nb].isize = (int)isize; blk[nb].uoff = utotal; utotal += isize; nb++;
+            off += bsize;
+        }
+        if (rc) break;
+        if (nb < W) ended = 1;
+        if ((size_t)(carry + utotal) + 64 > win_cap) {
+            win_cap = (size_t)(carry + utotal) + (1 << 20);
+            uint8_t *w2 = (uint8_t *)realloc(win, win_cap);
+            if (!w2) { rc = fail("out of memory (library statistics)"); break; }
+            win = w2;
+        }
+        int bad = 0;
+        #pragma omp parallel num_threads(n_threads)
+        {
+            struct grom_inflate_ctx *ctx = (struct grom_inflate_ctx *)malloc(grom_inflate_ctx_size());
+            if (ctx) grom_inflate_ctx_init(ctx);
+            #pragma omp for schedule(dynamic, 4)
+            for (int i = 0; i < nb; i++) {
+                const uint8_t *bp = cf + blk[i].off;
+                if (bgzf_inflate_block(ctx, bp + 18, blk[i].bsize - 26, win + carry + blk[i].uoff, blk[i].isize, rd_u32(bp + blk[i].bsize - 8)) < 0) {
+                    #pragma omp atomic write
+                    bad = 1;
+                }
+            }
+            free(ctx);
+        }
+        if (bad) { rc = fail("%s: BGZF inflate failed (corrupt deflate stream or CRC mismatch)", b->path); break; }
+        const int64_t have = carry + utotal;
+        int64_t p = skip, n = 0; skip = 0;
+        if (p > have) { skip = p - have; p = have; }                       /* (a header longer than the window) */
+        while (p + 36 <= have) {
+            const int32_t bl = rd_i32(win + p);
+            if (bl < 32) { ended = 1; break; }
+            if (p + 4 + (int64_t)bl > have) break;                          /* the record continues in the next window */
+            if (n == cap) break;                                            /* cannot happen: cap covers the smallest possible records */
+            const uint32_t bmq = rd_u32(win + p + 12), fnc = rd_u32(win + p + 16);
+            rt[n] = rd_i32(win + p + 4); pos[n] = rd_i32(win + p + 8); mapq[n] = (uint8_t)((bmq >> 8) & 0xff); flag[n] = (uint16_t)(fnc >> 16);
+            lq[n] = rd_i32(win + p + 20); mtid[n] = rd_i32(win + p + 24); mpos[n] = rd_i32(win + p + 28); tlen[n] = rd_i32(win + p + 32);
+            n++; p += 4 + bl;
+        }
+        /* feed the accumulator, one run of equal target id at a time (its pair test compares mtid with the batch's tid) */
+        for (int64_t i0 = 0; i0 < n && !full; ) {
+            int64_t i1 = i0 + 1;
+            while (i1 < n && rt[i1] == rt[i0]) i1++;
+            grom_read_batch v; memset(&v, 0, sizeof(v));
+            v.n_reads = i1 - i0; v.tid = rt[i0]; v.pos = pos + i0; v.mpos = mpos + i0; v.tlen = tlen + i0; v.mtid = mtid + i0; v.l_qseq = lq + i0; v.flag = flag + i0; v.mapq = mapq + i0;
+            full = gromhost_libstats_add(s, &v);
+            i0 = i1;
+        }
+        carry = have - p;
+        if (carry > 0 && !ended) {
+            if ((size_t)carry > win_cap / 2) {                               /* one record larger than half the window: make room for it */
+                win_cap = (size_t)carry * 2 + (size_t)W * 65536 + (1 << 20);
+                uint8_t *w2 = (uint8_t *)malloc(win_cap);
+                if (!w2) { rc = fail("out of memory (library statistics)"); break; }
+                memcpy(w2, win + p, (size_t)carry); free(win); win = w2;
+            } else memmove(win, win + p, (size_t)carry);
+        } else if (ended) carry = 0;
+    }
+    if (rc == 0 && gromhost_libstats_finish(s, insert_mean, lseq, insert_min, insert_max, mapped_reads)) rc = fail("%s: no reads to estimate the insert size from", b->path);
+    gromhost_libstats_free(s);
+    free(blk); free(win); free(pos); free(mpos); free(tlen); free(mtid); free(lq); free(rt); free(flag); free(mapq);
+    return rc;
+}
+
 /* ------------------------------------------------------------------ writer (tooling) */
 
 typedef struct {

@@ -120,6 +120,15 @@ class Bam:
         _check(lib().gromhost_bam_read_target(self._h, tid, int(keep_names), threads, C.byref(bt)))
         return OwnedBatch(bt)
 
+    def library_stats(self, rd_min_mapq: int = 20, threads: int = 0) -> dict:
+        """find_insert_mean (reference src/GROM.c:1205-1318) straight over the file (gromhost_bam_library_stats)."""
+        L = lib()
+        L.gromhost_bam_library_stats.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 5
+        v = [C.c_int(), C.c_int(), C.c_int(), C.c_int()]
+        m = C.c_int64()
+        _check(L.gromhost_bam_library_stats(self._h, rd_min_mapq, threads, C.byref(v[0]), C.byref(v[1]), C.byref(v[2]), C.byref(v[3]), C.byref(m)))
+        return dict(insert_mean=v[0].value, lseq=v[1].value, insert_min=v[2].value, insert_max=v[3].value, mapped_reads=m.value)
+
     def close(self):
         if self._h:
             lib().gromhost_bam_close(self._h)

@@ -92,8 +92,8 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
     prm = params if params is not None else Params.default()
     fasta = _LazyFasta(fasta_path)          # contig characters are loaded (by the C library) when a lane takes the contig, not all up front
     with hostlib.Bam(bam_path) as bam:
-        # library statistics first (find_insert_mean, src/GROM.c:1205-1318): the contigs stream through one at a time until the sample is full
-        st = hostlib.library_stats((bam.read_target(t) for t in range(len(bam.names))), prm.min_mapq)
+        # library statistics first (find_insert_mean, src/GROM.c:1205-1318): one windowed pass over the file that ends when the sample is full
+        st = bam.library_stats(prm.min_mapq)
         prm.insert_mean = max(st["insert_mean"], st["lseq"])            # src/GROM.c:22260
         prm.insert_min, prm.insert_max, prm.lseq = st["insert_min"], st["insert_max"], st["lseq"]
         prm.rd_min_mapq = prm.min_mapq                                    # src/GROM.c:22102

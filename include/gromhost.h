@@ -107,6 +107,10 @@ gromhost_libstats *gromhost_libstats_new(int rd_min_mapq);
 int  gromhost_libstats_add(gromhost_libstats *s, const grom_read_batch *b);        /* 1 = sample full (10,000,000 inserts) */
 int  gromhost_libstats_finish(gromhost_libstats *s, int *insert_mean, int *lseq, int *insert_min, int *insert_max, int64_t *mapped_reads);
 void gromhost_libstats_free(gromhost_libstats *s);
+/* the same statistics straight from an open BAM: records in file order, blocks inflated a window at a time by n_threads (<= 0: OpenMP
+ * default), core fields only, reading ends with the window in which the 10,000,000-insert sample fills up.  Equals _new / _add over the
+ * per-target batches in target order / _finish.  -1 = error (gromhost_last_error), e.g. no usable read. */
+int  gromhost_bam_library_stats(grom_bam *b, int rd_min_mapq, int n_threads, int *insert_mean, int *lseq, int *insert_min, int *insert_max, int64_t *mapped_reads);
 
 /* ---- structural-variant candidate lists (grom_b200/host/svlists.c): the state of cdp_dup_list / cdp_del_list / cdp_inv_f_list /
  * cdp_inv_r_list / cdp_ins_list / cdp_ctx_f_list / cdp_ctx_r_list at src/GROM.c:15164, rebuilt from the gate events of

@@ -40,4 +40,38 @@ def test_statistics_equal_the_live_reference(tmp_path, seed, read_len, ins_mean,
     ref = po.read_mean_file(bam)
     with hostlib.Bam(bam) as b:
         st = hostlib.library_stats([b.read_target(t) for t in range(len(b.names))], q)
+        st_file = b.library_stats(q)               # the pass the drivers run: straight over the file
     assert {k: st[k] for k in KEYS} == {k: ref[k] for k in KEYS}
+    assert st_file == st
+
+
+def test_statistics_straight_from_the_file_equal_the_per_contig_feed(tmp_path, monkeypatch):
+    """gromhost_bam_library_stats (windowed pass over the blocks, core fields only) against the accumulator fed with whole batches: the
+    committed BAM, and a file whose records straddle many windows (one thread -> windows of 32 blocks), with and without an index."""
+    from util import GOLDEN
+    names, batches = golden_batches()
+    want = hostlib.library_stats(batches, 20)
+    with hostlib.Bam(os.path.join(GOLDEN, "g1.bam")) as b:
+        assert b.library_stats(20) == want and b.library_stats(20, threads=1) == want and b.library_stats(20, threads=3) == want
+    spec = synth.SynthSpec(contigs=[("c1", 400_000), ("c2", 90_000)], depth=25, seed=71, dup_frac=0.03, clip_frac=0.04, disc_frac=0.03, munmap_frac=0.01,
+                           unpaired_frac=0.01, low_mapq_frac=0.05)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "s"), cs)
+    with hostlib.Bam(bam) as b:
+        want = hostlib.library_stats([b.read_target(t) for t in range(2)], 30)
+        assert os.path.getsize(bam) > 3 * 32 * 20_000                       # several one-thread windows
+        for thr in (1, 2, 5):
+            assert b.library_stats(30, threads=thr) == want
+    os.remove(bam + ".bai")
+    with hostlib.Bam(bam) as b:
+        assert b.library_stats(30, threads=1) == want
+
+
+def test_statistics_of_a_file_without_usable_reads(tmp_path):
+    spec = synth.SynthSpec(contigs=[("c1", 20_000)], depth=3, seed=72)
+    cs = synth.simulate(spec)
+    cs[0].batch.flag[:] |= 4                                                # everything unmapped
+    fa, bam = synth.write_dataset(str(tmp_path / "u"), cs)
+    with hostlib.Bam(bam) as b:
+        with pytest.raises(RuntimeError, match="no reads"):
+            b.library_stats(20)

@@ -360,22 +360,11 @@ static void exe_dir(const char *argv0, char *dst, size_t cap)
     snprintf(dst, cap, "%s", dirname(buf));
 }
 
-/* find_insert_mean over the contigs in BAM order until its sample is full (src/GROM.c:1205-1318) */
+/* find_insert_mean over the records in file order until its sample is full (src/GROM.c:1205-1318) */
 static void library_stats(const options *o, grom_bam *bam, int *mean, int *lseq, int *imin, int *imax)
 {
-    gromhost_libstats *s = gromhost_libstats_new(o->prm.min_mapq);
-    const int nt = gromhost_bam_n_targets(bam);
-    for (int t = 0; t < nt; t++) {
-        grom_batch *bt = NULL;
-        if (gromhost_bam_read_target(bam, t, 0, 0, &bt)) die("%s", gromhost_last_error());
-        grom_read_batch v; gromhost_batch_view(bt, &v);
-        const int full = gromhost_libstats_add(s, &v);
-        gromhost_batch_free(bt);
-        if (full) break;
-    }
     int64_t mapped = 0;
-    if (gromhost_libstats_finish(s, mean, lseq, imin, imax, &mapped)) die("GROM_b200: no reads to estimate the insert size from");
-    gromhost_libstats_free(s);
+    if (gromhost_bam_library_stats(bam, o->prm.min_mapq, 0, mean, lseq, imin, imax, &mapped)) die("GROM_b200: %s", gromhost_last_error());
 }
 
 static int run_worker(options *o, const char *argv0)
