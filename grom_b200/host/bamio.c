@@ -80,6 +80,70 @@ static int bgzf_inflate_at(FILE *f, int64_t off, uint8_t *raw, uint8_t *dst, int
     return (int)isize;
 }
 
+/* CRC-32 of the BGZF trailer (the gzip polynomial).  On x86-64 with carry-less multiply the bulk is folded 64 bytes at a time (the
+ * folding constants of the gzip polynomial: x^(512+64), x^512, x^(128+64), x^128, x^64 mod P, P and its Barrett inverse); the last
+ * n mod 16 bytes, short buffers and every other machine go through zlib's crc32, which also serves as the check in tests/test_inflate.py. */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("pclmul,sse4.1")))
+static uint32_t crc32_clmul(const uint8_t *buf, size_t len, uint32_t crc)   /* len >= 64, multiple of 16; crc = running state (inverted form) */
+{
+    static const uint64_t __attribute__((aligned(16))) k1k2[] = { 0x0154442bd4ULL, 0x01c6e41596ULL };
+    static const uint64_t __attribute__((aligned(16))) k3k4[] = { 0x01751997d0ULL, 0x00ccaa009eULL };
+    static const uint64_t __attribute__((aligned(16))) k5k0[] = { 0x0163cd6124ULL, 0x0000000000ULL };
+    static const uint64_t __attribute__((aligned(16))) poly[] = { 0x01db710641ULL, 0x01f7011641ULL };
+    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+    x1 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+    x2 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+    x3 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+    x4 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+    x0 = _mm_load_si128((const __m128i *)k1k2);
+    buf += 64; len -= 64;
+    while (len >= 64) {
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+        x7 = _mm_clmulepi64_si128(x3, x0, 0x00); x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+        x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+        x3 = _mm_clmulepi64_si128(x3, x0, 0x11); x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+        y5 = _mm_loadu_si128((const __m128i *)(buf + 0x00)); y6 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+        y7 = _mm_loadu_si128((const __m128i *)(buf + 0x20)); y8 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5); x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7); x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+        buf += 64; len -= 64;
+    }
+    x0 = _mm_load_si128((const __m128i *)k3k4);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+    while (len >= 16) {
+        x2 = _mm_loadu_si128((const __m128i *)buf);
+        x5 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_clmulepi64_si128(x1, x0, 0x11); x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+        buf += 16; len -= 16;
+    }
+    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
+    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+    x1 = _mm_srli_si128(x1, 8); x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_loadl_epi64((const __m128i *)k5k0);
+    x2 = _mm_srli_si128(x1, 4); x1 = _mm_and_si128(x1, x3); x1 = _mm_clmulepi64_si128(x1, x0, 0x00); x1 = _mm_xor_si128(x1, x2);
+    x0 = _mm_load_si128((const __m128i *)poly);
+    x2 = _mm_and_si128(x1, x3); x2 = _mm_clmulepi64_si128(x2, x0, 0x10); x2 = _mm_and_si128(x2, x3); x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x1 = _mm_xor_si128(x1, x2);
+    return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+#define GROM_HAVE_CLMUL 1
+#endif
+
+uint32_t gromhost_crc32(const uint8_t *p, int64_t n)
+{
+    uint32_t c = 0;
+#ifdef GROM_HAVE_CLMUL
+    static int have = -1;
+    if (have < 0) have = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1");
+    if (have && n >= 64) { const int64_t m = n & ~(int64_t)15; c = ~crc32_clmul(p, (size_t)m, ~c); p += m; n -= m; }
+#endif
+    return (uint32_t)crc32(c, p, (uInt)n);
+}
+
 /* inflate the deflate stream of one BGZF block (`clen` bytes, header and trailer stripped) into exactly `isize` bytes at dst and check
  * the CRC-32 of the trailer.  The batcher's own decoder (inflate.c) runs first; what it refuses is judged by zlib. */
 static int bgzf_inflate_block(struct grom_inflate_ctx *ctx, const uint8_t *src, int clen, uint8_t *dst, int isize, uint32_t crc)
@@ -92,7 +156,7 @@ static int bgzf_inflate_block(struct grom_inflate_ctx *ctx, const uint8_t *src, 
         inflateEnd(&s);
         if (!(rc == Z_STREAM_END && s.total_out == (uLong)isize)) return -1;
     }
-    return ((uint32_t)crc32(crc32(0L, NULL, 0), dst, (uInt)isize) == crc) ? 0 : -1;
+    return (gromhost_crc32(dst, isize) == crc) ? 0 : -1;
 }
 
 /* test / tooling entry: one raw deflate stream with a known output size through the batcher's own decoder only (no zlib fallback) */

@@ -47,6 +47,9 @@ int  gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_thread
 /* One raw DEFLATE stream (RFC 1951, e.g. the payload of a BGZF block) of known output size through the library's own decoder, without
  * the zlib second opinion: 0 = well formed and exactly dst_len bytes produced, -1 otherwise.  Test / tooling entry. */
 int  gromhost_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len);
+/* CRC-32 (gzip polynomial) as the batcher computes it for the BGZF trailers: carry-less-multiply folding where the CPU has it, zlib's
+ * crc32 otherwise; always equal to zlib's.  Test / tooling entry. */
+uint32_t gromhost_crc32(const uint8_t *p, int64_t n);
 
 /* view of an owned batch; pointers stay valid until gromhost_batch_free() */
 void gromhost_batch_view(const grom_batch *bt, grom_read_batch *view);

@@ -69,6 +69,17 @@ def test_decoder_equals_zlib_on_every_block_type():
     assert n_streams > 1000
 
 
+def test_crc32_equals_zlib():
+    L = _lib()
+    L.gromhost_crc32.argtypes = [C.c_char_p, C.c_int64]
+    L.gromhost_crc32.restype = C.c_uint32
+    rng = random.Random(4)
+    blob = bytes(rng.getrandbits(8) for _ in range(70_000))
+    for n in list(range(0, 200)) + [255, 256, 1023, 4096, 65279, 65280, 65536] + [rng.randrange(70_000) for _ in range(200)]:
+        o = rng.randrange(0, 70_000 - n + 1)
+        assert L.gromhost_crc32(blob[o:o + n], n) == zlib.crc32(blob[o:o + n]), n
+
+
 def test_multi_block_streams_with_flush_points():
     rng = random.Random(2)
     for kind in range(7):
