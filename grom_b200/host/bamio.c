@@ -148,7 +148,9 @@ uint32_t gromhost_crc32(const uint8_t *p, int64_t n)
  * the CRC-32 of the trailer.  The batcher's own decoder (inflate.c) runs first; what it refuses is judged by zlib. */
 static int bgzf_inflate_block(struct grom_inflate_ctx *ctx, const uint8_t *src, int clen, uint8_t *dst, int isize, uint32_t crc)
 {
-    if (!ctx || grom_inflate_raw(ctx, src, (size_t)clen, dst, (size_t)isize) != 0) {
+    static int generic = -1;                     /* GROMHOST_INFLATE=generic: the variant compiled without BMI2 (measurements, tests) */
+    if (generic < 0) { const char *v = getenv("GROMHOST_INFLATE"); generic = (v && !strcmp(v, "generic")) ? 1 : 0; }
+    if (!ctx || (generic ? grom_inflate_raw_generic(ctx, src, (size_t)clen, dst, (size_t)isize) : grom_inflate_raw(ctx, src, (size_t)clen, dst, (size_t)isize)) != 0) {
         z_stream s; memset(&s, 0, sizeof(s));
         s.next_in = (Bytef *)src; s.avail_in = (uInt)clen; s.next_out = dst; s.avail_out = (uInt)isize;
         if (inflateInit2(&s, -15) != Z_OK) return -1;
@@ -165,7 +167,9 @@ int gromhost_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int6
     struct grom_inflate_ctx *ctx = (struct grom_inflate_ctx *)malloc(grom_inflate_ctx_size());
     if (!ctx) return fail("out of memory");
     grom_inflate_ctx_init(ctx);
-    const int rc = grom_inflate_raw(ctx, src, (size_t)src_len, dst, (size_t)dst_len);
+    const char *v = getenv("GROMHOST_INFLATE");                     /* "generic": the variant compiled without BMI2 */
+    const int rc = (v && !strcmp(v, "generic")) ? grom_inflate_raw_generic(ctx, src, (size_t)src_len, dst, (size_t)dst_len)
+                                                : grom_inflate_raw(ctx, src, (size_t)src_len, dst, (size_t)dst_len);
     free(ctx);
     return rc == 0 ? 0 : fail("not a well-formed deflate stream of %lld bytes", (long long)dst_len);
 }

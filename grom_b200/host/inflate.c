@@ -151,190 +151,33 @@ static inline void store64(uint8_t *p, uint64_t v) { memcpy(p, &v, 8); }
 /* base + extra bits of a length / distance entry; `sv` is the reservoir before the entry's bits were dropped */
 #define BASE_PLUS_EXTRA(e, sv) (E_VAL(e) + (uint32_t)(((sv) >> E_CODE(e)) & ((1u << (E_TOTAL(e) - E_CODE(e))) - 1)))
 
+#define INFLATE_FN inflate_generic
+#define INFLATE_ATTR
+#include "inflate_body.inc"
+#undef INFLATE_FN
+#undef INFLATE_ATTR
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define INFLATE_FN inflate_bmi2
+#define INFLATE_ATTR __attribute__((target("bmi2")))
+#include "inflate_body.inc"
+#undef INFLATE_FN
+#undef INFLATE_ATTR
+#define GROM_INFLATE_BMI2 1
+#endif
+
 int grom_inflate_raw(struct grom_inflate_ctx *c, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
 {
-    const uint8_t *ip = in, *const in_end = in + in_len;
-    uint8_t *op = out, *const out_end = out + out_len;
-    uint64_t bb = 0; int bn = 0;
-    int last;
-    do {
-        REFILL_SAFE();
-        if (bn < 3) return -1;
-        last = (int)(bb & 1); const int type = (int)((bb >> 1) & 3); DROP(3);
-        const ent_t *ll, *ds;
-        if (type == 0) {                                   /* stored: skip to the byte boundary, LEN, ~LEN, bytes */
-            DROP(bn & 7);
-            REFILL_SAFE();
-            if (bn < 32) return -1;
-            const uint32_t len = (uint32_t)(bb & 0xffff), nlen = (uint32_t)((bb >> 16) & 0xffff); DROP(32);
-            if ((len ^ 0xffff) != nlen) return -1;
-            /* bytes still in the reservoir belong to the stored data */
-            uint32_t left = len;
-            while (left && bn >= 8) { if (op >= out_end) return -1; *op++ = (uint8_t)bb; DROP(8); left--; }
-            if (left) {
-                if (bn != 0) return -1;
-                if ((size_t)(in_end - ip) < left || (size_t)(out_end - op) < left) return -1;
-                memcpy(op, ip, left); ip += left; op += left;
-                bb = 0; bn = 0;
-            }
-            continue;
-        } else if (type == 1) {
-            if (!c->fixed_ready) {
-                uint8_t l[LL_SYMS];
-                for (int i = 0; i < 144; i++) l[i] = 8;
-                for (int i = 144; i < 256; i++) l[i] = 9;
-                for (int i = 256; i < 280; i++) l[i] = 7;
-                for (int i = 280; i < 288; i++) l[i] = 8;
-                if (build_table(0, l, 288, LL_BITS, c->fixed_ll, LL_TABLE) < 0) return -1;
-                for (int i = 0; i < 32; i++) l[i] = 5;
-                if (build_table(1, l, 32, D_BITS, c->fixed_ds, D_TABLE) < 0) return -1;
-                c->fixed_ready = 1;
-            }
-            ll = c->fixed_ll; ds = c->fixed_ds;
-        } else if (type == 2) {
-            REFILL_SAFE();
-            if (bn < 14) return -1;
-            const int hlit = (int)(bb & 31) + 257, hdist = (int)((bb >> 5) & 31) + 1, hclen = (int)((bb >> 10) & 15) + 4; DROP(14);
-            if (hlit > 286 || hdist > 30) return -1;
-            static const uint8_t order[19] = { 16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15 };
-            uint8_t pl[19]; memset(pl, 0, sizeof(pl));
-            for (int i = 0; i < hclen; i++) {
-                REFILL_SAFE();
-                if (bn < 3) return -1;
-                pl[order[i]] = (uint8_t)(bb & 7); DROP(3);
-            }
-            if (build_table(2, pl, 19, PRE_BITS, c->pre, 1 << PRE_BITS) < 0) return -1;
-            uint8_t lens[LL_SYMS + D_SYMS + 140];
-            int n = 0; const int total = hlit + hdist;
-            while (n < total) {
-                REFILL_SAFE();
-                const ent_t e = c->pre[bb & ((1 << PRE_BITS) - 1)];
-                if (!(e & E_LIT) || (int)E_TOTAL(e) > bn) return -1;
-                DROP_E(e);
-                const int sym = (int)E_VAL(e);
-                if (sym < 16) { lens[n++] = (uint8_t)sym; continue; }
-                int rep, val = 0;
-                if (sym == 16) { if (n == 0 || bn < 2) return -1; val = lens[n - 1]; rep = 3 + (int)(bb & 3); DROP(2); }
-                else if (sym == 17) { if (bn < 3) return -1; rep = 3 + (int)(bb & 7); DROP(3); }
-                else { if (bn < 7) return -1; rep = 11 + (int)(bb & 127); DROP(7); }
-                if (n + rep > total) return -1;
-                memset(lens + n, val, (size_t)rep); n += rep;
-            }
-            if (lens[256] == 0) return -1;                  /* no end-of-block code */
-            uint8_t l2[LL_SYMS]; memset(l2, 0, sizeof(l2)); memcpy(l2, lens, (size_t)hlit);
-            if (build_table(0, l2, 288, LL_BITS, c->ll, LL_TABLE) < 0) return -1;
-            uint8_t d2[D_SYMS]; memset(d2, 0, sizeof(d2)); memcpy(d2, lens + hlit, (size_t)hdist);
-            if (build_table(1, d2, 32, D_BITS, c->ds, D_TABLE) < 0) return -1;
-            ll = c->ll; ds = c->ds;
-        } else return -1;
+#ifdef GROM_INFLATE_BMI2
+    static int have = -1;
+    if (have < 0) have = __builtin_cpu_supports("bmi2") ? 1 : 0;
+    if (have) return inflate_bmi2(c, in, in_len, out, out_len);
+#endif
+    return inflate_generic(c, in, in_len, out, out_len);
+}
 
-        /* ---- fast loop: room for a whole iteration on both sides, no bounds tests inside.  `e` is looked up ahead of its use (before the
-         * match copy of the previous symbol) so that the table latency overlaps the copy. */
-        if ((size_t)(in_end - ip) >= FAST_IN && (size_t)(out_end - op) >= FAST_OUT) {
-            const uint8_t *const in_fast = in_end - FAST_IN; uint8_t *const out_fast = out_end - FAST_OUT;
-            REFILL_FAST();
-            ent_t e = ll[bb & ((1 << LL_BITS) - 1)];
-            for (;;) {
-                /* here: bn >= 56 counted bits, e = entry of the next symbol */
-                if (e & E_LIT) {
-                    DROP_E(e); *op++ = (uint8_t)(e >> 16);
-                    e = ll[bb & ((1 << LL_BITS) - 1)];
-                    if (e & E_LIT) {
-                        DROP_E(e); *op++ = (uint8_t)(e >> 16);
-                        e = ll[bb & ((1 << LL_BITS) - 1)];
-                        if (e & E_LIT) {                                       /* at most 33 bits so far */
-                            DROP_E(e); *op++ = (uint8_t)(e >> 16);
-                            if (ip > in_fast || op > out_fast) break;
-                            e = ll[bb & ((1 << LL_BITS) - 1)]; REFILL_FAST();          /* at least 19 stream bits are still in the reservoir */
-                            continue;
-                        }
-                    }
-                    REFILL_FAST();                                              /* up to 22 bits used; a match may need 48 */
-                }
-                if (e & E_EXC) {
-                    if (!(e & E_SUB)) {
-                        if (e & E_EOB) { DROP_E(e); goto block_done; }
-                        return -1;
-                    }
-                    DROP_E(e);
-                    e = ll[E_VAL(e) + (bb & ((1u << E_CODE(e)) - 1))];
-                    if (e & E_LIT) {
-                        DROP_E(e); *op++ = (uint8_t)(e >> 16);
-                        if (ip > in_fast || op > out_fast) break;
-                        REFILL_FAST(); e = ll[bb & ((1 << LL_BITS) - 1)];
-                        continue;
-                    }
-                    if (e & E_EXC) {
-                        if (e & E_EOB) { DROP_E(e); goto block_done; }
-                        return -1;
-                    }
-                }
-                uint64_t sv = bb;
-                DROP_E(e);
-                const uint32_t len = BASE_PLUS_EXTRA(e, sv);
-                ent_t d = ds[bb & ((1 << D_BITS) - 1)];
-                if (d & E_EXC) {
-                    if (!(d & E_SUB)) return -1;
-                    DROP_E(d);
-                    d = ds[E_VAL(d) + (bb & ((1u << E_CODE(d)) - 1))];
-                    if (d & E_EXC) return -1;
-                }
-                sv = bb;
-                DROP_E(d);
-                const uint32_t dist = BASE_PLUS_EXTRA(d, sv);
-                if (dist > (size_t)(op - out)) return -1;
-                const uint8_t *src = op - dist; uint8_t *dst = op; op += len;
-                const int more = !(ip > in_fast || op > out_fast);
-                /* a refill leaves all 64 bits of the reservoir valid (56+ of them counted), a match drops at most 48: the next entry can be
-                 * looked up before the refill, which takes the refill (it waits for the bit count) off the path from entry to entry */
-                if (more) { e = ll[bb & ((1 << LL_BITS) - 1)]; REFILL_FAST(); }
-                if (dist >= 8) {
-                    store64(dst, load64(src)); store64(dst + 8, load64(src + 8));            /* most matches are short */
-                    if (len > 16) { uint8_t *const e2 = op; dst += 16; src += 16; do { store64(dst, load64(src)); dst += 8; src += 8; } while (dst < e2); }
-                } else if (dist == 1) {
-                    const uint64_t v = 0x0101010101010101ULL * src[0];
-                    uint8_t *const e2 = op; do { store64(dst, v); dst += 8; } while (dst < e2);
-                } else {
-                    uint8_t *const e2 = op; do { *dst++ = *src++; } while (dst < e2);
-                }
-                if (!more) break;
-            }
-        }
-        /* ---- careful loop: the tail of the block / of the output */
-        for (;;) {
-            REFILL_SAFE();
-            ent_t e = ll[bb & ((1 << LL_BITS) - 1)];
-            if ((e & (E_EXC | E_SUB)) == (E_EXC | E_SUB)) {
-                if ((int)E_TOTAL(e) > bn) return -1;
-                DROP_E(e);
-                e = ll[E_VAL(e) + (bb & ((1u << E_CODE(e)) - 1))];
-            }
-            if ((int)E_TOTAL(e) > bn) return -1;
-            if (e & E_LIT) { if (op >= out_end) return -1; DROP_E(e); *op++ = (uint8_t)(e >> 16); continue; }
-            if (e & E_EXC) {
-                if (e & E_EOB) { DROP_E(e); goto block_done; }
-                return -1;
-            }
-            uint64_t sv = bb;
-            DROP_E(e);
-            const uint32_t len = BASE_PLUS_EXTRA(e, sv);
-            REFILL_SAFE();
-            ent_t d = ds[bb & ((1 << D_BITS) - 1)];
-            if ((d & (E_EXC | E_SUB)) == (E_EXC | E_SUB)) {
-                if ((int)E_TOTAL(d) > bn) return -1;
-                DROP_E(d);
-                d = ds[E_VAL(d) + (bb & ((1u << E_CODE(d)) - 1))];
-            }
-            if ((d & (E_EXC | E_LIT)) || (int)E_TOTAL(d) > bn) return -1;
-            sv = bb;
-            DROP_E(d);
-            const uint32_t dist = BASE_PLUS_EXTRA(d, sv);
-            if (dist > (size_t)(op - out) || len > (size_t)(out_end - op)) return -1;
-            const uint8_t *src = op - dist;
-            for (uint32_t k = 0; k < len; k++) op[k] = src[k];
-            op += len;
-        }
-block_done: ;
-    } while (!last);
-    return (op == out_end) ? 0 : -1;
+/* the plain x86-64 / portable variant whatever the CPU offers (tests) */
+int grom_inflate_raw_generic(struct grom_inflate_ctx *c, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
+{
+    return inflate_generic(c, in, in_len, out, out_len);
 }

@@ -10,5 +10,7 @@ void grom_inflate_ctx_init(struct grom_inflate_ctx *c);
 /* 0 = well-formed stream that ended with a final block after exactly out_len bytes; -1 = anything else (nothing outside the two
  * buffers is touched either way) */
 int grom_inflate_raw(struct grom_inflate_ctx *c, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
+/* the same through the variant compiled without BMI2 (grom_inflate_raw picks the BMI2 one where the CPU has it) */
+int grom_inflate_raw_generic(struct grom_inflate_ctx *c, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
 
 #endif

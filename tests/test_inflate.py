@@ -80,6 +80,18 @@ def test_crc32_equals_zlib():
         assert L.gromhost_crc32(blob[o:o + n], n) == zlib.crc32(blob[o:o + n]), n
 
 
+def test_variant_without_bmi2_decodes_the_same(monkeypatch):
+    """grom_inflate_raw picks the BMI2 build of the loop where the CPU has it; GROMHOST_INFLATE=generic sends the test entry through the other."""
+    rng = random.Random(5)
+    monkeypatch.setenv("GROMHOST_INFLATE", "generic")
+    for kind in range(7):
+        for n in (300, 5000, 65536):
+            d = payload(kind, n, rng)
+            for level in (1, 6):
+                rc, got, tail = own(deflate(d, level), n)
+                assert rc == 0 and got == d and tail == b"\0" * 64
+
+
 def test_multi_block_streams_with_flush_points():
     rng = random.Random(2)
     for kind in range(7):
