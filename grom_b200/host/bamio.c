@@ -225,8 +225,13 @@ int gromhost_bam_open(const char *path, grom_bam **out)
     free(r);
 
     /* optional index: keep only [min chunk_beg, max chunk_end] per target */
+    /* "<bam>.bai", else "<stem>.bai" for a name that ends in "bam" (the two places samtools' bam_index_load looks, src/GROM.c:220, 22129) */
     char iname[4096]; snprintf(iname, sizeof(iname), "%s.bai", path);
     FILE *fi = fopen(iname, "rb");
+    if (!fi) {
+        const size_t pl = strlen(path);
+        if (pl >= 3 && pl < sizeof(iname) && !strcmp(path + pl - 3, "bam")) { snprintf(iname, sizeof(iname), "%s", path); iname[pl - 1] = 'i'; fi = fopen(iname, "rb"); }
+    }
     if (fi) {
         char m[4]; int32_t nr = 0;
         if (fread(m, 1, 4, fi) == 4 && !memcmp(m, "BAI\1", 4) && fread(&nr, 4, 1, fi) == 1 && nr == n_ref) {

@@ -59,6 +59,18 @@ def test_reader_without_index(tmp_path):
             assert np.array_equal(r.pos, c.batch.pos) and np.array_equal(r.cigar, c.batch.cigar)
 
 
+def test_index_beside_the_stem(tmp_path):
+    """`x.bai` beside `x.bam` is found like `x.bam.bai` (the second place samtools' bam_index_load looks)."""
+    spec = synth.SynthSpec(contigs=[("c1", 30_000), ("c2", 20_000)], depth=8, seed=7)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "ix"), cs)
+    os.rename(bam + ".bai", bam[:-1] + "i")
+    with hostlib.Bam(bam) as b:
+        assert b.has_index
+        for tid, c in enumerate(cs):
+            assert np.array_equal(b.read_target(tid).pos, c.batch.pos)
+
+
 def test_golden_bam_decodes_and_hashes():
     names, batches = golden_batches()
     assert names == ["chrG", "chrH", "chrZ"]
