@@ -56,18 +56,40 @@ struct grom_bam {
 static inline uint32_t rd_u32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 static inline int32_t  rd_i32(const uint8_t *p) { return (int32_t)rd_u32(p); }
 
-/* inflate one BGZF block located at file offset `off`; returns isize or -1; *clen = block size */
+/* header of the BGZF block at h (`avail` bytes readable): gzip member with the FEXTRA flag whose extra field holds the 'B','C' subfield
+ * (block size - 1).  htslib writes that subfield alone (XLEN = 6); other subfields before or after it are stepped over.  Returns 0 and
+ * the block size and the offset of the deflate stream, or -1. */
+static int bgzf_block_header(const uint8_t *h, int64_t avail, int *bsize, int *coff)
+{
+    if (avail < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return -1;
+    const int xlen = h[10] | (h[11] << 8);
+    if (12 + (int64_t)xlen > avail) return -1;
+    int bs = -1;
+    for (int p = 12; p + 4 <= 12 + xlen; ) {
+        const int slen = h[p + 2] | (h[p + 3] << 8);
+        if (p + 4 + slen > 12 + xlen) return -1;
+        if (h[p] == 'B' && h[p + 1] == 'C' && slen == 2) bs = (h[p + 4] | (h[p + 5] << 8)) + 1;
+        p += 4 + slen;
+    }
+    if (bs < 12 + xlen + 8 + 2) return -1;             /* header + (at least) the empty deflate stream + CRC32 + ISIZE */
+    *bsize = bs; *coff = 12 + xlen;
+    return 0;
+}
+
+/* inflate one BGZF block located at file offset `off`; returns isize or -1; *bsize_out = block size */
 static int bgzf_inflate_at(FILE *f, int64_t off, uint8_t *raw, uint8_t *dst, int *bsize_out)
 {
-    uint8_t hdr[18];
+    uint8_t hdr[12 + 1024];
     if (fseeko(f, off, SEEK_SET) != 0) return -1;
     if (fread(hdr, 1, 18, f) != 18) return -1;
-    if (hdr[0] != 0x1f || hdr[1] != 0x8b || !(hdr[3] & 4)) return -1;
-    int xlen = hdr[10] | (hdr[11] << 8);
-    if (xlen != 6 || hdr[12] != 'B' || hdr[13] != 'C') return -1;
-    int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
-    int clen = bsize - 18;
-    if (bsize < 26) return -1;                         /* header + empty deflate stream + CRC32 + ISIZE */
+    const int xlen = hdr[10] | (hdr[11] << 8);
+    if (xlen > 1024) return -1;
+    if (xlen > 6 && fread(hdr + 18, 1, (size_t)xlen - 6, f) != (size_t)xlen - 6) return -1;
+    int bsize, coff;
+    if (bgzf_block_header(hdr, 12 + (xlen > 6 ? xlen : 6), &bsize, &coff) < 0) return -1;
+    if (fseeko(f, off + coff, SEEK_SET) != 0) return -1;
+    int clen = bsize - coff;
+    if (clen > 65536 + 64) return -1;
     if ((int)fread(raw, 1, clen, f) != clen) return -1;
     uint32_t isize = rd_u32(raw + clen - 4);
     z_stream s; memset(&s, 0, sizeof(s));
@@ -441,7 +463,7 @@ static void parse_sa(const uint8_t *aux, int l_aux, const char *target_name,
 static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 #define TRACE_MARK(what) do { if (trace) { double t_ = now_ms(); fprintf(stderr, "[bamio] %-22s %8.2f ms\n", what, t_ - t_last); t_last = t_; } } while (0)
 
-typedef struct { int64_t off; int bsize; int isize; int64_t uoff; } blkinfo;
+typedef struct { int64_t off; int bsize, coff, isize; int64_t uoff; } blkinfo;      /* coff: where the deflate stream starts inside the block */
 
 /* reads with a first XP / SA entry, collected per thread during the fill pass (a small minority of the reads) */
 typedef struct { int32_t idx, pos, start_adj, end_adj, end_adj_indel; int16_t mapq; uint8_t strand, same_chr; } sa_ent;
@@ -633,15 +655,13 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     if (vend != 0) {
         int64_t off = (int64_t)(vbeg >> 16), endoff = (vend == UINT64_MAX) ? INT64_MAX : (int64_t)(vend >> 16);
         while (off <= endoff && off + 18 <= cf_len) {
-            const uint8_t *hdr = cf + off;
-            if (hdr[0] != 0x1f || hdr[1] != 0x8b) { free(blk); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
-            const int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
-            if (bsize < 26 || !(hdr[3] & 4) || (hdr[10] | (hdr[11] << 8)) != 6 || hdr[12] != 'B' || hdr[13] != 'C') { free(blk); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
+            int bsize, coff;
+            if (bgzf_block_header(cf + off, cf_len - off, &bsize, &coff) < 0) { free(blk); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
             if (off + bsize > cf_len) break;                      /* truncated last block */
             const uint32_t isize = rd_u32(cf + off + bsize - 4);
             if (isize > 65536) { free(blk); return fail("%s: bad BGZF block at %lld", b->path, (long long)off); }
             if (nblk == capblk) { capblk = capblk ? capblk * 2 : 1024; blk = (blkinfo *)realloc(blk, capblk * sizeof(blkinfo)); }
-            blk[nblk].off = off; blk[nblk].bsize = bsize; blk[nblk].isize = (int)isize; nblk++;
+            blk[nblk].off = off; blk[nblk].bsize = bsize; blk[nblk].coff = coff; blk[nblk].isize = (int)isize; nblk++;
             off += bsize;
         }
     }
@@ -666,7 +686,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         #pragma omp for schedule(dynamic, 16)
         for (int64_t i = 0; i < nblk; i++) {
             const uint8_t *blkp = cf + blk[i].off;
-            if (bgzf_inflate_block(ctx, blkp + 18, blk[i].bsize - 26, u + blk[i].uoff, blk[i].isize, rd_u32(blkp + blk[i].bsize - 8)) < 0) {
+            if (bgzf_inflate_block(ctx, blkp + blk[i].coff, blk[i].bsize - blk[i].coff - 8, u + blk[i].uoff, blk[i].isize, rd_u32(blkp + blk[i].bsize - 8)) < 0) {
                 #pragma omp atomic write
                 bad = 1;
             }
@@ -908,13 +928,12 @@ int gromhost_bam_library_stats(grom_bam *b, int rd_min_mapq, int n_threads, int 
     while (rc == 0 && !full && !ended) {
         int nb = 0; int64_t utotal = 0;
         while (nb < W && off + 18 <= cf_len) {
-            const uint8_t *hdr = cf + off;
-            const int bsize = (hdr[16] | (hdr[17] << 8)) + 1;
-            if (hdr[0] != 0x1f || hdr[1] != 0x8b || bsize < 26 || !(hdr[3] & 4) || (hdr[10] | (hdr[11] << 8)) != 6 || hdr[12] != 'B' || hdr[13] != 'C') { rc = fail("%s: bad BGZF block at %lld", b->path, (long long)off); break; }
+            int bsize, coff;
+            if (bgzf_block_header(cf + off, cf_len - off, &bsize, &coff) < 0) { rc = fail("%s: bad BGZF block at %lld", b->path, (long long)off); break; }
             if (off + bsize > cf_len) { ended = 1; break; }
             const uint32_t isize = rd_u32(cf + off + bsize - 4);
             if (isize > 65536) { rc = fail("%s: bad BGZF block at %lld", b->path, (long long)off); break; }
-            blk[nb].off = off; blk[nb].bsize = bsize; blk[nb].isize = (int)isize; blk[nb].uoff = utotal; utotal += isize; nb++;
+            blk[nb].off = off; blk[nb].bsize = bsize; blk[nb].coff = coff; blk[nb].isize = (int)isize; blk[nb].uoff = utotal; utotal += isize; nb++;
             off += bsize;
         }
         if (rc) break;
@@ -933,7 +952,7 @@ int gromhost_bam_library_stats(grom_bam *b, int rd_min_mapq, int n_threads, int 
             #pragma omp for schedule(dynamic, 4)
             for (int i = 0; i < nb; i++) {
                 const uint8_t *bp = cf + blk[i].off;
-                if (bgzf_inflate_block(ctx, bp + 18, blk[i].bsize - 26, win + carry + blk[i].uoff, blk[i].isize, rd_u32(bp + blk[i].bsize - 8)) < 0) {
+                if (bgzf_inflate_block(ctx, bp + blk[i].coff, blk[i].bsize - blk[i].coff - 8, win + carry + blk[i].uoff, blk[i].isize, rd_u32(bp + blk[i].bsize - 8)) < 0) {
                     #pragma omp atomic write
                     bad = 1;
                 }

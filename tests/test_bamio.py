@@ -71,6 +71,40 @@ def test_index_beside_the_stem(tmp_path):
             assert np.array_equal(b.read_target(tid).pos, c.batch.pos)
 
 
+def test_bgzf_blocks_with_further_extra_subfields(tmp_path):
+    """The gzip extra field of a BGZF block may hold subfields besides 'BC' (htslib writes 'BC' alone): the committed BAM re-packed with one
+    before and one after it decodes to the same batches and statistics."""
+    import struct
+    import zlib
+    from util import GOLDEN
+    raw = open(os.path.join(GOLDEN, "g1.bam"), "rb").read()
+    data, off = b"", 0
+    while off + 18 <= len(raw):
+        bs = struct.unpack_from("<H", raw, off + 16)[0] + 1
+        data += zlib.decompressobj(-15).decompress(raw[off + 18:off + bs - 8]); off += bs
+
+    def block(chunk, k):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        d = co.compress(chunk) + co.flush()
+        before = b"XY" + struct.pack("<H", 3) + b"abc" if k % 2 else b""
+        after = b"ZZ" + struct.pack("<H", 0) if k % 3 == 0 else b""
+        xlen = len(before) + 6 + len(after)
+        bsize = 12 + xlen + len(d) + 8
+        extra = before + b"BC" + struct.pack("<HH", 2, bsize - 1) + after
+        return b"\x1f\x8b\x08\x04" + b"\0" * 6 + struct.pack("<H", xlen) + extra + d + struct.pack("<II", zlib.crc32(chunk), len(chunk))
+    out = b"".join(block(data[i:i + 50_001], k) for k, i in enumerate(range(0, len(data), 50_001))) + block(b"", 7)
+    p = tmp_path / "x.bam"
+    p.write_bytes(out)                                                    # no index: the offsets of the original no longer apply
+    with hostlib.Bam(os.path.join(GOLDEN, "g1.bam")) as a, hostlib.Bam(str(p)) as b:
+        assert a.names == b.names and not b.has_index
+        assert a.library_stats(20) == b.library_stats(20)
+        for t in range(len(a.names)):
+            x, y = a.read_target(t, keep_names=True), b.read_target(t, keep_names=True)
+            assert x.n_reads == y.n_reads > 0
+            for k in ("pos", "flag", "cigar", "seq4", "qual", "qname_hash", "sa_pos", "seq2", "qual2"):
+                assert np.array_equal(getattr(x, k), getattr(y, k)), k
+
+
 def test_golden_bam_decodes_and_hashes():
     names, batches = golden_batches()
     assert names == ["chrG", "chrH", "chrZ"]
