@@ -15,30 +15,78 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "gromhost.h"
+
+/* one SNV record (depth filter, genotype string, text); 0 = filtered out.  buf must have 1024 bytes of room */
+static int snv_record(const grom_params *p, const char *chr_name, const char *fasta, const grom_snv_cand *c, double ave_rd, char *buf)
+{
+    char gt[512];
+    if (!(c->v[GA_RC_ALL] <= round(p->snv_rd_min_factor * ave_rd) || c->ratio >= p->high_cov_min_snv_ratio)) return 0;
+    int cn = (int)round(c->ratio * p->ploidy);
+    if (cn == 0) cn = 1;
+    for (int k = 0; k < p->ploidy && k < 250; k++) { gt[2 * k] = k < cn ? '1' : '0'; gt[2 * k + 1] = k < p->ploidy - 1 ? '/' : '\0'; }
+    const int nb = c->v[GA_SNV_A + c->base];
+    return snprintf(buf, 1024,
+                    "%s\t%d\t\t%c\t%c\t.\t.\t.\tGT:PR:AF:A:C:G:T:AL:CL:GL:TL:BQ:MQ:PIR:FS\t%s:%e:%e:%d:%d:%d:%d:%d:%d:%d:%d:%.2f:%.2f:%.2f:%.2f\n",
+                    chr_name, c->pos + 1, fasta[c->pos], "ACGT"[c->base], gt, c->pr, c->ratio,
+                    c->v[GA_SNV_A], c->v[GA_SNV_C], c->v[GA_SNV_G], c->v[GA_SNV_T],
+                    c->v[GA_SNVLOW_A], c->v[GA_SNVLOW_C], c->v[GA_SNVLOW_G], c->v[GA_SNVLOW_T],
+                    (double)c->v[GA_BQ_ALL] / (double)c->v[GA_RC_ALL], (double)c->v[GA_MQ_ALL] / (double)c->v[GA_RC_ALL],
+                    (double)c->v[GA_PIR_A + c->base] / (double)nb, (double)c->v[GA_FS_A + c->base] / (double)nb);
+}
+
+#define SNV_PAR_MIN 4096          /* candidates from which the records are formatted by all threads (the text is glibc's printf either way) */
 
 int64_t gromhost_vcf_snv(const grom_params *p, const char *chr_name, const char *fasta,
                          const grom_snv_cand *snv, int64_t n, double ave_rd, char *buf, int64_t cap)
 {
-    int64_t w = 0;
-    char gt[512];
-    for (int64_t i = 0; i < n; i++) {
-        const grom_snv_cand *c = &snv[i];
-        if (!(c->v[GA_RC_ALL] <= round(p->snv_rd_min_factor * ave_rd) || c->ratio >= p->high_cov_min_snv_ratio)) continue;
-        int cn = (int)round(c->ratio * p->ploidy);
-        if (cn == 0) cn = 1;
-        for (int k = 0; k < p->ploidy && k < 250; k++) { gt[2 * k] = k < cn ? '1' : '0'; gt[2 * k + 1] = k < p->ploidy - 1 ? '/' : '\0'; }
-        const int nb = c->v[GA_SNV_A + c->base];
-        if (cap - w < 1024) return -1;
-        w += snprintf(buf + w, (size_t)(cap - w),
-                      "%s\t%d\t\t%c\t%c\t.\t.\t.\tGT:PR:AF:A:C:G:T:AL:CL:GL:TL:BQ:MQ:PIR:FS\t%s:%e:%e:%d:%d:%d:%d:%d:%d:%d:%d:%.2f:%.2f:%.2f:%.2f\n",
-                      chr_name, c->pos + 1, fasta[c->pos], "ACGT"[c->base], gt, c->pr, c->ratio,
-                      c->v[GA_SNV_A], c->v[GA_SNV_C], c->v[GA_SNV_G], c->v[GA_SNV_T],
-                      c->v[GA_SNVLOW_A], c->v[GA_SNVLOW_C], c->v[GA_SNVLOW_G], c->v[GA_SNVLOW_T],
-                      (double)c->v[GA_BQ_ALL] / (double)c->v[GA_RC_ALL], (double)c->v[GA_MQ_ALL] / (double)c->v[GA_RC_ALL],
-                      (double)c->v[GA_PIR_A + c->base] / (double)nb, (double)c->v[GA_FS_A + c->base] / (double)nb);
+    int T = 1;
+#ifdef _OPENMP
+    int64_t par_min = SNV_PAR_MIN;
+    { const char *e = getenv("GROMHOST_SNV_PAR_MIN"); if (e && *e) par_min = atoll(e); }          /* tests: force / forbid the all-thread path */
+    if (n >= par_min) { T = omp_get_max_threads(); if (T > 64) T = 64; if (T > n / 64) T = (int)(n / 64); if (T < 1) T = 1; }
+#endif
+    if (T == 1) {
+        int64_t w = 0;
+        for (int64_t i = 0; i < n; i++) {
+            if (cap - w < 1024) return -1;
+            w += snv_record(p, chr_name, fasta, &snv[i], ave_rd, buf + w);
+        }
+        return w;
     }
-    return w;
+    /* a contig of chromosome size has tens of thousands of candidates and printf's %e takes microseconds: contiguous shares of the
+     * candidates are formatted into per-thread buffers and laid end to end, which is the same text in the same order */
+    char *part[64]; int64_t len[64]; int bad = 0;
+    memset(part, 0, sizeof(part)); memset(len, 0, sizeof(len));
+#ifdef _OPENMP
+    #pragma omp parallel for schedule(static, 1) num_threads(T)
+#endif
+    for (int k = 0; k < T; k++) {
+        const int64_t i0 = n * k / T, i1 = n * (k + 1) / T;
+        int64_t c = (i1 - i0) * 192 + 2048, w = 0;
+        char *b = (char *)malloc((size_t)c);
+        for (int64_t i = i0; i < i1 && b; i++) {
+            if (c - w < 1024) { c *= 2; char *b2 = (char *)realloc(b, (size_t)c); if (!b2) { free(b); b = NULL; break; } b = b2; }
+            w += snv_record(p, chr_name, fasta, &snv[i], ave_rd, b + w);
+        }
+        if (!b) {
+#ifdef _OPENMP
+            #pragma omp atomic write
+#endif
+            bad = 1;
+        }
+        part[k] = b; len[k] = w;
+    }
+    int64_t total = 0;
+    for (int k = 0; k < T; k++) total += len[k];
+    if (bad || cap - total < 1024) { for (int k = 0; k < T; k++) free(part[k]); return bad ? -2 : -1; }
+    int64_t o = 0;
+    for (int k = 0; k < T; k++) { memcpy(buf + o, part[k], (size_t)len[k]); o += len[k]; free(part[k]); }
+    return total;
 }
 
 /* homopolymer length as the reference measures it: run of fasta[left] to the left of `left` (inclusive), and the
@@ -309,18 +357,27 @@ int64_t gromhost_vcf_contig(const grom_params *p, const char *chr_name, const ch
 {
     int64_t w = 0, k;
 #define ADD(call) do { k = (call); if (k < 0) { w = -1; goto done; } w += k; } while (0)
+    /* GROMHOST_TRACE=1: stage times on stderr */
+    const int trace = getenv("GROMHOST_TRACE") != NULL;
+    struct timespec ts0; if (trace) clock_gettime(CLOCK_MONOTONIC, &ts0);
+#define MARK(what) do { if (trace) { struct timespec t1_; clock_gettime(CLOCK_MONOTONIC, &t1_); fprintf(stderr, "[vcf] %-22s %8.2f ms\n", what, (t1_.tv_sec - ts0.tv_sec) * 1e3 + (t1_.tv_nsec - ts0.tv_nsec) * 1e-6); ts0 = t1_; } } while (0)
     gromhost_sv_lists_t L;
     grom_sv_pair *dup2 = NULL, *del2 = NULL, *invf2 = NULL, *invr2 = NULL;
     delrec *small = NULL;
     if (gromhost_sv_lists(p, sv_ev, n_sv_ev, &L) != 0) return -2;
+    MARK("sv lists");
     const int64_t n_dup2 = merge_pairs(p, L.dup, L.n_dup, &dup2), n_del2 = merge_pairs(p, L.del, L.n_del, &del2);
     const int64_t n_invf2 = merge_pairs(p, L.inv_f, L.n_inv_f, &invf2), n_invr2 = merge_pairs(p, L.inv_r, L.n_inv_r, &invr2);
+    MARK("merge pairs");
     ADD(gromhost_vcf_snv(p, chr_name, fasta, snv, n_snv, snv_ave_rd, buf + w, cap - w));
+    MARK("snv records");
     for (int64_t a = 0; a < n_dup2; a++) if (pair_passes(p, &dup2[a], 1)) ADD(pair_record(p, chr_name, "DUP", &dup2[a], buf + w, cap - w));
     ADD(inv_records(p, chr_name, invf2, n_invf2, invr2, n_invr2, 0, buf + w, cap - w));
     ADD(inv_records(p, chr_name, invr2, n_invr2, invf2, n_invf2, 1, buf + w, cap - w));
     ADD(ins_records(p, chr_name, L.ins, L.n_ins, buf + w, cap - w));
+    MARK("dup inv ins records");
     ADD(gromhost_vcf_ins(p, chr_name, fasta, chr_len, ins, n_ins, buf + w, cap - w));
+    MARK("small insertions");
     {
         int idx;
         small = smalldel_list(p, del_ev, n_del_ev, &idx);
@@ -341,12 +398,15 @@ int64_t gromhost_vcf_contig(const grom_params *p, const char *chr_name, const ch
             if (!covered) ADD(pair_record(p, chr_name, "DEL", q, buf + w, cap - w));
         }
     }
+    MARK("deletions");
     ADD(gromhost_vcf_cnv(p, chr_name, fasta, chr_len, cnv, n_cnv, buf + w, cap - w));
+    MARK("read-depth calls");
 done:
     free(dup2); free(del2); free(invf2); free(invr2); free(small);
     gromhost_sv_lists_free(&L);
     return w;
 #undef ADD
+#undef MARK
 }
 
 /* read-depth CNV calls: emission filter and text of src/GROM.c:17197-17240, 17280, 17414 */

@@ -225,13 +225,13 @@ def pval2sd():
     return pv, sd
 
 
-def _vcf(fn_name, params, chr_name, fasta, *args):
+def _vcf(fn_name, params, chr_name, fasta, *args, room: int = 0):
     from .params import Params
     L = lib()
     fn = getattr(L, fn_name)
     fn.restype = C.c_int64
     fa = np.ascontiguousarray(fasta, dtype=np.uint8)
-    cap = 1 << 16
+    cap = max(1 << 16, int(room))
     while True:
         buf = C.create_string_buffer(cap)
         n = fn(C.byref(params), chr_name.encode(), fa.ctypes.data_as(C.c_char_p), *args, buf, C.c_int64(cap))
@@ -304,7 +304,8 @@ def vcf_contig(params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, snv_av
                                                           (sv_ev, SV_EVENT_DTYPE), (cnv_calls, CNV_CALL_DTYPE))]
     return _vcf("gromhost_vcf_contig", params, chr_name, fasta, C.c_int64(len(fasta)), C.c_void_p(a[0].ctypes.data), C.c_int64(len(a[0])),
                 C.c_double(snv_ave_rd), C.c_void_p(a[1].ctypes.data), C.c_int64(len(a[1])), C.c_void_p(a[2].ctypes.data), C.c_int64(len(a[2])),
-                C.c_void_p(a[3].ctypes.data), C.c_int64(len(a[3])), C.c_void_p(a[4].ctypes.data), C.c_int64(len(a[4])))
+                C.c_void_p(a[3].ctypes.data), C.c_int64(len(a[3])), C.c_void_p(a[4].ctypes.data), C.c_int64(len(a[4])),
+                room=224 * len(a[0]) + 320 * (len(a[1]) + len(a[2]) + len(a[3]) + len(a[4])) + (1 << 16))     # every candidate as a record: no refused first call
 
 
 def library_stats(batches, rd_min_mapq: int = 20) -> dict:

@@ -72,3 +72,33 @@ def test_contig_writer_all_record_classes_against_reference_vcf():
     # per-class writers agree with the one-call writer on their share
     assert hostlib.vcf_snv(prm, "chra", g["fasta"], g["snv"], float(g["snv_ave_rd"])) == "".join(l for l in ref if l.split("\t")[2] == "")
     assert hostlib.vcf_cnv(prm, "chra", g["cnv"]) == "".join(l for l in ref if "\tSD:Z:CN:CS\t" in l)
+
+
+def test_snv_records_formatted_by_all_threads_equal_the_serial_text(monkeypatch):
+    """From a few thousand candidates on, gromhost_vcf_snv formats contiguous shares of them on all threads and lays the pieces end to end
+    (printf's %e costs microseconds per record and a chromosome has tens of thousands): same bytes as one thread, also when the shares are
+    uneven, when most candidates are filtered out, and through the one-call contig writer.  Forced here with GROMHOST_SNV_PAR_MIN."""
+    from grom_b200.params import Params
+    g = np.load(os.path.join(GOLDEN, "g4_vcf.npz"))
+    m = g["mean"]
+    prm = Params.default(insert_mean=int(max(m[0], m[1])), lseq=int(m[1]), insert_min=int(m[2]), insert_max=int(m[3]))
+    fa, ave = g["fasta"], float(g["snv_ave_rd"])
+    base = g["snv"]
+    assert len(base) > 200
+    snv = np.concatenate([base] * 9)[: 8 * len(base) + 37].copy()       # ~10 k candidates, not a multiple of anything
+    snv["pr"][::7] *= 1e-200                                             # the slow corner of %e
+    snv["ratio"][5::11] = 0.0                                            # ... and candidates the depth filter drops, in runs of different lengths per share
+    snv["v"][5::11] = snv["v"][5::11] + 1000
+    for par_min, threads in (("1", None), ("1", "3"), ("100000000", None)):
+        monkeypatch.setenv("GROMHOST_SNV_PAR_MIN", par_min)
+        if threads:
+            monkeypatch.setenv("OMP_NUM_THREADS", threads)
+        text = hostlib.vcf_snv(prm, "chra", fa, snv, ave)
+        if par_min == "1" and threads is None:
+            first = text
+        assert text == first
+    assert first.count("\n") > 0.8 * len(snv) * 0.9 and "e-2" in first
+    monkeypatch.setenv("GROMHOST_SNV_PAR_MIN", "1")
+    a = hostlib.vcf_contig(prm, "chra", fa, g["snv"], ave, g["ins"], g["del_ev"], g["sv_ev"], g["cnv"])
+    monkeypatch.setenv("GROMHOST_SNV_PAR_MIN", "100000000")
+    assert a == hostlib.vcf_contig(prm, "chra", fa, g["snv"], ave, g["ins"], g["del_ev"], g["sv_ev"], g["cnv"])

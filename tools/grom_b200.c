@@ -306,6 +306,10 @@ static void *lane_main(void *arg)
         int64_t nrec = 0;
         if (!bad) {
             int64_t n;
+            {   /* room for every candidate as a record up front: a refused call would format the contig again */
+                const size_t want = (size_t)res.n_snv * 224 + (size_t)(res.n_ins + res.n_del + res.n_sv + cnv.n_calls) * 320 + (1 << 16);
+                if (want > cap) { cap = want; text = (char *)realloc(text, cap); }
+            }
             for (;;) {
                 n = gromhost_vcf_contig(&o->prm, lname, chars, flen, res.snv, res.n_snv, res.snv_ave_rd, res.ins, res.n_ins, res.del_ev, res.n_del,
                                         res.sv_ev, res.n_sv, cnv.calls, cnv.n_calls, text, (int64_t)cap);
