@@ -7,6 +7,9 @@
  * structure-of-arrays batch of include/grom_reads.h.  Independent of
  * samtools/htslib; needs only zlib.
  */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE            /* mremap */
+#endif
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -486,34 +489,37 @@ static int reclist_grow(reclist *r, int keep_names)
 
 /* One pass over the record chain from offset p up to (not including) offset `stop`: validates the layout of every record of the target
  * (a truncated or corrupt file must not make the fill pass read past the inflated data) and lists them.  `started` says whether records
- * of the target came before p.  Outcome in *term: 0 = arrived exactly at `stop`; 1 = the chain ended (end of data, a record past the
- * target or in the unplaced tail); 2 = stepped over `stop` (it was no record boundary); 3 = corrupt record at *err_at; 4 = memory.
- * *lead = the first record seen was not one of the target. */
-typedef struct { int term, lead; int64_t err_at; } walk_end;
+ * of the target came before p.  Outcome in *term: 0 = arrived exactly at `stop`; 1 = the chain ended (a record past the target or in the
+ * unplaced tail, or a block_size that cannot be one); 5 = the data ended (inside a record, or exactly behind one): the chain may go on
+ * in data not yet inflated; 2 = stepped over `stop` (it was no record boundary); 3 = corrupt record at *err_at; 4 = memory.
+ * *stop_at = where the walk stopped; *lead = the first record seen was not one of the target. */
+typedef struct { int term, lead; int64_t err_at, stop_at; } walk_end;
 static void walk_records(const uint8_t *u, int64_t utotal, int64_t p, int64_t stop, int started, int tid, int keep_names, reclist *r, walk_end *w)
 {
     int first = 1;
-    w->term = 1; w->lead = 0; w->err_at = -1;
+    w->term = 5; w->lead = 0; w->err_at = -1;
     while (p + 36 <= utotal) {
-        if (p >= stop) { w->term = (p == stop) ? 0 : 2; return; }
+        if (p >= stop) { w->term = (p == stop) ? 0 : 2; w->stop_at = p; return; }
         const int32_t bl = rd_i32(u + p);
-        if (bl < 32 || p + 4 + bl > utotal) return;
+        if (bl < 32) { w->term = 1; w->stop_at = p; return; }
+        if (p + 4 + bl > utotal) { w->stop_at = p; return; }
         const int32_t rtid = rd_i32(u + p + 4);
         if (rtid == tid) {
             started = 1;
             const uint32_t bmq = rd_u32(u + p + 12), fnc = rd_u32(u + p + 16); const int32_t lq = rd_i32(u + p + 20);
-            if (lq < 0 || 32 + (int64_t)(bmq & 0xff) + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl) { w->term = 3; w->err_at = p; return; }
-            if (r->n == r->cap && reclist_grow(r, keep_names) < 0) { w->term = 4; return; }
+            if (lq < 0 || 32 + (int64_t)(bmq & 0xff) + 4 * (int64_t)(fnc & 0xffff) + ((int64_t)lq + 1) / 2 + (int64_t)lq > (int64_t)bl) { w->term = 3; w->err_at = p; w->stop_at = p; return; }
+            if (r->n == r->cap && reclist_grow(r, keep_names) < 0) { w->term = 4; w->stop_at = p; return; }
             r->recoff[r->n] = p; r->cig_off[r->n] = (uint64_t)r->n_cig; r->base_off[r->n] = (uint64_t)r->n_slots;
             if (keep_names) r->name_off[r->n] = (uint64_t)r->n_name;
             r->n++; r->n_cig += fnc & 0xffff; r->n_slots += (lq + GROM_BASE_ALIGN - 1) / GROM_BASE_ALIGN * GROM_BASE_ALIGN; r->n_name += bmq & 0xff;
         } else {
             if (first) w->lead = 1;
-            if (started || rtid > tid || rtid < 0) return;      /* coordinate-sorted: past the target (or into the unplaced tail) */
+            if (started || rtid > tid || rtid < 0) { w->term = 1; w->stop_at = p; return; }      /* coordinate-sorted: past the target (or into the unplaced tail) */
         }
         first = 0;
         p += 4 + bl;
     }
+    w->stop_at = p;
     if (p >= stop) w->term = (p == stop) ? 0 : 2;                /* the chain may end exactly where the next range begins */
 }
 
@@ -547,10 +553,11 @@ static inline int record_plausible(const uint8_t *u, int64_t utotal, int64_t p, 
  * guess counts only if the walk of the share before it arrives exactly at it, which makes it a boundary of the true chain by induction
  * from the known first record.  Any miss falls back to the one-thread walk, so the result never depends on the guesses.
  * Returns 0, -1 (corrupt record, message set) or -2 (memory); the lists of all shares are concatenated into *out. */
-static int walk_records_parallel(const uint8_t *u, int64_t utotal, int64_t p0, int tid, int n_targets, int keep_names, int n_threads,
-                                 const char *path, reclist *out)
+static int walk_records_parallel(const uint8_t *u, int64_t utotal, int64_t p0, int started0, int tid, int n_targets, int keep_names, int n_threads,
+                                 const char *path, reclist *out, walk_end *end)
 {
     memset(out, 0, sizeof(*out));
+    end->term = 5; end->lead = 0; end->err_at = -1; end->stop_at = p0;
     int T = n_threads;
     int64_t par_min = WALK_PAR_MIN;
     { const char *e = getenv("GROMHOST_WALK_PAR_MIN"); if (e && *e) par_min = atoll(e); }      /* tests: force / forbid the all-thread walk */
@@ -583,17 +590,19 @@ static int walk_records_parallel(const uint8_t *u, int64_t utotal, int64_t p0, i
         for (int k = 0; k < T; k++) {
             if (reclist_grow(&rl[k], keep_names) < 0) { we[k].term = 4; grow_bad = 1; continue; }
             if (k > 0 && start[k] == start[k + 1]) { we[k].term = 0; we[k].lead = 0; we[k].err_at = -1; continue; }    /* empty share */
-            walk_records(u, utotal, start[k], start[k + 1], 0, tid, keep_names, &rl[k], &we[k]);
+            walk_records(u, utotal, start[k], start[k + 1], k == 0 ? started0 : 0, tid, keep_names, &rl[k], &we[k]);
         }
         /* which shares are on the true chain: the first is; a share is reached when the one before arrived exactly at its start */
-        int started = 0, fallback = grow_bad;
+        int started = started0, fallback = grow_bad;
         for (int k = 0; k < T && !fallback; k++) {
-            if (started && we[k].lead && !(k > 0 && start[k] == start[k + 1])) break;          /* a foreign record after the target began ends the chain */
+            const int empty = k > 0 && start[k] == start[k + 1];
+            if (started && we[k].lead && !empty) { end->term = 1; end->stop_at = start[k]; break; }          /* a foreign record after the target began ends the chain */
             if (we[k].term == 2 || we[k].term == 4) { fallback = 1; break; }
             n_used = k + 1;
             if (rl[k].n) started = 1;
             if (we[k].term == 3) { rc = corrupt_record(path, u, we[k].err_at); break; }
-            if (we[k].term == 1) break;
+            if (!empty) { end->term = we[k].term; end->stop_at = we[k].stop_at; }
+            if (we[k].term == 1 || we[k].term == 5) break;
             /* a share that began after records of the target (started) but met a foreign record first was handled above; one that began
              * before the target and skipped foreign records is what the one-thread walk does as well */
         }
@@ -602,10 +611,10 @@ static int walk_records_parallel(const uint8_t *u, int64_t utotal, int64_t p0, i
     }
     if (T == 1) {
         if (reclist_grow(&rl[0], keep_names) < 0) { free(rl[0].recoff); free(rl[0].cig_off); free(rl[0].base_off); free(rl[0].name_off); return -2; }
-        walk_records(u, utotal, p0, INT64_MAX, 0, tid, keep_names, &rl[0], &we[0]);
+        walk_records(u, utotal, p0, INT64_MAX, started0, tid, keep_names, &rl[0], &we[0]);
         if (we[0].term == 3) rc = corrupt_record(path, u, we[0].err_at);
         else if (we[0].term == 4) rc = -2;
-        if (rc == 0) { *out = rl[0]; return 0; }
+        if (rc == 0) { *out = rl[0]; *end = we[0]; return 0; }
         free(rl[0].recoff); free(rl[0].cig_off); free(rl[0].base_off); free(rl[0].name_off);
         return rc;
     }
@@ -634,6 +643,85 @@ static int walk_records_parallel(const uint8_t *u, int64_t utotal, int64_t p0, i
     return rc;
 }
 
+/* ---- the batch under construction: every array grows with the windows of the target that have been decoded so far */
+typedef struct { int64_t reads, cig, slots, names; } batch_caps;
+
+static void *grow_zeroed(void *p, size_t old_bytes, size_t new_bytes)
+{
+    void *q = realloc(p, new_bytes);
+    if (q && new_bytes > old_bytes) memset((char *)q + old_bytes, 0, new_bytes - old_bytes);
+    return q;
+}
+/* a large per-base array: stays a zero-filled anonymous mapping (moved by the kernel when it has to grow: no copy) */
+static int big_grow(uint8_t **p, size_t *maplen, size_t old_bytes, size_t new_bytes)
+{
+    if (*p == NULL) { *p = (uint8_t *)big_zalloc(new_bytes, maplen); return *p ? 0 : -1; }
+    if (*maplen) {
+        if (new_bytes <= *maplen) return 0;
+        const size_t n = (new_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+        void *q = mremap(*p, *maplen, n, MREMAP_MAYMOVE);
+        if (q == MAP_FAILED) return -1;
+#ifdef MADV_HUGEPAGE
+        if (!getenv("GROMHOST_NO_HUGEPAGE")) madvise(q, n, MADV_HUGEPAGE);
+#endif
+        *p = (uint8_t *)q; *maplen = n;
+        return 0;
+    }
+    if (new_bytes >= ((size_t)8 << 20)) {                          /* outgrew calloc: move into a mapping */
+        size_t ml; uint8_t *q = (uint8_t *)big_zalloc(new_bytes, &ml);
+        if (!q) return -1;
+        memcpy(q, *p, old_bytes); free(*p); *p = q; *maplen = ml;
+        return 0;
+    }
+    uint8_t *q = (uint8_t *)grow_zeroed(*p, old_bytes, new_bytes);
+    if (!q) return -1;
+    *p = q;
+    return 0;
+}
+
+/* room for at least the given totals (reads, CIGAR operations, base slots, name bytes); grows by doubling */
+static int batch_reserve(grom_batch *t, batch_caps *c, int64_t reads, int64_t cig, int64_t slots, int64_t names, int keep_names, int with_seq2, int64_t **exc_at)
+{
+    /* per-read arrays, CIGAR operations and names are written in full by the fill pass: no zero fill (it would touch every page from one
+     * thread); only the per-base arrays rely on zero padding, and those are fresh pages of a mapping */
+#define GR(ptr, type, oldn, newn) do { (void)(oldn); void *q_ = realloc(t->ptr, (size_t)(newn) * sizeof(type)); if (!q_) return -1; t->ptr = (type *)q_; } while (0)
+    if (reads > c->reads) {
+        int64_t n = c->reads ? c->reads * 2 : 1; if (n < reads) n = reads;
+        const int64_t o = c->reads;
+        GR(pos, int32_t, o, n); GR(mpos, int32_t, o, n); GR(tlen, int32_t, o, n); GR(mtid, int32_t, o, n); GR(l_qseq, int32_t, o, n);
+        GR(sa_pos, int32_t, o, n); GR(sa_start_adj, int32_t, o, n); GR(sa_end_adj, int32_t, o, n); GR(sa_end_adj_indel, int32_t, o, n);
+        GR(flag, uint16_t, o, n); GR(n_cigar, uint16_t, o, n); GR(sa_mapq, int16_t, o, n);
+        GR(mapq, uint8_t, o, n); GR(qname_len, uint8_t, o, n); GR(sa_strand, uint8_t, o, n); GR(sa_same_chr, uint8_t, o, n);
+        GR(qname_hash, uint64_t, o, n); GR(cigar_off, uint64_t, o, n); GR(base_off, uint64_t, o, n);
+        if (keep_names) GR(qname_off, uint64_t, o ? o + 1 : 0, n + 1);
+        if (with_seq2) { void *q_ = realloc(*exc_at, (size_t)(n + 1) * sizeof(int64_t)); if (!q_) return -1; *exc_at = (int64_t *)q_; }
+        c->reads = n;
+    }
+    if (cig > c->cig) {
+        int64_t n = c->cig ? c->cig * 2 : 1; if (n < cig) n = cig;
+        GR(cigar, uint32_t, c->cig, n);
+        c->cig = n;
+    }
+#undef GR
+    if (slots > c->slots) {
+        int64_t n = c->slots ? c->slots * 2 : 0; if (n < slots) n = slots;
+        const size_t o = (size_t)c->slots;
+        if (big_grow(&t->qual, &t->big_qual, c->slots ? o + 16 : 0, (size_t)n + 16) < 0) return -1;
+        if (big_grow(&t->seq4, &t->big_seq4, c->slots ? o / 2 + 16 : 0, (size_t)n / 2 + 16) < 0) return -1;
+        if (with_seq2 && big_grow(&t->seq2, &t->big_seq2, c->slots ? o / 4 + 16 : 0, (size_t)n / 4 + 16) < 0) return -1;
+        c->slots = n;
+    }
+    if (keep_names && names > c->names) {
+        int64_t n = c->names ? c->names * 2 : 1; if (n < names) n = names;
+        char *q = (char *)realloc(t->qname_pool, (size_t)n + 1);
+        if (!q) return -1;
+        t->qname_pool = q; c->names = n;
+    }
+    return 0;
+}
+
+#define WINDOW_BLOCKS_PER_THREAD 64     /* BGZF blocks a thread inflates per window (4 MB of records) */
+
 int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out)
 {
     if (tid < 0 || tid >= b->n_targets) return fail("target id %d out of range", tid);
@@ -643,7 +731,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         else { vbeg = b->tgt_beg[tid]; vend = b->tgt_end[tid]; }
     }
     const int trace = getenv("GROMHOST_TRACE") != NULL;
-    double t_last = trace ? now_ms() : 0;
+    double t_last = trace ? now_ms() : 0, t_infl = 0, t_walk = 0, t_fill = 0, t_mark = 0;
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #else
@@ -666,147 +754,196 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         }
     }
     int64_t utotal = 0;
-    for (int64_t i = 0; i < nblk; i++) { blk[i].uoff = utotal; utotal += blk[i].isize; }
+    for (int64_t i = 0; i < nblk; i++) utotal += blk[i].isize;
     TRACE_MARK("enumerate blocks");
-    /* 2. inflate in parallel, every block straight to its place in the inflated stream */
-    /* (anonymous mapping with huge pages where the kernel grants them: far fewer page faults while the blocks land, and a cheap unmap) */
-    const size_t u_len = ((size_t)utotal + 64 + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
-    uint8_t *u = (uint8_t *)mmap(NULL, u_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
-    if (u == (uint8_t *)MAP_FAILED) { free(blk); return fail("out of memory (%lld bytes of inflated BAM)", (long long)utotal); }
+
+    /* 2. the target is decoded a window of blocks at a time: inflate (every block straight to its place behind what the window before
+     * left over), list the records, make room in the batch, fill.  Only one window of inflated data exists at any time (host memory of a
+     * call = the batch + one window, not the batch + the whole inflated target), and it is the same, already touched buffer every time. */
+    int64_t WB = (int64_t)WINDOW_BLOCKS_PER_THREAD * n_threads;
+    if (WB < 128) WB = 128;
+    { const char *e = getenv("GROMHOST_WINDOW_BLOCKS"); if (e && atoll(e) > 0) WB = atoll(e); }      /* tests: tiny windows */
+    if (WB > nblk) WB = nblk > 0 ? nblk : 1;
+    size_t win_len = ((size_t)WB * 65536 + ((size_t)1 << 20) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    uint8_t *win = (uint8_t *)mmap(NULL, win_len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (win == (uint8_t *)MAP_FAILED) { free(blk); return fail("out of memory (%lld bytes of inflated BAM)", (long long)win_len); }
 #ifdef MADV_HUGEPAGE
-    if (!getenv("GROMHOST_NO_HUGEPAGE")) madvise(u, u_len, MADV_HUGEPAGE);
+    if (!getenv("GROMHOST_NO_HUGEPAGE")) madvise(win, win_len, MADV_HUGEPAGE);
 #endif
-    int bad = 0;
     const char *force = getenv("GROMHOST_INFLATE");
     const int own = !(force && !strcmp(force, "zlib"));            /* GROMHOST_INFLATE=zlib: every block through zlib */
-    #pragma omp parallel num_threads(n_threads)
-    {
-        struct grom_inflate_ctx *ctx = own ? (struct grom_inflate_ctx *)malloc(grom_inflate_ctx_size()) : NULL;
-        if (ctx) grom_inflate_ctx_init(ctx);
-        #pragma omp for schedule(dynamic, 16)
-        for (int64_t i = 0; i < nblk; i++) {
-            const uint8_t *blkp = cf + blk[i].off;
-            if (bgzf_inflate_block(ctx, blkp + blk[i].coff, blk[i].bsize - blk[i].coff - 8, u + blk[i].uoff, blk[i].isize, rd_u32(blkp + blk[i].bsize - 8)) < 0) {
-                #pragma omp atomic write
-                bad = 1;
-            }
-        }
-        free(ctx);
-    }
-    free(blk);
-    if (bad) { munmap(u, u_len); return fail("%s: BGZF inflate failed (corrupt deflate stream or CRC mismatch)", b->path); }
-    TRACE_MARK("inflate");
-    /* 3. the record chain: count, validate, offsets */
-    reclist rl;
-    const int wrc = walk_records_parallel(u, utotal, (nblk > 0) ? (int64_t)(vbeg & 0xffff) : 0, tid, b->n_targets, keep_names, n_threads, b->path, &rl);
-    if (wrc < 0) {
-        munmap(u, u_len);
-        return wrc == -2 ? fail("out of memory (record list)") : -1;
-    }
-    const int64_t n_reads = rl.n, n_cig = rl.n_cig, n_slots = rl.n_slots, n_name = rl.n_name;
-    if (keep_names) rl.name_off[n_reads] = (uint64_t)n_name;
-    TRACE_MARK("record chain");
-    /* 4. allocate */
+
     grom_batch *t = (grom_batch *)calloc(1, sizeof(*t));
     t->v.tid = tid;
-    size_t nr = (size_t)(n_reads > 0 ? n_reads : 1);
-#define AL(ptr, type, cnt) t->ptr = (type *)calloc((cnt), sizeof(type))
-    AL(pos, int32_t, nr); AL(mpos, int32_t, nr); AL(tlen, int32_t, nr); AL(mtid, int32_t, nr); AL(l_qseq, int32_t, nr);
-    AL(sa_pos, int32_t, nr); AL(sa_start_adj, int32_t, nr); AL(sa_end_adj, int32_t, nr); AL(sa_end_adj_indel, int32_t, nr);
-    AL(flag, uint16_t, nr); AL(n_cigar, uint16_t, nr); AL(sa_mapq, int16_t, nr);
-    AL(mapq, uint8_t, nr); AL(qname_len, uint8_t, nr); AL(sa_strand, uint8_t, nr); AL(sa_same_chr, uint8_t, nr);
-    AL(qname_hash, uint64_t, nr);
-    AL(cigar, uint32_t, (size_t)(n_cig > 0 ? n_cig : 1));
-    t->seq4 = (uint8_t *)big_zalloc((size_t)(n_slots / 2 + 16), &t->big_seq4); t->qual = (uint8_t *)big_zalloc((size_t)(n_slots + 16), &t->big_qual);
-    if (keep_names) AL(qname_pool, char, (size_t)(n_name + 1));
-    t->cigar_off = rl.cig_off; t->base_off = rl.base_off; t->qname_off = rl.name_off;
-    /* transport-compact forms (include/grom_reads.h GROM_LAYOUT_*), all lossless; the CUDA library rebuilds the canonical device arrays.
-     * The offsets are running sums by construction here; base qualities of current instruments take a handful of distinct values, so a
-     * 4- or 16-entry dictionary shrinks them to 2 or 4 bits; bases travel as 2 bits + a list of everything that is not A/C/G/T; the
-     * first-SA-entry fields exist for a small minority of reads. */
-    const int64_t ns = n_slots;
+    batch_caps caps; memset(&caps, 0, sizeof(caps));
     int64_t *exc_at = NULL;
-    if (ns > 0) { t->seq2 = (uint8_t *)big_zalloc((size_t)(ns / 4 + 16), &t->big_seq2); exc_at = (int64_t *)malloc(sizeof(int64_t) * (size_t)(n_reads + 1)); }
-#undef AL
-    TRACE_MARK("allocate");
-    /* 5. fill, parallel over contiguous ranges of reads.  In the same pass over a record: the 2-bit form of its bases (table-driven, two
-     * nibbles per lookup) with the number of its non-A/C/G/T bases, the set of quality values seen, and the reads with an XP / SA entry. */
+    const int do_seq2 = 1;
+    int64_t n_reads = 0, n_cig = 0, n_slots = 0, n_name = 0;
+    /* what is collected across the windows besides the arrays: quality values seen, per thread; reads with an XP / SA entry, in read order */
+    fill_local *loc = (fill_local *)calloc((size_t)n_threads, sizeof(fill_local));
+    sa_ent *sa_all = NULL; int64_t n_sa = 0, cap_sa = 0;
     uint8_t S2[256], SX[256];
     for (int v = 0; v < 256; v++) {
         const int hi = v >> 4, lo = v & 15;
         const int th = hi == 1 ? 0 : hi == 2 ? 1 : hi == 4 ? 2 : hi == 8 ? 3 : -1, tl = lo == 1 ? 0 : lo == 2 ? 1 : lo == 4 ? 2 : lo == 8 ? 3 : -1;
         S2[v] = (uint8_t)(((th < 0 ? 0 : th) << 2) | (tl < 0 ? 0 : tl)); SX[v] = (uint8_t)((th < 0) + (tl < 0));
     }
-    const int do_seq2 = (t->seq2 != NULL && exc_at != NULL);
     const char *tname = b->names[tid];
-    fill_local *loc = (fill_local *)calloc((size_t)n_threads, sizeof(fill_local));
-    int n_team = 1;
-    #pragma omp parallel num_threads(n_threads)
-    {
-#ifdef _OPENMP
-        const int T = omp_get_num_threads(), me = omp_get_thread_num();
-#else
-        const int T = 1, me = 0;
-#endif
-        #pragma omp single
-        n_team = T;
-        fill_local *L = &loc[me];
-        const int64_t i0 = n_reads * me / T, i1 = n_reads * (me + 1) / T;
-        for (int64_t i = i0; i < i1; i++) {
-            const uint8_t *r = u + rl.recoff[i];
-            const int32_t bl = rd_i32(r);
-            const uint32_t bmq = rd_u32(r + 12), fnc = rd_u32(r + 16);
-            const int l_qname = bmq & 0xff, ncig = fnc & 0xffff; const int32_t lq = rd_i32(r + 20);
-            t->pos[i] = rd_i32(r + 8); t->mapq[i] = (bmq >> 8) & 0xff; t->flag[i] = (uint16_t)(fnc >> 16); t->n_cigar[i] = (uint16_t)ncig;
-            t->l_qseq[i] = lq; t->mtid[i] = rd_i32(r + 24); t->mpos[i] = rd_i32(r + 28); t->tlen[i] = rd_i32(r + 32);
-            const uint8_t *d = r + 36;
-            const int nl = (int)strnlen((const char *)d, l_qname);
-            t->qname_len[i] = (uint8_t)(nl > 255 ? 255 : nl);
-            t->qname_hash[i] = grom_qname_hash((const char *)d, nl);
-            if (keep_names) memcpy(t->qname_pool + t->qname_off[i], d, l_qname);
-            memcpy(t->cigar + t->cigar_off[i], d + l_qname, (size_t)ncig * 4);
-            const uint8_t *sq = d + l_qname + ncig * 4;
-            const uint64_t b0 = t->base_off[i];
-            const int nb = (lq + 1) / 2;
-            memcpy(t->seq4 + b0 / 2, sq, (size_t)nb);
-            const uint8_t *ql = sq + nb;
-            memcpy(t->qual + b0, ql, (size_t)lq);
-            for (int k = 0; k < lq; k++) L->present[ql[k]] = 1;
-            if (do_seq2) {
-                uint8_t *o2 = t->seq2 + b0 / 4; int64_t ne = 0;
-                const int nfull = (lq & 1) ? nb - 1 : nb;                     /* bytes whose two nibbles are both bases */
-                int k = 0;
-                for (; k + 2 <= nfull; k += 2) { const uint8_t x = sq[k], y = sq[k + 1]; o2[k >> 1] = (uint8_t)((S2[x] << 4) | S2[y]); ne += SX[x] + SX[y]; }
-                if (k < nb) {                                                  /* one or two bytes left; the padding nibble of an odd length is no base */
-                    uint8_t x = sq[k], y = 0x11;
-                    if (k + 1 < nb) y = sq[k + 1];
-                    if (lq & 1) { if (k + 1 < nb) y = (uint8_t)((y & 0xf0) | 1); else x = (uint8_t)((x & 0xf0) | 1); }
-                    o2[k >> 1] = (uint8_t)((S2[x] << 4) | S2[y]); ne += SX[x] + SX[y];
+    int rc = 0, started = 0, done = 0, n_team = 1;
+    int64_t carry = 0, inflated_so_far = 0;
+#define FAIL_OUT(code) do { rc = (code); goto out; } while (0)
+    for (int64_t w0 = 0; w0 < nblk && !done; w0 += WB) {
+        const int64_t w1 = w0 + WB < nblk ? w0 + WB : nblk;
+        int64_t wbytes = 0;
+        for (int64_t i = w0; i < w1; i++) { blk[i].uoff = carry + wbytes; wbytes += blk[i].isize; }
+        if ((size_t)(carry + wbytes) + 64 > win_len) {              /* a record longer than the spare room was carried over */
+            const size_t n = ((size_t)(carry + wbytes) + 64 + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+            void *q = mremap(win, win_len, n, MREMAP_MAYMOVE);
+            if (q == MAP_FAILED) FAIL_OUT(fail("out of memory (%lld bytes of inflated BAM)", (long long)n));
+            win = (uint8_t *)q; win_len = n;
+        }
+        if (trace) t_mark = now_ms();
+        int bad = 0;
+        #pragma omp parallel num_threads(n_threads)
+        {
+            struct grom_inflate_ctx *ctx = own ? (struct grom_inflate_ctx *)malloc(grom_inflate_ctx_size()) : NULL;
+            if (ctx) grom_inflate_ctx_init(ctx);
+            #pragma omp for schedule(dynamic, 8)
+            for (int64_t i = w0; i < w1; i++) {
+                const uint8_t *blkp = cf + blk[i].off;
+                if (bgzf_inflate_block(ctx, blkp + blk[i].coff, blk[i].bsize - blk[i].coff - 8, win + blk[i].uoff, blk[i].isize, rd_u32(blkp + blk[i].bsize - 8)) < 0) {
+                    #pragma omp atomic write
+                    bad = 1;
                 }
-                exc_at[i + 1] = ne;
             }
-            const uint8_t *aux = ql + lq;
-            const int l_aux = (int)((r + 4 + bl) - aux);
-            parse_sa(aux, l_aux, tname, &t->sa_pos[i], &t->sa_strand[i], &t->sa_mapq[i], &t->sa_same_chr[i],
-                     &t->sa_start_adj[i], &t->sa_end_adj[i], &t->sa_end_adj_indel[i]);
-            if (t->sa_pos[i] != -1 || t->sa_mapq[i] != -1 || t->sa_strand[i] || t->sa_same_chr[i] || t->sa_start_adj[i] || t->sa_end_adj[i] || t->sa_end_adj_indel[i]) {
-                if (L->n == L->cap) { L->cap = L->cap ? L->cap * 2 : 1024; L->e = (sa_ent *)realloc(L->e, sizeof(sa_ent) * (size_t)L->cap); }
-                sa_ent *e = &L->e[L->n++];                /* parse_sa leaves every other read at (-1, 0, -1, 0, 0, 0, 0) */
-                e->idx = (int32_t)i; e->pos = t->sa_pos[i]; e->start_adj = t->sa_start_adj[i]; e->end_adj = t->sa_end_adj[i];
-                e->end_adj_indel = t->sa_end_adj_indel[i]; e->mapq = t->sa_mapq[i]; e->strand = t->sa_strand[i]; e->same_chr = t->sa_same_chr[i];
+            free(ctx);
+        }
+        if (bad) FAIL_OUT(fail("%s: BGZF inflate failed (corrupt deflate stream or CRC mismatch)", b->path));
+        if (trace) { const double x = now_ms(); t_infl += x - t_mark; t_mark = x; }
+        const int64_t have = carry + wbytes;
+        inflated_so_far += wbytes;
+        /* the record chain of the window: count, validate, offsets */
+        reclist rl; walk_end we;
+        const int wrc = walk_records_parallel(win, have, w0 == 0 ? (int64_t)(vbeg & 0xffff) : 0, started, tid, b->n_targets, keep_names, n_threads, b->path, &rl, &we);
+        if (wrc < 0) FAIL_OUT(wrc == -2 ? fail("out of memory (record list)") : -1);
+        if (rl.n) started = 1;
+        if (trace) { const double x = now_ms(); t_walk += x - t_mark; t_mark = x; }
+        /* room for the window's records; the first window sizes the whole batch from its share of the inflated bytes */
+        {
+            int64_t wr = n_reads + rl.n, wc = n_cig + rl.n_cig, wsl = n_slots + rl.n_slots, wn = n_name + rl.n_name;
+            if (caps.reads == 0 && w1 < nblk && inflated_so_far > 0) {
+                const double f = 1.03 * (double)utotal / (double)inflated_so_far;
+                wr = (int64_t)((double)wr * f) + 1024; wc = (int64_t)((double)wc * f) + 1024; wsl = (int64_t)((double)wsl * f) + 32768; wn = (int64_t)((double)wn * f) + 32768;
+            }
+            if (wr < 1) wr = 1;
+            if (wc < 1) wc = 1;
+            if (batch_reserve(t, &caps, wr, wc, wsl, wn, keep_names, do_seq2, &exc_at) < 0) { free(rl.recoff); free(rl.cig_off); free(rl.base_off); free(rl.name_off); FAIL_OUT(fail("out of memory (read batch)")); }
+        }
+        /* fill, parallel over contiguous ranges of the window's reads.  In the same pass over a record: the 2-bit form of its bases
+         * (table-driven, two nibbles per lookup) with the number of its non-A/C/G/T bases, the set of quality values seen, and the
+         * reads with an XP / SA entry. */
+        const int64_t wn_reads = rl.n;
+        #pragma omp parallel num_threads(n_threads)
+        {
+#ifdef _OPENMP
+            const int T = omp_get_num_threads(), me = omp_get_thread_num();
+#else
+            const int T = 1, me = 0;
+#endif
+            #pragma omp single
+            n_team = T > n_team ? T : n_team;
+            fill_local *L = &loc[me];
+            L->n = 0;
+            const int64_t i0 = wn_reads * me / T, i1 = wn_reads * (me + 1) / T;
+            for (int64_t j = i0; j < i1; j++) {
+                const int64_t i = n_reads + j;
+                const uint8_t *r = win + rl.recoff[j];
+                const int32_t bl = rd_i32(r);
+                const uint32_t bmq = rd_u32(r + 12), fnc = rd_u32(r + 16);
+                const int l_qname = bmq & 0xff, ncig = fnc & 0xffff; const int32_t lq = rd_i32(r + 20);
+                t->pos[i] = rd_i32(r + 8); t->mapq[i] = (bmq >> 8) & 0xff; t->flag[i] = (uint16_t)(fnc >> 16); t->n_cigar[i] = (uint16_t)ncig;
+                t->l_qseq[i] = lq; t->mtid[i] = rd_i32(r + 24); t->mpos[i] = rd_i32(r + 28); t->tlen[i] = rd_i32(r + 32);
+                const uint64_t c0 = (uint64_t)n_cig + rl.cig_off[j], b0 = (uint64_t)n_slots + rl.base_off[j];
+                t->cigar_off[i] = c0; t->base_off[i] = b0;
+                const uint8_t *d = r + 36;
+                const int nl = (int)strnlen((const char *)d, l_qname);
+                t->qname_len[i] = (uint8_t)(nl > 255 ? 255 : nl);
+                t->qname_hash[i] = grom_qname_hash((const char *)d, nl);
+                if (keep_names) { const uint64_t m0 = (uint64_t)n_name + rl.name_off[j]; t->qname_off[i] = m0; memcpy(t->qname_pool + m0, d, l_qname); }
+                memcpy(t->cigar + c0, d + l_qname, (size_t)ncig * 4);
+                const uint8_t *sq = d + l_qname + ncig * 4;
+                const int nb = (lq + 1) / 2;
+                memcpy(t->seq4 + b0 / 2, sq, (size_t)nb);
+                const uint8_t *ql = sq + nb;
+                memcpy(t->qual + b0, ql, (size_t)lq);
+                for (int k = 0; k < lq; k++) L->present[ql[k]] = 1;
+                if (do_seq2) {
+                    uint8_t *o2 = t->seq2 + b0 / 4; int64_t ne = 0;
+                    const int nfull = (lq & 1) ? nb - 1 : nb;                     /* bytes whose two nibbles are both bases */
+                    int k = 0;
+                    for (; k + 2 <= nfull; k += 2) { const uint8_t x = sq[k], y = sq[k + 1]; o2[k >> 1] = (uint8_t)((S2[x] << 4) | S2[y]); ne += SX[x] + SX[y]; }
+                    if (k < nb) {                                                  /* one or two bytes left; the padding nibble of an odd length is no base */
+                        uint8_t x = sq[k], y = 0x11;
+                        if (k + 1 < nb) y = sq[k + 1];
+                        if (lq & 1) { if (k + 1 < nb) y = (uint8_t)((y & 0xf0) | 1); else x = (uint8_t)((x & 0xf0) | 1); }
+                        o2[k >> 1] = (uint8_t)((S2[x] << 4) | S2[y]); ne += SX[x] + SX[y];
+                    }
+                    exc_at[i + 1] = ne;
+                }
+                const uint8_t *aux = ql + lq;
+                const int l_aux = (int)((r + 4 + bl) - aux);
+                parse_sa(aux, l_aux, tname, &t->sa_pos[i], &t->sa_strand[i], &t->sa_mapq[i], &t->sa_same_chr[i],
+                         &t->sa_start_adj[i], &t->sa_end_adj[i], &t->sa_end_adj_indel[i]);
+                if (t->sa_pos[i] != -1 || t->sa_mapq[i] != -1 || t->sa_strand[i] || t->sa_same_chr[i] || t->sa_start_adj[i] || t->sa_end_adj[i] || t->sa_end_adj_indel[i]) {
+                    if (L->n == L->cap) { L->cap = L->cap ? L->cap * 2 : 1024; L->e = (sa_ent *)realloc(L->e, sizeof(sa_ent) * (size_t)L->cap); }
+                    sa_ent *e = &L->e[L->n++];                /* parse_sa leaves every other read at (-1, 0, -1, 0, 0, 0, 0) */
+                    e->idx = (int32_t)i; e->pos = t->sa_pos[i]; e->start_adj = t->sa_start_adj[i]; e->end_adj = t->sa_end_adj[i];
+                    e->end_adj_indel = t->sa_end_adj_indel[i]; e->mapq = t->sa_mapq[i]; e->strand = t->sa_strand[i]; e->same_chr = t->sa_same_chr[i];
+                }
             }
         }
+        /* the threads' SA entries of this window, in thread order = read order */
+        for (int k = 0; k < n_threads; k++) {
+            if (!loc[k].n) continue;
+            if (n_sa + loc[k].n > cap_sa) {
+                cap_sa = cap_sa ? cap_sa * 2 : 4096; if (cap_sa < n_sa + loc[k].n) cap_sa = n_sa + loc[k].n;
+                sa_ent *q = (sa_ent *)realloc(sa_all, sizeof(sa_ent) * (size_t)cap_sa);
+                if (!q) { free(rl.recoff); free(rl.cig_off); free(rl.base_off); free(rl.name_off); FAIL_OUT(fail("out of memory (SA list)")); }
+                sa_all = q;
+            }
+            memcpy(sa_all + n_sa, loc[k].e, sizeof(sa_ent) * (size_t)loc[k].n); n_sa += loc[k].n; loc[k].n = 0;
+        }
+        n_reads += rl.n; n_cig += rl.n_cig; n_slots += rl.n_slots; n_name += rl.n_name;
+        free(rl.recoff); free(rl.cig_off); free(rl.base_off); free(rl.name_off);
+        if (trace) { const double x = now_ms(); t_fill += x - t_mark; t_mark = x; }
+        /* what the walk left: the chain ended (a record past the target, a block_size that cannot be one), or the data of the window
+         * did; then the bytes from there on are the head of a record that continues in the next window */
+        if (we.term != 5) done = 1;
+        else {
+            carry = have - we.stop_at;
+            if (carry > 0 && w1 < nblk) memmove(win, win + we.stop_at, (size_t)carry);
+        }
     }
-    TRACE_MARK("fill");
-    free(rl.recoff);
+    if (trace) {
+        fprintf(stderr, "[bamio] %-22s %8.2f ms\n[bamio] %-22s %8.2f ms\n[bamio] %-22s %8.2f ms\n", "inflate", t_infl, "record chain", t_walk, "allocate + fill", t_fill);
+        t_last = now_ms();
+    }
+    if (batch_reserve(t, &caps, n_reads > 0 ? n_reads : 1, n_cig > 0 ? n_cig : 1, n_slots, n_name, keep_names, do_seq2, &exc_at) < 0) FAIL_OUT(fail("out of memory (read batch)"));
+    if (keep_names) t->qname_off[n_reads] = (uint64_t)n_name;
     t->v.n_reads = n_reads; t->v.n_cigar_total = n_cig; t->v.n_base_slots = n_slots;
     batch_publish(t);
+    {
+    /* transport-compact forms (include/grom_reads.h GROM_LAYOUT_*), all lossless; the CUDA library rebuilds the canonical device arrays.
+     * The offsets are running sums by construction here; base qualities of current instruments take a handful of distinct values, so a
+     * 4- or 16-entry dictionary shrinks them to 2 or 4 bits; bases travel as 2 bits + a list of everything that is not A/C/G/T; the
+     * first-SA-entry fields exist for a small minority of reads. */
+    const int64_t ns = n_slots;
     grom_read_batch *v = &t->v;
     int flags = GROM_LAYOUT_CANONICAL_OFFSETS;
-    /* 6. the forms that need a whole-batch decision.  Qualities: <= 4 distinct values on the bases (padding slots aside) -> 2 bits per
+    /* 3. the forms that need a whole-batch decision.  Qualities: <= 4 distinct values on the bases (padding slots aside) -> 2 bits per
      * slot, <= 16 -> 4 bits, else the bytes travel.  inv[0] is 0 either way, so the zero padding slots pack to 0 without a test. */
     int hist[256]; memset(hist, 0, sizeof(hist));
-    for (int k = 0; k < n_team; k++) for (int q = 0; q < 256; q++) hist[q] |= loc[k].present[q];
+    for (int k = 0; k < n_threads; k++) for (int q = 0; q < 256; q++) hist[q] |= loc[k].present[q];
     int nv = 0, qmode = 0; uint8_t inv[256]; memset(inv, 0, sizeof(inv));
     if (ns > 0) {
         for (int k = 0; k < 256; k++) if (hist[k]) { if (nv < 16) { v->qual_lut[nv] = (uint8_t)k; inv[k] = (uint8_t)nv; } nv++; }
@@ -824,15 +961,13 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         } else if (nv >= 1 && nv <= 16 && hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) qmode = 4;
         else memset(v->qual_lut, 0, 16);
     }
-    int64_t n_sa = 0;
-    for (int k = 0; k < n_team; k++) n_sa += loc[k].n;
     t->sa_index = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1)); t->sas_pos = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1));
     t->sas_start_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1)); t->sas_end_adj = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1));
     t->sas_end_adj_indel = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1)); t->sas_mapq = (int16_t *)malloc(sizeof(int16_t) * (size_t)(n_sa + 1));
     t->sas_strand = (uint8_t *)malloc((size_t)(n_sa + 1)); t->sas_same_chr = (uint8_t *)malloc((size_t)(n_sa + 1));
     const int sa_ok = t->sa_index && t->sas_pos && t->sas_start_adj && t->sas_end_adj && t->sas_end_adj_indel && t->sas_mapq && t->sas_strand && t->sas_same_chr;
     int64_t ne = 0; int seq2_ok = 0;
-    if (do_seq2) {
+    if (do_seq2 && ns > 0 && t->seq2 && exc_at) {
         exc_at[0] = 0;
         for (int64_t i = 0; i < n_reads; i++) exc_at[i + 1] += exc_at[i];
         ne = exc_at[n_reads];
@@ -843,9 +978,6 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     }
     #pragma omp parallel num_threads(n_threads)
     {
-        /* the inflated stream is no longer needed: unmapping it takes one thread a while, the others start on the packing */
-        #pragma omp single nowait
-        munmap(u, u_len);
         if (qmode == 2) {
             #pragma omp for schedule(dynamic, 1 << 16) nowait
             for (int64_t s = 0; s < ns; s += 4) t->qual2[s >> 2] = (uint8_t)((inv[t->qual[s]] << 6) | (inv[t->qual[s + 1]] << 4) | (inv[t->qual[s + 2]] << 2) | inv[t->qual[s + 3]]);
@@ -866,15 +998,11 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
             }
         }
         if (sa_ok) {
-            #pragma omp for schedule(static, 1) nowait
-            for (int k = 0; k < n_team; k++) {
-                int64_t w = 0;
-                for (int j = 0; j < k; j++) w += loc[j].n;
-                for (int64_t j = 0; j < loc[k].n; j++, w++) {
-                    const sa_ent *e = &loc[k].e[j];
-                    t->sa_index[w] = e->idx; t->sas_pos[w] = e->pos; t->sas_start_adj[w] = e->start_adj; t->sas_end_adj[w] = e->end_adj;
-                    t->sas_end_adj_indel[w] = e->end_adj_indel; t->sas_mapq[w] = e->mapq; t->sas_strand[w] = e->strand; t->sas_same_chr[w] = e->same_chr;
-                }
+            #pragma omp for schedule(static) nowait
+            for (int64_t w = 0; w < n_sa; w++) {
+                const sa_ent *e = &sa_all[w];
+                t->sa_index[w] = e->idx; t->sas_pos[w] = e->pos; t->sas_start_adj[w] = e->start_adj; t->sas_end_adj[w] = e->end_adj;
+                t->sas_end_adj_indel[w] = e->end_adj_indel; t->sas_mapq[w] = e->mapq; t->sas_strand[w] = e->strand; t->sas_same_chr[w] = e->same_chr;
             }
         }
     }
@@ -890,13 +1018,17 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         flags |= GROM_LAYOUT_SPARSE_SA;
     }
     v->layout_flags = flags;
-    for (int k = 0; k < n_threads; k++) free(loc[k].e);
-    free(loc); free(exc_at);
+    }
     TRACE_MARK("compact forms");
+out:
+    for (int k = 0; k < n_threads; k++) free(loc[k].e);
+    free(loc); free(exc_at); free(sa_all); free(blk);
+    munmap(win, win_len);
+    if (rc != 0) { gromhost_batch_free(t); return rc; }
     *out = t;
     return 0;
+#undef FAIL_OUT
 }
-
 
 /* ------------------------------------------------------------------ library statistics straight from the file */
 

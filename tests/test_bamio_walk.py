@@ -114,3 +114,24 @@ def test_corrupt_record_is_reported_by_the_all_thread_walk(tmp_path, monkeypatch
         with hostlib.Bam(str(bad)) as b:
             with pytest.raises(RuntimeError, match="corrupt BAM record"):
                 b.read_target(0, threads=4)
+
+
+@pytest.mark.parametrize("indexed", [True, False])
+def test_windows_do_not_change_the_batch(tmp_path, monkeypatch, indexed):
+    """A target is decoded a window of BGZF blocks at a time (one window of inflated data in memory, the batch grows); records that straddle
+    windows are carried over.  Windows of 1, 2 and 7 blocks -- most records straddle -- give the batch of one window over everything."""
+    spec = synth.SynthSpec(contigs=[("c1", 50_000), ("c2", 120_000), ("c3", 30_000)], depth=14, seed=31, dup_frac=0.05, clip_frac=0.05, sa_frac=0.8, disc_frac=0.03,
+                           long_name_frac=0.01)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "w"), cs)
+    if not indexed:
+        os.remove(bam + ".bai")
+    monkeypatch.setenv("GROMHOST_WINDOW_BLOCKS", "1000000")
+    whole = read_all(bam, monkeypatch, 1 << 60, 3)
+    for wb, par_min in (("1", 1 << 60), ("2", 1), ("7", 1)):
+        monkeypatch.setenv("GROMHOST_WINDOW_BLOCKS", wb)
+        got = read_all(bam, monkeypatch, par_min, 3)
+        for a, b in zip(whole, got):
+            same(a, b)
+    for c, a in zip(cs, whole):
+        assert a.n_reads == c.batch.n_reads and np.array_equal(a.pos, c.batch.pos) and np.array_equal(a.cigar, c.batch.cigar)
