@@ -51,6 +51,7 @@ struct grom_bam {
     int has_index;
     uint64_t *tgt_beg;        /* per target: smallest chunk_beg in the .bai, UINT64_MAX if none */
     uint64_t *tgt_end;        /* per target: largest chunk_end */
+    int64_t *tgt_mapped, *tgt_unmapped;   /* per target: record counts of the index's metadata pseudo-bin, -1 = the index has none */
     const uint8_t *map;       /* the whole file, mapped read-only (or read into memory where mapping is refused) */
     int64_t map_len;
     int map_is_mmap;
@@ -262,6 +263,9 @@ int gromhost_bam_open(const char *path, grom_bam **out)
         if (fread(m, 1, 4, fi) == 4 && !memcmp(m, "BAI\1", 4) && fread(&nr, 4, 1, fi) == 1 && nr == n_ref) {
             b->tgt_beg = (uint64_t *)malloc(sizeof(uint64_t) * (n_ref > 0 ? n_ref : 1));
             b->tgt_end = (uint64_t *)malloc(sizeof(uint64_t) * (n_ref > 0 ? n_ref : 1));
+            b->tgt_mapped = (int64_t *)malloc(sizeof(int64_t) * (n_ref > 0 ? n_ref : 1));
+            b->tgt_unmapped = (int64_t *)malloc(sizeof(int64_t) * (n_ref > 0 ? n_ref : 1));
+            for (int i = 0; i < n_ref; i++) b->tgt_mapped[i] = b->tgt_unmapped[i] = -1;
             int ok = 1;
             for (int i = 0; i < n_ref && ok; i++) {
                 int32_t n_bin, n_intv;
@@ -273,7 +277,10 @@ int gromhost_bam_open(const char *path, grom_bam **out)
                     for (int k = 0; k < n_chunk; k++) {
                         uint64_t be[2];
                         if (fread(be, 8, 2, fi) != 2) { ok = 0; break; }
-                        if (bin == 37450) continue;
+                        if (bin == 37450) {              /* metadata pseudo-bin: (first, last virtual offset), (mapped, unmapped records) */
+                            if (k == 1) { b->tgt_mapped[i] = (int64_t)be[0]; b->tgt_unmapped[i] = (int64_t)be[1]; }
+                            continue;
+                        }
                         if (be[0] < b->tgt_beg[i]) b->tgt_beg[i] = be[0];
                         if (be[1] > b->tgt_end[i]) b->tgt_end[i] = be[1];
                     }
@@ -305,7 +312,7 @@ void gromhost_bam_close(grom_bam *b)
     if (!b) return;
     if (b->map) { if (b->map_is_mmap) munmap((void *)b->map, (size_t)b->map_len); else free((void *)b->map); }
     for (int i = 0; i < b->n_targets; i++) free(b->names[i]);
-    free(b->names); free(b->lens); free(b->tgt_beg); free(b->tgt_end); free(b->path);
+    free(b->names); free(b->lens); free(b->tgt_beg); free(b->tgt_end); free(b->tgt_mapped); free(b->tgt_unmapped); free(b->path);
     if (b->f) fclose(b->f);
     free(b);
 }
@@ -313,6 +320,13 @@ int gromhost_bam_n_targets(const grom_bam *b) { return b->n_targets; }
 const char *gromhost_bam_target_name(const grom_bam *b, int tid) { return (tid >= 0 && tid < b->n_targets) ? b->names[tid] : NULL; }
 int64_t gromhost_bam_target_len(const grom_bam *b, int tid) { return (tid >= 0 && tid < b->n_targets) ? b->lens[tid] : -1; }
 int gromhost_bam_has_index(const grom_bam *b) { return b->has_index; }
+int gromhost_bam_target_reads(const grom_bam *b, int tid, int64_t *mapped, int64_t *unmapped)
+{
+    if (!b->has_index || tid < 0 || tid >= b->n_targets || !b->tgt_mapped || b->tgt_mapped[tid] < 0) return -1;
+    if (mapped) *mapped = b->tgt_mapped[tid];
+    if (unmapped) *unmapped = b->tgt_unmapped[tid];
+    return 0;
+}
 
 /* ------------------------------------------------------------------ batch */
 
@@ -789,7 +803,7 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         S2[v] = (uint8_t)(((th < 0 ? 0 : th) << 2) | (tl < 0 ? 0 : tl)); SX[v] = (uint8_t)((th < 0) + (tl < 0));
     }
     const char *tname = b->names[tid];
-    int rc = 0, started = 0, done = 0, n_team = 1;
+    int rc = 0, started = 0, done = 0;
     int64_t carry = 0, inflated_so_far = 0;
 #define FAIL_OUT(code) do { rc = (code); goto out; } while (0)
     for (int64_t w0 = 0; w0 < nblk && !done; w0 += WB) {
@@ -850,8 +864,6 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
 #else
             const int T = 1, me = 0;
 #endif
-            #pragma omp single
-            n_team = T > n_team ? T : n_team;
             fill_local *L = &loc[me];
             L->n = 0;
             const int64_t i0 = wn_reads * me / T, i1 = wn_reads * (me + 1) / T;

@@ -104,6 +104,13 @@ class Bam:
         self.names = [lib().gromhost_bam_target_name(self._h, i).decode() for i in range(n)]
         self.lens = [int(lib().gromhost_bam_target_len(self._h, i)) for i in range(n)]
         self.has_index = bool(lib().gromhost_bam_has_index(self._h))
+        # records per target from the index's metadata pseudo-bin (None when the index has none): load measure for contig -> GPU assignment
+        lib().gromhost_bam_target_reads.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        counts = []
+        for i in range(n):
+            m, u = C.c_int64(), C.c_int64()
+            counts.append(m.value + u.value if lib().gromhost_bam_target_reads(self._h, i, C.byref(m), C.byref(u)) == 0 else None)
+        self.read_counts = counts if n and all(c is not None for c in counts) else None
 
     def read_target(self, tid: int, keep_names: bool = False, threads: int = 0) -> ReadBatch:
         bt = C.c_void_p()

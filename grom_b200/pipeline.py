@@ -100,7 +100,9 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
         hez, mq = hostlib.tables(table_dir, prm.min_mapq)
         gpu.init(device, hez, mq, prm)
         todo = [t for t, n in enumerate(bam.names) if n.lower() in fasta and not skip_contig(n, prm.gender)]
-        mine = set(todo[i] for i in assign_contigs([bam.lens[t] for t in todo], ranks)[rank])
+        # load of a contig = its records where the index counts them (coverage differs between contigs), else its length (the reference's -P order)
+        weights = [float(bam.read_counts[t]) for t in todo] if bam.read_counts is not None else None
+        mine = set(todo[i] for i in assign_contigs([bam.lens[t] for t in todo], ranks, weights)[rank])
         text: Dict[int, str] = {}
         work = [t for t in todo if t in mine]
         work.sort(key=lambda t: -bam.lens[t])                              # largest first, like the reference's -P scheduler (src/GROM.c:22318-22336)

@@ -105,6 +105,23 @@ def test_bgzf_blocks_with_further_extra_subfields(tmp_path):
                 assert np.array_equal(getattr(x, k), getattr(y, k)), k
 
 
+def test_record_counts_from_the_index(tmp_path):
+    """The metadata pseudo-bin of the .bai gives the records per target without touching the BAM: the load measure of the contig -> GPU
+    assignment (grom_b200.pipeline, tools/grom_b200.c).  Absent without an index."""
+    from grom_b200.partition import assign_contigs
+    spec = synth.SynthSpec(contigs=[("c1", 60_000), ("c2", 30_000), ("c3", 30_000)], depth=6, seed=12)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "n"), cs)
+    with hostlib.Bam(bam) as b:
+        assert b.read_counts == [c.batch.n_reads for c in cs] and min(b.read_counts) > 0
+        assert assign_contigs(b.lens, 2) == [[0], [1, 2]]
+        # a thinly covered long contig no longer counts as the heaviest
+        assert assign_contigs(b.lens, 2, [100.0, 900.0, 800.0]) == [[1], [2, 0]]
+    os.remove(bam + ".bai")
+    with hostlib.Bam(bam) as b:
+        assert b.read_counts is None
+
+
 def test_golden_bam_decodes_and_hashes():
     names, batches = golden_batches()
     assert names == ["chrG", "chrH", "chrZ"]

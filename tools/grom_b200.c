@@ -210,18 +210,26 @@ static int plan(const grom_bam *bam, const fa_index *fa, const grom_params *prm,
         if (k < 0 || (is_y && prm->gender == 0)) continue;
         all[n].tid = t; all[n].fa = k; all[n].len = gromhost_bam_target_len(bam, t); n++;
     }
-    /* order by length descending, ties by tid */
-    for (int i = 1; i < n; i++) { contig x = all[i]; int j = i - 1; while (j >= 0 && (all[j].len < x.len || (all[j].len == x.len && all[j].tid > x.tid))) { all[j + 1] = all[j]; j--; } all[j + 1] = x; }
+    /* load of a contig: its records where the index counts them (coverage differs between contigs), else its length */
+    double *wgt = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int counted = 1;
+    for (int i = 0; i < n; i++) { int64_t mp = 0, um = 0; if (gromhost_bam_target_reads(bam, all[i].tid, &mp, &um)) { counted = 0; break; } wgt[i] = (double)(mp + um); }
+    /* order by length descending, ties by tid (the weights move along) */
+    for (int i = 1; i < n; i++) {
+        contig x = all[i]; const double wx = wgt[i]; int j = i - 1;
+        while (j >= 0 && (all[j].len < x.len || (all[j].len == x.len && all[j].tid > x.tid))) { all[j + 1] = all[j]; wgt[j + 1] = wgt[j]; j--; }
+        all[j + 1] = x; wgt[j + 1] = wx;
+    }
     double *load = (double *)calloc((size_t)(world > 0 ? world : 1), sizeof(double));
     contig *m = (contig *)malloc(sizeof(contig) * (size_t)(n > 0 ? n : 1));
     int nm = 0;
     for (int i = 0; i < n; i++) {
         int r = 0;
         for (int k = 1; k < world; k++) if (load[k] < load[r]) r = k;
-        load[r] += (double)all[i].len;
+        load[r] += counted ? wgt[i] : (double)all[i].len;
         if (r == rank) m[nm++] = all[i];
     }
-    free(load);
+    free(load); free(wgt);
     *mine = m; *n_all = n; *all_out = all;
     return nm;
 }
