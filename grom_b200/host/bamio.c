@@ -736,7 +736,21 @@ static int batch_reserve(grom_batch *t, batch_caps *c, int64_t reads, int64_t ci
 
 #define WINDOW_BLOCKS_PER_THREAD 64     /* BGZF blocks a thread inflates per window (4 MB of records) */
 
-int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out)
+/* ---- a target decoded in pieces: the iterator keeps what belongs to the target (its blocks, the window of inflated data with whatever the
+ * last window left over, how far the record chain has come); every gromhost_bam_iter_next() decodes windows into a new batch until the batch
+ * holds at least max_reads records or the target ends.  gromhost_bam_read_target() is one call with no limit. */
+struct grom_target_iter {
+    grom_bam *b; int tid, keep_names, n_threads, own;
+    uint64_t vbeg;
+    blkinfo *blk; int64_t nblk, utotal, WB, w0, inflated;
+    uint8_t *win; size_t win_len;
+    int64_t carry;
+    int started, done, n_batches;
+    fill_local *loc;
+    uint8_t S2[256], SX[256];
+};
+
+int gromhost_bam_iter_open(grom_bam *b, int tid, int keep_names, int n_threads, grom_target_iter **out)
 {
     if (tid < 0 || tid >= b->n_targets) return fail("target id %d out of range", tid);
     uint64_t vbeg = b->first_voff, vend = UINT64_MAX;
@@ -745,13 +759,13 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         else { vbeg = b->tgt_beg[tid]; vend = b->tgt_end[tid]; }
     }
     const int trace = getenv("GROMHOST_TRACE") != NULL;
-    double t_last = trace ? now_ms() : 0, t_infl = 0, t_walk = 0, t_fill = 0, t_mark = 0;
+    double t_last = trace ? now_ms() : 0;
 #ifdef _OPENMP
     if (n_threads <= 0) n_threads = omp_get_max_threads();
 #else
     n_threads = 1;
 #endif
-    /* 1. enumerate the compressed blocks in [vbeg, vend] (the file is mapped: headers and trailers are read in place) */
+    /* the compressed blocks in [vbeg, vend] (the file is mapped: headers and trailers are read in place) */
     blkinfo *blk = NULL; int64_t nblk = 0, capblk = 0;
     const uint8_t *cf = b->map; const int64_t cf_len = b->map_len;
     if (vend != 0) {
@@ -770,10 +784,9 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     int64_t utotal = 0;
     for (int64_t i = 0; i < nblk; i++) utotal += blk[i].isize;
     TRACE_MARK("enumerate blocks");
-
-    /* 2. the target is decoded a window of blocks at a time: inflate (every block straight to its place behind what the window before
-     * left over), list the records, make room in the batch, fill.  Only one window of inflated data exists at any time (host memory of a
-     * call = the batch + one window, not the batch + the whole inflated target), and it is the same, already touched buffer every time. */
+    /* The target is decoded a window of blocks at a time: inflate (every block straight to its place behind what the window before left
+     * over), list the records, make room in the batch, fill.  Only one window of inflated data exists at any time (host memory of a call =
+     * the batch + one window, not the batch + the whole inflated target), and it is the same, already touched buffer every time. */
     int64_t WB = (int64_t)WINDOW_BLOCKS_PER_THREAD * n_threads;
     if (WB < 128) WB = 128;
     { const char *e = getenv("GROMHOST_WINDOW_BLOCKS"); if (e && atoll(e) > 0) WB = atoll(e); }      /* tests: tiny windows */
@@ -785,28 +798,60 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     if (!getenv("GROMHOST_NO_HUGEPAGE")) madvise(win, win_len, MADV_HUGEPAGE);
 #endif
     const char *force = getenv("GROMHOST_INFLATE");
-    const int own = !(force && !strcmp(force, "zlib"));            /* GROMHOST_INFLATE=zlib: every block through zlib */
+    grom_target_iter *it = (grom_target_iter *)calloc(1, sizeof(*it));
+    fill_local *loc = (fill_local *)calloc((size_t)n_threads, sizeof(fill_local));
+    if (!it || !loc) { free(it); free(loc); free(blk); munmap(win, win_len); return fail("out of memory (target iterator)"); }
+    it->b = b; it->tid = tid; it->keep_names = keep_names; it->n_threads = n_threads;
+    it->own = !(force && !strcmp(force, "zlib"));                   /* GROMHOST_INFLATE=zlib: every block through zlib */
+    it->vbeg = vbeg; it->blk = blk; it->nblk = nblk; it->utotal = utotal; it->WB = WB; it->win = win; it->win_len = win_len; it->loc = loc;
+    for (int v = 0; v < 256; v++) {
+        const int hi = v >> 4, lo = v & 15;
+        const int th = hi == 1 ? 0 : hi == 2 ? 1 : hi == 4 ? 2 : hi == 8 ? 3 : -1, tl = lo == 1 ? 0 : lo == 2 ? 1 : lo == 4 ? 2 : lo == 8 ? 3 : -1;
+        it->S2[v] = (uint8_t)(((th < 0 ? 0 : th) << 2) | (tl < 0 ? 0 : tl)); it->SX[v] = (uint8_t)((th < 0) + (tl < 0));
+    }
+    *out = it;
+    return 0;
+}
 
+void gromhost_bam_iter_close(grom_target_iter *it)
+{
+    if (!it) return;
+    for (int k = 0; k < it->n_threads; k++) free(it->loc[k].e);
+    free(it->loc); free(it->blk);
+    if (it->win) munmap(it->win, it->win_len);
+    free(it);
+}
+
+int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch **out)
+{
+    if (it->n_batches > 0 && (it->done || it->w0 >= it->nblk)) return 1;          /* nothing left (an empty target still gives one empty batch) */
+    if (max_reads <= 0) max_reads = INT64_MAX;
+    grom_bam *b = it->b;
+    const int tid = it->tid, keep_names = it->keep_names, n_threads = it->n_threads, own = it->own;
+    const uint64_t vbeg = it->vbeg;
+    blkinfo *blk = it->blk; const int64_t nblk = it->nblk, WB = it->WB, utotal = it->utotal;
+    const uint8_t *cf = b->map;
+    const uint8_t *S2 = it->S2, *SX = it->SX;
+    fill_local *loc = it->loc;
+    uint8_t *win = it->win; size_t win_len = it->win_len;
+    int64_t carry = it->carry, w0 = it->w0, inflated_before = it->inflated;
+    int started = it->started, done = it->done;
+    const int trace = getenv("GROMHOST_TRACE") != NULL;
+    double t_last = trace ? now_ms() : 0, t_infl = 0, t_walk = 0, t_fill = 0, t_mark = 0;
+    for (int k = 0; k < n_threads; k++) { memset(loc[k].present, 0, sizeof(loc[k].present)); loc[k].n = 0; }
     grom_batch *t = (grom_batch *)calloc(1, sizeof(*t));
     t->v.tid = tid;
     batch_caps caps; memset(&caps, 0, sizeof(caps));
     int64_t *exc_at = NULL;
     const int do_seq2 = 1;
     int64_t n_reads = 0, n_cig = 0, n_slots = 0, n_name = 0;
-    /* what is collected across the windows besides the arrays: quality values seen, per thread; reads with an XP / SA entry, in read order */
-    fill_local *loc = (fill_local *)calloc((size_t)n_threads, sizeof(fill_local));
+    /* what is collected across the windows besides the arrays: quality values seen, per thread (it->loc); reads with an XP / SA entry, in read order */
     sa_ent *sa_all = NULL; int64_t n_sa = 0, cap_sa = 0;
-    uint8_t S2[256], SX[256];
-    for (int v = 0; v < 256; v++) {
-        const int hi = v >> 4, lo = v & 15;
-        const int th = hi == 1 ? 0 : hi == 2 ? 1 : hi == 4 ? 2 : hi == 8 ? 3 : -1, tl = lo == 1 ? 0 : lo == 2 ? 1 : lo == 4 ? 2 : lo == 8 ? 3 : -1;
-        S2[v] = (uint8_t)(((th < 0 ? 0 : th) << 2) | (tl < 0 ? 0 : tl)); SX[v] = (uint8_t)((th < 0) + (tl < 0));
-    }
     const char *tname = b->names[tid];
-    int rc = 0, started = 0, done = 0;
-    int64_t carry = 0, inflated_so_far = 0;
+    int rc = 0;
+    int64_t inflated_so_far = 0;
 #define FAIL_OUT(code) do { rc = (code); goto out; } while (0)
-    for (int64_t w0 = 0; w0 < nblk && !done; w0 += WB) {
+    for (; w0 < nblk && !done && n_reads < max_reads; w0 += WB) {
         const int64_t w1 = w0 + WB < nblk ? w0 + WB : nblk;
         int64_t wbytes = 0;
         for (int64_t i = w0; i < w1; i++) { blk[i].uoff = carry + wbytes; wbytes += blk[i].isize; }
@@ -845,8 +890,10 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
         /* room for the window's records; the first window sizes the whole batch from its share of the inflated bytes */
         {
             int64_t wr = n_reads + rl.n, wc = n_cig + rl.n_cig, wsl = n_slots + rl.n_slots, wn = n_name + rl.n_name;
-            if (caps.reads == 0 && w1 < nblk && inflated_so_far > 0) {
-                const double f = 1.03 * (double)utotal / (double)inflated_so_far;
+            if (caps.reads == 0 && w1 < nblk && inflated_so_far > 0 && wr > 0) {
+                /* what is left of the target, were it all like this window -- or the caller's limit plus one window, if that is less */
+                double f = 1.03 * (double)(utotal - inflated_before) / (double)inflated_so_far;
+                if (max_reads != INT64_MAX && (double)wr * f > (double)max_reads + 2.0 * (double)wr) f = ((double)max_reads + 2.0 * (double)wr) / (double)wr;
                 wr = (int64_t)((double)wr * f) + 1024; wc = (int64_t)((double)wc * f) + 1024; wsl = (int64_t)((double)wsl * f) + 32768; wn = (int64_t)((double)wn * f) + 32768;
             }
             if (wr < 1) wr = 1;
@@ -1033,13 +1080,23 @@ int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads
     }
     TRACE_MARK("compact forms");
 out:
-    for (int k = 0; k < n_threads; k++) free(loc[k].e);
-    free(loc); free(exc_at); free(sa_all); free(blk);
-    munmap(win, win_len);
+    free(exc_at); free(sa_all);
+    it->win = win; it->win_len = win_len; it->carry = carry; it->w0 = w0; it->started = started; it->done = done; it->inflated = inflated_before + inflated_so_far;
     if (rc != 0) { gromhost_batch_free(t); return rc; }
+    it->n_batches++;
     *out = t;
     return 0;
 #undef FAIL_OUT
+}
+
+int gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out)
+{
+    grom_target_iter *it = NULL;
+    int rc = gromhost_bam_iter_open(b, tid, keep_names, n_threads, &it);
+    if (rc) return rc;
+    rc = gromhost_bam_iter_next(it, 0, out);
+    gromhost_bam_iter_close(it);
+    return rc;
 }
 
 /* ------------------------------------------------------------------ library statistics straight from the file */

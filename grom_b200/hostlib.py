@@ -30,6 +30,9 @@ def lib() -> C.CDLL:
         L.gromhost_bam_target_len.restype = C.c_int64
         L.gromhost_bam_has_index.argtypes = [C.c_void_p]
         L.gromhost_bam_read_target.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.gromhost_bam_iter_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.gromhost_bam_iter_next.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]
+        L.gromhost_bam_iter_close.argtypes = [C.c_void_p]
         L.gromhost_batch_view.argtypes = [C.c_void_p, C.POINTER(CReadBatch)]
         L.gromhost_batch_free.argtypes = [C.c_void_p]
         L.gromhost_fasta_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
@@ -126,6 +129,30 @@ class Bam:
         bt = C.c_void_p()
         _check(lib().gromhost_bam_read_target(self._h, tid, int(keep_names), threads, C.byref(bt)))
         return OwnedBatch(bt)
+
+    def iter_target(self, tid: int, max_reads: int, keep_names: bool = False, threads: int = 0, owned: bool = False):
+        """The reads of a target in consecutive pieces of at least `max_reads` records (gromhost_bam_iter_*): host memory is bounded by the
+        piece, and the pieces are what consecutive gromgpu_push_reads calls take.  Yields ReadBatch copies, or OwnedBatch (free it) with
+        owned=True.  A trailing piece may be empty."""
+        it = C.c_void_p()
+        _check(lib().gromhost_bam_iter_open(self._h, tid, int(keep_names), threads, C.byref(it)))
+        try:
+            while True:
+                bt = C.c_void_p()
+                rc = lib().gromhost_bam_iter_next(it, int(max_reads), C.byref(bt))
+                if rc == 1:
+                    return
+                _check(rc)
+                ob = OwnedBatch(bt)
+                if owned:
+                    yield ob
+                else:
+                    try:
+                        yield ob.to_numpy(keep_names)
+                    finally:
+                        ob.free()
+        finally:
+            lib().gromhost_bam_iter_close(it)
 
     def library_stats(self, rd_min_mapq: int = 20, threads: int = 0) -> dict:
         """find_insert_mean (reference src/GROM.c:1205-1318) straight over the file (gromhost_bam_library_stats)."""

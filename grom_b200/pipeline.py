@@ -84,11 +84,14 @@ class _InFlight:
 
 
 def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = None, device: int = 0, rank: int = 0, ranks: int = 1,
-                  table_dir: Optional[str] = None, ctx_out: Optional[Dict[int, np.ndarray]] = None, lanes: int = 3) -> Tuple[Dict[int, str], Params]:
+                  table_dir: Optional[str] = None, ctx_out: Optional[Dict[int, np.ndarray]] = None, lanes: int = 3,
+                  slice_reads: Optional[int] = None) -> Tuple[Dict[int, str], Params]:
     """Returns ({tid: record text of that contig}, the parameters incl. the library statistics measured from the BAM).  If `ctx_out` is
     given it receives {tid: translocation records of that contig} for `ctx_vcf_text` (the pairing needs the records of all contigs).
     Up to `lanes` contigs are in flight on the GPU (one host thread and one stream each; uploads take turns on the PCIe link), so the
-    upload of one contig overlaps the kernels and the host stages of the others; results do not depend on `lanes`."""
+    upload of one contig overlaps the kernels and the host stages of the others; results do not depend on `lanes`.
+    `slice_reads` (needs an index with record counts): a contig's reads are decoded and pushed in consecutive pieces of about that many
+    records instead of as one batch, which bounds the host memory of a lane by the piece (gromhost_bam_iter_*); results do not depend on it."""
     prm = params if params is not None else Params.default()
     fasta = _LazyFasta(fasta_path)          # contig characters are loaded (by the C library) when a lane takes the contig, not all up front
     with hostlib.Bam(bam_path) as bam:
@@ -109,7 +112,7 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
         n_lanes = max(1, min(lanes, len(work)))
         inflight = _InFlight(int(0.9 * gpu.device_free_bytes()))
         bus, pick, errors = threading.Lock(), threading.Lock(), []
-        names, lens = list(bam.names), list(bam.lens)
+        names, lens, read_counts = list(bam.names), list(bam.lens), bam.read_counts
 
         def one_contig(lane_bam, t: int, stream: Optional[int], slot: list):
             """slot = [handle, reserved bytes] of this lane: the handle is begun for the lane's first contig (the largest it will see,
@@ -118,18 +121,33 @@ def call_variants(bam_path: str, fasta_path: str, params: Optional[Params] = Non
             chars = fasta[name]
             if len(chars) != lens[t]:
                 raise ValueError(f"{names[t]}: {len(chars)} bases in the FASTA, {lens[t]} in the BAM header")
-            batch = lane_bam.read_target_owned(t)                           # decoded just before it is pushed (the batcher's own memory goes to the CUDA library), dropped right after
+            sliced = bool(slice_reads) and read_counts is not None
+            if sliced:                                                      # totals from the index, pieces decoded one at a time below
+                n_total = int(read_counts[t]); slots_total = n_total * ((prm.lseq + 31) // 32 * 32)
+                batch = None
+            else:
+                batch = lane_bam.read_target_owned(t)                       # decoded just before it is pushed (the batcher's own memory goes to the CUDA library), dropped right after
+                n_total, slots_total = batch.n_reads, batch.n_base_slots
             if slot[0] is None or not slot[0].rebind(t, chars):
                 if slot[0] is not None:
                     slot[0].close(); inflight.release(slot[1]); slot[0] = None
-                need = gpu.chr_bytes_estimate(len(chars), batch.n_reads, batch.n_base_slots)
+                need = gpu.chr_bytes_estimate(len(chars), n_total, slots_total)
                 inflight.acquire(need)
                 slot[1] = need
                 slot[0] = gpu.Chromosome(t, chars, stream=stream)
             ch = slot[0]
-            with bus:
-                ch.push_reads(batch); ch.sync()
-            batch.free()
+            if sliced:
+                for piece in lane_bam.iter_target(t, int(slice_reads), owned=True):
+                    try:
+                        if piece.n_reads:
+                            with bus:
+                                ch.push_reads(piece); ch.sync()
+                    finally:
+                        piece.free()
+            else:
+                with bus:
+                    ch.push_reads(batch); ch.sync()
+                batch.free()
             res = ch.finish()
             cnv = ch.cnv(params=prm)
             text[t] = hostlib.vcf_contig(prm, name, chars, res.snv, res.snv_ave_rd, res.ins, res.del_ev, res.sv_ev, cnv.calls)

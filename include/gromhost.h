@@ -47,6 +47,16 @@ int  gromhost_bam_target_reads(const grom_bam *b, int tid, int64_t *mapped, int6
  * prints the phase times.  Replaces the record-at-a-time read supply of the reference (samread over bgzf/zlib, src/GROM.c:981-992). */
 int  gromhost_bam_read_target(grom_bam *b, int tid, int keep_names, int n_threads, grom_batch **out);
 
+/* The same decode in pieces, for targets whose batch should not exist in host memory at once: every _next() returns a new batch (BAM order
+ * continues where the one before ended; each batch carries its own canonical offsets and transport-compact forms, exactly what consecutive
+ * gromgpu_push_reads() calls take) holding at least max_reads records -- it stops at the end of the decode window in which the count is
+ * reached -- or what is left of the target; max_reads <= 0: no limit.  Returns 0 and a batch, 1 when the target is exhausted (an empty target
+ * still yields one empty batch first), -1 on error.  gromhost_bam_read_target() is _open + one _next without limit + _close. */
+typedef struct grom_target_iter grom_target_iter;
+int  gromhost_bam_iter_open(grom_bam *b, int tid, int keep_names, int n_threads, grom_target_iter **out);
+int  gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch **out);
+void gromhost_bam_iter_close(grom_target_iter *it);
+
 /* One raw DEFLATE stream (RFC 1951, e.g. the payload of a BGZF block) of known output size through the library's own decoder, without
  * the zlib second opinion: 0 = well formed and exactly dst_len bytes produced, -1 otherwise.  Test / tooling entry. */
 int  gromhost_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len);

@@ -135,3 +135,40 @@ def test_windows_do_not_change_the_batch(tmp_path, monkeypatch, indexed):
             same(a, b)
     for c, a in zip(cs, whole):
         assert a.n_reads == c.batch.n_reads and np.array_equal(a.pos, c.batch.pos) and np.array_equal(a.cigar, c.batch.cigar)
+
+
+@pytest.mark.parametrize("window_blocks", ["1000000", "2"])
+def test_target_in_pieces_equals_the_whole_target(tmp_path, monkeypatch, window_blocks):
+    """gromhost_bam_iter_*: consecutive batches of at least max_reads records.  Laid end to end they are the batch of the whole target;
+    every piece carries its own canonical offsets and transport-compact forms (what consecutive gromgpu_push_reads calls take)."""
+    spec = synth.SynthSpec(contigs=[("c1", 40_000), ("c2", 110_000), ("c3", 30_000)], depth=14, seed=33, dup_frac=0.05, clip_frac=0.05, sa_frac=0.8, disc_frac=0.03)
+    cs = synth.simulate(spec)
+    fa, bam = synth.write_dataset(str(tmp_path / "p"), cs)
+    monkeypatch.setenv("GROMHOST_WINDOW_BLOCKS", window_blocks)
+    per_read = ["pos", "mpos", "tlen", "mtid", "l_qseq", "flag", "n_cigar", "mapq", "qname_len", "qname_hash", "sa_pos", "sa_strand", "sa_mapq",
+                "sa_same_chr", "sa_start_adj", "sa_end_adj", "sa_end_adj_indel"]
+    with hostlib.Bam(bam) as b:
+        for tid in range(3):
+            whole = b.read_target(tid, keep_names=True, threads=3)
+            for max_reads in (1, 700, 10 ** 9):
+                pieces = list(b.iter_target(tid, max_reads, keep_names=True, threads=3))
+                pieces = [p for p in pieces if p.n_reads] or pieces[:1]
+                assert sum(p.n_reads for p in pieces) == whole.n_reads
+                if window_blocks == "2" and max_reads < 10 ** 9:
+                    assert len(pieces) > 3 and all(p.n_reads >= max_reads for p in pieces[:-1])
+                if max_reads == 10 ** 9:
+                    assert len(pieces) == 1
+                for k in per_read:
+                    assert np.array_equal(np.concatenate([getattr(p, k) for p in pieces]), getattr(whole, k)), k
+                assert np.array_equal(np.concatenate([p.cigar for p in pieces]), whole.cigar)
+                i0 = 0
+                for p in pieces:
+                    assert p.has_canonical_offsets() and p.layout_flags == whole.layout_flags
+                    for i in range(0, p.n_reads, 37):
+                        assert np.array_equal(p.bases(i), whole.bases(i0 + i)) and np.array_equal(p.quals(i), whole.quals(i0 + i)) and p.qname(i) == whole.qname(i0 + i)
+                    mine = synth.slice_batch(p, 0, p.n_reads).compact()
+                    assert np.array_equal(mine.seq2, p.seq2) and np.array_equal(mine.seq_exc_slot, p.seq_exc_slot) and np.array_equal(mine.qual2, p.qual2)
+                    assert np.array_equal(mine.qual_lut, p.qual_lut) and np.array_equal(mine.sa_index, p.sa_index)
+                    i0 += p.n_reads
+        # an empty target gives one empty piece
+        assert [p.n_reads for p in b.iter_target(0, 5)][-1] >= 0

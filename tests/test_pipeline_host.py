@@ -14,6 +14,7 @@ from util import GOLDEN
 from grom_b200 import hostlib, pipeline
 from grom_b200.params import CNV_CALL_DTYPE, Params
 from oracle import pyoracle as po
+from tools import synth
 
 
 def _calls(cn):
@@ -46,7 +47,12 @@ class OracleGpu:
 
             def push_reads(self, batch):
                 assert isinstance(batch, hostlib.OwnedBatch) and batch.as_c().n_reads == batch.n_reads
-                self.batch = batch.to_numpy()                      # the stand-in copies; the CUDA library uploads
+                piece = batch.to_numpy()                           # the stand-in copies; the CUDA library uploads
+                outer.log.append(("push", self.tid, piece.n_reads))
+                if self.batch is not None:                         # consecutive pieces of one target (gromgpu_push_reads may be called repeatedly)
+                    assert piece.pos[0] >= self.batch.pos[-1]
+                    piece = synth.concat_batches([self.batch, piece])
+                self.batch = piece
 
             def sync(self):
                 pass
@@ -102,7 +108,14 @@ def test_driver_reproduces_the_reference_vcf_with_the_oracle_behind_it(tmp_path,
     begun = [e for e in fake.log if e[0] == "begin"]
     assert len(begun) == lanes and len([e for e in fake.log if e[0] == "close"]) == lanes
     if lanes == 1:
-        assert [e[0] for e in fake.log] == ["begin", "rebind", "rebind", "close"]
+        assert [e[0] for e in fake.log if e[0] != "push"] == ["begin", "rebind", "rebind", "close"]
+    # the same with every contig decoded and pushed in pieces of >= 500 reads (small decode windows so that the pieces are small)
+    monkeypatch.setenv("GROMHOST_WINDOW_BLOCKS", "2")
+    fake.log.clear()
+    sliced, _ = pipeline.call_variants(os.path.join(GOLDEN, "g1.bam"), str(fa), Params.default(rmdup=rmdup), lanes=lanes, slice_reads=500)
+    assert sliced == text
+    pushes = [e for e in fake.log if e[0] == "push"]
+    assert len(pushes) > 6 and sum(e[2] for e in pushes) == 8000 + 5000 + 1600
 
 
 def test_driver_reports_a_fasta_that_does_not_match_the_bam(tmp_path, monkeypatch):

@@ -116,6 +116,25 @@ int main(int argc, char **argv)
             ok++;
             gromhost_batch_free(bt);
         }
+        /* the same target in pieces */
+        if (nt > 0 && rnd() % 2) {
+            grom_target_iter *itr = NULL;
+            if (gromhost_bam_iter_open(b, (int)(rnd() % (uint32_t)nt), (int)(rnd() % 2), 1 + (int)(rnd() % 3), &itr) == 0) {
+                const int64_t lim = 1 + (int64_t)(rnd() % 3000);
+                for (int guard = 0; guard < 100000; guard++) {
+                    grom_batch *bt = NULL;
+                    const int rc = gromhost_bam_iter_next(itr, lim, &bt);
+                    if (rc == 1) break;
+                    if (rc) { failed++; break; }
+                    grom_read_batch v; gromhost_batch_view(bt, &v);
+                    uint64_t acc = 0;
+                    for (int64_t i = 0; i < v.n_reads; i++) { acc += (uint64_t)v.pos[i]; for (int q = 0; q < v.l_qseq[i]; q++) acc += v.qual[v.base_off[i] + (uint64_t)q]; }
+                    reads += v.n_reads + (long)(acc & 1); ok++;
+                    gromhost_batch_free(bt);
+                }
+                gromhost_bam_iter_close(itr);
+            } else failed++;
+        }
         gromhost_bam_close(b);
     }
     printf("%d cases: %ld targets decoded (%ld reads), %ld calls refused\n", iters, ok, reads, failed);

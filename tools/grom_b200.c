@@ -111,6 +111,7 @@ typedef struct {
     grom_params prm;
     int P;                       /* -P: GPUs (worker processes) */
     int rank, world, device, lanes, threads, parts_only, merge_only, have_stats;
+    long slice_reads;            /* --slice-reads: decode and push a contig in pieces of about this many records (0 = whole contig) */
     int st_mean, st_lseq, st_min, st_max;
     const char *stats_json;
 } options;
@@ -123,7 +124,8 @@ static void usage(void)
            "\t-M remove duplicates   -P <GPUs>   -q <min MAPQ 20>   -b <min base quality 20>   -v <SV/SNV p-value 0.001>\n"
            "\t-e <insertion p-value 1e-10>   -V <read-depth p-value 1e-9>   -p <ploidy 2>   -g <1 = process chrY>   -A <window sampling 2>\n"
            "\t-S no split reads  -n -d -a -y -z -j -m -u -x -l -W -X: as in GROM\n"
-           "\t--lanes <contigs in flight per GPU, 3>   --threads <decode threads per lane>   --stats <json file>\n");
+           "\t--lanes <contigs in flight per GPU, 3>   --threads <decode threads per lane>   --stats <json file>\n"
+           "\t--slice-reads <n>: decode and upload a contig in pieces of about n records (bounds host memory; needs an index with record counts)\n");
 }
 
 static int parse(int argc, char **argv, options *o)
@@ -132,7 +134,7 @@ static int parse(int argc, char **argv, options *o)
     grom_params_default(&o->prm);
     o->rank = 0; o->world = 0; o->device = -1; o->lanes = getenv("GROM_LANES") ? atoi(getenv("GROM_LANES")) : 3;
     static const struct option lo[] = { {"rank", 1, 0, 1000}, {"world", 1, 0, 1001}, {"device", 1, 0, 1002}, {"lanes", 1, 0, 1003}, {"parts-only", 0, 0, 1004},
-                                        {"merge-only", 0, 0, 1005}, {"libstats", 1, 0, 1006}, {"threads", 1, 0, 1007}, {"stats", 1, 0, 1008}, {0, 0, 0, 0} };
+                                        {"merge-only", 0, 0, 1005}, {"libstats", 1, 0, 1006}, {"threads", 1, 0, 1007}, {"stats", 1, 0, 1008}, {"slice-reads", 1, 0, 1009}, {0, 0, 0, 0} };
     int c;
     /* the reference's option string; letters this build has no counterpart for are accepted only with the reference's default value */
     while ((c = getopt_long(argc, argv, "Z:W:X:Q:A:Y:B:D:E:K:N:V:U:L:F:SP:c:R:MG:i:r:o:p:q:s:v:g:l:d:b:n:a:y:z:e:fj:k:m:u:w:x:h", lo, NULL)) != -1) {
@@ -179,6 +181,7 @@ static int parse(int argc, char **argv, options *o)
         case 1006: if (sscanf(optarg, "%d,%d,%d,%d", &o->st_mean, &o->st_lseq, &o->st_min, &o->st_max) != 4) die("--libstats wants mean,lseq,min,max"); o->have_stats = 1; break;
         case 1007: o->threads = atoi(optarg); break;
         case 1008: o->stats_json = optarg; break;
+        case 1009: o->slice_reads = atol(optarg); break;
         default: return 1;
         }
     }
@@ -277,8 +280,16 @@ static void *lane_main(void *arg)
         if (flen != c.len) fprintf(stderr, "GROM_b200: warning: %s is %lld bases in the FASTA and %lld in the BAM header\n", lname, (long long)flen, (long long)c.len);
         double t0 = now_s();
         grom_batch *bt = NULL;
-        if (gromhost_bam_read_target(bam, c.tid, 0, o->threads, &bt)) { worker_fail(w, "gromhost_bam_read_target", gromhost_last_error()); free(chars); free(lname); break; }
-        grom_read_batch v; gromhost_batch_view(bt, &v);
+        grom_read_batch v; memset(&v, 0, sizeof(v));
+        /* --slice-reads: the contig's totals come from the index and its reads are decoded piece by piece while they are pushed (below);
+         * otherwise the whole contig is decoded here */
+        int64_t cnt_m = 0, cnt_u = 0;
+        const int sliced = o->slice_reads > 0 && gromhost_bam_target_reads(bam, c.tid, &cnt_m, &cnt_u) == 0;
+        if (sliced) { v.n_reads = cnt_m + cnt_u; v.n_base_slots = v.n_reads * (int64_t)((o->prm.lseq + 31) / 32 * 32); }
+        else {
+            if (gromhost_bam_read_target(bam, c.tid, 0, o->threads, &bt)) { worker_fail(w, "gromhost_bam_read_target", gromhost_last_error()); free(chars); free(lname); break; }
+            gromhost_batch_view(bt, &v);
+        }
         double t1 = now_s();
         /* admission: the handle's device memory must fit beside the contigs already in flight; a contig that fits nowhere runs alone */
         const int64_t need = gromgpu_chr_bytes_estimate(flen, v.n_reads, v.n_base_slots);
@@ -299,18 +310,39 @@ static void *lane_main(void *arg)
             pthread_mutex_unlock(&w->mem);
             if (gromgpu_chr_begin_on(&h, c.tid, chars, flen, stream)) bad = 1;
         }
-        if (!bad) {
+        int64_t n_reads = v.n_reads;
+        if (!bad && !sliced) {
             pthread_mutex_lock(&w->bus);                      /* one upload at a time: the PCIe link is the shared resource */
             bad = gromgpu_push_reads(h, &v) || gromgpu_chr_sync(h);
             pthread_mutex_unlock(&w->bus);
             t2 = now_s();
         }
-        const int64_t n_reads = v.n_reads;
+        if (!bad && sliced) {
+            grom_target_iter *it = NULL;
+            if (gromhost_bam_iter_open(bam, c.tid, 0, o->threads, &it)) { worker_fail(w, "gromhost_bam_iter_open", gromhost_last_error()); bad = 2; }
+            n_reads = 0;
+            while (!bad) {
+                grom_batch *piece = NULL;
+                const int rc = gromhost_bam_iter_next(it, o->slice_reads, &piece);
+                if (rc == 1) break;
+                if (rc) { worker_fail(w, "gromhost_bam_iter_next", gromhost_last_error()); bad = 2; break; }
+                grom_read_batch pv; gromhost_batch_view(piece, &pv);
+                if (pv.n_reads) {
+                    pthread_mutex_lock(&w->bus);
+                    bad = gromgpu_push_reads(h, &pv) || gromgpu_chr_sync(h);
+                    pthread_mutex_unlock(&w->bus);
+                    n_reads += pv.n_reads;
+                }
+                gromhost_batch_free(piece);
+            }
+            gromhost_bam_iter_close(it);
+            t2 = now_s();
+        }
         gromhost_batch_free(bt); bt = NULL;                   /* the reads live on the device now */
         if (!bad) { bad = gromgpu_chr_finish(h, &res); t3 = now_s(); }
         if (!bad) { bad = gromgpu_chr_cnv(h, w->p2s_p, w->p2s_sd, w->n_p2s, o->prm.ploidy, &cnv); t4 = now_s(); }
         if (!bad) gromgpu_chr_stats(h, &st);
-        if (bad) worker_fail(w, "gromgpu", gromgpu_last_error());
+        if (bad == 1) worker_fail(w, "gromgpu", gromgpu_last_error());
         int64_t nrec = 0;
         if (!bad) {
             int64_t n;

@@ -659,3 +659,20 @@ def slice_batch(b: ReadBatch, i0: int, i1: int) -> ReadBatch:
                                                    "sa_strand", "sa_mapq", "sa_same_chr"]}
     return ReadBatch(tid=b.tid, cigar_off=b.cigar_off[i0:i1] - np.uint64(c0), base_off=b.base_off[i0:i1] - np.uint64(s0),
                      cigar=b.cigar[c0:c1].copy(), seq4=b.seq4[s0 // 2:s1 // 2].copy(), qual=b.qual[s0:s1].copy(), **kw).normalise()
+
+
+def concat_batches(parts: List[ReadBatch]) -> ReadBatch:
+    """Consecutive pieces of one target (each self-contained, offsets from 0) as one batch -- the inverse of slice_batch."""
+    parts = [p for p in parts if p.n_reads]
+    if not parts:
+        raise ValueError("no reads")
+    per_read = ["pos", "mpos", "tlen", "mtid", "l_qseq", "flag", "n_cigar", "mapq", "qname_len", "qname_hash", "sa_pos", "sa_start_adj", "sa_end_adj",
+                "sa_end_adj_indel", "sa_strand", "sa_mapq", "sa_same_chr"]
+    kw = {k: np.concatenate([getattr(p, k) for p in parts]) for k in per_read}
+    c_at = np.cumsum([0] + [len(p.cigar) for p in parts])
+    s_at = np.cumsum([0] + [len(p.qual) for p in parts])
+    return ReadBatch(tid=parts[0].tid,
+                     cigar_off=np.concatenate([p.cigar_off + np.uint64(c_at[i]) for i, p in enumerate(parts)]),
+                     base_off=np.concatenate([p.base_off + np.uint64(s_at[i]) for i, p in enumerate(parts)]),
+                     cigar=np.concatenate([p.cigar for p in parts]), seq4=np.concatenate([p.seq4[:len(p.qual) // 2] for p in parts]),
+                     qual=np.concatenate([p.qual for p in parts]), **kw).normalise()
