@@ -322,7 +322,13 @@ int64_t gromhost_bam_target_len(const grom_bam *b, int tid) { return (tid >= 0 &
 int gromhost_bam_has_index(const grom_bam *b) { return b->has_index; }
 int gromhost_bam_target_reads(const grom_bam *b, int tid, int64_t *mapped, int64_t *unmapped)
 {
-    if (!b->has_index || tid < 0 || tid >= b->n_targets || !b->tgt_mapped || b->tgt_mapped[tid] < 0) return -1;
+    if (!b->has_index || tid < 0 || tid >= b->n_targets || !b->tgt_mapped) return -1;
+    if (b->tgt_mapped[tid] < 0) {
+        if (b->tgt_beg[tid] != UINT64_MAX) return -1;             /* records, but no count of them (an index from before samtools 0.1.8) */
+        if (mapped) *mapped = 0;                                   /* no bins at all: a target without records */
+        if (unmapped) *unmapped = 0;
+        return 0;
+    }
     if (mapped) *mapped = b->tgt_mapped[tid];
     if (unmapped) *unmapped = b->tgt_unmapped[tid];
     return 0;

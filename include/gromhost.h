@@ -36,8 +36,8 @@ int  gromhost_bam_n_targets(const grom_bam *b);
 const char *gromhost_bam_target_name(const grom_bam *b, int tid);
 int64_t gromhost_bam_target_len(const grom_bam *b, int tid);
 int  gromhost_bam_has_index(const grom_bam *b);
-/* records of target `tid` as counted in the index's metadata pseudo-bin (samtools >= 0.1.8 writes it): 0 and the two counts, or -1 when
- * the index has none.  A load measure for assigning contigs to GPUs that follows coverage, not just length. */
+/* records of target `tid` as counted in the index's metadata pseudo-bin (samtools >= 0.1.8 writes it): 0 and the two counts (both 0 for a
+ * target the index lists no bins for), or -1 when the index does not count them.  A load measure for assigning contigs to GPUs that follows coverage, not just length. */
 int  gromhost_bam_target_reads(const grom_bam *b, int tid, int64_t *mapped, int64_t *unmapped);
 
 /* decode every record of target `tid` (BAM order) into a new batch.

@@ -122,6 +122,42 @@ def test_record_counts_from_the_index(tmp_path):
         assert b.read_counts is None
 
 
+TILAPIA_BAI = "/root/reference/test_data/tilapia_SAMD00023995_GL831235-1.bam.bai"
+
+
+@pytest.mark.skipif(not os.path.exists(TILAPIA_BAI), reason="the reference's test data (build container only)")
+def test_index_written_by_samtools(tmp_path):
+    """The only real-world index at hand: the .bai of the reference's tilapia example (its BAM is a missing blob).  5,678 targets, reads on
+    one of them; the metadata pseudo-bin, the chunk range and the trailing unplaced-read count parse, and the target's records are the
+    130,504 the reference's run of that file saw."""
+    import shutil
+    import struct
+    import zlib
+
+    def bgzf(data):
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        d = c.compress(data) + c.flush()
+        return b"\x1f\x8b\x08\x04" + b"\0" * 6 + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, len(d) + 25) + d + struct.pack("<II", zlib.crc32(data), len(data))
+    n_ref = struct.unpack_from("<i", open(TILAPIA_BAI, "rb").read(8), 4)[0]
+    assert n_ref == 5678
+    head = b"BAM\1" + struct.pack("<i", 0) + struct.pack("<i", n_ref)
+    for i in range(n_ref):
+        name = (b"GL831235-1" if i == 29 else b"scaffold%d" % i) + b"\0"
+        head += struct.pack("<i", len(name)) + name + struct.pack("<i", 2653313 if i == 29 else 1000)
+    bam = tmp_path / "t.bam"
+    bam.write_bytes(b"".join(bgzf(head[i:i + 60000]) for i in range(0, len(head), 60000)) + bgzf(b""))
+    shutil.copy(TILAPIA_BAI, str(bam) + ".bai")
+    with hostlib.Bam(str(bam)) as b:
+        assert b.has_index and len(b.names) == n_ref and b.names[29] == "GL831235-1"
+        L = hostlib.lib()
+        import ctypes as C
+        m, u = C.c_int64(), C.c_int64()
+        assert L.gromhost_bam_target_reads(b._h, 29, C.byref(m), C.byref(u)) == 0 and (m.value, u.value) == (129050, 1454)
+        assert L.gromhost_bam_target_reads(b._h, 0, C.byref(m), C.byref(u)) == 0 and (m.value, u.value) == (0, 0)     # no bins: no records
+        assert b.read_counts is not None and sum(b.read_counts) == 130504 and b.read_counts[29] == 130504
+        assert b.read_target(3).n_reads == 0                                               # no chunks: nothing is inflated
+
+
 def test_golden_bam_decodes_and_hashes():
     names, batches = golden_batches()
     assert names == ["chrG", "chrH", "chrZ"]
