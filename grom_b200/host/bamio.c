@@ -729,6 +729,7 @@ static int batch_reserve(grom_batch *t, batch_caps *c, int64_t reads, int64_t ci
         if (big_grow(&t->qual, &t->big_qual, c->slots ? o + 16 : 0, (size_t)n + 16) < 0) return -1;
         if (big_grow(&t->seq4, &t->big_seq4, c->slots ? o / 2 + 16 : 0, (size_t)n / 2 + 16) < 0) return -1;
         if (with_seq2 && big_grow(&t->seq2, &t->big_seq2, c->slots ? o / 4 + 16 : 0, (size_t)n / 4 + 16) < 0) return -1;
+        if (with_seq2 && big_grow(&t->qual2, &t->big_qual2, c->slots ? o / 4 + 16 : 0, (size_t)n / 4 + 16) < 0) return -1;      /* (2-bit qualities: packed window by window) */
         c->slots = n;
     }
     if (keep_names && names > c->names) {
@@ -853,6 +854,11 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
     int64_t n_reads = 0, n_cig = 0, n_slots = 0, n_name = 0;
     /* what is collected across the windows besides the arrays: quality values seen, per thread (it->loc); reads with an XP / SA entry, in read order */
     sa_ent *sa_all = NULL; int64_t n_sa = 0, cap_sa = 0;
+    /* 2-bit qualities are packed at the end of every window, while the window's qualities are still in cache, with the dictionary of the
+     * values seen so far; that stands as long as the set of values does not change afterwards (instruments use a fixed handful, all of
+     * which show up in the first window) -- otherwise the whole batch is packed again at the end.  0 nothing packed, 1 packed up to
+     * q2_upto under q2_vals, 2 the set changed or is too large */
+    int q2_state = 0, q2_nv = 0; uint8_t q2_vals[4] = { 0, 0, 0, 0 }; int64_t q2_upto = 0;
     const char *tname = b->names[tid];
     int rc = 0;
     int64_t inflated_so_far = 0;
@@ -980,6 +986,20 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
         }
         n_reads += rl.n; n_cig += rl.n_cig; n_slots += rl.n_slots; n_name += rl.n_name;
         free(rl.recoff); free(rl.cig_off); free(rl.base_off); free(rl.name_off);
+        if (q2_state != 2 && n_slots > q2_upto && t->qual2) {
+            uint8_t seen[256]; memset(seen, 0, sizeof(seen));
+            for (int k = 0; k < n_threads; k++) for (int q = 0; q < 256; q++) seen[q] |= loc[k].present[q];
+            int nv = 0; uint8_t vals[4] = { 0, 0, 0, 0 }, inv2[256]; memset(inv2, 0, sizeof(inv2));
+            for (int q = 0; q < 256; q++) if (seen[q]) { if (nv < 4) { vals[nv] = (uint8_t)q; inv2[q] = (uint8_t)nv; } nv++; }
+            if (nv > 4 || (q2_state == 1 && (nv != q2_nv || memcmp(vals, q2_vals, 4)))) q2_state = 2;
+            else if (nv >= 1) {
+                const int64_t s0 = q2_upto, s1 = n_slots;
+                uint8_t *const q2 = t->qual2; const uint8_t *const qq = t->qual;
+                #pragma omp parallel for schedule(static) num_threads(n_threads)
+                for (int64_t sidx = s0; sidx < s1; sidx += 4) q2[sidx >> 2] = (uint8_t)((inv2[qq[sidx]] << 6) | (inv2[qq[sidx + 1]] << 4) | (inv2[qq[sidx + 2]] << 2) | inv2[qq[sidx + 3]]);
+                q2_state = 1; q2_nv = nv; memcpy(q2_vals, vals, 4); q2_upto = s1;
+            }
+        }
         if (trace) { const double x = now_ms(); t_fill += x - t_mark; t_mark = x; }
         /* what the walk left: the chain ended (a record past the target, a block_size that cannot be one), or the data of the window
          * did; then the bytes from there on are the head of a record that continues in the next window */
@@ -1012,7 +1032,7 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
     int nv = 0, qmode = 0; uint8_t inv[256]; memset(inv, 0, sizeof(inv));
     if (ns > 0) {
         for (int k = 0; k < 256; k++) if (hist[k]) { if (nv < 16) { v->qual_lut[nv] = (uint8_t)k; inv[k] = (uint8_t)nv; } nv++; }
-        if (nv >= 1 && nv <= 4 && (t->qual2 = (uint8_t *)big_zalloc((size_t)(ns / 4 + 16), &t->big_qual2))) qmode = 2;
+        if (nv >= 1 && nv <= 4 && (t->qual2 || (t->qual2 = (uint8_t *)big_zalloc((size_t)(ns / 4 + 16), &t->big_qual2)))) qmode = 2;
         else if (nv >= 1 && nv <= 16 && !hist[0] && (t->qual4 = (uint8_t *)malloc((size_t)(ns / 2 + 16)))) {
             /* 4-bit form: padding slots (0 in the canonical array) must decode to 0 as well, so 0 takes a dictionary entry */
             if (nv == 16) { free(t->qual4); t->qual4 = NULL; memset(v->qual_lut, 0, 16); }
@@ -1031,6 +1051,9 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
     t->sas_end_adj_indel = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n_sa + 1)); t->sas_mapq = (int16_t *)malloc(sizeof(int16_t) * (size_t)(n_sa + 1));
     t->sas_strand = (uint8_t *)malloc((size_t)(n_sa + 1)); t->sas_same_chr = (uint8_t *)malloc((size_t)(n_sa + 1));
     const int sa_ok = t->sa_index && t->sas_pos && t->sas_start_adj && t->sas_end_adj && t->sas_end_adj_indel && t->sas_mapq && t->sas_strand && t->sas_same_chr;
+    /* the windows' packing stands if it covers the batch under the dictionary the whole batch ends up with */
+    const int q2_done = qmode == 2 && q2_state == 1 && q2_upto == ns && q2_nv == nv && !memcmp(q2_vals, v->qual_lut, (size_t)nv);
+    if (qmode != 2 && t->qual2) { big_free(t->qual2, t->big_qual2); t->qual2 = NULL; t->big_qual2 = 0; }
     int64_t ne = 0; int seq2_ok = 0;
     if (do_seq2 && ns > 0 && t->seq2 && exc_at) {
         exc_at[0] = 0;
@@ -1043,7 +1066,7 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
     }
     #pragma omp parallel num_threads(n_threads)
     {
-        if (qmode == 2) {
+        if (qmode == 2 && !q2_done) {
             #pragma omp for schedule(dynamic, 1 << 16) nowait
             for (int64_t s = 0; s < ns; s += 4) t->qual2[s >> 2] = (uint8_t)((inv[t->qual[s]] << 6) | (inv[t->qual[s + 1]] << 4) | (inv[t->qual[s + 2]] << 2) | inv[t->qual[s + 3]]);
         } else if (qmode == 4) {

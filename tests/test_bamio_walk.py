@@ -172,3 +172,46 @@ def test_target_in_pieces_equals_the_whole_target(tmp_path, monkeypatch, window_
                     i0 += p.n_reads
         # an empty target gives one empty piece
         assert [p.n_reads for p in b.iter_target(0, 5)][-1] >= 0
+
+
+@pytest.mark.parametrize("case", ["late_value", "nine_values", "many_values", "late_fifth"])
+def test_quality_forms_when_the_set_of_values_moves(tmp_path, monkeypatch, case):
+    """2-bit qualities are packed window by window under the dictionary of the values seen so far; a value that first shows up in a later
+    window (or a fifth one) makes the batcher pack again at the end / fall back to 4 bits or plain bytes.  Whatever happened on the way, the
+    forms are the ones the numpy side derives from the finished canonical arrays."""
+    from grom_b200.reads import LAYOUT_QUAL2, LAYOUT_QUAL4
+    spec = synth.SynthSpec(contigs=[("c1", 90_000)], depth=14, seed=35, clip_frac=0.03)
+    cs = synth.simulate(spec)
+    bt = cs[0].batch
+    real = bt.qual > 0
+    if case == "late_value":                         # two values on the first 85 % of the slots, a third one only near the end
+        bt.qual[real] = np.where(np.arange(real.sum()) % 3 == 0, 30, 37).astype(np.uint8)
+        tail = np.flatnonzero(real)[int(real.sum() * 0.85)::5]
+        bt.qual[tail] = 12
+    elif case == "late_fifth":                       # four values throughout, a fifth near the end: 4-bit form
+        idx = np.flatnonzero(real)
+        bt.qual[idx] = np.array([12, 25, 30, 37], dtype=np.uint8)[np.arange(idx.size) % 4]
+        bt.qual[idx[int(idx.size * 0.9)::7]] = 40
+    elif case == "nine_values":
+        idx = np.flatnonzero(real)
+        bt.qual[idx] = (14 + np.arange(idx.size) % 9).astype(np.uint8)
+    else:                                            # more than 16: the bytes travel
+        idx = np.flatnonzero(real)
+        bt.qual[idx] = (3 + np.arange(idx.size) % 23).astype(np.uint8)
+    fa, bam = synth.write_dataset(str(tmp_path / "q"), cs)
+    for wb in ("1", "3", "1000000"):
+        monkeypatch.setenv("GROMHOST_WINDOW_BLOCKS", wb)
+        with hostlib.Bam(bam) as b:
+            r = b.read_target(0, threads=3)
+        want = {"late_value": LAYOUT_QUAL2, "late_fifth": LAYOUT_QUAL4, "nine_values": LAYOUT_QUAL4, "many_values": 0}[case]
+        assert r.layout_flags & (LAYOUT_QUAL2 | LAYOUT_QUAL4) == want, (case, wb)
+        mine = synth.slice_batch(r, 0, r.n_reads).compact()
+        assert mine.layout_flags == r.layout_flags
+        if want == LAYOUT_QUAL2:
+            assert np.array_equal(mine.qual2, r.qual2) and np.array_equal(mine.qual_lut, r.qual_lut) and r.qual4 is None
+        elif want == LAYOUT_QUAL4:
+            assert np.array_equal(mine.qual4, r.qual4) and np.array_equal(mine.qual_lut, r.qual_lut) and r.qual2 is None
+        else:
+            assert r.qual2 is None and r.qual4 is None
+        for i in range(0, r.n_reads, 101):
+            assert np.array_equal(r.quals(i), bt.quals(i))
