@@ -521,6 +521,8 @@ def main_b200(a):
                 parity = "ok"
             except AssertionError as e:
                 parity = f"FAILED: {e}"
+            except Exception as e:                       # the checker itself broke (not a difference): say so, keep the measured line
+                parity = f"ERROR: {type(e).__name__}: {str(e)[:200]}"
             parity_counts = dict(parity_counts or {}, seconds=round(time.time() - t_p, 1), contig_mb=a.parity_mb,
                                  what="all 56 per-position arrays, -M flags, 10 breakpoint clusters, SNV / indel / SV gate records, CNV mask + z + window table + calls, bit-exact vs oracle/")
             # ---- host batcher (BAM decode) throughput on the same data, reported separately (north star)
@@ -539,6 +541,8 @@ def main_b200(a):
                 ab = cp[0].batch.aligned_bases()
                 decode = {"bases_per_s": ab / best, "threads": nthr, "reads_per_s": bt.n_reads / best, "bam_bytes": os.path.getsize(bam_p),
                           "what": f"gromhost_bam_open + gromhost_bam_read_target (BGZF inflate + record parse + SA pre-parse -> packed SoA batch + transport-compact forms) on a {a.parity_mb:g} Mb / {a.depth:g}x BAM, best of 3"}
+            except Exception as e:                       # the separately reported host share must not take the line down with it
+                decode = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
             finally:
                 shutil.rmtree(tmpd, ignore_errors=True)
         cpu = None
