@@ -1,5 +1,5 @@
 """A few seconds on a GPU box, no pytest, no torch: the Python driver (grom_b200.pipeline) on the committed golden data set, compact FASTA
-through the C reader and the gzip one through the Python reader, three lanes and one; every record against the reference's VCF
+through the C reader and the gzip one through the Python reader, three lanes and one, whole contigs and contigs in pieces; every record against the reference's VCF
 (tests/golden/g1_*.npz).  Prints one line per case; exit code 1 on any difference."""
 import gzip
 import os
@@ -30,4 +30,16 @@ for tag, rmdup in (("default", 0), ("rmdup", 1)):
         ok_stats = (prm.insert_mean, prm.lseq, prm.insert_min, prm.insert_max) == (int(max(m[0], m[1])), int(m[1]), int(m[2]), int(m[3]))
         print(f"{tag:8s} lanes={lanes} fasta={'gz' if fa.endswith('.gz') else 'plain'}: {len(mine)} records, equal to the reference: {ok}, statistics: {ok_stats}, {time.time() - t0:.2f} s", flush=True)
         bad += (not ok) + (not ok_stats)
+# the same contigs decoded and pushed in pieces (gromhost_bam_iter_* -> consecutive gromgpu_push_reads): small decode windows so that the
+# pieces of this small data set are many
+os.environ["GROMHOST_WINDOW_BLOCKS"] = "2"
+for tag, rmdup in (("default", 0), ("rmdup", 1)):
+    g = np.load(os.path.join(G, f"g1_{tag}.npz"))
+    ref = [l for l in str(g["vcf"]).splitlines(keepends=True) if not l.startswith("#")]
+    t0 = time.time()
+    text, prm = pipeline.call_variants(os.path.join(G, "g1.bam"), plain, Params.default(rmdup=rmdup), lanes=3, slice_reads=500)
+    mine = "".join(text[t] for t in sorted(text)).splitlines(keepends=True)
+    ok = po.normalise_records(mine) == po.normalise_records(ref)
+    print(f"{tag:8s} lanes=3 in pieces of >= 500 reads: {len(mine)} records, equal to the reference: {ok}, {time.time() - t0:.2f} s", flush=True)
+    bad += not ok
 sys.exit(1 if bad else 0)
