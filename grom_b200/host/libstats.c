@@ -51,10 +51,25 @@ int gromhost_libstats_add(gromhost_libstats *s, const grom_read_batch *b)
 
 static int cmp_int(const void *a, const void *b) { const int x = *(const int *)a, y = *(const int *)b; return (x > y) - (x < y); }
 
+/* ascending order of up to 10 M insert sizes / read lengths: small non-negative integers, so a counting sort (one histogram pass, one
+ * write pass) where the values allow it; qsort otherwise.  Same result either way. */
+static void sort_ints(int *a, long n)
+{
+    int lo = 0, hi = 0;
+    for (long i = 0; i < n; i++) { if (i == 0 || a[i] < lo) lo = a[i]; if (i == 0 || a[i] > hi) hi = a[i]; }
+    if (n < 4096 || lo < 0 || hi >= (1 << 22)) { qsort(a, (size_t)n, sizeof(int), cmp_int); return; }
+    long *cnt = (long *)calloc((size_t)hi + 1, sizeof(long));
+    if (!cnt) { qsort(a, (size_t)n, sizeof(int), cmp_int); return; }
+    for (long i = 0; i < n; i++) cnt[a[i]]++;
+    long w = 0;
+    for (int v = lo; v <= hi; v++) for (long k = cnt[v]; k > 0; k--) a[w++] = v;
+    free(cnt);
+}
+
 int gromhost_libstats_finish(gromhost_libstats *s, int *insert_mean, int *lseq, int *insert_min, int *insert_max, int64_t *mapped_reads)
 {
     if (s->n == 0) return -1;
-    qsort(s->ins, (size_t)s->n, sizeof(int), cmp_int);
+    sort_ints(s->ins, s->n);
     int mean = s->ins[s->n / 2];
     const int max_insert = mean * MAX_MULT;
     long end = 0;
@@ -67,7 +82,7 @@ int gromhost_libstats_finish(gromhost_libstats *s, int *insert_mean, int *lseq, 
     const double prob2 = (1.0 - erf_) / 2.0;
     const long lo = (long)(int)(prob2 * end / 2), hi = end - lo;
     *insert_min = s->ins[lo]; *insert_max = s->ins[hi < s->n ? hi : s->n - 1];
-    qsort(s->len, (size_t)s->n, sizeof(int), cmp_int);
+    sort_ints(s->len, s->n);
     *lseq = s->len[s->n / 2];
     *insert_mean = mean;
     *mapped_reads = s->mapped;
