@@ -427,3 +427,46 @@ int64_t gromhost_vcf_cnv(const grom_params *p, const char *chr_name, const char 
         }
     return w;
 }
+
+/* ---- header blocks of <out> and <out>.ctx.vcf as the reference prints them (src/GROM.c:20517-20565, 22639-22677) ---- */
+static const char *HDR_COMMON1[] = {
+    "##ALT=<ID=DEL,Description=\"Deletion\">", "##ALT=<ID=DUP,Description=\"Duplication\">", "##ALT=<ID=INS,Description=\"Insertion\">",
+    "##ALT=<ID=INV,Description=\"Inversion\">", "##INFO=<ID=END,Number=1,Type=Integer,Description=\"End position of the structural variant\">", NULL };
+/* FORMAT keys shared by both files: id, type, description */
+static const char *HDR_FMT[][3] = {
+    {"SPR", "Float", "Probability of start breakpoint evidence occurring by chance"}, {"EPR", "Float", "Probability of end breakpoint evidence occurring by chance"},
+    {"SEV", "Integer", "Evidence supporting variant at start breakpoint"}, {"EEV", "Integer", "Evidence supporting variant at end breakpoint"},
+    {"SRD", "Integer", "Physical read depth at start breakpoint"}, {"ERD", "Integer", "Physical read depth at end breakpoint"},
+    {"SCO", "Integer", "Concordant pairs at start breakpoint"}, {"ECO", "Integer", "Concordant pairs at end breakpoint"},
+    {"SOT", "Integer", "Count of distinct SVs with evidence at start breakpoint"}, {"EOT", "Integer", "Count of distinct SVs with evidence at end breakpoint"},
+    {"SSC", "Integer", "Soft-clipped reads at start breakpoint"}, {"ESC", "Integer", "Soft-clipped at end breakpoint"},
+    {"SFR", "Integer", "Position of first read supporting start breakpoint"}, {"SLR", "Integer", "Position of last read supporting start breakpoint"},
+    {"EFR", "Integer", "Position of first read supporting end breakpoint"}, {"ELR", "Integer", "Position of last read supporting end breakpoint"},
+    {"AF", "Float", "Allele frequency (high mapping quality reads)"}, {"PR", "Float", "Probability of SNV evidence occurring by chance"},
+    {"A", "Integer", "A nucleotides (high mapping quality reads)"}, {"C", "Integer", "C nucleotides (high mapping quality reads)"},
+    {"G", "Integer", "G nucleotides (high mapping quality reads)"}, {"T", "Integer", "T nucleotides (high mapping quality reads)"},
+    {"AL", "Integer", "A nucleotides (low mapping quality reads)"}, {"CL", "Integer", "C nucleotides (low mapping quality reads)"},
+    {"GL", "Integer", "G nucleotides (low mapping quality reads)"}, {"TL", "Integer", "T nucleotides (low mapping quality reads)"},
+    {"BQ", "Float", "Average base quality (all reads)"}, {"MQ", "Float", "Average mapping quality (all reads)"},
+    {"PIR", "Float", "Average distance of SNV from DNA fragment end)"}, {"FS", "Integer", "SNV reads mapped to forward strand)"}, {NULL, NULL, NULL} };
+/* the four read-depth keys of the main file are printed without the closing '>' by the reference; kept byte for byte */
+static const char *HDR_CNV[][2] = { {"SD", "CNV standard deviation"}, {"Z", "CNV probability score"}, {"CN", "CNV copy number"}, {"CS", "CNV copy number standard deviation"}, {NULL, NULL} };
+
+
+int64_t gromhost_vcf_header(const char *fasta_name, int is_ctx, char *buf, int64_t cap)
+{
+    int64_t w = 0;
+#define HP(...) do { const int m_ = snprintf(buf + w, (size_t)(cap - w), __VA_ARGS__); if (m_ < 0 || w + m_ >= cap) return -1; w += m_; } while (0)
+    time_t t = time(NULL);
+    struct tm tm = *localtime(&t);
+    HP("##fileformat=VCFv4.2\n");
+    HP("##fileDate=%d%d%d\n", tm.tm_year + 1900, tm.tm_mon + 1, tm.tm_mday);        /* unpadded, like the reference */
+    HP("##reference=%s\n", fasta_name);
+    for (int i = 0; HDR_COMMON1[i]; i++) HP("%s\n", HDR_COMMON1[i]);
+    if (!is_ctx) HP("##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n");
+    for (int i = 0; HDR_FMT[i][0]; i++) HP("##FORMAT=<ID=%s,Number=1,Type=%s,Description=\"%s\">\n", HDR_FMT[i][0], HDR_FMT[i][1], HDR_FMT[i][2]);
+    if (!is_ctx) for (int i = 0; HDR_CNV[i][0]; i++) HP("##FORMAT=<ID=%s,Number=1,Type=Float,Description=\"%s\"\n", HDR_CNV[i][0], HDR_CNV[i][1]);
+    HP("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\n");
+#undef HP
+    return w;
+}

@@ -276,6 +276,18 @@ def _vcf(fn_name, params, chr_name, fasta, *args, room: int = 0):
         cap *= 4
 
 
+def vcf_header(fasta_name: str, is_ctx: bool = False) -> str:
+    """The reference's header block of <out> (or of <out>.ctx.vcf): gromhost_vcf_header."""
+    L = lib()
+    L.gromhost_vcf_header.restype = C.c_int64
+    L.gromhost_vcf_header.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int64]
+    buf = C.create_string_buffer(1 << 15)
+    n = L.gromhost_vcf_header(fasta_name.encode(), int(is_ctx), buf, len(buf))
+    if n < 0:
+        raise RuntimeError("gromhost_vcf_header: buffer too small")
+    return buf.raw[:n].decode()
+
+
 def vcf_snv(params, chr_name: str, fasta: np.ndarray, snv: np.ndarray, ave_rd: float) -> str:
     """SNV records (reference src/GROM.c:15046-15095) from the candidates gromgpu_chr_result returns."""
     a = np.ascontiguousarray(snv)

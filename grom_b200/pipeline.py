@@ -193,17 +193,16 @@ def ctx_vcf_text(params: Params, target_names: List[str], per_contig: Dict[int, 
     return hostlib.ctx_vcf(params, target_names, allrec)
 
 
-VCF_HEADER = "##fileformat=VCFv4.2\n##source=grom-b200\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tSAMPLE\n"
-
-
-def write_vcf(path: str, per_contig: Dict[int, str]):
+def write_vcf(path: str, per_contig: Dict[int, str], fasta_name: str = ""):
+    """<out>: the reference's header block (GROM.c:20517-20565; `fasta_name` is what it prints as ##reference) + the contigs in BAM header order."""
     with open(path, "w") as f:
-        f.write(VCF_HEADER)
+        f.write(hostlib.vcf_header(fasta_name, False))
         for t in sorted(per_contig):
             f.write(per_contig[t])
 
 
-def write_ctx_vcf(path: str, body: str):
+def write_ctx_vcf(path: str, body: str, fasta_name: str = ""):
+    """<out>.ctx.vcf: the reference's header block (GROM.c:22639-22677) + the paired translocation records."""
     with open(path, "w") as f:
-        f.write("##fileformat=VCFv4.2\n##source=grom-b200\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\n")
+        f.write(hostlib.vcf_header(fasta_name, True))
         f.write(body)

@@ -163,6 +163,11 @@ int64_t gromhost_vcf_contig(const grom_params *p, const char *chr_name, const ch
                             const grom_del_event *del_ev, int64_t n_del_ev, const grom_sv_event *sv_ev, int64_t n_sv_ev,
                             const grom_cnv_call *cnv, int64_t n_cnv, char *buf, int64_t cap);
 
+/* the header block of the main output file (is_ctx = 0) or of <out>.ctx.vcf (is_ctx = 1) exactly as the reference prints it
+ * (src/GROM.c:20517-20565, 22639-22677; ##fileDate unpadded, the four read-depth FORMAT lines without the closing '>'); returns the number of
+ * bytes written (no terminating NUL counted) or -1 when cap is too small */
+int64_t gromhost_vcf_header(const char *fasta_name, int is_ctx, char *buf, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,3 +102,23 @@ def test_snv_records_formatted_by_all_threads_equal_the_serial_text(monkeypatch)
     a = hostlib.vcf_contig(prm, "chra", fa, g["snv"], ave, g["ins"], g["del_ev"], g["sv_ev"], g["cnv"])
     monkeypatch.setenv("GROMHOST_SNV_PAR_MIN", "100000000")
     assert a == hostlib.vcf_contig(prm, "chra", fa, g["snv"], ave, g["ins"], g["del_ev"], g["sv_ev"], g["cnv"])
+
+
+TILAPIA_OUT = "/root/reference/test_data/test_outuput_tilapia_SAMD00023995_GL831235-1"
+
+
+@pytest.mark.skipif(not os.path.exists(TILAPIA_OUT + ".vcf"), reason="the reference's example output (build container only)")
+def test_header_blocks_equal_the_reference_example_output(tmp_path):
+    """gromhost_vcf_header (used by the C host program and by grom_b200.pipeline.write_vcf / write_ctx_vcf) against the header lines of the
+    two files the reference ships as its example output, date and reference path aside."""
+    from grom_b200 import pipeline
+    for ext, is_ctx in ((".vcf", False), (".ctx.vcf", True)):
+        ref = [l for l in open(TILAPIA_OUT + ext) if l.startswith("#")]
+        mine = hostlib.vcf_header("some/ref.fa", is_ctx).splitlines(keepends=True)
+        keep = lambda ls: [l for l in ls if not l.startswith(("##fileDate=", "##reference="))]
+        assert len(ref) > 20 and keep(mine) == keep(ref)
+        assert mine[1].startswith("##fileDate=") and mine[2] == "##reference=some/ref.fa\n"
+    pipeline.write_vcf(str(tmp_path / "o.vcf"), {1: "b\n", 0: "a\n"}, "r.fa")
+    pipeline.write_ctx_vcf(str(tmp_path / "o.ctx.vcf"), "c\n", "r.fa")
+    assert open(tmp_path / "o.vcf").read() == hostlib.vcf_header("r.fa", False) + "a\nb\n"
+    assert open(tmp_path / "o.ctx.vcf").read() == hostlib.vcf_header("r.fa", True) + "c\n"

@@ -17,10 +17,10 @@ prm = Params.default(rmdup=int(a.M), min_mapq=a.q, rd_min_mapq=a.q, min_base_qua
 from grom_b200 import hostlib
 ctx = {}
 text, prm = pipeline.call_variants(a.i, a.r, prm, device=a.device, ctx_out=ctx)
-pipeline.write_vcf(a.o, text)
+pipeline.write_vcf(a.o, text, a.r)
 with hostlib.Bam(a.i) as b:
     names = b.names
 ctx_path = a.o[:-4] + ".ctx.vcf" if a.o.endswith(".vcf") else a.o + ".ctx"          # the reference's naming, src/GROM.c:22431-22445
-pipeline.write_ctx_vcf(ctx_path, pipeline.ctx_vcf_text(prm, names, ctx))
+pipeline.write_ctx_vcf(ctx_path, pipeline.ctx_vcf_text(prm, names, ctx), a.r)
 print(f"insert_mean {prm.insert_mean} lseq {prm.lseq} insert_min {prm.insert_min} insert_max {prm.insert_max}; "
       f"{sum(t.count(chr(10)) for t in text.values())} records over {len(text)} contigs -> {a.o}")
