@@ -847,6 +847,7 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
     double t_last = trace ? now_ms() : 0, t_infl = 0, t_walk = 0, t_fill = 0, t_mark = 0;
     for (int k = 0; k < n_threads; k++) { memset(loc[k].present, 0, sizeof(loc[k].present)); loc[k].n = 0; }
     grom_batch *t = (grom_batch *)calloc(1, sizeof(*t));
+    if (!t) return fail("out of memory (read batch)");
     t->v.tid = tid;
     batch_caps caps; memset(&caps, 0, sizeof(caps));
     int64_t *exc_at = NULL;
@@ -916,6 +917,7 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
          * (table-driven, two nibbles per lookup) with the number of its non-A/C/G/T bases, the set of quality values seen, and the
          * reads with an XP / SA entry. */
         const int64_t wn_reads = rl.n;
+        int fill_oom = 0;
         #pragma omp parallel num_threads(n_threads)
         {
 #ifdef _OPENMP
@@ -966,13 +968,23 @@ int gromhost_bam_iter_next(grom_target_iter *it, int64_t max_reads, grom_batch *
                 parse_sa(aux, l_aux, tname, &t->sa_pos[i], &t->sa_strand[i], &t->sa_mapq[i], &t->sa_same_chr[i],
                          &t->sa_start_adj[i], &t->sa_end_adj[i], &t->sa_end_adj_indel[i]);
                 if (t->sa_pos[i] != -1 || t->sa_mapq[i] != -1 || t->sa_strand[i] || t->sa_same_chr[i] || t->sa_start_adj[i] || t->sa_end_adj[i] || t->sa_end_adj_indel[i]) {
-                    if (L->n == L->cap) { L->cap = L->cap ? L->cap * 2 : 1024; L->e = (sa_ent *)realloc(L->e, sizeof(sa_ent) * (size_t)L->cap); }
+                    if (L->n == L->cap) {
+                        const int64_t nc = L->cap ? L->cap * 2 : 1024;
+                        sa_ent *q = (sa_ent *)realloc(L->e, sizeof(sa_ent) * (size_t)nc);
+                        if (!q) {
+                            #pragma omp atomic write
+                            fill_oom = 1;
+                            continue;
+                        }
+                        L->e = q; L->cap = nc;
+                    }
                     sa_ent *e = &L->e[L->n++];                /* parse_sa leaves every other read at (-1, 0, -1, 0, 0, 0, 0) */
                     e->idx = (int32_t)i; e->pos = t->sa_pos[i]; e->start_adj = t->sa_start_adj[i]; e->end_adj = t->sa_end_adj[i];
                     e->end_adj_indel = t->sa_end_adj_indel[i]; e->mapq = t->sa_mapq[i]; e->strand = t->sa_strand[i]; e->same_chr = t->sa_same_chr[i];
                 }
             }
         }
+        if (fill_oom) { free(rl.recoff); free(rl.cig_off); free(rl.base_off); free(rl.name_off); FAIL_OUT(fail("out of memory (SA list)")); }
         /* the threads' SA entries of this window, in thread order = read order */
         for (int k = 0; k < n_threads; k++) {
             if (!loc[k].n) continue;
